@@ -1,0 +1,126 @@
+// Shared helpers for the gmeta_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gmeta_b200.h"
+
+namespace gmeta {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+// per-thread launch counter: gmeta_last_launch_count() reports what one driver call enqueued
+extern thread_local int g_launch_count;
+
+inline int check_launch() {
+  ++g_launch_count;
+  return cudaGetLastError() == cudaSuccess ? GMETA_OK : GMETA_ERR_LAUNCH;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+inline int ceil_div(int x, int m) { return (x + m - 1) / m; }
+
+__device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// Adjacency + row source of a gather: M[v,:] = sum_{e in [indptr[v],indptr[v+1])} norm[u_e] * in[map(u_e),:]
+struct GatherSrc {
+  const float* in;
+  const int32_t* in_row_map;  // nullable
+  const int32_t* indptr;
+  const int32_t* indices;
+  const float* norm;
+  int ld_in;
+  int f_in;
+};
+
+// One warp aggregates, for each of its rows r = warp, warp+NW, ... < R, the 4 columns
+// [kcol, kcol+4) (kcol = k0 + 4*lane) of M[row0+r] into As[r*lda + 4*lane .. +3]; rows >= nrows
+// (tile tail) are written as zero.  Neighbour ids, their norms and source rows are loaded
+// coalesced (one edge per lane) and broadcast with shuffles; the next row's edge batch is
+// prefetched while the current row's feature segments are in flight.  Summation follows edge
+// order, so results are run-to-run deterministic.  VEC: 16-byte loads (ld_in % 4 == 0 and
+// 16-byte aligned base); otherwise scalar loads with exact column bounds.
+template <bool VEC, int R, int NW, bool SCALE_DST>
+__device__ __forceinline__ void gather_rows(const GatherSrc& g, int row0, int nrows, int k0,
+                                            float* As, int lda) {
+  constexpr int RPW = R / NW;  // rows per warp
+  static_assert(RPW <= 32, "one lane per row for the indptr preload");
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int kcol = k0 + 4 * lane;
+
+  // lane i holds [beg,end) of this warp's i-th row
+  int my_beg = 0, my_end = 0;
+  {
+    const int r = warp + NW * lane;
+    if (lane < RPW && r < nrows) {
+      my_beg = g.indptr[row0 + r];
+      my_end = g.indptr[row0 + r + 1];
+    }
+  }
+  auto load_batch = [&](int base, int end, int& u_src, float& u_norm) {
+    const int e = base + lane;
+    u_src = 0;
+    u_norm = 0.f;
+    if (e < end) {
+      const int u = g.indices[e];
+      u_norm = g.norm[u];
+      u_src = g.in_row_map ? g.in_row_map[u] : u;
+    }
+  };
+  int nb = __shfl_sync(0xffffffffu, my_beg, 0), ne = __shfl_sync(0xffffffffu, my_end, 0);
+  int p_src;
+  float p_norm;
+  load_batch(nb, ne, p_src, p_norm);
+
+#pragma unroll 1
+  for (int i = 0; i < RPW; ++i) {
+    const int r = warp + NW * i;
+    const int beg = nb, end = ne;
+    int c_src = p_src;
+    float c_norm = p_norm;
+    if (i + 1 < RPW) {  // prefetch the next row's first edge batch
+      nb = __shfl_sync(0xffffffffu, my_beg, i + 1);
+      ne = __shfl_sync(0xffffffffu, my_end, i + 1);
+      load_batch(nb, ne, p_src, p_norm);
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int base = beg; base < end; base += 32) {
+      if (base != beg) load_batch(base, end, c_src, c_norm);
+      const int cnt = min(32, end - base);
+#pragma unroll 4
+      for (int j = 0; j < cnt; ++j) {
+        const int src = __shfl_sync(0xffffffffu, c_src, j);
+        const float nu = __shfl_sync(0xffffffffu, c_norm, j);
+        const float* p = g.in + (size_t)src * g.ld_in + kcol;
+        float4 x;
+        if (VEC) {
+          x = (kcol < g.f_in) ? ld_f4(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kcol + 4 > g.f_in) {  // ragged tail: columns >= f_in may hold anything
+            if (kcol + 1 >= g.f_in) x.y = 0.f;
+            if (kcol + 2 >= g.f_in) x.z = 0.f;
+            if (kcol + 3 >= g.f_in) x.w = 0.f;
+          }
+        } else {
+          x.x = (kcol + 0 < g.f_in) ? p[0] : 0.f;
+          x.y = (kcol + 1 < g.f_in) ? p[1] : 0.f;
+          x.z = (kcol + 2 < g.f_in) ? p[2] : 0.f;
+          x.w = (kcol + 3 < g.f_in) ? p[3] : 0.f;
+        }
+        acc.x = fmaf(nu, x.x, acc.x);
+        acc.y = fmaf(nu, x.y, acc.y);
+        acc.z = fmaf(nu, x.z, acc.z);
+        acc.w = fmaf(nu, x.w, acc.w);
+      }
+    }
+    if (SCALE_DST && r < nrows) {
+      const float nv = g.norm[row0 + r];
+      acc.x *= nv; acc.y *= nv; acc.z *= nv; acc.w *= nv;
+    }
+    st_f4(As + r * lda + 4 * lane, acc);
+  }
+}
+
+}  // namespace gmeta

@@ -1,0 +1,424 @@
+// Fused GCN layer over a packed meta-batch of local subgraphs -- fp32 FFMA implementation
+// (any shape; the tcgen05 3xTF32 implementation in gcn_layer_tc.cu covers the wide shapes).
+//
+// Replaces GraphConv.forward (reference G-Meta/learner.py:25-56): in-degree normalisation,
+// CSR neighbour gather + sum aggregation, feature x weight contraction, bias, ReLU -- one
+// kernel, per-task weights selected per row tile.  Also the layer's weight gradient
+// (autograd.grad at meta.py:125,149 restricted to this layer), which re-gathers the
+// aggregated rows instead of storing them.
+#include "common.cuh"
+
+namespace gmeta {
+
+thread_local int g_launch_count = 0;
+
+namespace {
+
+constexpr int TM = GMETA_TILE_ROWS;  // rows per tile
+constexpr int BN = 128;              // output columns per work item
+constexpr int KP = 128;              // K panel staged in shared memory
+constexpr int KC = 16;               // K chunk of the weight staging
+constexpr int LDA = KP + 4;
+constexpr int LDB = BN + 4;
+constexpr int NTHREADS = 256;
+constexpr int NWARPS = NTHREADS / 32;
+constexpr size_t kFwdSmem = (size_t)(TM * LDA + 2 * KC * LDB) * sizeof(float);
+
+struct FwdParams {
+  GatherSrc g;
+  const int32_t* tile_row0;
+  const int32_t* tile_nrows;
+  const int32_t* tile_task;
+  int n_tiles;
+  const float* W;
+  long long w_task_stride;
+  int ldw;
+  int trans_w;
+  const float* bias;
+  long long b_task_stride;
+  int f_out;
+  int relu;
+  const float* relu_mask;
+  float* out;
+  int ld_out;
+  int vec_out;  // 16-byte stores allowed
+};
+
+// B[k][j] of the contraction, bounds-masked.
+__device__ __forceinline__ float load_w(const float* W, int ldw, int trans, int k, int j, int f_in,
+                                        int f_out) {
+  if (k >= f_in || j >= f_out) return 0.f;
+  return trans ? W[(size_t)j * ldw + k] : W[(size_t)k * ldw + j];
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(NTHREADS, 2) gcn_layer_fwd_simt_kernel(const FwdParams p) {
+  extern __shared__ __align__(16) float smem[];
+  float* As = smem;                // [TM][LDA]   aggregated rows, one K panel
+  float* Bs = smem + TM * LDA;     // [2][KC][LDB] weight chunk, double buffered
+  const int tid = threadIdx.x;
+  const int tx = tid & 15;         // 8 output columns: 4*tx.. and 64+4*tx..
+  const int ty = tid >> 4;         // 8 output rows:    ty + 16*i
+  const int f_in = p.g.f_in, f_out = p.f_out;
+  const int n_cb = (f_out + BN - 1) / BN;
+  const int n_kp = (f_in + KP - 1) / KP;
+  const int n_work = p.n_tiles * n_cb;
+
+  for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
+    const int tile = work / n_cb, cb = work - tile * n_cb;
+    const int row0 = p.tile_row0[tile], nrows = p.tile_nrows[tile], task = p.tile_task[tile];
+    const float* W = p.W + (long long)task * p.w_task_stride;
+    const int col0 = cb * BN;
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    for (int kp = 0; kp < n_kp; ++kp) {
+      const int k0 = kp * KP;
+      const int klen = min(KP, f_in - k0);
+      const int n_kc = (klen + KC - 1) / KC;
+      __syncthreads();  // previous panel / work item finished reading As and Bs
+      gather_rows<VEC, TM, NWARPS, false>(p.g, row0, nrows, k0, As, LDA);
+
+      // weight chunk: 16 x 128 values, 8 per thread, staged through registers
+      float wreg[8];
+      auto fetch_w = [&](int kc) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int e = tid + NTHREADS * i;
+          int kk, jj;
+          if (p.trans_w) { jj = e >> 4; kk = e & 15; } else { kk = e >> 7; jj = e & 127; }
+          wreg[i] = load_w(W, p.ldw, p.trans_w, k0 + kc * KC + kk, col0 + jj, f_in, f_out);
+        }
+      };
+      auto stash_w = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int e = tid + NTHREADS * i;
+          int kk, jj;
+          if (p.trans_w) { jj = e >> 4; kk = e & 15; } else { kk = e >> 7; jj = e & 127; }
+          Bs[(buf * KC + kk) * LDB + jj] = wreg[i];
+        }
+      };
+      fetch_w(0);
+      stash_w(0);
+      __syncthreads();  // As panel and Bs[0] visible
+      for (int kc = 0; kc < n_kc; ++kc) {
+        const int buf = kc & 1;
+        if (kc + 1 < n_kc) fetch_w(kc + 1);
+        const float* Ab = As + kc * KC;
+        const float* Bb = Bs + buf * KC * LDB;
+#pragma unroll
+        for (int kk = 0; kk < KC; kk += 4) {
+          float4 a[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] = ld_f4(Ab + (ty + 16 * i) * LDA + kk);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 b0 = ld_f4(Bb + (kk + q) * LDB + 4 * tx);
+            const float4 b1 = ld_f4(Bb + (kk + q) * LDB + 64 + 4 * tx);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float av = q == 0 ? a[i].x : q == 1 ? a[i].y : q == 2 ? a[i].z : a[i].w;
+              acc[i][0] = fmaf(av, b0.x, acc[i][0]);
+              acc[i][1] = fmaf(av, b0.y, acc[i][1]);
+              acc[i][2] = fmaf(av, b0.z, acc[i][2]);
+              acc[i][3] = fmaf(av, b0.w, acc[i][3]);
+              acc[i][4] = fmaf(av, b1.x, acc[i][4]);
+              acc[i][5] = fmaf(av, b1.y, acc[i][5]);
+              acc[i][6] = fmaf(av, b1.z, acc[i][6]);
+              acc[i][7] = fmaf(av, b1.w, acc[i][7]);
+            }
+          }
+        }
+        if (kc + 1 < n_kc) stash_w(buf ^ 1);
+        __syncthreads();
+      }
+    }
+
+    // epilogue: norm[v] * acc + bias, ReLU / mask, store
+    const float* bias = p.bias ? p.bias + (long long)task * p.b_task_stride : nullptr;
+    const int f_out4 = min((f_out + 3) & ~3, p.ld_out);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = ty + 16 * i;
+      if (r >= nrows) continue;
+      const int v = row0 + r;
+      const float nv = p.g.norm[v];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = col0 + 64 * h + 4 * tx;
+        if (c >= f_out4) continue;
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float val = 0.f;
+          if (c + j < f_out) {
+            val = nv * acc[i][4 * h + j];
+            if (bias) val += bias[c + j];
+            if (p.relu) val = fmaxf(val, 0.f);
+            if (p.relu_mask && !(p.relu_mask[(size_t)v * p.ld_out + c + j] > 0.f)) val = 0.f;
+          }
+          o[j] = val;
+        }
+        float* dst = p.out + (size_t)v * p.ld_out + c;
+        if (p.vec_out && c + 4 <= f_out4) {
+          st_f4(dst, make_float4(o[0], o[1], o[2], o[3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (c + j < f_out4) dst[j] = o[j];
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight gradient
+// ------------------------------------------------------------------------------------------
+constexpr int WG_ROWS = 32;  // rows per staged chunk
+constexpr int WG_MAX_SPLIT = 16;
+constexpr size_t kWgSmem = (size_t)(2 * WG_ROWS * LDA) * sizeof(float);
+
+struct WgradParams {
+  GatherSrc g;
+  const int32_t* task_row_ptr;
+  int n_tasks;
+  const float* dZ;
+  int ld_dz;
+  int f_out;
+  int n_split;
+  int vec_dz;
+  float* part_w;  // [T][n_split][f_in][f_out]
+  float* part_b;  // [T][n_split][f_out]
+};
+
+template <bool VEC>
+__global__ void __launch_bounds__(NTHREADS, 2) gcn_layer_wgrad_simt_kernel(const WgradParams p) {
+  extern __shared__ __align__(16) float smem[];
+  float* As = smem;                  // [32][LDA]  norm[v] * M[v, kblock]
+  float* Bs = smem + WG_ROWS * LDA;  // [32][LDA]  dZ[v, jblock]
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int f_in = p.g.f_in, f_out = p.f_out;
+  const int n_kb = (f_in + KP - 1) / KP, n_jb = (f_out + BN - 1) / BN;
+  const int n_work = p.n_tasks * n_kb * n_jb * p.n_split;
+
+  for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
+    int w = work;
+    const int jb = w % n_jb; w /= n_jb;
+    const int kb = w % n_kb; w /= n_kb;
+    const int sp = w % p.n_split;
+    const int task = w / p.n_split;
+    const int rs = p.task_row_ptr[task], re = p.task_row_ptr[task + 1];
+    const int n_chunks = (re - rs + WG_ROWS - 1) / WG_ROWS;
+    const int c_beg = (int)((long long)n_chunks * sp / p.n_split);
+    const int c_end = (int)((long long)n_chunks * (sp + 1) / p.n_split);
+    const int k0 = kb * KP, j0 = jb * BN;
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    float bsum[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
+
+    for (int c = c_beg; c < c_end; ++c) {
+      const int row0 = rs + c * WG_ROWS;
+      const int nrows = min(WG_ROWS, re - row0);
+      __syncthreads();
+      gather_rows<VEC, WG_ROWS, NWARPS, true>(p.g, row0, nrows, k0, As, LDA);
+      // dZ chunk: 32 rows x 128 columns; thread -> (row = tid/32 + 8*i, 4 columns at 4*(tid%32))
+#pragma unroll
+      for (int i = 0; i < WG_ROWS / NWARPS; ++i) {
+        const int r = (tid >> 5) + NWARPS * i;
+        const int cc = j0 + 4 * (tid & 31);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nrows) {
+          const float* src = p.dZ + (size_t)(row0 + r) * p.ld_dz + cc;
+          if (p.vec_dz && cc + 4 <= f_out) {
+            v = ld_f4(src);
+          } else {
+            if (cc + 0 < f_out) v.x = src[0];
+            if (cc + 1 < f_out) v.y = src[1];
+            if (cc + 2 < f_out) v.z = src[2];
+            if (cc + 3 < f_out) v.w = src[3];
+          }
+        }
+        st_f4(Bs + r * LDA + 4 * (tid & 31), v);
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int r = 0; r < WG_ROWS; ++r) {
+        const float4 a0 = ld_f4(As + r * LDA + 4 * ty);
+        const float4 a1 = ld_f4(As + r * LDA + 64 + 4 * ty);
+        const float4 b0 = ld_f4(Bs + r * LDA + 4 * tx);
+        const float4 b1 = ld_f4(Bs + r * LDA + 64 + 4 * tx);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        if (ty == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bsum[j] += b[j];
+        }
+      }
+    }
+
+    float* pw = p.part_w + ((size_t)task * p.n_split + sp) * f_in * f_out;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = k0 + (i < 4 ? 4 * ty + i : 64 + 4 * ty + (i - 4));
+      if (k >= f_in) continue;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int jj = j0 + (j < 4 ? 4 * tx + j : 64 + 4 * tx + (j - 4));
+        if (jj < f_out) pw[(size_t)k * f_out + jj] = acc[i][j];
+      }
+    }
+    if (kb == 0 && ty == 0) {
+      float* pb = p.part_b + ((size_t)task * p.n_split + sp) * f_out;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int jj = j0 + (j < 4 ? 4 * tx + j : 64 + 4 * tx + (j - 4));
+        if (jj < f_out) pb[jj] = bsum[j];
+      }
+    }
+  }
+}
+
+// dW[t] = sum_sp part_w[t][sp], db[t] = sum_sp part_b[t][sp]  (fixed order)
+__global__ void wgrad_reduce_kernel(const float* part_w, const float* part_b, int n_tasks,
+                                    int n_split, int n_w, int f_out, float* dW,
+                                    long long dw_stride, float* db, long long db_stride) {
+  const long long total = (long long)n_tasks * (n_w + f_out);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i / (n_w + f_out));
+    const int e = (int)(i - (long long)t * (n_w + f_out));
+    float s = 0.f;
+    if (e < n_w) {
+      const float* src = part_w + (size_t)t * n_split * n_w + e;
+      for (int sp = 0; sp < n_split; ++sp) s += src[(size_t)sp * n_w];
+      dW[t * dw_stride + e] = s;
+    } else {
+      const int j = e - n_w;
+      const float* src = part_b + (size_t)t * n_split * f_out + j;
+      for (int sp = 0; sp < n_split; ++sp) s += src[(size_t)sp * f_out];
+      db[t * db_stride + j] = s;
+    }
+  }
+}
+
+__global__ void degree_norm_kernel(const int32_t* indptr, int n, float* norm) {
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+    const int d = max(indptr[v + 1] - indptr[v], 1);
+    norm[v] = __fdiv_rn(1.0f, __fsqrt_rn((float)d));  // == torch CPU pow(x, -0.5) -> rsqrt path
+  }
+}
+
+int pick_wgrad_split(int n_tasks, int f_in, int f_out) {
+  const int base = n_tasks * ceil_div(f_in, KP) * ceil_div(f_out, BN);
+  int s = ceil_div(4 * kNumSMs, base > 0 ? base : 1);
+  if (s < 1) s = 1;
+  if (s > WG_MAX_SPLIT) s = WG_MAX_SPLIT;
+  return s;
+}
+
+}  // namespace
+
+int gcn_layer_fwd_simt(const GatherSrc& g, const int32_t* tile_row0, const int32_t* tile_nrows,
+                       const int32_t* tile_task, int n_tiles, const float* W,
+                       int64_t w_task_stride, int ldw, int trans_w, const float* bias,
+                       int64_t b_task_stride, int f_out, int relu, const float* relu_mask,
+                       float* out, int ld_out, cudaStream_t stream) {
+  FwdParams p;
+  p.g = g;
+  p.tile_row0 = tile_row0; p.tile_nrows = tile_nrows; p.tile_task = tile_task; p.n_tiles = n_tiles;
+  p.W = W; p.w_task_stride = w_task_stride; p.ldw = ldw; p.trans_w = trans_w;
+  p.bias = bias; p.b_task_stride = b_task_stride; p.f_out = f_out; p.relu = relu;
+  p.relu_mask = relu_mask; p.out = out; p.ld_out = ld_out;
+  p.vec_out = (ld_out % 4 == 0) && aligned16(out);
+  const bool vec_in = (g.ld_in % 4 == 0) && aligned16(g.in) && g.ld_in >= round_up(g.f_in, 4);
+  const int n_work = n_tiles * ceil_div(f_out, BN);
+  const int grid = n_work < 16 * kNumSMs ? n_work : 16 * kNumSMs;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(gcn_layer_fwd_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
+    cudaFuncSetAttribute(gcn_layer_fwd_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
+    attr_done = true;
+  }
+  if (vec_in)
+    gcn_layer_fwd_simt_kernel<true><<<grid, NTHREADS, kFwdSmem, stream>>>(p);
+  else
+    gcn_layer_fwd_simt_kernel<false><<<grid, NTHREADS, kFwdSmem, stream>>>(p);
+  return check_launch();
+}
+
+}  // namespace gmeta
+
+using namespace gmeta;
+
+extern "C" int gmeta_degree_norm(const int32_t* indptr, int32_t n_nodes, float* norm, void* stream) {
+  if (n_nodes < 0 || (n_nodes > 0 && (!indptr || !norm))) return GMETA_ERR_BAD_ARG;
+  if (n_nodes == 0) return GMETA_OK;
+  const int grid = ceil_div(n_nodes, 256) < 8 * kNumSMs ? ceil_div(n_nodes, 256) : 8 * kNumSMs;
+  degree_norm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(indptr, n_nodes, norm);
+  return check_launch();
+}
+
+extern "C" int64_t gmeta_gcn_layer_wgrad_workspace_bytes(int32_t n_tasks, int32_t f_in, int32_t f_out) {
+  if (n_tasks <= 0 || f_in <= 0 || f_out <= 0) return 0;
+  const int s = pick_wgrad_split(n_tasks, f_in, f_out);
+  return (int64_t)n_tasks * s * ((int64_t)f_in * f_out + f_out) * (int64_t)sizeof(float);
+}
+
+extern "C" int gmeta_gcn_layer_wgrad(const float* in, int32_t ld_in, const int32_t* in_row_map,
+                                     const int32_t* indptr, const int32_t* indices, const float* norm,
+                                     const int32_t* task_row_ptr, int32_t n_tasks, const float* dZ,
+                                     int32_t ld_dz, int32_t f_in, int32_t f_out, float* dW,
+                                     int64_t dw_task_stride, float* db, int64_t db_task_stride,
+                                     void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!in || !indptr || !norm || !task_row_ptr || !dZ || !dW || !db || !workspace)
+    return GMETA_ERR_BAD_ARG;
+  if (n_tasks <= 0 || f_in <= 0 || f_out <= 0 || ld_in < f_in || ld_dz < f_out) return GMETA_ERR_BAD_ARG;
+  if (workspace_bytes < gmeta_gcn_layer_wgrad_workspace_bytes(n_tasks, f_in, f_out)) return GMETA_ERR_WORKSPACE;
+  if (!aligned16(workspace)) return GMETA_ERR_ALIGN;
+  WgradParams p;
+  p.g.in = in; p.g.in_row_map = in_row_map; p.g.indptr = indptr; p.g.indices = indices;
+  p.g.norm = norm; p.g.ld_in = ld_in; p.g.f_in = f_in;
+  p.task_row_ptr = task_row_ptr; p.n_tasks = n_tasks; p.dZ = dZ; p.ld_dz = ld_dz; p.f_out = f_out;
+  p.n_split = pick_wgrad_split(n_tasks, f_in, f_out);
+  p.vec_dz = (ld_dz % 4 == 0) && aligned16(dZ);
+  p.part_w = (float*)workspace;
+  p.part_b = p.part_w + (size_t)n_tasks * p.n_split * f_in * f_out;
+  const bool vec_in = (ld_in % 4 == 0) && aligned16(in) && ld_in >= round_up(f_in, 4);
+  const int n_work = n_tasks * ceil_div(f_in, KP) * ceil_div(f_out, BN) * p.n_split;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(gcn_layer_wgrad_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem);
+    cudaFuncSetAttribute(gcn_layer_wgrad_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem);
+    attr_done = true;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (vec_in)
+    gcn_layer_wgrad_simt_kernel<true><<<n_work, NTHREADS, kWgSmem, s>>>(p);
+  else
+    gcn_layer_wgrad_simt_kernel<false><<<n_work, NTHREADS, kWgSmem, s>>>(p);
+  int rc = check_launch();
+  if (rc != GMETA_OK) return rc;
+  const int n_w = f_in * f_out;
+  const long long total = (long long)n_tasks * (n_w + f_out);
+  const int grid = (int)((total + 255) / 256 < 8 * kNumSMs ? (total + 255) / 256 : 8 * kNumSMs);
+  wgrad_reduce_kernel<<<grid, 256, 0, s>>>(p.part_w, p.part_b, n_tasks, p.n_split, n_w, f_out, dW,
+                                          dw_task_stride, db, db_task_stride);
+  return check_launch();
+}

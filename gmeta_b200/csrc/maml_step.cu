@@ -1,0 +1,243 @@
+// C++ driver that enqueues the whole first-order ProtoMAML inner loop for every task of a
+// packed meta-batch (reference G-Meta/meta.py:118-161 forward_ProtoMAML and :193-230
+// finetunning_ProtoMAML, minus the optimizer step): K support forward/backward + SGD steps,
+// K+1 query forwards with their prototype losses, and -- for training -- the backward of the
+// last query loss through the query forward (weights fast_K) and, via the prototypes, through
+// the last support forward (weights fast_{K-1}); SURVEY 3.2.  No host synchronisation, no
+// allocation: every buffer is carved out of the caller's workspace.
+#include "common.cuh"
+
+namespace gmeta {
+
+int proto_loss_launch(bool spt, const float* logits, int n_out, const int32_t* task_sub_ptr, int n_tasks,
+                      const int32_t* class_pos, const int32_t* class_occ, const int32_t* n_classes,
+                      int n_support, int max_classes, int max_rows, float grad_scale, float* protos,
+                      float* loss, float* acc, int out_stride, float* dlogits, float* dprotos,
+                      cudaStream_t s);
+
+namespace {
+
+inline int64_t align_up(int64_t x) { return (x + 255) / 256 * 256; }
+
+struct Carver {
+  char* base;
+  int64_t off;
+  template <typename T>
+  T* take(int64_t count) {
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += align_up(count * (int64_t)sizeof(T));
+    return p;
+  }
+};
+
+struct StepBuffers {
+  float* fast[2];
+  float* g_spt;
+  float* g_qry;
+  float* act_spt[GMETA_MAX_LAYERS];
+  float* act_qry[GMETA_MAX_LAYERS];
+  float* dz_spt[2];
+  float* dz_qry[2];
+  float* logits_s;
+  float* logits_q;
+  float* dlogits_s;
+  float* dlogits_q;
+  float* protos;
+  float* dprotos;
+  float* acc_s;
+  void* wgrad_ws;
+  int64_t wgrad_ws_bytes;
+  int ld[GMETA_MAX_LAYERS];
+  int64_t total;
+};
+
+int validate(const gmeta_step_args_t* a) {
+  if (!a) return GMETA_ERR_BAD_ARG;
+  const gmeta_model_t& m = a->model;
+  if (m.n_layers < 1 || m.n_layers > GMETA_MAX_LAYERS || m.n_out <= 0 || m.n_params_padded <= 0)
+    return GMETA_ERR_BAD_ARG;
+  for (int l = 0; l < m.n_layers; ++l) {
+    if (m.f_in[l] <= 0 || m.f_out[l] <= 0) return GMETA_ERR_BAD_ARG;
+    if (l > 0 && m.f_in[l] != m.f_out[l - 1]) return GMETA_ERR_BAD_ARG;
+  }
+  if (a->spt.n_tasks <= 0 || a->spt.n_tasks != a->qry.n_tasks) return GMETA_ERR_BAD_ARG;
+  if (a->update_step < 1 || a->n_support < 1 || a->max_classes < 1) return GMETA_ERR_BAD_ARG;
+  if (a->compute_meta_grad && a->update_step < 2) return GMETA_ERR_UNSUPPORTED;  // meta.py:161 has no grad path at K=1
+  return GMETA_OK;
+}
+
+void carve(const gmeta_step_args_t* a, void* ws, StepBuffers& b) {
+  const gmeta_model_t& m = a->model;
+  const int64_t T = a->spt.n_tasks, P = m.n_params_padded, C = m.n_out, MC = a->max_classes;
+  const int64_t Ns = a->spt.n_nodes, Nq = a->qry.n_nodes, Ss = a->spt.n_subgraphs, Sq = a->qry.n_subgraphs;
+  Carver c{reinterpret_cast<char*>(ws), 0};
+  int ld_max = 4;
+  for (int l = 0; l < m.n_layers; ++l) {
+    b.ld[l] = round_up(m.f_out[l], 4);
+    if (b.ld[l] > ld_max) ld_max = b.ld[l];
+  }
+  b.fast[0] = c.take<float>(T * P);
+  b.fast[1] = c.take<float>(T * P);
+  b.g_spt = c.take<float>(T * P);
+  b.g_qry = c.take<float>(T * P);
+  for (int l = 0; l < m.n_layers; ++l) b.act_spt[l] = c.take<float>(Ns * b.ld[l]);
+  for (int l = 0; l < m.n_layers; ++l) b.act_qry[l] = c.take<float>(Nq * b.ld[l]);
+  b.dz_spt[0] = c.take<float>(Ns * ld_max);
+  b.dz_spt[1] = c.take<float>(m.n_layers > 1 ? Ns * ld_max : 0);
+  b.dz_qry[0] = c.take<float>(a->compute_meta_grad ? Nq * ld_max : 0);
+  b.dz_qry[1] = c.take<float>(a->compute_meta_grad && m.n_layers > 1 ? Nq * ld_max : 0);
+  b.logits_s = c.take<float>(Ss * C);
+  b.logits_q = c.take<float>(Sq * C);
+  b.dlogits_s = c.take<float>(Ss * C);
+  b.dlogits_q = c.take<float>(Sq * C);
+  b.protos = c.take<float>(T * MC * C);
+  b.dprotos = c.take<float>(T * MC * C);
+  b.acc_s = c.take<float>(T);
+  b.wgrad_ws_bytes = 0;
+  for (int l = 0; l < m.n_layers; ++l) {
+    const int64_t w = gmeta_gcn_layer_wgrad_workspace_bytes((int)T, m.f_in[l], m.f_out[l]);
+    if (w > b.wgrad_ws_bytes) b.wgrad_ws_bytes = w;
+  }
+  b.wgrad_ws = c.take<char>(b.wgrad_ws_bytes);
+  b.total = c.off;
+}
+
+struct Runner {
+  const gmeta_step_args_t* a;
+  StepBuffers b;
+  cudaStream_t s;
+  int rc = GMETA_OK;
+
+  bool ok() const { return rc == GMETA_OK; }
+  void run(int code) { if (rc == GMETA_OK) rc = code; }
+
+  void forward(const gmeta_packed_set_t& set, float* const* act, const float* W, int64_t stride, float* logits) {
+    const gmeta_model_t& m = a->model;
+    for (int l = 0; l < m.n_layers && ok(); ++l) {
+      const float* in = l == 0 ? a->feat_table : act[l - 1];
+      const int ld_in = l == 0 ? a->ld_feat : b.ld[l - 1];
+      run(gmeta_gcn_layer_fwd(in, ld_in, l == 0 ? set.feat_row : nullptr, set.indptr, set.indices, set.norm,
+                              set.tile_row0, set.tile_nrows, set.tile_task, set.n_tiles, W + m.w_off[l],
+                              stride, m.f_out[l], 0, W + m.b_off[l], stride, m.f_in[l], m.f_out[l], 1,
+                              nullptr, act[l], b.ld[l], a->impl, s));
+    }
+    const int L = m.n_layers;
+    run(gmeta_readout_linear_fwd(act[L - 1], b.ld[L - 1], m.f_out[L - 1], set.centre_row,
+                                 set.centres_per_subgraph, set.task_sub_ptr, set.n_tasks, set.n_subgraphs,
+                                 W + m.wlin_off, stride, W + m.blin_off, stride, m.n_out, logits, s));
+  }
+
+  void backward(const gmeta_packed_set_t& set, float* const* act, float* const* dz, const float* W,
+                int64_t stride, const float* dlogits, float* gout) {
+    const gmeta_model_t& m = a->model;
+    const int L = m.n_layers;
+    const int64_t P = m.n_params_padded;
+    int cur = 0;
+    run(gmeta_readout_linear_bwd(act[L - 1], b.ld[L - 1], m.f_out[L - 1], set.n_nodes, set.centre_row,
+                                 set.centres_per_subgraph, set.task_sub_ptr, set.n_tasks, set.n_subgraphs,
+                                 W + m.wlin_off, stride, m.n_out, dlogits, gout + m.wlin_off, P,
+                                 gout + m.blin_off, P, dz[cur], s));
+    for (int l = L - 1; l >= 0 && ok(); --l) {
+      const float* in = l == 0 ? a->feat_table : act[l - 1];
+      const int ld_in = l == 0 ? a->ld_feat : b.ld[l - 1];
+      run(gmeta_gcn_layer_wgrad(in, ld_in, l == 0 ? set.feat_row : nullptr, set.indptr, set.indices,
+                                set.norm, set.task_row_ptr, set.n_tasks, dz[cur], b.ld[l], m.f_in[l],
+                                m.f_out[l], gout + m.w_off[l], P, gout + m.b_off[l], P, b.wgrad_ws,
+                                b.wgrad_ws_bytes, s));
+      if (l > 0) {
+        // data gradient = the forward kernel on the transposed graph with W^T, masked by the
+        // ReLU of the layer below (features carry no gradient, so layer 0 stops here)
+        run(gmeta_gcn_layer_fwd(dz[cur], b.ld[l], nullptr, set.t_indptr, set.t_indices, set.norm,
+                                set.tile_row0, set.tile_nrows, set.tile_task, set.n_tiles, W + m.w_off[l],
+                                stride, m.f_out[l], 1, nullptr, 0, m.f_out[l], m.f_in[l], 0, act[l - 1],
+                                dz[cur ^ 1], b.ld[l - 1], a->impl, s));
+        cur ^= 1;
+      }
+    }
+  }
+
+  void qry_loss(int k, bool want_grad) {
+    const gmeta_packed_set_t& q = a->qry;
+    // prototypes (and their count) come from the support set of the same task (meta.py:132,154)
+    run(proto_loss_launch(false, b.logits_q, a->model.n_out, q.task_sub_ptr, q.n_tasks, q.class_pos, nullptr,
+                          a->spt.n_classes, 0, a->max_classes, max_rows_q, a->grad_scale, b.protos,
+                          a->loss_q + k, a->acc_q + k, a->update_step + 1, want_grad ? b.dlogits_q : nullptr,
+                          want_grad ? b.dprotos : nullptr, s));
+  }
+  int max_rows_s = 1, max_rows_q = 1;
+};
+
+}  // namespace
+}  // namespace gmeta
+
+using namespace gmeta;
+
+extern "C" int64_t gmeta_maml_step_workspace_bytes(const gmeta_step_args_t* args) {
+  if (validate(args) != GMETA_OK) return -1;
+  StepBuffers b;
+  carve(args, nullptr, b);
+  return b.total;
+}
+
+extern "C" int gmeta_last_launch_count(void) { return g_launch_count; }
+
+extern "C" int gmeta_maml_step(const gmeta_step_args_t* a, void* stream) {
+  int rc = validate(a);
+  if (rc != GMETA_OK) return rc;
+  if (!a->workspace || !a->theta || !a->feat_table || !a->loss_q || !a->acc_q || !a->loss_s)
+    return GMETA_ERR_BAD_ARG;
+  if (a->compute_meta_grad && !a->meta_grad) return GMETA_ERR_BAD_ARG;
+  if (!aligned16(a->workspace)) return GMETA_ERR_ALIGN;
+  Runner r;
+  r.a = a;
+  r.s = (cudaStream_t)stream;
+  carve(a, a->workspace, r.b);
+  if (r.b.total > a->workspace_bytes) return GMETA_ERR_WORKSPACE;
+  g_launch_count = 0;
+
+  const gmeta_model_t& m = a->model;
+  const gmeta_packed_set_t& sp = a->spt;
+  const gmeta_packed_set_t& qr = a->qry;
+  const int T = sp.n_tasks, K = a->update_step;
+  const int64_t P = m.n_params_padded;
+  StepBuffers& b = r.b;
+  cudaStream_t s = r.s;
+  // shared memory of the loss kernels is sized for the task with the most subgraphs
+  r.max_rows_s = a->spt_max_rows_per_task > 0 ? a->spt_max_rows_per_task : sp.n_subgraphs;
+  r.max_rows_q = a->qry_max_rows_per_task > 0 ? a->qry_max_rows_per_task : qr.n_subgraphs;
+
+  if (cudaMemsetAsync(b.g_spt, 0, (size_t)T * P * sizeof(float), s) != cudaSuccess) return GMETA_ERR_LAUNCH;
+  if (cudaMemsetAsync(b.g_qry, 0, (size_t)T * P * sizeof(float), s) != cudaSuccess) return GMETA_ERR_LAUNCH;
+  r.run(gmeta_degree_norm(sp.indptr, sp.n_nodes, sp.norm, s));
+  r.run(gmeta_degree_norm(qr.indptr, qr.n_nodes, qr.norm, s));
+  r.run(gmeta_proto_label_prep(sp.labels, sp.task_sub_ptr, T, sp.class_pos, sp.class_occ, sp.n_classes, s));
+  r.run(gmeta_proto_label_prep(qr.labels, qr.task_sub_ptr, T, qr.class_pos, qr.class_occ, qr.n_classes, s));
+
+  for (int k = 0; k < K && r.ok(); ++k) {
+    const float* Wcur = k == 0 ? a->theta : b.fast[(k - 1) & 1];
+    const int64_t stride = k == 0 ? 0 : P;
+    r.forward(sp, b.act_spt, Wcur, stride, b.logits_s);
+    if (k == 0 && a->logits_spt0 && r.ok())
+      if (cudaMemcpyAsync(a->logits_spt0, b.logits_s, (size_t)sp.n_subgraphs * m.n_out * sizeof(float),
+                          cudaMemcpyDeviceToDevice, s) != cudaSuccess) r.rc = GMETA_ERR_LAUNCH;
+    r.run(proto_loss_launch(true, b.logits_s, m.n_out, sp.task_sub_ptr, T, sp.class_pos, sp.class_occ,
+                            sp.n_classes, a->n_support, a->max_classes, r.max_rows_s, 1.0f, b.protos,
+                            a->loss_s + k, b.acc_s, K, b.dlogits_s, nullptr, s));
+    r.backward(sp, b.act_spt, b.dz_spt, Wcur, stride, b.dlogits_s, b.g_spt);
+    r.run(gmeta_sgd_update(Wcur, stride, b.g_spt, a->update_lr, T, (int)P, b.fast[k & 1], s));
+    if (k == 0) {  // query loss / accuracy before the first update (meta.py:129-134)
+      r.forward(qr, b.act_qry, a->theta, 0, b.logits_q);
+      r.qry_loss(0, false);
+    }
+    r.forward(qr, b.act_qry, b.fast[k & 1], P, b.logits_q);
+    r.qry_loss(k + 1, a->compute_meta_grad && k == K - 1);
+  }
+  if (a->compute_meta_grad && r.ok()) {
+    r.backward(qr, b.act_qry, b.dz_qry, b.fast[(K - 1) & 1], P, b.dlogits_q, b.g_qry);
+    r.run(gmeta_proto_grad_to_support(b.dprotos, m.n_out, a->max_classes, sp.task_sub_ptr, T, sp.class_pos,
+                                      sp.class_occ, a->n_support, sp.n_subgraphs, b.dlogits_s, s));
+    r.backward(sp, b.act_spt, b.dz_spt, b.fast[(K - 2) & 1], P, b.dlogits_s, b.g_spt);
+    r.run(gmeta_sum_over_tasks(b.g_qry, b.g_spt, T, (int)P, a->meta_grad, s));
+  }
+  return r.rc;
+}

@@ -1,0 +1,246 @@
+"""Drop-in for the reference's G-Meta/learner.py: `Classifier(config)` with the same
+constructor, parameter order/initialisers, `forward(g, to_fetch, features, vars=None)`,
+`parameters()` and `zero_grad(vars=None)` (learner.py:69-209) -- the arithmetic runs in the
+hand-written sm_100a kernels behind the C ABI (include/gmeta_b200.h), including under
+`torch.autograd.grad` (meta.py:125,149 style callers) through an autograd.Function.
+
+`g` is a `PackedSubgraphBatch` (the stand-in for the DGL batched graph the reference gets from
+`dgl.batch`, subgraph_data_processing.py:399-406).  There is no CPU path: tensors are moved to
+the CUDA device (as learner.py:145 does) and a missing extension raises.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.nn import init
+
+from . import _lib
+from ._lib import TILE_ROWS
+
+device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')   # learner.py:10
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class ModelSpec(object):
+    """`config` list (train.py:67-75) -> layer dims and offsets into the flat parameter buffer."""
+
+    def __init__(self, config):
+        self.link_pred = config[-1][0] == 'LinkPred'                      # learner.py:78-79
+        self.conv = [tuple(p) for n, p in config if n == 'GraphConv']
+        lin = [tuple(p) for n, p in config if n == 'Linear']
+        if len(lin) != 1 or not 1 <= len(self.conv) <= _lib.MAX_LAYERS:
+            raise ValueError("config must hold 1..%d 'GraphConv' entries and one 'Linear'" % _lib.MAX_LAYERS)
+        if any(n not in ('GraphConv', 'Linear', 'LinkPred') for n, _ in config):
+            raise ValueError("only 'GraphConv', 'Linear' and 'LinkPred' config entries are supported")
+        self.hid = self.conv[-1][1]
+        self.n_out = lin[0][1]
+        self.lin_in = lin[0][0] * (2 if self.link_pred else 1)
+        # creation order of learner.py:81-97: config order, (W, b) pairs
+        self.shapes, self.offsets, off = [], [], 0
+        for name, p in config:
+            if name == 'GraphConv':
+                shapes = [(p[0], p[1]), (p[1],)]
+            elif name == 'Linear':
+                shapes = [(p[1], self.lin_in), (p[1],)]
+            else:
+                continue
+            for s in shapes:
+                self.shapes.append(s)
+                self.offsets.append(off)
+                off = _round_up(off + int(np.prod(s)), 4)
+        self.n_params_padded = off
+        self.order = [n for n, _ in config if n in ('GraphConv', 'Linear')]
+
+    def c_model(self):
+        m = _lib.Model()
+        m.n_layers = len(self.conv)
+        k = 0
+        li = 0
+        for name in self.order:
+            if name == 'GraphConv':
+                m.f_in[li], m.f_out[li] = self.conv[li]
+                m.w_off[li], m.b_off[li] = self.offsets[k], self.offsets[k + 1]
+                li += 1
+            else:
+                m.wlin_off, m.blin_off = self.offsets[k], self.offsets[k + 1]
+            k += 2
+        m.n_out, m.link_pred, m.n_params_padded = self.n_out, int(self.link_pred), self.n_params_padded
+        return m
+
+    def flatten(self, tensors, out=None):
+        if out is None:
+            out = torch.zeros(self.n_params_padded, dtype=torch.float32, device=tensors[0].device)
+        for t, off, s in zip(tensors, self.offsets, self.shapes):
+            out[off:off + t.numel()].copy_(t.detach().reshape(-1))
+        return out
+
+    def unflatten(self, flat):
+        return [flat[off:off + int(np.prod(s))].view(s) for off, s in zip(self.offsets, self.shapes)]
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def tile_table(task_row_ptr):
+    """Row tiles of <= TILE_ROWS rows that never straddle a task."""
+    n = np.diff(task_row_ptr).astype(np.int64)
+    nt = (n + TILE_ROWS - 1) // TILE_ROWS
+    task = np.repeat(np.arange(n.shape[0], dtype=np.int32), nt)
+    first = np.concatenate([[0], np.cumsum(nt)])[:-1]
+    k = np.arange(int(nt.sum()), dtype=np.int64) - np.repeat(first, nt)
+    row0 = np.repeat(task_row_ptr[:-1].astype(np.int64), nt) + k * TILE_ROWS
+    nrows = np.minimum(TILE_ROWS, np.repeat(task_row_ptr[1:].astype(np.int64), nt) - row0)
+    return row0.astype(np.int32), nrows.astype(np.int32), task
+
+
+class _DeviceGraph(object):
+    """Device copy of one PackedSubgraphBatch as a single-task packed set (cached on the batch)."""
+
+    def __init__(self, g, dev):
+        N = g.n_nodes
+        trp = np.array([0, N], dtype=np.int32)
+        row0, nrows, task = tile_table(trp)
+        i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(dev)  # noqa: E731
+        self.N, self.n_tiles = N, int(row0.shape[0])
+        self.indptr, self.indices = i32(g.indptr), i32(g.indices)
+        self.t_indptr, self.t_indices = i32(g.t_indptr), i32(g.t_indices)
+        self.tile_row0, self.tile_nrows, self.tile_task = i32(row0), i32(nrows), i32(task)
+        self.task_row_ptr = i32(trp)
+        self.sub_off = torch.as_tensor(np.concatenate([[0], np.cumsum(g.batch_num_nodes)])[:-1]).to(dev)
+        self.S = len(g.batch_num_nodes)
+        self.task_sub_ptr = i32(np.array([0, self.S]))
+        self.norm = torch.empty(N, dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib().gmeta_degree_norm(_ptr(self.indptr), N, _ptr(self.norm), _stream()), "degree_norm")
+
+
+def _device_graph(g, dev):
+    dg = getattr(g, "_gmeta_dev", None)
+    if dg is None or dg.norm.device != dev:
+        dg = _DeviceGraph(g, dev)
+        g._gmeta_dev = dg
+    return dg
+
+
+class _ClassifierFn(torch.autograd.Function):
+    """logits = Linear(readout(GCN^h(features))) with per-call weights; backward = the kernels'
+    own weight/data gradients (no autograd graph of small ops)."""
+
+    @staticmethod
+    def forward(ctx, spec, dg, centre_row, features, impl, *vars):
+        L = _lib.lib()
+        dev = features.device
+        x = features.contiguous()
+        acts, inp, ld_in = [], x, x.shape[1]
+        n_conv = len(spec.conv)
+        ws = [v.detach().contiguous() for v in vars]
+        for l, (fi, fo) in enumerate(spec.conv):
+            ld_out = _round_up(fo, 4)
+            out = torch.empty(dg.N, ld_out, dtype=torch.float32, device=dev)
+            _lib.check(L.gmeta_gcn_layer_fwd(
+                _ptr(inp), ld_in, None, _ptr(dg.indptr), _ptr(dg.indices), _ptr(dg.norm),
+                _ptr(dg.tile_row0), _ptr(dg.tile_nrows), _ptr(dg.tile_task), dg.n_tiles,
+                _ptr(ws[2 * l]), 0, fo, 0, _ptr(ws[2 * l + 1]), 0, fi, fo, 1, None, _ptr(out), ld_out,
+                impl, _stream()), "gcn_layer_fwd")
+            acts.append(out)
+            inp, ld_in = out, ld_out
+        cps = 2 if spec.link_pred else 1
+        logits = torch.empty(dg.S, spec.n_out, dtype=torch.float32, device=dev)
+        _lib.check(L.gmeta_readout_linear_fwd(
+            _ptr(acts[-1]), ld_in, spec.hid, _ptr(centre_row), cps, _ptr(dg.task_sub_ptr), 1, dg.S,
+            _ptr(ws[2 * n_conv]), 0, _ptr(ws[2 * n_conv + 1]), 0, spec.n_out, _ptr(logits), _stream()),
+            "readout_linear_fwd")
+        ctx.spec, ctx.dg, ctx.centre_row, ctx.x, ctx.acts, ctx.ws, ctx.impl = spec, dg, centre_row, x, acts, ws, impl
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        L = _lib.lib()
+        spec, dg, acts, ws, x = ctx.spec, ctx.dg, ctx.acts, ctx.ws, ctx.x
+        dev = dlogits.device
+        dlogits = dlogits.contiguous()
+        n_conv = len(spec.conv)
+        cps = 2 if spec.link_pred else 1
+        grads = [torch.zeros_like(w) for w in ws]
+        ld_top = acts[-1].shape[1]
+        dz = torch.empty(dg.N, ld_top, dtype=torch.float32, device=dev)
+        _lib.check(L.gmeta_readout_linear_bwd(
+            _ptr(acts[-1]), ld_top, spec.hid, dg.N, _ptr(ctx.centre_row), cps, _ptr(dg.task_sub_ptr), 1, dg.S,
+            _ptr(ws[2 * n_conv]), 0, spec.n_out, _ptr(dlogits), _ptr(grads[2 * n_conv]), 0,
+            _ptr(grads[2 * n_conv + 1]), 0, _ptr(dz), _stream()), "readout_linear_bwd")
+        for l in range(n_conv - 1, -1, -1):
+            fi, fo = spec.conv[l]
+            inp = x if l == 0 else acts[l - 1]
+            nbytes = L.gmeta_gcn_layer_wgrad_workspace_bytes(1, fi, fo)
+            wsb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            _lib.check(L.gmeta_gcn_layer_wgrad(
+                _ptr(inp), inp.shape[1], None, _ptr(dg.indptr), _ptr(dg.indices), _ptr(dg.norm),
+                _ptr(dg.task_row_ptr), 1, _ptr(dz), dz.shape[1], fi, fo, _ptr(grads[2 * l]), 0,
+                _ptr(grads[2 * l + 1]), 0, _ptr(wsb), nbytes, _stream()), "gcn_layer_wgrad")
+            if l > 0:
+                ld_lo = acts[l - 1].shape[1]
+                dz_lo = torch.empty(dg.N, ld_lo, dtype=torch.float32, device=dev)
+                _lib.check(L.gmeta_gcn_layer_fwd(
+                    _ptr(dz), dz.shape[1], None, _ptr(dg.t_indptr), _ptr(dg.t_indices), _ptr(dg.norm),
+                    _ptr(dg.tile_row0), _ptr(dg.tile_nrows), _ptr(dg.tile_task), dg.n_tiles,
+                    _ptr(ws[2 * l]), 0, fo, 1, None, 0, fo, fi, 0, _ptr(acts[l - 1]), _ptr(dz_lo), ld_lo,
+                    ctx.impl, _stream()), "gcn_layer dgrad")
+                dz = dz_lo
+        return (None, None, None, None, None) + tuple(grads)
+
+
+class Classifier(nn.Module):
+    def __init__(self, config, impl=_lib.IMPL_AUTO):
+        super(Classifier, self).__init__()
+        self.vars = nn.ParameterList()
+        self.config = config
+        self.spec = ModelSpec(config)
+        self.LinkPred_mode = self.spec.link_pred
+        self.impl = impl
+        for name, param in config:                                      # learner.py:81-97
+            if name == 'Linear':
+                w = nn.Parameter(torch.ones(param[1], param[0] * (2 if self.LinkPred_mode else 1)))
+                init.kaiming_normal_(w)
+                self.vars.append(w)
+                self.vars.append(nn.Parameter(torch.zeros(param[1])))
+            if name == 'GraphConv':
+                w = nn.Parameter(torch.Tensor(param[0], param[1]))
+                init.xavier_uniform_(w)
+                self.vars.append(w)
+                self.vars.append(nn.Parameter(torch.zeros(param[1])))
+
+    def forward(self, g, to_fetch, features, vars=None):
+        if vars is None:
+            vars = self.vars
+        if not torch.cuda.is_available():
+            raise _lib.GMetaError("gmeta_b200 needs a CUDA device (there is no CPU path)")
+        _lib.lib()
+        dev = torch.device('cuda', torch.cuda.current_device())
+        h = torch.as_tensor(features).float().to(dev)                    # learner.py:144-145
+        dg = _device_graph(g, dev)
+        to_fetch = torch.as_tensor(to_fetch).to(dev).long()
+        if self.LinkPred_mode:                                           # learner.py:165-168
+            centre = torch.stack((to_fetch[:, 0] + dg.sub_off, to_fetch[:, 1] + dg.sub_off), 1)
+        else:                                                            # learner.py:170
+            centre = to_fetch + dg.sub_off
+        centre = centre.reshape(-1).to(torch.int32).contiguous()
+        vars = [v if v.device == dev else v.to(dev) for v in vars]
+        logits = _ClassifierFn.apply(self.spec, dg, centre, h, self.impl, *vars)
+        return logits, logits                                            # learner.py:194
+
+    def zero_grad(self, vars=None):                                      # learner.py:196-206
+        with torch.no_grad():
+            for p in (self.vars if vars is None else vars):
+                if p.grad is not None:
+                    p.grad.zero_()
+
+    def parameters(self):                                                # learner.py:208-209
+        return self.vars

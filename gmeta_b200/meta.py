@@ -1,0 +1,380 @@
+"""Drop-in for the reference's G-Meta/meta.py: `Meta(args, config)` with `.forward(...)` /
+`.finetunning(...)` of identical signature and return value (meta.py:236-244), plus the public
+`euclidean_dist`, `proto_loss_spt`, `proto_loss_qry` (meta.py:14-79).
+
+One call of `Meta.forward` packs the whole meta-batch (all tasks' support and query subgraph
+batches) into one HBM-resident structure, and enqueues the complete first-order ProtoMAML
+inner loop for every task at once through `gmeta_maml_step` (C++ driver over the sm_100a
+kernels), followed -- across ranks -- by ONE all-reduce of [meta-grad | loss | accuracies] and
+the fused Adam update.  Features are gathered on the device from a resident feature table by
+parent id instead of on the CPU every step (meta.py:119-120).  No CPU fallback.
+"""
+import ctypes as C
+from copy import deepcopy
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib, packing
+from .learner import Classifier, _ptr, _stream
+
+device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')   # meta.py:12
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        raise _lib.GMetaError("gmeta_b200 needs a CUDA device (there is no CPU path)")
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+# ---------------------------------------------------------------------------------------------
+# public loss functions (meta.py:14-79) on the device
+# ---------------------------------------------------------------------------------------------
+def euclidean_dist(x, y):
+    """Squared Euclidean distances between rows of x [N,D] and y [M,D] (meta.py:14-26)."""
+    if x.size(1) != y.size(1):
+        raise Exception                                                  # meta.py:20-21
+    return torch.pow(x.unsqueeze(1) - y.unsqueeze(0), 2).sum(2)
+
+
+def _labels_dev(y_t, dev):
+    y = torch.as_tensor(y_t)
+    return y.to(device=dev, dtype=torch.int32).contiguous()
+
+
+class _ProtoSptFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, y_dev, n_support, n_classes):
+        L = _lib.lib()
+        dev, (S, D) = logits.device, logits.shape
+        z = logits.detach().contiguous()
+        ptr = torch.tensor([0, S], dtype=torch.int32, device=dev)
+        cpos = torch.empty(S, dtype=torch.int32, device=dev)
+        cocc = torch.empty(S, dtype=torch.int32, device=dev)
+        ncls = torch.empty(1, dtype=torch.int32, device=dev)
+        _lib.check(L.gmeta_proto_label_prep(_ptr(y_dev), _ptr(ptr), 1, _ptr(cpos), _ptr(cocc), _ptr(ncls),
+                                            _stream()), "proto_label_prep")
+        protos = torch.zeros(n_classes, D, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        acc = torch.empty((), dtype=torch.float32, device=dev)
+        dz = torch.empty_like(z)
+        _lib.check(L.gmeta_proto_loss_spt(_ptr(z), D, _ptr(ptr), 1, _ptr(cpos), _ptr(cocc), _ptr(ncls),
+                                          n_support, n_classes, S, 1.0, _ptr(protos), _ptr(loss),
+                                          _ptr(acc), 1, _ptr(dz), _stream()), "proto_loss_spt")
+        ctx.save_for_backward(dz, ptr, cpos, cocc)
+        ctx.n_support, ctx.n_classes = n_support, n_classes
+        ctx.mark_non_differentiable(acc)
+        return loss, acc, protos
+
+    @staticmethod
+    def backward(ctx, g_loss, g_acc, g_protos):
+        dz, ptr, cpos, cocc = ctx.saved_tensors
+        grad = dz * g_loss
+        if g_protos is not None:
+            S, D = dz.shape
+            extra = torch.empty_like(dz)
+            gp = g_protos.contiguous()
+            _lib.check(_lib.lib().gmeta_proto_grad_to_support(
+                _ptr(gp), D, ctx.n_classes, _ptr(ptr), 1, _ptr(cpos), _ptr(cocc), ctx.n_support, S,
+                _ptr(extra), _stream()), "proto_grad_to_support")
+            grad = grad + extra
+        return grad, None, None, None
+
+
+class _ProtoQryFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, y_dev, prototypes):
+        L = _lib.lib()
+        dev, (S, D) = logits.device, logits.shape
+        z = logits.detach().contiguous()
+        P = prototypes.detach().contiguous()
+        M = P.shape[0]
+        ptr = torch.tensor([0, S], dtype=torch.int32, device=dev)
+        cpos = torch.empty(S, dtype=torch.int32, device=dev)
+        cocc = torch.empty(S, dtype=torch.int32, device=dev)
+        ncls = torch.empty(1, dtype=torch.int32, device=dev)
+        _lib.check(L.gmeta_proto_label_prep(_ptr(y_dev), _ptr(ptr), 1, _ptr(cpos), _ptr(cocc), _ptr(ncls),
+                                            _stream()), "proto_label_prep")
+        nproto = torch.tensor([M], dtype=torch.int32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        acc = torch.empty((), dtype=torch.float32, device=dev)
+        dz, dP = torch.empty_like(z), torch.empty_like(P)
+        _lib.check(L.gmeta_proto_loss_qry(_ptr(z), D, _ptr(ptr), 1, _ptr(cpos), _ptr(nproto), _ptr(P), M, S,
+                                          1.0, _ptr(loss), _ptr(acc), 1, _ptr(dz), _ptr(dP),
+                                          _stream()), "proto_loss_qry")
+        ctx.save_for_backward(dz, dP)
+        ctx.mark_non_differentiable(acc)
+        return loss, acc
+
+    @staticmethod
+    def backward(ctx, g_loss, g_acc):
+        dz, dP = ctx.saved_tensors
+        return dz * g_loss, None, dP * g_loss
+
+
+def proto_loss_spt(logits, y_t, n_support):
+    """(loss, acc, prototypes) of meta.py:28-54, computed on the device (prototypes carry grad)."""
+    dev = _dev()
+    logits = logits.to(dev)
+    y = torch.as_tensor(y_t)
+    counts = torch.unique(y.cpu(), return_counts=True)[1]
+    if int(counts.min()) < n_support:
+        raise RuntimeError("stack expects each tensor to be equal size (meta.py:42)")
+    return _ProtoSptFn.apply(logits, _labels_dev(y, dev), int(n_support), int(counts.numel()))
+
+
+def proto_loss_qry(logits, y_t, prototypes):
+    """(loss, acc) of meta.py:56-79 on the device."""
+    dev = _dev()
+    logits = logits.to(dev)
+    y = torch.as_tensor(y_t)
+    counts = torch.unique(y.cpu(), return_counts=True)[1]
+    if int(counts.min()) != int(counts.max()):
+        raise RuntimeError("stack expects each tensor to be equal size (meta.py:65)")
+    return _ProtoQryFn.apply(logits, _labels_dev(y, dev), prototypes.to(dev))
+
+
+# ---------------------------------------------------------------------------------------------
+# device-resident state
+# ---------------------------------------------------------------------------------------------
+class FeatureTable(object):
+    """All graphs' node features in one HBM table [sum_g N_g, ld] (ld = F0 rounded up to 4,
+    zero padded), uploaded once and reused by every meta-step; row = graph_row_off[g] + node."""
+
+    def __init__(self, feat, dev):
+        feats = [np.asarray(f, dtype=np.float32) for f in feat]
+        self.f0 = int(feats[0].shape[1])
+        self.ld = (self.f0 + 3) // 4 * 4
+        rows = np.array([f.shape[0] for f in feats], dtype=np.int64)
+        self.graph_row_off = np.concatenate([[0], np.cumsum(rows)])[:-1]
+        self.table = torch.zeros(int(rows.sum()), self.ld, dtype=torch.float32, device=dev)
+        r = 0
+        for f in feats:
+            self.table[r:r + f.shape[0], :self.f0].copy_(torch.from_numpy(np.ascontiguousarray(f)))
+            r += f.shape[0]
+        self._keep = feat          # keeps id(feat) unique while cached
+
+
+class FusedAdam(object):
+    """`meta_optim` (meta.py:97): Adam(lr, betas=(0.9,0.999), eps=1e-8) over the flat parameter
+    buffer, one kernel, with the reference's NaN-skip (meta.py:163-164) evaluated on the device."""
+
+    def __init__(self, n_params, lr, betas=(0.9, 0.999), eps=1e-8):
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.n_params = n_params
+        self.step_count = 0
+        self.exp_avg = None
+        self.exp_avg_sq = None
+
+    def _state(self, dev):
+        if self.exp_avg is None or self.exp_avg.device != dev:
+            self.exp_avg = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
+            self.exp_avg_sq = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
+
+    def step(self, flat_param, flat_grad, loss_gate=None, skipped=None, grad_scale=1.0):
+        self._state(flat_param.device)
+        self.step_count += 1
+        _lib.check(_lib.lib().gmeta_adam_update(
+            _ptr(flat_param), _ptr(flat_grad), _ptr(self.exp_avg), _ptr(self.exp_avg_sq), self.n_params,
+            self.lr, self.betas[0], self.betas[1], self.eps, self.step_count, grad_scale,
+            _ptr(loss_gate), _ptr(skipped), _stream()), "adam_update")
+
+    def state_dict(self):
+        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
+                "lr": self.lr, "betas": self.betas, "eps": self.eps}
+
+
+class Meta(nn.Module):
+    def __init__(self, args, config):
+        super(Meta, self).__init__()
+        self.update_lr = args.update_lr
+        self.meta_lr = args.meta_lr
+        self.n_way = args.n_way
+        self.k_spt = args.k_spt
+        self.k_qry = args.k_qry
+        self.task_num = args.task_num
+        self.update_step = args.update_step
+        self.update_step_test = args.update_step_test
+        self.impl = getattr(args, 'impl', _lib.IMPL_AUTO)
+
+        self.net = Classifier(config, impl=self.impl)
+        self.net = self.net.to(device)
+        self.spec = self.net.spec
+        self.meta_optim = FusedAdam(self.spec.n_params_padded, self.meta_lr)
+        self.method = args.method
+
+        self._staging = None
+        self._feat_cache = None
+        self._ws = None
+        self._scratch = {}
+        self.last = {}                 # diagnostics of the most recent call (loss, launches, bytes)
+        self.return_meta_grad = False  # tests: keep a copy of the reduced meta-gradient
+
+    # -- state that must not travel through copy.deepcopy(maml) (train.py:87,127) --
+    def __deepcopy__(self, memo):
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k in ("_staging", "_feat_cache", "_ws", "_scratch"):
+                new.__dict__[k] = {} if k == "_scratch" else None
+            else:
+                new.__dict__[k] = deepcopy(v, memo)
+        return new
+
+    # -- helpers --
+    def _features(self, feat, dev):
+        key = (id(feat), len(feat))
+        if self._feat_cache is None or self._feat_cache[0] != key:
+            self._feat_cache = (key, FeatureTable(feat, dev))
+        return self._feat_cache[1]
+
+    def _buf(self, name, shape, dtype, dev, zero=False):
+        t = self._scratch.get(name)
+        n = int(np.prod(shape))
+        if t is None or t.numel() < n or t.dtype != dtype or t.device != dev:
+            t = torch.empty(max(n, 1), dtype=dtype, device=dev)
+            self._scratch[name] = t
+        v = t[:n].view(shape)
+        if zero:
+            v.zero_()
+        return v
+
+    def _c_set(self, ps, base_ptr, dev, tag):
+        cs = _lib.PackedSet()
+        cs.n_nodes, cs.n_edges, cs.n_tiles, cs.n_tasks = ps.N, ps.E, ps.n_tiles, ps.T
+        cs.n_subgraphs, cs.centres_per_subgraph = ps.S, ps.cps
+        for k in packing._SEGS:
+            setattr(cs, k, base_ptr + 4 * ps.off[k])
+        cs.norm = self._buf(tag + "norm", (ps.N,), torch.float32, dev).data_ptr()
+        cs.class_pos = self._buf(tag + "cpos", (ps.S,), torch.int32, dev).data_ptr()
+        cs.class_occ = self._buf(tag + "cocc", (ps.S,), torch.int32, dev).data_ptr()
+        cs.n_classes = self._buf(tag + "ncls", (ps.T,), torch.int32, dev).data_ptr()
+        return cs
+
+    def _run(self, x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry, feat,
+             steps, train, flat_theta):
+        """Pack + upload one meta-batch and enqueue the inner loop.  Returns device tensors
+        (acc_q [T,K+1], loss_q [T,K+1], meta_grad [P] or None)."""
+        L = _lib.lib()
+        dev = _dev()
+        T = len(x_spt)
+        if train and steps < 2:
+            raise RuntimeError("element 0 of tensors does not require grad and does not have a grad_fn "
+                               "(update_step must be >= 2, as in the reference: meta.py:137-141,161)")
+        max_classes = packing.validate_labels(y_spt, y_qry, self.k_spt)
+        ft = self._features(feat, dev)
+        if ft.f0 != self.spec.conv[0][0]:
+            raise RuntimeError("feature width %d does not match the first GraphConv (%d)" % (ft.f0, self.spec.conv[0][0]))
+
+        # ---- pack (host, integer only) + one async upload ----
+        ps_s = packing.plan_set(x_spt, c_spt, 0)
+        ps_q = packing.plan_set(x_qry, c_qry, ps_s.end)
+        if self._staging is None or self._staging.device != dev:
+            self._staging = packing.Staging(dev)
+        buf = self._staging.reserve(ps_q.end)
+        packing.fill_set(buf, ps_s, x_spt, y_spt, c_spt, n_spt, g_spt, ft.graph_row_off)
+        packing.fill_set(buf, ps_q, x_qry, y_qry, c_qry, n_qry, g_qry, ft.graph_row_off)
+        h2d = self._staging.upload(ps_q.end)
+        base = self._staging.dev.data_ptr()
+
+        # ---- arguments ----
+        a = _lib.StepArgs()
+        a.model = self.spec.c_model()
+        a.spt = self._c_set(ps_s, base, dev, "s_")
+        a.qry = self._c_set(ps_q, base, dev, "q_")
+        a.feat_table, a.ld_feat = ft.table.data_ptr(), ft.ld
+        a.theta = flat_theta.data_ptr()
+        a.update_step, a.n_support, a.max_classes = steps, self.k_spt, max_classes
+        a.spt_max_rows_per_task, a.qry_max_rows_per_task = ps_s.max_rows_per_task, ps_q.max_rows_per_task
+        a.update_lr = self.update_lr
+        a.grad_scale = 1.0 / (self._global_task_num(T) if train else 1)
+        a.compute_meta_grad = 1 if train else 0
+        a.impl = self.impl
+        P = self.spec.n_params_padded
+        meta_grad = self._buf("meta_grad", (P,), torch.float32, dev) if train else None
+        loss_q = self._buf("loss_q", (T, steps + 1), torch.float32, dev)
+        acc_q = self._buf("acc_q", (T, steps + 1), torch.float32, dev)
+        loss_s = self._buf("loss_s", (T, steps), torch.float32, dev)
+        a.meta_grad = _ptr(meta_grad)
+        a.loss_q, a.acc_q, a.loss_s = loss_q.data_ptr(), acc_q.data_ptr(), loss_s.data_ptr()
+        logits0 = None
+        if getattr(self, "keep_logits_spt0", False):
+            logits0 = self._buf("logits0", (ps_s.S, self.spec.n_out), torch.float32, dev)
+        a.logits_spt0 = _ptr(logits0)
+        nbytes = L.gmeta_maml_step_workspace_bytes(C.byref(a))
+        if nbytes < 0:
+            raise _lib.GMetaError("invalid meta-step arguments")
+        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes * 1.1) + 4096, dtype=torch.uint8, device=dev)
+        a.workspace, a.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
+        _lib.check(L.gmeta_maml_step(C.byref(a), _stream()), "maml_step")
+        self.last = {"h2d_bytes": h2d, "gpu_launches": L.gmeta_last_launch_count(),
+                     "n_nodes": (ps_s.N, ps_q.N), "n_edges": (ps_s.E, ps_q.E), "workspace_bytes": int(nbytes),
+                     "logits_spt0": logits0, "loss_s": loss_s}
+        return acc_q, loss_q, meta_grad
+
+    def _global_task_num(self, local_tasks):
+        from . import dist
+        return dist.global_task_count(local_tasks)
+
+    def _flat_theta(self, params, dev):
+        flat = self._buf("theta", (self.spec.n_params_padded,), torch.float32, dev, zero=True)
+        return self.spec.flatten([p.to(dev) for p in params], flat)
+
+    # -- public API (meta.py:236-244) --
+    def forward_ProtoMAML(self, x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry, feat):
+        from . import dist
+        dev = _dev()
+        K = self.update_step
+        theta = self._flat_theta(self.net.parameters(), dev)
+        acc_q, loss_q, meta_grad = self._run(x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry,
+                                             g_spt, g_qry, feat, K, True, theta)
+        P = self.spec.n_params_padded
+        T_global = self._global_task_num(len(x_spt))
+        # [meta-grad | sum_t loss_q^K | sum_t acc_q[0..K]] -- the one collective of a meta-step
+        red = self._buf("reduce", (P + 1 + K + 1,), torch.float32, dev)
+        red[:P].copy_(meta_grad)
+        red[P] = loss_q[:, K].sum()
+        red[P + 1:] = acc_q.sum(0)
+        dist.allreduce_sum_(red)
+        gate = red[P:P + 1] / T_global                                    # meta.py:161
+        skipped = self._buf("skipped", (1,), torch.int32, dev)
+        self.meta_optim.step(theta, red[:P], loss_gate=gate, skipped=skipped)   # meta.py:163-169
+        for p, v in zip(self.net.parameters(), self.spec.unflatten(theta)):
+            p.data.copy_(v)
+        out = torch.empty(K + 3, dtype=torch.float32, device=dev)
+        out[:K + 1] = red[P + 1:] / T_global                              # meta.py:171
+        out[K + 1] = gate[0]
+        out[K + 2] = skipped[0].float()
+        host = out.cpu()                                                  # the step's only D2H + sync
+        if host[K + 2] != 0:
+            self.meta_optim.step_count -= 1                               # skipped step: no Adam state change
+        self.last.update({"loss_q": float(host[K + 1]), "skipped": bool(host[K + 2] != 0),
+                          "d2h_bytes": int(out.numel() * 4)})
+        if self.return_meta_grad:
+            self.last["meta_grad"] = [g.clone() for g in self.spec.unflatten(red[:P])]
+        return host[:K + 1].numpy().astype(np.float32)
+
+    def finetunning_ProtoMAML(self, x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry, feat):
+        dev = _dev()
+        K = self.update_step_test
+        theta = self._flat_theta(self.net.parameters(), dev)             # fine-tunes a copy (meta.py:181)
+        one = lambda v: [v[0]]                                            # noqa: E731  (meta.py:182-191)
+        acc_q, loss_q, _ = self._run(one(x_spt), one(y_spt), one(x_qry), one(y_qry), one(c_spt), one(c_qry),
+                                     one(n_spt), one(n_qry), one(g_spt), one(g_qry), feat, K, False, theta)
+        host = acc_q[0].cpu()
+        self.last["d2h_bytes"] = int(host.numel() * 4)
+        return host.numpy().astype(np.float32)                            # meta.py:232-234
+
+    def forward(self, x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry, feat):
+        if self.method == 'G-Meta':
+            accs = self.forward_ProtoMAML(x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry, feat)
+        return accs
+
+    def finetunning(self, x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry, feat):
+        if self.method == 'G-Meta':
+            accs = self.finetunning_ProtoMAML(x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry, feat)
+        return accs

@@ -1,0 +1,148 @@
+"""Host-side packing of a meta-batch into the "packed set" layout of include/gmeta_b200.h.
+
+Input is exactly what the reference's Meta.forward receives (meta.py:101, lists of length
+task_num produced by subgraph_data_processing.py:348-419); output is ONE pinned int32 staging
+buffer per meta-batch (so the host->device transfer is a single async copy) plus the counts the
+C ABI needs.  All integer work, vectorised numpy; nothing here touches feature values.
+"""
+import numpy as np
+import torch
+
+from .learner import tile_table
+
+_SEGS = ("indptr", "indices", "t_indptr", "t_indices", "tile_row0", "tile_nrows", "tile_task",
+         "task_row_ptr", "task_sub_ptr", "centre_row", "feat_row", "labels")
+
+
+def _al(n):
+    return (n + 3) // 4 * 4      # 16-byte aligned int32 segments
+
+
+class PackedSetHost(object):
+    """Segment offsets (in int32 elements) of one set inside the staging buffer + its counts."""
+
+    def __init__(self):
+        self.off = {}
+        self.N = self.E = self.S = self.T = self.n_tiles = self.cps = 0
+        self.max_rows_per_task = 0
+        self.max_label = 0
+
+
+def _flat_ids(node_ids):
+    """n_spt[i]: list (per subgraph) of parent-id lists/arrays -> one int64 array."""
+    if len(node_ids) == 0:
+        return np.zeros(0, dtype=np.int64)
+    return np.concatenate([np.asarray(x, dtype=np.int64) for x in node_ids])
+
+
+def plan_set(graphs, centres, off0):
+    """Sizes and segment offsets for one set (spt or qry) of all tasks."""
+    ps = PackedSetHost()
+    ps.T = len(graphs)
+    ns = np.array([g.n_nodes for g in graphs], dtype=np.int64)
+    es = np.array([g.n_edges for g in graphs], dtype=np.int64)
+    ss = np.array([len(g.batch_num_nodes) for g in graphs], dtype=np.int64)
+    ps.node_off = np.concatenate([[0], np.cumsum(ns)])
+    ps.edge_off = np.concatenate([[0], np.cumsum(es)])
+    ps.sub_off = np.concatenate([[0], np.cumsum(ss)])
+    ps.N, ps.E, ps.S = int(ps.node_off[-1]), int(ps.edge_off[-1]), int(ps.sub_off[-1])
+    ps.max_rows_per_task = int(ss.max()) if ps.T else 0
+    c0 = centres[0]
+    ps.cps = 2 if (hasattr(c0, "dim") and c0.dim() == 2) or (isinstance(c0, np.ndarray) and c0.ndim == 2) else 1
+    ps.tiles = tile_table(ps.node_off.astype(np.int64))
+    ps.n_tiles = int(ps.tiles[0].shape[0])
+    sizes = {"indptr": ps.N + 1, "indices": ps.E, "t_indptr": ps.N + 1, "t_indices": ps.E,
+             "tile_row0": ps.n_tiles, "tile_nrows": ps.n_tiles, "tile_task": ps.n_tiles,
+             "task_row_ptr": ps.T + 1, "task_sub_ptr": ps.T + 1, "centre_row": ps.S * ps.cps,
+             "feat_row": ps.N, "labels": ps.S}
+    off = off0
+    for k in _SEGS:
+        ps.off[k] = off
+        off += _al(sizes[k])
+    ps.sizes = sizes
+    ps.end = off
+    return ps
+
+
+def fill_set(buf, ps, graphs, labels, centres, node_ids, graph_idx, graph_row_off):
+    """Write one set's segments into the int32 numpy view `buf` of the staging buffer."""
+    o, N, E = ps.off, ps.N, ps.E
+    indptr = buf[o["indptr"]:o["indptr"] + N + 1]
+    t_indptr = buf[o["t_indptr"]:o["t_indptr"] + N + 1]
+    indices = buf[o["indices"]:o["indices"] + E]
+    t_indices = buf[o["t_indices"]:o["t_indices"] + E]
+    centre = buf[o["centre_row"]:o["centre_row"] + ps.S * ps.cps]
+    feat_row = buf[o["feat_row"]:o["feat_row"] + N]
+    lab = buf[o["labels"]:o["labels"] + ps.S]
+    indptr[0] = 0
+    t_indptr[0] = 0
+    single_graph = graph_row_off.shape[0] == 1
+    for t, g in enumerate(graphs):
+        a, b = int(ps.node_off[t]), int(ps.node_off[t + 1])
+        ea, eb = int(ps.edge_off[t]), int(ps.edge_off[t + 1])
+        sa, sb = int(ps.sub_off[t]), int(ps.sub_off[t + 1])
+        np.add(g.indptr[1:], ea, out=indptr[a + 1:b + 1])
+        np.add(g.t_indptr[1:], ea, out=t_indptr[a + 1:b + 1])
+        np.add(g.indices, a, out=indices[ea:eb])
+        np.add(g.t_indices, a, out=t_indices[ea:eb])
+        bnn = np.asarray(g.batch_num_nodes, dtype=np.int64)
+        sub_first = np.concatenate([[0], np.cumsum(bnn)])[:-1] + a           # learner.py:161-163
+        c = centres[t].numpy() if hasattr(centres[t], "numpy") else np.asarray(centres[t])
+        if ps.cps == 2:
+            centre[2 * sa:2 * sb] = (c.astype(np.int64) + sub_first[:, None]).reshape(-1)
+        else:
+            centre[sa:sb] = c.astype(np.int64) + sub_first
+        ids = _flat_ids(node_ids[t])                                          # meta.py:119-120
+        if single_graph:
+            feat_row[a:b] = ids
+        else:
+            feat_row[a:b] = ids + np.repeat(graph_row_off[np.asarray(graph_idx[t], dtype=np.int64)], bnn)
+        y = labels[t].numpy() if hasattr(labels[t], "numpy") else np.asarray(labels[t])
+        lab[sa:sb] = y
+    buf[o["tile_row0"]:o["tile_row0"] + ps.n_tiles] = ps.tiles[0]
+    buf[o["tile_nrows"]:o["tile_nrows"] + ps.n_tiles] = ps.tiles[1]
+    buf[o["tile_task"]:o["tile_task"] + ps.n_tiles] = ps.tiles[2]
+    buf[o["task_row_ptr"]:o["task_row_ptr"] + ps.T + 1] = ps.node_off
+    buf[o["task_sub_ptr"]:o["task_sub_ptr"] + ps.T + 1] = ps.sub_off
+
+
+def validate_labels(y_spt, y_qry, k_spt):
+    """The equal-count requirements the reference enforces implicitly through torch.stack
+    (meta.py:42,65-66): every support class has >= k_spt members, query classes are balanced
+    and the same as the support classes."""
+    max_classes = 1
+    for ys, yq in zip(y_spt, y_qry):
+        ys = ys.numpy() if hasattr(ys, "numpy") else np.asarray(ys)
+        yq = yq.numpy() if hasattr(yq, "numpy") else np.asarray(yq)
+        cs, ns = np.unique(ys, return_counts=True)
+        cq, nq = np.unique(yq, return_counts=True)
+        if ns.min() < k_spt:
+            raise RuntimeError("stack expects each tensor to be equal size: a support class has fewer "
+                               "than k_spt=%d members (meta.py:42)" % k_spt)
+        if nq.min() != nq.max():
+            raise RuntimeError("stack expects each tensor to be equal size: query classes are not "
+                               "balanced (meta.py:65)")
+        if cs.shape[0] != cq.shape[0] or (cs != cq).any():
+            raise RuntimeError("support and query sets must hold the same classes (meta.py:56-79)")
+        max_classes = max(max_classes, int(cs.shape[0]))
+    return max_classes
+
+
+class Staging(object):
+    """Grow-only pinned host buffer + device buffer for the packed integer arrays."""
+
+    def __init__(self, device):
+        self.device = device
+        self.host = None
+        self.dev = None
+
+    def reserve(self, n):
+        if self.host is None or self.host.numel() < n:
+            cap = int(n * 1.25) + 1024
+            self.host = torch.empty(cap, dtype=torch.int32, pin_memory=torch.cuda.is_available())
+            self.dev = torch.empty(cap, dtype=torch.int32, device=self.device)
+        return self.host.numpy()
+
+    def upload(self, n):
+        self.dev[:n].copy_(self.host[:n], non_blocking=True)
+        return n * 4

@@ -2,7 +2,7 @@
 
 Follows Subgraphs.generate_subgraph / generate_subgraph_link_pred
 (subgraph_data_processing.py:295-346): closure over IN-edges to h hops (link
-prediction: always 2 hops from both endpoints, union), uniform subsample to
+prediction: 2 hops from the first endpoint, 1 from the second -- a reference quirk --, union), uniform subsample to
 `sample_nodes` re-adding the centre(s) when larger, node-induced subgraph,
 memoised per item.  Integer work on numpy CSR; node order inside a subgraph is
 ascending parent id (the reference's is python-`set` order, :303 -- logits are
@@ -95,8 +95,11 @@ def extract_subgraph(G, i, h, sample_nodes, rng=np.random):
 
 
 def extract_subgraph_link_pred(G, i, j, sample_nodes, rng=np.random):
-    """generate_subgraph_link_pred (:323-346): 2-hop closures of both endpoints, union."""
-    nodes = np.union1d(G.khop_in_closure([i], 2), G.khop_in_closure([j], 2))
+    """generate_subgraph_link_pred (:323-346).  Reproduces a reference quirk: the closure of the
+    first endpoint is 2 hops (:327-329), but for the second endpoint the inner comprehension at
+    :332 reads `G.in_edges(j)` for every first-hop neighbour, so only j's ONE-hop in-neighbourhood
+    enters the union."""
+    nodes = np.union1d(G.khop_in_closure([i], 2), G.khop_in_closure([j], 1))
     if nodes.shape[0] > sample_nodes:                                   # :337-339
         nodes = rng.choice(nodes, sample_nodes, replace=False)
         nodes = np.unique(np.append(nodes, [i, j]))

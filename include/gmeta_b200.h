@@ -1,0 +1,247 @@
+/*
+ * gmeta_b200 -- C ABI of the B200-native G-Meta inner-loop hot path.
+ *
+ * The reference (mims-harvard/G-Meta) has no FFI layer: its device arithmetic is
+ * reached through the Python surface of G-Meta/learner.py and G-Meta/meta.py.  Each
+ * entry point below replaces one of those call sites (cited per function) and is what
+ * a maintainer would bind from that file (ctypes stubs in INTEGRATION.md).
+ *
+ * Conventions (all entry points):
+ *   - plain pointers + sizes; every pointer is a DEVICE pointer unless named host_*;
+ *   - fp32 row-major data with an explicit leading dimension (`ld*`, in floats);
+ *     int32 indices; rows of activations/features are 16-byte aligned when ld % 4 == 0
+ *     (the vectorised paths are selected at run time from ld and pointer alignment);
+ *   - returns GMETA_OK or a negative GMETA_ERR_* code; never throws, never allocates or
+ *     frees device memory (workspaces are passed in, sized by the *_workspace_bytes twin),
+ *     never synchronises the stream; launch errors are picked up with cudaGetLastError();
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - stateless, hence thread-safe per stream.
+ *
+ * Packed meta-batch layout ("packed set"): the support (or query) subgraphs of ALL tasks
+ * of a meta-batch are concatenated into one node range [0, N).  Rows of one task are
+ * contiguous (task_row_ptr), a row tile (<= GMETA_TILE_ROWS rows) never straddles two
+ * tasks, and every kernel picks the task's weight copy by tile_task[tile].
+ */
+#ifndef GMETA_B200_H_
+#define GMETA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GMETA_OK 0
+#define GMETA_ERR_BAD_ARG (-1)      /* null pointer / negative size / inconsistent dims */
+#define GMETA_ERR_ALIGN (-2)        /* pointer or leading dimension not aligned as required */
+#define GMETA_ERR_UNSUPPORTED (-3)  /* shape outside what the kernels implement */
+#define GMETA_ERR_LAUNCH (-4)       /* cudaGetLastError() != cudaSuccess after a launch */
+#define GMETA_ERR_WORKSPACE (-5)    /* workspace too small */
+
+#define GMETA_TILE_ROWS 128
+#define GMETA_MAX_LAYERS 3          /* h in {1,2,3}: subgraph_data_processing.py:300-311 */
+
+#define GMETA_IMPL_AUTO 0
+#define GMETA_IMPL_SIMT 1           /* fp32 FFMA, any shape */
+#define GMETA_IMPL_TCGEN05 2        /* tcgen05.mma kind::tf32, 3xTF32 error-compensated */
+
+int gmeta_version(void);
+const char* gmeta_error_string(int code);
+
+/* ---------------------------------------------------------------------------------------
+ * Packed set: adjacency + tiling of all tasks' subgraphs (device pointers).
+ * ------------------------------------------------------------------------------------- */
+typedef struct gmeta_packed_set {
+  int32_t n_nodes;               /* N */
+  int32_t n_edges;               /* E (directed, multi-edges counted) */
+  int32_t n_tiles;
+  int32_t n_tasks;               /* T */
+  int32_t n_subgraphs;           /* S (all tasks) */
+  int32_t centres_per_subgraph;  /* 1, or 2 in link-prediction mode (learner.py:165-168) */
+  const int32_t* indptr;         /* [N+1] CSR by destination: in-neighbours of v */
+  const int32_t* indices;        /* [E]   packed row ids */
+  const int32_t* t_indptr;       /* [N+1] CSR by source: out-neighbours of u (backward) */
+  const int32_t* t_indices;      /* [E] */
+  const int32_t* tile_row0;      /* [n_tiles] first row of the tile */
+  const int32_t* tile_nrows;     /* [n_tiles] 1..GMETA_TILE_ROWS */
+  const int32_t* tile_task;      /* [n_tiles] */
+  const int32_t* task_row_ptr;   /* [T+1] */
+  const int32_t* task_sub_ptr;   /* [T+1] */
+  const int32_t* centre_row;     /* [S * centres_per_subgraph] packed row of the centre node(s) */
+  const int32_t* feat_row;       /* [N] row of the device feature table feeding layer 1, or NULL */
+  const int32_t* labels;         /* [S] raw class labels */
+  float* norm;                   /* [N] clamp(in_deg,1)^-1/2, filled by gmeta_degree_norm */
+  int32_t* class_pos;            /* [S] rank of the label among the task's sorted unique labels */
+  int32_t* class_occ;            /* [S] how many earlier subgraphs of the task share the label */
+  int32_t* n_classes;            /* [T] */
+} gmeta_packed_set_t;
+
+/* Model topology = the reference's `config` list (train.py:67-75, learner.py:81-97) flattened.
+ * Parameters live in ONE flat fp32 buffer in the reference's creation order
+ * [W1 (in,out) | b1 | W2 | b2 | ... | Wlin (n_out, hid*(2 if link_pred)) | blin], each tensor
+ * starting at a multiple of 4 floats (offsets below); per-task copies are strided by
+ * n_params_padded. */
+typedef struct gmeta_model {
+  int32_t n_layers;
+  int32_t f_in[GMETA_MAX_LAYERS];
+  int32_t f_out[GMETA_MAX_LAYERS];
+  int32_t n_out;                 /* logits width (labels_num, train.py:58-61) */
+  int32_t link_pred;
+  int32_t n_params_padded;       /* P */
+  int32_t w_off[GMETA_MAX_LAYERS];
+  int32_t b_off[GMETA_MAX_LAYERS];
+  int32_t wlin_off;
+  int32_t blin_off;
+} gmeta_model_t;
+
+/* norm[v] = 1/sqrt(max(indptr[v+1]-indptr[v], 1)), IEEE-rounded.
+ * Replaces learner.py:29 `torch.pow(graph.in_degrees().float().clamp(min=1), -0.5)`. */
+int gmeta_degree_norm(const int32_t* indptr, int32_t n_nodes, float* norm, void* stream);
+
+/* One fused GCN layer over a packed set (replaces GraphConv.forward, learner.py:25-56, and the
+ * features gather of meta.py:119-120 when in_row_map != NULL):
+ *   M[v,:]   = sum_{u in indices[indptr[v]:indptr[v+1]]} norm[u] * in[map(u), :f_in]
+ *   out[v,j] = act( norm[v] * sum_k M[v,k] * B[k,j] + bias[j] ),   j < f_out
+ * with B[k,j] = W[k*ldw + j] (trans_w == 0) or W[j*ldw + k] (trans_w != 0), W/bias taken from
+ * task t = tile_task[tile] at W + t*w_task_stride / bias + t*b_task_stride (stride 0 = shared),
+ * act = ReLU iff relu != 0; if relu_mask != NULL the result is zeroed where relu_mask[v,j] <= 0
+ * (ld_out layout).  Columns [f_out, round_up(f_out,4)) of out are written as 0.
+ * The same entry point run on (t_indptr, t_indices) with trans_w=1, bias=NULL, relu=0 and
+ * relu_mask = the lower layer's activations is the layer's data-gradient. */
+int gmeta_gcn_layer_fwd(const float* in, int32_t ld_in, const int32_t* in_row_map,
+                        const int32_t* indptr, const int32_t* indices, const float* norm,
+                        const int32_t* tile_row0, const int32_t* tile_nrows,
+                        const int32_t* tile_task, int32_t n_tiles,
+                        const float* W, int64_t w_task_stride, int32_t ldw, int32_t trans_w,
+                        const float* bias, int64_t b_task_stride,
+                        int32_t f_in, int32_t f_out, int32_t relu, const float* relu_mask,
+                        float* out, int32_t ld_out, int32_t impl, void* stream);
+
+/* Weight/bias gradient of one GCN layer (the autograd.grad of meta.py:125,149 for that layer):
+ *   dW[t][k,j] = sum_{v in task t} norm[v] * M[v,k] * dZ[v,j],   db[t][j] = sum_v dZ[v,j]
+ * M as in gmeta_gcn_layer_fwd (re-gathered, not stored).  dZ is the gradient w.r.t. the
+ * pre-activation (already ReLU-masked).  dW / db are written (not accumulated) at
+ * dW + t*dw_task_stride (row-major [f_in, f_out], ld = f_out) and db + t*db_task_stride.
+ * Deterministic: row-range partials in `workspace` are summed in a fixed order. */
+int64_t gmeta_gcn_layer_wgrad_workspace_bytes(int32_t n_tasks, int32_t f_in, int32_t f_out);
+int gmeta_gcn_layer_wgrad(const float* in, int32_t ld_in, const int32_t* in_row_map,
+                          const int32_t* indptr, const int32_t* indices, const float* norm,
+                          const int32_t* task_row_ptr, int32_t n_tasks,
+                          const float* dZ, int32_t ld_dz, int32_t f_in, int32_t f_out,
+                          float* dW, int64_t dw_task_stride, float* db, int64_t db_task_stride,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Centre-row readout + linear head (learner.py:159-175):
+ *   r_s = H[centre_row[s]]   (link_pred: H[centre_row[2s]] || H[centre_row[2s+1]])
+ *   logits[s,c] = sum_k r_s[k] * Wlin[t][c,k] + blin[t][c],  t = task of subgraph s. */
+int gmeta_readout_linear_fwd(const float* H, int32_t ld_h, int32_t hid,
+                             const int32_t* centre_row, int32_t centres_per_subgraph,
+                             const int32_t* task_sub_ptr, int32_t n_tasks, int32_t n_subgraphs,
+                             const float* Wlin, int64_t w_task_stride,
+                             const float* blin, int64_t b_task_stride, int32_t n_out,
+                             float* logits, void* stream);
+
+/* Backward of the above plus the ReLU mask of the last GCN layer:
+ *   dWlin[t][c,k] = sum_s dlogits[s,c] r_s[k];  dblin[t][c] = sum_s dlogits[s,c];
+ *   dZ[N, ld_h] = 0 everywhere except dZ[centre rows] += (H > 0) ? dlogits[s,:] . Wlin[t][:,k] : 0. */
+int gmeta_readout_linear_bwd(const float* H, int32_t ld_h, int32_t hid, int32_t n_nodes,
+                             const int32_t* centre_row, int32_t centres_per_subgraph,
+                             const int32_t* task_sub_ptr, int32_t n_tasks, int32_t n_subgraphs,
+                             const float* Wlin, int64_t w_task_stride, int32_t n_out,
+                             const float* dlogits,
+                             float* dWlin, int64_t dw_task_stride,
+                             float* dblin, int64_t db_task_stride,
+                             float* dZ, void* stream);
+
+/* class_pos / class_occ / n_classes from raw labels, per task (the `torch.unique` +
+ * `eq(c).nonzero()` bookkeeping of meta.py:32-42,60-66), on device. */
+int gmeta_proto_label_prep(const int32_t* labels, const int32_t* task_sub_ptr, int32_t n_tasks,
+                           int32_t* class_pos, int32_t* class_occ, int32_t* n_classes,
+                           void* stream);
+
+/* proto_loss_spt (meta.py:28-54) for every task at once, forward + backward:
+ *   protos[t][c,:] = mean of the first n_support logits of class c; loss/acc over those rows;
+ *   dlogits = grad_scale * dloss/dlogits (including the path through the prototypes).
+ * protos is [T, max_classes, n_out]; loss, acc are [T] written at stride out_stride;
+ * max_rows_per_task = the largest number of subgraphs any one task has (sizes shared memory). */
+int gmeta_proto_loss_spt(const float* logits, int32_t n_out, const int32_t* task_sub_ptr,
+                         int32_t n_tasks, const int32_t* class_pos, const int32_t* class_occ,
+                         const int32_t* n_classes, int32_t n_support, int32_t max_classes,
+                         int32_t max_rows_per_task, float grad_scale, float* protos, float* loss,
+                         float* acc, int32_t out_stride, float* dlogits, void* stream);
+
+/* proto_loss_qry (meta.py:56-79): loss/acc of query logits against given prototypes
+ * (n_classes[t] = number of prototypes of task t, i.e. the SUPPORT set's class count);
+ * dlogits and dprotos (both optional, may be NULL) are grad_scale * dloss/d(.). */
+int gmeta_proto_loss_qry(const float* logits, int32_t n_out, const int32_t* task_sub_ptr,
+                         int32_t n_tasks, const int32_t* class_pos, const int32_t* n_classes,
+                         const float* protos, int32_t max_classes, int32_t max_rows_per_task,
+                         float grad_scale, float* loss, float* acc, int32_t out_stride,
+                         float* dlogits, float* dprotos, void* stream);
+
+/* Gradient reaching the SUPPORT logits through the prototypes used by the final query loss
+ * (meta.py:54 returns them un-detached):
+ *   dlogits_spt[s,:] = class_occ[s] < n_support ? dprotos[t][class_pos[s],:] / n_support : 0. */
+int gmeta_proto_grad_to_support(const float* dprotos, int32_t n_out, int32_t max_classes,
+                                const int32_t* task_sub_ptr, int32_t n_tasks,
+                                const int32_t* class_pos, const int32_t* class_occ,
+                                int32_t n_support, int32_t n_subgraphs, float* dlogits_spt,
+                                void* stream);
+
+/* fast[t][p] = w_in[t*w_in_task_stride + p] - lr * grad[t][p]   (meta.py:126,151). */
+int gmeta_sgd_update(const float* w_in, int64_t w_in_task_stride, const float* grad,
+                     float lr, int32_t n_tasks, int32_t n_params, float* w_out, void* stream);
+
+/* out[p] = sum_t a[t][p] (+ sum_t b[t][p] if b != NULL), tasks summed in index order. */
+int gmeta_sum_over_tasks(const float* a, const float* b, int32_t n_tasks, int32_t n_params,
+                         float* out, void* stream);
+
+/* torch.optim.Adam step (meta.py:97,169; betas/eps/lr given, no weight decay, no amsgrad) on
+ * the flat parameter buffer.  `step` is the 1-based step count AFTER this update.  If
+ * loss_gate != NULL and *loss_gate is NaN the update is skipped entirely (meta.py:163-164);
+ * *skipped (optional) is set to 1/0 accordingly.  grad is multiplied by grad_scale first. */
+int gmeta_adam_update(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                      int32_t n_params, double lr, double beta1, double beta2, double eps,
+                      int32_t step, float grad_scale, const float* loss_gate, int32_t* skipped,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Whole first-order ProtoMAML inner loop for every task of a packed meta-batch, enqueued
+ * from C++ in one call (replaces the body of Meta.forward_ProtoMAML, meta.py:118-161, and of
+ * finetunning_ProtoMAML, meta.py:193-230, minus the optimizer step).
+ * ------------------------------------------------------------------------------------- */
+typedef struct gmeta_step_args {
+  gmeta_model_t model;
+  gmeta_packed_set_t spt;
+  gmeta_packed_set_t qry;
+  const float* feat_table;       /* [rows, ld_feat] device-resident features of all graphs */
+  int32_t ld_feat;
+  const float* theta;            /* [P] meta-parameters */
+  int32_t update_step;           /* K >= 1 (training needs K >= 2, as in the reference) */
+  int32_t n_support;             /* k_spt */
+  int32_t max_classes;
+  int32_t spt_max_rows_per_task; /* most subgraphs any one task has in spt / qry (0 = use S) */
+  int32_t qry_max_rows_per_task;
+  float update_lr;
+  float grad_scale;              /* 1 / global task_num (meta.py:161) */
+  int32_t compute_meta_grad;     /* 1: training step; 0: finetunning (no backward of the query loss) */
+  int32_t impl;                  /* GMETA_IMPL_* for the GCN layers */
+  /* outputs */
+  float* meta_grad;              /* [P] sum over this call's tasks of d(grad_scale*loss_q^K)/d(theta) */
+  float* loss_q;                 /* [T, K+1] query loss per task per step */
+  float* acc_q;                  /* [T, K+1] query accuracy per task per step */
+  float* loss_s;                 /* [T, K]   support loss per task per step */
+  float* logits_spt0;            /* optional [S_spt, n_out]: support logits of step 0 (debug/parity) */
+  void* workspace;
+  int64_t workspace_bytes;
+} gmeta_step_args_t;
+
+int64_t gmeta_maml_step_workspace_bytes(const gmeta_step_args_t* args);
+int gmeta_maml_step(const gmeta_step_args_t* args, void* stream);
+/* number of kernel launches the last gmeta_maml_step call on this thread enqueued */
+int gmeta_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMETA_B200_H_ */

@@ -1,0 +1,90 @@
+"""Helpers for the -m gpu parity tests: call the C ABI with torch device tensors."""
+import numpy as np
+import torch
+
+from gmeta_b200 import _lib
+from gmeta_b200.learner import tile_table
+from gmeta_b200.packed import csr_transpose
+
+
+def dev():
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def i32(a):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(dev())
+
+
+def f32(a):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(dev())
+
+
+def p(t):
+    return None if t is None else t.data_ptr()
+
+
+class DevGraph(object):
+    """CSR (by destination) + transpose + tile table on the device for T tasks."""
+
+    def __init__(self, src, dst, n, task_row_ptr=None):
+        src, dst = np.asarray(src, dtype=np.int64), np.asarray(dst, dtype=np.int64)
+        order = np.argsort(dst, kind="stable")
+        indptr = np.zeros(n + 1, dtype=np.int32)
+        np.cumsum(np.bincount(dst, minlength=n), out=indptr[1:])
+        indices = src[order].astype(np.int32)
+        t_indptr, t_indices = csr_transpose(indptr, indices, n)
+        if task_row_ptr is None:
+            task_row_ptr = np.array([0, n])
+        self.task_row_ptr_h = np.asarray(task_row_ptr, dtype=np.int64)
+        row0, nrows, task = tile_table(self.task_row_ptr_h)
+        self.n, self.T, self.n_tiles = n, len(task_row_ptr) - 1, len(row0)
+        self.indptr, self.indices, self.t_indptr, self.t_indices = i32(indptr), i32(indices), i32(t_indptr), i32(t_indices)
+        self.tile_row0, self.tile_nrows, self.tile_task = i32(row0), i32(nrows), i32(task)
+        self.task_row_ptr = i32(task_row_ptr)
+        self.norm = torch.empty(n, dtype=torch.float32, device=dev())
+        _lib.check(_lib.lib().gmeta_degree_norm(p(self.indptr), n, p(self.norm), stream()))
+
+
+def layer_fwd(g, x, W, b, f_in, f_out, relu=1, transposed=False, trans_w=0, mask=None, row_map=None,
+              w_stride=0, b_stride=0, ldw=None, impl=_lib.IMPL_SIMT, ld_out=None):
+    ld_out = ld_out or (f_out + 3) // 4 * 4
+    out = torch.full((g.n, ld_out), float('nan'), dtype=torch.float32, device=dev())
+    ip, ix = (g.t_indptr, g.t_indices) if transposed else (g.indptr, g.indices)
+    if ldw is None:
+        ldw = f_in if trans_w else f_out
+    rc = _lib.lib().gmeta_gcn_layer_fwd(p(x), x.shape[1], p(row_map), p(ip), p(ix), p(g.norm), p(g.tile_row0),
+                                        p(g.tile_nrows), p(g.tile_task), g.n_tiles, p(W), w_stride, ldw, trans_w,
+                                        p(b), b_stride, f_in, f_out, relu, p(mask), p(out), ld_out, impl, stream())
+    _lib.check(rc, "gcn_layer_fwd")
+    return out
+
+
+def layer_wgrad(g, x, dz, f_in, f_out, row_map=None):
+    L = _lib.lib()
+    T = g.T
+    dW = torch.full((T, f_in, f_out), float('nan'), dtype=torch.float32, device=dev())
+    db = torch.full((T, f_out), float('nan'), dtype=torch.float32, device=dev())
+    nbytes = L.gmeta_gcn_layer_wgrad_workspace_bytes(T, f_in, f_out)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev())
+    rc = L.gmeta_gcn_layer_wgrad(p(x), x.shape[1], p(row_map), p(g.indptr), p(g.indices), p(g.norm),
+                                 p(g.task_row_ptr), T, p(dz), dz.shape[1], f_in, f_out, p(dW), f_in * f_out, p(db),
+                                 f_out, p(ws), nbytes, stream())
+    _lib.check(rc, "gcn_layer_wgrad")
+    return dW, db
+
+
+def report(name, got, want, atol, rtol=0.0):
+    got = got.detach().cpu().numpy() if hasattr(got, "detach") else np.asarray(got)
+    want = want.detach().cpu().numpy() if hasattr(want, "detach") else np.asarray(want)
+    err = np.abs(got.astype(np.float64) - want.astype(np.float64))
+    lim = atol + rtol * np.abs(want)
+    bad = ~(err <= lim)
+    msg = "%s: max|err|=%.3e (ref max %.3e), %d/%d outside atol=%g rtol=%g" % (
+        name, float(np.nanmax(err)) if err.size else 0.0, float(np.abs(want).max()) if want.size else 0.0,
+        int(bad.sum()), err.size, atol, rtol)
+    print(msg)
+    assert not bad.any(), msg

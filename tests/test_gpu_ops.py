@@ -1,0 +1,367 @@
+"""GPU parity of every C-ABI op against the oracle and the reference-generated golden fixtures.
+
+Tolerances (fp32): north_star asks logits within 1e-4 of the reference's fp32 CPU path; the
+per-op bounds here are tighter (FFMA path: 2e-5 abs + 1e-5 rel; 3xTF32 path: 5e-5 abs + 2e-5 rel)
+so that a 2-3 layer stack plus K inner steps stays inside 1e-4.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gmeta_b200 import _lib
+from oracle import gmeta_oracle as O
+from tests import gpu_util as U
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+IMPLS = [_lib.IMPL_SIMT, _lib.IMPL_TCGEN05]
+TOL = {_lib.IMPL_SIMT: (2e-5, 1e-5), _lib.IMPL_TCGEN05: (5e-5, 2e-5)}
+
+
+def _fwd_or_skip(impl, *a, **k):
+    try:
+        return U.layer_fwd(*a, impl=impl, **k)
+    except _lib.GMetaError as e:
+        if impl == _lib.IMPL_TCGEN05 and "not supported" in str(e):
+            pytest.skip("shape not covered by the tcgen05 path (FFMA path covers it)")
+        raise
+
+
+def test_library_loaded_and_version():
+    assert _lib.lib().gmeta_version() >= 100
+    assert os.path.isfile(_lib.LIB_PATH)
+
+
+def test_degree_norm_bit_exact():
+    rng = np.random.default_rng(0)
+    n = 5000
+    dst = np.concatenate([rng.integers(0, n - 50, 20000), np.zeros(3000, dtype=np.int64)])  # hub + isolated tail
+    g = U.DevGraph(rng.integers(0, n, dst.shape[0]), dst, n)
+    deg = torch.bincount(torch.as_tensor(dst), minlength=n)
+    want = torch.pow(deg.float().clamp(min=1), -0.5)            # learner.py:29
+    assert torch.equal(g.norm.cpu(), want)
+
+
+def test_known_answer_vectors():
+    k = np.load(os.path.join(GOLD, "kat.npz"))
+    g = U.DevGraph([0, 1, 1, 2], [1, 0, 2, 1], 3)
+    b = U.f32([0.5, -0.5])
+    y = U.layer_fwd(g, U.f32([[1., 0.], [0., 1.], [1., 1.]]), U.f32([[1., 2.], [3., 4.]]), b, 2, 2)
+    U.report("D1", y[:, :2], k['d1'], 1e-6)
+    y = U.layer_fwd(g, U.f32([[1., 0., 2.], [0., 1., -1.], [1., 1., 0.]]), U.f32([[1., 2.], [3., 4.], [-1., 0.5]]), b, 3, 2)
+    U.report("D1b", y[:, :2], k['d1b'], 1e-6)
+    from gmeta_b200.meta import proto_loss_qry, proto_loss_spt
+    z = U.f32([[0., 0.], [2., 0.], [0., 2.], [0., 4.]]).requires_grad_(True)
+    loss, acc, protos = proto_loss_spt(z, torch.LongTensor([0, 0, 1, 1]), 2)
+    U.report("D2 loss", loss, k['d2_loss'], 1e-8, 1e-5)
+    assert float(acc) == 1.0
+    U.report("D2 protos", protos, k['d2_protos'], 1e-7)
+    U.report("D2 dlogits", torch.autograd.grad(loss, z)[0], k['d2_dlogits'], 1e-8, 1e-5)
+    lq, aq = proto_loss_qry(U.f32([[1., 1.], [0., 3.], [3., 0.], [1., 2.]]), torch.LongTensor([0, 1, 0, 1]), protos.detach())
+    U.report("D2 qry loss", lq, k['d2q_loss'], 1e-8, 1e-5)
+    assert float(aq) == 1.0
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_layer_forward_and_gradients_vs_reference_golden(impl):
+    """GraphConv.forward and its autograd gradients as produced by the unmodified reference."""
+    d = np.load(os.path.join(GOLD, "layer_cases.npz"))
+    atol, rtol = TOL[impl]
+    ran = 0
+    for k in range(int(d['n_cases'])):
+        q = 'c%d_' % k
+        n = int(d[q + 'n'])
+        g = U.DevGraph(d[q + 'src'], d[q + 'dst'], n)
+        x, w, b = U.f32(d[q + 'x']), U.f32(d[q + 'w']), U.f32(d[q + 'b'])
+        fi, fo = w.shape
+        try:
+            y = U.layer_fwd(g, x, w, b, fi, fo, impl=impl)
+        except _lib.GMetaError:
+            if impl == _lib.IMPL_TCGEN05:
+                continue
+            raise
+        ran += 1
+        U.report("case %d fwd [%d->%d]" % (k, fi, fo), y[:, :fo], d[q + 'y'], atol, rtol)
+        assert torch.all(y[:, fo:] == 0)
+        # backward: dZ = gy * (y > 0); dW, db; dX = data gradient through the transposed graph
+        dz = torch.zeros_like(y)
+        dz[:, :fo] = U.f32(d[q + 'gy']) * (y[:, :fo] > 0)
+        dW, db = U.layer_wgrad(g, x, dz, fi, fo)
+        U.report("case %d dW" % k, dW[0], d[q + 'dw'], 5 * atol, 5 * rtol)
+        U.report("case %d db" % k, db[0], d[q + 'db'], 5 * atol, 5 * rtol)
+        try:
+            dx = U.layer_fwd(g, dz, w, None, fo, fi, relu=0, transposed=True, trans_w=1, impl=impl)
+        except _lib.GMetaError:
+            if impl == _lib.IMPL_TCGEN05:
+                continue
+            raise
+        U.report("case %d dX" % k, dx[:, :fi], d[q + 'dx'], 5 * atol, 5 * rtol)
+    if ran == 0:
+        pytest.skip("no golden case has a shape the tcgen05 path covers")
+
+
+def _random_multitask(rng, T, n_per_task, deg, f_in, f_out, hub=True, table_rows=None):
+    """T tasks packed back to back (ragged sizes), edges only inside a task, optional hubs,
+    isolated nodes and multi-edges; separate weights per task."""
+    sizes = rng.integers(n_per_task // 2, n_per_task + 1, size=T)
+    trp = np.concatenate([[0], np.cumsum(sizes)])
+    src, dst = [], []
+    for t in range(T):
+        e = int(sizes[t] * deg)
+        s = rng.integers(0, sizes[t], e)
+        dd = rng.integers(0, max(1, sizes[t] - 2), e)
+        if hub and sizes[t] > 70:
+            dd[:70] = 0                        # one node with in-degree > 64 (multi-batch gather path)
+            s[1:5] = s[0]                      # multi-edges into the hub
+        src.append(s + trp[t])
+        dst.append(dd + trp[t])
+    src, dst = np.concatenate(src), np.concatenate(dst)
+    N = int(trp[-1])
+    g = U.DevGraph(src, dst, N, trp)
+    W = rng.standard_normal((T, f_in, f_out), dtype=np.float32) / np.sqrt(f_in)
+    b = rng.standard_normal((T, f_out), dtype=np.float32) * 0.1
+    if table_rows:
+        table = rng.standard_normal((table_rows, f_in), dtype=np.float32)
+        row_map = rng.integers(0, table_rows, N)
+        x = table[row_map]
+    else:
+        table, row_map = None, None
+        x = rng.standard_normal((N, f_in), dtype=np.float32)
+    return g, src, dst, trp, x, W, b, table, row_map
+
+
+def _oracle_multitask(src, dst, trp, x, W, b, relu=True):
+    N = int(trp[-1])
+    og = O.OGraph(src, dst, N)
+    out = torch.empty(N, W.shape[2])
+    norm = torch.pow(og.in_degrees().float().clamp(min=1), -0.5).unsqueeze(1)
+    M = og.aggregate_sum(torch.tensor(x) * norm)
+    for t in range(len(trp) - 1):
+        a, e = int(trp[t]), int(trp[t + 1])
+        z = (M[a:e] @ torch.tensor(W[t])) * norm[a:e] + torch.tensor(b[t])
+        out[a:e] = torch.relu(z) if relu else z
+    return out, M, norm
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("shape", [(128, 256), (256, 256), (128, 64), (50, 128), (5, 128), (1, 256), (512, 128),
+                                   (256, 3), (20, 20)])
+def test_layer_forward_multitask_per_task_weights(impl, shape):
+    f_in, f_out = shape
+    rng = np.random.default_rng(100 + f_in + f_out)
+    T = 5
+    g, src, dst, trp, x, W, b, table, row_map = _random_multitask(rng, T, 700, 2.5, f_in, f_out, table_rows=3000)
+    ld = (f_in + 3) // 4 * 4
+    tab = np.zeros((table.shape[0], ld), dtype=np.float32)
+    tab[:, :f_in] = table
+    y = _fwd_or_skip(impl, g, U.f32(tab), U.f32(W), U.f32(b), f_in, f_out, row_map=U.i32(row_map),
+                     w_stride=f_in * f_out, b_stride=f_out)
+    want, _, _ = _oracle_multitask(src, dst, trp, x, W, b)
+    atol, rtol = TOL[impl]
+    U.report("fwd T=%d [%d->%d]" % (T, f_in, f_out), y[:, :f_out], want, atol, rtol)
+    assert torch.all(y[:, f_out:] == 0)
+    assert not torch.isnan(y).any()
+
+
+@pytest.mark.parametrize("shape", [(128, 256), (256, 256), (50, 128), (5, 16), (300, 130)])
+def test_layer_wgrad_and_dgrad_multitask(shape):
+    f_in, f_out = shape
+    rng = np.random.default_rng(7 + f_in)
+    T = 4
+    g, src, dst, trp, x, W, b, _, _ = _random_multitask(rng, T, 900, 2.0, f_in, f_out)
+    N = int(trp[-1])
+    xt = torch.tensor(x, requires_grad=True)
+    Wt = [torch.tensor(W[t], requires_grad=True) for t in range(T)]
+    bt = [torch.tensor(b[t], requires_grad=True) for t in range(T)]
+    og = O.OGraph(src, dst, N)
+    norm = torch.pow(og.in_degrees().float().clamp(min=1), -0.5).unsqueeze(1)
+    M = og.aggregate_sum(xt * norm)
+    z = torch.cat([(M[int(trp[t]):int(trp[t + 1])] @ Wt[t]) * norm[int(trp[t]):int(trp[t + 1])] + bt[t] for t in range(T)])
+    y = torch.relu(z)
+    gy = torch.tensor(rng.standard_normal((N, f_out), dtype=np.float32))
+    grads = torch.autograd.grad(y, [xt] + Wt + bt, gy)
+    dz = (gy * (y > 0)).detach()
+    ldz = (f_out + 3) // 4 * 4
+    dzp = torch.zeros(N, ldz)
+    dzp[:, :f_out] = dz
+    ldx = (f_in + 3) // 4 * 4
+    xp = torch.zeros(N, ldx)
+    xp[:, :f_in] = torch.tensor(x)
+    dW, db = U.layer_wgrad(g, xp.to(U.dev()), dzp.to(U.dev()), f_in, f_out)
+    for t in range(T):
+        U.report("dW[%d] [%d->%d]" % (t, f_in, f_out), dW[t], grads[1 + t], 1e-4, 1e-4)
+        U.report("db[%d]" % t, db[t], grads[1 + T + t], 1e-4, 1e-4)
+    dx = U.layer_fwd(g, dzp.to(U.dev()), U.f32(W), None, f_out, f_in, relu=0, transposed=True, trans_w=1,
+                     w_stride=f_in * f_out, ldw=f_out)
+    U.report("dX [%d->%d]" % (f_in, f_out), dx[:, :f_in], grads[0], 1e-4, 1e-4)
+    # the ReLU mask of the layer below is applied by the same kernel
+    mask = torch.tensor(rng.standard_normal((N, ldx), dtype=np.float32)).to(U.dev())
+    dxm = U.layer_fwd(g, dzp.to(U.dev()), U.f32(W), None, f_out, f_in, relu=0, transposed=True, trans_w=1,
+                      w_stride=f_in * f_out, ldw=f_out, mask=mask)
+    U.report("dX masked", dxm[:, :f_in], grads[0] * (mask[:, :f_in].cpu() > 0), 1e-4, 1e-4)
+
+
+@pytest.mark.parametrize("cps", [1, 2])
+def test_readout_linear_forward_backward(cps):
+    L = _lib.lib()
+    rng = np.random.default_rng(5)
+    T, hid, C, N = 3, 36, 5, 400
+    S_t = [7, 4, 9]
+    tsp = np.concatenate([[0], np.cumsum(S_t)])
+    S = int(tsp[-1])
+    H = rng.standard_normal((N, hid), dtype=np.float32)
+    centre = rng.integers(0, N, S * cps)
+    if cps == 2:
+        centre[1] = centre[0]                     # both endpoints naming one row
+    Wl = rng.standard_normal((T, C, hid * cps), dtype=np.float32)
+    bl = rng.standard_normal((T, C), dtype=np.float32)
+    Ht = torch.tensor(H, requires_grad=True)
+    Wt = torch.tensor(Wl, requires_grad=True)
+    bt = torch.tensor(bl, requires_grad=True)
+    Hr = torch.relu(Ht)
+    r = Hr[torch.as_tensor(centre)].reshape(S, cps * hid)
+    task = np.repeat(np.arange(T), S_t)
+    want = torch.stack([r[s] @ Wt[task[s]].T + bt[task[s]] for s in range(S)])
+    dl = torch.tensor(rng.standard_normal((S, C), dtype=np.float32))
+    gH, gW, gb = torch.autograd.grad(want, (Ht, Wt, bt), dl)
+
+    Hd = torch.relu(U.f32(H))
+    logits = torch.empty(S, C, device=U.dev())
+    _lib.check(L.gmeta_readout_linear_fwd(U.p(Hd), hid, hid, U.p(U.i32(centre)), cps, U.p(U.i32(tsp)), T, S,
+                                          U.p(U.f32(Wl)), C * hid * cps, U.p(U.f32(bl)), C, C, U.p(logits), U.stream()))
+    U.report("readout logits", logits, want, 1e-5, 1e-5)
+    dW = torch.empty(T, C, hid * cps, device=U.dev())
+    db = torch.empty(T, C, device=U.dev())
+    dZ = torch.full((N, hid), float('nan'), device=U.dev())
+    _lib.check(L.gmeta_readout_linear_bwd(U.p(Hd), hid, hid, N, U.p(U.i32(centre)), cps, U.p(U.i32(tsp)), T, S,
+                                          U.p(U.f32(Wl)), C * hid * cps, C, U.p(U.f32(dl.numpy())), U.p(dW),
+                                          C * hid * cps, U.p(db), C, U.p(dZ), U.stream()))
+    U.report("readout dWlin", dW, gW, 1e-5, 1e-5)
+    U.report("readout dblin", db, gb, 1e-5, 1e-5)
+    U.report("readout dZ (masked, scattered)", dZ, gH, 1e-5, 1e-5)
+
+
+def test_proto_losses_vs_reference_golden():
+    from gmeta_b200.meta import proto_loss_qry, proto_loss_spt
+    d = np.load(os.path.join(GOLD, "loss_cases.npz"))
+    for k in range(int(d['n_cases'])):
+        q = 'c%d_' % k
+        zs = U.f32(d[q + 'zs']).requires_grad_(True)
+        zq = U.f32(d[q + 'zq']).requires_grad_(True)
+        ls, accs, protos = proto_loss_spt(zs, torch.LongTensor(d[q + 'ys']), int(d[q + 'ks']))
+        U.report("case %d loss_s" % k, ls, d[q + 'loss_s'], 1e-6, 1e-5)
+        assert abs(float(accs) - float(d[q + 'acc_s'])) < 1e-6
+        U.report("case %d protos" % k, protos, d[q + 'protos'], 1e-6, 1e-6)
+        U.report("case %d dzs" % k, torch.autograd.grad(ls, zs, retain_graph=True)[0], d[q + 'dzs'], 1e-6, 1e-4)
+        lq, accq = proto_loss_qry(zq, torch.LongTensor(d[q + 'yq']), protos)
+        U.report("case %d loss_q" % k, lq, d[q + 'loss_q'], 1e-6, 1e-5)
+        assert abs(float(accq) - float(d[q + 'acc_q'])) < 1e-6
+        dzq, dzs2 = torch.autograd.grad(lq, (zq, zs))
+        U.report("case %d dzq" % k, dzq, d[q + 'dzq'], 1e-6, 1e-4)
+        U.report("case %d dzs via prototypes" % k, dzs2, d[q + 'dzs_via_protos'], 1e-6, 1e-4)
+
+
+def test_proto_losses_batched_over_tasks():
+    """All tasks in one launch (different label sets / class counts per task) == oracle per task."""
+    L = _lib.lib()
+    rng = np.random.default_rng(9)
+    T, D, ks, kq, MC = 4, 6, 3, 5, 5
+    ncls = [3, 5, 2, 4]
+    ys, yq, zs, zq = [], [], [], []
+    for t in range(T):
+        labels = rng.choice(100, ncls[t], replace=False)
+        ys.append(rng.permutation(np.repeat(labels, ks + (1 if t == 1 else 0))))   # task 1: one extra per class
+        yq.append(rng.permutation(np.repeat(labels, kq)))
+        zs.append(rng.standard_normal((len(ys[-1]), D), dtype=np.float32))
+        zq.append(rng.standard_normal((len(yq[-1]), D), dtype=np.float32))
+    sp = np.concatenate([[0], np.cumsum([len(y) for y in ys])])
+    qp = np.concatenate([[0], np.cumsum([len(y) for y in yq])])
+    Ss, Sq = int(sp[-1]), int(qp[-1])
+    dv = U.dev()
+    lab_s, lab_q, sp_d, qp_d = U.i32(np.concatenate(ys)), U.i32(np.concatenate(yq)), U.i32(sp), U.i32(qp)
+    cps, cos, ncs = (torch.empty(Ss, dtype=torch.int32, device=dv), torch.empty(Ss, dtype=torch.int32, device=dv),
+                     torch.empty(T, dtype=torch.int32, device=dv))
+    cpq, coq, ncq = (torch.empty(Sq, dtype=torch.int32, device=dv), torch.empty(Sq, dtype=torch.int32, device=dv),
+                     torch.empty(T, dtype=torch.int32, device=dv))
+    _lib.check(L.gmeta_proto_label_prep(U.p(lab_s), U.p(sp_d), T, U.p(cps), U.p(cos), U.p(ncs), U.stream()))
+    _lib.check(L.gmeta_proto_label_prep(U.p(lab_q), U.p(qp_d), T, U.p(cpq), U.p(coq), U.p(ncq), U.stream()))
+    assert ncs.cpu().tolist() == ncls and ncq.cpu().tolist() == ncls
+    zs_d, zq_d = U.f32(np.concatenate(zs)), U.f32(np.concatenate(zq))
+    protos = torch.zeros(T, MC, D, device=dv)
+    loss_s, acc_s = torch.empty(T, device=dv), torch.empty(T, device=dv)
+    dzs = torch.empty(Ss, D, device=dv)
+    _lib.check(L.gmeta_proto_loss_spt(U.p(zs_d), D, U.p(sp_d), T, U.p(cps), U.p(cos), U.p(ncs), ks, MC,
+                                      max(len(y) for y in ys), 1.0, U.p(protos), U.p(loss_s), U.p(acc_s), 1,
+                                      U.p(dzs), U.stream()))
+    loss_q, acc_q = torch.empty(T, 2, device=dv), torch.empty(T, 2, device=dv)
+    dzq, dpr = torch.empty(Sq, D, device=dv), torch.zeros(T, MC, D, device=dv)
+    scale = 0.25
+    _lib.check(L.gmeta_proto_loss_qry(U.p(zq_d), D, U.p(qp_d), T, U.p(cpq), U.p(ncs), U.p(protos), MC,
+                                      max(len(y) for y in yq), scale, loss_q.data_ptr() + 4, acc_q.data_ptr() + 4, 2,
+                                      U.p(dzq), U.p(dpr), U.stream()))
+    dzs2 = torch.empty(Ss, D, device=dv)
+    _lib.check(L.gmeta_proto_grad_to_support(U.p(dpr), D, MC, U.p(sp_d), T, U.p(cps), U.p(cos), ks, Ss, U.p(dzs2),
+                                             U.stream()))
+    for t in range(T):
+        a = torch.tensor(zs[t], requires_grad=True)
+        bq = torch.tensor(zq[t], requires_grad=True)
+        ls, accs, pr = O.proto_loss_spt(a, torch.LongTensor(ys[t]), ks)
+        U.report("task %d loss_s" % t, loss_s[t], ls.detach(), 1e-6, 1e-5)
+        assert abs(float(acc_s[t]) - float(accs)) < 1e-6
+        U.report("task %d protos" % t, protos[t, :ncls[t]], pr.detach(), 1e-6, 1e-6)
+        U.report("task %d dzs" % t, dzs[sp[t]:sp[t + 1]], torch.autograd.grad(ls, a, retain_graph=True)[0], 1e-6, 1e-4)
+        lq, accq = O.proto_loss_qry(bq, torch.LongTensor(yq[t]), pr)
+        U.report("task %d loss_q" % t, loss_q[t, 1], lq.detach(), 1e-6, 1e-5)
+        assert abs(float(acc_q[t, 1]) - float(accq)) < 1e-6
+        gq, gs = torch.autograd.grad(lq * scale, (bq, a))
+        U.report("task %d dzq" % t, dzq[qp[t]:qp[t + 1]], gq, 1e-6, 1e-4)
+        U.report("task %d dzs via prototypes" % t, dzs2[sp[t]:sp[t + 1]], gs, 1e-6, 1e-4)
+
+
+def test_sgd_and_adam_match_torch():
+    L = _lib.lib()
+    rng = np.random.default_rng(2)
+    T, P = 3, 1000
+    theta = rng.standard_normal(P, dtype=np.float32)
+    g = rng.standard_normal((T, P), dtype=np.float32)
+    out = torch.empty(T, P, device=U.dev())
+    _lib.check(L.gmeta_sgd_update(U.p(U.f32(theta)), 0, U.p(U.f32(g)), 0.01, T, P, U.p(out), U.stream()))
+    want = torch.tensor(theta)[None] - 0.01 * torch.tensor(g)               # meta.py:126
+    assert torch.equal(out.cpu(), want)
+    out2 = torch.empty(T, P, device=U.dev())
+    _lib.check(L.gmeta_sgd_update(U.p(out), P, U.p(U.f32(g)), 0.01, T, P, U.p(out2), U.stream()))
+    assert torch.equal(out2.cpu(), want - 0.01 * torch.tensor(g))
+    s = torch.empty(P, device=U.dev())
+    _lib.check(L.gmeta_sum_over_tasks(U.p(U.f32(g)), U.p(U.f32(2 * g)), T, P, U.p(s), U.stream()))
+    U.report("sum over tasks", s, torch.tensor(3 * g).sum(0), 1e-5, 1e-5)
+
+    p_ref = torch.tensor(theta.copy(), requires_grad=True)
+    opt = torch.optim.Adam([p_ref], lr=1e-3)                               # meta.py:97
+    p_dev, m, v = U.f32(theta), torch.zeros(P, device=U.dev()), torch.zeros(P, device=U.dev())
+    skipped = torch.zeros(1, dtype=torch.int32, device=U.dev())
+    gate = U.f32([0.5])
+    for step in range(1, 6):
+        gr = rng.standard_normal(P, dtype=np.float32) * (10.0 ** rng.integers(-4, 1))
+        p_ref.grad = torch.tensor(gr)
+        opt.step()
+        _lib.check(L.gmeta_adam_update(U.p(p_dev), U.p(U.f32(gr)), U.p(m), U.p(v), P, 1e-3, 0.9, 0.999, 1e-8, step,
+                                       1.0, U.p(gate), U.p(skipped), U.stream()))
+        assert int(skipped) == 0
+        U.report("adam step %d" % step, p_dev, p_ref.detach(), 1e-7, 1e-6)
+    before = p_dev.clone()
+    _lib.check(L.gmeta_adam_update(U.p(p_dev), U.p(U.f32(gr)), U.p(m), U.p(v), P, 1e-3, 0.9, 0.999, 1e-8, 6, 1.0,
+                                   U.p(U.f32([float('nan')])), U.p(skipped), U.stream()))
+    assert int(skipped) == 1 and torch.equal(before, p_dev)                # NaN loss: no update (meta.py:163-164)
+
+
+def test_bad_arguments_return_error_codes():
+    L = _lib.lib()
+    assert L.gmeta_degree_norm(None, 5, None, None) == -1
+    assert L.gmeta_sgd_update(None, 0, None, 0.1, 1, 1, None, None) == -1
+    assert L.gmeta_gcn_layer_wgrad_workspace_bytes(0, 4, 4) == 0
+    g = U.DevGraph([0], [1], 2)
+    x = U.f32(np.zeros((2, 4)))
+    with pytest.raises(_lib.GMetaError):
+        U.layer_fwd(g, x, U.f32(np.zeros((8, 4))), None, 8, 4)             # ld_in < f_in

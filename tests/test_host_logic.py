@@ -1,0 +1,206 @@
+"""CPU: host-side logic of the product (packing, tiling, extraction, parameter layout, label
+validation) and the C-ABI surface (library loads and exports every symbol the header declares;
+no compute calls -- there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from gmeta_b200 import _lib, packing
+from gmeta_b200.learner import Classifier, ModelSpec, tile_table
+from gmeta_b200.packed import PackedSubgraphBatch, SubgraphCSR, csr_transpose
+from gmeta_b200.subgraphs import ParentGraph, extract_subgraph, extract_subgraph_link_pred
+from oracle import ref_loader
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "gmeta_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(gmeta_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 18
+    h = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(h, name), "libgmeta_b200.so does not export %s" % name
+    assert sorted(_lib.exported_symbols()) == declared       # the ctypes table binds all of them
+    assert _lib.lib().gmeta_version() >= 100
+    assert _lib.lib().gmeta_error_string(-3).decode().startswith("shape")
+
+
+def test_ctypes_structs_match_header_layout():
+    """sizeof of the mirrored structs (pointer/int layout) -- a drifted field would shift these."""
+    assert ctypes.sizeof(_lib.PackedSet) == 6 * 4 + 16 * 8
+    assert ctypes.sizeof(_lib.Model) == 4 * (1 + 3 + 3 + 3 + 3 + 3 + 2)
+    a = _lib.StepArgs()
+    assert ctypes.sizeof(a) % 8 == 0 and _lib.StepArgs.workspace_bytes.offset + 8 == ctypes.sizeof(a)
+
+
+def test_parameter_counts_match_reference_logs():
+    """Trainable-parameter counts printed by the reference (test.ipynb:27,112,211,284,369)."""
+    cases = [
+        ([('GraphConv', [128, 256]), ('GraphConv', [256, 256]), ('Linear', [256, 3])], 99587),
+        ([('GraphConv', [50, 128]), ('GraphConv', [128, 128]), ('Linear', [128, 2])], 23298),
+        ([('GraphConv', [512, 128]), ('GraphConv', [128, 128]), ('Linear', [128, 30])], 85982),
+        ([('GraphConv', [5, 128]), ('GraphConv', [128, 128]), ('Linear', [128, 2]), ('LinkPred', [True])], 17794),
+        ([('GraphConv', [1, 256]), ('GraphConv', [256, 256]), ('Linear', [256, 2]), ('LinkPred', [True])], 67330),
+    ]
+    for cfg, want in cases:
+        net = Classifier(cfg)
+        n = sum(int(np.prod(p.shape)) for p in net.parameters())
+        if want != 85982:
+            assert n == want, (cfg, n)
+        spec = ModelSpec(cfg)
+        assert spec.n_params_padded >= n and all(o % 4 == 0 for o in spec.offsets)
+        flat = spec.flatten(list(net.parameters()))
+        for p, v in zip(net.parameters(), spec.unflatten(flat)):
+            assert torch.equal(p.detach(), v)
+
+
+def test_parameter_init_matches_reference_order_and_rng():
+    if not ref_loader.available():
+        pytest.skip("reference tree not mounted")
+    learner, _, _ = ref_loader.load()
+    cfg = [('GraphConv', [12, 16]), ('GraphConv', [16, 16]), ('Linear', [16, 4]), ('LinkPred', [True])]
+    torch.manual_seed(222)
+    ref = learner.Classifier(cfg)
+    torch.manual_seed(222)
+    ours = Classifier(cfg)
+    for a, b in zip(ref.parameters(), ours.parameters()):
+        assert a.shape == b.shape and torch.equal(a, b)
+
+
+def test_tile_table_never_straddles_tasks():
+    trp = np.array([0, 5, 5, 300, 428, 1000])
+    row0, nrows, task = tile_table(trp)
+    assert nrows.min() >= 1 and nrows.max() <= _lib.TILE_ROWS
+    covered = np.concatenate([np.arange(r, r + n) for r, n in zip(row0, nrows)])
+    assert np.array_equal(covered, np.arange(1000))
+    for r, n, t in zip(row0, nrows, task):
+        assert trp[t] <= r and r + n <= trp[t + 1]
+
+
+def test_csr_transpose_and_batching():
+    rng = np.random.default_rng(0)
+    subs = []
+    for n, e in [(5, 12), (1, 0), (9, 30)]:
+        subs.append(SubgraphCSR.from_edges(rng.integers(0, n, e), rng.integers(0, n, e), n, centre=0))
+    g = PackedSubgraphBatch.batch(subs)
+    assert g.batch_num_nodes == [5, 1, 9] and g.n_nodes == 15 and g.n_edges == 42
+    src, dst = g.edges()
+    dense = np.zeros((15, 15), dtype=np.int64)
+    np.add.at(dense, (dst, src), 1)
+    tp, ti = g.t_indptr, g.t_indices
+    dense_t = np.zeros((15, 15), dtype=np.int64)
+    np.add.at(dense_t, (np.repeat(np.arange(15), np.diff(tp)), ti), 1)
+    assert np.array_equal(dense.T, dense_t)
+    assert (src[dst < 5] < 5).all() and (src[dst >= 6] >= 6).all()      # block diagonal
+    tp2, ti2 = csr_transpose(g.indptr, g.indices, 15)
+    assert np.array_equal(tp, tp2) and np.array_equal(ti, ti2)
+
+
+@pytest.mark.parametrize("kind", H.TINY_KINDS)
+def test_packing_layout(kind):
+    ds = H.tiny_dataset(kind)
+    mb = ds.sample_meta_batch(np.random.default_rng(4))
+    xs, ys, xq, yq, cs, cq, ns, nq, gs, gq = mb
+    ps = packing.plan_set(xq, cq, 0)
+    buf = np.zeros(ps.end, dtype=np.int32)
+    rows = np.array([f.shape[0] for f in ds.feats])
+    goff = np.concatenate([[0], np.cumsum(rows)])[:-1]
+    packing.fill_set(buf, ps, xq, yq, cq, nq, gq, goff)
+    o = ps.off
+    indptr = buf[o["indptr"]:o["indptr"] + ps.N + 1]
+    indices = buf[o["indices"]:o["indices"] + ps.E]
+    assert indptr[0] == 0 and indptr[-1] == ps.E and (np.diff(indptr) >= 0).all()
+    assert all(v % 4 == 0 for v in o.values())
+    table = np.vstack(ds.feats)
+    feat_row = buf[o["feat_row"]:o["feat_row"] + ps.N]
+    centre = buf[o["centre_row"]:o["centre_row"] + ps.S * ps.cps]
+    labels = buf[o["labels"]:o["labels"] + ps.S]
+    trp = buf[o["task_row_ptr"]:o["task_row_ptr"] + ps.T + 1]
+    tsp = buf[o["task_sub_ptr"]:o["task_sub_ptr"] + ps.T + 1]
+    for t in range(ps.T):
+        a, b = trp[t], trp[t + 1]
+        assert b - a == xq[t].n_nodes
+        # features reached through feat_row == the reference's host gather (meta.py:119-120)
+        want = np.vstack([ds.feats[gq[t][j]][np.array(x)] for j, x in enumerate(nq[t])])
+        assert np.array_equal(table[feat_row[a:b]], want)
+        # edges stay inside the task, shifted by its row offset
+        lo, hi = indptr[a], indptr[b]
+        assert np.array_equal(indices[lo:hi], xq[t].indices + a)
+        off = np.concatenate([[0], np.cumsum(xq[t].batch_num_nodes)])[:-1] + a
+        c = cq[t].numpy()
+        want_c = (c + off[:, None]).reshape(-1) if ps.cps == 2 else c + off
+        assert np.array_equal(centre[tsp[t] * ps.cps:tsp[t + 1] * ps.cps], want_c)
+        assert np.array_equal(labels[tsp[t]:tsp[t + 1]], yq[t].numpy())
+    assert ps.cps == (2 if ds.link_pred else 1)
+
+
+def test_label_validation_mirrors_reference_errors():
+    y = torch.LongTensor
+    assert packing.validate_labels([y([0, 0, 1, 1])], [y([0, 1, 1, 0])], 2) == 2
+    with pytest.raises(RuntimeError):
+        packing.validate_labels([y([0, 0, 1])], [y([0, 1])], 2)            # class 1 has < k_spt members
+    with pytest.raises(RuntimeError):
+        packing.validate_labels([y([0, 0, 1, 1])], [y([0, 1, 1])], 2)      # unbalanced query
+
+
+def test_extraction_matches_reference_generate_subgraph():
+    """Same node set / induced edges as Subgraphs.generate_subgraph when the neighbourhood is
+    below the sampling cap (subgraph_data_processing.py:295-321), for h = 1, 2, 3."""
+    if not ref_loader.available():
+        pytest.skip("reference tree not mounted")
+    _, _, sdp = ref_loader.load()
+    dgl = ref_loader.shim_dgl()
+    rng = np.random.default_rng(8)
+    n, e = 300, 900
+    src, dst = rng.integers(0, n, e), rng.integers(0, n, e)
+    G = ParentGraph.from_edges(src, dst, n)
+    Gd = dgl.DGLGraph(src, dst, n)
+    for h in (1, 2, 3):
+        ref = sdp.Subgraphs.__new__(sdp.Subgraphs)
+        ref.h, ref.sample_nodes, ref.subgraphs = h, 10 ** 6, {}
+        for i in rng.choice(n, 5, replace=False):
+            sub, centre, parent = ref.generate_subgraph(Gd, int(i), "0_%d" % i)
+            ours = extract_subgraph(G, int(i), h, 10 ** 6)
+            assert sorted(parent) == ours.parent_nid.tolist()
+            assert ours.parent_nid[ours.centre] == i and parent[centre] == i
+            # induced edge multiset in parent ids
+            rs, rd = sub.edges()
+            ref_edges = sorted(zip(np.array(parent)[rs.numpy()].tolist(), np.array(parent)[rd.numpy()].tolist()))
+            od = np.repeat(np.arange(ours.n), np.diff(ours.indptr))
+            our_edges = sorted(zip(ours.parent_nid[ours.indices].tolist(), ours.parent_nid[od].tolist()))
+            assert ref_edges == our_edges
+    ref = sdp.Subgraphs.__new__(sdp.Subgraphs)
+    ref.sample_nodes, ref.subgraphs = 10 ** 6, {}
+    sub, centres, parent = ref.generate_subgraph_link_pred(Gd, 3, 77, "0_3_77")
+    ours = extract_subgraph_link_pred(G, 3, 77, 10 ** 6)
+    assert sorted(parent) == ours.parent_nid.tolist()
+    assert [parent[c] for c in centres] == [3, 77] and ours.parent_nid[ours.centre].tolist() == [3, 77]
+
+
+def test_extraction_sampling_cap():
+    """Above the cap: exactly sample_nodes uniformly chosen nodes plus the centre (:312-314)."""
+    rng = np.random.default_rng(1)
+    n = 400
+    src, dst = rng.integers(0, n, 6000), rng.integers(0, n, 6000)
+    G = ParentGraph.from_edges(src, dst, n)
+    full = extract_subgraph(G, 5, 2, 10 ** 6)
+    assert full.n > 60
+    s = extract_subgraph(G, 5, 2, 50, np.random.default_rng(0))
+    assert s.n in (50, 51) and 5 in s.parent_nid and set(s.parent_nid) <= set(full.parent_nid)
+    assert s.parent_nid[s.centre] == 5
+    with pytest.raises(NameError):
+        extract_subgraph(G, 5, 4, 50)              # the reference only defines h in {1,2,3}
+
+
+def test_product_code_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "gmeta_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("the oracle", ""), fn
