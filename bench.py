@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py -- meta-tasks/s of the G-Meta inner-loop hot path (BASELINE.json metric) on N GPUs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2]
+
+A "step" is one meta-step: the complete first-order ProtoMAML inner loop (K_inner support
+fwd/bwd + SGD, K_inner+1 query forwards + prototype losses, final query/prototype-path backward)
+for every task of one synthetic meta-batch, the single all-reduce and the fused Adam update.
+At N=1 the workload is BASELINE.json configs[1] (arxiv-shaped C2: 169,343 nodes, 1.17M edges,
+feat 128, hidden 256, 3-way 3-shot 24-query, update_step 10, task_num 32).  For N>1 every rank
+runs its own 32-task share (weak scaling, task-sharded; one NCCL all-reduce per step).
+
+  value : device-resident -- packed meta-batches already in HBM when the timed region starts.
+  e2e   : through the reference-facing call Meta.forward(host batch): host packing, ONE pinned
+          H2D copy of the packed integer arrays, the device work, D2H of the accuracy vector.
+  roofline : the dominant kernel (fused GCN layer, query set, hidden->hidden) timed alone with
+          CUDA events on its launch stream; algorithmic bytes per SURVEY 8d / DESIGN.md.
+  cpu_baseline : the oracle port of the reference (oracle/gmeta_oracle.py, torch CPU, all host
+          threads) on a bounded sample (a few tasks of the same workload).
+`--impl reference` prints the CPU arm as its own line (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "meta-tasks/sec (inner-loop fwd+bwd)"
+UNIT = "meta-tasks/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the synthetic graph (debug only)")
+    ap.add_argument("--tasks", type=int, default=0, help="tasks per rank (default: the config's task_num)")
+    ap.add_argument("--batches", type=int, default=3, help="distinct pre-extracted meta-batches to cycle")
+    ap.add_argument("--kernel-impl", type=int, default=0, help="0 auto, 1 FFMA, 2 tcgen05")
+    ap.add_argument("--cpu-tasks", type=int, default=2, help="tasks in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_desc(ds, tasks):
+    g = ds.graphs[0]
+    return {"workload": "%s synthetic (%s): %d graph(s), %d nodes / %d directed nnz in graph 0, feat=%d, "
+                        "hidden=%d, %d-way %d-shot %d-query, h=%d, update_step=%d, task_num=%d per rank, "
+                        "sample_nodes=%d" % (ds.name, ds.task_setup + (" link-pred" if ds.link_pred else ""),
+                                             len(ds.graphs), g.n, g.number_of_edges(), ds.feats[0].shape[1],
+                                             ds.hidden_dim, ds.n_way, ds.k_spt, ds.k_qry, ds.h, ds.update_step,
+                                             tasks, ds.sample_nodes)}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].startswith("Active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_arm(ds, batch_host, n_tasks, steps, warmup):
+    """The reference's CPU path (oracle port, bit-for-bit checked against the unmodified reference
+    in tests/) on `n_tasks` tasks of the workload, all host threads."""
+    from oracle import gmeta_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sub = tuple(lst[:n_tasks] for lst in batch_host)
+    xs, ys, xq, yq, cs, cq, ns, nq, gs, gq = sub
+    oxs = [O.OGraph.from_csr(x.indptr, x.indices, x.batch_num_nodes) for x in xs]
+    oxq = [O.OGraph.from_csr(x.indptr, x.indices, x.batch_num_nodes) for x in xq]
+    torch.manual_seed(222)
+    om = O.OracleMeta(ds.args(), ds.config(), fast=True)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        om.forward(oxs, ys, oxq, yq, cs, cq, ns, nq, gs, gq, ds.feats)
+        times.append(time.perf_counter() - t0)
+    t = float(np.mean(times[warmup:]))
+    return {"value": n_tasks / t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d tasks of the same workload per step (full update_step=%d inner loop + Adam), "
+                      "%d timed steps after %d warm-up; oracle/gmeta_oracle.py with MKL CSR SpMM"
+                      % (n_tasks, ds.update_step, steps, warmup), "s_per_step": t}
+
+
+def layer_roofline(m, db, peaks, impl):
+    """Time the dominant kernel -- the fused GCN layer (hidden->hidden) over the packed QUERY set
+    of the whole meta-batch -- alone, CUDA events on its launch stream, working set > L2."""
+    from gmeta_b200 import _lib, packing
+    L = _lib.lib()
+    spec, ps = m.spec, db.ps_q
+    li = len(spec.conv) - 1
+    f_in, f_out = spec.conv[li]
+    if li == 0:
+        return None
+    dev = db.ints.device
+    N, E, T = ps.N, ps.E, ps.T
+    ld_in, ld_out = (f_in + 3) // 4 * 4, (f_out + 3) // 4 * 4
+    x = torch.randn(N, ld_in, device=dev)
+    out = torch.empty(N, ld_out, device=dev)
+    P = spec.n_params_padded
+    W = torch.randn(T, P, device=dev) * 0.05
+    norm = torch.empty(N, device=dev)
+    base = db.ints.data_ptr()
+    seg = lambda k: base + 4 * ps.off[k]  # noqa: E731
+    cm = spec.c_model()
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.gmeta_degree_norm(seg("indptr"), N, norm.data_ptr(), st))
+
+    def launch():
+        _lib.check(L.gmeta_gcn_layer_fwd(x.data_ptr(), ld_in, None, seg("indptr"), seg("indices"), norm.data_ptr(),
+                                         seg("tile_row0"), seg("tile_nrows"), seg("tile_task"), ps.n_tiles,
+                                         W.data_ptr() + 4 * cm.w_off[li], P, f_out, 0,
+                                         W.data_ptr() + 4 * cm.b_off[li], P, f_in, f_out, 1, None, out.data_ptr(),
+                                         ld_out, impl, st), "gcn_layer_fwd")
+    for _ in range(3):
+        launch()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    # each input row read once, each output row written once, CSR read once, norm derived
+    # from indptr, one weight copy per task
+    alg_bytes = 4.0 * (N * f_in + N * f_out + E + (N + 1) + T * (f_in * f_out + f_out))
+    flops = 2.0 * N * f_in * f_out + 2.0 * E * min(f_in, f_out)
+    achieved = alg_bytes / (ms * 1e-3) / 1e9
+    peak = peaks.get("hbm_gbs", 6650.0)
+    return {"bound": "hbm", "kernel": "gcn_layer_fwd %d->%d over the packed query set (N=%d, E=%d, T=%d)"
+                                      % (f_in, f_out, N, E, T),
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "peak_source": "measured (MEASURED_PEAKS.json, burst copy)" if "hbm_gbs" in peaks else "fallback",
+            "traffic": None, "ms_per_launch": ms, "algorithmic_bytes": alg_bytes,
+            "tflops_fp32_equiv": flops / (ms * 1e-3) / 1e12,
+            "share_note": "working set %.2f GB > 126 MB L2, no flush needed" % (alg_bytes / 1e9)}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from gmeta_b200.synthetic import make_dataset
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        ds = make_dataset(args.workload, scale=args.scale)
+        n_tasks = max(1, args.cpu_tasks)
+        batch = ds.sample_meta_batch(np.random.default_rng(1000), n_tasks)
+        steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+        cb = cpu_arm(ds, batch, n_tasks, steps, warmup)
+        cfg = workload_desc(ds, n_tasks)
+        cfg["note"] = "reference CPU path = oracle port (the reference's own files need DGL, absent here)"
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
+                          "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+                          "ms_per_step": cb["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+                          "cpu_baseline": cb,
+                          "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                                  "d2h_bytes_per_step": 0}}))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (gmeta_b200 has no CPU path)"
+    torch.cuda.set_device(local_rank)
+    from gmeta_b200 import dist
+    import torch.distributed as td
+    if world > 1:
+        dist.init_from_env("nccl")
+    from gmeta_b200.meta import Meta
+
+    ds = make_dataset(args.workload, scale=args.scale)
+    tasks = args.tasks or ds.task_num
+    rng = np.random.default_rng(1000 + rank)
+    t0 = time.perf_counter()
+    batches = [ds.sample_meta_batch(rng, tasks) for _ in range(args.batches)]
+    extract_s = (time.perf_counter() - t0) / args.batches
+    margs = ds.args()
+    margs.impl = args.kernel_impl
+    torch.manual_seed(222)
+    m = Meta(margs, ds.config()).to(torch.device("cuda", local_rank))
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(pk):
+        peaks = json.load(open(pk))
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm ----------------
+    dbs = [m.upload_batch(b, ds.feats, own_buffer=True) for b in batches]
+    for i in range(args.warmup):
+        m.step_device(dbs[i % len(dbs)])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    e0.record()
+    for i in range(args.steps):
+        out_dev = m.step_device(dbs[i % len(dbs)])
+        launches += m.last["gpu_launches"]
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    last_out = out_dev.cpu().numpy()
+    # ---------------- end-to-end arm (host batch in, accuracy vector out) ----------------
+    for i in range(min(2, args.warmup)):
+        m(*batches[i % len(batches)], ds.feats)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        accs = m(*batches[i % len(batches)], ds.feats)
+    f1.record()
+    barrier()
+    sampler.stop_flag = True
+    ms_e2e = f0.elapsed_time(f1)
+    h2d, d2h = m.last["h2d_bytes"], m.last["d2h_bytes"]
+
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)      # max over ranks
+    ms_total, ms_e2e = float(t[0]), float(t[1])
+    total_tasks = tasks * world * args.steps
+    value = total_tasks / (ms_total * 1e-3)
+    e2e_value = total_tasks / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        return
+    roof = layer_roofline(m, dbs[0], peaks, args.kernel_impl)
+    cb = None
+    if not args.no_cpu_baseline:
+        cb = cpu_arm(ds, batches[0], max(1, args.cpu_tasks), 1, 1)
+    cfg = workload_desc(ds, tasks)
+    cfg.update({"parallelism": "task-sharded x%d" % world, "l2_policy": "inputs larger than L2 (packed meta-batch "
+                "activations %.1f GB per step; %d distinct meta-batches cycled)"
+                % (4e-9 * m.last["n_nodes"][1] * ds.hidden_dim * 2, len(batches)),
+                "packed_nodes_spt_qry": m.last["n_nodes"], "packed_edges_spt_qry": m.last["n_edges"],
+                "kernel_impl": {0: "auto", 1: "ffma", 2: "tcgen05-3xtf32"}[args.kernel_impl],
+                "subgraph_extraction_s_per_meta_batch_host": extract_s,
+                "final_accs": [float(a) for a in accs], "loss_q": float(last_out[-2])})
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cb}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

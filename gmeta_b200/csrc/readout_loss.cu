@@ -133,7 +133,8 @@ __global__ void proto_label_prep_kernel(const int32_t* __restrict__ labels,
 // Shared device routine: per query row q (thread-per-row), distances to the prototypes,
 // log-softmax(-d), NLL term, argmax hit, and a[q][c] = dL/dd_qc.
 __device__ __forceinline__ void proto_row(const float* z, const float* mu, int D, int ncls, int target,
-                                          float inv_q, float* a_row, float& nll, float& hit) {
+                                          float inv_q, bool squeeze_quirk, float* a_row, float& nll,
+                                          float& hit) {
   float dmin = INFINITY;
   for (int c = 0; c < ncls; ++c) {
     float d = 0.f;
@@ -157,7 +158,12 @@ __device__ __forceinline__ void proto_row(const float* z, const float* mu, int D
     a_row[c] = ((c == target ? 1.f : 0.f) - expf(lp)) * inv_q;
   }
   nll = -lp_t;
-  hit = (best == target) ? 1.f : 0.f;
+  // Accuracy as the reference computes it (meta.py:52-53,77-78): y_hat.eq(target_inds.squeeze()).
+  // With ONE row per class (1-shot support / 1 query per class) squeeze() drops that axis and the
+  // comparison broadcasts [n_cls,1] against [n_cls]: every row then scores 1/n_cls whatever it
+  // predicts.  Reproduced so the accuracy vector stays identical to the reference's.
+  if (squeeze_quirk) hit = 1.f / (float)ncls;
+  else hit = (best == target) ? 1.f : 0.f;
 }
 
 // one CTA per task.  smem: z[n*D] | mu[C*D] | a[n*C] | red[n*2]
@@ -204,11 +210,12 @@ __global__ void proto_loss_kernel(const float* __restrict__ logits, int D,
   int n_q = 0;
   for (int s = 0; s < n; ++s) n_q += (!SPT || class_occ[s0 + s] < n_support) ? 1 : 0;
   const float inv_q = 1.f / (float)max(n_q, 1);
+  const bool squeeze_quirk = ncls > 1 && (SPT ? n_support == 1 : n_q == ncls);
   for (int s = threadIdx.x; s < n; s += blockDim.x) {
     float nll = 0.f, hit = 0.f;
     const bool used = !SPT || class_occ[s0 + s] < n_support;
     if (used) {
-      proto_row(z + s * D, mu, D, ncls, class_pos[s0 + s], inv_q, a + s * max_classes, nll, hit);
+      proto_row(z + s * D, mu, D, ncls, class_pos[s0 + s], inv_q, squeeze_quirk, a + s * max_classes, nll, hit);
     } else {
       for (int c = 0; c < ncls; ++c) a[s * max_classes + c] = 0.f;
     }
@@ -219,8 +226,8 @@ __global__ void proto_loss_kernel(const float* __restrict__ logits, int D,
   if (threadIdx.x == 0) {
     float l = 0.f, h = 0.f;
     for (int s = 0; s < n; ++s) { l += red[2 * s]; h += red[2 * s + 1]; }
-    loss[(size_t)t * out_stride] = l * inv_q;
-    acc[(size_t)t * out_stride] = h * inv_q;
+    loss[(size_t)t * out_stride] = l / (float)max(n_q, 1);
+    acc[(size_t)t * out_stride] = h / (float)max(n_q, 1);
   }
   if (dlogits == nullptr && dprotos == nullptr) return;
 

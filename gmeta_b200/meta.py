@@ -156,6 +156,11 @@ class FeatureTable(object):
         self._keep = feat          # keeps id(feat) unique while cached
 
 
+class _DeviceBatch(object):
+    """An uploaded meta-batch: segment plans of both sets + the device int32 buffer holding them."""
+    __slots__ = ("T", "max_classes", "ft", "ps_s", "ps_q", "ints", "h2d_bytes")
+
+
 class FusedAdam(object):
     """`meta_optim` (meta.py:97): Adam(lr, betas=(0.9,0.999), eps=1e-8) over the flat parameter
     buffer, one kernel, with the reference's NaN-skip (meta.py:163-164) evaluated on the device."""
@@ -210,6 +215,7 @@ class Meta(nn.Module):
         self._scratch = {}
         self.last = {}                 # diagnostics of the most recent call (loss, launches, bytes)
         self.return_meta_grad = False  # tests: keep a copy of the reduced meta-gradient
+        self.global_task_num = None    # set when ranks hold unequal task shares
 
     # -- state that must not travel through copy.deepcopy(maml) (train.py:87,127) --
     def __deepcopy__(self, memo):
@@ -253,40 +259,54 @@ class Meta(nn.Module):
         cs.n_classes = self._buf(tag + "ncls", (ps.T,), torch.int32, dev).data_ptr()
         return cs
 
-    def _run(self, x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry, feat,
-             steps, train, flat_theta):
-        """Pack + upload one meta-batch and enqueue the inner loop.  Returns device tensors
+    def upload_batch(self, batch, feat, own_buffer=False):
+        """Pack one collated meta-batch (host, integer only) and copy it to the device with ONE
+        async transfer from pinned memory.  With own_buffer=True the device copy gets its own
+        allocation (so several batches can stay resident, e.g. for device-resident benchmarking);
+        otherwise the grow-only staging buffer is reused."""
+        x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry = batch
+        dev = _dev()
+        db = _DeviceBatch()
+        db.T = len(x_spt)
+        db.max_classes = packing.validate_labels(y_spt, y_qry, self.k_spt)
+        db.ft = self._features(feat, dev)
+        if db.ft.f0 != self.spec.conv[0][0]:
+            raise RuntimeError("feature width %d does not match the first GraphConv (%d)"
+                               % (db.ft.f0, self.spec.conv[0][0]))
+        db.ps_s = packing.plan_set(x_spt, c_spt, 0)
+        db.ps_q = packing.plan_set(x_qry, c_qry, db.ps_s.end)
+        if self._staging is None or self._staging.device != dev:
+            self._staging = packing.Staging(dev)
+        buf = self._staging.reserve(db.ps_q.end)
+        packing.fill_set(buf, db.ps_s, x_spt, y_spt, c_spt, n_spt, g_spt, db.ft.graph_row_off)
+        packing.fill_set(buf, db.ps_q, x_qry, y_qry, c_qry, n_qry, g_qry, db.ft.graph_row_off)
+        if own_buffer:
+            db.ints = torch.empty(db.ps_q.end, dtype=torch.int32, device=dev)
+            db.ints.copy_(self._staging.host[:db.ps_q.end], non_blocking=True)
+            torch.cuda.current_stream().synchronize()     # staging is reused by the next upload
+        else:
+            self._staging.upload(db.ps_q.end)
+            db.ints = self._staging.dev
+        db.h2d_bytes = db.ps_q.end * 4
+        return db
+
+    def _enqueue(self, db, steps, train, flat_theta):
+        """Enqueue the whole inner loop for an uploaded meta-batch.  Returns device tensors
         (acc_q [T,K+1], loss_q [T,K+1], meta_grad [P] or None)."""
         L = _lib.lib()
         dev = _dev()
-        T = len(x_spt)
+        T, ps_s, ps_q, ft = db.T, db.ps_s, db.ps_q, db.ft
         if train and steps < 2:
             raise RuntimeError("element 0 of tensors does not require grad and does not have a grad_fn "
                                "(update_step must be >= 2, as in the reference: meta.py:137-141,161)")
-        max_classes = packing.validate_labels(y_spt, y_qry, self.k_spt)
-        ft = self._features(feat, dev)
-        if ft.f0 != self.spec.conv[0][0]:
-            raise RuntimeError("feature width %d does not match the first GraphConv (%d)" % (ft.f0, self.spec.conv[0][0]))
-
-        # ---- pack (host, integer only) + one async upload ----
-        ps_s = packing.plan_set(x_spt, c_spt, 0)
-        ps_q = packing.plan_set(x_qry, c_qry, ps_s.end)
-        if self._staging is None or self._staging.device != dev:
-            self._staging = packing.Staging(dev)
-        buf = self._staging.reserve(ps_q.end)
-        packing.fill_set(buf, ps_s, x_spt, y_spt, c_spt, n_spt, g_spt, ft.graph_row_off)
-        packing.fill_set(buf, ps_q, x_qry, y_qry, c_qry, n_qry, g_qry, ft.graph_row_off)
-        h2d = self._staging.upload(ps_q.end)
-        base = self._staging.dev.data_ptr()
-
-        # ---- arguments ----
+        base = db.ints.data_ptr()
         a = _lib.StepArgs()
         a.model = self.spec.c_model()
         a.spt = self._c_set(ps_s, base, dev, "s_")
         a.qry = self._c_set(ps_q, base, dev, "q_")
         a.feat_table, a.ld_feat = ft.table.data_ptr(), ft.ld
         a.theta = flat_theta.data_ptr()
-        a.update_step, a.n_support, a.max_classes = steps, self.k_spt, max_classes
+        a.update_step, a.n_support, a.max_classes = steps, self.k_spt, db.max_classes
         a.spt_max_rows_per_task, a.qry_max_rows_per_task = ps_s.max_rows_per_task, ps_q.max_rows_per_task
         a.update_lr = self.update_lr
         a.grad_scale = 1.0 / (self._global_task_num(T) if train else 1)
@@ -311,29 +331,40 @@ class Meta(nn.Module):
             self._ws = torch.empty(int(nbytes * 1.1) + 4096, dtype=torch.uint8, device=dev)
         a.workspace, a.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
         _lib.check(L.gmeta_maml_step(C.byref(a), _stream()), "maml_step")
-        self.last = {"h2d_bytes": h2d, "gpu_launches": L.gmeta_last_launch_count(),
+        self.last = {"h2d_bytes": db.h2d_bytes, "gpu_launches": L.gmeta_last_launch_count(),
                      "n_nodes": (ps_s.N, ps_q.N), "n_edges": (ps_s.E, ps_q.E), "workspace_bytes": int(nbytes),
                      "logits_spt0": logits0, "loss_s": loss_s}
         return acc_q, loss_q, meta_grad
 
+    def _run(self, x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry, feat,
+             steps, train, flat_theta):
+        db = self.upload_batch((x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry), feat)
+        return self._enqueue(db, steps, train, flat_theta)
+
     def _global_task_num(self, local_tasks):
+        """task_num of the whole meta-batch across ranks (meta.py:161).  Ranks hold equal shares
+        (dist.shard_tasks), so no collective is needed unless `global_task_num` says otherwise."""
+        if self.global_task_num is not None:
+            return int(self.global_task_num)
         from . import dist
-        return dist.global_task_count(local_tasks)
+        return local_tasks * dist.world_size()
 
     def _flat_theta(self, params, dev):
         flat = self._buf("theta", (self.spec.n_params_padded,), torch.float32, dev, zero=True)
         return self.spec.flatten([p.to(dev) for p in params], flat)
 
     # -- public API (meta.py:236-244) --
-    def forward_ProtoMAML(self, x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry, feat):
+    def step_device(self, db):
+        """One training meta-step on an uploaded batch, everything on the device: inner loop, the
+        single all-reduce, fused Adam.  Returns a device tensor [K+3] = mean accuracies (K+1),
+        mean query loss, skipped flag -- no host synchronisation."""
         from . import dist
         dev = _dev()
         K = self.update_step
         theta = self._flat_theta(self.net.parameters(), dev)
-        acc_q, loss_q, meta_grad = self._run(x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry,
-                                             g_spt, g_qry, feat, K, True, theta)
+        acc_q, loss_q, meta_grad = self._enqueue(db, K, True, theta)
         P = self.spec.n_params_padded
-        T_global = self._global_task_num(len(x_spt))
+        T_global = self._global_task_num(db.T)
         # [meta-grad | sum_t loss_q^K | sum_t acc_q[0..K]] -- the one collective of a meta-step
         red = self._buf("reduce", (P + 1 + K + 1,), torch.float32, dev)
         red[:P].copy_(meta_grad)
@@ -345,17 +376,23 @@ class Meta(nn.Module):
         self.meta_optim.step(theta, red[:P], loss_gate=gate, skipped=skipped)   # meta.py:163-169
         for p, v in zip(self.net.parameters(), self.spec.unflatten(theta)):
             p.data.copy_(v)
-        out = torch.empty(K + 3, dtype=torch.float32, device=dev)
+        out = self._buf("step_out", (K + 3,), torch.float32, dev)
         out[:K + 1] = red[P + 1:] / T_global                              # meta.py:171
         out[K + 1] = gate[0]
         out[K + 2] = skipped[0].float()
-        host = out.cpu()                                                  # the step's only D2H + sync
+        self.last["gpu_launches"] += 1                                    # the Adam kernel
+        if self.return_meta_grad:
+            self.last["meta_grad"] = [g.clone() for g in self.spec.unflatten(red[:P])]
+        return out
+
+    def forward_ProtoMAML(self, x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry, feat):
+        K = self.update_step
+        db = self.upload_batch((x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry), feat)
+        host = self.step_device(db).cpu()                                 # the step's only D2H + sync
         if host[K + 2] != 0:
             self.meta_optim.step_count -= 1                               # skipped step: no Adam state change
         self.last.update({"loss_q": float(host[K + 1]), "skipped": bool(host[K + 2] != 0),
-                          "d2h_bytes": int(out.numel() * 4)})
-        if self.return_meta_grad:
-            self.last["meta_grad"] = [g.clone() for g in self.spec.unflatten(red[:P])]
+                          "d2h_bytes": int(host.numel() * 4)})
         return host[:K + 1].numpy().astype(np.float32)
 
     def finetunning_ProtoMAML(self, x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry, feat):

@@ -20,3 +20,13 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _release_device_temporaries():
+    yield
+    try:
+        from tests import gpu_util
+        gpu_util._KEEP.clear()
+    except Exception:
+        pass

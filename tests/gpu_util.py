@@ -15,12 +15,22 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# Device tensors made by i32()/f32() are kept alive until the end of the test: the C ABI takes raw
+# pointers, so a temporary freed right after .data_ptr() could be recycled by torch's caching
+# allocator for the next argument of the same call.
+_KEEP = []
+
+
 def i32(a):
-    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(dev())
+    t = torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(dev())
+    _KEEP.append(t)
+    return t
 
 
 def f32(a):
-    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(dev())
+    t = torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(dev())
+    _KEEP.append(t)
+    return t
 
 
 def p(t):

@@ -120,7 +120,7 @@ def _random_multitask(rng, T, n_per_task, deg, f_in, f_out, hub=True, table_rows
     src, dst = np.concatenate(src), np.concatenate(dst)
     N = int(trp[-1])
     g = U.DevGraph(src, dst, N, trp)
-    W = rng.standard_normal((T, f_in, f_out), dtype=np.float32) / np.sqrt(f_in)
+    W = (rng.standard_normal((T, f_in, f_out), dtype=np.float32) / np.sqrt(f_in)).astype(np.float32)
     b = rng.standard_normal((T, f_out), dtype=np.float32) * 0.1
     if table_rows:
         table = rng.standard_normal((table_rows, f_in), dtype=np.float32)
@@ -343,7 +343,7 @@ def test_sgd_and_adam_match_torch():
     skipped = torch.zeros(1, dtype=torch.int32, device=U.dev())
     gate = U.f32([0.5])
     for step in range(1, 6):
-        gr = rng.standard_normal(P, dtype=np.float32) * (10.0 ** rng.integers(-4, 1))
+        gr = (rng.standard_normal(P, dtype=np.float32) * (10.0 ** rng.integers(-4, 1))).astype(np.float32)
         p_ref.grad = torch.tensor(gr)
         opt.step()
         _lib.check(L.gmeta_adam_update(U.p(p_dev), U.p(U.f32(gr)), U.p(m), U.p(v), P, 1e-3, 0.9, 0.999, 1e-8, step,
