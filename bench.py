@@ -138,13 +138,15 @@ def layer_roofline(m, db, peaks, impl):
     cm = spec.c_model()
     st = torch.cuda.current_stream().cuda_stream
     _lib.check(L.gmeta_degree_norm(seg("indptr"), N, norm.data_ptr(), st))
+    nb = L.gmeta_gcn_layer_fwd_workspace_bytes(T, P, f_in, f_out, impl)
+    scratch = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
 
     def launch():
         _lib.check(L.gmeta_gcn_layer_fwd(x.data_ptr(), ld_in, None, seg("indptr"), seg("indices"), norm.data_ptr(),
-                                         seg("tile_row0"), seg("tile_nrows"), seg("tile_task"), ps.n_tiles,
+                                         seg("tile_row0"), seg("tile_nrows"), seg("tile_task"), ps.n_tiles, T,
                                          W.data_ptr() + 4 * cm.w_off[li], P, f_out, 0,
                                          W.data_ptr() + 4 * cm.b_off[li], P, f_in, f_out, 1, None, out.data_ptr(),
-                                         ld_out, impl, st), "gcn_layer_fwd")
+                                         ld_out, impl, scratch.data_ptr(), nb, st), "gcn_layer_fwd")
     for _ in range(3):
         launch()
     reps = 10

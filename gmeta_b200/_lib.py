@@ -46,8 +46,9 @@ _SIGNATURES = {
     "gmeta_version": (C.c_int, []),
     "gmeta_error_string": (C.c_char_p, [C.c_int]),
     "gmeta_degree_norm": (C.c_int, [vp, i32, vp, vp]),
-    "gmeta_gcn_layer_fwd": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, i32, vp, i64,
-                                      i32, i32, i32, vp, vp, i32, i32, vp]),
+    "gmeta_gcn_layer_fwd": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, i64, i32, i32, vp, i64,
+                                      i32, i32, i32, vp, vp, i32, i32, vp, i64, vp]),
+    "gmeta_gcn_layer_fwd_workspace_bytes": (i64, [i32, i64, i32, i32, i32]),
     "gmeta_gcn_layer_wgrad_workspace_bytes": (i64, [i32, i32, i32]),
     "gmeta_gcn_layer_wgrad": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp, i64, vp, i64,
                                         vp, i64, vp]),

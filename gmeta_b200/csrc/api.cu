@@ -8,10 +8,12 @@ int gcn_layer_fwd_simt(const GatherSrc& g, const int32_t* tile_row0, const int32
                        int relu, const float* relu_mask, float* out, int ld_out, cudaStream_t stream);
 bool gcn_layer_fwd_tc_supported(const GatherSrc& g, int ldw, int trans_w, int f_out, const float* out,
                                 int ld_out);
+int64_t gcn_layer_fwd_tc_workspace_bytes(int n_copies, int f_in, int f_out);
 int gcn_layer_fwd_tc(const GatherSrc& g, const int32_t* tile_row0, const int32_t* tile_nrows,
-                     const int32_t* tile_task, int n_tiles, const float* W, int64_t w_task_stride,
-                     int ldw, int trans_w, const float* bias, int64_t b_task_stride, int f_out,
-                     int relu, const float* relu_mask, float* out, int ld_out, cudaStream_t stream);
+                     const int32_t* tile_task, int n_tiles, int n_copies, const float* W, int64_t w_task_stride,
+                     int ldw, int trans_w, const float* bias, int64_t b_task_stride, int f_out, int relu,
+                     const float* relu_mask, float* out, int ld_out, void* workspace, int64_t workspace_bytes,
+                     cudaStream_t stream);
 }  // namespace gmeta
 
 using namespace gmeta;
@@ -33,25 +35,36 @@ extern "C" const char* gmeta_error_string(int code) {
 extern "C" int gmeta_gcn_layer_fwd(const float* in, int32_t ld_in, const int32_t* in_row_map,
                                    const int32_t* indptr, const int32_t* indices, const float* norm,
                                    const int32_t* tile_row0, const int32_t* tile_nrows,
-                                   const int32_t* tile_task, int32_t n_tiles, const float* W,
+                                   const int32_t* tile_task, int32_t n_tiles, int32_t n_tasks, const float* W,
                                    int64_t w_task_stride, int32_t ldw, int32_t trans_w, const float* bias,
                                    int64_t b_task_stride, int32_t f_in, int32_t f_out, int32_t relu,
                                    const float* relu_mask, float* out, int32_t ld_out, int32_t impl,
-                                   void* stream) {
+                                   void* workspace, int64_t workspace_bytes, void* stream) {
   if (!in || !indptr || !norm || !tile_row0 || !tile_nrows || !tile_task || !W || !out) return GMETA_ERR_BAD_ARG;
-  if (n_tiles < 0 || f_in <= 0 || f_out <= 0 || ld_in < f_in || ld_out < f_out) return GMETA_ERR_BAD_ARG;
+  if (n_tiles < 0 || n_tasks <= 0 || f_in <= 0 || f_out <= 0 || ld_in < f_in || ld_out < f_out) return GMETA_ERR_BAD_ARG;
   if (ldw < (trans_w ? f_in : f_out)) return GMETA_ERR_BAD_ARG;
   if (n_tiles == 0) return GMETA_OK;
   GatherSrc g;
   g.in = in; g.in_row_map = in_row_map; g.indptr = indptr; g.indices = indices; g.norm = norm;
   g.ld_in = ld_in; g.f_in = f_in;
   cudaStream_t s = (cudaStream_t)stream;
+  const int n_copies = w_task_stride == 0 ? 1 : n_tasks;
   const bool tc_ok = gcn_layer_fwd_tc_supported(g, ldw, trans_w, f_out, out, ld_out);
   if (impl == GMETA_IMPL_TCGEN05 && !tc_ok) return GMETA_ERR_UNSUPPORTED;
-  if (impl == GMETA_IMPL_TCGEN05 || (impl == GMETA_IMPL_AUTO && tc_ok))
-    return gcn_layer_fwd_tc(g, tile_row0, tile_nrows, tile_task, n_tiles, W, w_task_stride, ldw, trans_w, bias,
-                            b_task_stride, f_out, relu, relu_mask, out, ld_out, s);
+  // AUTO falls back to the FFMA kernel when no workspace for the weight image was provided
+  const bool ws_ok = workspace && workspace_bytes >= gcn_layer_fwd_tc_workspace_bytes(n_copies, f_in, f_out);
+  if (impl == GMETA_IMPL_TCGEN05 || (impl == GMETA_IMPL_AUTO && tc_ok && ws_ok))
+    return gcn_layer_fwd_tc(g, tile_row0, tile_nrows, tile_task, n_tiles, n_copies, W, w_task_stride, ldw,
+                            trans_w, bias, b_task_stride, f_out, relu, relu_mask, out, ld_out, workspace,
+                            workspace_bytes, s);
   if (impl != GMETA_IMPL_AUTO && impl != GMETA_IMPL_SIMT) return GMETA_ERR_BAD_ARG;
   return gcn_layer_fwd_simt(g, tile_row0, tile_nrows, tile_task, n_tiles, W, w_task_stride, ldw, trans_w, bias,
                             b_task_stride, f_out, relu, relu_mask, out, ld_out, s);
+}
+
+extern "C" int64_t gmeta_gcn_layer_fwd_workspace_bytes(int32_t n_tasks, int64_t w_task_stride, int32_t f_in,
+                                                       int32_t f_out, int32_t impl) {
+  if (n_tasks <= 0 || f_in <= 0 || f_out <= 0) return 0;
+  if (impl == GMETA_IMPL_SIMT) return 0;
+  return gcn_layer_fwd_tc_workspace_bytes(w_task_stride == 0 ? 1 : n_tasks, f_in, f_out);
 }

@@ -1,11 +1,456 @@
-// tcgen05 (3xTF32) implementation of the fused GCN layer -- placeholder until the kernel lands.
+// Fused GCN layer over a packed meta-batch -- Blackwell tensor-core implementation (sm_100a).
+//
+// One persistent CTA per SM, warp-specialised:
+//   warps 0..15  gather producers: CSR neighbour gather + norm-weighted sum of the input rows for a
+//                128-row tile, one 32-float K chunk at a time, written as an error-compensated
+//                TF32 pair (hi = top 19 bits, lo = exact remainder) into 128B-swizzled K-major
+//                shared-memory operand tiles;
+//   warp 16      bulk-async (TMA) copies of the pre-split, pre-swizzled weight chunk of the
+//                tile's TASK (per-task fast weights) into shared memory;
+//   warp 17      one elected thread issues tcgen05.mma kind::tf32 -- three MMAs per K step
+//                (hi*hi + lo*hi + hi*lo, "3xTF32") accumulating fp32 in tensor memory (TMEM);
+//   warps 18..21 epilogue: tcgen05.ld of the accumulator rows, * norm[v] + bias, ReLU / mask,
+//                16-byte stores; TMEM is double buffered so the epilogue of tile i overlaps the
+//                MMAs of tile i+1.
+// Stages are handed over with mbarriers (full/empty per ring stage, full/empty per accumulator).
+// Replaces GraphConv.forward (reference G-Meta/learner.py:25-56) for K % 32 == 0 and
+// N % 16 == 0, N <= 256; everything else takes the FFMA kernel in gcn_layer_simt.cu.
+#include <cstdio>
+
 #include "common.cuh"
 
 namespace gmeta {
-bool gcn_layer_fwd_tc_supported(const GatherSrc&, int, int, int, const float*, int) { return false; }
-int gcn_layer_fwd_tc(const GatherSrc&, const int32_t*, const int32_t*, const int32_t*, int, const float*,
-                     int64_t, int, int, const float*, int64_t, int, int, const float*, float*, int,
-                     cudaStream_t) {
-  return GMETA_ERR_UNSUPPORTED;
+namespace {
+
+constexpr int TM = GMETA_TILE_ROWS;     // 128 = UMMA M
+constexpr int KCH = 32;                 // floats per K chunk = one 128-byte swizzle row
+constexpr int A_TILE_BYTES = TM * KCH * 4;   // 16 KB (hi or lo)
+constexpr int N_PROD_WARPS = 16;
+constexpr int WARP_TMA = 16;
+constexpr int WARP_MMA = 17;
+constexpr int WARP_EPI0 = 18;
+constexpr int NTHREADS_TC = 22 * 32;
+constexpr int MAX_STAGES = 4;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_COLS = 256;           // columns per accumulator buffer
+constexpr int PRE = 4;                  // neighbours per row whose (row, norm) stay in registers
+constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000LL;  // ~2 s: trap instead of hanging the GPU
+
+struct TcParams {
+  GatherSrc g;
+  const int32_t* tile_row0;
+  const int32_t* tile_nrows;
+  const int32_t* tile_task;
+  int n_tiles;
+  const float* w_image;      // [copies][K/32][hi|lo][N rows][32 floats, 128B swizzle]
+  long long image_task_stride;  // floats between task copies (0 = shared weights)
+  const float* bias;
+  long long b_task_stride;
+  int f_out;
+  int relu;
+  const float* relu_mask;
+  float* out;
+  int ld_out;
+  int n_stages;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > WAIT_TIMEOUT_CYCLES) {
+      printf("gmeta tc kernel: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
+             (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, M=128
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory operand descriptor (cute::UMMA::SmemDescriptor layout):
+// start address >> 4 [0,14), LBO (ignored for swizzled K-major, set 1) [16,30), SBO = 1024 B
+// between 8-row groups [32,46), version 1 [46,48), layout SWIZZLE_128B = 2 at [61,64).
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 at [4,6), a/b format
+// TF32 = 2 at [7,10)/[10,13), a/b K-major (0) at 15/16, N >> 3 at [17,23), M >> 4 at [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float tf32_hi(float a) { return __uint_as_float(__float_as_uint(a) & 0xFFFFE000u); }
+
+struct Smem {
+  // dynamic shared memory, 1024-byte aligned: [stage][A_hi | A_lo | B_hi | B_lo], then barriers
+  uint8_t* base;
+  int stage_bytes;
+  int b_bytes;  // one of B_hi / B_lo
+  __device__ uint8_t* a_hi(int s) const { return base + (size_t)s * stage_bytes; }
+  __device__ uint8_t* a_lo(int s) const { return a_hi(s) + A_TILE_BYTES; }
+  __device__ uint8_t* b_hi(int s) const { return a_hi(s) + 2 * A_TILE_BYTES; }
+};
+
+__global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = p.f_out;
+  const int nkc = p.g.f_in / KCH;
+  const int NS = p.n_stages;
+  Smem sm;
+  sm.base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B needs 1024-byte alignment
+  sm.b_bytes = N * KCH * 4;
+  sm.stage_bytes = 2 * A_TILE_BYTES + 2 * sm.b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm.base + (size_t)NS * sm.stage_bytes);
+  // barrier slots: a_full[4] b_full[4] empty[4] acc_full[2] acc_empty[2]
+  const uint32_t bar0 = smem_u32(bars);
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto b_full = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
+  auto empty = [&](int s) { return bar0 + 8u * (2 * MAX_STAGES + s); };
+  auto acc_full = [&](int b) { return bar0 + 8u * (3 * MAX_STAGES + b); };
+  auto acc_empty = [&](int b) { return bar0 + 8u * (3 * MAX_STAGES + 2 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(a_full(s), N_PROD_WARPS);
+      mbar_init(b_full(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == WARP_TMA) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < N_PROD_WARPS) {
+    // ===================== gather producers =====================
+    // a quarter-warp (8 lanes x 16 B = one 128-byte chunk row) owns tile rows q and q+64
+    const int q = warp * 4 + (lane >> 3);
+    const int sub = lane & 7;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const int row0 = p.tile_row0[tile], nrows = p.tile_nrows[tile];
+      int beg[2], end[2];
+      int src_off[2][PRE];       // element offset of the neighbour's row (+ this lane's 16-byte unit)
+      float src_norm[2][PRE];
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int r = q + 64 * rr;
+        beg[rr] = end[rr] = 0;
+        if (r < nrows) {
+          beg[rr] = p.g.indptr[row0 + r];
+          end[rr] = p.g.indptr[row0 + r + 1];
+        }
+#pragma unroll
+        for (int i = 0; i < PRE; ++i) {
+          src_off[rr][i] = 0;
+          src_norm[rr][i] = 0.f;
+          if (beg[rr] + i < end[rr]) {
+            const int u = p.g.indices[beg[rr] + i];
+            src_norm[rr][i] = p.g.norm[u];
+            const int srow = p.g.in_row_map ? p.g.in_row_map[u] : u;
+            src_off[rr][i] = srow * p.g.ld_in + 4 * sub;
+          }
+        }
+      }
+      for (int kc = 0; kc < nkc; ++kc, ++it) {
+        const int s = it % NS;
+        const uint32_t ph = (uint32_t)((it / NS) & 1);
+        mbar_wait(empty(s), ph ^ 1u);
+        float4 x[2][PRE];
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+          for (int i = 0; i < PRE; ++i)
+            x[rr][i] = (beg[rr] + i < end[rr]) ? ld_f4(p.g.in + src_off[rr][i] + kc * KCH) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int r = q + 64 * rr;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < PRE; ++i) {
+            acc.x = fmaf(src_norm[rr][i], x[rr][i].x, acc.x);
+            acc.y = fmaf(src_norm[rr][i], x[rr][i].y, acc.y);
+            acc.z = fmaf(src_norm[rr][i], x[rr][i].z, acc.z);
+            acc.w = fmaf(src_norm[rr][i], x[rr][i].w, acc.w);
+          }
+          for (int e = beg[rr] + PRE; e < end[rr]; ++e) {   // rows with more than PRE in-neighbours
+            const int u = p.g.indices[e];
+            const float nu = p.g.norm[u];
+            const int srow = p.g.in_row_map ? p.g.in_row_map[u] : u;
+            const float4 xv = ld_f4(p.g.in + (size_t)srow * p.g.ld_in + kc * KCH + 4 * sub);
+            acc.x = fmaf(nu, xv.x, acc.x);
+            acc.y = fmaf(nu, xv.y, acc.y);
+            acc.z = fmaf(nu, xv.z, acc.z);
+            acc.w = fmaf(nu, xv.w, acc.w);
+          }
+          const float4 hi = make_float4(tf32_hi(acc.x), tf32_hi(acc.y), tf32_hi(acc.z), tf32_hi(acc.w));
+          const float4 lo = make_float4(acc.x - hi.x, acc.y - hi.y, acc.z - hi.z, acc.w - hi.w);
+          const int off = r * 128 + ((sub ^ (r & 7)) << 4);   // 128B swizzle: 16-byte unit ^ (row % 8)
+          *reinterpret_cast<float4*>(sm.a_hi(s) + off) = hi;
+          *reinterpret_cast<float4*>(sm.a_lo(s) + off) = lo;
+        }
+        fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full(s));
+      }
+    }
+  } else if (warp == WARP_TMA) {
+    // ===================== weight chunk loader (bulk async copy) =====================
+    if (lane == 0) {
+      int it = 0;
+      const uint32_t bytes = 2u * (uint32_t)sm.b_bytes;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const float* img = p.w_image + (long long)p.tile_task[tile] * p.image_task_stride;
+        for (int kc = 0; kc < nkc; ++kc, ++it) {
+          const int s = it % NS;
+          const uint32_t ph = (uint32_t)((it / NS) & 1);
+          mbar_wait(empty(s), ph ^ 1u);
+          mbar_arrive_expect_tx(b_full(s), bytes);
+          bulk_copy_g2s(smem_u32(sm.b_hi(s)), img + (size_t)kc * 2 * N * KCH, bytes, b_full(s));
+        }
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(TM, N);
+      int it = 0;
+      int ti = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
+        const int buf = ti & 1;
+        mbar_wait(acc_empty(buf), (uint32_t)(((ti >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
+        for (int kc = 0; kc < nkc; ++kc, ++it) {
+          const int s = it % NS;
+          const uint32_t ph = (uint32_t)((it / NS) & 1);
+          mbar_wait(a_full(s), ph);
+          mbar_wait(b_full(s), ph);
+          tc_fence_after();
+          const uint64_t da_hi = umma_desc_k_sw128(smem_u32(sm.a_hi(s)));
+          const uint64_t da_lo = umma_desc_k_sw128(smem_u32(sm.a_lo(s)));
+          const uint64_t db_hi = umma_desc_k_sw128(smem_u32(sm.b_hi(s)));
+          const uint64_t db_lo = umma_desc_k_sw128(smem_u32(sm.b_hi(s) + sm.b_bytes));
+#pragma unroll
+          for (int k = 0; k < KCH / 8; ++k) {     // UMMA_K = 8 tf32 = 32 bytes = 2 descriptor units
+            const uint64_t adv = (uint64_t)(2 * k);
+            tc_mma_tf32(d_tmem, da_hi + adv, db_hi + adv, idesc, (kc | k) != 0 ? 1u : 0u);
+            tc_mma_tf32(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
+            tc_mma_tf32(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
+          }
+          tc_commit(empty(s));          // frees the stage once these MMAs have read it
+        }
+        tc_commit(acc_full(buf));       // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int quarter = warp & 3;       // TMEM lanes 32*quarter .. +31 are the ones this warp may read
+    const int r = quarter * 32 + lane;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
+      const int buf = ti & 1;
+      const int row0 = p.tile_row0[tile], nrows = p.tile_nrows[tile], task = p.tile_task[tile];
+      const float* bias = p.bias ? p.bias + (long long)task * p.b_task_stride : nullptr;
+      const bool live = r < nrows;
+      const int v = row0 + (live ? r : 0);
+      const float nv = p.g.norm[v];
+      float* orow = p.out + (size_t)v * p.ld_out;
+      const float* mrow = p.relu_mask ? p.relu_mask + (size_t)v * p.ld_out : nullptr;
+      mbar_wait(acc_full(buf), (uint32_t)((ti >> 1) & 1));
+      tc_fence_after();
+      for (int c0 = 0; c0 < N; c0 += 16) {
+        uint32_t acc[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * ACC_COLS + c0), acc);
+        const float bl = (bias && lane < 16) ? bias[c0 + lane] : 0.f;
+        tmem_ld_wait();
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float val = fmaf(nv, __uint_as_float(acc[j]), __shfl_sync(0xffffffffu, bl, j));
+          if (p.relu) val = fmaxf(val, 0.f);
+          o[j] = val;
+        }
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 w4 = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            if (mrow) {
+              const float4 m4 = ld_f4(mrow + c0 + j);
+              if (!(m4.x > 0.f)) w4.x = 0.f;
+              if (!(m4.y > 0.f)) w4.y = 0.f;
+              if (!(m4.z > 0.f)) w4.z = 0.f;
+              if (!(m4.w > 0.f)) w4.w = 0.f;
+            }
+            st_f4(orow + c0 + j, w4);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(buf));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WARP_TMA) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// raw fp32 weights (either orientation) -> per-copy UMMA image [K/32][hi|lo][N][32, swizzled]
+__global__ void pack_w_umma_kernel(const float* __restrict__ W, long long w_stride, int ldw, int trans, int K,
+                                   int N, int n_copies, float* __restrict__ image, long long image_stride) {
+  const long long total = (long long)n_copies * (K / KCH) * N * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int unit = (int)(i & 7);
+    long long rest = i >> 3;
+    const int n = (int)(rest % N); rest /= N;
+    const int kc = (int)(rest % (K / KCH));
+    const int c = (int)(rest / (K / KCH));
+    const float* w = W + c * w_stride;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = kc * KCH + unit * 4 + j;
+      v[j] = trans ? w[(size_t)n * ldw + k] : w[(size_t)k * ldw + n];
+    }
+    const float4 hi = make_float4(tf32_hi(v[0]), tf32_hi(v[1]), tf32_hi(v[2]), tf32_hi(v[3]));
+    const float4 lo = make_float4(v[0] - hi.x, v[1] - hi.y, v[2] - hi.z, v[3] - hi.w);
+    float* chunk = image + c * image_stride + (size_t)kc * 2 * N * KCH;
+    const int off = n * KCH + ((unit ^ (n & 7)) << 2);
+    st_f4(chunk + off, hi);
+    st_f4(chunk + (size_t)N * KCH + off, lo);
+  }
+}
+
+int stages_for(int N) {
+  const int stage = 2 * A_TILE_BYTES + 2 * N * KCH * 4;
+  int s = (200 * 1024) / stage;
+  return s > MAX_STAGES ? MAX_STAGES : s;
+}
+
+}  // namespace
+
+bool gcn_layer_fwd_tc_supported(const GatherSrc& g, int ldw, int trans_w, int f_out, const float* out,
+                                int ld_out) {
+  (void)ldw; (void)trans_w;
+  if (g.f_in % KCH != 0 || g.f_in < KCH || g.f_in > 2048) return false;
+  if (f_out % 16 != 0 || f_out < 16 || f_out > 256) return false;
+  if (g.ld_in % 4 != 0 || !aligned16(g.in) || g.ld_in < g.f_in) return false;
+  if (ld_out % 4 != 0 || !aligned16(out)) return false;
+  return true;
+}
+
+int64_t gcn_layer_fwd_tc_workspace_bytes(int n_copies, int f_in, int f_out) {
+  return (int64_t)n_copies * 2 * f_in * f_out * (int64_t)sizeof(float);
+}
+
+int gcn_layer_fwd_tc(const GatherSrc& g, const int32_t* tile_row0, const int32_t* tile_nrows,
+                     const int32_t* tile_task, int n_tiles, int n_copies, const float* W, int64_t w_task_stride,
+                     int ldw, int trans_w, const float* bias, int64_t b_task_stride, int f_out, int relu,
+                     const float* relu_mask, float* out, int ld_out, void* workspace, int64_t workspace_bytes,
+                     cudaStream_t stream) {
+  const int K = g.f_in, N = f_out;
+  if (!workspace || !aligned16(workspace)) return GMETA_ERR_WORKSPACE;
+  if (workspace_bytes < gcn_layer_fwd_tc_workspace_bytes(n_copies, K, N)) return GMETA_ERR_WORKSPACE;
+  float* image = reinterpret_cast<float*>(workspace);
+  const long long image_stride = 2LL * K * N;
+  {
+    const long long total = (long long)n_copies * (K / KCH) * N * 8;
+    const int grid = (int)((total + 255) / 256 < 8 * kNumSMs ? (total + 255) / 256 : 8 * kNumSMs);
+    pack_w_umma_kernel<<<grid, 256, 0, stream>>>(W, w_task_stride, ldw, trans_w, K, N, n_copies, image, image_stride);
+    int rc = check_launch();
+    if (rc != GMETA_OK) return rc;
+  }
+  TcParams p;
+  p.g = g;
+  p.tile_row0 = tile_row0; p.tile_nrows = tile_nrows; p.tile_task = tile_task; p.n_tiles = n_tiles;
+  p.w_image = image; p.image_task_stride = n_copies > 1 ? image_stride : 0;
+  p.bias = bias; p.b_task_stride = b_task_stride; p.f_out = N; p.relu = relu; p.relu_mask = relu_mask;
+  p.out = out; p.ld_out = ld_out;
+  p.n_stages = stages_for(N);
+  const size_t smem = (size_t)p.n_stages * (2 * A_TILE_BYTES + 2 * N * KCH * 4) + 256 + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(gcn_layer_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_done = true;
+  }
+  const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+  gcn_layer_fwd_tc_kernel<<<grid, NTHREADS_TC, smem, stream>>>(p);
+  return check_launch();
+}
+
 }  // namespace gmeta

@@ -47,6 +47,8 @@ struct StepBuffers {
   float* acc_s;
   void* wgrad_ws;
   int64_t wgrad_ws_bytes;
+  void* layer_ws;            // weight image of the tensor-core layer kernel
+  int64_t layer_ws_bytes;
   int ld[GMETA_MAX_LAYERS];
   int64_t total;
 };
@@ -99,6 +101,12 @@ void carve(const gmeta_step_args_t* a, void* ws, StepBuffers& b) {
     if (w > b.wgrad_ws_bytes) b.wgrad_ws_bytes = w;
   }
   b.wgrad_ws = c.take<char>(b.wgrad_ws_bytes);
+  b.layer_ws_bytes = 0;
+  for (int l = 0; l < m.n_layers; ++l) {
+    const int64_t w = gmeta_gcn_layer_fwd_workspace_bytes((int)T, P, m.f_in[l], m.f_out[l], a->impl);
+    if (w > b.layer_ws_bytes) b.layer_ws_bytes = w;
+  }
+  b.layer_ws = c.take<char>(b.layer_ws_bytes);
   b.total = c.off;
 }
 
@@ -117,9 +125,9 @@ struct Runner {
       const float* in = l == 0 ? a->feat_table : act[l - 1];
       const int ld_in = l == 0 ? a->ld_feat : b.ld[l - 1];
       run(gmeta_gcn_layer_fwd(in, ld_in, l == 0 ? set.feat_row : nullptr, set.indptr, set.indices, set.norm,
-                              set.tile_row0, set.tile_nrows, set.tile_task, set.n_tiles, W + m.w_off[l],
-                              stride, m.f_out[l], 0, W + m.b_off[l], stride, m.f_in[l], m.f_out[l], 1,
-                              nullptr, act[l], b.ld[l], a->impl, s));
+                              set.tile_row0, set.tile_nrows, set.tile_task, set.n_tiles, set.n_tasks,
+                              W + m.w_off[l], stride, m.f_out[l], 0, W + m.b_off[l], stride, m.f_in[l],
+                              m.f_out[l], 1, nullptr, act[l], b.ld[l], a->impl, b.layer_ws, b.layer_ws_bytes, s));
     }
     const int L = m.n_layers;
     run(gmeta_readout_linear_fwd(act[L - 1], b.ld[L - 1], m.f_out[L - 1], set.centre_row,
@@ -148,9 +156,9 @@ struct Runner {
         // data gradient = the forward kernel on the transposed graph with W^T, masked by the
         // ReLU of the layer below (features carry no gradient, so layer 0 stops here)
         run(gmeta_gcn_layer_fwd(dz[cur], b.ld[l], nullptr, set.t_indptr, set.t_indices, set.norm,
-                                set.tile_row0, set.tile_nrows, set.tile_task, set.n_tiles, W + m.w_off[l],
-                                stride, m.f_out[l], 1, nullptr, 0, m.f_out[l], m.f_in[l], 0, act[l - 1],
-                                dz[cur ^ 1], b.ld[l - 1], a->impl, s));
+                                set.tile_row0, set.tile_nrows, set.tile_task, set.n_tiles, set.n_tasks,
+                                W + m.w_off[l], stride, m.f_out[l], 1, nullptr, 0, m.f_out[l], m.f_in[l], 0,
+                                act[l - 1], dz[cur ^ 1], b.ld[l - 1], a->impl, b.layer_ws, b.layer_ws_bytes, s));
         cur ^= 1;
       }
     }

@@ -145,11 +145,13 @@ class _ClassifierFn(torch.autograd.Function):
         for l, (fi, fo) in enumerate(spec.conv):
             ld_out = _round_up(fo, 4)
             out = torch.empty(dg.N, ld_out, dtype=torch.float32, device=dev)
+            nb = L.gmeta_gcn_layer_fwd_workspace_bytes(1, 0, fi, fo, impl)
+            scratch = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
             _lib.check(L.gmeta_gcn_layer_fwd(
                 _ptr(inp), ld_in, None, _ptr(dg.indptr), _ptr(dg.indices), _ptr(dg.norm),
-                _ptr(dg.tile_row0), _ptr(dg.tile_nrows), _ptr(dg.tile_task), dg.n_tiles,
+                _ptr(dg.tile_row0), _ptr(dg.tile_nrows), _ptr(dg.tile_task), dg.n_tiles, 1,
                 _ptr(ws[2 * l]), 0, fo, 0, _ptr(ws[2 * l + 1]), 0, fi, fo, 1, None, _ptr(out), ld_out,
-                impl, _stream()), "gcn_layer_fwd")
+                impl, _ptr(scratch), nb, _stream()), "gcn_layer_fwd")
             acts.append(out)
             inp, ld_in = out, ld_out
         cps = 2 if spec.link_pred else 1
@@ -188,11 +190,13 @@ class _ClassifierFn(torch.autograd.Function):
             if l > 0:
                 ld_lo = acts[l - 1].shape[1]
                 dz_lo = torch.empty(dg.N, ld_lo, dtype=torch.float32, device=dev)
+                nb = L.gmeta_gcn_layer_fwd_workspace_bytes(1, 0, fo, fi, ctx.impl)
+                scratch = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
                 _lib.check(L.gmeta_gcn_layer_fwd(
                     _ptr(dz), dz.shape[1], None, _ptr(dg.t_indptr), _ptr(dg.t_indices), _ptr(dg.norm),
-                    _ptr(dg.tile_row0), _ptr(dg.tile_nrows), _ptr(dg.tile_task), dg.n_tiles,
+                    _ptr(dg.tile_row0), _ptr(dg.tile_nrows), _ptr(dg.tile_task), dg.n_tiles, 1,
                     _ptr(ws[2 * l]), 0, fo, 1, None, 0, fo, fi, 0, _ptr(acts[l - 1]), _ptr(dz_lo), ld_lo,
-                    ctx.impl, _stream()), "gcn_layer dgrad")
+                    ctx.impl, _ptr(scratch), nb, _stream()), "gcn_layer dgrad")
                 dz = dz_lo
         return (None, None, None, None, None) + tuple(grads)
 

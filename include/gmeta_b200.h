@@ -107,15 +107,24 @@ int gmeta_degree_norm(const int32_t* indptr, int32_t n_nodes, float* norm, void*
  * act = ReLU iff relu != 0; if relu_mask != NULL the result is zeroed where relu_mask[v,j] <= 0
  * (ld_out layout).  Columns [f_out, round_up(f_out,4)) of out are written as 0.
  * The same entry point run on (t_indptr, t_indices) with trans_w=1, bias=NULL, relu=0 and
- * relu_mask = the lower layer's activations is the layer's data-gradient. */
+ * relu_mask = the lower layer's activations is the layer's data-gradient.
+ * impl: GMETA_IMPL_SIMT (fp32 FFMA, any shape), GMETA_IMPL_TCGEN05 (tcgen05.mma 3xTF32 with TMEM
+ * accumulators; needs f_in % 32 == 0, f_out % 16 == 0, f_out <= 256, ld % 4 == 0 and the
+ * workspace below) or GMETA_IMPL_AUTO. */
 int gmeta_gcn_layer_fwd(const float* in, int32_t ld_in, const int32_t* in_row_map,
                         const int32_t* indptr, const int32_t* indices, const float* norm,
                         const int32_t* tile_row0, const int32_t* tile_nrows,
-                        const int32_t* tile_task, int32_t n_tiles,
+                        const int32_t* tile_task, int32_t n_tiles, int32_t n_tasks,
                         const float* W, int64_t w_task_stride, int32_t ldw, int32_t trans_w,
                         const float* bias, int64_t b_task_stride,
                         int32_t f_in, int32_t f_out, int32_t relu, const float* relu_mask,
-                        float* out, int32_t ld_out, int32_t impl, void* stream);
+                        float* out, int32_t ld_out, int32_t impl,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+/* Scratch for the tensor-core path's pre-split (hi/lo TF32), pre-swizzled weight image:
+ * 2 * f_in * f_out floats per weight copy (n_tasks copies, or 1 when w_task_stride == 0).
+ * 0 for GMETA_IMPL_SIMT.  With GMETA_IMPL_AUTO and a NULL/too small workspace the FFMA kernel runs. */
+int64_t gmeta_gcn_layer_fwd_workspace_bytes(int32_t n_tasks, int64_t w_task_stride, int32_t f_in,
+                                            int32_t f_out, int32_t impl);
 
 /* Weight/bias gradient of one GCN layer (the autograd.grad of meta.py:125,149 for that layer):
  *   dW[t][k,j] = sum_{v in task t} norm[v] * M[v,k] * dZ[v,j],   db[t][j] = sum_v dZ[v,j]

@@ -66,9 +66,12 @@ def layer_fwd(g, x, W, b, f_in, f_out, relu=1, transposed=False, trans_w=0, mask
     ip, ix = (g.t_indptr, g.t_indices) if transposed else (g.indptr, g.indices)
     if ldw is None:
         ldw = f_in if trans_w else f_out
+    nb = _lib.lib().gmeta_gcn_layer_fwd_workspace_bytes(g.T, w_stride, f_in, f_out, impl)
+    ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev())
     rc = _lib.lib().gmeta_gcn_layer_fwd(p(x), x.shape[1], p(row_map), p(ip), p(ix), p(g.norm), p(g.tile_row0),
-                                        p(g.tile_nrows), p(g.tile_task), g.n_tiles, p(W), w_stride, ldw, trans_w,
-                                        p(b), b_stride, f_in, f_out, relu, p(mask), p(out), ld_out, impl, stream())
+                                        p(g.tile_nrows), p(g.tile_task), g.n_tiles, g.T, p(W), w_stride, ldw,
+                                        trans_w, p(b), b_stride, f_in, f_out, relu, p(mask), p(out), ld_out, impl,
+                                        p(ws), nb, stream())
     _lib.check(rc, "gcn_layer_fwd")
     return out
 
