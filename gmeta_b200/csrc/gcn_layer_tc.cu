@@ -34,6 +34,8 @@ constexpr int MAX_STAGES = 4;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_COLS = 256;           // columns per accumulator buffer
 constexpr int PRE = 4;                  // neighbours per row whose (row, norm) stay in registers
+constexpr int N_PROD_THREADS = N_PROD_WARPS * 32;
+constexpr int LCAP = 1024;              // long-edge records staged per window
 constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000LL;  // ~2 s: trap instead of hanging the GPU
 
 struct TcParams {
@@ -52,6 +54,7 @@ struct TcParams {
   float* out;
   int ld_out;
   int n_stages;
+  float* long_scratch;       // [gridDim.x][128][f_in] aggregated rows of long (hub) rows, L2 resident
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -138,6 +141,20 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 __device__ __forceinline__ float tf32_hi(float a) { return __uint_as_float(__float_as_uint(a) & 0xFFFFE000u); }
 
+// producer-side bookkeeping in shared memory (after the pipeline stages and barriers)
+struct alignas(16) ProdSmem {
+  float part[2 * N_PROD_THREADS * 4];   // [group][continued-from-left | continues-right][f_in] partial sums
+  int src[LCAP];                        // source row offset (elements) of each staged long edge
+  float nrm[LCAP];                      // its norm
+  int beg[TM];                          // first edge of each tile row
+  int deg[TM];
+  int lpos[TM + 1];                     // start of each row in the flattened long-edge list
+  uint8_t row[LCAP];                    // tile row of each staged long edge
+  uint8_t is_long[TM];
+};
+
+__device__ __forceinline__ void producer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N_PROD_THREADS) : "memory"); }
+
 struct Smem {
   // dynamic shared memory, 1024-byte aligned: [stage][A_hi | A_lo | B_hi | B_lo], then barriers
   uint8_t* base;
@@ -167,6 +184,7 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const 
   auto acc_full = [&](int b) { return bar0 + 8u * (3 * MAX_STAGES + b); };
   auto acc_empty = [&](int b) { return bar0 + 8u * (3 * MAX_STAGES + 2 + b); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
+  ProdSmem* ps = reinterpret_cast<ProdSmem*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) {
@@ -192,45 +210,176 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const 
 
   if (warp < N_PROD_WARPS) {
     // ===================== gather producers =====================
-    // a quarter-warp (8 lanes x 16 B = one 128-byte chunk row) owns tile rows q and q+64
+    // Rows with at most PRE in-neighbours (97% of the rows of a 2-hop subgraph batch) are gathered
+    // chunk by chunk by a quarter-warp each.  The few LONG rows (hubs: ~3% of rows, ~half of the
+    // edges) would serialise a quarter-warp for hundreds of dependent loads, so they are
+    // aggregated ONCE per tile over the full feature width by all 512 producer threads,
+    // edge-parallel and balanced (contiguous slices of the flattened long-edge list per thread
+    // group, partial sums of rows that straddle slices combined in slice order -> deterministic),
+    // into an L2-resident per-CTA scratch row that the chunk loop then reads like a single
+    // neighbour with weight 1.
+    const int tid = threadIdx.x;
     const int q = warp * 4 + (lane >> 3);
     const int sub = lane & 7;
+    const int f_in = p.g.f_in;
+    const int tpr = f_in >> 2;                      // threads covering one full row (16 B each)
+    const int G = N_PROD_THREADS / tpr;             // thread groups working on different edges
+    const int g = tid / tpr, cu = tid - g * tpr;    // my group / my 16-byte column unit
+    float* scratch = p.long_scratch + (size_t)blockIdx.x * TM * f_in;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int row0 = p.tile_row0[tile], nrows = p.tile_nrows[tile];
-      int beg[2], end[2];
+      // ---- tile setup: row extents, long flags, positions in the flattened long-edge list ----
+      if (warp == 0) {
+        int b[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) b[j] = p.g.indptr[row0 + min(lane * 4 + j, nrows)];
+        int w[4], tot = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = lane * 4 + j, d = b[j + 1] - b[j];
+          const bool lg = d > PRE;
+          ps->beg[r] = b[j];
+          ps->deg[r] = d;
+          ps->is_long[r] = lg ? 1 : 0;
+          w[j] = lg ? d : 0;
+          tot += w[j];
+        }
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        int run = incl - tot;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { ps->lpos[lane * 4 + j] = run; run += w[j]; }
+        if (lane == 31) ps->lpos[TM] = incl;
+      }
+      producer_sync();
+      const int nLE = ps->lpos[TM];
+      for (int wbeg = 0; wbeg < nLE; wbeg += LCAP) {
+        const int wlen = min(LCAP, nLE - wbeg);
+        // ---- edge records of this window, one per thread, coalesced ----
+        for (int i = tid; i < wlen; i += N_PROD_THREADS) {
+          const int pos = wbeg + i;
+          int lo = 0, hi = TM;                      // largest r with lpos[r] <= pos (a long row)
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (ps->lpos[mid] <= pos) lo = mid; else hi = mid;
+          }
+          const int u = p.g.indices[ps->beg[lo] + (pos - ps->lpos[lo])];
+          ps->nrm[i] = p.g.norm[u];
+          ps->src[i] = (p.g.in_row_map ? p.g.in_row_map[u] : u) * p.g.ld_in;
+          ps->row[i] = (uint8_t)lo;
+        }
+        producer_sync();
+        // ---- balanced accumulation: group g owns list slice [sb, se) ----
+        int own_r = -1;
+        if (g < G) {
+          const int per = (wlen + G - 1) / G;
+          const int sb = min(g * per, wlen), se = min(sb + per, wlen);
+          int pos = sb;
+          while (pos < se) {
+            const int r = ps->row[pos];
+            const int rbeg = ps->lpos[r] - wbeg, rend = rbeg + ps->deg[r];
+            const int wrb = max(rbeg, 0), wre = min(rend, wlen);   // the row's span inside this window
+            const int run_end = min(se, wre);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int e = pos; e < run_end; e += 8) {
+              float4 xv[8];
+              float nn[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const bool ok = e + j < run_end;
+                nn[j] = ok ? ps->nrm[e + j] : 0.f;
+                xv[j] = ok ? ld_f4(p.g.in + ps->src[e + j] + 4 * cu) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                acc.x = fmaf(nn[j], xv[j].x, acc.x);
+                acc.y = fmaf(nn[j], xv[j].y, acc.y);
+                acc.z = fmaf(nn[j], xv[j].z, acc.z);
+                acc.w = fmaf(nn[j], xv[j].w, acc.w);
+              }
+            }
+            const bool from_left = pos > wrb, to_right = run_end < wre;
+            if (!from_left && !to_right) {            // whole row (within this window) in my slice
+              float* dst = scratch + r * f_in + 4 * cu;
+              if (rbeg < 0) {                         // row began in an earlier window: accumulate
+                const float4 old = __ldcg(reinterpret_cast<const float4*>(dst));
+                acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w;
+              }
+              __stcg(reinterpret_cast<float4*>(dst), acc);
+            } else {
+              st_f4(ps->part + ((g * 2 + (from_left ? 0 : 1)) * f_in + 4 * cu), acc);
+              if (!from_left) own_r = r;              // I own the row: it starts in my slice
+            }
+            pos = run_end;
+          }
+        }
+        producer_sync();
+        // ---- rows straddling slices: the owner adds the partials in slice order ----
+        if (own_r >= 0) {
+          const int per = (wlen + G - 1) / G;
+          const int rbeg = ps->lpos[own_r] - wbeg;
+          const int wre = min(rbeg + ps->deg[own_r], wlen);
+          const int g_last = (wre - 1) / per;
+          float4 acc = ld_f4(ps->part + ((g * 2 + 1) * f_in + 4 * cu));
+          for (int g2 = g + 1; g2 <= g_last; ++g2) {
+            const float4 v = ld_f4(ps->part + ((g2 * 2 + 0) * f_in + 4 * cu));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+          }
+          float* dst = scratch + own_r * f_in + 4 * cu;
+          if (rbeg < 0) {
+            const float4 old = __ldcg(reinterpret_cast<const float4*>(dst));
+            acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w;
+          }
+          __stcg(reinterpret_cast<float4*>(dst), acc);
+        }
+        producer_sync();
+      }
+      // ---- per-row neighbour records kept in registers for the whole tile ----
+      int cnt[2];
       int src_off[2][PRE];       // element offset of the neighbour's row (+ this lane's 16-byte unit)
       float src_norm[2][PRE];
+      const float* base0[2];     // base of neighbour 0: the input, or the scratch row of a long row
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
         const int r = q + 64 * rr;
-        beg[rr] = end[rr] = 0;
-        if (r < nrows) {
-          beg[rr] = p.g.indptr[row0 + r];
-          end[rr] = p.g.indptr[row0 + r + 1];
-        }
+        const int rb = ps->beg[r], d = ps->deg[r];
+        const bool lg = ps->is_long[r] != 0;
+        cnt[rr] = lg ? 1 : d;
+        base0[rr] = lg ? scratch : p.g.in;
 #pragma unroll
         for (int i = 0; i < PRE; ++i) {
           src_off[rr][i] = 0;
           src_norm[rr][i] = 0.f;
-          if (beg[rr] + i < end[rr]) {
-            const int u = p.g.indices[beg[rr] + i];
+          if (!lg && i < d) {
+            const int u = p.g.indices[rb + i];
             src_norm[rr][i] = p.g.norm[u];
-            const int srow = p.g.in_row_map ? p.g.in_row_map[u] : u;
-            src_off[rr][i] = srow * p.g.ld_in + 4 * sub;
+            src_off[rr][i] = (p.g.in_row_map ? p.g.in_row_map[u] : u) * p.g.ld_in + 4 * sub;
           }
         }
+        if (lg) {
+          src_off[rr][0] = r * f_in + 4 * sub;
+          src_norm[rr][0] = 1.f;
+        }
       }
+      producer_sync();   // everyone has read ps / may still read scratch until the next tile's first sync
       for (int kc = 0; kc < nkc; ++kc, ++it) {
         const int s = it % NS;
         const uint32_t ph = (uint32_t)((it / NS) & 1);
         mbar_wait(empty(s), ph ^ 1u);
         float4 x[2][PRE];
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr)
+        for (int rr = 0; rr < 2; ++rr) {
+          x[rr][0] = cnt[rr] > 0 ? __ldcg(reinterpret_cast<const float4*>(base0[rr] + src_off[rr][0] + kc * KCH))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int i = 0; i < PRE; ++i)
-            x[rr][i] = (beg[rr] + i < end[rr]) ? ld_f4(p.g.in + src_off[rr][i] + kc * KCH) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = 1; i < PRE; ++i)
+            x[rr][i] = i < cnt[rr] ? ld_f4(p.g.in + src_off[rr][i] + kc * KCH) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
           const int r = q + 64 * rr;
@@ -241,16 +390,6 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const 
             acc.y = fmaf(src_norm[rr][i], x[rr][i].y, acc.y);
             acc.z = fmaf(src_norm[rr][i], x[rr][i].z, acc.z);
             acc.w = fmaf(src_norm[rr][i], x[rr][i].w, acc.w);
-          }
-          for (int e = beg[rr] + PRE; e < end[rr]; ++e) {   // rows with more than PRE in-neighbours
-            const int u = p.g.indices[e];
-            const float nu = p.g.norm[u];
-            const int srow = p.g.in_row_map ? p.g.in_row_map[u] : u;
-            const float4 xv = ld_f4(p.g.in + (size_t)srow * p.g.ld_in + kc * KCH + 4 * sub);
-            acc.x = fmaf(nu, xv.x, acc.x);
-            acc.y = fmaf(nu, xv.y, acc.y);
-            acc.z = fmaf(nu, xv.z, acc.z);
-            acc.w = fmaf(nu, xv.w, acc.w);
           }
           const float4 hi = make_float4(tf32_hi(acc.x), tf32_hi(acc.y), tf32_hi(acc.z), tf32_hi(acc.w));
           const float4 lo = make_float4(acc.x - hi.x, acc.y - hi.y, acc.z - hi.z, acc.w - hi.w);
@@ -396,9 +535,11 @@ __global__ void pack_w_umma_kernel(const float* __restrict__ W, long long w_stri
   }
 }
 
+constexpr int kSmemFixed = 1024 /*alignment slack*/ + 256 /*barriers*/ + (int)sizeof(ProdSmem);
+
 int stages_for(int N) {
   const int stage = 2 * A_TILE_BYTES + 2 * N * KCH * 4;
-  int s = (200 * 1024) / stage;
+  int s = (227 * 1024 - kSmemFixed) / stage;
   return s > MAX_STAGES ? MAX_STAGES : s;
 }
 
@@ -414,8 +555,13 @@ bool gcn_layer_fwd_tc_supported(const GatherSrc& g, int ldw, int trans_w, int f_
   return true;
 }
 
+static int64_t image_bytes(int n_copies, int f_in, int f_out) {
+  return ((int64_t)n_copies * 2 * f_in * f_out * (int64_t)sizeof(float) + 255) / 256 * 256;
+}
+
 int64_t gcn_layer_fwd_tc_workspace_bytes(int n_copies, int f_in, int f_out) {
-  return (int64_t)n_copies * 2 * f_in * f_out * (int64_t)sizeof(float);
+  // weight image + per-CTA scratch rows for long (hub) rows
+  return image_bytes(n_copies, f_in, f_out) + (int64_t)kNumSMs * TM * f_in * (int64_t)sizeof(float);
 }
 
 int gcn_layer_fwd_tc(const GatherSrc& g, const int32_t* tile_row0, const int32_t* tile_nrows,
@@ -442,7 +588,8 @@ int gcn_layer_fwd_tc(const GatherSrc& g, const int32_t* tile_row0, const int32_t
   p.bias = bias; p.b_task_stride = b_task_stride; p.f_out = N; p.relu = relu; p.relu_mask = relu_mask;
   p.out = out; p.ld_out = ld_out;
   p.n_stages = stages_for(N);
-  const size_t smem = (size_t)p.n_stages * (2 * A_TILE_BYTES + 2 * N * KCH * 4) + 256 + 1024;
+  p.long_scratch = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + image_bytes(n_copies, K, N));
+  const size_t smem = (size_t)p.n_stages * (2 * A_TILE_BYTES + 2 * N * KCH * 4) + kSmemFixed;
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(gcn_layer_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""Micro-benchmark of the fused GCN layer kernel on a synthetic packed set shaped like the C2
+query set (T tasks x ~38k rows, subgraph blocks of ~500 rows, ~1.8 in-edges per row).
+Prints ms/launch, algorithmic GB/s and the fraction of the measured HBM peak for each impl."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from gmeta_b200 import _lib  # noqa: E402
+from gmeta_b200.learner import tile_table  # noqa: E402
+
+
+def synth(T, rows_per_task, block, deg, rng):
+    sizes = np.full(T, rows_per_task)
+    trp = np.concatenate([[0], np.cumsum(sizes)])
+    N = int(trp[-1])
+    e = int(N * deg)
+    dst = np.sort(rng.integers(0, N, e))
+    blk = dst // block
+    src = np.minimum(blk * block + rng.integers(0, block, e), N - 1)
+    indptr = np.zeros(N + 1, dtype=np.int32)
+    np.cumsum(np.bincount(dst, minlength=N), out=indptr[1:])
+    return trp, indptr, src.astype(np.int32), N, e
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--tasks", type=int, default=32)
+    ap.add_argument("--rows", type=int, default=38000)
+    ap.add_argument("--fin", type=int, default=256)
+    ap.add_argument("--fout", type=int, default=256)
+    ap.add_argument("--deg", type=float, default=1.76)
+    ap.add_argument("--impls", default="1,2")
+    ap.add_argument("--reps", type=int, default=10)
+    a = ap.parse_args()
+    L = _lib.lib()
+    dev = torch.device("cuda")
+    rng = np.random.default_rng(0)
+    trp, indptr, indices, N, E = synth(a.tasks, a.rows, 500, a.deg, rng)
+    row0, nrows, task = tile_table(trp)
+    i32 = lambda x: torch.as_tensor(np.ascontiguousarray(x, dtype=np.int32)).to(dev)  # noqa: E731
+    d_indptr, d_indices, d_row0, d_nrows, d_task = i32(indptr), i32(indices), i32(row0), i32(nrows), i32(task)
+    x = torch.randn(N, a.fin, device=dev)
+    W = torch.randn(a.tasks, a.fin * a.fout + a.fout, device=dev) * 0.05
+    out = torch.empty(N, a.fout, device=dev)
+    norm = torch.empty(N, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.gmeta_degree_norm(d_indptr.data_ptr(), N, norm.data_ptr(), st))
+    P = a.fin * a.fout + a.fout
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    peak = peaks.get("hbm_gbs", 6650.0)
+    alg = 4.0 * (N * a.fin + N * a.fout + E + N + 1 + a.tasks * (a.fin * a.fout + a.fout))
+    res = {}
+    outs = {}
+    for impl in [int(v) for v in a.impls.split(",")]:
+        nb = L.gmeta_gcn_layer_fwd_workspace_bytes(a.tasks, P, a.fin, a.fout, impl)
+        ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
+
+        def launch():
+            _lib.check(L.gmeta_gcn_layer_fwd(x.data_ptr(), a.fin, None, d_indptr.data_ptr(), d_indices.data_ptr(),
+                                             norm.data_ptr(), d_row0.data_ptr(), d_nrows.data_ptr(), d_task.data_ptr(),
+                                             len(row0), a.tasks, W.data_ptr(), P, a.fout, 0,
+                                             W.data_ptr() + 4 * a.fin * a.fout, P, a.fin, a.fout, 1, None,
+                                             out.data_ptr(), a.fout, impl, ws.data_ptr(), nb, st))
+        for _ in range(2):
+            launch()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(a.reps):
+            launch()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.reps
+        outs[impl] = out.clone()
+        res[impl] = {"ms": ms, "GBps": alg / ms / 1e6, "frac_hbm": alg / ms / 1e6 / peak}
+    if 1 in outs and 2 in outs:
+        res["max_abs_diff"] = float((outs[1] - outs[2]).abs().max())
+    print(json.dumps({"N": N, "E": E, "tiles": len(row0), "alg_GB": alg / 1e9, "res": res}))
+
+
+if __name__ == "__main__":
+    main()
