@@ -142,7 +142,7 @@ def layer_roofline(m, db, peaks, impl):
     scratch = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
 
     def launch():
-        _lib.check(L.gmeta_gcn_layer_fwd(x.data_ptr(), ld_in, None, seg("indptr"), seg("indices"), norm.data_ptr(),
+        _lib.check(L.gmeta_gcn_layer_fwd(x.data_ptr(), ld_in, None, None, seg("indptr"), seg("indices"), norm.data_ptr(),
                                          seg("tile_row0"), seg("tile_nrows"), seg("tile_task"), ps.n_tiles, T,
                                          W.data_ptr() + 4 * cm.w_off[li], P, f_out, 0,
                                          W.data_ptr() + 4 * cm.b_off[li], P, f_in, f_out, 1, None, out.data_ptr(),

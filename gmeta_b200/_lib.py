@@ -23,7 +23,10 @@ class PackedSet(C.Structure):
                                     "centres_per_subgraph")] + \
                [(n, vp) for n in ("indptr", "indices", "t_indptr", "t_indices", "tile_row0", "tile_nrows",
                                    "tile_task", "task_row_ptr", "task_sub_ptr", "centre_row", "feat_row",
-                                   "labels", "norm", "class_pos", "class_occ", "n_classes")]
+                                   "labels", "norm", "class_pos", "class_occ", "n_classes")] + \
+               [("n_act", i32 * MAX_LAYERS), ("n_act_tiles", i32 * MAX_LAYERS)] + \
+               [(n, vp * MAX_LAYERS) for n in ("act_rows", "act_task_ptr", "act_tile_row0", "act_tile_nrows",
+                                               "act_tile_task", "row_pos")]
 
 
 class Model(C.Structure):
@@ -37,7 +40,8 @@ class StepArgs(C.Structure):
     _fields_ = [("model", Model), ("spt", PackedSet), ("qry", PackedSet), ("feat_table", vp),
                 ("ld_feat", i32), ("theta", vp), ("update_step", i32), ("n_support", i32),
                 ("max_classes", i32), ("spt_max_rows_per_task", i32), ("qry_max_rows_per_task", i32),
-                ("update_lr", f32), ("grad_scale", f32), ("compute_meta_grad", i32), ("impl", i32),
+                ("update_lr", f32), ("grad_scale", f32), ("compute_meta_grad", i32), ("dense_backward", i32),
+                ("impl", i32),
                 ("meta_grad", vp), ("loss_q", vp), ("acc_q", vp), ("loss_s", vp), ("logits_spt0", vp),
                 ("workspace", vp), ("workspace_bytes", i64)]
 
@@ -46,15 +50,16 @@ _SIGNATURES = {
     "gmeta_version": (C.c_int, []),
     "gmeta_error_string": (C.c_char_p, [C.c_int]),
     "gmeta_degree_norm": (C.c_int, [vp, i32, vp, vp]),
-    "gmeta_gcn_layer_fwd": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, i64, i32, i32, vp, i64,
+    "gmeta_gcn_layer_fwd": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, i64, i32, i32, vp, i64,
                                       i32, i32, i32, vp, vp, i32, i32, vp, i64, vp]),
     "gmeta_gcn_layer_fwd_workspace_bytes": (i64, [i32, i64, i32, i32, i32]),
     "gmeta_gcn_layer_wgrad_workspace_bytes": (i64, [i32, i32, i32]),
-    "gmeta_gcn_layer_wgrad": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp, i64, vp, i64,
+    "gmeta_gcn_layer_wgrad": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp, i64, vp, i64,
                                         vp, i64, vp]),
     "gmeta_readout_linear_fwd": (C.c_int, [vp, i32, i32, vp, i32, vp, i32, i32, vp, i64, vp, i64, i32, vp, vp]),
-    "gmeta_readout_linear_bwd": (C.c_int, [vp, i32, i32, i32, vp, i32, vp, i32, i32, vp, i64, i32, vp, vp, i64,
+    "gmeta_readout_linear_bwd": (C.c_int, [vp, i32, i32, i32, vp, vp, i32, vp, i32, i32, vp, i64, i32, vp, vp, i64,
                                            vp, i64, vp, vp]),
+    "gmeta_build_row_pos": (C.c_int, [vp, i32, i32, vp, vp]),
     "gmeta_proto_label_prep": (C.c_int, [vp, vp, i32, vp, vp, vp, vp]),
     "gmeta_proto_loss_spt": (C.c_int, [vp, i32, vp, i32, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, i32, vp, vp]),
     "gmeta_proto_loss_qry": (C.c_int, [vp, i32, vp, i32, vp, vp, vp, i32, i32, f32, vp, vp, i32, vp, vp, vp]),

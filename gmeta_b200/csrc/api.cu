@@ -33,7 +33,7 @@ extern "C" const char* gmeta_error_string(int code) {
 }
 
 extern "C" int gmeta_gcn_layer_fwd(const float* in, int32_t ld_in, const int32_t* in_row_map,
-                                   const int32_t* indptr, const int32_t* indices, const float* norm,
+                                   const int32_t* dst_rows, const int32_t* indptr, const int32_t* indices, const float* norm,
                                    const int32_t* tile_row0, const int32_t* tile_nrows,
                                    const int32_t* tile_task, int32_t n_tiles, int32_t n_tasks, const float* W,
                                    int64_t w_task_stride, int32_t ldw, int32_t trans_w, const float* bias,
@@ -45,7 +45,7 @@ extern "C" int gmeta_gcn_layer_fwd(const float* in, int32_t ld_in, const int32_t
   if (ldw < (trans_w ? f_in : f_out)) return GMETA_ERR_BAD_ARG;
   if (n_tiles == 0) return GMETA_OK;
   GatherSrc g;
-  g.in = in; g.in_row_map = in_row_map; g.indptr = indptr; g.indices = indices; g.norm = norm;
+  g.in = in; g.in_row_map = in_row_map; g.dst_rows = dst_rows; g.indptr = indptr; g.indices = indices; g.norm = norm;
   g.ld_in = ld_in; g.f_in = f_in;
   cudaStream_t s = (cudaStream_t)stream;
   const int n_copies = w_task_stride == 0 ? 1 : n_tasks;

@@ -27,7 +27,8 @@ __device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<fl
 // Adjacency + row source of a gather: M[v,:] = sum_{e in [indptr[v],indptr[v+1])} norm[u_e] * in[map(u_e),:]
 struct GatherSrc {
   const float* in;
-  const int32_t* in_row_map;  // nullable
+  const int32_t* in_row_map;  // nullable; a negative entry means "this neighbour contributes nothing"
+  const int32_t* dst_rows;    // nullable; real row of compact row i (adjacency, norm, mask use the real row)
   const int32_t* indptr;
   const int32_t* indices;
   const float* norm;
@@ -56,8 +57,9 @@ __device__ __forceinline__ void gather_rows(const GatherSrc& g, int row0, int nr
   {
     const int r = warp + NW * lane;
     if (lane < RPW && r < nrows) {
-      my_beg = g.indptr[row0 + r];
-      my_end = g.indptr[row0 + r + 1];
+      const int v = g.dst_rows ? g.dst_rows[row0 + r] : row0 + r;
+      my_beg = g.indptr[v];
+      my_end = g.indptr[v + 1];
     }
   }
   auto load_batch = [&](int base, int end, int& u_src, float& u_norm) {
@@ -68,6 +70,7 @@ __device__ __forceinline__ void gather_rows(const GatherSrc& g, int row0, int nr
       const int u = g.indices[e];
       u_norm = g.norm[u];
       u_src = g.in_row_map ? g.in_row_map[u] : u;
+      if (u_src < 0) { u_src = 0; u_norm = 0.f; }   // skipped neighbour: weight 0 on a valid row
     }
   };
   int nb = __shfl_sync(0xffffffffu, my_beg, 0), ne = __shfl_sync(0xffffffffu, my_end, 0);
@@ -116,7 +119,7 @@ __device__ __forceinline__ void gather_rows(const GatherSrc& g, int row0, int nr
       }
     }
     if (SCALE_DST && r < nrows) {
-      const float nv = g.norm[row0 + r];
+      const float nv = g.norm[g.dst_rows ? g.dst_rows[row0 + r] : row0 + r];
       acc.x *= nv; acc.y *= nv; acc.z *= nv; acc.w *= nv;
     }
     st_f4(As + r * lda + 4 * lane, acc);

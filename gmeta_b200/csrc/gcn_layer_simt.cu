@@ -146,7 +146,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) gcn_layer_fwd_simt_kernel(const F
     for (int i = 0; i < 8; ++i) {
       const int r = ty + 16 * i;
       if (r >= nrows) continue;
-      const int v = row0 + r;
+      const int orow = row0 + r;                                     // output row (compact or dense)
+      const int v = p.g.dst_rows ? p.g.dst_rows[orow] : orow;        // real row: norm and mask
       const float nv = p.g.norm[v];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gcn_layer_fwd_simt_kernel(const F
           }
           o[j] = val;
         }
-        float* dst = p.out + (size_t)v * p.ld_out + c;
+        float* dst = p.out + (size_t)orow * p.ld_out + c;
         if (p.vec_out && c + 4 <= f_out4) {
           st_f4(dst, make_float4(o[0], o[1], o[2], o[3]));
         } else {
@@ -382,7 +383,7 @@ extern "C" int64_t gmeta_gcn_layer_wgrad_workspace_bytes(int32_t n_tasks, int32_
 }
 
 extern "C" int gmeta_gcn_layer_wgrad(const float* in, int32_t ld_in, const int32_t* in_row_map,
-                                     const int32_t* indptr, const int32_t* indices, const float* norm,
+                                     const int32_t* dst_rows, const int32_t* indptr, const int32_t* indices, const float* norm,
                                      const int32_t* task_row_ptr, int32_t n_tasks, const float* dZ,
                                      int32_t ld_dz, int32_t f_in, int32_t f_out, float* dW,
                                      int64_t dw_task_stride, float* db, int64_t db_task_stride,
@@ -393,7 +394,7 @@ extern "C" int gmeta_gcn_layer_wgrad(const float* in, int32_t ld_in, const int32
   if (workspace_bytes < gmeta_gcn_layer_wgrad_workspace_bytes(n_tasks, f_in, f_out)) return GMETA_ERR_WORKSPACE;
   if (!aligned16(workspace)) return GMETA_ERR_ALIGN;
   WgradParams p;
-  p.g.in = in; p.g.in_row_map = in_row_map; p.g.indptr = indptr; p.g.indices = indices;
+  p.g.in = in; p.g.in_row_map = in_row_map; p.g.dst_rows = dst_rows; p.g.indptr = indptr; p.g.indices = indices;
   p.g.norm = norm; p.g.ld_in = ld_in; p.g.f_in = f_in;
   p.task_row_ptr = task_row_ptr; p.n_tasks = n_tasks; p.dZ = dZ; p.ld_dz = ld_dz; p.f_out = f_out;
   p.n_split = pick_wgrad_split(n_tasks, f_in, f_out);

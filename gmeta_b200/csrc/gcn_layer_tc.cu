@@ -231,15 +231,18 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const 
       const int row0 = p.tile_row0[tile], nrows = p.tile_nrows[tile];
       // ---- tile setup: row extents, long flags, positions in the flattened long-edge list ----
       if (warp == 0) {
-        int b[5];
-#pragma unroll
-        for (int j = 0; j < 5; ++j) b[j] = p.g.indptr[row0 + min(lane * 4 + j, nrows)];
         int w[4], tot = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int r = lane * 4 + j, d = b[j + 1] - b[j];
+          const int r = lane * 4 + j;
+          int rb = 0, d = 0;
+          if (r < nrows) {
+            const int v = p.g.dst_rows ? p.g.dst_rows[row0 + r] : row0 + r;
+            rb = p.g.indptr[v];
+            d = p.g.indptr[v + 1] - rb;
+          }
           const bool lg = d > PRE;
-          ps->beg[r] = b[j];
+          ps->beg[r] = rb;
           ps->deg[r] = d;
           ps->is_long[r] = lg ? 1 : 0;
           w[j] = lg ? d : 0;
@@ -269,8 +272,9 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const 
             if (ps->lpos[mid] <= pos) lo = mid; else hi = mid;
           }
           const int u = p.g.indices[ps->beg[lo] + (pos - ps->lpos[lo])];
-          ps->nrm[i] = p.g.norm[u];
-          ps->src[i] = (p.g.in_row_map ? p.g.in_row_map[u] : u) * p.g.ld_in;
+          const int srow = p.g.in_row_map ? p.g.in_row_map[u] : u;
+          ps->nrm[i] = srow < 0 ? 0.f : p.g.norm[u];       // negative map entry: neighbour skipped
+          ps->src[i] = (srow < 0 ? 0 : srow) * p.g.ld_in;
           ps->row[i] = (uint8_t)lo;
         }
         producer_sync();
@@ -357,8 +361,9 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const 
           src_norm[rr][i] = 0.f;
           if (!lg && i < d) {
             const int u = p.g.indices[rb + i];
-            src_norm[rr][i] = p.g.norm[u];
-            src_off[rr][i] = (p.g.in_row_map ? p.g.in_row_map[u] : u) * p.g.ld_in + 4 * sub;
+            const int srow = p.g.in_row_map ? p.g.in_row_map[u] : u;
+            src_norm[rr][i] = srow < 0 ? 0.f : p.g.norm[u];
+            src_off[rr][i] = (srow < 0 ? 0 : srow) * p.g.ld_in + 4 * sub;
           }
         }
         if (lg) {
@@ -461,9 +466,10 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const 
       const int row0 = p.tile_row0[tile], nrows = p.tile_nrows[tile], task = p.tile_task[tile];
       const float* bias = p.bias ? p.bias + (long long)task * p.b_task_stride : nullptr;
       const bool live = r < nrows;
-      const int v = row0 + (live ? r : 0);
+      const int oi = row0 + (live ? r : 0);                          // output row (compact or dense)
+      const int v = p.g.dst_rows ? p.g.dst_rows[oi] : oi;            // real row: norm and mask
       const float nv = p.g.norm[v];
-      float* orow = p.out + (size_t)v * p.ld_out;
+      float* orow = p.out + (size_t)oi * p.ld_out;
       const float* mrow = p.relu_mask ? p.relu_mask + (size_t)v * p.ld_out : nullptr;
       mbar_wait(acc_full(buf), (uint32_t)((ti >> 1) & 1));
       tc_fence_after();

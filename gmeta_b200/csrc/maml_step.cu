@@ -36,7 +36,7 @@ struct StepBuffers {
   float* g_qry;
   float* act_spt[GMETA_MAX_LAYERS];
   float* act_qry[GMETA_MAX_LAYERS];
-  float* dz_spt[2];
+  float* dz_spt[2];          // dense: [N, ld]; sparse backward: [max n_act, ld]
   float* dz_qry[2];
   float* logits_s;
   float* logits_q;
@@ -84,10 +84,18 @@ void carve(const gmeta_step_args_t* a, void* ws, StepBuffers& b) {
   b.g_qry = c.take<float>(T * P);
   for (int l = 0; l < m.n_layers; ++l) b.act_spt[l] = c.take<float>(Ns * b.ld[l]);
   for (int l = 0; l < m.n_layers; ++l) b.act_qry[l] = c.take<float>(Nq * b.ld[l]);
-  b.dz_spt[0] = c.take<float>(Ns * ld_max);
-  b.dz_spt[1] = c.take<float>(m.n_layers > 1 ? Ns * ld_max : 0);
-  b.dz_qry[0] = c.take<float>(a->compute_meta_grad ? Nq * ld_max : 0);
-  b.dz_qry[1] = c.take<float>(a->compute_meta_grad && m.n_layers > 1 ? Nq * ld_max : 0);
+  int64_t rows_s = Ns, rows_q = Nq;   // rows of the dZ buffers
+  if (!a->dense_backward) {
+    rows_s = rows_q = 1;
+    for (int l = 0; l < m.n_layers; ++l) {
+      if (a->spt.n_act[l] > rows_s) rows_s = a->spt.n_act[l];
+      if (a->qry.n_act[l] > rows_q) rows_q = a->qry.n_act[l];
+    }
+  }
+  b.dz_spt[0] = c.take<float>(rows_s * ld_max);
+  b.dz_spt[1] = c.take<float>(m.n_layers > 1 ? rows_s * ld_max : 0);
+  b.dz_qry[0] = c.take<float>(a->compute_meta_grad ? rows_q * ld_max : 0);
+  b.dz_qry[1] = c.take<float>(a->compute_meta_grad && m.n_layers > 1 ? rows_q * ld_max : 0);
   b.logits_s = c.take<float>(Ss * C);
   b.logits_q = c.take<float>(Sq * C);
   b.dlogits_s = c.take<float>(Ss * C);
@@ -124,7 +132,7 @@ struct Runner {
     for (int l = 0; l < m.n_layers && ok(); ++l) {
       const float* in = l == 0 ? a->feat_table : act[l - 1];
       const int ld_in = l == 0 ? a->ld_feat : b.ld[l - 1];
-      run(gmeta_gcn_layer_fwd(in, ld_in, l == 0 ? set.feat_row : nullptr, set.indptr, set.indices, set.norm,
+      run(gmeta_gcn_layer_fwd(in, ld_in, l == 0 ? set.feat_row : nullptr, nullptr, set.indptr, set.indices, set.norm,
                               set.tile_row0, set.tile_nrows, set.tile_task, set.n_tiles, set.n_tasks,
                               W + m.w_off[l], stride, m.f_out[l], 0, W + m.b_off[l], stride, m.f_in[l],
                               m.f_out[l], 1, nullptr, act[l], b.ld[l], a->impl, b.layer_ws, b.layer_ws_bytes, s));
@@ -140,25 +148,34 @@ struct Runner {
     const gmeta_model_t& m = a->model;
     const int L = m.n_layers;
     const int64_t P = m.n_params_padded;
+    const bool sparse = !a->dense_backward;
     int cur = 0;
-    run(gmeta_readout_linear_bwd(act[L - 1], b.ld[L - 1], m.f_out[L - 1], set.n_nodes, set.centre_row,
-                                 set.centres_per_subgraph, set.task_sub_ptr, set.n_tasks, set.n_subgraphs,
-                                 W + m.wlin_off, stride, m.n_out, dlogits, gout + m.wlin_off, P,
-                                 gout + m.blin_off, P, dz[cur], s));
+    // dZ of the last GCN layer: zero except at the centre rows (dense [N, ld] like the reference's
+    // autograd, or compact over the active rows)
+    run(gmeta_readout_linear_bwd(act[L - 1], b.ld[L - 1], m.f_out[L - 1], sparse ? set.n_act[L - 1] : set.n_nodes,
+                                 sparse ? set.row_pos[L - 1] : nullptr, set.centre_row, set.centres_per_subgraph,
+                                 set.task_sub_ptr, set.n_tasks, set.n_subgraphs, W + m.wlin_off, stride, m.n_out,
+                                 dlogits, gout + m.wlin_off, P, gout + m.blin_off, P, dz[cur], s));
     for (int l = L - 1; l >= 0 && ok(); --l) {
       const float* in = l == 0 ? a->feat_table : act[l - 1];
       const int ld_in = l == 0 ? a->ld_feat : b.ld[l - 1];
-      run(gmeta_gcn_layer_wgrad(in, ld_in, l == 0 ? set.feat_row : nullptr, set.indptr, set.indices,
-                                set.norm, set.task_row_ptr, set.n_tasks, dz[cur], b.ld[l], m.f_in[l],
-                                m.f_out[l], gout + m.w_off[l], P, gout + m.b_off[l], P, b.wgrad_ws,
-                                b.wgrad_ws_bytes, s));
+      run(gmeta_gcn_layer_wgrad(in, ld_in, l == 0 ? set.feat_row : nullptr, sparse ? set.act_rows[l] : nullptr,
+                                set.indptr, set.indices, set.norm, sparse ? set.act_task_ptr[l] : set.task_row_ptr,
+                                set.n_tasks, dz[cur], b.ld[l], m.f_in[l], m.f_out[l], gout + m.w_off[l], P,
+                                gout + m.b_off[l], P, b.wgrad_ws, b.wgrad_ws_bytes, s));
       if (l > 0) {
         // data gradient = the forward kernel on the transposed graph with W^T, masked by the
-        // ReLU of the layer below (features carry no gradient, so layer 0 stops here)
-        run(gmeta_gcn_layer_fwd(dz[cur], b.ld[l], nullptr, set.t_indptr, set.t_indices, set.norm,
-                                set.tile_row0, set.tile_nrows, set.tile_task, set.n_tiles, set.n_tasks,
-                                W + m.w_off[l], stride, m.f_out[l], 1, nullptr, 0, m.f_out[l], m.f_in[l], 0,
-                                act[l - 1], dz[cur ^ 1], b.ld[l - 1], a->impl, b.layer_ws, b.layer_ws_bytes, s));
+        // ReLU of the layer below (features carry no gradient, so layer 0 stops here).  Sparse:
+        // only rows with an out-edge into an active row of layer l are computed, reading the
+        // compact dZ_l through row_pos[l] (inactive out-neighbours are dropped).
+        run(gmeta_gcn_layer_fwd(dz[cur], b.ld[l], sparse ? set.row_pos[l] : nullptr,
+                                sparse ? set.act_rows[l - 1] : nullptr, set.t_indptr, set.t_indices, set.norm,
+                                sparse ? set.act_tile_row0[l - 1] : set.tile_row0,
+                                sparse ? set.act_tile_nrows[l - 1] : set.tile_nrows,
+                                sparse ? set.act_tile_task[l - 1] : set.tile_task,
+                                sparse ? set.n_act_tiles[l - 1] : set.n_tiles, set.n_tasks, W + m.w_off[l], stride,
+                                m.f_out[l], 1, nullptr, 0, m.f_out[l], m.f_in[l], 0, act[l - 1], dz[cur ^ 1],
+                                b.ld[l - 1], a->impl, b.layer_ws, b.layer_ws_bytes, s));
         cur ^= 1;
       }
     }
@@ -220,6 +237,13 @@ extern "C" int gmeta_maml_step(const gmeta_step_args_t* a, void* stream) {
   r.run(gmeta_degree_norm(qr.indptr, qr.n_nodes, qr.norm, s));
   r.run(gmeta_proto_label_prep(sp.labels, sp.task_sub_ptr, T, sp.class_pos, sp.class_occ, sp.n_classes, s));
   r.run(gmeta_proto_label_prep(qr.labels, qr.task_sub_ptr, T, qr.class_pos, qr.class_occ, qr.n_classes, s));
+  if (!a->dense_backward) {   // row -> position maps of the active-row lists (structure only: once per step)
+    for (int l = 0; l < m.n_layers; ++l) {
+      r.run(gmeta_build_row_pos(sp.act_rows[l], sp.n_act[l], sp.n_nodes, sp.row_pos[l], s));
+      if (a->compute_meta_grad)
+        r.run(gmeta_build_row_pos(qr.act_rows[l], qr.n_act[l], qr.n_nodes, qr.row_pos[l], s));
+    }
+  }
 
   for (int k = 0; k < K && r.ok(); ++k) {
     const float* Wcur = k == 0 ? a->theta : b.fast[(k - 1) & 1];

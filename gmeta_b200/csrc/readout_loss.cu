@@ -60,7 +60,7 @@ __global__ void readout_linear_bwd_kernel(const float* __restrict__ H, int ld_h,
                                           int n_out, const float* __restrict__ dlogits,
                                           float* __restrict__ dWlin, long long dw_stride,
                                           float* __restrict__ dblin, long long db_stride,
-                                          float* __restrict__ dZ) {
+                                          const int32_t* __restrict__ row_pos, float* __restrict__ dZ) {
   const int t = blockIdx.x;
   const int s0 = task_sub_ptr[t], s1 = task_sub_ptr[t + 1];
   const int width = cps * hid;
@@ -90,7 +90,8 @@ __global__ void readout_linear_bwd_kernel(const float* __restrict__ H, int ld_h,
       if (H[row * ld_h + kk] > 0.f) {  // ReLU of the last GCN layer (learner.py:53-54)
         float g = 0.f;
         for (int c = 0; c < n_out; ++c) g = fmaf(dlogits[(size_t)s * n_out + c], W[(size_t)c * width + k], g);
-        atomicAdd(dZ + row * ld_h + kk, g);  // both endpoints of a pair may name the same row
+        const size_t orow = row_pos ? (size_t)row_pos[row] : row;   // compact row of the active-row list
+        atomicAdd(dZ + orow * ld_h + kk, g);  // both endpoints of a pair may name the same row
       }
     }
   }
@@ -301,8 +302,8 @@ extern "C" int gmeta_readout_linear_fwd(const float* H, int32_t ld_h, int32_t hi
   return check_launch();
 }
 
-extern "C" int gmeta_readout_linear_bwd(const float* H, int32_t ld_h, int32_t hid, int32_t n_nodes,
-                                        const int32_t* centre_row, int32_t cps,
+extern "C" int gmeta_readout_linear_bwd(const float* H, int32_t ld_h, int32_t hid, int32_t n_dz_rows,
+                                        const int32_t* row_pos, const int32_t* centre_row, int32_t cps,
                                         const int32_t* task_sub_ptr, int32_t n_tasks,
                                         int32_t n_subgraphs, const float* Wlin, int64_t w_task_stride,
                                         int32_t n_out, const float* dlogits, float* dWlin,
@@ -310,13 +311,32 @@ extern "C" int gmeta_readout_linear_bwd(const float* H, int32_t ld_h, int32_t hi
                                         float* dZ, void* stream) {
   if (!H || !centre_row || !task_sub_ptr || !Wlin || !dlogits || !dWlin || !dblin || !dZ)
     return GMETA_ERR_BAD_ARG;
-  if (hid <= 0 || ld_h < hid || (cps != 1 && cps != 2) || n_tasks <= 0 || n_out <= 0 || n_nodes < 0)
+  if (hid <= 0 || ld_h < hid || (cps != 1 && cps != 2) || n_tasks <= 0 || n_out <= 0 || n_dz_rows < 0)
     return GMETA_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
-  if (cudaMemsetAsync(dZ, 0, (size_t)n_nodes * ld_h * sizeof(float), s) != cudaSuccess) return GMETA_ERR_LAUNCH;
+  if (cudaMemsetAsync(dZ, 0, (size_t)n_dz_rows * ld_h * sizeof(float), s) != cudaSuccess) return GMETA_ERR_LAUNCH;
   readout_linear_bwd_kernel<<<dim3(n_tasks, 2), 256, 0, s>>>(H, ld_h, hid, centre_row, cps, task_sub_ptr,
                                                             Wlin, w_task_stride, n_out, dlogits, dWlin,
-                                                            dw_task_stride, dblin, db_task_stride, dZ);
+                                                            dw_task_stride, dblin, db_task_stride, row_pos, dZ);
+  return check_launch();
+}
+
+namespace gmeta {
+namespace {
+__global__ void scatter_row_pos_kernel(const int32_t* __restrict__ rows, int n_rows, int32_t* __restrict__ row_pos) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += gridDim.x * blockDim.x) row_pos[rows[i]] = i;
+}
+}  // namespace
+}  // namespace gmeta
+
+extern "C" int gmeta_build_row_pos(const int32_t* rows, int32_t n_rows, int32_t n_nodes, int32_t* row_pos,
+                                   void* stream) {
+  if (n_rows < 0 || n_nodes < 0 || (n_nodes > 0 && !row_pos) || (n_rows > 0 && !rows)) return GMETA_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n_nodes == 0) return GMETA_OK;
+  if (cudaMemsetAsync(row_pos, 0xFF, (size_t)n_nodes * sizeof(int32_t), s) != cudaSuccess) return GMETA_ERR_LAUNCH;
+  if (n_rows == 0) return GMETA_OK;
+  scatter_row_pos_kernel<<<ceil_div(n_rows, 256), 256, 0, s>>>(rows, n_rows, row_pos);
   return check_launch();
 }
 

@@ -148,7 +148,7 @@ class _ClassifierFn(torch.autograd.Function):
             nb = L.gmeta_gcn_layer_fwd_workspace_bytes(1, 0, fi, fo, impl)
             scratch = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
             _lib.check(L.gmeta_gcn_layer_fwd(
-                _ptr(inp), ld_in, None, _ptr(dg.indptr), _ptr(dg.indices), _ptr(dg.norm),
+                _ptr(inp), ld_in, None, None, _ptr(dg.indptr), _ptr(dg.indices), _ptr(dg.norm),
                 _ptr(dg.tile_row0), _ptr(dg.tile_nrows), _ptr(dg.tile_task), dg.n_tiles, 1,
                 _ptr(ws[2 * l]), 0, fo, 0, _ptr(ws[2 * l + 1]), 0, fi, fo, 1, None, _ptr(out), ld_out,
                 impl, _ptr(scratch), nb, _stream()), "gcn_layer_fwd")
@@ -175,7 +175,7 @@ class _ClassifierFn(torch.autograd.Function):
         ld_top = acts[-1].shape[1]
         dz = torch.empty(dg.N, ld_top, dtype=torch.float32, device=dev)
         _lib.check(L.gmeta_readout_linear_bwd(
-            _ptr(acts[-1]), ld_top, spec.hid, dg.N, _ptr(ctx.centre_row), cps, _ptr(dg.task_sub_ptr), 1, dg.S,
+            _ptr(acts[-1]), ld_top, spec.hid, dg.N, None, _ptr(ctx.centre_row), cps, _ptr(dg.task_sub_ptr), 1, dg.S,
             _ptr(ws[2 * n_conv]), 0, spec.n_out, _ptr(dlogits), _ptr(grads[2 * n_conv]), 0,
             _ptr(grads[2 * n_conv + 1]), 0, _ptr(dz), _stream()), "readout_linear_bwd")
         for l in range(n_conv - 1, -1, -1):
@@ -184,7 +184,7 @@ class _ClassifierFn(torch.autograd.Function):
             nbytes = L.gmeta_gcn_layer_wgrad_workspace_bytes(1, fi, fo)
             wsb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             _lib.check(L.gmeta_gcn_layer_wgrad(
-                _ptr(inp), inp.shape[1], None, _ptr(dg.indptr), _ptr(dg.indices), _ptr(dg.norm),
+                _ptr(inp), inp.shape[1], None, None, _ptr(dg.indptr), _ptr(dg.indices), _ptr(dg.norm),
                 _ptr(dg.task_row_ptr), 1, _ptr(dz), dz.shape[1], fi, fo, _ptr(grads[2 * l]), 0,
                 _ptr(grads[2 * l + 1]), 0, _ptr(wsb), nbytes, _stream()), "gcn_layer_wgrad")
             if l > 0:
@@ -193,7 +193,7 @@ class _ClassifierFn(torch.autograd.Function):
                 nb = L.gmeta_gcn_layer_fwd_workspace_bytes(1, 0, fo, fi, ctx.impl)
                 scratch = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
                 _lib.check(L.gmeta_gcn_layer_fwd(
-                    _ptr(dz), dz.shape[1], None, _ptr(dg.t_indptr), _ptr(dg.t_indices), _ptr(dg.norm),
+                    _ptr(dz), dz.shape[1], None, None, _ptr(dg.t_indptr), _ptr(dg.t_indices), _ptr(dg.norm),
                     _ptr(dg.tile_row0), _ptr(dg.tile_nrows), _ptr(dg.tile_task), dg.n_tiles, 1,
                     _ptr(ws[2 * l]), 0, fo, 1, None, 0, fo, fi, 0, _ptr(acts[l - 1]), _ptr(dz_lo), ld_lo,
                     ctx.impl, _ptr(scratch), nb, _stream()), "gcn_layer dgrad")

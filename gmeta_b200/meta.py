@@ -202,6 +202,9 @@ class Meta(nn.Module):
         self.update_step = args.update_step
         self.update_step_test = args.update_step_test
         self.impl = getattr(args, 'impl', _lib.IMPL_AUTO)
+        # False (default): the backward skips rows whose gradient is structurally zero (only centre
+        # rows are read out); True: back-propagate over every row like the reference's autograd.
+        self.dense_backward = bool(getattr(args, 'dense_backward', False))
 
         self.net = Classifier(config, impl=self.impl)
         self.net = self.net.to(device)
@@ -257,6 +260,11 @@ class Meta(nn.Module):
         cs.class_pos = self._buf(tag + "cpos", (ps.S,), torch.int32, dev).data_ptr()
         cs.class_occ = self._buf(tag + "cocc", (ps.S,), torch.int32, dev).data_ptr()
         cs.n_classes = self._buf(tag + "ncls", (ps.T,), torch.int32, dev).data_ptr()
+        for l in range(ps.n_layers):
+            cs.n_act[l], cs.n_act_tiles[l] = ps.act[l]["n"], ps.act[l]["n_tiles"]
+            for k in ("act_rows", "act_task_ptr", "act_tile_row0", "act_tile_nrows", "act_tile_task"):
+                getattr(cs, k)[l] = base_ptr + 4 * ps.off["%s%d" % (k, l)]
+            cs.row_pos[l] = self._buf("%srow_pos%d" % (tag, l), (ps.N,), torch.int32, dev).data_ptr()
         return cs
 
     def upload_batch(self, batch, feat, own_buffer=False):
@@ -273,8 +281,9 @@ class Meta(nn.Module):
         if db.ft.f0 != self.spec.conv[0][0]:
             raise RuntimeError("feature width %d does not match the first GraphConv (%d)"
                                % (db.ft.f0, self.spec.conv[0][0]))
-        db.ps_s = packing.plan_set(x_spt, c_spt, 0)
-        db.ps_q = packing.plan_set(x_qry, c_qry, db.ps_s.end)
+        L = len(self.spec.conv)
+        db.ps_s = packing.plan_set(x_spt, c_spt, 0, L)
+        db.ps_q = packing.plan_set(x_qry, c_qry, db.ps_s.end, L)
         if self._staging is None or self._staging.device != dev:
             self._staging = packing.Staging(dev)
         buf = self._staging.reserve(db.ps_q.end)
@@ -311,6 +320,7 @@ class Meta(nn.Module):
         a.update_lr = self.update_lr
         a.grad_scale = 1.0 / (self._global_task_num(T) if train else 1)
         a.compute_meta_grad = 1 if train else 0
+        a.dense_backward = 1 if self.dense_backward else 0
         a.impl = self.impl
         P = self.spec.n_params_padded
         meta_grad = self._buf("meta_grad", (P,), torch.float32, dev) if train else None

@@ -35,7 +35,33 @@ def _flat_ids(node_ids):
     return np.concatenate([np.asarray(x, dtype=np.int64) for x in node_ids])
 
 
-def plan_set(graphs, centres, off0):
+def _rows_concat(indptr, indices, rows):
+    """Concatenated in-neighbour lists of `rows` of a CSR-by-destination graph."""
+    lo = indptr[rows].astype(np.int64)
+    cnt = indptr[rows + 1].astype(np.int64) - lo
+    tot = int(cnt.sum())
+    if tot == 0:
+        return np.zeros(0, dtype=np.int64)
+    starts = np.repeat(lo - np.concatenate([[0], np.cumsum(cnt)[:-1]]), cnt)
+    return indices[starts + np.arange(tot, dtype=np.int64)].astype(np.int64)
+
+
+def active_rows(g, centre, n_layers):
+    """Rows of one task's batched graph where dL/dZ_l can be non-zero, per GCN layer l: only the
+    centre rows are read out (learner.py:166-170), so act[L-1] = centres and act[l-1] = the
+    in-neighbours of act[l].  Local (task-relative) sorted row ids."""
+    c = centre.numpy() if hasattr(centre, "numpy") else np.asarray(centre)
+    sub_first = np.concatenate([[0], np.cumsum(g.batch_num_nodes)])[:-1]
+    rows = np.unique((c.astype(np.int64) + (sub_first[:, None] if c.ndim == 2 else sub_first)).reshape(-1))
+    out = [None] * n_layers
+    out[n_layers - 1] = rows
+    for l in range(n_layers - 1, 0, -1):
+        rows = np.unique(_rows_concat(g.indptr, g.indices, rows))
+        out[l - 1] = rows
+    return out
+
+
+def plan_set(graphs, centres, off0, n_layers=0):
     """Sizes and segment offsets for one set (spt or qry) of all tasks."""
     ps = PackedSetHost()
     ps.T = len(graphs)
@@ -55,8 +81,27 @@ def plan_set(graphs, centres, off0):
              "tile_row0": ps.n_tiles, "tile_nrows": ps.n_tiles, "tile_task": ps.n_tiles,
              "task_row_ptr": ps.T + 1, "task_sub_ptr": ps.T + 1, "centre_row": ps.S * ps.cps,
              "feat_row": ps.N, "labels": ps.S}
+    # active rows of the backward pass (per layer), their task pointers and tile tables
+    ps.n_layers = n_layers
+    ps.act = []
+    for l in range(n_layers):
+        ps.act.append({})
+    if n_layers:
+        per_task = [active_rows(g, c, n_layers) for g, c in zip(graphs, centres)]
+        for l in range(n_layers):
+            cnt = np.array([pt[l].shape[0] for pt in per_task], dtype=np.int64)
+            tptr = np.concatenate([[0], np.cumsum(cnt)])
+            rows = (np.concatenate([pt[l] + ps.node_off[t] for t, pt in enumerate(per_task)])
+                    if ps.T else np.zeros(0, dtype=np.int64))
+            tiles = tile_table(tptr)
+            ps.act[l] = {"rows": rows, "task_ptr": tptr, "tiles": tiles, "n": int(tptr[-1]),
+                         "n_tiles": int(tiles[0].shape[0])}
+            sizes["act_rows%d" % l] = ps.act[l]["n"]
+            sizes["act_task_ptr%d" % l] = ps.T + 1
+            for k in ("act_tile_row0", "act_tile_nrows", "act_tile_task"):
+                sizes["%s%d" % (k, l)] = ps.act[l]["n_tiles"]
     off = off0
-    for k in _SEGS:
+    for k in sizes:
         ps.off[k] = off
         off += _al(sizes[k])
     ps.sizes = sizes
@@ -104,6 +149,12 @@ def fill_set(buf, ps, graphs, labels, centres, node_ids, graph_idx, graph_row_of
     buf[o["tile_task"]:o["tile_task"] + ps.n_tiles] = ps.tiles[2]
     buf[o["task_row_ptr"]:o["task_row_ptr"] + ps.T + 1] = ps.node_off
     buf[o["task_sub_ptr"]:o["task_sub_ptr"] + ps.T + 1] = ps.sub_off
+    for l in range(ps.n_layers):
+        a = ps.act[l]
+        buf[o["act_rows%d" % l]:o["act_rows%d" % l] + a["n"]] = a["rows"]
+        buf[o["act_task_ptr%d" % l]:o["act_task_ptr%d" % l] + ps.T + 1] = a["task_ptr"]
+        for k, arr in zip(("act_tile_row0", "act_tile_nrows", "act_tile_task"), a["tiles"]):
+            buf[o["%s%d" % (k, l)]:o["%s%d" % (k, l)] + a["n_tiles"]] = arr
 
 
 def validate_labels(y_spt, y_qry, k_spt):

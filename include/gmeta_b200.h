@@ -74,6 +74,18 @@ typedef struct gmeta_packed_set {
   int32_t* class_pos;            /* [S] rank of the label among the task's sorted unique labels */
   int32_t* class_occ;            /* [S] how many earlier subgraphs of the task share the label */
   int32_t* n_classes;            /* [T] */
+  /* Active rows of the backward pass, per GCN layer l (0-based): the rows where dL/dZ_l can be
+   * non-zero.  Only the centre rows are read out (learner.py:166-170), so act[L-1] = the centre
+   * rows and act[l-1] = the in-neighbours of act[l]; every other row of dZ_l is structurally 0
+   * and the backward kernels skip it (exact).  Sorted by row, tasks contiguous. */
+  int32_t n_act[GMETA_MAX_LAYERS];
+  int32_t n_act_tiles[GMETA_MAX_LAYERS];
+  const int32_t* act_rows[GMETA_MAX_LAYERS];       /* [n_act]  packed row ids */
+  const int32_t* act_task_ptr[GMETA_MAX_LAYERS];   /* [T+1]    into act_rows */
+  const int32_t* act_tile_row0[GMETA_MAX_LAYERS];  /* tile table over positions of act_rows */
+  const int32_t* act_tile_nrows[GMETA_MAX_LAYERS];
+  const int32_t* act_tile_task[GMETA_MAX_LAYERS];
+  int32_t* row_pos[GMETA_MAX_LAYERS];              /* [N] scratch: row -> position in act_rows or -1 */
 } gmeta_packed_set_t;
 
 /* Model topology = the reference's `config` list (train.py:67-75, learner.py:81-97) flattened.
@@ -101,18 +113,21 @@ int gmeta_degree_norm(const int32_t* indptr, int32_t n_nodes, float* norm, void*
 /* One fused GCN layer over a packed set (replaces GraphConv.forward, learner.py:25-56, and the
  * features gather of meta.py:119-120 when in_row_map != NULL):
  *   M[v,:]   = sum_{u in indices[indptr[v]:indptr[v+1]]} norm[u] * in[map(u), :f_in]
- *   out[v,j] = act( norm[v] * sum_k M[v,k] * B[k,j] + bias[j] ),   j < f_out
+ *   out[i,j] = act( norm[v] * sum_k M[v,k] * B[k,j] + bias[j] ),   j < f_out
+ * where i runs over the tile rows and v = dst_rows ? dst_rows[i] : i (dst_rows selects a subset
+ * of rows and makes `out` compact); map(u) = in_row_map ? in_row_map[u] : u, and a negative
+ * in_row_map entry drops that neighbour;
  * with B[k,j] = W[k*ldw + j] (trans_w == 0) or W[j*ldw + k] (trans_w != 0), W/bias taken from
  * task t = tile_task[tile] at W + t*w_task_stride / bias + t*b_task_stride (stride 0 = shared),
  * act = ReLU iff relu != 0; if relu_mask != NULL the result is zeroed where relu_mask[v,j] <= 0
- * (ld_out layout).  Columns [f_out, round_up(f_out,4)) of out are written as 0.
+ * (ld_out layout, indexed by the real row v).  Columns [f_out, round_up(f_out,4)) of out are written as 0.
  * The same entry point run on (t_indptr, t_indices) with trans_w=1, bias=NULL, relu=0 and
  * relu_mask = the lower layer's activations is the layer's data-gradient.
  * impl: GMETA_IMPL_SIMT (fp32 FFMA, any shape), GMETA_IMPL_TCGEN05 (tcgen05.mma 3xTF32 with TMEM
  * accumulators; needs f_in % 32 == 0, f_out % 16 == 0, f_out <= 256, ld % 4 == 0 and the
  * workspace below) or GMETA_IMPL_AUTO. */
 int gmeta_gcn_layer_fwd(const float* in, int32_t ld_in, const int32_t* in_row_map,
-                        const int32_t* indptr, const int32_t* indices, const float* norm,
+                        const int32_t* dst_rows, const int32_t* indptr, const int32_t* indices, const float* norm,
                         const int32_t* tile_row0, const int32_t* tile_nrows,
                         const int32_t* tile_task, int32_t n_tiles, int32_t n_tasks,
                         const float* W, int64_t w_task_stride, int32_t ldw, int32_t trans_w,
@@ -131,10 +146,12 @@ int64_t gmeta_gcn_layer_fwd_workspace_bytes(int32_t n_tasks, int64_t w_task_stri
  * M as in gmeta_gcn_layer_fwd (re-gathered, not stored).  dZ is the gradient w.r.t. the
  * pre-activation (already ReLU-masked).  dW / db are written (not accumulated) at
  * dW + t*dw_task_stride (row-major [f_in, f_out], ld = f_out) and db + t*db_task_stride.
- * Deterministic: row-range partials in `workspace` are summed in a fixed order. */
+ * Deterministic: row-range partials in `workspace` are summed in a fixed order.
+ * With dst_rows != NULL the sums run over the listed rows only (task_row_ptr then indexes the
+ * list and dZ is compact: row i of dZ belongs to row dst_rows[i]). */
 int64_t gmeta_gcn_layer_wgrad_workspace_bytes(int32_t n_tasks, int32_t f_in, int32_t f_out);
 int gmeta_gcn_layer_wgrad(const float* in, int32_t ld_in, const int32_t* in_row_map,
-                          const int32_t* indptr, const int32_t* indices, const float* norm,
+                          const int32_t* dst_rows, const int32_t* indptr, const int32_t* indices, const float* norm,
                           const int32_t* task_row_ptr, int32_t n_tasks,
                           const float* dZ, int32_t ld_dz, int32_t f_in, int32_t f_out,
                           float* dW, int64_t dw_task_stride, float* db, int64_t db_task_stride,
@@ -152,15 +169,20 @@ int gmeta_readout_linear_fwd(const float* H, int32_t ld_h, int32_t hid,
 
 /* Backward of the above plus the ReLU mask of the last GCN layer:
  *   dWlin[t][c,k] = sum_s dlogits[s,c] r_s[k];  dblin[t][c] = sum_s dlogits[s,c];
- *   dZ[N, ld_h] = 0 everywhere except dZ[centre rows] += (H > 0) ? dlogits[s,:] . Wlin[t][:,k] : 0. */
-int gmeta_readout_linear_bwd(const float* H, int32_t ld_h, int32_t hid, int32_t n_nodes,
-                             const int32_t* centre_row, int32_t centres_per_subgraph,
+ *   dZ[n_dz_rows, ld_h] = 0 everywhere except dZ[pos(centre rows)] += (H > 0) ? dlogits[s,:] . Wlin[t][:,k] : 0
+ * with pos(v) = row_pos ? row_pos[v] : v (row_pos: compact dZ over the active rows). */
+int gmeta_readout_linear_bwd(const float* H, int32_t ld_h, int32_t hid, int32_t n_dz_rows,
+                             const int32_t* row_pos, const int32_t* centre_row, int32_t centres_per_subgraph,
                              const int32_t* task_sub_ptr, int32_t n_tasks, int32_t n_subgraphs,
                              const float* Wlin, int64_t w_task_stride, int32_t n_out,
                              const float* dlogits,
                              float* dWlin, int64_t dw_task_stride,
                              float* dblin, int64_t db_task_stride,
                              float* dZ, void* stream);
+
+/* row_pos[0..n_nodes) = -1, then row_pos[rows[i]] = i  (row -> position in an active-row list). */
+int gmeta_build_row_pos(const int32_t* rows, int32_t n_rows, int32_t n_nodes, int32_t* row_pos,
+                        void* stream);
 
 /* class_pos / class_occ / n_classes from raw labels, per task (the `torch.unique` +
  * `eq(c).nonzero()` bookkeeping of meta.py:32-42,60-66), on device. */
@@ -234,6 +256,8 @@ typedef struct gmeta_step_args {
   float update_lr;
   float grad_scale;              /* 1 / global task_num (meta.py:161) */
   int32_t compute_meta_grad;     /* 1: training step; 0: finetunning (no backward of the query loss) */
+  int32_t dense_backward;        /* 1: back-propagate over every row like the reference's autograd;
+                                    0: skip the structurally-zero rows (packed set's act_* lists) */
   int32_t impl;                  /* GMETA_IMPL_* for the GCN layers */
   /* outputs */
   float* meta_grad;              /* [P] sum over this call's tasks of d(grad_scale*loss_q^K)/d(theta) */

@@ -60,31 +60,34 @@ class DevGraph(object):
 
 
 def layer_fwd(g, x, W, b, f_in, f_out, relu=1, transposed=False, trans_w=0, mask=None, row_map=None,
-              w_stride=0, b_stride=0, ldw=None, impl=_lib.IMPL_SIMT, ld_out=None):
+              w_stride=0, b_stride=0, ldw=None, impl=_lib.IMPL_SIMT, ld_out=None, dst_rows=None, tiles=None):
+    """tiles = (row0, nrows, task) device tensors over the compact row list when dst_rows is given."""
     ld_out = ld_out or (f_out + 3) // 4 * 4
-    out = torch.full((g.n, ld_out), float('nan'), dtype=torch.float32, device=dev())
+    n_out_rows = g.n if dst_rows is None else dst_rows.shape[0]
+    out = torch.full((n_out_rows, ld_out), float('nan'), dtype=torch.float32, device=dev())
+    t_row0, t_nrows, t_task = (g.tile_row0, g.tile_nrows, g.tile_task) if tiles is None else tiles
     ip, ix = (g.t_indptr, g.t_indices) if transposed else (g.indptr, g.indices)
     if ldw is None:
         ldw = f_in if trans_w else f_out
     nb = _lib.lib().gmeta_gcn_layer_fwd_workspace_bytes(g.T, w_stride, f_in, f_out, impl)
     ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev())
-    rc = _lib.lib().gmeta_gcn_layer_fwd(p(x), x.shape[1], p(row_map), p(ip), p(ix), p(g.norm), p(g.tile_row0),
-                                        p(g.tile_nrows), p(g.tile_task), g.n_tiles, g.T, p(W), w_stride, ldw,
+    rc = _lib.lib().gmeta_gcn_layer_fwd(p(x), x.shape[1], p(row_map), p(dst_rows), p(ip), p(ix), p(g.norm), p(t_row0),
+                                        p(t_nrows), p(t_task), t_row0.shape[0], g.T, p(W), w_stride, ldw,
                                         trans_w, p(b), b_stride, f_in, f_out, relu, p(mask), p(out), ld_out, impl,
                                         p(ws), nb, stream())
     _lib.check(rc, "gcn_layer_fwd")
     return out
 
 
-def layer_wgrad(g, x, dz, f_in, f_out, row_map=None):
+def layer_wgrad(g, x, dz, f_in, f_out, row_map=None, dst_rows=None, task_ptr=None):
     L = _lib.lib()
     T = g.T
     dW = torch.full((T, f_in, f_out), float('nan'), dtype=torch.float32, device=dev())
     db = torch.full((T, f_out), float('nan'), dtype=torch.float32, device=dev())
     nbytes = L.gmeta_gcn_layer_wgrad_workspace_bytes(T, f_in, f_out)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev())
-    rc = L.gmeta_gcn_layer_wgrad(p(x), x.shape[1], p(row_map), p(g.indptr), p(g.indices), p(g.norm),
-                                 p(g.task_row_ptr), T, p(dz), dz.shape[1], f_in, f_out, p(dW), f_in * f_out, p(db),
+    rc = L.gmeta_gcn_layer_wgrad(p(x), x.shape[1], p(row_map), p(dst_rows), p(g.indptr), p(g.indices), p(g.norm),
+                                 p(g.task_row_ptr if task_ptr is None else task_ptr), T, p(dz), dz.shape[1], f_in, f_out, p(dW), f_in * f_out, p(db),
                                  f_out, p(ws), nbytes, stream())
     _lib.check(rc, "gcn_layer_wgrad")
     return dW, db

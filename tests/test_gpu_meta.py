@@ -21,12 +21,13 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 LOGIT_TOL = 1e-4
 
 
-def _meta_from_golden(kind, impl=_lib.IMPL_AUTO):
+def _meta_from_golden(kind, impl=_lib.IMPL_AUTO, dense_backward=False):
     from gmeta_b200.meta import Meta
     d = np.load(os.path.join(GOLD, "meta_%s.npz" % kind))
     ds = H.tiny_dataset(kind)
     args = ds.args()
     args.impl = impl
+    args.dense_backward = dense_backward
     m = Meta(args, ds.config()).to(U.dev())
     with torch.no_grad():
         for k, p in enumerate(m.net.parameters()):
@@ -35,11 +36,15 @@ def _meta_from_golden(kind, impl=_lib.IMPL_AUTO):
     return m, d, H.unpack_meta_batch(d), feats
 
 
+@pytest.mark.parametrize("impl", [_lib.IMPL_AUTO, _lib.IMPL_SIMT])
+@pytest.mark.parametrize("dense_backward", [False, True])
 @pytest.mark.parametrize("kind", H.TINY_KINDS)
-def test_meta_forward_matches_reference_golden(kind):
+def test_meta_forward_matches_reference_golden(kind, dense_backward, impl):
     """Meta.forward == the reference's: accuracy vector identical, meta-gradient and step-0 support
-    logits within tolerance, second step (Adam state carried) accuracies identical."""
-    m, d, mb, feats = _meta_from_golden(kind)
+    logits within tolerance, second step (Adam state carried) accuracies identical.  Both backward
+    formulations (every row like autograd / structurally non-zero rows only) and both layer
+    implementations (auto = tcgen05 where the shape allows / FFMA)."""
+    m, d, mb, feats = _meta_from_golden(kind, impl, dense_backward)
     m.return_meta_grad = True
     m.keep_logits_spt0 = True
     accs = m(*mb, feats)

@@ -203,6 +203,51 @@ def test_layer_wgrad_and_dgrad_multitask(shape):
     U.report("dX masked", dxm[:, :f_in], grads[0] * (mask[:, :f_in].cpu() > 0), 1e-4, 1e-4)
 
 
+@pytest.mark.parametrize("impl", IMPLS)
+def test_layer_on_row_subset_with_dropped_neighbours(impl):
+    """dst_rows (compute a subset of rows, compact output) and negative in_row_map entries
+    (neighbour dropped) -- the two hooks the structurally-sparse backward uses."""
+    f_in, f_out = 64, 32
+    rng = np.random.default_rng(77)
+    T = 3
+    g, src, dst, trp, x, W, b, _, _ = _random_multitask(rng, T, 600, 3.0, f_in, f_out)
+    N = int(trp[-1])
+    # compact input: only ~30% of the rows exist in `xc`; the others are dropped neighbours
+    keep = rng.random(N) < 0.3
+    pos = np.full(N, -1, dtype=np.int64)
+    pos[keep] = np.arange(int(keep.sum()))
+    xc = x[keep]
+    # rows to compute: a random subset per task, sorted; tile table over the compact list
+    sel = np.sort(rng.choice(N, 500, replace=False))
+    tptr = np.searchsorted(sel, trp)
+    from gmeta_b200.learner import tile_table
+    row0, nrows, task = tile_table(tptr)
+    tiles = (U.i32(row0), U.i32(nrows), U.i32(task))
+    mask = rng.standard_normal((N, f_out), dtype=np.float32)
+    try:
+        y = U.layer_fwd(g, U.f32(xc), U.f32(W), U.f32(b), f_in, f_out, relu=0, row_map=U.i32(pos), w_stride=f_in * f_out,
+                        b_stride=f_out, impl=impl, dst_rows=U.i32(sel), tiles=tiles, mask=U.f32(mask))
+    except _lib.GMetaError:
+        if impl == _lib.IMPL_TCGEN05:
+            pytest.skip("shape not covered by the tcgen05 path")
+        raise
+    xz = np.where(keep[:, None], x, 0.0).astype(np.float32)        # dropped neighbour == zero row
+    want, _, _ = _oracle_multitask(src, dst, trp, xz, W, b, relu=False)
+    want = (want * (torch.tensor(mask) > 0))[sel]
+    atol, rtol = TOL[impl]
+    U.report("row subset + dropped neighbours", y[:, :f_out], want, atol, rtol)
+    # weight gradient over the same row subset
+    dz = rng.standard_normal((sel.shape[0], f_out), dtype=np.float32)
+    dW, db = U.layer_wgrad(g, U.f32(xc), U.f32(dz), f_in, f_out, row_map=U.i32(pos), dst_rows=U.i32(sel), task_ptr=U.i32(tptr))
+    og = O.OGraph(src, dst, N)
+    norm = torch.pow(og.in_degrees().float().clamp(min=1), -0.5).unsqueeze(1)
+    M = og.aggregate_sum(torch.tensor(xz) * norm) * norm
+    for t in range(T):
+        a, e = int(tptr[t]), int(tptr[t + 1])
+        U.report("dW[%d] over row subset" % t, dW[t], M[sel[a:e]].T @ torch.tensor(dz[a:e]), 1e-4, 1e-4)
+        U.report("db[%d] over row subset" % t, db[t], torch.tensor(dz[a:e]).sum(0), 1e-4, 1e-4)
+
+
 @pytest.mark.parametrize("cps", [1, 2])
 def test_readout_linear_forward_backward(cps):
     L = _lib.lib()
@@ -235,12 +280,22 @@ def test_readout_linear_forward_backward(cps):
     dW = torch.empty(T, C, hid * cps, device=U.dev())
     db = torch.empty(T, C, device=U.dev())
     dZ = torch.full((N, hid), float('nan'), device=U.dev())
-    _lib.check(L.gmeta_readout_linear_bwd(U.p(Hd), hid, hid, N, U.p(U.i32(centre)), cps, U.p(U.i32(tsp)), T, S,
+    _lib.check(L.gmeta_readout_linear_bwd(U.p(Hd), hid, hid, N, None, U.p(U.i32(centre)), cps, U.p(U.i32(tsp)), T, S,
                                           U.p(U.f32(Wl)), C * hid * cps, C, U.p(U.f32(dl.numpy())), U.p(dW),
                                           C * hid * cps, U.p(db), C, U.p(dZ), U.stream()))
     U.report("readout dWlin", dW, gW, 1e-5, 1e-5)
     U.report("readout dblin", db, gb, 1e-5, 1e-5)
     U.report("readout dZ (masked, scattered)", dZ, gH, 1e-5, 1e-5)
+    # compact variant: dZ only over the (unique) centre rows, addressed through row_pos
+    rows = np.unique(centre)
+    pos = torch.empty(N, dtype=torch.int32, device=U.dev())
+    _lib.check(L.gmeta_build_row_pos(U.p(U.i32(rows)), len(rows), N, U.p(pos), U.stream()))
+    dZc = torch.full((len(rows), hid), float('nan'), device=U.dev())
+    _lib.check(L.gmeta_readout_linear_bwd(U.p(Hd), hid, hid, len(rows), U.p(pos), U.p(U.i32(centre)), cps,
+                                          U.p(U.i32(tsp)), T, S, U.p(U.f32(Wl)), C * hid * cps, C,
+                                          U.p(U.f32(dl.numpy())), U.p(dW), C * hid * cps, U.p(db), C, U.p(dZc), U.stream()))
+    U.report("readout dZ compact", dZc, gH[torch.as_tensor(rows)], 1e-5, 1e-5)
+    assert float(gH.abs().sum()) == pytest.approx(float(gH[torch.as_tensor(rows)].abs().sum()))
 
 
 def test_proto_losses_vs_reference_golden():

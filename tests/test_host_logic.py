@@ -33,7 +33,7 @@ def test_c_abi_library_exports_every_declared_symbol():
 
 def test_ctypes_structs_match_header_layout():
     """sizeof of the mirrored structs (pointer/int layout) -- a drifted field would shift these."""
-    assert ctypes.sizeof(_lib.PackedSet) == 6 * 4 + 16 * 8
+    assert ctypes.sizeof(_lib.PackedSet) == 6 * 4 + 16 * 8 + 2 * 3 * 4 + 6 * 3 * 8
     assert ctypes.sizeof(_lib.Model) == 4 * (1 + 3 + 3 + 3 + 3 + 3 + 2)
     a = _lib.StepArgs()
     assert ctypes.sizeof(a) % 8 == 0 and _lib.StepArgs.workspace_bytes.offset + 8 == ctypes.sizeof(a)
@@ -138,6 +138,38 @@ def test_packing_layout(kind):
         assert np.array_equal(centre[tsp[t] * ps.cps:tsp[t + 1] * ps.cps], want_c)
         assert np.array_equal(labels[tsp[t]:tsp[t + 1]], yq[t].numpy())
     assert ps.cps == (2 if ds.link_pred else 1)
+
+
+@pytest.mark.parametrize("kind", H.TINY_KINDS)
+def test_active_rows_cover_every_row_with_a_gradient(kind):
+    """act[L-1] = centre rows, act[l-1] = in-neighbours of act[l]: checked against autograd on the
+    oracle -- every row of dL/dZ_l outside the list is exactly zero."""
+    from oracle import gmeta_oracle as O
+    ds = H.tiny_dataset(kind)
+    xs, ys, xq, yq, cs, cq, ns, nq, gs, gq = ds.sample_task(np.random.default_rng(3))
+    cfg = ds.config()
+    L = sum(1 for n, _ in cfg if n == 'GraphConv')
+    act = packing.active_rows(xq, cq, L)
+    torch.manual_seed(0)
+    params = O.init_params(cfg)
+    feat = O.gather_features(ds.feats, gq, nq)
+    g = H.to_ograph(xq)
+    # pre-activations of every layer with a hook on their gradient
+    hs, h, idx = [], feat, 0
+    for l in range(L):
+        norm = torch.pow(g.in_degrees().float().clamp(min=1), -0.5).unsqueeze(1)
+        z = (g.aggregate_sum(h * norm) @ params[idx]) * norm + params[idx + 1]
+        z.retain_grad()
+        hs.append(z)
+        h = torch.relu(z)
+        idx += 2
+    off = torch.cumsum(torch.LongTensor([0] + list(g.batch_num_nodes)), 0)[:-1]
+    r = torch.cat((h[cq[:, 0] + off], h[cq[:, 1] + off]), 1) if ds.link_pred else h[cq + off]
+    (r @ params[idx].T + params[idx + 1]).pow(2).sum().backward()
+    for l in range(L):
+        nz = np.nonzero(hs[l].grad.abs().sum(1).numpy())[0]
+        assert set(nz.tolist()) <= set(act[l].tolist()), (kind, l)
+        assert (np.diff(act[l]) > 0).all()
 
 
 def test_label_validation_mirrors_reference_errors():

@@ -63,7 +63,7 @@ def main():
         ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
 
         def launch():
-            _lib.check(L.gmeta_gcn_layer_fwd(x.data_ptr(), a.fin, None, d_indptr.data_ptr(), d_indices.data_ptr(),
+            _lib.check(L.gmeta_gcn_layer_fwd(x.data_ptr(), a.fin, None, None, d_indptr.data_ptr(), d_indices.data_ptr(),
                                              norm.data_ptr(), d_row0.data_ptr(), d_nrows.data_ptr(), d_task.data_ptr(),
                                              len(row0), a.tasks, W.data_ptr(), P, a.fout, 0,
                                              W.data_ptr() + 4 * a.fin * a.fout, P, a.fin, a.fout, 1, None,
