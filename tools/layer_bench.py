@@ -29,8 +29,24 @@ def synth(T, rows_per_task, block, deg, rng):
     return trp, indptr, src.astype(np.int32), N, e
 
 
+def real_c2(T, rng):
+    """Packed query set of T tasks of the C2 workload (skewed degrees, hubs)."""
+    from gmeta_b200 import packing
+    from gmeta_b200.synthetic import make_dataset
+    ds = make_dataset('C2')
+    mb = ds.sample_meta_batch(rng, T)
+    xq, cq = mb[2], mb[5]
+    ps = packing.plan_set(xq, cq, 0)
+    buf = np.zeros(ps.end, dtype=np.int32)
+    packing.fill_set(buf, ps, xq, mb[3], cq, mb[7], mb[9], np.array([0]))
+    o = ps.off
+    return (ps.node_off, buf[o["indptr"]:o["indptr"] + ps.N + 1].copy(), buf[o["indices"]:o["indices"] + ps.E].copy(),
+            ps.N, ps.E)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--real", action="store_true", help="use a real C2 query set instead of the uniform synthetic")
     ap.add_argument("--tasks", type=int, default=32)
     ap.add_argument("--rows", type=int, default=38000)
     ap.add_argument("--fin", type=int, default=256)
@@ -42,7 +58,10 @@ def main():
     L = _lib.lib()
     dev = torch.device("cuda")
     rng = np.random.default_rng(0)
-    trp, indptr, indices, N, E = synth(a.tasks, a.rows, 500, a.deg, rng)
+    if a.real:
+        trp, indptr, indices, N, E = real_c2(a.tasks, rng)
+    else:
+        trp, indptr, indices, N, E = synth(a.tasks, a.rows, 500, a.deg, rng)
     row0, nrows, task = tile_table(trp)
     i32 = lambda x: torch.as_tensor(np.ascontiguousarray(x, dtype=np.int32)).to(dev)  # noqa: E731
     d_indptr, d_indices, d_row0, d_nrows, d_task = i32(indptr), i32(indices), i32(row0), i32(nrows), i32(task)
