@@ -70,6 +70,8 @@ _SIGNATURES = {
     "gmeta_maml_step_workspace_bytes": (i64, [C.POINTER(StepArgs)]),
     "gmeta_maml_step": (C.c_int, [C.POINTER(StepArgs), vp]),
     "gmeta_last_launch_count": (C.c_int, []),
+    "gmeta_debug_set_tc_profile": (None, [vp]),
+    "gmeta_debug_set_tc_flags": (None, [C.c_int]),
 }
 
 _lib = None

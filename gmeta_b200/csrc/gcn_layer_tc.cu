@@ -33,9 +33,12 @@ constexpr int NTHREADS_TC = 22 * 32;
 constexpr int MAX_STAGES = 4;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_COLS = 256;           // columns per accumulator buffer
-constexpr int PRE = 4;                  // neighbours per row whose (row, norm) stay in registers
+constexpr int PRE = 2;                  // neighbours per row whose (row, norm) stay in registers
 constexpr int N_PROD_THREADS = N_PROD_WARPS * 32;
-constexpr int LCAP = 1024;              // long-edge records staged per window
+constexpr int LCAP = 512;               // long-edge records staged per window
+constexpr int EPI_LD = 20;              // floats per row of the epilogue transpose tile (16 + pad, conflict-free)
+constexpr int ST_TILES = 4;             // row tiles per super-tile (one prologue per super-tile)
+constexpr int ST_ROWS = ST_TILES * TM;  // 512 = one row per producer thread
 constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000LL;  // ~2 s: trap instead of hanging the GPU
 
 struct TcParams {
@@ -54,7 +57,9 @@ struct TcParams {
   float* out;
   int ld_out;
   int n_stages;
-  float* long_scratch;       // [gridDim.x][128][f_in] aggregated rows of long (hub) rows, L2 resident
+  int dbg;                   // debug ablation flags (0 in production): 1 skip output stores, 2 skip gather loads, 4 skip MMAs, 8 skip weight copies
+  long long* prof;           // optional [gridDim.x][16] cycle counters per role (debug), or NULL
+  float* long_scratch;       // per CTA: [ST_ROWS][f_in] aggregated long (hub) rows + 4096 floats of slice partials, L2 resident
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -141,19 +146,30 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 __device__ __forceinline__ float tf32_hi(float a) { return __uint_as_float(__float_as_uint(a) & 0xFFFFE000u); }
 
-// producer-side bookkeeping in shared memory (after the pipeline stages and barriers)
+// producer-side bookkeeping in shared memory (after the pipeline stages and barriers), for one
+// SUPER-TILE = ST_TILES consecutive row tiles whose structure-dependent prologue is done at once
 struct alignas(16) ProdSmem {
-  float part[2 * N_PROD_THREADS * 4];   // [group][continued-from-left | continues-right][f_in] partial sums
   int src[LCAP];                        // source row offset (elements) of each staged long edge
   float nrm[LCAP];                      // its norm
-  int beg[TM];                          // first edge of each tile row
-  int deg[TM];
-  int lpos[TM + 1];                     // start of each row in the flattened long-edge list
-  uint8_t row[LCAP];                    // tile row of each staged long edge
-  uint8_t is_long[TM];
+  int beg[ST_ROWS];                     // first edge of each row
+  int deg[ST_ROWS];
+  int lpos[ST_ROWS + 1];                // start of each row in the flattened long-edge list
+  int s_off[ST_ROWS][PRE];              // short rows: element offset of neighbour i's row
+  float s_nrm[ST_ROWS][PRE];            //             and its norm (0 = absent / dropped)
+  uint16_t row[LCAP];                   // super-tile row of each staged long edge
+  uint8_t is_long[ST_ROWS];
+  int wsum[N_PROD_WARPS];
+  float bias_s[2][ACC_COLS];            // bias of the tile's task, double buffered by tile parity
+  alignas(16) float epi[4][32 * EPI_LD];  // per epilogue warp: 32 rows x 16 columns, transposed on the way out
 };
 
 __device__ __forceinline__ void producer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N_PROD_THREADS) : "memory"); }
+
+// every role walks the tiles in the same order: super-tiles round-robin over CTAs, tiles inside
+#define TILE_LOOP_BEGIN                                                                        \
+  for (int st_ = blockIdx.x; st_ < (p.n_tiles + ST_TILES - 1) / ST_TILES; st_ += gridDim.x)    \
+    for (int tile = st_ * ST_TILES; tile < min((st_ + 1) * ST_TILES, p.n_tiles); ++tile) {
+#define TILE_LOOP_END }
 
 struct Smem {
   // dynamic shared memory, 1024-byte aligned: [stage][A_hi | A_lo | B_hi | B_lo], then barriers
@@ -225,57 +241,81 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const 
     const int tpr = f_in >> 2;                      // threads covering one full row (16 B each)
     const int G = N_PROD_THREADS / tpr;             // thread groups working on different edges
     const int g = tid / tpr, cu = tid - g * tpr;    // my group / my 16-byte column unit
-    float* scratch = p.long_scratch + (size_t)blockIdx.x * TM * f_in;
+    float* scratch = p.long_scratch + (size_t)blockIdx.x * ((size_t)ST_ROWS * f_in + 4 * N_PROD_THREADS * 2);
+    float* part = scratch + (size_t)ST_ROWS * f_in; // [group][from-left | to-right][f_in] slice partials
+    const int n_super = (p.n_tiles + ST_TILES - 1) / ST_TILES;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const int row0 = p.tile_row0[tile], nrows = p.tile_nrows[tile];
-      // ---- tile setup: row extents, long flags, positions in the flattened long-edge list ----
-      if (warp == 0) {
-        int w[4], tot = 0;
+    long long t_pro = 0, t_wait = 0, t_body = 0, t_mark = clock64();
+    auto lap = [&](long long& acc) { const long long now = clock64(); acc += now - t_mark; t_mark = now; };
+    for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
+      const int tile0 = st * ST_TILES;
+      const int nt = min(ST_TILES, p.n_tiles - tile0);
+      // ---- super-tile setup, one row per thread: extents, long flag, short-row neighbour records,
+      //      positions in the flattened long-edge list ----
+      int w = 0;
+      {
+        const int j = tid >> 7, r = tid & (TM - 1);
+        int rb = 0, d = 0;
+        if (j < nt && r < p.tile_nrows[tile0 + j]) {
+          const int oi = p.tile_row0[tile0 + j] + r;
+          const int v = p.g.dst_rows ? p.g.dst_rows[oi] : oi;
+          rb = p.g.indptr[v];
+          d = p.g.indptr[v + 1] - rb;
+        }
+        const bool lg = d > PRE;
+        ps->beg[tid] = rb;
+        ps->deg[tid] = d;
+        ps->is_long[tid] = lg ? 1 : 0;
+        w = lg ? d : 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int r = lane * 4 + j;
-          int rb = 0, d = 0;
-          if (r < nrows) {
-            const int v = p.g.dst_rows ? p.g.dst_rows[row0 + r] : row0 + r;
-            rb = p.g.indptr[v];
-            d = p.g.indptr[v + 1] - rb;
+        for (int i = 0; i < PRE; ++i) {
+          int off = 0;
+          float nn = 0.f;
+          if (!lg && i < d) {
+            const int u = p.g.indices[rb + i];
+            const int srow = p.g.in_row_map ? p.g.in_row_map[u] : u;
+            nn = srow < 0 ? 0.f : p.g.norm[u];        // negative map entry: neighbour dropped
+            off = (srow < 0 ? 0 : srow) * p.g.ld_in;
           }
-          const bool lg = d > PRE;
-          ps->beg[r] = rb;
-          ps->deg[r] = d;
-          ps->is_long[r] = lg ? 1 : 0;
-          w[j] = lg ? d : 0;
-          tot += w[j];
+          ps->s_off[tid][i] = off;
+          ps->s_nrm[tid][i] = nn;
         }
-        int incl = tot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int v = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += v;
+        if (lg) {                                     // long row: one "neighbour" = its scratch row
+          ps->s_off[tid][0] = tid * f_in;
+          ps->s_nrm[tid][0] = 1.f;
         }
-        int run = incl - tot;
+      }
+      int incl = w;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { ps->lpos[lane * 4 + j] = run; run += w[j]; }
-        if (lane == 31) ps->lpos[TM] = incl;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v2 = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v2;
+      }
+      if (lane == 31) ps->wsum[warp] = incl;
+      producer_sync();
+      {
+        int off = 0;
+        for (int w2 = 0; w2 < warp; ++w2) off += ps->wsum[w2];
+        ps->lpos[tid] = off + incl - w;
+        if (tid == ST_ROWS - 1) ps->lpos[ST_ROWS] = off + incl;
       }
       producer_sync();
-      const int nLE = ps->lpos[TM];
+      const int nLE = ps->lpos[ST_ROWS];
       for (int wbeg = 0; wbeg < nLE; wbeg += LCAP) {
         const int wlen = min(LCAP, nLE - wbeg);
         // ---- edge records of this window, one per thread, coalesced ----
         for (int i = tid; i < wlen; i += N_PROD_THREADS) {
           const int pos = wbeg + i;
-          int lo = 0, hi = TM;                      // largest r with lpos[r] <= pos (a long row)
+          int lo = 0, hi = ST_ROWS;                 // largest r with lpos[r] <= pos (a long row)
           while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
             if (ps->lpos[mid] <= pos) lo = mid; else hi = mid;
           }
           const int u = p.g.indices[ps->beg[lo] + (pos - ps->lpos[lo])];
           const int srow = p.g.in_row_map ? p.g.in_row_map[u] : u;
-          ps->nrm[i] = srow < 0 ? 0.f : p.g.norm[u];       // negative map entry: neighbour skipped
+          ps->nrm[i] = srow < 0 ? 0.f : p.g.norm[u];
           ps->src[i] = (srow < 0 ? 0 : srow) * p.g.ld_in;
-          ps->row[i] = (uint8_t)lo;
+          ps->row[i] = (uint16_t)lo;
         }
         producer_sync();
         // ---- balanced accumulation: group g owns list slice [sb, se) ----
@@ -316,7 +356,7 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const 
               }
               __stcg(reinterpret_cast<float4*>(dst), acc);
             } else {
-              st_f4(ps->part + ((g * 2 + (from_left ? 0 : 1)) * f_in + 4 * cu), acc);
+              __stcg(reinterpret_cast<float4*>(part + ((g * 2 + (from_left ? 0 : 1)) * f_in + 4 * cu)), acc);
               if (!from_left) own_r = r;              // I own the row: it starts in my slice
             }
             pos = run_end;
@@ -329,9 +369,9 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const 
           const int rbeg = ps->lpos[own_r] - wbeg;
           const int wre = min(rbeg + ps->deg[own_r], wlen);
           const int g_last = (wre - 1) / per;
-          float4 acc = ld_f4(ps->part + ((g * 2 + 1) * f_in + 4 * cu));
+          float4 acc = __ldcg(reinterpret_cast<const float4*>(part + ((g * 2 + 1) * f_in + 4 * cu)));
           for (int g2 = g + 1; g2 <= g_last; ++g2) {
-            const float4 v = ld_f4(ps->part + ((g2 * 2 + 0) * f_in + 4 * cu));
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(part + ((g2 * 2 + 0) * f_in + 4 * cu)));
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
           }
           float* dst = scratch + own_r * f_in + 4 * cu;
@@ -343,85 +383,96 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const 
         }
         producer_sync();
       }
-      // ---- per-row neighbour records kept in registers for the whole tile ----
-      int cnt[2];
-      int src_off[2][PRE];       // element offset of the neighbour's row (+ this lane's 16-byte unit)
-      float src_norm[2][PRE];
-      const float* base0[2];     // base of neighbour 0: the input, or the scratch row of a long row
-#pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int r = q + 64 * rr;
-        const int rb = ps->beg[r], d = ps->deg[r];
-        const bool lg = ps->is_long[r] != 0;
-        cnt[rr] = lg ? 1 : d;
-        base0[rr] = lg ? scratch : p.g.in;
-#pragma unroll
-        for (int i = 0; i < PRE; ++i) {
-          src_off[rr][i] = 0;
-          src_norm[rr][i] = 0.f;
-          if (!lg && i < d) {
-            const int u = p.g.indices[rb + i];
-            const int srow = p.g.in_row_map ? p.g.in_row_map[u] : u;
-            src_norm[rr][i] = srow < 0 ? 0.f : p.g.norm[u];
-            src_off[rr][i] = (srow < 0 ? 0 : srow) * p.g.ld_in + 4 * sub;
-          }
-        }
-        if (lg) {
-          src_off[rr][0] = r * f_in + 4 * sub;
-          src_norm[rr][0] = 1.f;
-        }
-      }
-      producer_sync();   // everyone has read ps / may still read scratch until the next tile's first sync
-      for (int kc = 0; kc < nkc; ++kc, ++it) {
-        const int s = it % NS;
-        const uint32_t ph = (uint32_t)((it / NS) & 1);
-        mbar_wait(empty(s), ph ^ 1u);
-        float4 x[2][PRE];
+      lap(t_pro);
+      // ---- the row tiles of the super-tile, chunk by chunk ----
+      for (int j = 0; j < nt; ++j) {
+        int src_off[2][PRE];       // element offset of the neighbour's row (+ this lane's 16-byte unit)
+        float src_norm[2][PRE];
+        const float* base0[2];     // base of neighbour 0: the input, or the scratch row of a long row
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
-          x[rr][0] = cnt[rr] > 0 ? __ldcg(reinterpret_cast<const float4*>(base0[rr] + src_off[rr][0] + kc * KCH))
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int i = 1; i < PRE; ++i)
-            x[rr][i] = i < cnt[rr] ? ld_f4(p.g.in + src_off[rr][i] + kc * KCH) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-          const int r = q + 64 * rr;
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int sr = j * TM + q + 64 * rr;         // row index inside the super-tile
+          base0[rr] = ps->is_long[sr] ? scratch : p.g.in;
 #pragma unroll
           for (int i = 0; i < PRE; ++i) {
-            acc.x = fmaf(src_norm[rr][i], x[rr][i].x, acc.x);
-            acc.y = fmaf(src_norm[rr][i], x[rr][i].y, acc.y);
-            acc.z = fmaf(src_norm[rr][i], x[rr][i].z, acc.z);
-            acc.w = fmaf(src_norm[rr][i], x[rr][i].w, acc.w);
+            src_off[rr][i] = ps->s_off[sr][i] + 4 * sub;
+            src_norm[rr][i] = ps->s_nrm[sr][i];
           }
-          const float4 hi = make_float4(tf32_hi(acc.x), tf32_hi(acc.y), tf32_hi(acc.z), tf32_hi(acc.w));
-          const float4 lo = make_float4(acc.x - hi.x, acc.y - hi.y, acc.z - hi.z, acc.w - hi.w);
-          const int off = r * 128 + ((sub ^ (r & 7)) << 4);   // 128B swizzle: 16-byte unit ^ (row % 8)
-          *reinterpret_cast<float4*>(sm.a_hi(s) + off) = hi;
-          *reinterpret_cast<float4*>(sm.a_lo(s) + off) = lo;
         }
-        fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a_full(s));
+        // the feature segments of chunk kc+1 are requested before chunk kc is reduced and stored,
+        // so their latency overlaps the barrier wait, the FMAs and the stores
+        float4 xn[2][PRE];
+        auto request = [&](int kc) {
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            xn[rr][0] = (src_norm[rr][0] != 0.f && !(p.dbg & 2))
+                            ? __ldcg(reinterpret_cast<const float4*>(base0[rr] + src_off[rr][0] + kc * KCH))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 1; i < PRE; ++i)
+              xn[rr][i] = (src_norm[rr][i] != 0.f && !(p.dbg & 2)) ? ld_f4(p.g.in + src_off[rr][i] + kc * KCH)
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+        request(0);
+        for (int kc = 0; kc < nkc; ++kc, ++it) {
+          const int s = it % NS;
+          const uint32_t ph = (uint32_t)((it / NS) & 1);
+          float4 x[2][PRE];
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+            for (int i = 0; i < PRE; ++i) x[rr][i] = xn[rr][i];
+          if (kc + 1 < nkc) request(kc + 1);
+          lap(t_body);
+          mbar_wait(empty(s), ph ^ 1u);
+          lap(t_wait);
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const int r = q + 64 * rr;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < PRE; ++i) {
+              acc.x = fmaf(src_norm[rr][i], x[rr][i].x, acc.x);
+              acc.y = fmaf(src_norm[rr][i], x[rr][i].y, acc.y);
+              acc.z = fmaf(src_norm[rr][i], x[rr][i].z, acc.z);
+              acc.w = fmaf(src_norm[rr][i], x[rr][i].w, acc.w);
+            }
+            const float4 hi = make_float4(tf32_hi(acc.x), tf32_hi(acc.y), tf32_hi(acc.z), tf32_hi(acc.w));
+            const float4 lo = make_float4(acc.x - hi.x, acc.y - hi.y, acc.z - hi.z, acc.w - hi.w);
+            const int off = r * 128 + ((sub ^ (r & 7)) << 4);   // 128B swizzle: 16-byte unit ^ (row % 8)
+            *reinterpret_cast<float4*>(sm.a_hi(s) + off) = hi;
+            *reinterpret_cast<float4*>(sm.a_lo(s) + off) = lo;
+          }
+          fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_full(s));
+        }
       }
+      lap(t_body);
+      producer_sync();   // ps / scratch of this super-tile are dead: the next prologue may overwrite them
+      lap(t_wait);
+    }
+    if (p.prof && (tid == 0 || tid == 255)) {
+      long long* o = p.prof + blockIdx.x * 16 + (tid == 0 ? 0 : 3);
+      o[0] = t_pro; o[1] = t_wait; o[2] = t_body;
     }
   } else if (warp == WARP_TMA) {
     // ===================== weight chunk loader (bulk async copy) =====================
     if (lane == 0) {
       int it = 0;
       const uint32_t bytes = 2u * (uint32_t)sm.b_bytes;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      TILE_LOOP_BEGIN
         const float* img = p.w_image + (long long)p.tile_task[tile] * p.image_task_stride;
         for (int kc = 0; kc < nkc; ++kc, ++it) {
           const int s = it % NS;
           const uint32_t ph = (uint32_t)((it / NS) & 1);
           mbar_wait(empty(s), ph ^ 1u);
+          if (p.dbg & 8) { mbar_arrive(b_full(s)); continue; }
           mbar_arrive_expect_tx(b_full(s), bytes);
           bulk_copy_g2s(smem_u32(sm.b_hi(s)), img + (size_t)kc * 2 * N * KCH, bytes, b_full(s));
         }
-      }
+      TILE_LOOP_END
     }
   } else if (warp == WARP_MMA) {
     // ===================== MMA issuer =====================
@@ -429,23 +480,30 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const 
       const uint32_t idesc = umma_idesc_tf32(TM, N);
       int it = 0;
       int ti = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
+      long long t_acc = 0, t_a = 0, t_b = 0, t_issue = 0, t_mark = clock64();
+      auto lap = [&](long long& acc) { const long long now = clock64(); acc += now - t_mark; t_mark = now; };
+      TILE_LOOP_BEGIN
         const int buf = ti & 1;
+        lap(t_issue);
         mbar_wait(acc_empty(buf), (uint32_t)(((ti >> 1) & 1) ^ 1));
+        lap(t_acc);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
         for (int kc = 0; kc < nkc; ++kc, ++it) {
           const int s = it % NS;
           const uint32_t ph = (uint32_t)((it / NS) & 1);
-          mbar_wait(a_full(s), ph);
+          lap(t_issue);
           mbar_wait(b_full(s), ph);
+          lap(t_b);
+          mbar_wait(a_full(s), ph);
+          lap(t_a);
           tc_fence_after();
           const uint64_t da_hi = umma_desc_k_sw128(smem_u32(sm.a_hi(s)));
           const uint64_t da_lo = umma_desc_k_sw128(smem_u32(sm.a_lo(s)));
           const uint64_t db_hi = umma_desc_k_sw128(smem_u32(sm.b_hi(s)));
           const uint64_t db_lo = umma_desc_k_sw128(smem_u32(sm.b_hi(s) + sm.b_bytes));
 #pragma unroll
-          for (int k = 0; k < KCH / 8; ++k) {     // UMMA_K = 8 tf32 = 32 bytes = 2 descriptor units
+          for (int k = 0; k < ((p.dbg & 4) ? 1 : KCH / 8); ++k) {     // UMMA_K = 8 tf32 = 32 bytes = 2 descriptor units
             const uint64_t adv = (uint64_t)(2 * k);
             tc_mma_tf32(d_tmem, da_hi + adv, db_hi + adv, idesc, (kc | k) != 0 ? 1u : 0u);
             tc_mma_tf32(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
@@ -454,6 +512,12 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const 
           tc_commit(empty(s));          // frees the stage once these MMAs have read it
         }
         tc_commit(acc_full(buf));       // accumulator complete -> epilogue
+        ++ti;
+      TILE_LOOP_END
+      lap(t_issue);
+      if (p.prof) {
+        long long* o = p.prof + blockIdx.x * 16 + 6;
+        o[0] = t_acc; o[1] = t_a; o[2] = t_b; o[3] = t_issue;
       }
     }
   } else {
@@ -461,7 +525,9 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const 
     const int quarter = warp & 3;       // TMEM lanes 32*quarter .. +31 are the ones this warp may read
     const int r = quarter * 32 + lane;
     int ti = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
+    long long t_wacc = 0, t_epi = 0, t_ldtm = 0, t_store = 0, t_mark = clock64();
+    auto lap = [&](long long& acc) { const long long now = clock64(); acc += now - t_mark; t_mark = now; };
+    TILE_LOOP_BEGIN
       const int buf = ti & 1;
       const int row0 = p.tile_row0[tile], nrows = p.tile_nrows[tile], task = p.tile_task[tile];
       const float* bias = p.bias ? p.bias + (long long)task * p.b_task_stride : nullptr;
@@ -469,40 +535,69 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const 
       const int oi = row0 + (live ? r : 0);                          // output row (compact or dense)
       const int v = p.g.dst_rows ? p.g.dst_rows[oi] : oi;            // real row: norm and mask
       const float nv = p.g.norm[v];
-      float* orow = p.out + (size_t)oi * p.ld_out;
       const float* mrow = p.relu_mask ? p.relu_mask + (size_t)v * p.ld_out : nullptr;
+      lap(t_epi);
       mbar_wait(acc_full(buf), (uint32_t)((ti >> 1) & 1));
+      lap(t_wacc);
       tc_fence_after();
+      float* stg = ps->epi[quarter];
+      // bias of this tile's task -> shared memory once per tile (one coalesced load per lane), so the
+      // chunk loop below has no dependent global load; double buffered + one 128-thread barrier
+      float* bias_s = ps->bias_s[ti & 1];
+      for (int c = (warp - WARP_EPI0) * 32 + lane; c < N; c += 128) bias_s[c] = bias ? bias[c] : 0.f;
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      // rows this lane stores after the transpose: 8*j + lane/4, 16-byte unit lane%4 of the chunk
+      const int orow_base = p.tile_row0[tile] + quarter * 32 + (lane >> 2);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * ACC_COLS);
+      uint32_t acc_n[16];
+      tmem_ld16(t_addr, acc_n);
       for (int c0 = 0; c0 < N; c0 += 16) {
         uint32_t acc[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * ACC_COLS + c0), acc);
-        const float bl = (bias && lane < 16) ? bias[c0 + lane] : 0.f;
         tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = acc_n[j];
+        if (c0 + 16 < N) tmem_ld16(t_addr + (uint32_t)(c0 + 16), acc_n);   // next chunk in flight
         float o[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float val = fmaf(nv, __uint_as_float(acc[j]), __shfl_sync(0xffffffffu, bl, j));
+          float val = fmaf(nv, __uint_as_float(acc[j]), bias_s[c0 + j]);
           if (p.relu) val = fmaxf(val, 0.f);
           o[j] = val;
         }
-        if (live) {
+        if (mrow && live) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
-            float4 w4 = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-            if (mrow) {
-              const float4 m4 = ld_f4(mrow + c0 + j);
-              if (!(m4.x > 0.f)) w4.x = 0.f;
-              if (!(m4.y > 0.f)) w4.y = 0.f;
-              if (!(m4.z > 0.f)) w4.z = 0.f;
-              if (!(m4.w > 0.f)) w4.w = 0.f;
-            }
-            st_f4(orow + c0 + j, w4);
+            const float4 m4 = ld_f4(mrow + c0 + j);
+            if (!(m4.x > 0.f)) o[j] = 0.f;
+            if (!(m4.y > 0.f)) o[j + 1] = 0.f;
+            if (!(m4.z > 0.f)) o[j + 2] = 0.f;
+            if (!(m4.w > 0.f)) o[j + 3] = 0.f;
+          }
+        }
+        // transpose through shared memory so that a store instruction writes 8 rows x 64 contiguous
+        // bytes (whole 32-byte sectors) instead of 32 rows x 16 bytes
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) st_f4(stg + lane * EPI_LD + j, make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]));
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int rr = 8 * j + (lane >> 2);
+          if (quarter * 32 + rr < nrows && !(p.dbg & 1)) {
+            const float4 w4 = ld_f4(stg + rr * EPI_LD + 4 * (lane & 3));
+            st_f4(p.out + (size_t)(orow_base + 8 * j) * p.ld_out + c0 + 4 * (lane & 3), w4);
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));
+      ++ti;
+    TILE_LOOP_END
+    lap(t_epi);
+    if (p.prof && warp == WARP_EPI0 && lane == 0) {
+      long long* o = p.prof + blockIdx.x * 16 + 10;
+      o[0] = t_wacc; o[1] = t_epi; o[2] = t_ldtm; o[3] = t_store;
     }
   }
 
@@ -543,6 +638,9 @@ __global__ void pack_w_umma_kernel(const float* __restrict__ W, long long w_stri
 
 constexpr int kSmemFixed = 1024 /*alignment slack*/ + 256 /*barriers*/ + (int)sizeof(ProdSmem);
 
+long long* g_tc_prof = nullptr;   // set through gmeta_debug_set_tc_profile
+int g_tc_dbg = 0;                 // set through gmeta_debug_set_tc_flags
+
 int stages_for(int N) {
   const int stage = 2 * A_TILE_BYTES + 2 * N * KCH * 4;
   int s = (227 * 1024 - kSmemFixed) / stage;
@@ -567,7 +665,7 @@ static int64_t image_bytes(int n_copies, int f_in, int f_out) {
 
 int64_t gcn_layer_fwd_tc_workspace_bytes(int n_copies, int f_in, int f_out) {
   // weight image + per-CTA scratch rows for long (hub) rows
-  return image_bytes(n_copies, f_in, f_out) + (int64_t)kNumSMs * TM * f_in * (int64_t)sizeof(float);
+  return image_bytes(n_copies, f_in, f_out) + (int64_t)kNumSMs * ((int64_t)ST_ROWS * f_in + 4 * N_PROD_THREADS * 2) * (int64_t)sizeof(float);
 }
 
 int gcn_layer_fwd_tc(const GatherSrc& g, const int32_t* tile_row0, const int32_t* tile_nrows,
@@ -594,6 +692,8 @@ int gcn_layer_fwd_tc(const GatherSrc& g, const int32_t* tile_row0, const int32_t
   p.bias = bias; p.b_task_stride = b_task_stride; p.f_out = N; p.relu = relu; p.relu_mask = relu_mask;
   p.out = out; p.ld_out = ld_out;
   p.n_stages = stages_for(N);
+  p.prof = g_tc_prof;
+  p.dbg = g_tc_dbg;
   p.long_scratch = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + image_bytes(n_copies, K, N));
   const size_t smem = (size_t)p.n_stages * (2 * A_TILE_BYTES + 2 * N * KCH * 4) + kSmemFixed;
   static bool attr_done = false;
@@ -601,9 +701,16 @@ int gcn_layer_fwd_tc(const GatherSrc& g, const int32_t* tile_row0, const int32_t
     cudaFuncSetAttribute(gcn_layer_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_done = true;
   }
-  const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+  const int n_super = (n_tiles + ST_TILES - 1) / ST_TILES;
+  const int grid = n_super < kNumSMs ? n_super : kNumSMs;
   gcn_layer_fwd_tc_kernel<<<grid, NTHREADS_TC, smem, stream>>>(p);
   return check_launch();
 }
 
 }  // namespace gmeta
+
+// Debug hook (not part of the reference-facing surface): device buffer of 148*16 int64 cycle
+// counters filled by subsequent tensor-core layer launches; NULL switches it off.
+extern "C" void gmeta_debug_set_tc_profile(long long* device_buffer) { gmeta::g_tc_prof = device_buffer; }
+// Debug ablation switches for performance triage (results are WRONG with any flag set).
+extern "C" void gmeta_debug_set_tc_flags(int flags) { gmeta::g_tc_dbg = flags; }

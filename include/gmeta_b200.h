@@ -141,6 +141,13 @@ int gmeta_gcn_layer_fwd(const float* in, int32_t ld_in, const int32_t* in_row_ma
 int64_t gmeta_gcn_layer_fwd_workspace_bytes(int32_t n_tasks, int64_t w_task_stride, int32_t f_in,
                                             int32_t f_out, int32_t impl);
 
+/* Debug hook: device buffer [148][16] of int64 cycle counters that subsequent tensor-core layer
+ * launches fill per role (producer prologue/wait/body, MMA waits, epilogue); NULL = off. */
+void gmeta_debug_set_tc_profile(long long* device_buffer);
+/* Debug ablation flags for performance triage (outputs are wrong while non-zero): 1 skip output
+ * stores, 2 skip gather loads, 4 issue 1/4 of the MMAs, 8 skip the weight-chunk copies. */
+void gmeta_debug_set_tc_flags(int flags);
+
 /* Weight/bias gradient of one GCN layer (the autograd.grad of meta.py:125,149 for that layer):
  *   dW[t][k,j] = sum_{v in task t} norm[v] * M[v,k] * dZ[v,j],   db[t][j] = sum_v dZ[v,j]
  * M as in gmeta_gcn_layer_fwd (re-gathered, not stored).  dZ is the gradient w.r.t. the

@@ -54,6 +54,8 @@ def main():
     ap.add_argument("--deg", type=float, default=1.76)
     ap.add_argument("--impls", default="1,2")
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--ablate", default="", help="comma list of debug flag masks to time (tcgen05 impl)")
+    ap.add_argument("--profile", action="store_true", help="per-role cycle counters of the tcgen05 kernel")
     a = ap.parse_args()
     L = _lib.lib()
     dev = torch.device("cuda")
@@ -97,6 +99,30 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / a.reps
+        if impl == 2 and a.profile:
+            prof = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+            L.gmeta_debug_set_tc_profile(prof.data_ptr())
+            launch()
+            torch.cuda.synchronize()
+            L.gmeta_debug_set_tc_profile(None)
+            pr = prof.cpu().numpy().reshape(148, 16).astype(np.float64)
+            names = ["prod0.prologue", "prod0.wait", "prod0.body", "prod7.prologue", "prod7.wait", "prod7.body",
+                     "mma.wait_acc_empty", "mma.wait_a_full", "mma.wait_b_full", "mma.issue", "epi.wait_acc_full",
+                     "epi.body", "epi.ldtm", "epi.store"]
+            res["profile_kcycles_mean_per_cta"] = {n: round(float(pr[:, i].mean()) / 1e3, 1) for i, n in enumerate(names)}
+        if impl == 2 and a.ablate:
+            for fl in [int(v) for v in a.ablate.split(",")]:
+                L.gmeta_debug_set_tc_flags(fl)
+                launch()
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(a.reps):
+                    launch()
+                e1.record()
+                torch.cuda.synchronize()
+                res["ablate_%d_ms" % fl] = round(e0.elapsed_time(e1) / a.reps, 4)
+            L.gmeta_debug_set_tc_flags(0)
+            launch()
         outs[impl] = out.clone()
         res[impl] = {"ms": ms, "GBps": alg / ms / 1e6, "frac_hbm": alg / ms / 1e6 / peak}
     if 1 in outs and 2 in outs:
