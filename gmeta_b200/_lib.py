@@ -13,7 +13,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 
 MAX_LAYERS = 3
 TILE_ROWS = 128
-IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
+IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, IMPL_TCPAIR = 0, 1, 2, 3
 
 i32, i64, f32, f64, vp = C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_void_p
 
@@ -53,6 +53,10 @@ _SIGNATURES = {
     "gmeta_gcn_layer_fwd": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, i64, i32, i32, vp, i64,
                                       i32, i32, i32, vp, vp, i32, i32, vp, i64, vp]),
     "gmeta_gcn_layer_fwd_workspace_bytes": (i64, [i32, i64, i32, i32, i32]),
+    "gmeta_gcn_layer_fwd_ex": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, i64, i32, i32, vp, i64,
+                                         i32, i32, i32, vp, vp, i32, i32, vp, i64, i32, i32, vp, vp, vp]),
+    "gmeta_gcn_layer_fwd_ex_workspace_bytes": (i64, [i32, i64, i32, i32, i32, i32, i32, i32]),
+    "gmeta_row_absmax": (C.c_int, [vp, i32, i32, i32, vp, vp]),
     "gmeta_gcn_layer_wgrad_workspace_bytes": (i64, [i32, i32, i32]),
     "gmeta_gcn_layer_wgrad": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp, i64, vp, i64,
                                         vp, i64, vp]),
@@ -72,6 +76,7 @@ _SIGNATURES = {
     "gmeta_last_launch_count": (C.c_int, []),
     "gmeta_debug_set_tc_profile": (None, [vp]),
     "gmeta_debug_set_tc_flags": (None, [C.c_int]),
+    "gmeta_debug_set_pair_flags": (None, [C.c_int]),
 }
 
 _lib = None

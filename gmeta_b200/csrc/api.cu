@@ -14,6 +14,17 @@ int gcn_layer_fwd_tc(const GatherSrc& g, const int32_t* tile_row0, const int32_t
                      int ldw, int trans_w, const float* bias, int64_t b_task_stride, int f_out, int relu,
                      const float* relu_mask, float* out, int ld_out, void* workspace, int64_t workspace_bytes,
                      cudaStream_t stream);
+bool gcn_layer_fwd_pair_supported(const GatherSrc& g, int f_out, const float* bias, int64_t b_task_stride,
+                                  const float* relu_mask, const float* out, int ld_out, int n_tasks);
+int64_t gcn_layer_fwd_pair_workspace_bytes(int n_copies, int n_tiles, int n_tasks, int n_rows, int n_edges, int f_in,
+                                           int f_out);
+int gcn_layer_fwd_pair(const GatherSrc& g, const int32_t* tile_row0, const int32_t* tile_nrows,
+                       const int32_t* tile_task, int n_tiles, int n_tasks, int n_copies, int n_rows, int n_edges,
+                       const float* in_rowmax, const float* W, int64_t w_task_stride, int ldw, int trans_w,
+                       const float* bias, int64_t b_task_stride, int f_out, int relu, const float* relu_mask,
+                       float* out, int ld_out, float* out_rowmax, void* workspace, int64_t workspace_bytes,
+                       cudaStream_t stream);
+int row_absmax(const float* x, int ld, int n_rows, int f, float* out, cudaStream_t stream);
 }  // namespace gmeta
 
 using namespace gmeta;
@@ -32,6 +43,53 @@ extern "C" const char* gmeta_error_string(int code) {
   }
 }
 
+extern "C" int gmeta_gcn_layer_fwd_ex(const float* in, int32_t ld_in, const int32_t* in_row_map,
+                                      const int32_t* dst_rows, const int32_t* indptr, const int32_t* indices,
+                                      const float* norm, const int32_t* tile_row0, const int32_t* tile_nrows,
+                                      const int32_t* tile_task, int32_t n_tiles, int32_t n_tasks, const float* W,
+                                      int64_t w_task_stride, int32_t ldw, int32_t trans_w, const float* bias,
+                                      int64_t b_task_stride, int32_t f_in, int32_t f_out, int32_t relu,
+                                      const float* relu_mask, float* out, int32_t ld_out, int32_t impl,
+                                      void* workspace, int64_t workspace_bytes, int32_t n_rows, int32_t n_edges,
+                                      const float* in_rowmax, float* out_rowmax, void* stream) {
+  if (!in || !indptr || !norm || !tile_row0 || !tile_nrows || !tile_task || !W || !out) return GMETA_ERR_BAD_ARG;
+  if (n_tiles < 0 || n_tasks <= 0 || f_in <= 0 || f_out <= 0 || ld_in < f_in || ld_out < f_out) return GMETA_ERR_BAD_ARG;
+  if (ldw < (trans_w ? f_in : f_out)) return GMETA_ERR_BAD_ARG;
+  if (out_rowmax && n_rows <= 0) return GMETA_ERR_BAD_ARG;
+  if (n_tiles == 0) return GMETA_OK;
+  GatherSrc g;
+  g.in = in; g.in_row_map = in_row_map; g.dst_rows = dst_rows; g.indptr = indptr; g.indices = indices; g.norm = norm;
+  g.ld_in = ld_in; g.f_in = f_in;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n_copies = w_task_stride == 0 ? 1 : n_tasks;
+  const bool ws_aligned = workspace && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0;
+  const bool pair_ok = in_rowmax && n_rows > 0 && n_edges >= 0 &&
+                       gcn_layer_fwd_pair_supported(g, f_out, bias, b_task_stride, relu_mask, out, ld_out, n_tasks);
+  if (impl == GMETA_IMPL_TCPAIR && !pair_ok) return GMETA_ERR_UNSUPPORTED;
+  if (impl == GMETA_IMPL_TCPAIR ||
+      (impl == GMETA_IMPL_AUTO && pair_ok && ws_aligned &&
+       workspace_bytes >= gcn_layer_fwd_pair_workspace_bytes(n_copies, n_tiles, n_tasks, n_rows, n_edges, f_in, f_out)))
+    return gcn_layer_fwd_pair(g, tile_row0, tile_nrows, tile_task, n_tiles, n_tasks, n_copies, n_rows, n_edges,
+                              in_rowmax, W, w_task_stride, ldw, trans_w, bias, b_task_stride, f_out, relu, relu_mask,
+                              out, ld_out, out_rowmax, workspace, workspace_bytes, s);
+  const bool tc_ok = gcn_layer_fwd_tc_supported(g, ldw, trans_w, f_out, out, ld_out);
+  if (impl == GMETA_IMPL_TCGEN05 && !tc_ok) return GMETA_ERR_UNSUPPORTED;
+  // AUTO falls back to the FFMA kernel when no workspace for the weight image was provided
+  const bool ws_ok = workspace && workspace_bytes >= gcn_layer_fwd_tc_workspace_bytes(n_copies, f_in, f_out);
+  int rc;
+  if (impl == GMETA_IMPL_TCGEN05 || (impl == GMETA_IMPL_AUTO && tc_ok && ws_ok))
+    rc = gcn_layer_fwd_tc(g, tile_row0, tile_nrows, tile_task, n_tiles, n_copies, W, w_task_stride, ldw,
+                          trans_w, bias, b_task_stride, f_out, relu, relu_mask, out, ld_out, workspace,
+                          workspace_bytes, s);
+  else if (impl != GMETA_IMPL_AUTO && impl != GMETA_IMPL_SIMT)
+    return GMETA_ERR_BAD_ARG;
+  else
+    rc = gcn_layer_fwd_simt(g, tile_row0, tile_nrows, tile_task, n_tiles, W, w_task_stride, ldw, trans_w, bias,
+                            b_task_stride, f_out, relu, relu_mask, out, ld_out, s);
+  if (rc == GMETA_OK && out_rowmax) rc = row_absmax(out, ld_out, n_rows, f_out, out_rowmax, s);
+  return rc;
+}
+
 extern "C" int gmeta_gcn_layer_fwd(const float* in, int32_t ld_in, const int32_t* in_row_map,
                                    const int32_t* dst_rows, const int32_t* indptr, const int32_t* indices, const float* norm,
                                    const int32_t* tile_row0, const int32_t* tile_nrows,
@@ -40,26 +98,11 @@ extern "C" int gmeta_gcn_layer_fwd(const float* in, int32_t ld_in, const int32_t
                                    int64_t b_task_stride, int32_t f_in, int32_t f_out, int32_t relu,
                                    const float* relu_mask, float* out, int32_t ld_out, int32_t impl,
                                    void* workspace, int64_t workspace_bytes, void* stream) {
-  if (!in || !indptr || !norm || !tile_row0 || !tile_nrows || !tile_task || !W || !out) return GMETA_ERR_BAD_ARG;
-  if (n_tiles < 0 || n_tasks <= 0 || f_in <= 0 || f_out <= 0 || ld_in < f_in || ld_out < f_out) return GMETA_ERR_BAD_ARG;
-  if (ldw < (trans_w ? f_in : f_out)) return GMETA_ERR_BAD_ARG;
-  if (n_tiles == 0) return GMETA_OK;
-  GatherSrc g;
-  g.in = in; g.in_row_map = in_row_map; g.dst_rows = dst_rows; g.indptr = indptr; g.indices = indices; g.norm = norm;
-  g.ld_in = ld_in; g.f_in = f_in;
-  cudaStream_t s = (cudaStream_t)stream;
-  const int n_copies = w_task_stride == 0 ? 1 : n_tasks;
-  const bool tc_ok = gcn_layer_fwd_tc_supported(g, ldw, trans_w, f_out, out, ld_out);
-  if (impl == GMETA_IMPL_TCGEN05 && !tc_ok) return GMETA_ERR_UNSUPPORTED;
-  // AUTO falls back to the FFMA kernel when no workspace for the weight image was provided
-  const bool ws_ok = workspace && workspace_bytes >= gcn_layer_fwd_tc_workspace_bytes(n_copies, f_in, f_out);
-  if (impl == GMETA_IMPL_TCGEN05 || (impl == GMETA_IMPL_AUTO && tc_ok && ws_ok))
-    return gcn_layer_fwd_tc(g, tile_row0, tile_nrows, tile_task, n_tiles, n_copies, W, w_task_stride, ldw,
-                            trans_w, bias, b_task_stride, f_out, relu, relu_mask, out, ld_out, workspace,
-                            workspace_bytes, s);
-  if (impl != GMETA_IMPL_AUTO && impl != GMETA_IMPL_SIMT) return GMETA_ERR_BAD_ARG;
-  return gcn_layer_fwd_simt(g, tile_row0, tile_nrows, tile_task, n_tiles, W, w_task_stride, ldw, trans_w, bias,
-                            b_task_stride, f_out, relu, relu_mask, out, ld_out, s);
+  if (impl == GMETA_IMPL_TCPAIR) return GMETA_ERR_UNSUPPORTED;   // needs the _ex arguments
+  return gmeta_gcn_layer_fwd_ex(in, ld_in, in_row_map, dst_rows, indptr, indices, norm, tile_row0, tile_nrows,
+                                tile_task, n_tiles, n_tasks, W, w_task_stride, ldw, trans_w, bias, b_task_stride, f_in,
+                                f_out, relu, relu_mask, out, ld_out, impl, workspace, workspace_bytes, 0, 0, nullptr,
+                                nullptr, stream);
 }
 
 extern "C" int64_t gmeta_gcn_layer_fwd_workspace_bytes(int32_t n_tasks, int64_t w_task_stride, int32_t f_in,
@@ -67,4 +110,23 @@ extern "C" int64_t gmeta_gcn_layer_fwd_workspace_bytes(int32_t n_tasks, int64_t 
   if (n_tasks <= 0 || f_in <= 0 || f_out <= 0) return 0;
   if (impl == GMETA_IMPL_SIMT) return 0;
   return gcn_layer_fwd_tc_workspace_bytes(w_task_stride == 0 ? 1 : n_tasks, f_in, f_out);
+}
+
+extern "C" int64_t gmeta_gcn_layer_fwd_ex_workspace_bytes(int32_t n_tasks, int64_t w_task_stride, int32_t n_tiles,
+                                                          int32_t n_rows, int32_t n_edges, int32_t f_in,
+                                                          int32_t f_out, int32_t impl) {
+  if (n_tasks <= 0 || f_in <= 0 || f_out <= 0) return 0;
+  if (impl == GMETA_IMPL_SIMT) return 0;
+  const int n_copies = w_task_stride == 0 ? 1 : n_tasks;
+  int64_t b = impl == GMETA_IMPL_TCPAIR ? 0 : gcn_layer_fwd_tc_workspace_bytes(n_copies, f_in, f_out);
+  if (impl != GMETA_IMPL_TCGEN05 && f_in % 64 == 0 && f_out % 16 == 0 && n_rows > 0) {
+    const int64_t p = gcn_layer_fwd_pair_workspace_bytes(n_copies, n_tiles, n_tasks, n_rows, n_edges, f_in, f_out);
+    if (p > b) b = p;
+  }
+  return b;
+}
+
+extern "C" int gmeta_row_absmax(const float* x, int32_t ld, int32_t n_rows, int32_t f, float* out, void* stream) {
+  if (!x || !out || n_rows < 0 || f <= 0 || ld < f) return GMETA_ERR_BAD_ARG;
+  return row_absmax(x, ld, n_rows, f, out, (cudaStream_t)stream);
 }

@@ -43,7 +43,8 @@ extern "C" {
 
 #define GMETA_IMPL_AUTO 0
 #define GMETA_IMPL_SIMT 1           /* fp32 FFMA, any shape */
-#define GMETA_IMPL_TCGEN05 2        /* tcgen05.mma kind::tf32, 3xTF32 error-compensated */
+#define GMETA_IMPL_TCGEN05 2        /* tcgen05.mma kind::tf32, 3xTF32 error-compensated, weights streamed per tile */
+#define GMETA_IMPL_TCPAIR 3         /* tcgen05.mma.cta_group::2 kind::f16, scaled FP16 hi/lo split, weights resident per CTA pair */
 
 int gmeta_version(void);
 const char* gmeta_error_string(int code);
@@ -141,12 +142,42 @@ int gmeta_gcn_layer_fwd(const float* in, int32_t ld_in, const int32_t* in_row_ma
 int64_t gmeta_gcn_layer_fwd_workspace_bytes(int32_t n_tasks, int64_t w_task_stride, int32_t f_in,
                                             int32_t f_out, int32_t impl);
 
+/* Extended form of gmeta_gcn_layer_fwd.  Additional arguments:
+ *   n_rows     rows covered by the tile table (N, or the length of dst_rows);
+ *   n_edges    >= number of CSR entries of those rows (E of the packed set is always enough);
+ *   in_rowmax  [rows of `in`] max_k |in[r,k]| of every input row, or NULL;
+ *   out_rowmax [n_rows] receives max_j |out[i,j]| (the in_rowmax of the next layer), or NULL.
+ * With in_rowmax given, GMETA_IMPL_AUTO selects GMETA_IMPL_TCPAIR when the shape allows
+ * (f_in % 64 == 0, f_out % 16 == 0, f_out <= 256, 2*f_in*f_out + 64 KB <= 227 KB of shared memory,
+ * n_tasks <= 2048): the row abs-max vector gives the rigorous per-row bound from which the
+ * FP16 operand scaling is derived (csrc/gcn_layer_pair.cu).  The tile table must list the tiles
+ * of a task contiguously.  Workspace: gmeta_gcn_layer_fwd_ex_workspace_bytes, 256-byte aligned. */
+int gmeta_gcn_layer_fwd_ex(const float* in, int32_t ld_in, const int32_t* in_row_map,
+                           const int32_t* dst_rows, const int32_t* indptr, const int32_t* indices, const float* norm,
+                           const int32_t* tile_row0, const int32_t* tile_nrows,
+                           const int32_t* tile_task, int32_t n_tiles, int32_t n_tasks,
+                           const float* W, int64_t w_task_stride, int32_t ldw, int32_t trans_w,
+                           const float* bias, int64_t b_task_stride,
+                           int32_t f_in, int32_t f_out, int32_t relu, const float* relu_mask,
+                           float* out, int32_t ld_out, int32_t impl,
+                           void* workspace, int64_t workspace_bytes,
+                           int32_t n_rows, int32_t n_edges, const float* in_rowmax, float* out_rowmax,
+                           void* stream);
+int64_t gmeta_gcn_layer_fwd_ex_workspace_bytes(int32_t n_tasks, int64_t w_task_stride, int32_t n_tiles,
+                                               int32_t n_rows, int32_t n_edges, int32_t f_in,
+                                               int32_t f_out, int32_t impl);
+
+/* out[r] = max_k |x[r*ld + k]|, k < f  (prepares in_rowmax for gmeta_gcn_layer_fwd_ex). */
+int gmeta_row_absmax(const float* x, int32_t ld, int32_t n_rows, int32_t f, float* out, void* stream);
+
 /* Debug hook: device buffer [148][16] of int64 cycle counters that subsequent tensor-core layer
  * launches fill per role (producer prologue/wait/body, MMA waits, epilogue); NULL = off. */
 void gmeta_debug_set_tc_profile(long long* device_buffer);
 /* Debug ablation flags for performance triage (outputs are wrong while non-zero): 1 skip output
  * stores, 2 skip gather loads, 4 issue 1/4 of the MMAs, 8 skip the weight-chunk copies. */
 void gmeta_debug_set_tc_flags(int flags);
+/* Same for the CTA-pair kernel: 1 skip output stores, 2 skip gather loads, 4 issue 1/4 of the MMAs. */
+void gmeta_debug_set_pair_flags(int flags);
 
 /* Weight/bias gradient of one GCN layer (the autograd.grad of meta.py:125,149 for that layer):
  *   dW[t][k,j] = sum_{v in task t} norm[v] * M[v,k] * dZ[v,j],   db[t][j] = sum_v dZ[v,j]

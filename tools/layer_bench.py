@@ -80,15 +80,21 @@ def main():
     res = {}
     outs = {}
     for impl in [int(v) for v in a.impls.split(",")]:
-        nb = L.gmeta_gcn_layer_fwd_workspace_bytes(a.tasks, P, a.fin, a.fout, impl)
-        ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
+        nb = L.gmeta_gcn_layer_fwd_ex_workspace_bytes(a.tasks, P, len(row0), N, E, a.fin, a.fout, impl)
+        ws = torch.empty(max(nb, 16) + 256, dtype=torch.uint8, device=dev)
+        ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+        rmax_in = torch.empty(N, device=dev)
+        rmax_out = torch.empty(N, device=dev)
+        _lib.check(L.gmeta_row_absmax(x.data_ptr(), a.fin, N, a.fin, rmax_in.data_ptr(), st))
 
         def launch():
-            _lib.check(L.gmeta_gcn_layer_fwd(x.data_ptr(), a.fin, None, None, d_indptr.data_ptr(), d_indices.data_ptr(),
-                                             norm.data_ptr(), d_row0.data_ptr(), d_nrows.data_ptr(), d_task.data_ptr(),
-                                             len(row0), a.tasks, W.data_ptr(), P, a.fout, 0,
-                                             W.data_ptr() + 4 * a.fin * a.fout, P, a.fin, a.fout, 1, None,
-                                             out.data_ptr(), a.fout, impl, ws.data_ptr(), nb, st))
+            _lib.check(L.gmeta_gcn_layer_fwd_ex(x.data_ptr(), a.fin, None, None, d_indptr.data_ptr(), d_indices.data_ptr(),
+                                                norm.data_ptr(), d_row0.data_ptr(), d_nrows.data_ptr(), d_task.data_ptr(),
+                                                len(row0), a.tasks, W.data_ptr(), P, a.fout, 0,
+                                                W.data_ptr() + 4 * a.fin * a.fout, P, a.fin, a.fout, 1, None,
+                                                out.data_ptr(), a.fout, impl, ws_ptr, nb, N, E,
+                                                rmax_in.data_ptr() if impl == 3 else None,
+                                                rmax_out.data_ptr() if impl == 3 else None, st))
         for _ in range(2):
             launch()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -110,9 +116,10 @@ def main():
                      "mma.wait_acc_empty", "mma.wait_a_full", "mma.wait_b_full", "mma.issue", "epi.wait_acc_full",
                      "epi.body", "epi.ldtm", "epi.store"]
             res["profile_kcycles_mean_per_cta"] = {n: round(float(pr[:, i].mean()) / 1e3, 1) for i, n in enumerate(names)}
-        if impl == 2 and a.ablate:
+        if impl in (2, 3) and a.ablate:
+            set_flags = L.gmeta_debug_set_tc_flags if impl == 2 else L.gmeta_debug_set_pair_flags
             for fl in [int(v) for v in a.ablate.split(",")]:
-                L.gmeta_debug_set_tc_flags(fl)
+                set_flags(fl)
                 launch()
                 torch.cuda.synchronize()
                 e0.record()
@@ -120,13 +127,18 @@ def main():
                     launch()
                 e1.record()
                 torch.cuda.synchronize()
-                res["ablate_%d_ms" % fl] = round(e0.elapsed_time(e1) / a.reps, 4)
-            L.gmeta_debug_set_tc_flags(0)
+                res["impl%d_ablate_%d_ms" % (impl, fl)] = round(e0.elapsed_time(e1) / a.reps, 4)
+            set_flags(0)
             launch()
+        if impl == 3:
+            torch.cuda.synchronize()
+            res["rowmax_max_abs_diff"] = float((rmax_out - out.abs().amax(1)).abs().max())
         outs[impl] = out.clone()
         res[impl] = {"ms": ms, "GBps": alg / ms / 1e6, "frac_hbm": alg / ms / 1e6 / peak}
-    if 1 in outs and 2 in outs:
-        res["max_abs_diff"] = float((outs[1] - outs[2]).abs().max())
+    for k in outs:
+        if k != 1 and 1 in outs:
+            res["max_abs_diff_impl%d_vs_ffma" % k] = float((outs[1] - outs[k]).abs().max())
+            res["max_abs_ref"] = float(outs[1].abs().max())
     print(json.dumps({"N": N, "E": E, "tiles": len(row0), "alg_GB": alg / 1e9, "res": res}))
 
 
