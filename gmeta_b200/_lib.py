@@ -54,7 +54,9 @@ _SIGNATURES = {
                                       i32, i32, i32, vp, vp, i32, i32, vp, i64, vp]),
     "gmeta_gcn_layer_fwd_workspace_bytes": (i64, [i32, i64, i32, i32, i32]),
     "gmeta_gcn_layer_fwd_ex": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, i64, i32, i32, vp, i64,
-                                         i32, i32, i32, vp, vp, i32, i32, vp, i64, i32, i32, vp, vp, vp]),
+                                         i32, i32, i32, vp, vp, i32, i32, vp, i64, i32, i32, vp, vp, vp, vp]),
+    "gmeta_layer_plan_bytes": (i64, [i32, i32, i32, i32]),
+    "gmeta_layer_plan_build": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]),
     "gmeta_gcn_layer_fwd_ex_workspace_bytes": (i64, [i32, i64, i32, i32, i32, i32, i32, i32]),
     "gmeta_row_absmax": (C.c_int, [vp, i32, i32, i32, vp, vp]),
     "gmeta_gcn_layer_wgrad_workspace_bytes": (i64, [i32, i32, i32]),
@@ -77,6 +79,7 @@ _SIGNATURES = {
     "gmeta_debug_set_tc_profile": (None, [vp]),
     "gmeta_debug_set_tc_flags": (None, [C.c_int]),
     "gmeta_debug_set_pair_flags": (None, [C.c_int]),
+    "gmeta_debug_set_pair_profile": (None, [vp]),
 }
 
 _lib = None

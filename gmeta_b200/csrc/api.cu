@@ -20,10 +20,15 @@ int64_t gcn_layer_fwd_pair_workspace_bytes(int n_copies, int n_tiles, int n_task
                                            int f_out);
 int gcn_layer_fwd_pair(const GatherSrc& g, const int32_t* tile_row0, const int32_t* tile_nrows,
                        const int32_t* tile_task, int n_tiles, int n_tasks, int n_copies, int n_rows, int n_edges,
-                       const float* in_rowmax, const float* W, int64_t w_task_stride, int ldw, int trans_w,
-                       const float* bias, int64_t b_task_stride, int f_out, int relu, const float* relu_mask,
-                       float* out, int ld_out, float* out_rowmax, void* workspace, int64_t workspace_bytes,
-                       cudaStream_t stream);
+                       const float* in_rowmax, const void* plan, const float* W, int64_t w_task_stride, int ldw,
+                       int trans_w, const float* bias, int64_t b_task_stride, int f_out, int relu,
+                       const float* relu_mask, float* out, int ld_out, float* out_rowmax, void* workspace,
+                       int64_t workspace_bytes, cudaStream_t stream);
+int64_t layer_plan_bytes(int n_tiles, int n_tasks, int n_rows, int n_edges);
+int layer_plan_build(const int32_t* indptr, const int32_t* indices, const float* norm, const int32_t* in_row_map,
+                     const int32_t* dst_rows, const int32_t* tile_row0, const int32_t* tile_nrows,
+                     const int32_t* tile_task, int n_tiles, int n_tasks, int n_rows, int n_edges, void* plan,
+                     cudaStream_t stream);
 int row_absmax(const float* x, int ld, int n_rows, int f, float* out, cudaStream_t stream);
 }  // namespace gmeta
 
@@ -51,7 +56,7 @@ extern "C" int gmeta_gcn_layer_fwd_ex(const float* in, int32_t ld_in, const int3
                                       int64_t b_task_stride, int32_t f_in, int32_t f_out, int32_t relu,
                                       const float* relu_mask, float* out, int32_t ld_out, int32_t impl,
                                       void* workspace, int64_t workspace_bytes, int32_t n_rows, int32_t n_edges,
-                                      const float* in_rowmax, float* out_rowmax, void* stream) {
+                                      const float* in_rowmax, float* out_rowmax, const void* plan, void* stream) {
   if (!in || !indptr || !norm || !tile_row0 || !tile_nrows || !tile_task || !W || !out) return GMETA_ERR_BAD_ARG;
   if (n_tiles < 0 || n_tasks <= 0 || f_in <= 0 || f_out <= 0 || ld_in < f_in || ld_out < f_out) return GMETA_ERR_BAD_ARG;
   if (ldw < (trans_w ? f_in : f_out)) return GMETA_ERR_BAD_ARG;
@@ -70,8 +75,8 @@ extern "C" int gmeta_gcn_layer_fwd_ex(const float* in, int32_t ld_in, const int3
       (impl == GMETA_IMPL_AUTO && pair_ok && ws_aligned &&
        workspace_bytes >= gcn_layer_fwd_pair_workspace_bytes(n_copies, n_tiles, n_tasks, n_rows, n_edges, f_in, f_out)))
     return gcn_layer_fwd_pair(g, tile_row0, tile_nrows, tile_task, n_tiles, n_tasks, n_copies, n_rows, n_edges,
-                              in_rowmax, W, w_task_stride, ldw, trans_w, bias, b_task_stride, f_out, relu, relu_mask,
-                              out, ld_out, out_rowmax, workspace, workspace_bytes, s);
+                              in_rowmax, plan, W, w_task_stride, ldw, trans_w, bias, b_task_stride, f_out, relu,
+                              relu_mask, out, ld_out, out_rowmax, workspace, workspace_bytes, s);
   const bool tc_ok = gcn_layer_fwd_tc_supported(g, ldw, trans_w, f_out, out, ld_out);
   if (impl == GMETA_IMPL_TCGEN05 && !tc_ok) return GMETA_ERR_UNSUPPORTED;
   // AUTO falls back to the FFMA kernel when no workspace for the weight image was provided
@@ -102,7 +107,7 @@ extern "C" int gmeta_gcn_layer_fwd(const float* in, int32_t ld_in, const int32_t
   return gmeta_gcn_layer_fwd_ex(in, ld_in, in_row_map, dst_rows, indptr, indices, norm, tile_row0, tile_nrows,
                                 tile_task, n_tiles, n_tasks, W, w_task_stride, ldw, trans_w, bias, b_task_stride, f_in,
                                 f_out, relu, relu_mask, out, ld_out, impl, workspace, workspace_bytes, 0, 0, nullptr,
-                                nullptr, stream);
+                                nullptr, nullptr, stream);
 }
 
 extern "C" int64_t gmeta_gcn_layer_fwd_workspace_bytes(int32_t n_tasks, int64_t w_task_stride, int32_t f_in,
@@ -129,4 +134,19 @@ extern "C" int64_t gmeta_gcn_layer_fwd_ex_workspace_bytes(int32_t n_tasks, int64
 extern "C" int gmeta_row_absmax(const float* x, int32_t ld, int32_t n_rows, int32_t f, float* out, void* stream) {
   if (!x || !out || n_rows < 0 || f <= 0 || ld < f) return GMETA_ERR_BAD_ARG;
   return row_absmax(x, ld, n_rows, f, out, (cudaStream_t)stream);
+}
+
+extern "C" int64_t gmeta_layer_plan_bytes(int32_t n_tiles, int32_t n_tasks, int32_t n_rows, int32_t n_edges) {
+  if (n_tiles < 0 || n_tasks <= 0 || n_rows < 0 || n_edges < 0) return -1;
+  return layer_plan_bytes(n_tiles, n_tasks, n_rows, n_edges);
+}
+
+extern "C" int gmeta_layer_plan_build(const int32_t* indptr, const int32_t* indices, const float* norm,
+                                      const int32_t* in_row_map, const int32_t* dst_rows, const int32_t* tile_row0,
+                                      const int32_t* tile_nrows, const int32_t* tile_task, int32_t n_tiles,
+                                      int32_t n_tasks, int32_t n_rows, int32_t n_edges, void* plan, void* stream) {
+  if (!indptr || !norm || !tile_row0 || !tile_nrows || !tile_task || !plan) return GMETA_ERR_BAD_ARG;
+  if (n_tiles < 0 || n_tasks <= 0 || n_rows < 0 || n_edges < 0) return GMETA_ERR_BAD_ARG;
+  return layer_plan_build(indptr, indices, norm, in_row_map, dst_rows, tile_row0, tile_nrows, tile_task, n_tiles,
+                          n_tasks, n_rows, n_edges, plan, (cudaStream_t)stream);
 }

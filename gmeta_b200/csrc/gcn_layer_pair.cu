@@ -29,13 +29,15 @@
 //     that a small edge-parallel kernel aggregates first; the fused kernel then reads a hub like
 //     a single neighbour with weight 1.
 //
-// Warp roles per CTA (704 threads): warps 0..15 gather producers (quarter-warp per row, 64-float
-// K chunks, fp32 sum -> scaled FP16 hi/lo -> 128B-swizzled K-major operand stage), warp 16 weight
-// loader (cp.async.bulk of the pre-split, pre-swizzled image), warp 17 MMA issuer (leader CTA
-// only; one thread), warps 18..21 epilogue (tcgen05.ld, * norm * 2^-e + bias, ReLU / mask, row
-// abs-max for the next layer, 16-byte stores).  Hand-offs are mbarriers; the peer CTA signals
-// the leader's barriers through the cluster address space, the MMA thread releases operand
-// stages / accumulators in both CTAs with multicast commits.
+// Warp roles per CTA (704 threads): warps 0..15 gather producers (one row per thread quad,
+// 32-float K chunks, the next chunk's segments requested before the current one is reduced:
+// fp32 sum -> scaled FP16 hi/lo -> 64B-swizzled K-major operand stage), warp 16 weight loader
+// (cp.async.bulk of the pre-split, pre-swizzled image), warp 17 MMA issuer (leader CTA only; one
+// thread), warps 18..21 epilogue (tcgen05.ld, * norm * 2^-e + bias, ReLU, transposed through
+// shared memory so that every store instruction writes whole 128-byte row segments, mask, row
+// abs-max for the next layer).  Hand-offs are mbarriers; the peer CTA signals the leader's
+// barriers through the cluster address space, the MMA thread releases operand stages /
+// accumulators in both CTAs with multicast commits.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -47,78 +49,97 @@ namespace {
 using namespace ptx;
 
 constexpr int TM = GMETA_TILE_ROWS;            // 128 rows per CTA tile; the pair's MMA has M = 256
-constexpr int KCH = 64;                        // fp16 elements per K chunk = one 128-byte swizzle row
-constexpr int A_HALF_BYTES = TM * 128;         // 16 KB: hi (or lo) operand tile of one chunk
-constexpr int STAGE_BYTES = 2 * A_HALF_BYTES;  // 32 KB
+constexpr int KCH = 32;                        // K elements per operand stage (64-byte swizzle rows of FP16)
+constexpr int WCH = 64;                        // K elements per resident weight chunk (128-byte swizzle rows)
+constexpr int A_HALF_BYTES = TM * 64;          // 8 KB: hi (or lo) operand tile of one chunk
+constexpr int STAGE_BYTES = 2 * A_HALF_BYTES;  // 16 KB
 constexpr int N_PROD_WARPS = 16;
 constexpr int WARP_LOAD = 16;
 constexpr int WARP_MMA = 17;
 constexpr int WARP_EPI0 = 18;
 constexpr int NTHREADS = 22 * 32;
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 6;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_COLS = 256;
 constexpr int PRE = 2;                         // in-neighbours per row the fused kernel gathers itself
-constexpr int SMEM_FIXED = 256 /*barriers*/ + 4 * TM /*row scale exponents*/;
+constexpr int EPI_LD = 36;                     // floats per row of an epilogue transpose tile (32 + pad, conflict-free)
+constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4; // one 32x32 tile per epilogue warp
+constexpr int SMEM_FIXED = 256 /*barriers*/ + 4 * TM /*row scale exponents*/ + EPI_BYTES;
 constexpr int SMEM_MAX = 227 * 1024;
 constexpr int PT_MAXT = 2048;                  // tasks the pair-table kernel handles
 constexpr int SCALE_TARGET = 13;               // scaled bound in [2^13, 2^14): 4x below the FP16 maximum
 constexpr int SCALE_CLAMP = 100;
 
-// ---- plan (structure only) ----
+// ---- plan (graph structure + tiling only; built once per packed set and operand mapping) ----
 struct PlanRec {      // 16 bytes per output row
   int r0, r1;         // mapped source rows of in-neighbours 0/1; hub row: r0 = slot, r1 = -1
   float n0, n1;       // their norms (0 = absent or dropped)
 };
 struct Plan {
-  int* hdr;           // [0] n_long  [1] n_long_edges  [2] n_pairs
+  int* hdr;           // [0] n_hubs  [1] n_hub_edges  [2] n_pairs
   PlanRec* rec;       // [n_rows]
   int2* pair_tiles;   // [cap_pairs] the two tiles of a pair (same task); .y = -1 when the task has an odd tile count
   int* pair_task;     // [cap_pairs]
-  int* long_row;      // [cap_long] real row of each hub slot
-  int* long_beg;      // [cap_long] first record of the slot in long_src / long_nrm
-  int* long_deg;      // [cap_long]
-  int* long_src;      // [n_edges] mapped source row of each hub edge
-  float* long_nrm;    // [n_edges]
+  int2* tile_hubs;    // [n_tiles] (first slot, count) of the tile's hub rows
+  int* hub_row;       // [cap_hub] real row of each hub slot
+  int* hub_beg;       // [cap_hub] first record of the slot in hub_src / hub_nrm
+  int* hub_deg;       // [cap_hub]
+  int* hub_src;       // [n_edges] mapped source row of each hub edge
+  float* hub_nrm;     // [n_edges]
+  int64_t total;
 };
 struct Workspace {
-  Plan plan;
   unsigned* w_absmax;   // [n_copies] bit pattern of max|W_c|
   float* w_inv_scale;   // [n_copies] 2^-e(c)
   __half* w_image;      // [n_copies][rank 2][K/64][hi|lo][N/2 rows][64 halves, 128B swizzle]
-  float* mlong;         // [cap_long][f_in] aggregated hub rows
-  float* mlong_rowmax;  // [cap_long]
+  float* mlong;         // [cap_hub][f_in] aggregated hub rows
+  float* mlong_bound;   // [cap_hub] sum_e norm_e * max|in[src_e,:]| >= max|mlong[slot,:]|
+  void* plan;           // plan built per call when the caller passes none
   int64_t total;
 };
 
 inline int64_t al(int64_t x) { return (x + 255) / 256 * 256; }
 inline int cap_pairs_for(int n_tiles, int n_tasks) { return (n_tiles + n_tasks) / 2 + 1; }
-inline int cap_long_for(int n_rows, int n_edges) {
+inline int cap_hub_for(int n_rows, int n_edges) {
   const int64_t by_edges = (int64_t)n_edges / (PRE + 1) + 1;
   return (int)(by_edges < n_rows ? by_edges : n_rows) + 1;
 }
 
-Workspace carve(void* base, int n_copies, int n_tiles, int n_tasks, int n_rows, int n_edges, int K, int N) {
+struct Carver {
+  char* p;
+  int64_t off;
+  char* take(int64_t bytes) { char* q = p ? p + off : nullptr; off += al(bytes); return q; }
+};
+
+Plan carve_plan(void* base, int n_tiles, int n_tasks, int n_rows, int n_edges) {
+  Plan pl;
+  Carver c{reinterpret_cast<char*>(base), 0};
+  const int cp = cap_pairs_for(n_tiles, n_tasks), ch = cap_hub_for(n_rows, n_edges);
+  pl.hdr = reinterpret_cast<int*>(c.take(256));
+  pl.rec = reinterpret_cast<PlanRec*>(c.take((int64_t)n_rows * 16));
+  pl.pair_tiles = reinterpret_cast<int2*>(c.take((int64_t)cp * 8));
+  pl.pair_task = reinterpret_cast<int*>(c.take((int64_t)cp * 4));
+  pl.tile_hubs = reinterpret_cast<int2*>(c.take((int64_t)n_tiles * 8));
+  pl.hub_row = reinterpret_cast<int*>(c.take((int64_t)ch * 4));
+  pl.hub_beg = reinterpret_cast<int*>(c.take((int64_t)ch * 4));
+  pl.hub_deg = reinterpret_cast<int*>(c.take((int64_t)ch * 4));
+  pl.hub_src = reinterpret_cast<int*>(c.take((int64_t)n_edges * 4 + 4));
+  pl.hub_nrm = reinterpret_cast<float*>(c.take((int64_t)n_edges * 4 + 4));
+  pl.total = c.off;
+  return pl;
+}
+
+Workspace carve_ws(void* base, int n_copies, int n_tiles, int n_tasks, int n_rows, int n_edges, int K, int N) {
   Workspace w;
-  char* p = reinterpret_cast<char*>(base);
-  int64_t off = 0;
-  auto take = [&](int64_t bytes) { char* q = p ? p + off : nullptr; off += al(bytes); return q; };
-  const int cp = cap_pairs_for(n_tiles, n_tasks), cl = cap_long_for(n_rows, n_edges);
-  w.plan.hdr = reinterpret_cast<int*>(take(256));
-  w.w_absmax = reinterpret_cast<unsigned*>(take((int64_t)n_copies * 4));
-  w.w_inv_scale = reinterpret_cast<float*>(take((int64_t)n_copies * 4));
-  w.w_image = reinterpret_cast<__half*>(take((int64_t)n_copies * 2 * K * N * 2));
-  w.plan.rec = reinterpret_cast<PlanRec*>(take((int64_t)n_rows * 16));
-  w.plan.pair_tiles = reinterpret_cast<int2*>(take((int64_t)cp * 8));
-  w.plan.pair_task = reinterpret_cast<int*>(take((int64_t)cp * 4));
-  w.plan.long_row = reinterpret_cast<int*>(take((int64_t)cl * 4));
-  w.plan.long_beg = reinterpret_cast<int*>(take((int64_t)cl * 4));
-  w.plan.long_deg = reinterpret_cast<int*>(take((int64_t)cl * 4));
-  w.plan.long_src = reinterpret_cast<int*>(take((int64_t)n_edges * 4 + 4));
-  w.plan.long_nrm = reinterpret_cast<float*>(take((int64_t)n_edges * 4 + 4));
-  w.mlong = reinterpret_cast<float*>(take((int64_t)cl * K * 4));
-  w.mlong_rowmax = reinterpret_cast<float*>(take((int64_t)cl * 4));
-  w.total = off;
+  Carver c{reinterpret_cast<char*>(base), 0};
+  const int ch = cap_hub_for(n_rows, n_edges);
+  w.w_absmax = reinterpret_cast<unsigned*>(c.take((int64_t)n_copies * 4));
+  w.w_inv_scale = reinterpret_cast<float*>(c.take((int64_t)n_copies * 4));
+  w.w_image = reinterpret_cast<__half*>(c.take((int64_t)n_copies * 2 * K * N * 2));
+  w.mlong = reinterpret_cast<float*>(c.take((int64_t)ch * K * 4));
+  w.mlong_bound = reinterpret_cast<float*>(c.take((int64_t)ch * 4));
+  w.plan = c.take(carve_plan(nullptr, n_tiles, n_tasks, n_rows, n_edges).total);
+  w.total = c.off;
   return w;
 }
 
@@ -136,7 +157,7 @@ struct PairParams {
   int f_in;
   const float* in_rowmax;
   const float* mlong;
-  const float* mlong_rowmax;
+  const float* mlong_bound;
   const PlanRec* rec;
   const int* hdr;
   const int2* pair_tiles;
@@ -158,7 +179,8 @@ struct PairParams {
   float* out_rowmax;
   int n_stages;
   int w_bytes;                   // this CTA's resident weight image: 2 * f_in * f_out bytes
-  int dbg;                       // debug ablation flags: 1 skip output stores, 2 skip gather loads, 4 issue 1/4 of the MMAs
+  int dbg;                       // debug ablation flags: 1 skip output stores, 2 skip gather loads, 4 issue 1/2 of the MMAs
+  long long* prof;               // optional [gridDim.x][16] cycle counters per role (debug), or NULL
 };
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
@@ -187,7 +209,7 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
   const int N = p.f_out, K = p.f_in;
   const int nkc = K / KCH;
   const int NS = p.n_stages;
-  const int half_n_bytes = (N / 2) * 128;                 // one chunk of W hi (or lo) in this CTA
+  const int half_n_bytes = (N / 2) * 128;                 // one 64-wide chunk of W hi (or lo) in this CTA
   uint8_t* w_s = smem;
   uint8_t* a_s = smem + p.w_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(a_s + (size_t)NS * STAGE_BYTES);
@@ -201,6 +223,7 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
   const uint32_t w_free = bar0 + 8u * (2 * MAX_STAGES + 6);              // per CTA: MMAs of the previous task are done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 8);
   int8_t* scale_e = reinterpret_cast<int8_t*>(bars) + 256;               // [4][TM]
+  float* epi_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256 + 4 * TM);
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) { printf("gmeta pair kernel: shared memory base not 1024-byte aligned\n"); __trap(); }
@@ -236,81 +259,89 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
 
   if (warp < N_PROD_WARPS) {
     // ===================== gather producers =====================
-    const int q = warp * 4 + (lane >> 3);   // a quarter-warp owns tile rows q and q + 64
-    const int sub = lane & 7;               // and, within a chunk, floats [8*sub, 8*sub + 8)
+    const int r = warp * 8 + (lane >> 2);   // a thread quad owns tile row r
+    const int sub = lane & 3;               // and, within a chunk, floats [8*sub, 8*sub + 8)
+    const int soff = r * 64 + ((sub ^ ((r >> 1) & 3)) << 4);   // 64B swizzle: 16-byte unit ^ ((row / 2) % 4)
     int it = 0, ti = 0;
+    long long t_setup = 0, t_wait = 0, t_body = 0, t_mark = clock64();
+    auto lap = [&](long long& acc) { const long long now = clock64(); acc += now - t_mark; t_mark = now; };
     for (int pr = p_beg; pr < p_end; ++pr, ++ti) {
       const int2 pt = p.pair_tiles[pr];
       const int tile = rank ? pt.y : pt.x;
       int nrows = 0, row0 = 0;
       if (tile >= 0) { nrows = p.tile_nrows[tile]; row0 = p.tile_row0[tile]; }
-      const float* src0[2];
-      const float* src1[2];
-      float n0[2], n1[2];
-#pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int r = q + 64 * rr;
-        src0[rr] = src1[rr] = p.in;
-        n0[rr] = n1[rr] = 0.f;
-        if (r < nrows) {
-          const int4 rc = __ldg(reinterpret_cast<const int4*>(p.rec + row0 + r));
-          const bool hub = rc.y < 0;
-          float a0 = __int_as_float(rc.z), a1 = __int_as_float(rc.w);
-          float rm0 = 0.f, rm1 = 0.f;
-          if (a0 != 0.f) {
-            src0[rr] = hub ? p.mlong + (size_t)rc.x * K : p.in + (size_t)rc.x * p.ld_in;
-            rm0 = hub ? p.mlong_rowmax[rc.x] : p.in_rowmax[rc.x];
-          }
-          if (a1 != 0.f) {
-            src1[rr] = p.in + (size_t)rc.y * p.ld_in;
-            rm1 = p.in_rowmax[rc.y];
-          }
-          const int e = scale_exponent(a0 * rm0 + a1 * rm1);
-          const float sc = exp2i(e);
-          n0[rr] = a0 * sc;
-          n1[rr] = a1 * sc;
-          if (sub == 0) scale_e[(ti & 3) * TM + r] = (int8_t)e;
+      const bool live = r < nrows;
+      const float* src0 = p.in;
+      const float* src1 = p.in;
+      float n0 = 0.f, n1 = 0.f;
+      if (live) {
+        const int4 rc = __ldg(reinterpret_cast<const int4*>(p.rec + row0 + r));
+        const bool hub = rc.y < 0;
+        const float a0 = __int_as_float(rc.z), a1 = __int_as_float(rc.w);
+        float rm0 = 0.f, rm1 = 0.f;
+        if (a0 != 0.f) {
+          src0 = hub ? p.mlong + (size_t)rc.x * K : p.in + (size_t)rc.x * p.ld_in;
+          rm0 = hub ? p.mlong_bound[rc.x] : p.in_rowmax[rc.x];
         }
+        if (a1 != 0.f) {
+          src1 = p.in + (size_t)rc.y * p.ld_in;
+          rm1 = p.in_rowmax[rc.y];
+        }
+        const int e = scale_exponent(a0 * rm0 + a1 * rm1);
+        const float sc = exp2i(e);
+        n0 = a0 * sc;
+        n1 = a1 * sc;
+        if (sub == 0) scale_e[(ti & 3) * TM + r] = (int8_t)e;
       }
+      src0 += sub * 8;
+      src1 += sub * 8;
+      // the segments of chunk kc+1 are requested before chunk kc is reduced and stored, so their
+      // latency overlaps the stage wait, the conversion and the stores
+      float4 xn[4];
+      auto request = [&](int kc) {
+        const bool g0 = n0 != 0.f && !(p.dbg & 2), g1 = n1 != 0.f && !(p.dbg & 2);
+        xn[0] = g0 ? ld_f4(src0 + kc * KCH) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xn[1] = g0 ? ld_f4(src0 + kc * KCH + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xn[2] = g1 ? ld_f4(src1 + kc * KCH) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xn[3] = g1 ? ld_f4(src1 + kc * KCH + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      request(0);
+      lap(t_setup);
       for (int kc = 0; kc < nkc; ++kc, ++it) {
         const int s = it % NS;
         const uint32_t ph = (uint32_t)((it / NS) & 1);
-        // issue this chunk's loads before waiting for the stage: their latency overlaps the wait
-        float4 x0[2][2], x1[2][2];
+        float4 x[4];
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr)
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int off = kc * KCH + sub * 8 + 4 * h;
-            x0[rr][h] = (n0[rr] != 0.f && !(p.dbg & 2)) ? ld_f4(src0[rr] + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-            x1[rr][h] = (n1[rr] != 0.f && !(p.dbg & 2)) ? ld_f4(src1[rr] + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+        for (int i = 0; i < 4; ++i) x[i] = xn[i];
+        if (kc + 1 < nkc) request(kc + 1);
+        lap(t_body);
         mbar_wait(empty(s), ph ^ 1u, 1);
-        uint8_t* stage = a_s + (size_t)s * STAGE_BYTES;
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-          const int r = q + 64 * rr;
-          if (r < nrows) {
-            float v[8];
-            v[0] = fmaf(n1[rr], x1[rr][0].x, n0[rr] * x0[rr][0].x);
-            v[1] = fmaf(n1[rr], x1[rr][0].y, n0[rr] * x0[rr][0].y);
-            v[2] = fmaf(n1[rr], x1[rr][0].z, n0[rr] * x0[rr][0].z);
-            v[3] = fmaf(n1[rr], x1[rr][0].w, n0[rr] * x0[rr][0].w);
-            v[4] = fmaf(n1[rr], x1[rr][1].x, n0[rr] * x0[rr][1].x);
-            v[5] = fmaf(n1[rr], x1[rr][1].y, n0[rr] * x0[rr][1].y);
-            v[6] = fmaf(n1[rr], x1[rr][1].z, n0[rr] * x0[rr][1].z);
-            v[7] = fmaf(n1[rr], x1[rr][1].w, n0[rr] * x0[rr][1].w);
-            uint4 hi, lo;
-            split8(v, hi, lo);
-            const int off = r * 128 + ((sub ^ (r & 7)) << 4);   // 128B swizzle: 16-byte unit ^ (row % 8)
-            *reinterpret_cast<uint4*>(stage + off) = hi;
-            *reinterpret_cast<uint4*>(stage + A_HALF_BYTES + off) = lo;
-          }
+        lap(t_wait);
+        if (live) {
+          float v[8];
+          v[0] = fmaf(n1, x[2].x, n0 * x[0].x);
+          v[1] = fmaf(n1, x[2].y, n0 * x[0].y);
+          v[2] = fmaf(n1, x[2].z, n0 * x[0].z);
+          v[3] = fmaf(n1, x[2].w, n0 * x[0].w);
+          v[4] = fmaf(n1, x[3].x, n0 * x[1].x);
+          v[5] = fmaf(n1, x[3].y, n0 * x[1].y);
+          v[6] = fmaf(n1, x[3].z, n0 * x[1].z);
+          v[7] = fmaf(n1, x[3].w, n0 * x[1].w);
+          uint4 hi, lo;
+          split8(v, hi, lo);
+          uint8_t* stage = a_s + (size_t)s * STAGE_BYTES;
+          *reinterpret_cast<uint4*>(stage + soff) = hi;
+          *reinterpret_cast<uint4*>(stage + A_HALF_BYTES + soff) = lo;
         }
         fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(a_full(s), 0);
       }
+      lap(t_body);
+    }
+    if (p.prof && (threadIdx.x == 0 || threadIdx.x == 511)) {
+      long long* o = p.prof + blockIdx.x * 16 + (threadIdx.x == 0 ? 0 : 3);
+      o[0] = t_setup; o[1] = t_wait; o[2] = t_body;
     }
   } else if (warp == WARP_LOAD) {
     // ===================== weight loader: one bulk copy per task change =====================
@@ -338,47 +369,65 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
     if (rank == 0 && lane == 0) {
       const uint32_t idesc = umma_idesc_f16(2 * TM, N);
       int it = 0, ti = 0, cur = -1, nw = 0;
+      long long t_w = 0, t_acc = 0, t_a = 0, t_issue = 0, t_mark = clock64();
+      auto lap = [&](long long& acc) { const long long now = clock64(); acc += now - t_mark; t_mark = now; };
       for (int pr = p_beg; pr < p_end; ++pr, ++ti) {
         const int task = p.pair_task[pr];
+        lap(t_issue);
         if (task != cur) {
           mbar_wait_cluster(w_ready, (uint32_t)(nw & 1), 4);
           cur = task;
           ++nw;
         }
+        lap(t_w);
         const int buf = ti & 1;
         mbar_wait_cluster(acc_empty(buf), (uint32_t)(((ti >> 1) & 1) ^ 1), 5);
+        lap(t_acc);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
         for (int kc = 0; kc < nkc; ++kc, ++it) {
           const int s = it % NS;
           const uint32_t ph = (uint32_t)((it / NS) & 1);
+          lap(t_issue);
           mbar_wait_cluster(a_full(s), ph, 6);
+          lap(t_a);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(a_s + (size_t)s * STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(w_s + (size_t)kc * 2 * half_n_bytes);
-          const uint64_t da_hi = umma_desc_k_sw128(a_addr);
-          const uint64_t da_lo = umma_desc_k_sw128(a_addr + A_HALF_BYTES);
+          const uint32_t b_addr = smem_u32(w_s + (size_t)(kc >> 1) * 2 * half_n_bytes);
+          const uint64_t da_hi = umma_desc_k_sw64(a_addr);
+          const uint64_t da_lo = umma_desc_k_sw64(a_addr + A_HALF_BYTES);
           const uint64_t db_hi = umma_desc_k_sw128(b_addr);
           const uint64_t db_lo = umma_desc_k_sw128(b_addr + half_n_bytes);
 #pragma unroll
           for (int k = 0; k < KCH / 16; ++k) {        // UMMA_K = 16 halves = 32 bytes = 2 descriptor units
             if ((p.dbg & 4) && k) break;
-            const uint64_t adv = (uint64_t)(2 * k);
-            tc_mma_f16_pair(d_tmem, da_hi + adv, db_hi + adv, idesc, (kc | k) != 0 ? 1u : 0u);
-            tc_mma_f16_pair(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
-            tc_mma_f16_pair(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
+            const uint64_t adv_a = (uint64_t)(2 * k);
+            const uint64_t adv_b = (uint64_t)(2 * ((kc & 1) * 2 + k));
+            tc_mma_f16_pair(d_tmem, da_hi + adv_a, db_hi + adv_b, idesc, (kc | k) != 0 ? 1u : 0u);
+            tc_mma_f16_pair(d_tmem, da_lo + adv_a, db_hi + adv_b, idesc, 1u);
+            tc_mma_f16_pair(d_tmem, da_hi + adv_a, db_lo + adv_b, idesc, 1u);
           }
           tc_commit_pair(empty(s));          // frees the stage in both CTAs once these MMAs have read it
         }
         tc_commit_pair(acc_full(buf));       // accumulators complete -> both epilogues
         if (pr + 1 < p_end && p.pair_task[pr + 1] != task) tc_commit_pair(w_free);
       }
+      lap(t_issue);
+      if (p.prof) {
+        long long* o = p.prof + blockIdx.x * 16 + 6;
+        o[0] = t_w; o[1] = t_acc; o[2] = t_a; o[3] = t_issue;
+      }
     }
   } else {
     // ===================== epilogue =====================
     const int quarter = warp & 3;            // TMEM lanes 32*quarter .. +31 are the ones this warp may read
     const int r = quarter * 32 + lane;
-    int ti = 0;
+    float* stg = epi_s + quarter * 32 * EPI_LD;
+    const int tr = lane >> 3, tc4 = (lane & 7) * 4;   // transposed read: rows 4*i + tr, columns tc4 .. +3
+    int ti = 0, bias_task = -1;
+    float4 bias_r[8];
+    long long t_wacc = 0, t_epi = 0, t_mark = clock64();
+    auto lap = [&](long long& acc) { const long long now = clock64(); acc += now - t_mark; t_mark = now; };
     for (int pr = p_beg; pr < p_end; ++pr, ++ti) {
       const int buf = ti & 1;
       const int2 pt = p.pair_tiles[pr];
@@ -391,56 +440,85 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       const int v = p.dst_rows ? p.dst_rows[oi] : oi;                 // real row: norm and mask
       const float nv = p.norm[v];
       const float wis = p.w_inv_scale[p.image_task_stride ? task : 0];
-      const float* bias = p.bias ? p.bias + (long long)task * p.b_task_stride : nullptr;
-      const float* mrow = p.relu_mask ? p.relu_mask + (size_t)v * p.ld_out : nullptr;
-      float* orow = p.out + (size_t)oi * p.ld_out;
+      if (task != bias_task) {     // this lane's bias columns (tc4 .. tc4+3 of every 32-column block), once per task
+        bias_task = task;
+        const float* bias = p.bias ? p.bias + (long long)task * p.b_task_stride : nullptr;
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+          bias_r[b] = (bias && 32 * b + tc4 < N) ? __ldg(reinterpret_cast<const float4*>(bias + 32 * b + tc4))
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      lap(t_epi);
       mbar_wait(acc_full(buf), (uint32_t)((ti >> 1) & 1), 7);
+      lap(t_wacc);
       tc_fence_after();
       const float f = live ? nv * exp2i(-(int)scale_e[(ti & 3) * TM + r]) * wis : 0.f;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * ACC_COLS);
-      float rmax = 0.f;
-      uint32_t acc_n[16];
-      tmem_ld16(t_addr, acc_n);
-      for (int c0 = 0; c0 < N; c0 += 16) {
-        uint32_t acc[16];
+      float pmax[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pmax[i] = 0.f;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const int c0 = 32 * b;
+        if (c0 >= N) break;
+        uint32_t acc[32];
+        if (c0 + 32 <= N) {
+          tmem_ld32(t_addr + (uint32_t)c0, acc);
+        } else {                                  // N % 32 == 16: last half block
+          uint32_t a16[16];
+          tmem_ld16(t_addr + (uint32_t)c0, a16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { acc[j] = a16[j]; acc[16 + j] = 0u; }
+        }
         tmem_ld_wait();
+        __syncwarp();                             // the previous block's transposed reads are done
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = acc_n[j];
-        if (c0 + 16 < N) tmem_ld16(t_addr + (uint32_t)(c0 + 16), acc_n);   // next chunk in flight
-        float o[16];
+        for (int j = 0; j < 32; j += 4)
+          st_f4(stg + lane * EPI_LD + j, make_float4(f * __uint_as_float(acc[j]), f * __uint_as_float(acc[j + 1]),
+                                                     f * __uint_as_float(acc[j + 2]), f * __uint_as_float(acc[j + 3])));
+        __syncwarp();
+        // transposed: a store instruction writes 4 rows x 128 contiguous bytes; bias / ReLU / mask here
+        const bool col_ok = c0 + tc4 < N;
+        const float4 b4 = bias_r[b];
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 b4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + c0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          o[j] = fmaf(f, __uint_as_float(acc[j]), b4.x);
-          o[j + 1] = fmaf(f, __uint_as_float(acc[j + 1]), b4.y);
-          o[j + 2] = fmaf(f, __uint_as_float(acc[j + 2]), b4.z);
-          o[j + 3] = fmaf(f, __uint_as_float(acc[j + 3]), b4.w);
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
-        }
-        if (mrow && live) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 m4 = ld_f4(mrow + c0 + j);
-            if (!(m4.x > 0.f)) o[j] = 0.f;
-            if (!(m4.y > 0.f)) o[j + 1] = 0.f;
-            if (!(m4.z > 0.f)) o[j + 2] = 0.f;
-            if (!(m4.w > 0.f)) o[j + 3] = 0.f;
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + tr;
+          const int vr = __shfl_sync(0xffffffffu, v, rr);       // real row of tile row quarter*32 + rr
+          if (quarter * 32 + rr < nrows && col_ok) {
+            float4 w4 = ld_f4(stg + rr * EPI_LD + tc4);
+            w4.x += b4.x; w4.y += b4.y; w4.z += b4.z; w4.w += b4.w;
+            if (p.relu) { w4.x = fmaxf(w4.x, 0.f); w4.y = fmaxf(w4.y, 0.f); w4.z = fmaxf(w4.z, 0.f); w4.w = fmaxf(w4.w, 0.f); }
+            if (p.relu_mask) {
+              const float4 m4 = ld_f4(p.relu_mask + (size_t)vr * p.ld_out + c0 + tc4);
+              if (!(m4.x > 0.f)) w4.x = 0.f;
+              if (!(m4.y > 0.f)) w4.y = 0.f;
+              if (!(m4.z > 0.f)) w4.z = 0.f;
+              if (!(m4.w > 0.f)) w4.w = 0.f;
+            }
+            pmax[i] = fmaxf(pmax[i], fmaxf(fmaxf(fabsf(w4.x), fabsf(w4.y)), fmaxf(fabsf(w4.z), fabsf(w4.w))));
+            if (!(p.dbg & 1)) st_f4(p.out + (size_t)(row0 + quarter * 32 + rr) * p.ld_out + c0 + tc4, w4);
           }
         }
+      }
+      if (p.out_rowmax) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) rmax = fmaxf(rmax, fabsf(o[j]));
-        if (live && !(p.dbg & 1)) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) st_f4(orow + c0 + j, make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]));
+        for (int i = 0; i < 8; ++i) {
+          float m = pmax[i];
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+          const int rr = 4 * i + tr;
+          if ((lane & 7) == 0 && quarter * 32 + rr < nrows) p.out_rowmax[row0 + quarter * 32 + rr] = m;
         }
       }
-      if (p.out_rowmax && live) p.out_rowmax[oi] = rmax;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(acc_empty(buf), 0);
+    }
+    lap(t_epi);
+    if (p.prof && warp == WARP_EPI0 && lane == 0) {
+      long long* o = p.prof + blockIdx.x * 16 + 10;
+      o[0] = t_wacc; o[1] = t_epi;
     }
   }
 
@@ -477,7 +555,7 @@ __global__ void __launch_bounds__(256) w_absmax_kernel(const float* __restrict__
 __global__ void pack_w_pair_kernel(const float* __restrict__ W, long long w_stride, int ldw, int trans, int K, int N,
                                    int n_copies, const unsigned* __restrict__ absmax, __half* __restrict__ image,
                                    long long image_stride, float* __restrict__ w_inv_scale) {
-  const int ku = K / 8, nkc = K / KCH, hn = N / 2;
+  const int ku = K / 8, nwc = K / WCH, hn = N / 2;
   const long long total = (long long)n_copies * ku * N;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -497,7 +575,7 @@ __global__ void pack_w_pair_kernel(const float* __restrict__ W, long long w_stri
     uint4 hi, lo;
     split8(v, hi, lo);
     const int rank = n / hn, nn = n - rank * hn, kc = u >> 3, unit = u & 7;
-    __half* dst = image + c * image_stride + ((((size_t)rank * nkc + kc) * 2) * hn + nn) * 64 + ((unit ^ (nn & 7)) << 3);
+    __half* dst = image + c * image_stride + ((((size_t)rank * nwc + kc) * 2) * hn + nn) * 64 + ((unit ^ (nn & 7)) << 3);
     *reinterpret_cast<uint4*>(dst) = hi;
     *reinterpret_cast<uint4*>(dst + (size_t)hn * 64) = lo;
   }
@@ -519,48 +597,92 @@ __global__ void row_absmax_kernel(const float* __restrict__ x, int ld, int n_row
 // ------------------------------------------------------------------------------------------
 // plan construction (structure only) and the hub-row pre-aggregation
 // ------------------------------------------------------------------------------------------
-__global__ void plan_classify_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                                     const float* __restrict__ norm, const int32_t* __restrict__ in_row_map,
-                                     const int32_t* __restrict__ dst_rows, int n_rows, Plan pl) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += gridDim.x * blockDim.x) {
-    const int v = dst_rows ? dst_rows[i] : i;
-    const int beg = indptr[v], deg = indptr[v + 1] - beg;
-    PlanRec r = {0, 0, 0.f, 0.f};
-    if (deg > PRE) {
-      const int slot = atomicAdd(pl.hdr + 0, 1);          // slot order does not affect any value
-      pl.long_row[slot] = v;
-      pl.long_beg[slot] = atomicAdd(pl.hdr + 1, deg);
-      pl.long_deg[slot] = deg;
-      r.r0 = slot; r.r1 = -1; r.n0 = 1.f;
-    } else {
-      if (deg > 0) {
-        const int u = indices[beg];
-        const int s = in_row_map ? in_row_map[u] : u;
-        if (s >= 0) { r.r0 = s; r.n0 = norm[u]; }          // negative map entry: neighbour dropped
+__device__ __forceinline__ int warp_incl_scan(int x, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  return x;
+}
+
+// one warp per tile: row records, and the tile's hub rows as one contiguous run of slots
+__global__ void plan_tiles_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                  const float* __restrict__ norm, const int32_t* __restrict__ in_row_map,
+                                  const int32_t* __restrict__ dst_rows, const int32_t* __restrict__ tile_row0,
+                                  const int32_t* __restrict__ tile_nrows, int n_tiles, Plan pl) {
+  const int lane = threadIdx.x & 31;
+  for (int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < n_tiles; tile += (gridDim.x * blockDim.x) >> 5) {
+    const int row0 = tile_row0[tile], nrows = tile_nrows[tile];
+    int v[4], beg[4], deg[4], hrank[4], eoff[4];
+    bool hub[4];
+    int n_h = 0, n_e = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = 32 * j + lane;
+      v[j] = 0; beg[j] = 0; deg[j] = 0;
+      if (r < nrows) {
+        v[j] = dst_rows ? dst_rows[row0 + r] : row0 + r;
+        beg[j] = indptr[v[j]];
+        deg[j] = indptr[v[j] + 1] - beg[j];
       }
-      if (deg > 1) {
-        const int u = indices[beg + 1];
-        const int s = in_row_map ? in_row_map[u] : u;
-        if (s >= 0) { r.r1 = s; r.n1 = norm[u]; }
-      }
+      hub[j] = deg[j] > PRE;
+      const unsigned bal = __ballot_sync(0xffffffffu, hub[j]);
+      hrank[j] = n_h + __popc(bal & ((1u << lane) - 1u));
+      n_h += __popc(bal);
+      const int incl = warp_incl_scan(hub[j] ? deg[j] : 0, lane);
+      eoff[j] = n_e + incl - (hub[j] ? deg[j] : 0);
+      n_e += __shfl_sync(0xffffffffu, incl, 31);
     }
-    pl.rec[i] = r;
+    int hbase = 0, ebase = 0;
+    if (lane == 0 && n_h > 0) {
+      hbase = atomicAdd(pl.hdr + 0, n_h);        // the order of tiles among the slots does not affect any value
+      ebase = atomicAdd(pl.hdr + 1, n_e);
+    }
+    hbase = __shfl_sync(0xffffffffu, hbase, 0);
+    ebase = __shfl_sync(0xffffffffu, ebase, 0);
+    if (lane == 0) pl.tile_hubs[tile] = make_int2(hbase, n_h);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = 32 * j + lane;
+      if (r >= nrows) continue;
+      PlanRec rc = {0, 0, 0.f, 0.f};
+      if (hub[j]) {
+        const int slot = hbase + hrank[j];
+        pl.hub_row[slot] = v[j];
+        pl.hub_beg[slot] = ebase + eoff[j];
+        pl.hub_deg[slot] = deg[j];
+        rc.r0 = slot; rc.r1 = -1; rc.n0 = 1.f;
+      } else {
+        if (deg[j] > 0) {
+          const int u = indices[beg[j]];
+          const int s = in_row_map ? in_row_map[u] : u;
+          if (s >= 0) { rc.r0 = s; rc.n0 = norm[u]; }          // negative map entry: neighbour dropped
+        }
+        if (deg[j] > 1) {
+          const int u = indices[beg[j] + 1];
+          const int s = in_row_map ? in_row_map[u] : u;
+          if (s >= 0) { rc.r1 = s; rc.n1 = norm[u]; }
+        }
+      }
+      pl.rec[row0 + r] = rc;
+    }
   }
 }
 
 // one warp per hub slot: its edges, coalesced, in CSR order
-__global__ void plan_long_edges_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                                       const float* __restrict__ norm, const int32_t* __restrict__ in_row_map,
-                                       Plan pl) {
-  const int n_long = pl.hdr[0];
+__global__ void plan_hub_edges_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                      const float* __restrict__ norm, const int32_t* __restrict__ in_row_map,
+                                      Plan pl) {
+  const int n_hub = pl.hdr[0];
   const int lane = threadIdx.x & 31;
-  for (int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < n_long; slot += (gridDim.x * blockDim.x) >> 5) {
-    const int beg = indptr[pl.long_row[slot]], deg = pl.long_deg[slot], dst = pl.long_beg[slot];
+  for (int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < n_hub; slot += (gridDim.x * blockDim.x) >> 5) {
+    const int beg = indptr[pl.hub_row[slot]], deg = pl.hub_deg[slot], dst = pl.hub_beg[slot];
     for (int e = lane; e < deg; e += 32) {
       const int u = indices[beg + e];
       const int s = in_row_map ? in_row_map[u] : u;
-      pl.long_src[dst + e] = s < 0 ? 0 : s;
-      pl.long_nrm[dst + e] = s < 0 ? 0.f : norm[u];
+      pl.hub_src[dst + e] = s < 0 ? 0 : s;
+      pl.hub_nrm[dst + e] = s < 0 ? 0.f : norm[u];
     }
   }
 }
@@ -577,7 +699,7 @@ __global__ void __launch_bounds__(1024) pair_table_kernel(const int32_t* __restr
     atomicAdd(&cnt[t], 1);
   }
   __syncthreads();
-  // exclusive scan of ceil(cnt/2) over tasks (Hillis-Steele, double buffered)
+  // inclusive scan of ceil(cnt/2) over tasks (Hillis-Steele, double buffered)
   for (int t = threadIdx.x; t < n_tasks; t += blockDim.x) base[t] = (cnt[t] + 1) >> 1;
   __syncthreads();
   int* a = base;
@@ -587,7 +709,7 @@ __global__ void __launch_bounds__(1024) pair_table_kernel(const int32_t* __restr
     __syncthreads();
     int* c = a; a = b; b = c;
   }
-  const int total = n_tasks > 0 ? a[n_tasks - 1] : 0;     // inclusive sums in a[]
+  const int total = n_tasks > 0 ? a[n_tasks - 1] : 0;
   for (int i = threadIdx.x; i < total; i += blockDim.x) pl.pair_tiles[i] = make_int2(-1, -1);
   __syncthreads();
   for (int i = threadIdx.x; i < n_tiles; i += blockDim.x) {
@@ -600,64 +722,65 @@ __global__ void __launch_bounds__(1024) pair_table_kernel(const int32_t* __restr
   if (threadIdx.x == 0) pl.hdr[2] = total;
 }
 
-// mlong[slot][:] = sum_e long_nrm[e] * in[long_src[e]][:] and its abs-max, for every hub slot.  One CTA
-// per slot at a time; thread groups of f_in/4 threads take edges round-robin (8 in flight each), partial
-// sums are added in group order -> deterministic.
-constexpr int LR_THREADS = 256;
-__global__ void __launch_bounds__(LR_THREADS) long_rows_kernel(const float* __restrict__ in, int ld_in, int f_in,
-                                                               Plan pl, float* __restrict__ mlong,
-                                                               float* __restrict__ mlong_rowmax) {
-  __shared__ __align__(16) float part[LR_THREADS * 4];
-  __shared__ float wmax[LR_THREADS / 32];
-  const int n_long = pl.hdr[0];
-  const int tpr = f_in >> 2, G = LR_THREADS / tpr;
-  const int g = threadIdx.x / tpr, cu = threadIdx.x - g * tpr;
-  for (int slot = blockIdx.x; slot < n_long; slot += gridDim.x) {
-    const int beg = pl.long_beg[slot], deg = pl.long_deg[slot];
+// mlong[slot][:] = sum_e hub_nrm[e] * in[hub_src[e]][:] for every hub slot, and the bound
+// sum_e hub_nrm[e] * in_rowmax[hub_src[e]].  One warp per (slot, 32-column slice): no reduction across
+// warps; inside the warp the four 8-lane groups take edges round-robin (8 x 16 bytes in flight per
+// lane) and are combined with a fixed shuffle tree -> deterministic.
+__global__ void __launch_bounds__(256) hub_rows_kernel(const float* __restrict__ in, int ld_in, int f_in,
+                                                       const float* __restrict__ in_rowmax, Plan pl,
+                                                       float* __restrict__ mlong, float* __restrict__ mlong_bound) {
+  const int n_hub = pl.hdr[0];
+  const int n_slices = f_in >> 5;
+  const int lane = threadIdx.x & 31, g = lane >> 3, c4 = (lane & 7) * 4;
+  const long long items = (long long)n_hub * n_slices;
+  for (long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; w < items;
+       w += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const int slot = (int)(w / n_slices), slice = (int)(w - (long long)slot * n_slices);
+    const int beg = pl.hub_beg[slot], deg = pl.hub_deg[slot];
+    const float* col = in + 32 * slice + c4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (g < G) {
-      for (int e = g; e < deg; e += 8 * G) {
-        float4 xv[8];
-        float nn[8];
+    float bsum = 0.f;
+    for (int base = 0; base < deg; base += 32) {
+      const int e = base + lane;
+      int s = 0;
+      float nr = 0.f;
+      if (e < deg) { s = pl.hub_src[beg + e]; nr = pl.hub_nrm[beg + e]; }
+      if (slice == 0 && nr != 0.f) bsum = fmaf(nr, in_rowmax[s], bsum);
+      float4 xv[8];
+      float wv[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int ee = e + j * G;
-          const bool ok = ee < deg;
-          nn[j] = ok ? pl.long_nrm[beg + ee] : 0.f;
-          xv[j] = ok ? ld_f4(in + (size_t)pl.long_src[beg + ee] * ld_in + 4 * cu) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+      for (int j = 0; j < 8; ++j) {
+        const int idx = 4 * j + g;
+        wv[j] = __shfl_sync(0xffffffffu, nr, idx);
+        const int sj = __shfl_sync(0xffffffffu, s, idx);
+        xv[j] = wv[j] != 0.f ? ld_f4(col + (size_t)sj * ld_in) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          acc.x = fmaf(nn[j], xv[j].x, acc.x);
-          acc.y = fmaf(nn[j], xv[j].y, acc.y);
-          acc.z = fmaf(nn[j], xv[j].z, acc.z);
-          acc.w = fmaf(nn[j], xv[j].w, acc.w);
-        }
+      for (int j = 0; j < 8; ++j) {
+        acc.x = fmaf(wv[j], xv[j].x, acc.x);
+        acc.y = fmaf(wv[j], xv[j].y, acc.y);
+        acc.z = fmaf(wv[j], xv[j].z, acc.z);
+        acc.w = fmaf(wv[j], xv[j].w, acc.w);
       }
-      st_f4(part + threadIdx.x * 4, acc);
-    }
-    __syncthreads();
-    float m = 0.f;
-    if (g == 0) {
-      for (int g2 = 1; g2 < G; ++g2) {
-        const float4 v = ld_f4(part + (g2 * tpr + cu) * 4);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-      }
-      st_f4(mlong + (size_t)slot * f_in + 4 * cu, acc);
-      m = fmaxf(fmaxf(fabsf(acc.x), fabsf(acc.y)), fmaxf(fabsf(acc.z), fabsf(acc.w)));
     }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int i = 1; i < LR_THREADS / 32; ++i) m = fmaxf(m, wmax[i]);
-      mlong_rowmax[slot] = m;
+    for (int o = 8; o <= 16; o <<= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+      acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (g == 0) st_f4(mlong + (size_t)slot * f_in + 32 * slice + c4, acc);
+    if (slice == 0) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+      if (lane == 0) mlong_bound[slot] = bsum;
     }
   }
 }
 
 int g_pair_dbg = 0;
+long long* g_pair_prof = nullptr;
 
 int stages_for(int K, int N) {
   const int w_bytes = 2 * K * N;
@@ -671,17 +794,41 @@ bool gcn_layer_fwd_pair_supported(const GatherSrc& g, int f_out, const float* bi
                                   const float* relu_mask, const float* out, int ld_out, int n_tasks) {
   if (bias && (!aligned16(bias) || b_task_stride % 4 != 0)) return false;
   if (relu_mask && !aligned16(relu_mask)) return false;
-  if (g.f_in % KCH != 0 || g.f_in < KCH || g.f_in > 1024) return false;
+  if (g.f_in % WCH != 0 || g.f_in < WCH || g.f_in > 1024) return false;
   if (f_out % 16 != 0 || f_out < 16 || f_out > 256) return false;
   if (g.ld_in % 4 != 0 || !aligned16(g.in) || g.ld_in < g.f_in) return false;
   if (ld_out % 4 != 0 || !aligned16(out)) return false;
   if (n_tasks > PT_MAXT) return false;
-  return stages_for(g.f_in, f_out) >= 2;
+  return stages_for(g.f_in, f_out) >= 3;
+}
+
+int64_t layer_plan_bytes(int n_tiles, int n_tasks, int n_rows, int n_edges) {
+  return carve_plan(nullptr, n_tiles, n_tasks, n_rows, n_edges).total;
+}
+
+int layer_plan_build(const int32_t* indptr, const int32_t* indices, const float* norm, const int32_t* in_row_map,
+                     const int32_t* dst_rows, const int32_t* tile_row0, const int32_t* tile_nrows,
+                     const int32_t* tile_task, int n_tiles, int n_tasks, int n_rows, int n_edges, void* plan,
+                     cudaStream_t stream) {
+  if (n_tasks > PT_MAXT) return GMETA_ERR_UNSUPPORTED;
+  if (!plan || (reinterpret_cast<uintptr_t>(plan) & 255u)) return GMETA_ERR_ALIGN;
+  Plan pl = carve_plan(plan, n_tiles, n_tasks, n_rows, n_edges);
+  if (cudaMemsetAsync(pl.hdr, 0, 256, stream) != cudaSuccess) return GMETA_ERR_LAUNCH;
+  if (n_tiles == 0) return GMETA_OK;
+  int rc;
+  const int grid = ceil_div(n_tiles, 8) < 8 * kNumSMs ? ceil_div(n_tiles, 8) : 8 * kNumSMs;
+  plan_tiles_kernel<<<grid, 256, 0, stream>>>(indptr, indices, norm, in_row_map, dst_rows, tile_row0, tile_nrows,
+                                             n_tiles, pl);
+  if ((rc = check_launch()) != GMETA_OK) return rc;
+  plan_hub_edges_kernel<<<4 * kNumSMs, 256, 0, stream>>>(indptr, indices, norm, in_row_map, pl);
+  if ((rc = check_launch()) != GMETA_OK) return rc;
+  pair_table_kernel<<<1, 1024, 0, stream>>>(tile_task, n_tiles, n_tasks, pl);
+  return check_launch();
 }
 
 int64_t gcn_layer_fwd_pair_workspace_bytes(int n_copies, int n_tiles, int n_tasks, int n_rows, int n_edges, int f_in,
                                            int f_out) {
-  return carve(nullptr, n_copies, n_tiles, n_tasks, n_rows, n_edges, f_in, f_out).total;
+  return carve_ws(nullptr, n_copies, n_tiles, n_tasks, n_rows, n_edges, f_in, f_out).total;
 }
 
 int row_absmax(const float* x, int ld, int n_rows, int f, float* out, cudaStream_t stream) {
@@ -693,20 +840,25 @@ int row_absmax(const float* x, int ld, int n_rows, int f, float* out, cudaStream
 
 int gcn_layer_fwd_pair(const GatherSrc& g, const int32_t* tile_row0, const int32_t* tile_nrows,
                        const int32_t* tile_task, int n_tiles, int n_tasks, int n_copies, int n_rows, int n_edges,
-                       const float* in_rowmax, const float* W, int64_t w_task_stride, int ldw, int trans_w,
-                       const float* bias, int64_t b_task_stride, int f_out, int relu, const float* relu_mask,
-                       float* out, int ld_out, float* out_rowmax, void* workspace, int64_t workspace_bytes,
-                       cudaStream_t stream) {
+                       const float* in_rowmax, const void* plan, const float* W, int64_t w_task_stride, int ldw,
+                       int trans_w, const float* bias, int64_t b_task_stride, int f_out, int relu,
+                       const float* relu_mask, float* out, int ld_out, float* out_rowmax, void* workspace,
+                       int64_t workspace_bytes, cudaStream_t stream) {
   const int K = g.f_in, N = f_out;
   if (!in_rowmax || n_rows <= 0 || n_edges < 0) return GMETA_ERR_BAD_ARG;
   if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return GMETA_ERR_WORKSPACE;
-  Workspace ws = carve(workspace, n_copies, n_tiles, n_tasks, n_rows, n_edges, K, N);
+  if (plan && (reinterpret_cast<uintptr_t>(plan) & 255u)) return GMETA_ERR_ALIGN;
+  Workspace ws = carve_ws(workspace, n_copies, n_tiles, n_tasks, n_rows, n_edges, K, N);
   if (workspace_bytes < ws.total) return GMETA_ERR_WORKSPACE;
   int rc;
-  // header + weight abs-max are adjacent: one memset
-  if (cudaMemsetAsync(ws.plan.hdr, 0, (size_t)(reinterpret_cast<char*>(ws.w_inv_scale) - reinterpret_cast<char*>(ws.plan.hdr)),
-                      stream) != cudaSuccess)
-    return GMETA_ERR_LAUNCH;
+  if (!plan) {
+    rc = layer_plan_build(g.indptr, g.indices, g.norm, g.in_row_map, g.dst_rows, tile_row0, tile_nrows, tile_task,
+                          n_tiles, n_tasks, n_rows, n_edges, ws.plan, stream);
+    if (rc != GMETA_OK) return rc;
+    plan = ws.plan;
+  }
+  const Plan pl = carve_plan(const_cast<void*>(plan), n_tiles, n_tasks, n_rows, n_edges);
+  if (cudaMemsetAsync(ws.w_absmax, 0, (size_t)n_copies * 4, stream) != cudaSuccess) return GMETA_ERR_LAUNCH;
   {
     w_absmax_kernel<<<dim3(8, n_copies), 256, 0, stream>>>(W, w_task_stride, ldw, trans_w, K, N, ws.w_absmax);
     if ((rc = check_launch()) != GMETA_OK) return rc;
@@ -716,22 +868,12 @@ int gcn_layer_fwd_pair(const GatherSrc& g, const int32_t* tile_row0, const int32
                                                 ws.w_image, 2LL * K * N, ws.w_inv_scale);
     if ((rc = check_launch()) != GMETA_OK) return rc;
   }
-  {
-    const int grid = ceil_div(n_rows, 256) < 8 * kNumSMs ? ceil_div(n_rows, 256) : 8 * kNumSMs;
-    plan_classify_kernel<<<grid, 256, 0, stream>>>(g.indptr, g.indices, g.norm, g.in_row_map, g.dst_rows, n_rows,
-                                                  ws.plan);
-    if ((rc = check_launch()) != GMETA_OK) return rc;
-    plan_long_edges_kernel<<<4 * kNumSMs, 256, 0, stream>>>(g.indptr, g.indices, g.norm, g.in_row_map, ws.plan);
-    if ((rc = check_launch()) != GMETA_OK) return rc;
-    pair_table_kernel<<<1, 1024, 0, stream>>>(tile_task, n_tiles, n_tasks, ws.plan);
-    if ((rc = check_launch()) != GMETA_OK) return rc;
-    long_rows_kernel<<<8 * kNumSMs, LR_THREADS, 0, stream>>>(g.in, g.ld_in, K, ws.plan, ws.mlong, ws.mlong_rowmax);
-    if ((rc = check_launch()) != GMETA_OK) return rc;
-  }
+  hub_rows_kernel<<<8 * kNumSMs, 256, 0, stream>>>(g.in, g.ld_in, K, in_rowmax, pl, ws.mlong, ws.mlong_bound);
+  if ((rc = check_launch()) != GMETA_OK) return rc;
   PairParams p;
   p.in = g.in; p.ld_in = g.ld_in; p.f_in = K; p.in_rowmax = in_rowmax;
-  p.mlong = ws.mlong; p.mlong_rowmax = ws.mlong_rowmax;
-  p.rec = ws.plan.rec; p.hdr = ws.plan.hdr; p.pair_tiles = ws.plan.pair_tiles; p.pair_task = ws.plan.pair_task;
+  p.mlong = ws.mlong; p.mlong_bound = ws.mlong_bound;
+  p.rec = pl.rec; p.hdr = pl.hdr; p.pair_tiles = pl.pair_tiles; p.pair_task = pl.pair_task;
   p.tile_row0 = tile_row0; p.tile_nrows = tile_nrows; p.dst_rows = g.dst_rows; p.norm = g.norm;
   p.w_image = ws.w_image; p.image_task_stride = n_copies > 1 ? 2LL * K * N : 0; p.w_inv_scale = ws.w_inv_scale;
   p.bias = bias; p.b_task_stride = b_task_stride; p.f_out = N; p.relu = relu; p.relu_mask = relu_mask;
@@ -739,6 +881,7 @@ int gcn_layer_fwd_pair(const GatherSrc& g, const int32_t* tile_row0, const int32
   p.n_stages = stages_for(K, N);
   p.w_bytes = 2 * K * N;   // bytes per CTA: K x N/2 halves, hi + lo
   p.dbg = g_pair_dbg;
+  p.prof = g_pair_prof;
   const size_t smem = (size_t)p.w_bytes + (size_t)p.n_stages * STAGE_BYTES + SMEM_FIXED;
   static int n_clusters = -1;
   if (n_clusters < 0) {
@@ -765,3 +908,4 @@ int gcn_layer_fwd_pair(const GatherSrc& g, const int32_t* tile_row0, const int32
 
 // Debug ablation switches of the CTA-pair kernel for performance triage (results are WRONG with any flag set).
 extern "C" void gmeta_debug_set_pair_flags(int flags) { gmeta::g_pair_dbg = flags; }
+extern "C" void gmeta_debug_set_pair_profile(long long* device_buffer) { gmeta::g_pair_prof = device_buffer; }

@@ -151,7 +151,10 @@ int64_t gmeta_gcn_layer_fwd_workspace_bytes(int32_t n_tasks, int64_t w_task_stri
  * (f_in % 64 == 0, f_out % 16 == 0, f_out <= 256, 2*f_in*f_out + 64 KB <= 227 KB of shared memory,
  * n_tasks <= 2048): the row abs-max vector gives the rigorous per-row bound from which the
  * FP16 operand scaling is derived (csrc/gcn_layer_pair.cu).  The tile table must list the tiles
- * of a task contiguously.  Workspace: gmeta_gcn_layer_fwd_ex_workspace_bytes, 256-byte aligned. */
+ * of a task contiguously.  Workspace: gmeta_gcn_layer_fwd_ex_workspace_bytes, 256-byte aligned.
+ *   plan       a layer plan built by gmeta_layer_plan_build for exactly these (indptr, indices,
+ *              norm, in_row_map, dst_rows, tile table) arguments, or NULL (then it is rebuilt
+ *              inside the workspace on every call).  Only GMETA_IMPL_TCPAIR uses it. */
 int gmeta_gcn_layer_fwd_ex(const float* in, int32_t ld_in, const int32_t* in_row_map,
                            const int32_t* dst_rows, const int32_t* indptr, const int32_t* indices, const float* norm,
                            const int32_t* tile_row0, const int32_t* tile_nrows,
@@ -162,10 +165,21 @@ int gmeta_gcn_layer_fwd_ex(const float* in, int32_t ld_in, const int32_t* in_row
                            float* out, int32_t ld_out, int32_t impl,
                            void* workspace, int64_t workspace_bytes,
                            int32_t n_rows, int32_t n_edges, const float* in_rowmax, float* out_rowmax,
-                           void* stream);
+                           const void* plan, void* stream);
 int64_t gmeta_gcn_layer_fwd_ex_workspace_bytes(int32_t n_tasks, int64_t w_task_stride, int32_t n_tiles,
                                                int32_t n_rows, int32_t n_edges, int32_t f_in,
                                                int32_t f_out, int32_t impl);
+
+/* Layer plan: everything the CTA-pair layer kernel derives from the graph STRUCTURE and the
+ * tiling alone (per-row source rows / norms of the first two in-neighbours, hub rows and their
+ * flattened edge lists, pairs of same-task tiles).  Build once per packed set and operand mapping,
+ * reuse for every layer call of the meta-step.  `plan` is caller-owned, 256-byte aligned. */
+int64_t gmeta_layer_plan_bytes(int32_t n_tiles, int32_t n_tasks, int32_t n_rows, int32_t n_edges);
+int gmeta_layer_plan_build(const int32_t* indptr, const int32_t* indices, const float* norm,
+                           const int32_t* in_row_map, const int32_t* dst_rows,
+                           const int32_t* tile_row0, const int32_t* tile_nrows, const int32_t* tile_task,
+                           int32_t n_tiles, int32_t n_tasks, int32_t n_rows, int32_t n_edges,
+                           void* plan, void* stream);
 
 /* out[r] = max_k |x[r*ld + k]|, k < f  (prepares in_rowmax for gmeta_gcn_layer_fwd_ex). */
 int gmeta_row_absmax(const float* x, int32_t ld, int32_t n_rows, int32_t f, float* out, void* stream);
@@ -178,6 +192,7 @@ void gmeta_debug_set_tc_profile(long long* device_buffer);
 void gmeta_debug_set_tc_flags(int flags);
 /* Same for the CTA-pair kernel: 1 skip output stores, 2 skip gather loads, 4 issue 1/4 of the MMAs. */
 void gmeta_debug_set_pair_flags(int flags);
+void gmeta_debug_set_pair_profile(long long* device_buffer);
 
 /* Weight/bias gradient of one GCN layer (the autograd.grad of meta.py:125,149 for that layer):
  *   dW[t][k,j] = sum_{v in task t} norm[v] * M[v,k] * dZ[v,j],   db[t][j] = sum_v dZ[v,j]

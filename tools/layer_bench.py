@@ -55,6 +55,7 @@ def main():
     ap.add_argument("--impls", default="1,2")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--ablate", default="", help="comma list of debug flag masks to time (tcgen05 impl)")
+    ap.add_argument("--plan", type=int, default=1, help="1: reuse a prebuilt layer plan (impl 3); 0: rebuild per call")
     ap.add_argument("--profile", action="store_true", help="per-role cycle counters of the tcgen05 kernel")
     a = ap.parse_args()
     L = _lib.lib()
@@ -79,6 +80,12 @@ def main():
     alg = 4.0 * (N * a.fin + N * a.fout + E + N + 1 + a.tasks * (a.fin * a.fout + a.fout))
     res = {}
     outs = {}
+    pb = L.gmeta_layer_plan_bytes(len(row0), a.tasks, N, E)
+    plan = torch.empty(pb + 256, dtype=torch.uint8, device=dev)
+    plan_ptr = (plan.data_ptr() + 255) // 256 * 256
+    _lib.check(L.gmeta_layer_plan_build(d_indptr.data_ptr(), d_indices.data_ptr(), norm.data_ptr(), None, None,
+                                        d_row0.data_ptr(), d_nrows.data_ptr(), d_task.data_ptr(), len(row0), a.tasks,
+                                        N, E, plan_ptr, st))
     for impl in [int(v) for v in a.impls.split(",")]:
         nb = L.gmeta_gcn_layer_fwd_ex_workspace_bytes(a.tasks, P, len(row0), N, E, a.fin, a.fout, impl)
         ws = torch.empty(max(nb, 16) + 256, dtype=torch.uint8, device=dev)
@@ -94,7 +101,8 @@ def main():
                                                 W.data_ptr() + 4 * a.fin * a.fout, P, a.fin, a.fout, 1, None,
                                                 out.data_ptr(), a.fout, impl, ws_ptr, nb, N, E,
                                                 rmax_in.data_ptr() if impl == 3 else None,
-                                                rmax_out.data_ptr() if impl == 3 else None, st))
+                                                rmax_out.data_ptr() if impl == 3 else None,
+                                                plan_ptr if (impl == 3 and a.plan) else None, st))
         for _ in range(2):
             launch()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -116,6 +124,17 @@ def main():
                      "mma.wait_acc_empty", "mma.wait_a_full", "mma.wait_b_full", "mma.issue", "epi.wait_acc_full",
                      "epi.body", "epi.ldtm", "epi.store"]
             res["profile_kcycles_mean_per_cta"] = {n: round(float(pr[:, i].mean()) / 1e3, 1) for i, n in enumerate(names)}
+        if impl == 3 and a.profile:
+            prof = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+            L.gmeta_debug_set_pair_profile(prof.data_ptr())
+            launch()
+            torch.cuda.synchronize()
+            L.gmeta_debug_set_pair_profile(None)
+            pr = prof.cpu().numpy().reshape(148, 16).astype(np.float64)
+            names = ["prod0.setup", "prod0.wait_empty", "prod0.body", "prod15.setup", "prod15.wait_empty", "prod15.body",
+                     "mma.wait_w", "mma.wait_acc_empty", "mma.wait_a_full", "mma.issue", "epi.wait_acc_full", "epi.body"]
+            res["pair_profile_kcycles_mean_per_cta"] = {n: round(float(pr[:, i].mean()) / 1e3, 1) for i, n in enumerate(names)}
+            res["pair_profile_leader_only"] = {n: round(float(pr[0::2, i].mean()) / 1e3, 1) for i, n in enumerate(names)}
         if impl in (2, 3) and a.ablate:
             set_flags = L.gmeta_debug_set_tc_flags if impl == 2 else L.gmeta_debug_set_pair_flags
             for fl in [int(v) for v in a.ablate.split(",")]:
