@@ -53,19 +53,28 @@ constexpr int KCH = 32;                        // K elements per operand stage (
 constexpr int WCH = 64;                        // K elements per resident weight chunk (128-byte swizzle rows)
 constexpr int A_HALF_BYTES = TM * 64;          // 8 KB: hi (or lo) operand tile of one chunk
 constexpr int STAGE_BYTES = 2 * A_HALF_BYTES;  // 16 KB
-constexpr int N_PROD_WARPS = 16;
-constexpr int WARP_LOAD = 16;
-constexpr int WARP_MMA = 17;
-constexpr int WARP_EPI0 = 18;
-constexpr int NTHREADS = 22 * 32;
+// warp roles (register budgets are re-balanced per warpgroup with setmaxnreg)
+constexpr int N_PROD_WARPS = 8;                // warps 0..7   gather producers
+constexpr int WARP_HUB0 = 8;                   // warps 8..15  hub-row aggregation
+constexpr int WARP_LOAD = 16;                  // warp 16      weight loader (+ TMEM allocation)
+constexpr int WARP_MMA = 17;                   // warp 17      MMA issuer (18, 19 idle)
+constexpr int WARP_EPI0 = 20;                  // warps 20..23 epilogue
+constexpr int NTHREADS = 24 * 32;
+constexpr int REGS_PROD = 104, REGS_HUB = 72, REGS_CTRL = 40, REGS_EPI = 88;
+// setmaxnreg re-distributes the registers the CTA got at launch (768 threads x 80): 256*104 + 256*72 + 128*40 + 128*88 = 61440
+static_assert(8 * 32 * REGS_PROD + 8 * 32 * REGS_HUB + 4 * 32 * REGS_CTRL + 4 * 32 * REGS_EPI <= NTHREADS * 80, "register budget");
+#ifndef GMETA_PAIR_PROF
+#define GMETA_PAIR_PROF 0      // 1: per-role cycle counters (costs registers; debug builds only)
+#endif
 constexpr int MAX_STAGES = 6;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_COLS = 256;
 constexpr int PRE = 2;                         // in-neighbours per row the fused kernel gathers itself
-constexpr int EPI_LD = 36;                     // floats per row of an epilogue transpose tile (32 + pad, conflict-free)
-constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4; // one 32x32 tile per epilogue warp
-constexpr int SMEM_FIXED = 256 /*barriers*/ + 4 * TM /*row scale exponents*/ + EPI_BYTES;
+constexpr int SMEM_FIXED = 256 /*barriers*/ + 4 * TM /*row scale exponents*/ + ACC_COLS * 4 /*bias*/;
 constexpr int SMEM_MAX = 227 * 1024;
+constexpr int N_HUB_WARPS = 8;
+constexpr int HUB_DEPTH = 4;                   // tiles the hub warps may run ahead of the producers
+constexpr int HUB_SMALL = 32;                  // hubs up to this degree are aggregated by one warp
 constexpr int PT_MAXT = 2048;                  // tasks the pair-table kernel handles
 constexpr int SCALE_TARGET = 13;               // scaled bound in [2^13, 2^14): 4x below the FP16 maximum
 constexpr int SCALE_CLAMP = 100;
@@ -75,11 +84,14 @@ struct PlanRec {      // 16 bytes per output row
   int r0, r1;         // mapped source rows of in-neighbours 0/1; hub row: r0 = slot, r1 = -1
   float n0, n1;       // their norms (0 = absent or dropped)
 };
+struct PairEnt {      // 32 bytes; nrows[1] = 0 when the task has an odd tile count
+  int row0[2], nrows[2];
+  int task, tile[2], pad;
+};
 struct Plan {
   int* hdr;           // [0] n_hubs  [1] n_hub_edges  [2] n_pairs
   PlanRec* rec;       // [n_rows]
-  int2* pair_tiles;   // [cap_pairs] the two tiles of a pair (same task); .y = -1 when the task has an odd tile count
-  int* pair_task;     // [cap_pairs]
+  PairEnt* pairs;     // [cap_pairs] two tiles of the same task each
   int2* tile_hubs;    // [n_tiles] (first slot, count) of the tile's hub rows
   int* hub_row;       // [cap_hub] real row of each hub slot
   int* hub_beg;       // [cap_hub] first record of the slot in hub_src / hub_nrm
@@ -94,6 +106,7 @@ struct Workspace {
   __half* w_image;      // [n_copies][rank 2][K/64][hi|lo][N/2 rows][64 halves, 128B swizzle]
   float* mlong;         // [cap_hub][f_in] aggregated hub rows
   float* mlong_bound;   // [cap_hub] sum_e norm_e * max|in[src_e,:]| >= max|mlong[slot,:]|
+  float* hub_scratch;   // [148 CTAs][2][8][K + 32]
   void* plan;           // plan built per call when the caller passes none
   int64_t total;
 };
@@ -117,8 +130,7 @@ Plan carve_plan(void* base, int n_tiles, int n_tasks, int n_rows, int n_edges) {
   const int cp = cap_pairs_for(n_tiles, n_tasks), ch = cap_hub_for(n_rows, n_edges);
   pl.hdr = reinterpret_cast<int*>(c.take(256));
   pl.rec = reinterpret_cast<PlanRec*>(c.take((int64_t)n_rows * 16));
-  pl.pair_tiles = reinterpret_cast<int2*>(c.take((int64_t)cp * 8));
-  pl.pair_task = reinterpret_cast<int*>(c.take((int64_t)cp * 4));
+  pl.pairs = reinterpret_cast<PairEnt*>(c.take((int64_t)cp * 32));
   pl.tile_hubs = reinterpret_cast<int2*>(c.take((int64_t)n_tiles * 8));
   pl.hub_row = reinterpret_cast<int*>(c.take((int64_t)ch * 4));
   pl.hub_beg = reinterpret_cast<int*>(c.take((int64_t)ch * 4));
@@ -138,6 +150,7 @@ Workspace carve_ws(void* base, int n_copies, int n_tiles, int n_tasks, int n_row
   w.w_image = reinterpret_cast<__half*>(c.take((int64_t)n_copies * 2 * K * N * 2));
   w.mlong = reinterpret_cast<float*>(c.take((int64_t)ch * K * 4));
   w.mlong_bound = reinterpret_cast<float*>(c.take((int64_t)ch * 4));
+  w.hub_scratch = reinterpret_cast<float*>(c.take((int64_t)kNumSMs * 2 * N_HUB_WARPS * (K + 32) * 4));
   w.plan = c.take(carve_plan(nullptr, n_tiles, n_tasks, n_rows, n_edges).total);
   w.total = c.off;
   return w;
@@ -160,10 +173,15 @@ struct PairParams {
   const float* mlong_bound;
   const PlanRec* rec;
   const int* hdr;
-  const int2* pair_tiles;
-  const int* pair_task;
-  const int32_t* tile_row0;
-  const int32_t* tile_nrows;
+  const PairEnt* pairs;
+  const int2* tile_hubs;         // per tile: (first hub slot, hub count)
+  const int* hub_beg;
+  const int* hub_deg;
+  const int* hub_src;
+  const float* hub_nrm;
+  float* mlong_w;                // == mlong (written by the hub warps, read by the producers of the same CTA)
+  float* mlong_bound_w;
+  float* hub_scratch;            // [gridDim.x][2][N_HUB_WARPS][f_in + 32] partial sums of cooperative hubs
   const int32_t* dst_rows;
   const float* norm;
   const __half* w_image;
@@ -183,6 +201,25 @@ struct PairParams {
   long long* prof;               // optional [gridDim.x][16] cycle counters per role (debug), or NULL
 };
 
+struct F8 { float v[8]; };
+__device__ __forceinline__ F8 ld_f8(const float* p) {      // 256-bit global load (32-byte aligned)
+  F8 r;
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_f8(float* p, const float (&v)[8]) {   // 256-bit global store: one full sector per lane
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ F8 zero_f8() {
+  F8 r;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r.v[j] = 0.f;
+  return r;
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -201,6 +238,62 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+__device__ __forceinline__ void ld8(float* d, const float* p) {      // 256-bit global load (32-byte aligned)
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]), "=f"(d[4]), "=f"(d[5]), "=f"(d[6]), "=f"(d[7])
+               : "l"(p));
+}
+// One output row's gather state for one tile: where its (<= 2) sources live, their norms and abs-max.
+struct RowCtx {
+  const float* s0;
+  const float* s1;
+  float a0, a1, rm0, rm1;
+  bool live;
+  __device__ __forceinline__ void clear(const float* base) {
+    s0 = s1 = base;
+    a0 = a1 = rm0 = rm1 = 0.f;
+    live = false;
+  }
+  __device__ __forceinline__ void decode(const int4 rc, bool lv, const PairParams& p, int sub) {
+    clear(p.in);
+    live = lv;
+    if (!lv) return;
+    const bool hub = rc.y < 0;
+    a0 = __int_as_float(rc.z);
+    a1 = __int_as_float(rc.w);
+    if (a0 != 0.f) {
+      s0 = (hub ? p.mlong + (size_t)rc.x * p.f_in : p.in + (size_t)rc.x * p.ld_in) + 16 * sub;
+      rm0 = hub ? p.mlong_bound[rc.x] : p.in_rowmax[rc.x];
+    }
+    if (a1 != 0.f) {
+      s1 = p.in + (size_t)rc.y * p.ld_in + 16 * sub;
+      rm1 = p.in_rowmax[rc.y];
+    }
+  }
+};
+// buf[0..15] = 16 floats of source 0 at column offset `off`, buf[16..31] = of source 1 (zeros when absent)
+__device__ __forceinline__ void gather_request(float (&buf)[32], const RowCtx& c, int off, int dbg) {
+  if (c.a0 != 0.f && !(dbg & 2)) {
+    ld8(buf, c.s0 + off);
+    ld8(buf + 8, c.s0 + off + 8);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) buf[j] = 0.f;
+  }
+  if (c.a1 != 0.f && !(dbg & 2)) {
+    ld8(buf + 16, c.s1 + off);
+    ld8(buf + 24, c.s1 + off + 8);
+  } else {
+#pragma unroll
+    for (int j = 16; j < 32; ++j) buf[j] = 0.f;
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 gcn_layer_fwd_pair_kernel(const PairParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -214,19 +307,21 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
   uint8_t* a_s = smem + p.w_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(a_s + (size_t)NS * STAGE_BYTES);
   const uint32_t bar0 = smem_u32(bars);
-  auto a_full = [&](int s) { return bar0 + 8u * s; };                    // leader's: 32 producer warps of the pair
+  auto a_full = [&](int s) { return bar0 + 8u * s; };                    // leader's: producer warps of the pair
   auto empty = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };      // per CTA: multicast commit
   auto acc_full = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + b); };       // per CTA: multicast commit
   auto acc_empty = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + 2 + b); };  // leader's: 8 epilogue warps of the pair
   const uint32_t w_local = bar0 + 8u * (2 * MAX_STAGES + 4);             // per CTA: bulk copy landed
   const uint32_t w_ready = bar0 + 8u * (2 * MAX_STAGES + 5);             // leader's: both CTAs hold the task's weights
   const uint32_t w_free = bar0 + 8u * (2 * MAX_STAGES + 6);              // per CTA: MMAs of the previous task are done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 8);
+  auto hub_full = [&](int d) { return bar0 + 8u * (2 * MAX_STAGES + 7 + d); };              // per CTA: 8 hub warps
+  auto hub_free = [&](int d) { return bar0 + 8u * (2 * MAX_STAGES + 7 + HUB_DEPTH + d); };  // per CTA: 8 producer warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 240);
   int8_t* scale_e = reinterpret_cast<int8_t*>(bars) + 256;               // [4][TM]
-  float* epi_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256 + 4 * TM);
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256 + 4 * TM);   // [ACC_COLS]
 
   if (threadIdx.x == 0) {
-    if (smem_u32(smem) & 1023u) { printf("gmeta pair kernel: shared memory base not 1024-byte aligned\n"); __trap(); }
+    if (smem_u32(smem) & 1023u) __trap();   // SWIZZLE_128B operand tiles need a 1024-byte aligned base
     for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(a_full(s), 2 * N_PROD_WARPS);
       mbar_init(empty(s), 1);
@@ -238,6 +333,10 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
     mbar_init(w_local, 1);
     mbar_init(w_ready, 2);
     mbar_init(w_free, 1);
+    for (int d = 0; d < HUB_DEPTH; ++d) {
+      mbar_init(hub_full(d), N_HUB_WARPS);
+      mbar_init(hub_free(d), N_PROD_WARPS);
+    }
     fence_mbar_init_cluster();
   }
   if (warp == WARP_LOAD) {
@@ -256,197 +355,325 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
   const int ppc = (n_pairs + n_cl - 1) / n_cl;
   const int p_beg = cid * ppc < n_pairs ? cid * ppc : n_pairs;
   const int p_end = p_beg + ppc < n_pairs ? p_beg + ppc : n_pairs;
+  // row range of this CTA's tile in a pair entry (loaded as two 16-byte halves)
+  auto ent_tile = [&](int pr, int& row0, int& nrows) {
+    const int4 e = __ldg(reinterpret_cast<const int4*>(p.pairs + pr));
+    row0 = rank ? e.y : e.x;
+    nrows = rank ? e.w : e.z;
+  };
 
   if (warp < N_PROD_WARPS) {
     // ===================== gather producers =====================
-    const int r = warp * 8 + (lane >> 2);   // a thread quad owns tile row r
-    const int sub = lane & 3;               // and, within a chunk, floats [8*sub, 8*sub + 8)
-    const int soff = r * 64 + ((sub ^ ((r >> 1) & 3)) << 4);   // 64B swizzle: 16-byte unit ^ ((row / 2) % 4)
-    int it = 0, ti = 0;
+    reg_inc<REGS_PROD>();
+    const int r = warp * 16 + (lane >> 1);  // a lane pair owns tile row r
+    const int sub = lane & 1;               // and, within a 32-float chunk, floats [16*sub, 16*sub + 16)
+    const int sw = (r >> 1) & 3;            // 64B swizzle: 16-byte unit ^ ((row / 2) % 4)
+    const int soff0 = r * 64 + (((2 * sub) ^ sw) << 4);
+    const int soff1 = r * 64 + (((2 * sub + 1) ^ sw) << 4);
+#if GMETA_PAIR_PROF
     long long t_setup = 0, t_wait = 0, t_body = 0, t_mark = clock64();
-    auto lap = [&](long long& acc) { const long long now = clock64(); acc += now - t_mark; t_mark = now; };
-    for (int pr = p_beg; pr < p_end; ++pr, ++ti) {
-      const int2 pt = p.pair_tiles[pr];
-      const int tile = rank ? pt.y : pt.x;
-      int nrows = 0, row0 = 0;
-      if (tile >= 0) { nrows = p.tile_nrows[tile]; row0 = p.tile_row0[tile]; }
-      const bool live = r < nrows;
-      const float* src0 = p.in;
-      const float* src1 = p.in;
-      float n0 = 0.f, n1 = 0.f;
-      if (live) {
-        const int4 rc = __ldg(reinterpret_cast<const int4*>(p.rec + row0 + r));
-        const bool hub = rc.y < 0;
-        const float a0 = __int_as_float(rc.z), a1 = __int_as_float(rc.w);
-        float rm0 = 0.f, rm1 = 0.f;
-        if (a0 != 0.f) {
-          src0 = hub ? p.mlong + (size_t)rc.x * K : p.in + (size_t)rc.x * p.ld_in;
-          rm0 = hub ? p.mlong_bound[rc.x] : p.in_rowmax[rc.x];
-        }
-        if (a1 != 0.f) {
-          src1 = p.in + (size_t)rc.y * p.ld_in;
-          rm1 = p.in_rowmax[rc.y];
-        }
-        const int e = scale_exponent(a0 * rm0 + a1 * rm1);
-        const float sc = exp2i(e);
-        n0 = a0 * sc;
-        n1 = a1 * sc;
-        if (sub == 0) scale_e[(ti & 3) * TM + r] = (int8_t)e;
-      }
-      src0 += sub * 8;
-      src1 += sub * 8;
-      // the segments of chunk kc+1 are requested before chunk kc is reduced and stored, so their
-      // latency overlaps the stage wait, the conversion and the stores
-      float4 xn[4];
-      auto request = [&](int kc) {
-        const bool g0 = n0 != 0.f && !(p.dbg & 2), g1 = n1 != 0.f && !(p.dbg & 2);
-        xn[0] = g0 ? ld_f4(src0 + kc * KCH) : make_float4(0.f, 0.f, 0.f, 0.f);
-        xn[1] = g0 ? ld_f4(src0 + kc * KCH + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        xn[2] = g1 ? ld_f4(src1 + kc * KCH) : make_float4(0.f, 0.f, 0.f, 0.f);
-        xn[3] = g1 ? ld_f4(src1 + kc * KCH + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      };
-      request(0);
-      lap(t_setup);
-      for (int kc = 0; kc < nkc; ++kc, ++it) {
-        const int s = it % NS;
-        const uint32_t ph = (uint32_t)((it / NS) & 1);
-        float4 x[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) x[i] = xn[i];
-        if (kc + 1 < nkc) request(kc + 1);
-        lap(t_body);
-        mbar_wait(empty(s), ph ^ 1u, 1);
-        lap(t_wait);
-        if (live) {
-          float v[8];
-          v[0] = fmaf(n1, x[2].x, n0 * x[0].x);
-          v[1] = fmaf(n1, x[2].y, n0 * x[0].y);
-          v[2] = fmaf(n1, x[2].z, n0 * x[0].z);
-          v[3] = fmaf(n1, x[2].w, n0 * x[0].w);
-          v[4] = fmaf(n1, x[3].x, n0 * x[1].x);
-          v[5] = fmaf(n1, x[3].y, n0 * x[1].y);
-          v[6] = fmaf(n1, x[3].z, n0 * x[1].z);
-          v[7] = fmaf(n1, x[3].w, n0 * x[1].w);
-          uint4 hi, lo;
-          split8(v, hi, lo);
-          uint8_t* stage = a_s + (size_t)s * STAGE_BYTES;
-          *reinterpret_cast<uint4*>(stage + soff) = hi;
-          *reinterpret_cast<uint4*>(stage + A_HALF_BYTES + soff) = lo;
-        }
-        fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(a_full(s), 0);
-      }
-      lap(t_body);
+#define PLAP(acc) { const long long now_ = clock64(); acc += now_ - t_mark; t_mark = now_; }
+#else
+#define PLAP(acc)
+#endif
+    // per-tile context: source pointers (+ this lane's 16-float offset), raw norms, source abs-max
+    RowCtx cur, nxt;
+    float bufA[32], bufB[32];               // two chunks of this lane's segments: [nbr0 16 | nbr1 16]
+    int it = 0, ti = 0;
+    int row0_n = 0, nrows_n = 0, row0_nn = 0, nrows_nn = 0;
+    cur.clear(p.in);
+    if (p_beg < p_end) {
+      int row0, nrows;
+      ent_tile(p_beg, row0, nrows);
+      if (p_beg + 1 < p_end) ent_tile(p_beg + 1, row0_n, nrows_n);
+      int4 rc = make_int4(0, 0, 0, 0);
+      if (r < nrows) rc = __ldg(reinterpret_cast<const int4*>(p.rec + row0 + r));
+      mbar_wait(hub_full(0), 0u, 8);        // the first tile's hub rows are aggregated
+      cur.decode(rc, r < nrows, p, sub);
+      gather_request(bufA, cur, 0, p.dbg);
     }
-    if (p.prof && (threadIdx.x == 0 || threadIdx.x == 511)) {
+    // one chunk: `mine` holds this chunk's segments, `other` receives the next chunk's (requested first,
+    // so their latency overlaps the stage wait, the conversion and the stores)
+    auto step = [&](float (&mine)[32], float (&other)[32], int kc, float n0, float n1) {
+      const int s = it % NS;
+      const uint32_t ph = (uint32_t)((it / NS) & 1);
+      if (kc + 1 < nkc) gather_request(other, cur, (kc + 1) * KCH, p.dbg);
+      else gather_request(other, nxt, 0, p.dbg);                // first chunk of the next tile
+      PLAP(t_body);
+      mbar_wait(empty(s), ph ^ 1u, 1);
+      PLAP(t_wait);
+      if (cur.live) {
+        uint8_t* stage = a_s + (size_t)s * STAGE_BYTES;
+        float v[8];
+        uint4 hi, lo;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(n1, mine[16 + j], n0 * mine[j]);
+        split8(v, hi, lo);
+        *reinterpret_cast<uint4*>(stage + soff0) = hi;
+        *reinterpret_cast<uint4*>(stage + A_HALF_BYTES + soff0) = lo;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(n1, mine[24 + j], n0 * mine[8 + j]);
+        split8(v, hi, lo);
+        *reinterpret_cast<uint4*>(stage + soff1) = hi;
+        *reinterpret_cast<uint4*>(stage + A_HALF_BYTES + soff1) = lo;
+      }
+      fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(a_full(s), 0);
+      ++it;
+    };
+    for (int pr = p_beg; pr < p_end; ++pr, ++ti) {
+      // scale of this tile's row from the rigorous bound (see header comment)
+      const int e = scale_exponent(cur.a0 * cur.rm0 + cur.a1 * cur.rm1);
+      const float sc = exp2i(e);
+      const float n0 = cur.a0 * sc, n1 = cur.a1 * sc;
+      if (sub == 0 && cur.live) scale_e[(ti & 3) * TM + r] = (int8_t)e;
+      // context of the next tile, fetched while this one streams: pair entry two tiles ahead, row record
+      // at chunk 0, source abs-max at the middle chunk, first feature segments at the last chunk
+      nrows_nn = 0;
+      if (pr + 2 < p_end) ent_tile(pr + 2, row0_nn, nrows_nn);
+      const bool live_n = r < nrows_n;
+      int4 rc_n = make_int4(0, 0, 0, 0);
+      nxt.clear(p.in);
+      PLAP(t_setup);
+      for (int kc = 0; kc < nkc; kc += 2) {
+        if (kc == 0 && live_n) rc_n = __ldg(reinterpret_cast<const int4*>(p.rec + row0_n + r));
+        if (kc == ((nkc >> 2) << 1)) {
+          if (pr + 1 < p_end) mbar_wait(hub_full((ti + 1) % HUB_DEPTH), (uint32_t)(((ti + 1) / HUB_DEPTH) & 1), 8);
+          nxt.decode(rc_n, live_n, p, sub);
+        }
+        step(bufA, bufB, kc, n0, n1);
+        step(bufB, bufA, kc + 1, n0, n1);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(hub_free(ti % HUB_DEPTH));   // this tile's hub rows have been consumed
+      cur = nxt;
+      row0_n = row0_nn; nrows_n = nrows_nn;
+      PLAP(t_body);
+    }
+#if GMETA_PAIR_PROF
+    if (p.prof && (threadIdx.x == 0 || threadIdx.x == 255)) {
       long long* o = p.prof + blockIdx.x * 16 + (threadIdx.x == 0 ? 0 : 3);
       o[0] = t_setup; o[1] = t_wait; o[2] = t_body;
     }
-  } else if (warp == WARP_LOAD) {
-    // ===================== weight loader: one bulk copy per task change =====================
-    if (lane == 0) {
-      int cur = -1, n = 0;
-      for (int pr = p_beg; pr < p_end; ++pr) {
-        const int task = p.pair_task[pr];
-        if (task == cur) continue;
-        if (n > 0) mbar_wait(w_free, (uint32_t)((n - 1) & 1), 2);   // MMAs reading the old image are complete
-        const uint8_t* img = reinterpret_cast<const uint8_t*>(p.w_image + (long long)task * p.image_task_stride) +
-                             (size_t)rank * p.w_bytes;
-        mbar_arrive_expect_tx(w_local, (uint32_t)p.w_bytes);
-        for (int o = 0; o < p.w_bytes; o += 16384) {
-          const int nb = p.w_bytes - o < 16384 ? p.w_bytes - o : 16384;
-          bulk_copy_g2s(smem_u32(w_s + o), img + o, (uint32_t)nb, w_local);
-        }
-        mbar_wait(w_local, (uint32_t)(n & 1), 3);
-        mbar_arrive_cluster(w_ready, 0);
-        cur = task;
-        ++n;
-      }
-    }
-  } else if (warp == WARP_MMA) {
-    // ===================== MMA issuer (leader CTA, one thread) =====================
-    if (rank == 0 && lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(2 * TM, N);
-      int it = 0, ti = 0, cur = -1, nw = 0;
-      long long t_w = 0, t_acc = 0, t_a = 0, t_issue = 0, t_mark = clock64();
-      auto lap = [&](long long& acc) { const long long now = clock64(); acc += now - t_mark; t_mark = now; };
-      for (int pr = p_beg; pr < p_end; ++pr, ++ti) {
-        const int task = p.pair_task[pr];
-        lap(t_issue);
-        if (task != cur) {
-          mbar_wait_cluster(w_ready, (uint32_t)(nw & 1), 4);
-          cur = task;
-          ++nw;
-        }
-        lap(t_w);
-        const int buf = ti & 1;
-        mbar_wait_cluster(acc_empty(buf), (uint32_t)(((ti >> 1) & 1) ^ 1), 5);
-        lap(t_acc);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
-        for (int kc = 0; kc < nkc; ++kc, ++it) {
-          const int s = it % NS;
-          const uint32_t ph = (uint32_t)((it / NS) & 1);
-          lap(t_issue);
-          mbar_wait_cluster(a_full(s), ph, 6);
-          lap(t_a);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(a_s + (size_t)s * STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(w_s + (size_t)(kc >> 1) * 2 * half_n_bytes);
-          const uint64_t da_hi = umma_desc_k_sw64(a_addr);
-          const uint64_t da_lo = umma_desc_k_sw64(a_addr + A_HALF_BYTES);
-          const uint64_t db_hi = umma_desc_k_sw128(b_addr);
-          const uint64_t db_lo = umma_desc_k_sw128(b_addr + half_n_bytes);
+#endif
+  } else if (warp < WARP_LOAD) {
+    // ===================== hub-row aggregation warps =====================
+    // mlong[slot][:] = sum_e hub_nrm[e] * in[hub_src[e]][:] for the hub rows of this CTA's tiles, a few tiles
+    // ahead of the producers (which then find the subgraph's rows in L2).  Hubs of degree <= HUB_SMALL: one
+    // warp each; larger hubs: the eight warps take 32-edge blocks round-robin and the partial sums are combined
+    // through an L2-resident scratch in a fixed order -> deterministic.
+    reg_dec<REGS_HUB>();
+    const int hw = warp - WARP_HUB0;
+    const int lpr = K >= 256 ? 32 : K / 8;          // lanes per row: 8 floats (32 bytes) each
+    const int eg = lane / lpr, lc = (lane - eg * lpr) * 8;
+    const int epw = 32 / lpr;                        // edges per warp-wide load
+    float* scratch = p.hub_scratch + (size_t)blockIdx.x * 2 * N_HUB_WARPS * (K + 32);
+    // partial sum over edges [e0, e1) of one hub (at most 32 of them) for columns cb + lc .. +7
+    auto edge_block = [&](int beg, int e0, int e1, int cb, float (&acc)[8], float& bsum, bool want_bound) {
+      const int e = e0 + lane;
+      int src = 0;
+      float nr = 0.f;
+      if (e < e1) { src = p.hub_src[beg + e]; nr = p.hub_nrm[beg + e]; }
+      if (want_bound && nr != 0.f) bsum = fmaf(nr, p.in_rowmax[src], bsum);
+      const int cnt = e1 - e0;
+      for (int j = 0; j < cnt; j += 4 * epw) {
+        float xv[4][8], wv[4];
 #pragma unroll
-          for (int k = 0; k < KCH / 16; ++k) {        // UMMA_K = 16 halves = 32 bytes = 2 descriptor units
-            if ((p.dbg & 4) && k) break;
-            const uint64_t adv_a = (uint64_t)(2 * k);
-            const uint64_t adv_b = (uint64_t)(2 * ((kc & 1) * 2 + k));
-            tc_mma_f16_pair(d_tmem, da_hi + adv_a, db_hi + adv_b, idesc, (kc | k) != 0 ? 1u : 0u);
-            tc_mma_f16_pair(d_tmem, da_lo + adv_a, db_hi + adv_b, idesc, 1u);
-            tc_mma_f16_pair(d_tmem, da_hi + adv_a, db_lo + adv_b, idesc, 1u);
+        for (int u = 0; u < 4; ++u) {
+          const int idx = j + u * epw + eg;
+          wv[u] = __shfl_sync(0xffffffffu, nr, idx & 31);
+          const int sj = __shfl_sync(0xffffffffu, src, idx & 31);
+          if (idx >= cnt) wv[u] = 0.f;
+          if (wv[u] != 0.f && !(p.dbg & 2)) ld8(xv[u], p.in + (size_t)sj * p.ld_in + cb + lc);
+          else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) xv[u][k] = 0.f;
           }
-          tc_commit_pair(empty(s));          // frees the stage in both CTAs once these MMAs have read it
         }
-        tc_commit_pair(acc_full(buf));       // accumulators complete -> both epilogues
-        if (pr + 1 < p_end && p.pair_task[pr + 1] != task) tc_commit_pair(w_free);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] = fmaf(wv[u], xv[u][k], acc[k]);
       }
-      lap(t_issue);
-      if (p.prof) {
-        long long* o = p.prof + blockIdx.x * 16 + 6;
-        o[0] = t_w; o[1] = t_acc; o[2] = t_a; o[3] = t_issue;
+    };
+    auto reduce_groups = [&](float (&acc)[8]) {     // combine the edge groups of a warp (K < 256)
+      for (int o = lpr; o < 32; o <<= 1)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    };
+    int ti = 0, n_big = 0;
+    for (int pr = p_beg; pr < p_end; ++pr, ++ti) {
+      const int tile = p.pairs[pr].tile[rank];
+      int2 th = make_int2(0, 0);
+      if (tile >= 0) th = __ldg(p.tile_hubs + tile);
+      if (ti >= HUB_DEPTH) mbar_wait(hub_free(ti % HUB_DEPTH), (uint32_t)(((ti / HUB_DEPTH) - 1) & 1), 9);
+      for (int cb = 0; cb < K; cb += 256) {          // 256-column blocks (one for K <= 256)
+        // small hubs: warp hw takes hubs hw, hw + 8, ...
+        for (int i = hw; i < th.y; i += N_HUB_WARPS) {
+          const int slot = th.x + i;
+          const int deg = p.hub_deg[slot];
+          if (deg > HUB_SMALL) continue;
+          const int beg = p.hub_beg[slot];
+          float acc[8], bsum = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+          edge_block(beg, 0, deg, cb, acc, bsum, cb == 0);
+          reduce_groups(acc);
+          if (eg == 0) st_f8(p.mlong_w + (size_t)slot * K + cb + lc, acc);
+          if (cb == 0) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+            if (lane == 0) p.mlong_bound_w[slot] = bsum;
+          }
+        }
+        // large hubs: all eight warps together
+        for (int i = 0; i < th.y; ++i) {
+          const int slot = th.x + i;
+          const int deg = p.hub_deg[slot];
+          if (deg <= HUB_SMALL) continue;
+          const int beg = p.hub_beg[slot];
+          float acc[8], bsum = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+          for (int e0 = 32 * hw; e0 < deg; e0 += 32 * N_HUB_WARPS)
+            edge_block(beg, e0, e0 + 32 < deg ? e0 + 32 : deg, cb, acc, bsum, cb == 0);
+          reduce_groups(acc);
+          float* sc = scratch + (size_t)(n_big & 1) * N_HUB_WARPS * (K + 32);
+          const int kw = K < 256 ? K : 256;           // columns of this block
+          if (eg == 0) st_f8(sc + (size_t)hw * (K + 32) + lc, acc);
+          if (cb == 0) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+            if (lane == 0) sc[(size_t)hw * (K + 32) + K] = bsum;
+          }
+          asm volatile("bar.sync 3, 256;" ::: "memory");
+          // warp hw sums the eight partials of columns [hw * kw/8, (hw+1) * kw/8) in warp order
+          const int per = kw / N_HUB_WARPS;
+          if (lane < per) {
+            float t = 0.f;
+#pragma unroll
+            for (int j = 0; j < N_HUB_WARPS; ++j) t += sc[(size_t)j * (K + 32) + hw * per + lane];
+            p.mlong_w[(size_t)slot * K + cb + hw * per + lane] = t;
+          }
+          if (cb == 0 && hw == 0 && lane == 0) {
+            float t = 0.f;
+#pragma unroll
+            for (int j = 0; j < N_HUB_WARPS; ++j) t += sc[(size_t)j * (K + 32) + K];
+            p.mlong_bound_w[slot] = t;
+          }
+          ++n_big;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(hub_full(ti % HUB_DEPTH));
+    }
+  } else if (warp < WARP_EPI0) {
+    reg_dec<REGS_CTRL>();
+    if (warp == WARP_LOAD) {
+      // ===================== weight loader: one bulk copy per task change =====================
+      if (lane == 0) {
+        int cur = -1, n = 0;
+        for (int pr = p_beg; pr < p_end; ++pr) {
+          const int task = p.pairs[pr].task;
+          if (task == cur) continue;
+          if (n > 0) mbar_wait(w_free, (uint32_t)((n - 1) & 1), 2);   // MMAs reading the old image are complete
+          const uint8_t* img = reinterpret_cast<const uint8_t*>(p.w_image + (long long)task * p.image_task_stride) +
+                               (size_t)rank * p.w_bytes;
+          mbar_arrive_expect_tx(w_local, (uint32_t)p.w_bytes);
+          for (int o = 0; o < p.w_bytes; o += 16384) {
+            const int nb = p.w_bytes - o < 16384 ? p.w_bytes - o : 16384;
+            bulk_copy_g2s(smem_u32(w_s + o), img + o, (uint32_t)nb, w_local);
+          }
+          mbar_wait(w_local, (uint32_t)(n & 1), 3);
+          mbar_arrive_cluster(w_ready, 0);
+          cur = task;
+          ++n;
+        }
+      }
+    } else if (warp == WARP_MMA) {
+      // ===================== MMA issuer (leader CTA, one thread) =====================
+      if (rank == 0 && lane == 0) {
+        const uint32_t idesc = umma_idesc_f16(2 * TM, N);
+        int it = 0, ti = 0, cur = -1, nw = 0;
+        long long t_w = 0, t_acc = 0, t_a = 0, t_issue = 0, t_mark = clock64();
+        auto lap = [&](long long& acc) { const long long now = clock64(); acc += now - t_mark; t_mark = now; };
+        int task_n = p_beg < p_end ? p.pairs[p_beg].task : 0;
+        for (int pr = p_beg; pr < p_end; ++pr, ++ti) {
+          const int task = task_n;
+          if (pr + 1 < p_end) task_n = p.pairs[pr + 1].task;
+          lap(t_issue);
+          if (task != cur) {
+            mbar_wait_cluster(w_ready, (uint32_t)(nw & 1), 4);
+            cur = task;
+            ++nw;
+          }
+          lap(t_w);
+          const int buf = ti & 1;
+          mbar_wait_cluster(acc_empty(buf), (uint32_t)(((ti >> 1) & 1) ^ 1), 5);
+          lap(t_acc);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
+          for (int kc = 0; kc < nkc; ++kc, ++it) {
+            const int s = it % NS;
+            const uint32_t ph = (uint32_t)((it / NS) & 1);
+            lap(t_issue);
+            mbar_wait_cluster(a_full(s), ph, 6);
+            lap(t_a);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(a_s + (size_t)s * STAGE_BYTES);
+            const uint32_t b_addr = smem_u32(w_s + (size_t)(kc >> 1) * 2 * half_n_bytes);
+            const uint64_t da_hi = umma_desc_k_sw64(a_addr);
+            const uint64_t da_lo = umma_desc_k_sw64(a_addr + A_HALF_BYTES);
+            const uint64_t db_hi = umma_desc_k_sw128(b_addr);
+            const uint64_t db_lo = umma_desc_k_sw128(b_addr + half_n_bytes);
+#pragma unroll
+            for (int k = 0; k < KCH / 16; ++k) {        // UMMA_K = 16 halves = 32 bytes = 2 descriptor units
+              if ((p.dbg & 4) && k) break;
+              const uint64_t adv_a = (uint64_t)(2 * k);
+              const uint64_t adv_b = (uint64_t)(2 * ((kc & 1) * 2 + k));
+              tc_mma_f16_pair(d_tmem, da_hi + adv_a, db_hi + adv_b, idesc, (kc | k) != 0 ? 1u : 0u);
+              tc_mma_f16_pair(d_tmem, da_lo + adv_a, db_hi + adv_b, idesc, 1u);
+              tc_mma_f16_pair(d_tmem, da_hi + adv_a, db_lo + adv_b, idesc, 1u);
+            }
+            tc_commit_pair(empty(s));          // frees the stage in both CTAs once these MMAs have read it
+          }
+          tc_commit_pair(acc_full(buf));       // accumulators complete -> both epilogues
+          if (pr + 1 < p_end && task_n != task) tc_commit_pair(w_free);
+        }
+        lap(t_issue);
+        if (p.prof) {
+          long long* o = p.prof + blockIdx.x * 16 + 6;
+          o[0] = t_w; o[1] = t_acc; o[2] = t_a; o[3] = t_issue;
+        }
       }
     }
   } else {
     // ===================== epilogue =====================
+    reg_inc<REGS_EPI>();
     const int quarter = warp & 3;            // TMEM lanes 32*quarter .. +31 are the ones this warp may read
-    const int r = quarter * 32 + lane;
-    float* stg = epi_s + quarter * 32 * EPI_LD;
-    const int tr = lane >> 3, tc4 = (lane & 7) * 4;   // transposed read: rows 4*i + tr, columns tc4 .. +3
+    const int r = quarter * 32 + lane;       // this lane owns tile row r: one full 32-byte sector per store
+    const int et = threadIdx.x - WARP_EPI0 * 32;
     int ti = 0, bias_task = -1;
-    float4 bias_r[8];
     long long t_wacc = 0, t_epi = 0, t_mark = clock64();
     auto lap = [&](long long& acc) { const long long now = clock64(); acc += now - t_mark; t_mark = now; };
     for (int pr = p_beg; pr < p_end; ++pr, ++ti) {
       const int buf = ti & 1;
-      const int2 pt = p.pair_tiles[pr];
-      const int tile = rank ? pt.y : pt.x;
-      const int task = p.pair_task[pr];
-      int nrows = 0, row0 = 0;
-      if (tile >= 0) { nrows = p.tile_nrows[tile]; row0 = p.tile_row0[tile]; }
+      const PairEnt ent = p.pairs[pr];
+      const int row0 = ent.row0[rank], nrows = ent.nrows[rank], task = ent.task;
       const bool live = r < nrows;
       const int oi = row0 + (live ? r : 0);                           // output row (compact or dense)
       const int v = p.dst_rows ? p.dst_rows[oi] : oi;                 // real row: norm and mask
       const float nv = p.norm[v];
       const float wis = p.w_inv_scale[p.image_task_stride ? task : 0];
-      if (task != bias_task) {     // this lane's bias columns (tc4 .. tc4+3 of every 32-column block), once per task
+      const float* mrow = p.relu_mask ? p.relu_mask + (size_t)v * p.ld_out : nullptr;
+      float* orow = p.out + (size_t)oi * p.ld_out;
+      if (task != bias_task) {     // the task's bias -> shared memory (broadcast reads below), once per task
         bias_task = task;
+        asm volatile("bar.sync 2, 128;" ::: "memory");     // every epilogue warp is done with the old bias
         const float* bias = p.bias ? p.bias + (long long)task * p.b_task_stride : nullptr;
-#pragma unroll
-        for (int b = 0; b < 8; ++b)
-          bias_r[b] = (bias && 32 * b + tc4 < N) ? __ldg(reinterpret_cast<const float4*>(bias + 32 * b + tc4))
-                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = et; c < ACC_COLS; c += 128) bias_s[c] = (bias && c < N) ? bias[c] : 0.f;
+        asm volatile("bar.sync 2, 128;" ::: "memory");
       }
       lap(t_epi);
       mbar_wait(acc_full(buf), (uint32_t)((ti >> 1) & 1), 7);
@@ -454,13 +681,8 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       tc_fence_after();
       const float f = live ? nv * exp2i(-(int)scale_e[(ti & 3) * TM + r]) * wis : 0.f;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * ACC_COLS);
-      float pmax[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) pmax[i] = 0.f;
-#pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        const int c0 = 32 * b;
-        if (c0 >= N) break;
+      float rmax = 0.f;
+      for (int c0 = 0; c0 < N; c0 += 32) {
         uint32_t acc[32];
         if (c0 + 32 <= N) {
           tmem_ld32(t_addr + (uint32_t)c0, acc);
@@ -471,46 +693,35 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
           for (int j = 0; j < 16; ++j) { acc[j] = a16[j]; acc[16 + j] = 0u; }
         }
         tmem_ld_wait();
-        __syncwarp();                             // the previous block's transposed reads are done
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          st_f4(stg + lane * EPI_LD + j, make_float4(f * __uint_as_float(acc[j]), f * __uint_as_float(acc[j + 1]),
-                                                     f * __uint_as_float(acc[j + 2]), f * __uint_as_float(acc[j + 3])));
-        __syncwarp();
-        // transposed: a store instruction writes 4 rows x 128 contiguous bytes; bias / ReLU / mask here
-        const bool col_ok = c0 + tc4 < N;
-        const float4 b4 = bias_r[b];
+        for (int j = 0; j < 32; j += 8) {
+          if (c0 + j >= N) break;
+          const float4 b0 = ld_f4(bias_s + c0 + j), b1 = ld_f4(bias_s + c0 + j + 4);
+          float o[8];
+          o[0] = fmaf(f, __uint_as_float(acc[j]), b0.x);
+          o[1] = fmaf(f, __uint_as_float(acc[j + 1]), b0.y);
+          o[2] = fmaf(f, __uint_as_float(acc[j + 2]), b0.z);
+          o[3] = fmaf(f, __uint_as_float(acc[j + 3]), b0.w);
+          o[4] = fmaf(f, __uint_as_float(acc[j + 4]), b1.x);
+          o[5] = fmaf(f, __uint_as_float(acc[j + 5]), b1.y);
+          o[6] = fmaf(f, __uint_as_float(acc[j + 6]), b1.z);
+          o[7] = fmaf(f, __uint_as_float(acc[j + 7]), b1.w);
+          if (p.relu) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = 4 * i + tr;
-          const int vr = __shfl_sync(0xffffffffu, v, rr);       // real row of tile row quarter*32 + rr
-          if (quarter * 32 + rr < nrows && col_ok) {
-            float4 w4 = ld_f4(stg + rr * EPI_LD + tc4);
-            w4.x += b4.x; w4.y += b4.y; w4.z += b4.z; w4.w += b4.w;
-            if (p.relu) { w4.x = fmaxf(w4.x, 0.f); w4.y = fmaxf(w4.y, 0.f); w4.z = fmaxf(w4.z, 0.f); w4.w = fmaxf(w4.w, 0.f); }
-            if (p.relu_mask) {
-              const float4 m4 = ld_f4(p.relu_mask + (size_t)vr * p.ld_out + c0 + tc4);
-              if (!(m4.x > 0.f)) w4.x = 0.f;
-              if (!(m4.y > 0.f)) w4.y = 0.f;
-              if (!(m4.z > 0.f)) w4.z = 0.f;
-              if (!(m4.w > 0.f)) w4.w = 0.f;
-            }
-            pmax[i] = fmaxf(pmax[i], fmaxf(fmaxf(fabsf(w4.x), fabsf(w4.y)), fmaxf(fabsf(w4.z), fabsf(w4.w))));
-            if (!(p.dbg & 1)) st_f4(p.out + (size_t)(row0 + quarter * 32 + rr) * p.ld_out + c0 + tc4, w4);
+            for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k], 0.f);
           }
-        }
-      }
-      if (p.out_rowmax) {
+          if (mrow && live) {
+            const F8 m = ld_f8(mrow + c0 + j);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float m = pmax[i];
-          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
-          const int rr = 4 * i + tr;
-          if ((lane & 7) == 0 && quarter * 32 + rr < nrows) p.out_rowmax[row0 + quarter * 32 + rr] = m;
+            for (int k = 0; k < 8; ++k)
+              if (!(m.v[k] > 0.f)) o[k] = 0.f;
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) rmax = fmaxf(rmax, fabsf(o[k]));
+          if (live && !(p.dbg & 1)) st_f8(orow + c0 + j, o);
         }
       }
+      if (p.out_rowmax && live) p.out_rowmax[oi] = rmax;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(acc_empty(buf), 0);
@@ -688,7 +899,9 @@ __global__ void plan_hub_edges_kernel(const int32_t* __restrict__ indptr, const 
 }
 
 // tiles -> pairs of tiles of the same task (tiles of a task are contiguous in the tile table)
-__global__ void __launch_bounds__(1024) pair_table_kernel(const int32_t* __restrict__ tile_task, int n_tiles,
+__global__ void __launch_bounds__(1024) pair_table_kernel(const int32_t* __restrict__ tile_row0,
+                                                          const int32_t* __restrict__ tile_nrows,
+                                                          const int32_t* __restrict__ tile_task, int n_tiles,
                                                           int n_tasks, Plan pl) {
   __shared__ int first[PT_MAXT], cnt[PT_MAXT], base[PT_MAXT], tmp[PT_MAXT];
   for (int t = threadIdx.x; t < n_tasks; t += blockDim.x) { first[t] = 0x7fffffff; cnt[t] = 0; }
@@ -710,14 +923,21 @@ __global__ void __launch_bounds__(1024) pair_table_kernel(const int32_t* __restr
     int* c = a; a = b; b = c;
   }
   const int total = n_tasks > 0 ? a[n_tasks - 1] : 0;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) pl.pair_tiles[i] = make_int2(-1, -1);
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    PairEnt e;
+    e.row0[0] = e.row0[1] = e.nrows[0] = e.nrows[1] = e.task = e.pad = 0;
+    e.tile[0] = e.tile[1] = -1;
+    pl.pairs[i] = e;
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < n_tiles; i += blockDim.x) {
     const int t = tile_task[i];
     const int j = i - first[t];
-    const int pr = a[t] - ((cnt[t] + 1) >> 1) + (j >> 1);
-    if (j & 1) pl.pair_tiles[pr].y = i;
-    else { pl.pair_tiles[pr].x = i; pl.pair_task[pr] = t; }
+    PairEnt* e = pl.pairs + a[t] - ((cnt[t] + 1) >> 1) + (j >> 1);
+    e->row0[j & 1] = tile_row0[i];
+    e->nrows[j & 1] = tile_nrows[i];
+    e->tile[j & 1] = i;
+    if (!(j & 1)) e->task = t;
   }
   if (threadIdx.x == 0) pl.hdr[2] = total;
 }
@@ -796,8 +1016,9 @@ bool gcn_layer_fwd_pair_supported(const GatherSrc& g, int f_out, const float* bi
   if (relu_mask && !aligned16(relu_mask)) return false;
   if (g.f_in % WCH != 0 || g.f_in < WCH || g.f_in > 1024) return false;
   if (f_out % 16 != 0 || f_out < 16 || f_out > 256) return false;
-  if (g.ld_in % 4 != 0 || !aligned16(g.in) || g.ld_in < g.f_in) return false;
-  if (ld_out % 4 != 0 || !aligned16(out)) return false;
+  if (g.ld_in % 8 != 0 || (reinterpret_cast<uintptr_t>(g.in) & 31u) || g.ld_in < g.f_in) return false;   // 256-bit loads
+  if (ld_out % 8 != 0 || (reinterpret_cast<uintptr_t>(out) & 31u)) return false;
+  if (relu_mask && (reinterpret_cast<uintptr_t>(relu_mask) & 31u)) return false;
   if (n_tasks > PT_MAXT) return false;
   return stages_for(g.f_in, f_out) >= 3;
 }
@@ -822,7 +1043,7 @@ int layer_plan_build(const int32_t* indptr, const int32_t* indices, const float*
   if ((rc = check_launch()) != GMETA_OK) return rc;
   plan_hub_edges_kernel<<<4 * kNumSMs, 256, 0, stream>>>(indptr, indices, norm, in_row_map, pl);
   if ((rc = check_launch()) != GMETA_OK) return rc;
-  pair_table_kernel<<<1, 1024, 0, stream>>>(tile_task, n_tiles, n_tasks, pl);
+  pair_table_kernel<<<1, 1024, 0, stream>>>(tile_row0, tile_nrows, tile_task, n_tiles, n_tasks, pl);
   return check_launch();
 }
 
@@ -868,13 +1089,13 @@ int gcn_layer_fwd_pair(const GatherSrc& g, const int32_t* tile_row0, const int32
                                                 ws.w_image, 2LL * K * N, ws.w_inv_scale);
     if ((rc = check_launch()) != GMETA_OK) return rc;
   }
-  hub_rows_kernel<<<8 * kNumSMs, 256, 0, stream>>>(g.in, g.ld_in, K, in_rowmax, pl, ws.mlong, ws.mlong_bound);
-  if ((rc = check_launch()) != GMETA_OK) return rc;
   PairParams p;
   p.in = g.in; p.ld_in = g.ld_in; p.f_in = K; p.in_rowmax = in_rowmax;
   p.mlong = ws.mlong; p.mlong_bound = ws.mlong_bound;
-  p.rec = pl.rec; p.hdr = pl.hdr; p.pair_tiles = pl.pair_tiles; p.pair_task = pl.pair_task;
-  p.tile_row0 = tile_row0; p.tile_nrows = tile_nrows; p.dst_rows = g.dst_rows; p.norm = g.norm;
+  p.rec = pl.rec; p.hdr = pl.hdr; p.pairs = pl.pairs;
+  p.tile_hubs = pl.tile_hubs; p.hub_beg = pl.hub_beg; p.hub_deg = pl.hub_deg; p.hub_src = pl.hub_src; p.hub_nrm = pl.hub_nrm;
+  p.mlong_w = ws.mlong; p.mlong_bound_w = ws.mlong_bound; p.hub_scratch = ws.hub_scratch;
+  p.dst_rows = g.dst_rows; p.norm = g.norm;
   p.w_image = ws.w_image; p.image_task_stride = n_copies > 1 ? 2LL * K * N : 0; p.w_inv_scale = ws.w_inv_scale;
   p.bias = bias; p.b_task_stride = b_task_stride; p.f_out = N; p.relu = relu; p.relu_mask = relu_mask;
   p.out = out; p.ld_out = ld_out; p.out_rowmax = out_rowmax;

@@ -59,9 +59,18 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
-__device__ __noinline__ void wait_timed_out(uint32_t bar, uint32_t parity, int what) {
+// A printf here would be an ABI call, which makes ptxas cap EVERY warp role at the launch-bound
+// register count (setmaxnreg.inc regions included); debug builds only.
+#ifndef GMETA_TC_DEBUG_PRINT
+#define GMETA_TC_DEBUG_PRINT 0
+#endif
+__device__ __forceinline__ void wait_timed_out(uint32_t bar, uint32_t parity, int what) {
+#if GMETA_TC_DEBUG_PRINT
   printf("gmeta pair kernel: mbarrier wait timed out (block %d thread %d bar %u parity %u site %d)\n",
          (int)blockIdx.x, (int)threadIdx.x, bar, parity, what);
+#else
+  (void)bar; (void)parity; (void)what;
+#endif
   __trap();
 }
 // `what` tags the call site in the time-out message
