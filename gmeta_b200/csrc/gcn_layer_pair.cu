@@ -74,7 +74,6 @@ constexpr int SMEM_FIXED = 256 /*barriers*/ + 4 * TM /*row scale exponents*/ + A
 constexpr int SMEM_MAX = 227 * 1024;
 constexpr int N_HUB_WARPS = 8;
 constexpr int HUB_DEPTH = 4;                   // tiles the hub warps may run ahead of the producers
-constexpr int HUB_SMALL = 32;                  // hubs up to this degree are aggregated by one warp
 constexpr int PT_MAXT = 2048;                  // tasks the pair-table kernel handles
 constexpr int SCALE_TARGET = 13;               // scaled bound in [2^13, 2^14): 4x below the FP16 maximum
 constexpr int SCALE_CLAMP = 100;
@@ -84,20 +83,24 @@ struct PlanRec {      // 16 bytes per output row
   int r0, r1;         // mapped source rows of in-neighbours 0/1; hub row: r0 = slot, r1 = -1
   float n0, n1;       // their norms (0 = absent or dropped)
 };
-struct PairEnt {      // 32 bytes; nrows[1] = 0 when the task has an odd tile count
+struct PairEnt {      // 64 bytes; nrows[1] = 0 when the task has an odd tile count
   int row0[2], nrows[2];
   int task, tile[2], pad;
+  int hub_eb[2], hub_ne[2];   // the tile's slice of the padded hub edge list: first record, record count
+  int pad2[4];
 };
 struct Plan {
   int* hdr;           // [0] n_hubs  [1] n_hub_edges  [2] n_pairs
   PlanRec* rec;       // [n_rows]
   PairEnt* pairs;     // [cap_pairs] two tiles of the same task each
-  int2* tile_hubs;    // [n_tiles] (first slot, count) of the tile's hub rows
+  int2* tile_hubs;    // [n_tiles] (first record, record count) of the tile's slice of the hub edge list
   int* hub_row;       // [cap_hub] real row of each hub slot
-  int* hub_beg;       // [cap_hub] first record of the slot in hub_src / hub_nrm
+  int* hub_beg;       // [cap_hub] first record of the slot
   int* hub_deg;       // [cap_hub]
-  int* hub_src;       // [n_edges] mapped source row of each hub edge
-  float* hub_nrm;     // [n_edges]
+  // hub edge list, grouped by tile then hub, every hub padded to a multiple of 4 records (pads: norm 0)
+  int* hub_src;       // [cap_edges] mapped source row
+  float* hub_nrm;     // [cap_edges]
+  int* hub_slot;      // [cap_edges] hub slot the record belongs to
   int64_t total;
 };
 struct Workspace {
@@ -106,7 +109,6 @@ struct Workspace {
   __half* w_image;      // [n_copies][rank 2][K/64][hi|lo][N/2 rows][64 halves, 128B swizzle]
   float* mlong;         // [cap_hub][f_in] aggregated hub rows
   float* mlong_bound;   // [cap_hub] sum_e norm_e * max|in[src_e,:]| >= max|mlong[slot,:]|
-  float* hub_scratch;   // [148 CTAs][2][8][K + 32]
   void* plan;           // plan built per call when the caller passes none
   int64_t total;
 };
@@ -130,13 +132,15 @@ Plan carve_plan(void* base, int n_tiles, int n_tasks, int n_rows, int n_edges) {
   const int cp = cap_pairs_for(n_tiles, n_tasks), ch = cap_hub_for(n_rows, n_edges);
   pl.hdr = reinterpret_cast<int*>(c.take(256));
   pl.rec = reinterpret_cast<PlanRec*>(c.take((int64_t)n_rows * 16));
-  pl.pairs = reinterpret_cast<PairEnt*>(c.take((int64_t)cp * 32));
+  pl.pairs = reinterpret_cast<PairEnt*>(c.take((int64_t)cp * 64));
   pl.tile_hubs = reinterpret_cast<int2*>(c.take((int64_t)n_tiles * 8));
   pl.hub_row = reinterpret_cast<int*>(c.take((int64_t)ch * 4));
   pl.hub_beg = reinterpret_cast<int*>(c.take((int64_t)ch * 4));
   pl.hub_deg = reinterpret_cast<int*>(c.take((int64_t)ch * 4));
-  pl.hub_src = reinterpret_cast<int*>(c.take((int64_t)n_edges * 4 + 4));
-  pl.hub_nrm = reinterpret_cast<float*>(c.take((int64_t)n_edges * 4 + 4));
+  const int64_t ce = (int64_t)n_edges + 3LL * ch + 64;
+  pl.hub_src = reinterpret_cast<int*>(c.take(ce * 4));
+  pl.hub_nrm = reinterpret_cast<float*>(c.take(ce * 4));
+  pl.hub_slot = reinterpret_cast<int*>(c.take(ce * 4));
   pl.total = c.off;
   return pl;
 }
@@ -150,7 +154,6 @@ Workspace carve_ws(void* base, int n_copies, int n_tiles, int n_tasks, int n_row
   w.w_image = reinterpret_cast<__half*>(c.take((int64_t)n_copies * 2 * K * N * 2));
   w.mlong = reinterpret_cast<float*>(c.take((int64_t)ch * K * 4));
   w.mlong_bound = reinterpret_cast<float*>(c.take((int64_t)ch * 4));
-  w.hub_scratch = reinterpret_cast<float*>(c.take((int64_t)kNumSMs * 2 * N_HUB_WARPS * (K + 32) * 4));
   w.plan = c.take(carve_plan(nullptr, n_tiles, n_tasks, n_rows, n_edges).total);
   w.total = c.off;
   return w;
@@ -174,14 +177,11 @@ struct PairParams {
   const PlanRec* rec;
   const int* hdr;
   const PairEnt* pairs;
-  const int2* tile_hubs;         // per tile: (first hub slot, hub count)
-  const int* hub_beg;
-  const int* hub_deg;
-  const int* hub_src;
+  const int* hub_src;            // padded hub edge records (see Plan)
   const float* hub_nrm;
+  const int* hub_slot;
   float* mlong_w;                // == mlong (written by the hub warps, read by the producers of the same CTA)
   float* mlong_bound_w;
-  float* hub_scratch;            // [gridDim.x][2][N_HUB_WARPS][f_in + 32] partial sums of cooperative hubs
   const int32_t* dst_rows;
   const float* norm;
   const __half* w_image;
@@ -294,6 +294,129 @@ __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.al
 template <int R>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 
+template <int VEC> struct VecLd;
+template <> struct VecLd<4> {
+  static __device__ __forceinline__ void ld(float (&d)[4], const float* p) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float (&d)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(d[0], d[1], d[2], d[3]);
+  }
+};
+template <> struct VecLd<2> {
+  static __device__ __forceinline__ void ld(float (&d)[2], const float* p) {
+    const float2 v = *reinterpret_cast<const float2*>(p);
+    d[0] = v.x; d[1] = v.y;
+  }
+  static __device__ __forceinline__ void st(float* p, const float (&d)[2]) {
+    *reinterpret_cast<float2*>(p) = make_float2(d[0], d[1]);
+  }
+};
+template <> struct VecLd<1> {
+  static __device__ __forceinline__ void ld(float (&d)[1], const float* p) { d[0] = *p; }
+  static __device__ __forceinline__ void st(float* p, const float (&d)[1]) { *p = d[0]; }
+};
+
+// One hub warp (see the call site).  K = 64 * VEC; lane = 8 * g + c: edge group g (edges 4j + g of a
+// round-of-4 sequence), column unit c (VEC floats at hw*K/8 + c*VEC).
+template <int VEC>
+__device__ __forceinline__ void hub_warp_loop(const PairParams& p, int hw, int lane, uint32_t rank, int p_beg,
+                                              int p_end, uint32_t hub_full0, uint32_t hub_free0) {
+  const int K = 64 * VEC;
+  const int g = lane >> 3, c = lane & 7;
+  const float* col = p.in + hw * (K / 8) + c * VEC;
+  float acc[VEC], bacc = 0.f;
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+  int cur_slot = -1;
+  auto flush = [&]() {
+    if (cur_slot >= 0) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 8);
+        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
+      }
+      if (g == 0) VecLd<VEC>::st(p.mlong_w + (size_t)cur_slot * K + hw * (K / 8) + c * VEC, acc);
+      if (hw == 0) {
+        bacc += __shfl_xor_sync(0xffffffffu, bacc, 8);
+        bacc += __shfl_xor_sync(0xffffffffu, bacc, 16);
+        if (lane == 0) p.mlong_bound_w[cur_slot] = bacc;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    bacc = 0.f;
+  };
+  // 32 edge records starting at eb + b0 (one per lane); records past the tile's slice are empty
+  int src_n = 0, slot_n = -1;
+  float nrm_n = 0.f;
+  auto load_records = [&](int eb, int ne, int b0) {
+    const int idx = b0 + lane;
+    src_n = 0; nrm_n = 0.f; slot_n = -1;
+    if (idx < ne) {
+      src_n = p.hub_src[eb + idx];
+      nrm_n = p.hub_nrm[eb + idx];
+      slot_n = p.hub_slot[eb + idx];
+    }
+  };
+  auto tile_slice = [&](int pr, int& eb, int& ne) {
+    eb = 0; ne = 0;
+    if (pr < p_end) {
+      const PairEnt* e = p.pairs + pr;
+      eb = __ldg(&e->hub_eb[rank]);
+      ne = __ldg(&e->hub_ne[rank]);
+    }
+  };
+  int eb, ne, eb_n, ne_n, eb_nn, ne_nn;
+  tile_slice(p_beg, eb, ne);
+  tile_slice(p_beg + 1, eb_n, ne_n);
+  load_records(eb, ne, 0);
+  int ti = 0;
+  for (int pr = p_beg; pr < p_end; ++pr, ++ti) {
+    tile_slice(pr + 2, eb_nn, ne_nn);
+    if (ti >= HUB_DEPTH)      // bounded run-ahead: keeps what these warps fetch in L2 until the producers use it
+      mbar_wait(hub_free0 + 8u * (ti % HUB_DEPTH), (uint32_t)(((ti / HUB_DEPTH) - 1) & 1), 9);
+    int b0 = 0;
+    if (p.dbg & 16) { ne = 0; ne_n = 0; }     // ablation: no hub work at all
+    do {
+      const int src = src_n, slot = slot_n;
+      const float nrm = nrm_n;
+      // next batch's records (possibly the first of the next tile) while this batch's rows are fetched
+      if (b0 + 32 < ne) load_records(eb, ne, b0 + 32);
+      else load_records(eb_n, ne_n, 0);
+      float term = 0.f;
+      if (hw == 0 && nrm != 0.f) term = nrm * p.in_rowmax[src];
+      float x[8][VEC], w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        w[j] = __shfl_sync(0xffffffffu, nrm, 4 * j + g);
+        const int sj = __shfl_sync(0xffffffffu, src, 4 * j + g);
+        if (w[j] != 0.f && !(p.dbg & 2)) VecLd<VEC>::ld(x[j], col + (size_t)sj * p.ld_in);
+        else {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) x[j][k] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int sl = __shfl_sync(0xffffffffu, slot, 4 * j);     // hubs start on round boundaries
+        const float tj = __shfl_sync(0xffffffffu, term, 4 * j + g);
+        if (sl != cur_slot) { flush(); cur_slot = sl; }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] = fmaf(w[j], x[j][k], acc[k]);
+        if (c == 0) bacc += tj;
+      }
+      b0 += 32;
+    } while (b0 < ne);
+    flush();
+    cur_slot = -1;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(hub_full0 + 8u * (ti % HUB_DEPTH));
+    eb = eb_n; ne = ne_n; eb_n = eb_nn; ne_n = ne_nn;
+  }
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 gcn_layer_fwd_pair_kernel(const PairParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -388,7 +511,7 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       if (p_beg + 1 < p_end) ent_tile(p_beg + 1, row0_n, nrows_n);
       int4 rc = make_int4(0, 0, 0, 0);
       if (r < nrows) rc = __ldg(reinterpret_cast<const int4*>(p.rec + row0 + r));
-      mbar_wait(hub_full(0), 0u, 8);        // the first tile's hub rows are aggregated
+      if (!(p.dbg & 8)) mbar_wait(hub_full(0), 0u, 8);        // the first tile's hub rows are aggregated
       cur.decode(rc, r < nrows, p, sub);
       gather_request(bufA, cur, 0, p.dbg);
     }
@@ -439,7 +562,8 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       for (int kc = 0; kc < nkc; kc += 2) {
         if (kc == 0 && live_n) rc_n = __ldg(reinterpret_cast<const int4*>(p.rec + row0_n + r));
         if (kc == ((nkc >> 2) << 1)) {
-          if (pr + 1 < p_end) mbar_wait(hub_full((ti + 1) % HUB_DEPTH), (uint32_t)(((ti + 1) / HUB_DEPTH) & 1), 8);
+          if (pr + 1 < p_end && !(p.dbg & 8))
+            mbar_wait(hub_full((ti + 1) % HUB_DEPTH), (uint32_t)(((ti + 1) / HUB_DEPTH) & 1), 8);
           nxt.decode(rc_n, live_n, p, sub);
         }
         step(bufA, bufB, kc, n0, n1);
@@ -459,115 +583,15 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
 #endif
   } else if (warp < WARP_LOAD) {
     // ===================== hub-row aggregation warps =====================
-    // mlong[slot][:] = sum_e hub_nrm[e] * in[hub_src[e]][:] for the hub rows of this CTA's tiles, a few tiles
-    // ahead of the producers (which then find the subgraph's rows in L2).  Hubs of degree <= HUB_SMALL: one
-    // warp each; larger hubs: the eight warps take 32-edge blocks round-robin and the partial sums are combined
-    // through an L2-resident scratch in a fixed order -> deterministic.
+    // mlong[slot][:] = sum_e nrm[e] * in[src[e]][:] for the hub rows of this CTA's tiles, a few tiles ahead
+    // of the producers (which then find the subgraph's rows in L2).  Warp hw owns the column slice
+    // [hw*K/8, (hw+1)*K/8) of EVERY hub row and streams through the tile's padded edge records, 32 at a
+    // time (8 rounds of 4 edges: 8 lanes x VEC floats per edge), so no partial sums cross warps, no
+    // barriers are needed, and the summation order is fixed.
     reg_dec<REGS_HUB>();
-    const int hw = warp - WARP_HUB0;
-    const int lpr = K >= 256 ? 32 : K / 8;          // lanes per row: 8 floats (32 bytes) each
-    const int eg = lane / lpr, lc = (lane - eg * lpr) * 8;
-    const int epw = 32 / lpr;                        // edges per warp-wide load
-    float* scratch = p.hub_scratch + (size_t)blockIdx.x * 2 * N_HUB_WARPS * (K + 32);
-    // partial sum over edges [e0, e1) of one hub (at most 32 of them) for columns cb + lc .. +7
-    auto edge_block = [&](int beg, int e0, int e1, int cb, float (&acc)[8], float& bsum, bool want_bound) {
-      const int e = e0 + lane;
-      int src = 0;
-      float nr = 0.f;
-      if (e < e1) { src = p.hub_src[beg + e]; nr = p.hub_nrm[beg + e]; }
-      if (want_bound && nr != 0.f) bsum = fmaf(nr, p.in_rowmax[src], bsum);
-      const int cnt = e1 - e0;
-      for (int j = 0; j < cnt; j += 4 * epw) {
-        float xv[4][8], wv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int idx = j + u * epw + eg;
-          wv[u] = __shfl_sync(0xffffffffu, nr, idx & 31);
-          const int sj = __shfl_sync(0xffffffffu, src, idx & 31);
-          if (idx >= cnt) wv[u] = 0.f;
-          if (wv[u] != 0.f && !(p.dbg & 2)) ld8(xv[u], p.in + (size_t)sj * p.ld_in + cb + lc);
-          else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) xv[u][k] = 0.f;
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int k = 0; k < 8; ++k) acc[k] = fmaf(wv[u], xv[u][k], acc[k]);
-      }
-    };
-    auto reduce_groups = [&](float (&acc)[8]) {     // combine the edge groups of a warp (K < 256)
-      for (int o = lpr; o < 32; o <<= 1)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-    };
-    int ti = 0, n_big = 0;
-    for (int pr = p_beg; pr < p_end; ++pr, ++ti) {
-      const int tile = p.pairs[pr].tile[rank];
-      int2 th = make_int2(0, 0);
-      if (tile >= 0) th = __ldg(p.tile_hubs + tile);
-      if (ti >= HUB_DEPTH) mbar_wait(hub_free(ti % HUB_DEPTH), (uint32_t)(((ti / HUB_DEPTH) - 1) & 1), 9);
-      for (int cb = 0; cb < K; cb += 256) {          // 256-column blocks (one for K <= 256)
-        // small hubs: warp hw takes hubs hw, hw + 8, ...
-        for (int i = hw; i < th.y; i += N_HUB_WARPS) {
-          const int slot = th.x + i;
-          const int deg = p.hub_deg[slot];
-          if (deg > HUB_SMALL) continue;
-          const int beg = p.hub_beg[slot];
-          float acc[8], bsum = 0.f;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-          edge_block(beg, 0, deg, cb, acc, bsum, cb == 0);
-          reduce_groups(acc);
-          if (eg == 0) st_f8(p.mlong_w + (size_t)slot * K + cb + lc, acc);
-          if (cb == 0) {
-#pragma unroll
-            for (int o = 16; o; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
-            if (lane == 0) p.mlong_bound_w[slot] = bsum;
-          }
-        }
-        // large hubs: all eight warps together
-        for (int i = 0; i < th.y; ++i) {
-          const int slot = th.x + i;
-          const int deg = p.hub_deg[slot];
-          if (deg <= HUB_SMALL) continue;
-          const int beg = p.hub_beg[slot];
-          float acc[8], bsum = 0.f;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-          for (int e0 = 32 * hw; e0 < deg; e0 += 32 * N_HUB_WARPS)
-            edge_block(beg, e0, e0 + 32 < deg ? e0 + 32 : deg, cb, acc, bsum, cb == 0);
-          reduce_groups(acc);
-          float* sc = scratch + (size_t)(n_big & 1) * N_HUB_WARPS * (K + 32);
-          const int kw = K < 256 ? K : 256;           // columns of this block
-          if (eg == 0) st_f8(sc + (size_t)hw * (K + 32) + lc, acc);
-          if (cb == 0) {
-#pragma unroll
-            for (int o = 16; o; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
-            if (lane == 0) sc[(size_t)hw * (K + 32) + K] = bsum;
-          }
-          asm volatile("bar.sync 3, 256;" ::: "memory");
-          // warp hw sums the eight partials of columns [hw * kw/8, (hw+1) * kw/8) in warp order
-          const int per = kw / N_HUB_WARPS;
-          if (lane < per) {
-            float t = 0.f;
-#pragma unroll
-            for (int j = 0; j < N_HUB_WARPS; ++j) t += sc[(size_t)j * (K + 32) + hw * per + lane];
-            p.mlong_w[(size_t)slot * K + cb + hw * per + lane] = t;
-          }
-          if (cb == 0 && hw == 0 && lane == 0) {
-            float t = 0.f;
-#pragma unroll
-            for (int j = 0; j < N_HUB_WARPS; ++j) t += sc[(size_t)j * (K + 32) + K];
-            p.mlong_bound_w[slot] = t;
-          }
-          ++n_big;
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(hub_full(ti % HUB_DEPTH));
-    }
+    if (K == 256) hub_warp_loop<4>(p, warp - WARP_HUB0, lane, rank, p_beg, p_end, hub_full(0), hub_free(0));
+    else if (K == 128) hub_warp_loop<2>(p, warp - WARP_HUB0, lane, rank, p_beg, p_end, hub_full(0), hub_free(0));
+    else hub_warp_loop<1>(p, warp - WARP_HUB0, lane, rank, p_beg, p_end, hub_full(0), hub_free(0));
   } else if (warp < WARP_EPI0) {
     reg_dec<REGS_CTRL>();
     if (warp == WARP_LOAD) {
@@ -841,8 +865,9 @@ __global__ void plan_tiles_kernel(const int32_t* __restrict__ indptr, const int3
       const unsigned bal = __ballot_sync(0xffffffffu, hub[j]);
       hrank[j] = n_h + __popc(bal & ((1u << lane) - 1u));
       n_h += __popc(bal);
-      const int incl = warp_incl_scan(hub[j] ? deg[j] : 0, lane);
-      eoff[j] = n_e + incl - (hub[j] ? deg[j] : 0);
+      const int pdeg = hub[j] ? (deg[j] + 3) & ~3 : 0;     // records of this hub, padded to whole rounds of 4
+      const int incl = warp_incl_scan(pdeg, lane);
+      eoff[j] = n_e + incl - pdeg;
       n_e += __shfl_sync(0xffffffffu, incl, 31);
     }
     int hbase = 0, ebase = 0;
@@ -852,7 +877,7 @@ __global__ void plan_tiles_kernel(const int32_t* __restrict__ indptr, const int3
     }
     hbase = __shfl_sync(0xffffffffu, hbase, 0);
     ebase = __shfl_sync(0xffffffffu, ebase, 0);
-    if (lane == 0) pl.tile_hubs[tile] = make_int2(hbase, n_h);
+    if (lane == 0) pl.tile_hubs[tile] = make_int2(ebase, n_e);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int r = 32 * j + lane;
@@ -881,7 +906,7 @@ __global__ void plan_tiles_kernel(const int32_t* __restrict__ indptr, const int3
   }
 }
 
-// one warp per hub slot: its edges, coalesced, in CSR order
+// one warp per hub slot: its edge records, coalesced, in CSR order, padded with zero-weight records
 __global__ void plan_hub_edges_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                       const float* __restrict__ norm, const int32_t* __restrict__ in_row_map,
                                       Plan pl) {
@@ -889,11 +914,18 @@ __global__ void plan_hub_edges_kernel(const int32_t* __restrict__ indptr, const 
   const int lane = threadIdx.x & 31;
   for (int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < n_hub; slot += (gridDim.x * blockDim.x) >> 5) {
     const int beg = indptr[pl.hub_row[slot]], deg = pl.hub_deg[slot], dst = pl.hub_beg[slot];
-    for (int e = lane; e < deg; e += 32) {
-      const int u = indices[beg + e];
-      const int s = in_row_map ? in_row_map[u] : u;
+    const int pdeg = (deg + 3) & ~3;
+    for (int e = lane; e < pdeg; e += 32) {
+      int s = -1;
+      float nr = 0.f;
+      if (e < deg) {
+        const int u = indices[beg + e];
+        s = in_row_map ? in_row_map[u] : u;
+        nr = norm[u];
+      }
       pl.hub_src[dst + e] = s < 0 ? 0 : s;
-      pl.hub_nrm[dst + e] = s < 0 ? 0.f : norm[u];
+      pl.hub_nrm[dst + e] = s < 0 ? 0.f : nr;
+      pl.hub_slot[dst + e] = slot;
     }
   }
 }
@@ -927,6 +959,8 @@ __global__ void __launch_bounds__(1024) pair_table_kernel(const int32_t* __restr
     PairEnt e;
     e.row0[0] = e.row0[1] = e.nrows[0] = e.nrows[1] = e.task = e.pad = 0;
     e.tile[0] = e.tile[1] = -1;
+    e.hub_eb[0] = e.hub_eb[1] = e.hub_ne[0] = e.hub_ne[1] = 0;
+    e.pad2[0] = e.pad2[1] = e.pad2[2] = e.pad2[3] = 0;
     pl.pairs[i] = e;
   }
   __syncthreads();
@@ -937,66 +971,12 @@ __global__ void __launch_bounds__(1024) pair_table_kernel(const int32_t* __restr
     e->row0[j & 1] = tile_row0[i];
     e->nrows[j & 1] = tile_nrows[i];
     e->tile[j & 1] = i;
+    const int2 th = pl.tile_hubs[i];
+    e->hub_eb[j & 1] = th.x;
+    e->hub_ne[j & 1] = th.y;
     if (!(j & 1)) e->task = t;
   }
   if (threadIdx.x == 0) pl.hdr[2] = total;
-}
-
-// mlong[slot][:] = sum_e hub_nrm[e] * in[hub_src[e]][:] for every hub slot, and the bound
-// sum_e hub_nrm[e] * in_rowmax[hub_src[e]].  One warp per (slot, 32-column slice): no reduction across
-// warps; inside the warp the four 8-lane groups take edges round-robin (8 x 16 bytes in flight per
-// lane) and are combined with a fixed shuffle tree -> deterministic.
-__global__ void __launch_bounds__(256) hub_rows_kernel(const float* __restrict__ in, int ld_in, int f_in,
-                                                       const float* __restrict__ in_rowmax, Plan pl,
-                                                       float* __restrict__ mlong, float* __restrict__ mlong_bound) {
-  const int n_hub = pl.hdr[0];
-  const int n_slices = f_in >> 5;
-  const int lane = threadIdx.x & 31, g = lane >> 3, c4 = (lane & 7) * 4;
-  const long long items = (long long)n_hub * n_slices;
-  for (long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; w < items;
-       w += ((long long)gridDim.x * blockDim.x) >> 5) {
-    const int slot = (int)(w / n_slices), slice = (int)(w - (long long)slot * n_slices);
-    const int beg = pl.hub_beg[slot], deg = pl.hub_deg[slot];
-    const float* col = in + 32 * slice + c4;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    float bsum = 0.f;
-    for (int base = 0; base < deg; base += 32) {
-      const int e = base + lane;
-      int s = 0;
-      float nr = 0.f;
-      if (e < deg) { s = pl.hub_src[beg + e]; nr = pl.hub_nrm[beg + e]; }
-      if (slice == 0 && nr != 0.f) bsum = fmaf(nr, in_rowmax[s], bsum);
-      float4 xv[8];
-      float wv[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int idx = 4 * j + g;
-        wv[j] = __shfl_sync(0xffffffffu, nr, idx);
-        const int sj = __shfl_sync(0xffffffffu, s, idx);
-        xv[j] = wv[j] != 0.f ? ld_f4(col + (size_t)sj * ld_in) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc.x = fmaf(wv[j], xv[j].x, acc.x);
-        acc.y = fmaf(wv[j], xv[j].y, acc.y);
-        acc.z = fmaf(wv[j], xv[j].z, acc.z);
-        acc.w = fmaf(wv[j], xv[j].w, acc.w);
-      }
-    }
-#pragma unroll
-    for (int o = 8; o <= 16; o <<= 1) {
-      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
-      acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
-    }
-    if (g == 0) st_f4(mlong + (size_t)slot * f_in + 32 * slice + c4, acc);
-    if (slice == 0) {
-#pragma unroll
-      for (int o = 16; o; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
-      if (lane == 0) mlong_bound[slot] = bsum;
-    }
-  }
 }
 
 int g_pair_dbg = 0;
@@ -1014,7 +994,7 @@ bool gcn_layer_fwd_pair_supported(const GatherSrc& g, int f_out, const float* bi
                                   const float* relu_mask, const float* out, int ld_out, int n_tasks) {
   if (bias && (!aligned16(bias) || b_task_stride % 4 != 0)) return false;
   if (relu_mask && !aligned16(relu_mask)) return false;
-  if (g.f_in % WCH != 0 || g.f_in < WCH || g.f_in > 1024) return false;
+  if (g.f_in != 64 && g.f_in != 128 && g.f_in != 256) return false;   // hub warps: K/8 columns per warp
   if (f_out % 16 != 0 || f_out < 16 || f_out > 256) return false;
   if (g.ld_in % 8 != 0 || (reinterpret_cast<uintptr_t>(g.in) & 31u) || g.ld_in < g.f_in) return false;   // 256-bit loads
   if (ld_out % 8 != 0 || (reinterpret_cast<uintptr_t>(out) & 31u)) return false;
@@ -1093,8 +1073,8 @@ int gcn_layer_fwd_pair(const GatherSrc& g, const int32_t* tile_row0, const int32
   p.in = g.in; p.ld_in = g.ld_in; p.f_in = K; p.in_rowmax = in_rowmax;
   p.mlong = ws.mlong; p.mlong_bound = ws.mlong_bound;
   p.rec = pl.rec; p.hdr = pl.hdr; p.pairs = pl.pairs;
-  p.tile_hubs = pl.tile_hubs; p.hub_beg = pl.hub_beg; p.hub_deg = pl.hub_deg; p.hub_src = pl.hub_src; p.hub_nrm = pl.hub_nrm;
-  p.mlong_w = ws.mlong; p.mlong_bound_w = ws.mlong_bound; p.hub_scratch = ws.hub_scratch;
+  p.hub_src = pl.hub_src; p.hub_nrm = pl.hub_nrm; p.hub_slot = pl.hub_slot;
+  p.mlong_w = ws.mlong; p.mlong_bound_w = ws.mlong_bound;
   p.dst_rows = g.dst_rows; p.norm = g.norm;
   p.w_image = ws.w_image; p.image_task_stride = n_copies > 1 ? 2LL * K * N : 0; p.w_inv_scale = ws.w_inv_scale;
   p.bias = bias; p.b_task_stride = b_task_stride; p.f_out = N; p.relu = relu; p.relu_mask = relu_mask;
