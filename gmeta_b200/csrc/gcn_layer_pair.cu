@@ -55,14 +55,17 @@ constexpr int A_HALF_BYTES = TM * 64;          // 8 KB: hi (or lo) operand tile 
 constexpr int STAGE_BYTES = 2 * A_HALF_BYTES;  // 16 KB
 // warp roles (register budgets are re-balanced per warpgroup with setmaxnreg)
 constexpr int N_PROD_WARPS = 8;                // warps 0..7   gather producers
-constexpr int WARP_HUB0 = 8;                   // warps 8..15  hub-row aggregation
-constexpr int WARP_LOAD = 16;                  // warp 16      weight loader (+ TMEM allocation)
-constexpr int WARP_MMA = 17;                   // warp 17      MMA issuer (18, 19 idle)
-constexpr int WARP_EPI0 = 20;                  // warps 20..23 epilogue
-constexpr int NTHREADS = 24 * 32;
-constexpr int REGS_PROD = 104, REGS_HUB = 72, REGS_CTRL = 40, REGS_EPI = 88;
-// setmaxnreg re-distributes the registers the CTA got at launch (768 threads x 80): 256*104 + 256*72 + 128*40 + 128*88 = 61440
-static_assert(8 * 32 * REGS_PROD + 8 * 32 * REGS_HUB + 4 * 32 * REGS_CTRL + 4 * 32 * REGS_EPI <= NTHREADS * 80, "register budget");
+constexpr int WARP_HUB0 = 8;                   // warps 8..11  hub-row aggregation
+constexpr int N_HUB_WARPS = 4;
+constexpr int WARP_LOAD = 12;                  // warp 12      weight loader (+ TMEM allocation)
+constexpr int WARP_MMA = 13;                   // warp 13      MMA issuer (14, 15 idle)
+constexpr int WARP_EPI0 = 16;                  // warps 16..19 epilogue
+constexpr int NTHREADS = 20 * 32;
+constexpr int REGS_ENTRY = 96;                 // registers per thread at launch: 64K / 640 threads, rounded down to 8
+constexpr int REGS_PROD = 120, REGS_HUB = 120, REGS_CTRL = 24, REGS_EPI = 96;
+// setmaxnreg re-distributes the registers the CTA got at launch (640 threads x 96 = 61440)
+static_assert(8 * 32 * REGS_PROD + 4 * 32 * REGS_HUB + 4 * 32 * REGS_CTRL + 4 * 32 * REGS_EPI <= NTHREADS * REGS_ENTRY,
+              "register budget");
 #ifndef GMETA_PAIR_PROF
 #define GMETA_PAIR_PROF 0      // 1: per-role cycle counters (costs registers; debug builds only)
 #endif
@@ -70,9 +73,9 @@ constexpr int MAX_STAGES = 6;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_COLS = 256;
 constexpr int PRE = 2;                         // in-neighbours per row the fused kernel gathers itself
-constexpr int SMEM_FIXED = 256 /*barriers*/ + 4 * TM /*row scale exponents*/ + ACC_COLS * 4 /*bias*/;
+constexpr int EPI_STAGE_BYTES = 4 * 32 * 32 * 4;   // one 32x32 fp32 transpose tile per epilogue warp (XOR-swizzled)
+constexpr int SMEM_FIXED = 256 /*barriers*/ + 4 * TM /*row scale exponents*/ + ACC_COLS * 4 /*bias*/ + EPI_STAGE_BYTES;
 constexpr int SMEM_MAX = 227 * 1024;
-constexpr int N_HUB_WARPS = 8;
 constexpr int HUB_DEPTH = 4;                   // tiles the hub warps may run ahead of the producers
 constexpr int PT_MAXT = 2048;                  // tasks the pair-table kernel handles
 constexpr int SCALE_TARGET = 13;               // scaled bound in [2^13, 2^14): 4x below the FP16 maximum
@@ -262,37 +265,34 @@ struct RowCtx {
     a0 = __int_as_float(rc.z);
     a1 = __int_as_float(rc.w);
     if (a0 != 0.f) {
-      s0 = (hub ? p.mlong + (size_t)rc.x * p.f_in : p.in + (size_t)rc.x * p.ld_in) + 16 * sub;
+      s0 = (hub ? p.mlong + (size_t)rc.x * p.f_in : p.in + (size_t)rc.x * p.ld_in) + 8 * sub;
       rm0 = hub ? p.mlong_bound[rc.x] : p.in_rowmax[rc.x];
     }
     if (a1 != 0.f) {
-      s1 = p.in + (size_t)rc.y * p.ld_in + 16 * sub;
+      s1 = p.in + (size_t)rc.y * p.ld_in + 8 * sub;
       rm1 = p.in_rowmax[rc.y];
     }
   }
 };
-// buf[0..15] = 16 floats of source 0 at column offset `off`, buf[16..31] = of source 1 (zeros when absent)
-__device__ __forceinline__ void gather_request(float (&buf)[32], const RowCtx& c, int off, int dbg) {
-  if (c.a0 != 0.f && !(dbg & 2)) {
-    ld8(buf, c.s0 + off);
-    ld8(buf + 8, c.s0 + off + 8);
-  } else {
+// buf[0..7] = 8 floats of source 0 at column offset `off`, buf[8..15] = of source 1 (zeros when absent)
+__device__ __forceinline__ void gather_request(float* buf, const RowCtx& c, int off, int dbg) {
+  if (c.a0 != 0.f && !(dbg & 2)) ld8(buf, c.s0 + off);
+  else {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) buf[j] = 0.f;
+    for (int j = 0; j < 8; ++j) buf[j] = 0.f;
   }
-  if (c.a1 != 0.f && !(dbg & 2)) {
-    ld8(buf + 16, c.s1 + off);
-    ld8(buf + 24, c.s1 + off + 8);
-  } else {
+  if (c.a1 != 0.f && !(dbg & 2)) ld8(buf + 8, c.s1 + off);
+  else {
 #pragma unroll
-    for (int j = 16; j < 32; ++j) buf[j] = 0.f;
+    for (int j = 8; j < 16; ++j) buf[j] = 0.f;
   }
 }
 
 template <int R>
-__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
-template <int R>
-__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+__device__ __forceinline__ void reg_set() {      // setmaxnreg for the executing warpgroup
+  if constexpr (R > REGS_ENTRY) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R));
+  else if constexpr (R < REGS_ENTRY) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R));
+}
 
 template <int VEC> struct VecLd;
 template <> struct VecLd<4> {
@@ -304,6 +304,10 @@ template <> struct VecLd<4> {
     *reinterpret_cast<float4*>(p) = make_float4(d[0], d[1], d[2], d[3]);
   }
 };
+template <> struct VecLd<8> {
+  static __device__ __forceinline__ void ld(float (&d)[8], const float* p) { ld8(d, p); }
+  static __device__ __forceinline__ void st(float* p, const float (&d)[8]) { st_f8(p, d); }
+};
 template <> struct VecLd<2> {
   static __device__ __forceinline__ void ld(float (&d)[2], const float* p) {
     const float2 v = *reinterpret_cast<const float2*>(p);
@@ -313,19 +317,15 @@ template <> struct VecLd<2> {
     *reinterpret_cast<float2*>(p) = make_float2(d[0], d[1]);
   }
 };
-template <> struct VecLd<1> {
-  static __device__ __forceinline__ void ld(float (&d)[1], const float* p) { d[0] = *p; }
-  static __device__ __forceinline__ void st(float* p, const float (&d)[1]) { *p = d[0]; }
-};
 
-// One hub warp (see the call site).  K = 64 * VEC; lane = 8 * g + c: edge group g (edges 4j + g of a
-// round-of-4 sequence), column unit c (VEC floats at hw*K/8 + c*VEC).
+// One hub warp (see the call site).  K = 32 * VEC; lane = 8 * g + c: edge group g (edges 4j + g of a
+// round-of-4 sequence), column unit c (VEC floats at hw*K/4 + c*VEC).
 template <int VEC>
 __device__ __forceinline__ void hub_warp_loop(const PairParams& p, int hw, int lane, uint32_t rank, int p_beg,
                                               int p_end, uint32_t hub_full0, uint32_t hub_free0) {
-  const int K = 64 * VEC;
+  const int K = 32 * VEC;
   const int g = lane >> 3, c = lane & 7;
-  const float* col = p.in + hw * (K / 8) + c * VEC;
+  const float* col = p.in + hw * (K / N_HUB_WARPS) + c * VEC;
   float acc[VEC], bacc = 0.f;
 #pragma unroll
   for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
@@ -337,7 +337,7 @@ __device__ __forceinline__ void hub_warp_loop(const PairParams& p, int hw, int l
         acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 8);
         acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
       }
-      if (g == 0) VecLd<VEC>::st(p.mlong_w + (size_t)cur_slot * K + hw * (K / 8) + c * VEC, acc);
+      if (g == 0) VecLd<VEC>::st(p.mlong_w + (size_t)cur_slot * K + hw * (K / N_HUB_WARPS) + c * VEC, acc);
       if (hw == 0) {
         bacc += __shfl_xor_sync(0xffffffffu, bacc, 8);
         bacc += __shfl_xor_sync(0xffffffffu, bacc, 16);
@@ -382,9 +382,9 @@ __device__ __forceinline__ void hub_warp_loop(const PairParams& p, int hw, int l
     do {
       const int src = src_n, slot = slot_n;
       const float nrm = nrm_n;
-      // next batch's records (possibly the first of the next tile) while this batch's rows are fetched
+      // next batch's records while this batch's rows are fetched (the next TILE's first batch is requested
+      // after the tile's arrive below: a release-arrive waits for the thread's outstanding loads)
       if (b0 + 32 < ne) load_records(eb, ne, b0 + 32);
-      else load_records(eb_n, ne_n, 0);
       float term = 0.f;
       if (hw == 0 && nrm != 0.f) term = nrm * p.in_rowmax[src];
       float x[8][VEC], w[8];
@@ -412,8 +412,9 @@ __device__ __forceinline__ void hub_warp_loop(const PairParams& p, int hw, int l
     flush();
     cur_slot = -1;
     __syncwarp();
-    if (lane == 0) mbar_arrive(hub_full0 + 8u * (ti % HUB_DEPTH));
+    if (lane == 0) mbar_arrive(hub_full0 + 8u * (ti % HUB_DEPTH));   // release: the mlong rows are visible to the producers
     eb = eb_n; ne = ne_n; eb_n = eb_nn; ne_n = ne_nn;
+    load_records(eb, ne, 0);
   }
 }
 
@@ -442,6 +443,7 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 240);
   int8_t* scale_e = reinterpret_cast<int8_t*>(bars) + 256;               // [4][TM]
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256 + 4 * TM);   // [ACC_COLS]
+  float* epi_s = bias_s + ACC_COLS;                                      // [4 warps][32 rows][32 floats]
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();   // SWIZZLE_128B operand tiles need a 1024-byte aligned base
@@ -487,91 +489,117 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
 
   if (warp < N_PROD_WARPS) {
     // ===================== gather producers =====================
-    reg_inc<REGS_PROD>();
-    const int r = warp * 16 + (lane >> 1);  // a lane pair owns tile row r
-    const int sub = lane & 1;               // and, within a 32-float chunk, floats [16*sub, 16*sub + 16)
-    const int sw = (r >> 1) & 3;            // 64B swizzle: 16-byte unit ^ ((row / 2) % 4)
-    const int soff0 = r * 64 + (((2 * sub) ^ sw) << 4);
-    const int soff1 = r * 64 + (((2 * sub + 1) ^ sw) << 4);
+    reg_set<REGS_PROD>();
+    // a lane quad owns tile rows rA = 8*warp + lane/4 and rA + 64; within a 32-float chunk lane `sub` holds floats
+    // [8*sub, 8*sub + 8): the quad's loads cover one whole 128-byte line per source row
+    const int rA = warp * 8 + (lane >> 2);
+    const int sub = lane & 3;
+    const int soffA = rA * 64 + ((sub ^ ((rA >> 1) & 3)) << 4);          // 64B swizzle: 16-byte unit ^ ((row / 2) % 4)
+    const int soffB = soffA + 64 * 64;                                    // row + 64: same swizzle phase
 #if GMETA_PAIR_PROF
     long long t_setup = 0, t_wait = 0, t_body = 0, t_mark = clock64();
 #define PLAP(acc) { const long long now_ = clock64(); acc += now_ - t_mark; t_mark = now_; }
 #else
 #define PLAP(acc)
 #endif
-    // per-tile context: source pointers (+ this lane's 16-float offset), raw norms, source abs-max
-    RowCtx cur, nxt;
-    float bufA[32], bufB[32];               // two chunks of this lane's segments: [nbr0 16 | nbr1 16]
+    RowCtx curA, curB, nxtA, nxtB;
+    float buf0[32], buf1[32];               // two chunks: [rowA src0 | rowA src1 | rowB src0 | rowB src1] x 8 floats
     int it = 0, ti = 0;
     int row0_n = 0, nrows_n = 0, row0_nn = 0, nrows_nn = 0;
-    cur.clear(p.in);
+    curA.clear(p.in);
+    curB.clear(p.in);
     if (p_beg < p_end) {
       int row0, nrows;
       ent_tile(p_beg, row0, nrows);
       if (p_beg + 1 < p_end) ent_tile(p_beg + 1, row0_n, nrows_n);
-      int4 rc = make_int4(0, 0, 0, 0);
-      if (r < nrows) rc = __ldg(reinterpret_cast<const int4*>(p.rec + row0 + r));
-      if (!(p.dbg & 8)) mbar_wait(hub_full(0), 0u, 8);        // the first tile's hub rows are aggregated
-      cur.decode(rc, r < nrows, p, sub);
-      gather_request(bufA, cur, 0, p.dbg);
+      int4 rcA = make_int4(0, 0, 0, 0), rcB = make_int4(0, 0, 0, 0);
+      if (rA < nrows) rcA = __ldg(reinterpret_cast<const int4*>(p.rec + row0 + rA));
+      if (rA + 64 < nrows) rcB = __ldg(reinterpret_cast<const int4*>(p.rec + row0 + rA + 64));
+      mbar_wait(hub_full(0), 0u, 8);        // the first tile's hub rows are aggregated
+      curA.decode(rcA, rA < nrows, p, sub);
+      curB.decode(rcB, rA + 64 < nrows, p, sub);
+      gather_request(buf0, curA, 0, p.dbg);
+      gather_request(buf0 + 16, curB, 0, p.dbg);
     }
+    float nA0 = 0.f, nA1 = 0.f, nB0 = 0.f, nB1 = 0.f;
     // one chunk: `mine` holds this chunk's segments, `other` receives the next chunk's (requested first,
     // so their latency overlaps the stage wait, the conversion and the stores)
-    auto step = [&](float (&mine)[32], float (&other)[32], int kc, float n0, float n1) {
+    auto step = [&](float (&mine)[32], float (&other)[32], int kc) {
       const int s = it % NS;
       const uint32_t ph = (uint32_t)((it / NS) & 1);
-      if (kc + 1 < nkc) gather_request(other, cur, (kc + 1) * KCH, p.dbg);
-      else gather_request(other, nxt, 0, p.dbg);                // first chunk of the next tile
+      if (kc + 1 < nkc) {
+        gather_request(other, curA, (kc + 1) * KCH, p.dbg);
+        gather_request(other + 16, curB, (kc + 1) * KCH, p.dbg);
+      } else {                                                  // first chunk of the next tile
+        gather_request(other, nxtA, 0, p.dbg);
+        gather_request(other + 16, nxtB, 0, p.dbg);
+      }
       PLAP(t_body);
       mbar_wait(empty(s), ph ^ 1u, 1);
       PLAP(t_wait);
-      if (cur.live) {
-        uint8_t* stage = a_s + (size_t)s * STAGE_BYTES;
-        float v[8];
-        uint4 hi, lo;
+      uint8_t* stage = a_s + (size_t)s * STAGE_BYTES;
+      float v[8];
+      uint4 hi, lo;
+      if (curA.live) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaf(n1, mine[16 + j], n0 * mine[j]);
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(nA1, mine[8 + j], nA0 * mine[j]);
         split8(v, hi, lo);
-        *reinterpret_cast<uint4*>(stage + soff0) = hi;
-        *reinterpret_cast<uint4*>(stage + A_HALF_BYTES + soff0) = lo;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaf(n1, mine[24 + j], n0 * mine[8 + j]);
-        split8(v, hi, lo);
-        *reinterpret_cast<uint4*>(stage + soff1) = hi;
-        *reinterpret_cast<uint4*>(stage + A_HALF_BYTES + soff1) = lo;
+        *reinterpret_cast<uint4*>(stage + soffA) = hi;
+        *reinterpret_cast<uint4*>(stage + A_HALF_BYTES + soffA) = lo;
       }
-      fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+      if (curB.live) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(nB1, mine[24 + j], nB0 * mine[16 + j]);
+        split8(v, hi, lo);
+        *reinterpret_cast<uint4*>(stage + soffB) = hi;
+        *reinterpret_cast<uint4*>(stage + A_HALF_BYTES + soffB) = lo;
+      }
+      // generic-proxy stores -> visible to the tensor core (async proxy).  The arrive is RELAXED: a release
+      // would also wait for this thread's outstanding global loads (the next chunk is always in flight).
+      if (!(p.dbg & 32)) fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(a_full(s), 0);
+      if (lane == 0) mbar_arrive_cluster_relaxed(a_full(s), 0);
       ++it;
     };
     for (int pr = p_beg; pr < p_end; ++pr, ++ti) {
-      // scale of this tile's row from the rigorous bound (see header comment)
-      const int e = scale_exponent(cur.a0 * cur.rm0 + cur.a1 * cur.rm1);
-      const float sc = exp2i(e);
-      const float n0 = cur.a0 * sc, n1 = cur.a1 * sc;
-      if (sub == 0 && cur.live) scale_e[(ti & 3) * TM + r] = (int8_t)e;
-      // context of the next tile, fetched while this one streams: pair entry two tiles ahead, row record
+      // scale of this tile's rows from the rigorous bound (see header comment)
+      {
+        const int eA = scale_exponent(curA.a0 * curA.rm0 + curA.a1 * curA.rm1);
+        const int eB = scale_exponent(curB.a0 * curB.rm0 + curB.a1 * curB.rm1);
+        nA0 = curA.a0 * exp2i(eA); nA1 = curA.a1 * exp2i(eA);
+        nB0 = curB.a0 * exp2i(eB); nB1 = curB.a1 * exp2i(eB);
+        if (sub == 0 && curA.live) scale_e[(ti & 3) * TM + rA] = (int8_t)eA;
+        if (sub == 0 && curB.live) scale_e[(ti & 3) * TM + rA + 64] = (int8_t)eB;
+      }
+      // context of the next tile, fetched while this one streams: pair entry two tiles ahead, row records
       // at chunk 0, source abs-max at the middle chunk, first feature segments at the last chunk
       nrows_nn = 0;
       if (pr + 2 < p_end) ent_tile(pr + 2, row0_nn, nrows_nn);
-      const bool live_n = r < nrows_n;
-      int4 rc_n = make_int4(0, 0, 0, 0);
-      nxt.clear(p.in);
+      const bool liveA_n = rA < nrows_n, liveB_n = rA + 64 < nrows_n;
+      int4 rcA_n = make_int4(0, 0, 0, 0), rcB_n = make_int4(0, 0, 0, 0);
+      nxtA.clear(p.in);
+      nxtB.clear(p.in);
       PLAP(t_setup);
       for (int kc = 0; kc < nkc; kc += 2) {
-        if (kc == 0 && live_n) rc_n = __ldg(reinterpret_cast<const int4*>(p.rec + row0_n + r));
+        if (kc == 0) {
+          if (liveA_n) rcA_n = __ldg(reinterpret_cast<const int4*>(p.rec + row0_n + rA));
+          if (liveB_n) rcB_n = __ldg(reinterpret_cast<const int4*>(p.rec + row0_n + rA + 64));
+        }
         if (kc == ((nkc >> 2) << 1)) {
+          PLAP(t_body);
           if (pr + 1 < p_end && !(p.dbg & 8))
             mbar_wait(hub_full((ti + 1) % HUB_DEPTH), (uint32_t)(((ti + 1) / HUB_DEPTH) & 1), 8);
-          nxt.decode(rc_n, live_n, p, sub);
+          PLAP(t_setup);
+          nxtA.decode(rcA_n, liveA_n, p, sub);
+          nxtB.decode(rcB_n, liveB_n, p, sub);
         }
-        step(bufA, bufB, kc, n0, n1);
-        step(bufB, bufA, kc + 1, n0, n1);
+        step(buf0, buf1, kc);
+        step(buf1, buf0, kc + 1);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(hub_free(ti % HUB_DEPTH));   // this tile's hub rows have been consumed
-      cur = nxt;
+      if (lane == 0) mbar_arrive_cluster_relaxed(hub_free(ti % HUB_DEPTH), rank);   // throttle only: no data ordering needed
+      curA = nxtA;
+      curB = nxtB;
       row0_n = row0_nn; nrows_n = nrows_nn;
       PLAP(t_body);
     }
@@ -585,15 +613,15 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
     // ===================== hub-row aggregation warps =====================
     // mlong[slot][:] = sum_e nrm[e] * in[src[e]][:] for the hub rows of this CTA's tiles, a few tiles ahead
     // of the producers (which then find the subgraph's rows in L2).  Warp hw owns the column slice
-    // [hw*K/8, (hw+1)*K/8) of EVERY hub row and streams through the tile's padded edge records, 32 at a
+    // [hw*K/4, (hw+1)*K/4) of EVERY hub row and streams through the tile's padded edge records, 32 at a
     // time (8 rounds of 4 edges: 8 lanes x VEC floats per edge), so no partial sums cross warps, no
     // barriers are needed, and the summation order is fixed.
-    reg_dec<REGS_HUB>();
-    if (K == 256) hub_warp_loop<4>(p, warp - WARP_HUB0, lane, rank, p_beg, p_end, hub_full(0), hub_free(0));
-    else if (K == 128) hub_warp_loop<2>(p, warp - WARP_HUB0, lane, rank, p_beg, p_end, hub_full(0), hub_free(0));
-    else hub_warp_loop<1>(p, warp - WARP_HUB0, lane, rank, p_beg, p_end, hub_full(0), hub_free(0));
+    reg_set<REGS_HUB>();
+    if (K == 256) hub_warp_loop<8>(p, warp - WARP_HUB0, lane, rank, p_beg, p_end, hub_full(0), hub_free(0));
+    else if (K == 128) hub_warp_loop<4>(p, warp - WARP_HUB0, lane, rank, p_beg, p_end, hub_full(0), hub_free(0));
+    else hub_warp_loop<2>(p, warp - WARP_HUB0, lane, rank, p_beg, p_end, hub_full(0), hub_free(0));
   } else if (warp < WARP_EPI0) {
-    reg_dec<REGS_CTRL>();
+    reg_set<REGS_CTRL>();
     if (warp == WARP_LOAD) {
       // ===================== weight loader: one bulk copy per task change =====================
       if (lane == 0) {
@@ -620,30 +648,34 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       if (rank == 0 && lane == 0) {
         const uint32_t idesc = umma_idesc_f16(2 * TM, N);
         int it = 0, ti = 0, cur = -1, nw = 0;
+#if GMETA_PAIR_PROF
         long long t_w = 0, t_acc = 0, t_a = 0, t_issue = 0, t_mark = clock64();
-        auto lap = [&](long long& acc) { const long long now = clock64(); acc += now - t_mark; t_mark = now; };
+#define MLAP(acc) { const long long now_ = clock64(); acc += now_ - t_mark; t_mark = now_; }
+#else
+#define MLAP(acc)
+#endif
         int task_n = p_beg < p_end ? p.pairs[p_beg].task : 0;
         for (int pr = p_beg; pr < p_end; ++pr, ++ti) {
           const int task = task_n;
           if (pr + 1 < p_end) task_n = p.pairs[pr + 1].task;
-          lap(t_issue);
+          MLAP(t_issue);
           if (task != cur) {
             mbar_wait_cluster(w_ready, (uint32_t)(nw & 1), 4);
             cur = task;
             ++nw;
           }
-          lap(t_w);
+          MLAP(t_w);
           const int buf = ti & 1;
           mbar_wait_cluster(acc_empty(buf), (uint32_t)(((ti >> 1) & 1) ^ 1), 5);
-          lap(t_acc);
+          MLAP(t_acc);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
           for (int kc = 0; kc < nkc; ++kc, ++it) {
             const int s = it % NS;
             const uint32_t ph = (uint32_t)((it / NS) & 1);
-            lap(t_issue);
+            MLAP(t_issue);
             mbar_wait_cluster(a_full(s), ph, 6);
-            lap(t_a);
+            MLAP(t_a);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(a_s + (size_t)s * STAGE_BYTES);
             const uint32_t b_addr = smem_u32(w_s + (size_t)(kc >> 1) * 2 * half_n_bytes);
@@ -660,52 +692,60 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
               tc_mma_f16_pair(d_tmem, da_lo + adv_a, db_hi + adv_b, idesc, 1u);
               tc_mma_f16_pair(d_tmem, da_hi + adv_a, db_lo + adv_b, idesc, 1u);
             }
-            tc_commit_pair(empty(s));          // frees the stage in both CTAs once these MMAs have read it
+            if (!(p.dbg & 64)) tc_commit_pair(empty(s));          // frees the stage in both CTAs once these MMAs have read it
           }
           tc_commit_pair(acc_full(buf));       // accumulators complete -> both epilogues
           if (pr + 1 < p_end && task_n != task) tc_commit_pair(w_free);
         }
-        lap(t_issue);
+        MLAP(t_issue);
+#if GMETA_PAIR_PROF
         if (p.prof) {
           long long* o = p.prof + blockIdx.x * 16 + 6;
           o[0] = t_w; o[1] = t_acc; o[2] = t_a; o[3] = t_issue;
         }
+#endif
       }
     }
   } else {
     // ===================== epilogue =====================
-    reg_inc<REGS_EPI>();
+    reg_set<REGS_EPI>();
     const int quarter = warp & 3;            // TMEM lanes 32*quarter .. +31 are the ones this warp may read
-    const int r = quarter * 32 + lane;       // this lane owns tile row r: one full 32-byte sector per store
+    const int r = quarter * 32 + lane;       // accumulator row of this lane
     const int et = threadIdx.x - WARP_EPI0 * 32;
+    float* stg = epi_s + quarter * 32 * 32;  // [32 rows][8 x 16-byte units, unit ^ (row % 8)]
+    const int tr = lane >> 3, tu = lane & 7; // transposed side: rows 4*i + tr, 16-byte unit tu of the 32-column block
     int ti = 0, bias_task = -1;
+#if GMETA_PAIR_PROF
     long long t_wacc = 0, t_epi = 0, t_mark = clock64();
-    auto lap = [&](long long& acc) { const long long now = clock64(); acc += now - t_mark; t_mark = now; };
+#define ELAP(acc) { const long long now_ = clock64(); acc += now_ - t_mark; t_mark = now_; }
+#else
+#define ELAP(acc)
+#endif
     for (int pr = p_beg; pr < p_end; ++pr, ++ti) {
       const int buf = ti & 1;
-      const PairEnt ent = p.pairs[pr];
-      const int row0 = ent.row0[rank], nrows = ent.nrows[rank], task = ent.task;
+      const PairEnt* ent = p.pairs + pr;
+      const int row0 = __ldg(&ent->row0[rank]), nrows = __ldg(&ent->nrows[rank]), task = __ldg(&ent->task);
       const bool live = r < nrows;
       const int oi = row0 + (live ? r : 0);                           // output row (compact or dense)
       const int v = p.dst_rows ? p.dst_rows[oi] : oi;                 // real row: norm and mask
       const float nv = p.norm[v];
       const float wis = p.w_inv_scale[p.image_task_stride ? task : 0];
-      const float* mrow = p.relu_mask ? p.relu_mask + (size_t)v * p.ld_out : nullptr;
-      float* orow = p.out + (size_t)oi * p.ld_out;
-      if (task != bias_task) {     // the task's bias -> shared memory (broadcast reads below), once per task
+      if (task != bias_task) {     // the task's bias -> shared memory, once per task
         bias_task = task;
         asm volatile("bar.sync 2, 128;" ::: "memory");     // every epilogue warp is done with the old bias
         const float* bias = p.bias ? p.bias + (long long)task * p.b_task_stride : nullptr;
         for (int c = et; c < ACC_COLS; c += 128) bias_s[c] = (bias && c < N) ? bias[c] : 0.f;
         asm volatile("bar.sync 2, 128;" ::: "memory");
       }
-      lap(t_epi);
+      ELAP(t_epi);
       mbar_wait(acc_full(buf), (uint32_t)((ti >> 1) & 1), 7);
-      lap(t_wacc);
+      ELAP(t_wacc);
       tc_fence_after();
       const float f = live ? nv * exp2i(-(int)scale_e[(ti & 3) * TM + r]) * wis : 0.f;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * ACC_COLS);
-      float rmax = 0.f;
+      float pmax[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pmax[i] = 0.f;
       for (int c0 = 0; c0 < N; c0 += 32) {
         uint32_t acc[32];
         if (c0 + 32 <= N) {
@@ -717,44 +757,58 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
           for (int j = 0; j < 16; ++j) { acc[j] = a16[j]; acc[16 + j] = 0u; }
         }
         tmem_ld_wait();
+        __syncwarp();                             // the previous block's transposed reads are done
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          if (c0 + j >= N) break;
-          const float4 b0 = ld_f4(bias_s + c0 + j), b1 = ld_f4(bias_s + c0 + j + 4);
-          float o[8];
-          o[0] = fmaf(f, __uint_as_float(acc[j]), b0.x);
-          o[1] = fmaf(f, __uint_as_float(acc[j + 1]), b0.y);
-          o[2] = fmaf(f, __uint_as_float(acc[j + 2]), b0.z);
-          o[3] = fmaf(f, __uint_as_float(acc[j + 3]), b0.w);
-          o[4] = fmaf(f, __uint_as_float(acc[j + 4]), b1.x);
-          o[5] = fmaf(f, __uint_as_float(acc[j + 5]), b1.y);
-          o[6] = fmaf(f, __uint_as_float(acc[j + 6]), b1.z);
-          o[7] = fmaf(f, __uint_as_float(acc[j + 7]), b1.w);
-          if (p.relu) {
+        for (int u = 0; u < 8; ++u)
+          st_f4(stg + lane * 32 + ((u ^ (lane & 7)) << 2),
+                make_float4(f * __uint_as_float(acc[4 * u]), f * __uint_as_float(acc[4 * u + 1]),
+                            f * __uint_as_float(acc[4 * u + 2]), f * __uint_as_float(acc[4 * u + 3])));
+        __syncwarp();
+        // transposed: a store instruction writes 4 rows x 128 contiguous bytes (whole lines); bias / ReLU / mask here
+        const bool col_ok = c0 + 4 * tu < N;
+        const float4 b4 = ld_f4(bias_s + ((c0 + 4 * tu) & (ACC_COLS - 1)));
 #pragma unroll
-            for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k], 0.f);
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + tr;
+          const int vr = __shfl_sync(0xffffffffu, v, rr);       // real row of tile row quarter*32 + rr
+          if (quarter * 32 + rr < nrows && col_ok) {
+            float4 w4 = ld_f4(stg + rr * 32 + ((tu ^ (rr & 7)) << 2));
+            w4.x += b4.x; w4.y += b4.y; w4.z += b4.z; w4.w += b4.w;
+            if (p.relu) { w4.x = fmaxf(w4.x, 0.f); w4.y = fmaxf(w4.y, 0.f); w4.z = fmaxf(w4.z, 0.f); w4.w = fmaxf(w4.w, 0.f); }
+            if (p.relu_mask) {
+              const float4 m4 = ld_f4(p.relu_mask + (size_t)vr * p.ld_out + c0 + 4 * tu);
+              if (!(m4.x > 0.f)) w4.x = 0.f;
+              if (!(m4.y > 0.f)) w4.y = 0.f;
+              if (!(m4.z > 0.f)) w4.z = 0.f;
+              if (!(m4.w > 0.f)) w4.w = 0.f;
+            }
+            pmax[i] = fmaxf(pmax[i], fmaxf(fmaxf(fabsf(w4.x), fabsf(w4.y)), fmaxf(fabsf(w4.z), fabsf(w4.w))));
+            if (!(p.dbg & 1)) st_f4(p.out + (size_t)(row0 + quarter * 32 + rr) * p.ld_out + c0 + 4 * tu, w4);
           }
-          if (mrow && live) {
-            const F8 m = ld_f8(mrow + c0 + j);
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              if (!(m.v[k] > 0.f)) o[k] = 0.f;
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) rmax = fmaxf(rmax, fabsf(o[k]));
-          if (live && !(p.dbg & 1)) st_f8(orow + c0 + j, o);
         }
       }
-      if (p.out_rowmax && live) p.out_rowmax[oi] = rmax;
+      if (p.out_rowmax) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float m = pmax[i];
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+          const int rr = 4 * i + tr;
+          if (tu == 0 && quarter * 32 + rr < nrows) p.out_rowmax[row0 + quarter * 32 + rr] = m;
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(acc_empty(buf), 0);
     }
-    lap(t_epi);
+    ELAP(t_epi);
+#if GMETA_PAIR_PROF
     if (p.prof && warp == WARP_EPI0 && lane == 0) {
       long long* o = p.prof + blockIdx.x * 16 + 10;
       o[0] = t_wacc; o[1] = t_epi;
     }
+#endif
   }
 
   __syncwarp();

@@ -38,6 +38,16 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
       "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar), "r"(cta) : "memory");
 }
+// same without release semantics: the caller has already ordered its shared-memory writes with
+// fence.proxy.async, and a release here would also wait for the thread's outstanding global loads
+// (the gather producers always have the next chunk's loads in flight)
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -79,6 +89,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int wha
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity))
     if (clock64() - t0 > kWaitTimeoutCycles) wait_timed_out(bar, parity, what);
+}
+// whole-warp wait: one lane polls (with back-off), the warp re-converges on __syncwarp.  Hundreds of
+// threads spinning on try_wait would otherwise flood the shared-memory pipe of the SM.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int what = 0) {
+  if ((threadIdx.x & 31) == 0 && !mbar_try_wait(bar, parity)) {
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+      __nanosleep(32);
+      if (clock64() - t0 > kWaitTimeoutCycles) wait_timed_out(bar, parity, what);
+    }
+  }
+  __syncwarp();
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int what = 0) {
   if (mbar_try_wait_cluster(bar, parity)) return;

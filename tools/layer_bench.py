@@ -56,6 +56,7 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--ablate", default="", help="comma list of debug flag masks to time (tcgen05 impl)")
     ap.add_argument("--plan", type=int, default=1, help="1: reuse a prebuilt layer plan (impl 3); 0: rebuild per call")
+    ap.add_argument("--profile-flags", type=int, default=0, help="ablation flags active during the --profile launch")
     ap.add_argument("--profile", action="store_true", help="per-role cycle counters of the tcgen05 kernel")
     a = ap.parse_args()
     L = _lib.lib()
@@ -127,7 +128,9 @@ def main():
         if impl == 3 and a.profile:
             prof = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
             L.gmeta_debug_set_pair_profile(prof.data_ptr())
+            L.gmeta_debug_set_pair_flags(a.profile_flags)
             launch()
+            L.gmeta_debug_set_pair_flags(0)
             torch.cuda.synchronize()
             L.gmeta_debug_set_pair_profile(None)
             pr = prof.cpu().numpy().reshape(148, 16).astype(np.float64)
