@@ -320,12 +320,19 @@ template <> struct VecLd<2> {
 
 // One hub warp (see the call site).  K = 32 * VEC; lane = 8 * g + c: edge group g (edges 4j + g of a
 // round-of-4 sequence), column unit c (VEC floats at hw*K/4 + c*VEC).
+// The warp walks a flat sequence of items = 32-record batches of its CTA's tiles (one empty item for a
+// tile without hub rows), three deep: the records of item i+2 are being loaded, the rows of item i+1
+// are being pulled into L2 (prefetch.global.L2: needs no registers), item i is gathered and summed.
+struct HubCursor {        // position of the next item to fetch
+  int pr, b0, eb, ne;
+};
 template <int VEC>
 __device__ __forceinline__ void hub_warp_loop(const PairParams& p, int hw, int lane, uint32_t rank, int p_beg,
                                               int p_end, uint32_t hub_full0, uint32_t hub_free0) {
   const int K = 32 * VEC;
   const int g = lane >> 3, c = lane & 7;
   const float* col = p.in + hw * (K / N_HUB_WARPS) + c * VEC;
+  const float* pf_col = p.in + hw * (K / N_HUB_WARPS);
   float acc[VEC], bacc = 0.f;
 #pragma unroll
   for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
@@ -348,50 +355,67 @@ __device__ __forceinline__ void hub_warp_loop(const PairParams& p, int hw, int l
     for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
     bacc = 0.f;
   };
-  // 32 edge records starting at eb + b0 (one per lane); records past the tile's slice are empty
-  int src_n = 0, slot_n = -1;
-  float nrm_n = 0.f;
-  auto load_records = [&](int eb, int ne, int b0) {
-    const int idx = b0 + lane;
-    src_n = 0; nrm_n = 0.f; slot_n = -1;
-    if (idx < ne) {
-      src_n = p.hub_src[eb + idx];
-      nrm_n = p.hub_nrm[eb + idx];
-      slot_n = p.hub_slot[eb + idx];
-    }
-  };
   auto tile_slice = [&](int pr, int& eb, int& ne) {
     eb = 0; ne = 0;
     if (pr < p_end) {
       const PairEnt* e = p.pairs + pr;
       eb = __ldg(&e->hub_eb[rank]);
-      ne = __ldg(&e->hub_ne[rank]);
+      ne = (p.dbg & 16) ? 0 : __ldg(&e->hub_ne[rank]);
     }
   };
-  int eb, ne, eb_n, ne_n, eb_nn, ne_nn;
-  tile_slice(p_beg, eb, ne);
-  tile_slice(p_beg + 1, eb_n, ne_n);
-  load_records(eb, ne, 0);
+  // record sets: [0] item i (being processed), [1] item i+1, [2] item i+2; `last` = last item of its tile
+  int src[3], slot[3], last[3];
+  float nrm[3];
+  HubCursor f;
+  int eb1, ne1, eb2, ne2;              // slices of the two tiles after the cursor's
+  f.pr = p_beg; f.b0 = 0;
+  tile_slice(p_beg, f.eb, f.ne);
+  tile_slice(p_beg + 1, eb1, ne1);
+  tile_slice(p_beg + 2, eb2, ne2);
+  auto fetch = [&](int q) {            // records of the cursor's item -> set q; advance the cursor
+    src[q] = 0; nrm[q] = 0.f; slot[q] = -1; last[q] = 1;
+    if (f.pr >= p_end) return;
+    const int idx = f.b0 + lane;
+    if (idx < f.ne) {
+      src[q] = p.hub_src[f.eb + idx];
+      nrm[q] = p.hub_nrm[f.eb + idx];
+      slot[q] = p.hub_slot[f.eb + idx];
+    }
+    f.b0 += 32;
+    last[q] = f.b0 >= f.ne;
+    if (last[q]) {
+      ++f.pr; f.b0 = 0;
+      f.eb = eb1; f.ne = ne1; eb1 = eb2; ne1 = ne2;
+      tile_slice(f.pr + 2, eb2, ne2);
+    }
+  };
+  fetch(0);
+  fetch(1);
   int ti = 0;
-  for (int pr = p_beg; pr < p_end; ++pr, ++ti) {
-    tile_slice(pr + 2, eb_nn, ne_nn);
-    if (ti >= HUB_DEPTH)      // bounded run-ahead: keeps what these warps fetch in L2 until the producers use it
+  bool tile_start = true;
+  // bound terms nrm * max|in[src,:]| (warp 0 only), requested one item ahead like the row prefetch
+  float term = 0.f, term_n = 0.f;
+  if (hw == 0 && nrm[0] != 0.f) term = nrm[0] * p.in_rowmax[src[0]];
+  for (int pr = p_beg; pr < p_end;) {
+    fetch(2);
+    // rows of item i+1 -> L2 (each lane: the lines of its record's column slice)
+    if (nrm[1] != 0.f && !(p.dbg & 2)) {
+      const float* q = pf_col + (size_t)src[1] * p.ld_in;
+#pragma unroll
+      for (int o = 0; o < K / N_HUB_WARPS; o += 32)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q + o));
+    }
+    if (tile_start && ti >= HUB_DEPTH)      // bounded run-ahead: keeps what these warps fetch in L2 until the producers use it
       mbar_wait(hub_free0 + 8u * (ti % HUB_DEPTH), (uint32_t)(((ti / HUB_DEPTH) - 1) & 1), 9);
-    int b0 = 0;
-    if (p.dbg & 16) { ne = 0; ne_n = 0; }     // ablation: no hub work at all
-    do {
-      const int src = src_n, slot = slot_n;
-      const float nrm = nrm_n;
-      // next batch's records while this batch's rows are fetched (the next TILE's first batch is requested
-      // after the tile's arrive below: a release-arrive waits for the thread's outstanding loads)
-      if (b0 + 32 < ne) load_records(eb, ne, b0 + 32);
-      float term = 0.f;
-      if (hw == 0 && nrm != 0.f) term = nrm * p.in_rowmax[src];
+    tile_start = false;
+    term_n = 0.f;
+    if (hw == 0 && nrm[1] != 0.f) term_n = nrm[1] * p.in_rowmax[src[1]];
+    {
       float x[8][VEC], w[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        w[j] = __shfl_sync(0xffffffffu, nrm, 4 * j + g);
-        const int sj = __shfl_sync(0xffffffffu, src, 4 * j + g);
+        w[j] = __shfl_sync(0xffffffffu, nrm[0], 4 * j + g);
+        const int sj = __shfl_sync(0xffffffffu, src[0], 4 * j + g);
         if (w[j] != 0.f && !(p.dbg & 2)) VecLd<VEC>::ld(x[j], col + (size_t)sj * p.ld_in);
         else {
 #pragma unroll
@@ -400,21 +424,28 @@ __device__ __forceinline__ void hub_warp_loop(const PairParams& p, int hw, int l
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int sl = __shfl_sync(0xffffffffu, slot, 4 * j);     // hubs start on round boundaries
+        const int sl = __shfl_sync(0xffffffffu, slot[0], 4 * j);     // hubs start on round boundaries
         const float tj = __shfl_sync(0xffffffffu, term, 4 * j + g);
         if (sl != cur_slot) { flush(); cur_slot = sl; }
 #pragma unroll
         for (int k = 0; k < VEC; ++k) acc[k] = fmaf(w[j], x[j][k], acc[k]);
         if (c == 0) bacc += tj;
       }
-      b0 += 32;
-    } while (b0 < ne);
-    flush();
-    cur_slot = -1;
-    __syncwarp();
-    if (lane == 0) mbar_arrive(hub_full0 + 8u * (ti % HUB_DEPTH));   // release: the mlong rows are visible to the producers
-    eb = eb_n; ne = ne_n; eb_n = eb_nn; ne_n = ne_nn;
-    load_records(eb, ne, 0);
+    }
+    if (last[0]) {        // tile complete: publish its hub rows
+      flush();
+      cur_slot = -1;
+      __syncwarp();
+      if (lane == 0) {
+        if (p.dbg & 128) mbar_arrive_cluster_relaxed(hub_full0 + 8u * (ti % HUB_DEPTH), rank);
+        else mbar_arrive(hub_full0 + 8u * (ti % HUB_DEPTH));   // release: the mlong rows are visible to the producers
+      }
+      ++pr; ++ti;
+      tile_start = true;
+    }
+    term = term_n;
+    src[0] = src[1]; nrm[0] = nrm[1]; slot[0] = slot[1]; last[0] = last[1];
+    src[1] = src[2]; nrm[1] = nrm[2]; slot[1] = slot[2]; last[1] = last[2];
   }
 }
 
