@@ -26,7 +26,8 @@ class PackedSet(C.Structure):
                                    "labels", "norm", "class_pos", "class_occ", "n_classes")] + \
                [("n_act", i32 * MAX_LAYERS), ("n_act_tiles", i32 * MAX_LAYERS)] + \
                [(n, vp * MAX_LAYERS) for n in ("act_rows", "act_task_ptr", "act_tile_row0", "act_tile_nrows",
-                                               "act_tile_task", "row_pos")]
+                                               "act_tile_task", "row_pos")] + \
+               [("centre_pos", vp)]
 
 
 class Model(C.Structure):
@@ -41,7 +42,7 @@ class StepArgs(C.Structure):
                 ("ld_feat", i32), ("theta", vp), ("update_step", i32), ("n_support", i32),
                 ("max_classes", i32), ("spt_max_rows_per_task", i32), ("qry_max_rows_per_task", i32),
                 ("update_lr", f32), ("grad_scale", f32), ("compute_meta_grad", i32), ("dense_backward", i32),
-                ("impl", i32),
+                ("impl", i32), ("pruned_forward", i32),
                 ("meta_grad", vp), ("loss_q", vp), ("acc_q", vp), ("loss_s", vp), ("logits_spt0", vp),
                 ("workspace", vp), ("workspace_bytes", i64)]
 

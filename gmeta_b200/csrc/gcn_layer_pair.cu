@@ -805,9 +805,9 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
           if (quarter * 32 + rr < nrows && col_ok) {
             float4 w4 = ld_f4(stg + rr * 32 + ((tu ^ (rr & 7)) << 2));
             w4.x += b4.x; w4.y += b4.y; w4.z += b4.z; w4.w += b4.w;
-            if (p.relu) { w4.x = fmaxf(w4.x, 0.f); w4.y = fmaxf(w4.y, 0.f); w4.z = fmaxf(w4.z, 0.f); w4.w = fmaxf(w4.w, 0.f); }
+            if (p.relu & 1) { w4.x = fmaxf(w4.x, 0.f); w4.y = fmaxf(w4.y, 0.f); w4.z = fmaxf(w4.z, 0.f); w4.w = fmaxf(w4.w, 0.f); }
             if (p.relu_mask) {
-              const float4 m4 = ld_f4(p.relu_mask + (size_t)vr * p.ld_out + c0 + 4 * tu);
+              const float4 m4 = ld_f4(p.relu_mask + (size_t)((p.relu & 2) ? row0 + quarter * 32 + rr : vr) * p.ld_out + c0 + 4 * tu);
               if (!(m4.x > 0.f)) w4.x = 0.f;
               if (!(m4.y > 0.f)) w4.y = 0.f;
               if (!(m4.z > 0.f)) w4.z = 0.f;

@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const 
       const int oi = row0 + (live ? r : 0);                          // output row (compact or dense)
       const int v = p.g.dst_rows ? p.g.dst_rows[oi] : oi;            // real row: norm and mask
       const float nv = p.g.norm[v];
-      const float* mrow = p.relu_mask ? p.relu_mask + (size_t)v * p.ld_out : nullptr;
+      const float* mrow = p.relu_mask ? p.relu_mask + (size_t)((p.relu & 2) ? oi : v) * p.ld_out : nullptr;
       lap(t_epi);
       mbar_wait(acc_full(buf), (uint32_t)((ti >> 1) & 1));
       lap(t_wacc);
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const 
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           float val = fmaf(nv, __uint_as_float(acc[j]), bias_s[c0 + j]);
-          if (p.relu) val = fmaxf(val, 0.f);
+          if (p.relu & 1) val = fmaxf(val, 0.f);
           o[j] = val;
         }
         if (mrow && live) {

@@ -65,6 +65,8 @@ int validate(const gmeta_step_args_t* a) {
   if (a->spt.n_tasks <= 0 || a->spt.n_tasks != a->qry.n_tasks) return GMETA_ERR_BAD_ARG;
   if (a->update_step < 1 || a->n_support < 1 || a->max_classes < 1) return GMETA_ERR_BAD_ARG;
   if (a->compute_meta_grad && a->update_step < 2) return GMETA_ERR_UNSUPPORTED;  // meta.py:161 has no grad path at K=1
+  if (a->pruned_forward && a->dense_backward) return GMETA_ERR_UNSUPPORTED;
+  if (a->pruned_forward && (!a->spt.centre_pos || !a->qry.centre_pos)) return GMETA_ERR_BAD_ARG;
   return GMETA_OK;
 }
 
@@ -82,8 +84,11 @@ void carve(const gmeta_step_args_t* a, void* ws, StepBuffers& b) {
   b.fast[1] = c.take<float>(T * P);
   b.g_spt = c.take<float>(T * P);
   b.g_qry = c.take<float>(T * P);
-  for (int l = 0; l < m.n_layers; ++l) b.act_spt[l] = c.take<float>(Ns * b.ld[l]);
-  for (int l = 0; l < m.n_layers; ++l) b.act_qry[l] = c.take<float>(Nq * b.ld[l]);
+  // pruned forward: activations are compact over the active rows of each layer
+  for (int l = 0; l < m.n_layers; ++l)
+    b.act_spt[l] = c.take<float>((a->pruned_forward ? (int64_t)a->spt.n_act[l] : Ns) * b.ld[l]);
+  for (int l = 0; l < m.n_layers; ++l)
+    b.act_qry[l] = c.take<float>((a->pruned_forward ? (int64_t)a->qry.n_act[l] : Nq) * b.ld[l]);
   int64_t rows_s = Ns, rows_q = Nq;   // rows of the dZ buffers
   if (!a->dense_backward) {
     rows_s = rows_q = 1;
@@ -129,16 +134,24 @@ struct Runner {
 
   void forward(const gmeta_packed_set_t& set, float* const* act, const float* W, int64_t stride, float* logits) {
     const gmeta_model_t& m = a->model;
+    const bool pruned = a->pruned_forward != 0;
     for (int l = 0; l < m.n_layers && ok(); ++l) {
       const float* in = l == 0 ? a->feat_table : act[l - 1];
       const int ld_in = l == 0 ? a->ld_feat : b.ld[l - 1];
-      run(gmeta_gcn_layer_fwd(in, ld_in, l == 0 ? set.feat_row : nullptr, nullptr, set.indptr, set.indices, set.norm,
-                              set.tile_row0, set.tile_nrows, set.tile_task, set.n_tiles, set.n_tasks,
+      // pruned: layer l over its active rows only (compact output); its inputs are the compact
+      // activations of layer l-1, addressed through row_pos[l-1] (every in-neighbour of an active
+      // row of layer l is an active row of layer l-1 by construction)
+      const int32_t* map = l == 0 ? set.feat_row : (pruned ? set.row_pos[l - 1] : nullptr);
+      run(gmeta_gcn_layer_fwd(in, ld_in, map, pruned ? set.act_rows[l] : nullptr, set.indptr, set.indices, set.norm,
+                              pruned ? set.act_tile_row0[l] : set.tile_row0,
+                              pruned ? set.act_tile_nrows[l] : set.tile_nrows,
+                              pruned ? set.act_tile_task[l] : set.tile_task,
+                              pruned ? set.n_act_tiles[l] : set.n_tiles, set.n_tasks,
                               W + m.w_off[l], stride, m.f_out[l], 0, W + m.b_off[l], stride, m.f_in[l],
                               m.f_out[l], 1, nullptr, act[l], b.ld[l], a->impl, b.layer_ws, b.layer_ws_bytes, s));
     }
     const int L = m.n_layers;
-    run(gmeta_readout_linear_fwd(act[L - 1], b.ld[L - 1], m.f_out[L - 1], set.centre_row,
+    run(gmeta_readout_linear_fwd(act[L - 1], b.ld[L - 1], m.f_out[L - 1], pruned ? set.centre_pos : set.centre_row,
                                  set.centres_per_subgraph, set.task_sub_ptr, set.n_tasks, set.n_subgraphs,
                                  W + m.wlin_off, stride, W + m.blin_off, stride, m.n_out, logits, s));
   }
@@ -149,17 +162,21 @@ struct Runner {
     const int L = m.n_layers;
     const int64_t P = m.n_params_padded;
     const bool sparse = !a->dense_backward;
+    const bool pruned = a->pruned_forward != 0;
     int cur = 0;
     // dZ of the last GCN layer: zero except at the centre rows (dense [N, ld] like the reference's
     // autograd, or compact over the active rows)
+    // pruned: H is compact in the order of act_rows[L-1], and so is dZ -> centre positions index both
     run(gmeta_readout_linear_bwd(act[L - 1], b.ld[L - 1], m.f_out[L - 1], sparse ? set.n_act[L - 1] : set.n_nodes,
-                                 sparse ? set.row_pos[L - 1] : nullptr, set.centre_row, set.centres_per_subgraph,
+                                 pruned ? nullptr : (sparse ? set.row_pos[L - 1] : nullptr),
+                                 pruned ? set.centre_pos : set.centre_row, set.centres_per_subgraph,
                                  set.task_sub_ptr, set.n_tasks, set.n_subgraphs, W + m.wlin_off, stride, m.n_out,
                                  dlogits, gout + m.wlin_off, P, gout + m.blin_off, P, dz[cur], s));
     for (int l = L - 1; l >= 0 && ok(); --l) {
       const float* in = l == 0 ? a->feat_table : act[l - 1];
       const int ld_in = l == 0 ? a->ld_feat : b.ld[l - 1];
-      run(gmeta_gcn_layer_wgrad(in, ld_in, l == 0 ? set.feat_row : nullptr, sparse ? set.act_rows[l] : nullptr,
+      run(gmeta_gcn_layer_wgrad(in, ld_in, l == 0 ? set.feat_row : (pruned ? set.row_pos[l - 1] : nullptr),
+                                sparse ? set.act_rows[l] : nullptr,
                                 set.indptr, set.indices, set.norm, sparse ? set.act_task_ptr[l] : set.task_row_ptr,
                                 set.n_tasks, dz[cur], b.ld[l], m.f_in[l], m.f_out[l], gout + m.w_off[l], P,
                                 gout + m.b_off[l], P, b.wgrad_ws, b.wgrad_ws_bytes, s));
@@ -174,7 +191,7 @@ struct Runner {
                                 sparse ? set.act_tile_nrows[l - 1] : set.tile_nrows,
                                 sparse ? set.act_tile_task[l - 1] : set.tile_task,
                                 sparse ? set.n_act_tiles[l - 1] : set.n_tiles, set.n_tasks, W + m.w_off[l], stride,
-                                m.f_out[l], 1, nullptr, 0, m.f_out[l], m.f_in[l], 0, act[l - 1], dz[cur ^ 1],
+                                m.f_out[l], 1, nullptr, 0, m.f_out[l], m.f_in[l], pruned ? 2 : 0, act[l - 1], dz[cur ^ 1],
                                 b.ld[l - 1], a->impl, b.layer_ws, b.layer_ws_bytes, s));
         cur ^= 1;
       }
@@ -240,7 +257,7 @@ extern "C" int gmeta_maml_step(const gmeta_step_args_t* a, void* stream) {
   if (!a->dense_backward) {   // row -> position maps of the active-row lists (structure only: once per step)
     for (int l = 0; l < m.n_layers; ++l) {
       r.run(gmeta_build_row_pos(sp.act_rows[l], sp.n_act[l], sp.n_nodes, sp.row_pos[l], s));
-      if (a->compute_meta_grad)
+      if (a->compute_meta_grad || a->pruned_forward)
         r.run(gmeta_build_row_pos(qr.act_rows[l], qr.n_act[l], qr.n_nodes, qr.row_pos[l], s));
     }
   }

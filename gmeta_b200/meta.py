@@ -205,6 +205,9 @@ class Meta(nn.Module):
         # False (default): the backward skips rows whose gradient is structurally zero (only centre
         # rows are read out); True: back-propagate over every row like the reference's autograd.
         self.dense_backward = bool(getattr(args, 'dense_backward', False))
+        # True (default): every forward computes only the rows the read-out depends on (exact: only centre
+        # rows are read out, learner.py:166-170); False: every row of every layer, like the reference.
+        self.pruned_forward = bool(getattr(args, 'pruned_forward', not self.dense_backward))
 
         self.net = Classifier(config, impl=self.impl)
         self.net = self.net.to(device)
@@ -321,6 +324,7 @@ class Meta(nn.Module):
         a.grad_scale = 1.0 / (self._global_task_num(T) if train else 1)
         a.compute_meta_grad = 1 if train else 0
         a.dense_backward = 1 if self.dense_backward else 0
+        a.pruned_forward = 1 if (self.pruned_forward and not self.dense_backward) else 0
         a.impl = self.impl
         P = self.spec.n_params_padded
         meta_grad = self._buf("meta_grad", (P,), torch.float32, dev) if train else None

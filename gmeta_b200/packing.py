@@ -11,7 +11,7 @@ import torch
 from .learner import tile_table
 
 _SEGS = ("indptr", "indices", "t_indptr", "t_indices", "tile_row0", "tile_nrows", "tile_task",
-         "task_row_ptr", "task_sub_ptr", "centre_row", "feat_row", "labels")
+         "task_row_ptr", "task_sub_ptr", "centre_row", "feat_row", "labels", "centre_pos")
 
 
 def _al(n):
@@ -80,7 +80,7 @@ def plan_set(graphs, centres, off0, n_layers=0):
     sizes = {"indptr": ps.N + 1, "indices": ps.E, "t_indptr": ps.N + 1, "t_indices": ps.E,
              "tile_row0": ps.n_tiles, "tile_nrows": ps.n_tiles, "tile_task": ps.n_tiles,
              "task_row_ptr": ps.T + 1, "task_sub_ptr": ps.T + 1, "centre_row": ps.S * ps.cps,
-             "feat_row": ps.N, "labels": ps.S}
+             "feat_row": ps.N, "labels": ps.S, "centre_pos": ps.S * ps.cps}
     # active rows of the backward pass (per layer), their task pointers and tile tables
     ps.n_layers = n_layers
     ps.act = []
@@ -149,6 +149,8 @@ def fill_set(buf, ps, graphs, labels, centres, node_ids, graph_idx, graph_row_of
     buf[o["tile_task"]:o["tile_task"] + ps.n_tiles] = ps.tiles[2]
     buf[o["task_row_ptr"]:o["task_row_ptr"] + ps.T + 1] = ps.node_off
     buf[o["task_sub_ptr"]:o["task_sub_ptr"] + ps.T + 1] = ps.sub_off
+    if ps.n_layers:     # position of every centre row in the (globally sorted) active-row list of the last layer
+        buf[o["centre_pos"]:o["centre_pos"] + ps.S * ps.cps] = np.searchsorted(ps.act[ps.n_layers - 1]["rows"], centre)
     for l in range(ps.n_layers):
         a = ps.act[l]
         buf[o["act_rows%d" % l]:o["act_rows%d" % l] + a["n"]] = a["rows"]

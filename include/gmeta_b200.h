@@ -87,6 +87,7 @@ typedef struct gmeta_packed_set {
   const int32_t* act_tile_nrows[GMETA_MAX_LAYERS];
   const int32_t* act_tile_task[GMETA_MAX_LAYERS];
   int32_t* row_pos[GMETA_MAX_LAYERS];              /* [N] scratch: row -> position in act_rows or -1 */
+  const int32_t* centre_pos;     /* [S * centres_per_subgraph] position of each centre row in act_rows[L-1] */
 } gmeta_packed_set_t;
 
 /* Model topology = the reference's `config` list (train.py:67-75, learner.py:81-97) flattened.
@@ -120,8 +121,9 @@ int gmeta_degree_norm(const int32_t* indptr, int32_t n_nodes, float* norm, void*
  * in_row_map entry drops that neighbour;
  * with B[k,j] = W[k*ldw + j] (trans_w == 0) or W[j*ldw + k] (trans_w != 0), W/bias taken from
  * task t = tile_task[tile] at W + t*w_task_stride / bias + t*b_task_stride (stride 0 = shared),
- * act = ReLU iff relu != 0; if relu_mask != NULL the result is zeroed where relu_mask[v,j] <= 0
- * (ld_out layout, indexed by the real row v).  Columns [f_out, round_up(f_out,4)) of out are written as 0.
+ * act = ReLU iff (relu & 1); if relu_mask != NULL the result is zeroed where relu_mask[m,j] <= 0
+ * (ld_out layout), m = the real row v, or the output row i when (relu & 2) (a compact mask stored in
+ * the order of dst_rows).  Columns [f_out, round_up(f_out,4)) of out are written as 0.
  * The same entry point run on (t_indptr, t_indices) with trans_w=1, bias=NULL, relu=0 and
  * relu_mask = the lower layer's activations is the layer's data-gradient.
  * impl: GMETA_IMPL_SIMT (fp32 FFMA, any shape), GMETA_IMPL_TCGEN05 (tcgen05.mma 3xTF32 with TMEM
@@ -312,6 +314,10 @@ typedef struct gmeta_step_args {
   int32_t dense_backward;        /* 1: back-propagate over every row like the reference's autograd;
                                     0: skip the structurally-zero rows (packed set's act_* lists) */
   int32_t impl;                  /* GMETA_IMPL_* for the GCN layers */
+  int32_t pruned_forward;        /* 1: every forward computes only the rows the read-out depends on (the same
+                                    active-row lists: layer l over act_rows[l], compact activations) -- exact,
+                                    because only centre rows are read out (learner.py:166-170); needs
+                                    dense_backward == 0.  0: every row of every layer, like the reference. */
   /* outputs */
   float* meta_grad;              /* [P] sum over this call's tasks of d(grad_scale*loss_q^K)/d(theta) */
   float* loss_q;                 /* [T, K+1] query loss per task per step */

@@ -134,6 +134,31 @@ def test_meta_forward_matches_oracle_midsize():
         U.report("meta-grad[%d]" % k, g, r, 2e-5 + 1e-4 * float(r.abs().max()), 1e-3)
 
 
+def test_pruned_forward_equals_full_forward():
+    """Exact shortcut: computing only the rows the read-out depends on (layer l over its
+    active rows, compact activations) gives the same accuracies, losses and meta-gradient as computing
+    every row of every layer like the reference -- per-row arithmetic is identical, so the results
+    agree to fp32 summation-order noise of the weight-gradient reductions."""
+    from gmeta_b200.meta import Meta
+    from gmeta_b200.synthetic import make_dataset
+    for name, scale, tasks in (('C1', 0.3, 4), ('C4', 1.0, 3)):
+        ds = make_dataset(name, scale=scale)
+        mb = ds.sample_meta_batch(np.random.default_rng(5), tasks)
+        outs = []
+        for pruned in (False, True):
+            args = ds.args()
+            args.pruned_forward = pruned
+            torch.manual_seed(222)
+            m = Meta(args, ds.config()).to(U.dev())
+            m.return_meta_grad = True
+            accs = m(*mb, ds.feats)
+            outs.append((accs, m.last["loss_q"], [g.clone() for g in m.last["meta_grad"]], m.last["gpu_launches"]))
+        np.testing.assert_allclose(outs[0][0], outs[1][0], atol=1e-6, err_msg=name)
+        assert abs(outs[0][1] - outs[1][1]) < 1e-6, name
+        for k, (a, b) in enumerate(zip(outs[0][2], outs[1][2])):
+            U.report("%s grad[%d] full vs pruned" % (name, k), b, a, 1e-7 + 1e-5 * float(a.abs().max()), 1e-4)
+
+
 def test_task_batching_equals_task_by_task():
     """Size-independent property: packing T tasks into one launch == running them one at a time
     (tasks only interact through the final sum, meta.py:155,161)."""

@@ -31,12 +31,22 @@ def test_c_abi_library_exports_every_declared_symbol():
     assert _lib.lib().gmeta_error_string(-3).decode().startswith("shape")
 
 
-def test_ctypes_structs_match_header_layout():
-    """sizeof of the mirrored structs (pointer/int layout) -- a drifted field would shift these."""
-    assert ctypes.sizeof(_lib.PackedSet) == 6 * 4 + 16 * 8 + 2 * 3 * 4 + 6 * 3 * 8
-    assert ctypes.sizeof(_lib.Model) == 4 * (1 + 3 + 3 + 3 + 3 + 3 + 2)
-    a = _lib.StepArgs()
-    assert ctypes.sizeof(a) % 8 == 0 and _lib.StepArgs.workspace_bytes.offset + 8 == ctypes.sizeof(a)
+def test_ctypes_structs_match_header_layout(tmp_path):
+    """sizeof / offsetof of the ctypes mirrors against the header, measured with a gcc-compiled probe."""
+    import subprocess
+    probe = tmp_path / "probe.c"
+    probe.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "gmeta_b200.h"\n'
+        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(gmeta_packed_set_t), sizeof(gmeta_model_t),'
+        ' sizeof(gmeta_step_args_t), offsetof(gmeta_packed_set_t, centre_pos), offsetof(gmeta_step_args_t, pruned_forward),'
+        ' offsetof(gmeta_step_args_t, meta_grad), offsetof(gmeta_step_args_t, workspace_bytes));return 0;}\n')
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(probe), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [ctypes.sizeof(_lib.PackedSet), ctypes.sizeof(_lib.Model), ctypes.sizeof(_lib.StepArgs),
+            _lib.PackedSet.centre_pos.offset, _lib.StepArgs.pruned_forward.offset, _lib.StepArgs.meta_grad.offset,
+            _lib.StepArgs.workspace_bytes.offset]
+    assert got == want, (got, want)
 
 
 def test_parameter_counts_match_reference_logs():
