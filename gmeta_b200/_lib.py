@@ -74,6 +74,9 @@ _SIGNATURES = {
     "gmeta_sgd_update": (C.c_int, [vp, i64, vp, f32, i32, i32, vp, vp]),
     "gmeta_sum_over_tasks": (C.c_int, [vp, vp, i32, i32, vp, vp]),
     "gmeta_adam_update": (C.c_int, [vp, vp, vp, vp, i32, f64, f64, f64, f64, i32, f32, vp, vp, vp]),
+    "gmeta_khop_workspace_bytes": (i64, [i32, i32, i32]),
+    "gmeta_khop_select": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, C.c_uint64, vp, vp, vp, vp, i64, vp]),
+    "gmeta_khop_build": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
     "gmeta_maml_step_workspace_bytes": (i64, [C.POINTER(StepArgs)]),
     "gmeta_maml_step": (C.c_int, [C.POINTER(StepArgs), vp]),
     "gmeta_last_launch_count": (C.c_int, []),

@@ -106,3 +106,78 @@ def extract_subgraph_link_pred(G, i, j, sample_nodes, rng=np.random):
     indptr, indices = G.induced(nodes)
     centre = [int(np.searchsorted(nodes, i)), int(np.searchsorted(nodes, j))]
     return SubgraphCSR(indptr, indices, nodes, centre)
+
+
+class DeviceExtractor(object):
+    """Device-side extraction of a whole batch of local subgraphs (gmeta_khop_select / gmeta_khop_build,
+    csrc/khop.cu): the parent graphs live in HBM as ONE int32 CSR over their concatenated node ranges, a
+    request is a centre (or a centre pair) in one of the graphs, and the result is the packed CSR of all
+    requested subgraphs with batch offsets applied -- the layout the layer kernels consume -- without the
+    subgraphs ever existing on the host.  Mirrors Subgraphs.generate_subgraph[_link_pred]
+    (subgraph_data_processing.py:295-346); there is no CPU fallback."""
+
+    def __init__(self, graphs, device=None):
+        import torch
+        from . import _lib
+        self._lib = _lib
+        self.L = _lib.lib()
+        self.dev = device if device is not None else torch.device('cuda', torch.cuda.current_device())
+        ns = np.array([g.n for g in graphs], dtype=np.int64)
+        self.node_off = np.concatenate([[0], np.cumsum(ns)])
+        edge_off = np.concatenate([[0], np.cumsum([g.indices.shape[0] for g in graphs])])
+        if self.node_off[-1] >= 2 ** 31 or edge_off[-1] >= 2 ** 31:
+            raise _lib.GMetaError("parent graphs exceed the int32 index range")
+        indptr = np.zeros(int(self.node_off[-1]) + 1, dtype=np.int32)
+        indices = np.zeros(int(edge_off[-1]), dtype=np.int32)
+        for k, g in enumerate(graphs):
+            a, b = int(self.node_off[k]), int(self.node_off[k + 1])
+            indptr[a + 1:b + 1] = g.indptr[1:] + edge_off[k]
+            indices[int(edge_off[k]):int(edge_off[k + 1])] = g.indices.astype(np.int64) + a
+        self.max_graph_nodes = int(ns.max())
+        self.indptr = torch.from_numpy(indptr).to(self.dev)
+        self.indices = torch.from_numpy(indices).to(self.dev)
+        self._ws = None
+
+    def extract(self, graph_idx, centre_a, centre_b=None, h=2, sample_nodes=1000, seed=222):
+        """graph_idx / centre_a / centre_b: int arrays of length R (node ids inside their graph).
+        Node classification: `h` hops from centre_a.  Link prediction (centre_b given): 2 hops from a, 1 from b
+        (the reference ignores h there, :327-333).  Returns a dict of device tensors (packed layout) and
+        the per-request pointers."""
+        import torch
+        L = self.L
+        i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(self.dev)  # noqa: E731
+        gi = np.asarray(graph_idx, dtype=np.int64)
+        R = int(gi.shape[0])
+        lo = self.node_off[gi]
+        hi = self.node_off[gi + 1]
+        a = i32(np.asarray(centre_a, dtype=np.int64) + lo)
+        b = i32(np.asarray(centre_b, dtype=np.int64) + lo) if centre_b is not None else None
+        d_lo, d_hi = i32(lo), i32(hi)
+        hops_a, hops_b = (2, 1) if centre_b is not None else (int(h), 0)
+        if centre_b is None and h not in (1, 2, 3):
+            raise NameError("h_hops_neighbor")      # like the reference for other h (:300-311)
+        nb = L.gmeta_khop_workspace_bytes(R, sample_nodes, self.max_graph_nodes)
+        if self._ws is None or self._ws.numel() < nb + 256:
+            self._ws = torch.empty(int(nb) + 256, dtype=torch.uint8, device=self.dev)
+        ws_ptr = (self._ws.data_ptr() + 255) // 256 * 256
+        node_ptr = torch.empty(R + 1, dtype=torch.int32, device=self.dev)
+        edge_ptr = torch.empty(R + 1, dtype=torch.int32, device=self.dev)
+        closure = torch.empty(max(R, 1), dtype=torch.int32, device=self.dev)
+        st = torch.cuda.current_stream().cuda_stream
+        ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        self._lib.check(L.gmeta_khop_select(ptr(self.indptr), ptr(self.indices), ptr(a), ptr(b), ptr(d_lo), ptr(d_hi), R,
+                                            hops_a, hops_b, sample_nodes, self.max_graph_nodes, seed, ptr(node_ptr),
+                                            ptr(edge_ptr), ptr(closure), ws_ptr, nb, st), "khop_select")
+        totals = torch.stack((node_ptr[R], edge_ptr[R])).cpu()       # the batch's only D2H: 8 bytes
+        N, E = int(totals[0]), int(totals[1])
+        out = {"node_ptr": node_ptr, "edge_ptr": edge_ptr, "closure_size": closure, "N": N, "E": E,
+               "indptr": torch.empty(N + 1, dtype=torch.int32, device=self.dev),
+               "indices": torch.empty(max(E, 1), dtype=torch.int32, device=self.dev),
+               "parent": torch.empty(max(N, 1), dtype=torch.int32, device=self.dev),
+               "feat_row": torch.empty(max(N, 1), dtype=torch.int32, device=self.dev),
+               "centre_row": torch.empty(max(R, 1) * (2 if b is not None else 1), dtype=torch.int32, device=self.dev)}
+        self._lib.check(L.gmeta_khop_build(ptr(self.indptr), ptr(self.indices), ptr(a), ptr(b), ptr(d_lo), R, sample_nodes,
+                                           self.max_graph_nodes, ptr(node_ptr), ptr(edge_ptr), ptr(out["indptr"]),
+                                           ptr(out["indices"]), ptr(out["parent"]), ptr(out["feat_row"]),
+                                           ptr(out["centre_row"]), ws_ptr, nb, st), "khop_build")
+        return out

@@ -333,6 +333,37 @@ int gmeta_maml_step(const gmeta_step_args_t* args, void* stream);
 /* number of kernel launches the last gmeta_maml_step call on this thread enqueued */
 int gmeta_last_launch_count(void);
 
+/* ---------------------------------------------------------------------------------------
+ * Device-side h-hop local-subgraph extraction for a whole meta-batch of requests (replaces
+ * Subgraphs.generate_subgraph / generate_subgraph_link_pred, subgraph_data_processing.py:295-346),
+ * emitting the packed-set CSR directly.  The parent graphs are ONE int32 CSR by destination over
+ * their concatenated node ranges; request r = (req_a[r], optional req_b[r], node range
+ * [req_lo[r], req_hi[r]) of its graph), all global ids.
+ *   closure  = <= hops_a in-hops from a, plus b and (hops_b == 1) b's in-neighbours -- the reference
+ *              takes 2 hops from the first endpoint and, through :332, ONE from the second;
+ *   sampling = if |closure| > sample_nodes: the sample_nodes nodes with the smallest values of a
+ *              counter-based hash of (seed, r, node) -- a uniform sample without replacement --
+ *              then the centre(s) re-added (:312-314, :337-339);
+ *   output   = nodes in ascending id order (np.unique), node-induced edges in parent-CSR order with
+ *              multiplicity, local ids = rank: identical to the host extractor whenever the closure
+ *              fits (integer work, bit-exact).
+ * Two calls: gmeta_khop_select writes node_ptr / edge_ptr [n_req + 1] (exclusive sums; the last
+ * entries are the packed totals the caller reads to size the outputs), gmeta_khop_build fills
+ *   out_indptr [N+1], out_indices [E] (packed row ids), out_parent [N] (id inside the graph),
+ *   out_global [N] or NULL (global id = feature-table row), out_centre [n_req * (req_b ? 2 : 1)].
+ * Same 256-byte aligned workspace for both (gmeta_khop_workspace_bytes); sample_nodes <= 2046. */
+int64_t gmeta_khop_workspace_bytes(int32_t n_req, int32_t sample_nodes, int32_t max_graph_nodes);
+int gmeta_khop_select(const int32_t* indptr, const int32_t* indices, const int32_t* req_a,
+                      const int32_t* req_b, const int32_t* req_lo, const int32_t* req_hi, int32_t n_req,
+                      int32_t hops_a, int32_t hops_b, int32_t sample_nodes, int32_t max_graph_nodes,
+                      uint64_t seed, int32_t* node_ptr, int32_t* edge_ptr, int32_t* closure_size,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+int gmeta_khop_build(const int32_t* indptr, const int32_t* indices, const int32_t* req_a,
+                     const int32_t* req_b, const int32_t* req_lo, int32_t n_req, int32_t sample_nodes,
+                     int32_t max_graph_nodes, const int32_t* node_ptr, const int32_t* edge_ptr,
+                     int32_t* out_indptr, int32_t* out_indices, int32_t* out_parent, int32_t* out_global,
+                     int32_t* out_centre, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
