@@ -55,16 +55,16 @@ constexpr int A_HALF_BYTES = TM * 64;          // 8 KB: hi (or lo) operand tile 
 constexpr int STAGE_BYTES = 2 * A_HALF_BYTES;  // 16 KB
 // warp roles (register budgets are re-balanced per warpgroup with setmaxnreg)
 constexpr int N_PROD_WARPS = 8;                // warps 0..7   gather producers
-constexpr int WARP_HUB0 = 8;                   // warps 8..11  hub-row aggregation
-constexpr int N_HUB_WARPS = 4;
+constexpr int WARP_EPI_B0 = 8;                 // warps 8..11  epilogue, upper half of the output columns
 constexpr int WARP_LOAD = 12;                  // warp 12      weight loader (+ TMEM allocation)
 constexpr int WARP_MMA = 13;                   // warp 13      MMA issuer (14, 15 idle)
-constexpr int WARP_EPI0 = 16;                  // warps 16..19 epilogue
+constexpr int WARP_EPI0 = 16;                  // warps 16..19 epilogue, lower half of the output columns
+constexpr int N_EPI_WARPS = 8;
 constexpr int NTHREADS = 20 * 32;
 constexpr int REGS_ENTRY = 96;                 // registers per thread at launch: 64K / 640 threads, rounded down to 8
-constexpr int REGS_PROD = 120, REGS_HUB = 120, REGS_CTRL = 24, REGS_EPI = 96;
+constexpr int REGS_PROD = 120, REGS_CTRL = 24, REGS_EPI = 96;
 // setmaxnreg re-distributes the registers the CTA got at launch (640 threads x 96 = 61440)
-static_assert(8 * 32 * REGS_PROD + 4 * 32 * REGS_HUB + 4 * 32 * REGS_CTRL + 4 * 32 * REGS_EPI <= NTHREADS * REGS_ENTRY,
+static_assert(8 * 32 * REGS_PROD + 4 * 32 * REGS_CTRL + 8 * 32 * REGS_EPI <= NTHREADS * REGS_ENTRY,
               "register budget");
 #ifndef GMETA_PAIR_PROF
 #define GMETA_PAIR_PROF 0      // 1: per-role cycle counters (costs registers; debug builds only)
@@ -73,10 +73,11 @@ constexpr int MAX_STAGES = 6;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_COLS = 256;
 constexpr int PRE = 2;                         // in-neighbours per row the fused kernel gathers itself
-constexpr int EPI_STAGE_BYTES = 4 * 32 * 32 * 4;   // one 32x32 fp32 transpose tile per epilogue warp (XOR-swizzled)
-constexpr int SMEM_FIXED = 256 /*barriers*/ + 4 * TM /*row scale exponents*/ + ACC_COLS * 4 /*bias*/ + EPI_STAGE_BYTES;
+constexpr int EPI_STAGE_BYTES = N_EPI_WARPS * 32 * 16 * 4;   // one 32x16 fp32 transpose tile per epilogue warp (XOR-swizzled)
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_FIXED = BAR_BYTES /*barriers*/ + 4 * TM /*row scale exponents*/ + ACC_COLS * 4 /*bias*/ + 2 * TM * 4 /*row max exchange*/ + EPI_STAGE_BYTES;
 constexpr int SMEM_MAX = 227 * 1024;
-constexpr int HUB_DEPTH = 4;                   // tiles the hub warps may run ahead of the producers
+constexpr int HUB_BIG = 128;                    // hubs with more (padded) edge records are aggregated by a whole CTA
 constexpr int PT_MAXT = 2048;                  // tasks the pair-table kernel handles
 constexpr int SCALE_TARGET = 13;               // scaled bound in [2^13, 2^14): 4x below the FP16 maximum
 constexpr int SCALE_CLAMP = 100;
@@ -93,13 +94,14 @@ struct PairEnt {      // 64 bytes; nrows[1] = 0 when the task has an odd tile co
   int pad2[4];
 };
 struct Plan {
-  int* hdr;           // [0] n_hubs  [1] n_hub_edges  [2] n_pairs
+  int* hdr;           // [0] n_hubs  [1] n_hub_edges  [2] n_pairs  [3] n_big_hubs
   PlanRec* rec;       // [n_rows]
   PairEnt* pairs;     // [cap_pairs] two tiles of the same task each
   int2* tile_hubs;    // [n_tiles] (first record, record count) of the tile's slice of the hub edge list
   int* hub_row;       // [cap_hub] real row of each hub slot
   int* hub_beg;       // [cap_hub] first record of the slot
   int* hub_deg;       // [cap_hub]
+  int* big_list;      // [cap_big] slots of the hubs with more than HUB_BIG records (aggregated by a whole CTA)
   // hub edge list, grouped by tile then hub, every hub padded to a multiple of 4 records (pads: norm 0)
   int* hub_src;       // [cap_edges] mapped source row
   float* hub_nrm;     // [cap_edges]
@@ -140,6 +142,7 @@ Plan carve_plan(void* base, int n_tiles, int n_tasks, int n_rows, int n_edges) {
   pl.hub_row = reinterpret_cast<int*>(c.take((int64_t)ch * 4));
   pl.hub_beg = reinterpret_cast<int*>(c.take((int64_t)ch * 4));
   pl.hub_deg = reinterpret_cast<int*>(c.take((int64_t)ch * 4));
+  pl.big_list = reinterpret_cast<int*>(c.take(((int64_t)n_edges / HUB_BIG + 2) * 4));
   const int64_t ce = (int64_t)n_edges + 3LL * ch + 64;
   pl.hub_src = reinterpret_cast<int*>(c.take(ce * 4));
   pl.hub_nrm = reinterpret_cast<float*>(c.take(ce * 4));
@@ -180,11 +183,6 @@ struct PairParams {
   const PlanRec* rec;
   const int* hdr;
   const PairEnt* pairs;
-  const int* hub_src;            // padded hub edge records (see Plan)
-  const float* hub_nrm;
-  const int* hub_slot;
-  float* mlong_w;                // == mlong (written by the hub warps, read by the producers of the same CTA)
-  float* mlong_bound_w;
   const int32_t* dst_rows;
   const float* norm;
   const __half* w_image;
@@ -318,137 +316,6 @@ template <> struct VecLd<2> {
   }
 };
 
-// One hub warp (see the call site).  K = 32 * VEC; lane = 8 * g + c: edge group g (edges 4j + g of a
-// round-of-4 sequence), column unit c (VEC floats at hw*K/4 + c*VEC).
-// The warp walks a flat sequence of items = 32-record batches of its CTA's tiles (one empty item for a
-// tile without hub rows), three deep: the records of item i+2 are being loaded, the rows of item i+1
-// are being pulled into L2 (prefetch.global.L2: needs no registers), item i is gathered and summed.
-struct HubCursor {        // position of the next item to fetch
-  int pr, b0, eb, ne;
-};
-template <int VEC>
-__device__ __forceinline__ void hub_warp_loop(const PairParams& p, int hw, int lane, uint32_t rank, int p_beg,
-                                              int p_end, uint32_t hub_full0, uint32_t hub_free0) {
-  const int K = 32 * VEC;
-  const int g = lane >> 3, c = lane & 7;
-  const float* col = p.in + hw * (K / N_HUB_WARPS) + c * VEC;
-  const float* pf_col = p.in + hw * (K / N_HUB_WARPS);
-  float acc[VEC], bacc = 0.f;
-#pragma unroll
-  for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
-  int cur_slot = -1;
-  auto flush = [&]() {
-    if (cur_slot >= 0) {
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) {
-        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 8);
-        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
-      }
-      if (g == 0) VecLd<VEC>::st(p.mlong_w + (size_t)cur_slot * K + hw * (K / N_HUB_WARPS) + c * VEC, acc);
-      if (hw == 0) {
-        bacc += __shfl_xor_sync(0xffffffffu, bacc, 8);
-        bacc += __shfl_xor_sync(0xffffffffu, bacc, 16);
-        if (lane == 0) p.mlong_bound_w[cur_slot] = bacc;
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
-    bacc = 0.f;
-  };
-  auto tile_slice = [&](int pr, int& eb, int& ne) {
-    eb = 0; ne = 0;
-    if (pr < p_end) {
-      const PairEnt* e = p.pairs + pr;
-      eb = __ldg(&e->hub_eb[rank]);
-      ne = (p.dbg & 16) ? 0 : __ldg(&e->hub_ne[rank]);
-    }
-  };
-  // record sets: [0] item i (being processed), [1] item i+1, [2] item i+2; `last` = last item of its tile
-  int src[3], slot[3], last[3];
-  float nrm[3];
-  HubCursor f;
-  int eb1, ne1, eb2, ne2;              // slices of the two tiles after the cursor's
-  f.pr = p_beg; f.b0 = 0;
-  tile_slice(p_beg, f.eb, f.ne);
-  tile_slice(p_beg + 1, eb1, ne1);
-  tile_slice(p_beg + 2, eb2, ne2);
-  auto fetch = [&](int q) {            // records of the cursor's item -> set q; advance the cursor
-    src[q] = 0; nrm[q] = 0.f; slot[q] = -1; last[q] = 1;
-    if (f.pr >= p_end) return;
-    const int idx = f.b0 + lane;
-    if (idx < f.ne) {
-      src[q] = p.hub_src[f.eb + idx];
-      nrm[q] = p.hub_nrm[f.eb + idx];
-      slot[q] = p.hub_slot[f.eb + idx];
-    }
-    f.b0 += 32;
-    last[q] = f.b0 >= f.ne;
-    if (last[q]) {
-      ++f.pr; f.b0 = 0;
-      f.eb = eb1; f.ne = ne1; eb1 = eb2; ne1 = ne2;
-      tile_slice(f.pr + 2, eb2, ne2);
-    }
-  };
-  fetch(0);
-  fetch(1);
-  int ti = 0;
-  bool tile_start = true;
-  // bound terms nrm * max|in[src,:]| (warp 0 only), requested one item ahead like the row prefetch
-  float term = 0.f, term_n = 0.f;
-  if (hw == 0 && nrm[0] != 0.f) term = nrm[0] * p.in_rowmax[src[0]];
-  for (int pr = p_beg; pr < p_end;) {
-    fetch(2);
-    // rows of item i+1 -> L2 (each lane: the lines of its record's column slice)
-    if (nrm[1] != 0.f && !(p.dbg & 2)) {
-      const float* q = pf_col + (size_t)src[1] * p.ld_in;
-#pragma unroll
-      for (int o = 0; o < K / N_HUB_WARPS; o += 32)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(q + o));
-    }
-    if (tile_start && ti >= HUB_DEPTH)      // bounded run-ahead: keeps what these warps fetch in L2 until the producers use it
-      mbar_wait(hub_free0 + 8u * (ti % HUB_DEPTH), (uint32_t)(((ti / HUB_DEPTH) - 1) & 1), 9);
-    tile_start = false;
-    term_n = 0.f;
-    if (hw == 0 && nrm[1] != 0.f) term_n = nrm[1] * p.in_rowmax[src[1]];
-    {
-      float x[8][VEC], w[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        w[j] = __shfl_sync(0xffffffffu, nrm[0], 4 * j + g);
-        const int sj = __shfl_sync(0xffffffffu, src[0], 4 * j + g);
-        if (w[j] != 0.f && !(p.dbg & 2)) VecLd<VEC>::ld(x[j], col + (size_t)sj * p.ld_in);
-        else {
-#pragma unroll
-          for (int k = 0; k < VEC; ++k) x[j][k] = 0.f;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int sl = __shfl_sync(0xffffffffu, slot[0], 4 * j);     // hubs start on round boundaries
-        const float tj = __shfl_sync(0xffffffffu, term, 4 * j + g);
-        if (sl != cur_slot) { flush(); cur_slot = sl; }
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) acc[k] = fmaf(w[j], x[j][k], acc[k]);
-        if (c == 0) bacc += tj;
-      }
-    }
-    if (last[0]) {        // tile complete: publish its hub rows
-      flush();
-      cur_slot = -1;
-      __syncwarp();
-      if (lane == 0) {
-        if (p.dbg & 128) mbar_arrive_cluster_relaxed(hub_full0 + 8u * (ti % HUB_DEPTH), rank);
-        else mbar_arrive(hub_full0 + 8u * (ti % HUB_DEPTH));   // release: the mlong rows are visible to the producers
-      }
-      ++pr; ++ti;
-      tile_start = true;
-    }
-    term = term_n;
-    src[0] = src[1]; nrm[0] = nrm[1]; slot[0] = slot[1]; last[0] = last[1];
-    src[1] = src[2]; nrm[1] = nrm[2]; slot[1] = slot[2]; last[1] = last[2];
-  }
-}
-
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 gcn_layer_fwd_pair_kernel(const PairParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -465,16 +332,15 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
   auto a_full = [&](int s) { return bar0 + 8u * s; };                    // leader's: producer warps of the pair
   auto empty = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };      // per CTA: multicast commit
   auto acc_full = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + b); };       // per CTA: multicast commit
-  auto acc_empty = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + 2 + b); };  // leader's: 8 epilogue warps of the pair
+  auto acc_empty = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + 2 + b); };  // leader's: 16 epilogue warps of the pair
   const uint32_t w_local = bar0 + 8u * (2 * MAX_STAGES + 4);             // per CTA: bulk copy landed
   const uint32_t w_ready = bar0 + 8u * (2 * MAX_STAGES + 5);             // leader's: both CTAs hold the task's weights
   const uint32_t w_free = bar0 + 8u * (2 * MAX_STAGES + 6);              // per CTA: MMAs of the previous task are done
-  auto hub_full = [&](int d) { return bar0 + 8u * (2 * MAX_STAGES + 7 + d); };              // per CTA: 8 hub warps
-  auto hub_free = [&](int d) { return bar0 + 8u * (2 * MAX_STAGES + 7 + HUB_DEPTH + d); };  // per CTA: 8 producer warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 240);
-  int8_t* scale_e = reinterpret_cast<int8_t*>(bars) + 256;               // [4][TM]
-  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256 + 4 * TM);   // [ACC_COLS]
-  float* epi_s = bias_s + ACC_COLS;                                      // [4 warps][32 rows][32 floats]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + BAR_BYTES - 16);
+  int8_t* scale_e = reinterpret_cast<int8_t*>(bars) + BAR_BYTES;               // [4][TM]
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + BAR_BYTES + 4 * TM);   // [ACC_COLS]
+  float* rmax_s = bias_s + ACC_COLS;                                     // [2 tile parities][TM] row abs-max of the upper column half
+  float* epi_s = rmax_s + 2 * TM;                                        // [8 warps][32 rows][16 floats]
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();   // SWIZZLE_128B operand tiles need a 1024-byte aligned base
@@ -484,15 +350,11 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc_full(b), 1);
-      mbar_init(acc_empty(b), 8);
+      mbar_init(acc_empty(b), 2 * N_EPI_WARPS);
     }
     mbar_init(w_local, 1);
     mbar_init(w_ready, 2);
     mbar_init(w_free, 1);
-    for (int d = 0; d < HUB_DEPTH; ++d) {
-      mbar_init(hub_full(d), N_HUB_WARPS);
-      mbar_init(hub_free(d), N_PROD_WARPS);
-    }
     fence_mbar_init_cluster();
   }
   if (warp == WARP_LOAD) {
@@ -546,7 +408,6 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       int4 rcA = make_int4(0, 0, 0, 0), rcB = make_int4(0, 0, 0, 0);
       if (rA < nrows) rcA = __ldg(reinterpret_cast<const int4*>(p.rec + row0 + rA));
       if (rA + 64 < nrows) rcB = __ldg(reinterpret_cast<const int4*>(p.rec + row0 + rA + 64));
-      mbar_wait(hub_full(0), 0u, 8);        // the first tile's hub rows are aggregated
       curA.decode(rcA, rA < nrows, p, sub);
       curB.decode(rcB, rA + 64 < nrows, p, sub);
       gather_request(buf0, curA, 0, p.dbg);
@@ -617,18 +478,12 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
           if (liveB_n) rcB_n = __ldg(reinterpret_cast<const int4*>(p.rec + row0_n + rA + 64));
         }
         if (kc == ((nkc >> 2) << 1)) {
-          PLAP(t_body);
-          if (pr + 1 < p_end && !(p.dbg & 8))
-            mbar_wait(hub_full((ti + 1) % HUB_DEPTH), (uint32_t)(((ti + 1) / HUB_DEPTH) & 1), 8);
-          PLAP(t_setup);
           nxtA.decode(rcA_n, liveA_n, p, sub);
           nxtB.decode(rcB_n, liveB_n, p, sub);
         }
         step(buf0, buf1, kc);
         step(buf1, buf0, kc + 1);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster_relaxed(hub_free(ti % HUB_DEPTH), rank);   // throttle only: no data ordering needed
       curA = nxtA;
       curB = nxtB;
       row0_n = row0_nn; nrows_n = nrows_nn;
@@ -640,18 +495,7 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       o[0] = t_setup; o[1] = t_wait; o[2] = t_body;
     }
 #endif
-  } else if (warp < WARP_LOAD) {
-    // ===================== hub-row aggregation warps =====================
-    // mlong[slot][:] = sum_e nrm[e] * in[src[e]][:] for the hub rows of this CTA's tiles, a few tiles ahead
-    // of the producers (which then find the subgraph's rows in L2).  Warp hw owns the column slice
-    // [hw*K/4, (hw+1)*K/4) of EVERY hub row and streams through the tile's padded edge records, 32 at a
-    // time (8 rounds of 4 edges: 8 lanes x VEC floats per edge), so no partial sums cross warps, no
-    // barriers are needed, and the summation order is fixed.
-    reg_set<REGS_HUB>();
-    if (K == 256) hub_warp_loop<8>(p, warp - WARP_HUB0, lane, rank, p_beg, p_end, hub_full(0), hub_free(0));
-    else if (K == 128) hub_warp_loop<4>(p, warp - WARP_HUB0, lane, rank, p_beg, p_end, hub_full(0), hub_free(0));
-    else hub_warp_loop<2>(p, warp - WARP_HUB0, lane, rank, p_beg, p_end, hub_full(0), hub_free(0));
-  } else if (warp < WARP_EPI0) {
+  } else if (warp >= WARP_LOAD && warp < WARP_EPI0) {
     reg_set<REGS_CTRL>();
     if (warp == WARP_LOAD) {
       // ===================== weight loader: one bulk copy per task change =====================
@@ -738,13 +582,20 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       }
     }
   } else {
-    // ===================== epilogue =====================
+    // ===================== epilogue (8 warps) =====================
+    // Warps 16..19 drain the lower half of the accumulator columns, warps 8..11 the upper half; warp w may
+    // read TMEM lanes 32*(w%4)..+31, so warps w and w+8 share the same 32 rows.  Per 16-column block:
+    // tcgen05.ld (the next block is already in flight) -> * norm * 2^-e -> transposed through shared memory
+    // so that a store instruction writes 8 rows x 64 contiguous bytes -> + bias, ReLU / mask, row abs-max.
     reg_set<REGS_EPI>();
-    const int quarter = warp & 3;            // TMEM lanes 32*quarter .. +31 are the ones this warp may read
+    const int quarter = warp & 3;
+    const int half = warp < WARP_EPI0 ? 1 : 0;
     const int r = quarter * 32 + lane;       // accumulator row of this lane
-    const int et = threadIdx.x - WARP_EPI0 * 32;
-    float* stg = epi_s + quarter * 32 * 32;  // [32 rows][8 x 16-byte units, unit ^ (row % 8)]
-    const int tr = lane >> 3, tu = lane & 7; // transposed side: rows 4*i + tr, 16-byte unit tu of the 32-column block
+    const int et = half * 128 + r;           // index among the 256 epilogue threads
+    float* stg = epi_s + (half * 4 + quarter) * 32 * 16;   // [32 rows][4 x 16-byte units, unit ^ ((row / 2) % 4)]
+    const int tr = lane >> 2, tu = lane & 3; // transposed side: rows 8*i + tr, 16-byte unit tu of the 16-column block
+    const int nblk = N >> 4;
+    const int blk0 = half ? (nblk + 1) >> 1 : 0, blk1 = half ? nblk : (nblk + 1) >> 1;
     int ti = 0, bias_task = -1;
 #if GMETA_PAIR_PROF
     long long t_wacc = 0, t_epi = 0, t_mark = clock64();
@@ -763,10 +614,10 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       const float wis = p.w_inv_scale[p.image_task_stride ? task : 0];
       if (task != bias_task) {     // the task's bias -> shared memory, once per task
         bias_task = task;
-        asm volatile("bar.sync 2, 128;" ::: "memory");     // every epilogue warp is done with the old bias
+        asm volatile("bar.sync 2, 256;" ::: "memory");     // every epilogue warp is done with the old bias
         const float* bias = p.bias ? p.bias + (long long)task * p.b_task_stride : nullptr;
-        for (int c = et; c < ACC_COLS; c += 128) bias_s[c] = (bias && c < N) ? bias[c] : 0.f;
-        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (et < ACC_COLS) bias_s[et] = (bias && et < N) ? bias[et] : 0.f;
+        asm volatile("bar.sync 2, 256;" ::: "memory");
       }
       ELAP(t_epi);
       mbar_wait(acc_full(buf), (uint32_t)((ti >> 1) & 1), 7);
@@ -774,36 +625,32 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       tc_fence_after();
       const float f = live ? nv * exp2i(-(int)scale_e[(ti & 3) * TM + r]) * wis : 0.f;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * ACC_COLS);
-      float pmax[8];
+      float pmax[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) pmax[i] = 0.f;
-      for (int c0 = 0; c0 < N; c0 += 32) {
-        uint32_t acc[32];
-        if (c0 + 32 <= N) {
-          tmem_ld32(t_addr + (uint32_t)c0, acc);
-        } else {                                  // N % 32 == 16: last half block
-          uint32_t a16[16];
-          tmem_ld16(t_addr + (uint32_t)c0, a16);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) { acc[j] = a16[j]; acc[16 + j] = 0u; }
-        }
+      for (int i = 0; i < 4; ++i) pmax[i] = 0.f;
+      uint32_t acc_n[16];
+      if (blk0 < blk1) tmem_ld16(t_addr + (uint32_t)(blk0 * 16), acc_n);
+      for (int blk = blk0; blk < blk1; ++blk) {
+        const int c0 = blk * 16;
+        uint32_t acc[16];
         tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = acc_n[j];
+        if (blk + 1 < blk1) tmem_ld16(t_addr + (uint32_t)(c0 + 16), acc_n);   // next block in flight
         __syncwarp();                             // the previous block's transposed reads are done
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          st_f4(stg + lane * 32 + ((u ^ (lane & 7)) << 2),
+        for (int u = 0; u < 4; ++u)
+          st_f4(stg + lane * 16 + ((u ^ ((lane >> 1) & 3)) << 2),
                 make_float4(f * __uint_as_float(acc[4 * u]), f * __uint_as_float(acc[4 * u + 1]),
                             f * __uint_as_float(acc[4 * u + 2]), f * __uint_as_float(acc[4 * u + 3])));
         __syncwarp();
-        // transposed: a store instruction writes 4 rows x 128 contiguous bytes (whole lines); bias / ReLU / mask here
-        const bool col_ok = c0 + 4 * tu < N;
-        const float4 b4 = ld_f4(bias_s + ((c0 + 4 * tu) & (ACC_COLS - 1)));
+        const float4 b4 = ld_f4(bias_s + c0 + 4 * tu);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = 4 * i + tr;
+        for (int i = 0; i < 4; ++i) {
+          const int rr = 8 * i + tr;
           const int vr = __shfl_sync(0xffffffffu, v, rr);       // real row of tile row quarter*32 + rr
-          if (quarter * 32 + rr < nrows && col_ok) {
-            float4 w4 = ld_f4(stg + rr * 32 + ((tu ^ (rr & 7)) << 2));
+          if (quarter * 32 + rr < nrows) {
+            float4 w4 = ld_f4(stg + rr * 16 + ((tu ^ ((rr >> 1) & 3)) << 2));
             w4.x += b4.x; w4.y += b4.y; w4.z += b4.z; w4.w += b4.w;
             if (p.relu & 1) { w4.x = fmaxf(w4.x, 0.f); w4.y = fmaxf(w4.y, 0.f); w4.z = fmaxf(w4.z, 0.f); w4.w = fmaxf(w4.w, 0.f); }
             if (p.relu_mask) {
@@ -818,20 +665,29 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
           }
         }
       }
-      if (p.out_rowmax) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float m = pmax[i];
-          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
-          const int rr = 4 * i + tr;
-          if (tu == 0 && quarter * 32 + rr < nrows) p.out_rowmax[row0 + quarter * 32 + rr] = m;
-        }
-      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(acc_empty(buf), 0);
+      if (p.out_rowmax) {
+        // row abs-max over all columns: the upper-half warp hands its part to the lower-half warp of the same rows
+        float* rm = rmax_s + (ti & 1) * TM + quarter * 32;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float m = pmax[i];
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+          pmax[i] = m;
+          if (half && tu == 0) rm[8 * i + tr] = m;
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(3 + quarter) : "memory");
+        if (!half && tu == 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = 8 * i + tr;
+            if (quarter * 32 + rr < nrows) p.out_rowmax[row0 + quarter * 32 + rr] = fmaxf(pmax[i], rm[rr]);
+          }
+        }
+      }
     }
     ELAP(t_epi);
 #if GMETA_PAIR_PROF
@@ -915,6 +771,126 @@ __global__ void row_absmax_kernel(const float* __restrict__ x, int ld, int n_row
 }
 
 // ------------------------------------------------------------------------------------------
+// hub rows: mlong[slot][:] = sum_e nrm[e] * in[src[e]][:] and the bound sum_e nrm[e] * max|in[src[e],:]|
+// Runs before the fused kernel with the whole chip's memory-level parallelism (a hub row has up to
+// ~1000 in-neighbours: half of all edges of a 2-hop subgraph batch sit in ~3% of its rows); the fused
+// kernel then reads a hub like a single neighbour with weight 1.  Summation order is fixed.
+// ------------------------------------------------------------------------------------------
+template <int VEC>
+__device__ __forceinline__ void hub_accumulate(const float* __restrict__ in, int ld_in, const float* __restrict__ in_rowmax,
+                                               const int* __restrict__ src, const float* __restrict__ nrm, int n,
+                                               int lane, float (&acc)[VEC], float& bacc) {
+  // records [0, n) of one hub (n a multiple of 4), 32 at a time; lane covers columns [lane*VEC, lane*VEC + VEC)
+  for (int b = 0; b < n; b += 32) {
+    const int idx = b + lane;
+    int s_l = 0;
+    float n_l = 0.f;
+    if (idx < n) { s_l = src[idx]; n_l = nrm[idx]; }
+    if (n_l != 0.f) bacc += n_l * in_rowmax[s_l];
+    const int cnt = n - b < 32 ? n - b : 32;
+    for (int j0 = 0; j0 < cnt; j0 += 8) {
+      float x[8][VEC], w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        w[j] = __shfl_sync(0xffffffffu, n_l, (j0 + j) & 31);
+        const int sj = __shfl_sync(0xffffffffu, s_l, (j0 + j) & 31);
+        if (j0 + j < cnt && w[j] != 0.f) VecLd<VEC>::ld(x[j], in + (size_t)sj * ld_in + lane * VEC);
+        else {
+          w[j] = 0.f;
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) x[j][k] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] = fmaf(w[j], x[j][k], acc[k]);
+    }
+  }
+}
+
+// one warp per hub with at most HUB_BIG records
+template <int VEC>
+__global__ void __launch_bounds__(256) hub_small_kernel(const float* __restrict__ in, int ld_in,
+                                                        const float* __restrict__ in_rowmax, const int* __restrict__ hdr,
+                                                        const int* __restrict__ hub_beg, const int* __restrict__ hub_deg,
+                                                        const int* __restrict__ hub_src, const float* __restrict__ hub_nrm,
+                                                        float* __restrict__ mlong, float* __restrict__ mlong_bound) {
+  const int lane = threadIdx.x & 31;
+  const int n_hub = hdr[0];
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  for (int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < n_hub; slot += nw) {
+    const int n = (hub_deg[slot] + 3) & ~3;
+    if (n > HUB_BIG) continue;
+    const int beg = hub_beg[slot];
+    float acc[VEC], bacc = 0.f;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    hub_accumulate<VEC>(in, ld_in, in_rowmax, hub_src + beg, hub_nrm + beg, n, lane, acc, bacc);
+    VecLd<VEC>::st(mlong + (size_t)slot * (32 * VEC) + lane * VEC, acc);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) bacc += __shfl_xor_sync(0xffffffffu, bacc, o);
+    if (lane == 0) mlong_bound[slot] = bacc;
+  }
+}
+
+// one CTA (8 warps) per big hub: warp w sums the 32-record blocks w, w+8, ...; partials added in warp order
+template <int VEC>
+__global__ void __launch_bounds__(256) hub_big_kernel(const float* __restrict__ in, int ld_in,
+                                                      const float* __restrict__ in_rowmax, const int* __restrict__ hdr,
+                                                      const int* __restrict__ big_list, const int* __restrict__ hub_beg,
+                                                      const int* __restrict__ hub_deg, const int* __restrict__ hub_src,
+                                                      const float* __restrict__ hub_nrm, float* __restrict__ mlong,
+                                                      float* __restrict__ mlong_bound) {
+  constexpr int K = 32 * VEC;
+  __shared__ float part[8][K];
+  __shared__ float bpart[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_big = hdr[3];
+  for (int i = blockIdx.x; i < n_big; i += gridDim.x) {
+    const int slot = big_list[i];
+    const int n = (hub_deg[slot] + 3) & ~3, beg = hub_beg[slot];
+    float acc[VEC], bacc = 0.f;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    for (int b = warp * 32; b < n; b += 256) {
+      const int m = n - b < 32 ? n - b : 32;
+      hub_accumulate<VEC>(in, ld_in, in_rowmax, hub_src + beg + b, hub_nrm + beg + b, m, lane, acc, bacc);
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) part[warp][lane * VEC + k] = acc[k];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) bacc += __shfl_xor_sync(0xffffffffu, bacc, o);
+    if (lane == 0) bpart[warp] = bacc;
+    __syncthreads();
+    if (threadIdx.x < K) {
+      float v = part[0][threadIdx.x];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) v += part[w][threadIdx.x];
+      mlong[(size_t)slot * K + threadIdx.x] = v;
+    }
+    if (threadIdx.x == 0) {
+      float v = bpart[0];
+      for (int w = 1; w < 8; ++w) v += bpart[w];
+      mlong_bound[slot] = v;
+    }
+    __syncthreads();
+  }
+}
+
+template <int VEC>
+int hub_prepass_launch(const float* in, int ld_in, const float* in_rowmax, const Plan& pl, float* mlong,
+                       float* mlong_bound, cudaStream_t stream) {
+  hub_small_kernel<VEC><<<8 * kNumSMs, 256, 0, stream>>>(in, ld_in, in_rowmax, pl.hdr, pl.hub_beg, pl.hub_deg, pl.hub_src,
+                                                        pl.hub_nrm, mlong, mlong_bound);
+  int rc = check_launch();
+  if (rc != GMETA_OK) return rc;
+  hub_big_kernel<VEC><<<4 * kNumSMs, 256, 0, stream>>>(in, ld_in, in_rowmax, pl.hdr, pl.big_list, pl.hub_beg, pl.hub_deg,
+                                                      pl.hub_src, pl.hub_nrm, mlong, mlong_bound);
+  return check_launch();
+}
+
+// ------------------------------------------------------------------------------------------
 // plan construction (structure only) and the hub-row pre-aggregation
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int warp_incl_scan(int x, int lane) {
@@ -973,6 +949,7 @@ __global__ void plan_tiles_kernel(const int32_t* __restrict__ indptr, const int3
         pl.hub_row[slot] = v[j];
         pl.hub_beg[slot] = ebase + eoff[j];
         pl.hub_deg[slot] = deg[j];
+        if (((deg[j] + 3) & ~3) > HUB_BIG) pl.big_list[atomicAdd(pl.hdr + 3, 1)] = slot;   // order does not affect any value
         rc.r0 = slot; rc.r1 = -1; rc.n0 = 1.f;
       } else {
         if (deg[j] > 0) {
@@ -1154,12 +1131,16 @@ int gcn_layer_fwd_pair(const GatherSrc& g, const int32_t* tile_row0, const int32
                                                 ws.w_image, 2LL * K * N, ws.w_inv_scale);
     if ((rc = check_launch()) != GMETA_OK) return rc;
   }
+  if (!(g_pair_dbg & 16)) {     // hub rows first (debug flag 16: skip, results are wrong)
+    if (K == 256) rc = hub_prepass_launch<8>(g.in, g.ld_in, in_rowmax, pl, ws.mlong, ws.mlong_bound, stream);
+    else if (K == 128) rc = hub_prepass_launch<4>(g.in, g.ld_in, in_rowmax, pl, ws.mlong, ws.mlong_bound, stream);
+    else rc = hub_prepass_launch<2>(g.in, g.ld_in, in_rowmax, pl, ws.mlong, ws.mlong_bound, stream);
+    if (rc != GMETA_OK) return rc;
+  }
   PairParams p;
   p.in = g.in; p.ld_in = g.ld_in; p.f_in = K; p.in_rowmax = in_rowmax;
   p.mlong = ws.mlong; p.mlong_bound = ws.mlong_bound;
   p.rec = pl.rec; p.hdr = pl.hdr; p.pairs = pl.pairs;
-  p.hub_src = pl.hub_src; p.hub_nrm = pl.hub_nrm; p.hub_slot = pl.hub_slot;
-  p.mlong_w = ws.mlong; p.mlong_bound_w = ws.mlong_bound;
   p.dst_rows = g.dst_rows; p.norm = g.norm;
   p.w_image = ws.w_image; p.image_task_stride = n_copies > 1 ? 2LL * K * N : 0; p.w_inv_scale = ws.w_inv_scale;
   p.bias = bias; p.b_task_stride = b_task_stride; p.f_out = N; p.relu = relu; p.relu_mask = relu_mask;
