@@ -285,6 +285,13 @@ __device__ __forceinline__ void gather_request(float* buf, const RowCtx& c, int 
     for (int j = 8; j < 16; ++j) buf[j] = 0.f;
   }
 }
+// v = n0 * src0 + n1 * src1 over 8 columns -> scaled FP16 hi/lo
+__device__ __forceinline__ void combine(const float* m, float n0, float n1, uint4& hi, uint4& lo) {
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = fmaf(n1, m[8 + j], n0 * m[j]);
+  split8(v, hi, lo);
+}
 
 template <int R>
 __device__ __forceinline__ void reg_set() {      // setmaxnreg for the executing warpgroup
@@ -397,7 +404,7 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
 #endif
     RowCtx curA, curB, nxtA, nxtB;
     float buf0[32], buf1[32];               // two chunks: [rowA src0 | rowA src1 | rowB src0 | rowB src1] x 8 floats
-    int it = 0, ti = 0;
+    int ti = 0;
     int row0_n = 0, nrows_n = 0, row0_nn = 0, nrows_nn = 0;
     curA.clear(p.in);
     curB.clear(p.in);
@@ -414,11 +421,14 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       gather_request(buf0 + 16, curB, 0, p.dbg);
     }
     float nA0 = 0.f, nA1 = 0.f, nB0 = 0.f, nB1 = 0.f;
+    int st_i = 0;
+    uint32_t st_ph = 0u;
     // one chunk: `mine` holds this chunk's segments, `other` receives the next chunk's (requested first,
     // so their latency overlaps the stage wait, the conversion and the stores)
     auto step = [&](float (&mine)[32], float (&other)[32], int kc) {
-      const int s = it % NS;
-      const uint32_t ph = (uint32_t)((it / NS) & 1);
+      const int s = st_i;
+      const uint32_t ph = st_ph;
+      if (++st_i == NS) { st_i = 0; st_ph ^= 1u; }
       if (kc + 1 < nkc) {
         gather_request(other, curA, (kc + 1) * KCH, p.dbg);
         gather_request(other + 16, curB, (kc + 1) * KCH, p.dbg);
@@ -430,19 +440,14 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       mbar_wait(empty(s), ph ^ 1u, 1);
       PLAP(t_wait);
       uint8_t* stage = a_s + (size_t)s * STAGE_BYTES;
-      float v[8];
       uint4 hi, lo;
       if (curA.live) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaf(nA1, mine[8 + j], nA0 * mine[j]);
-        split8(v, hi, lo);
+        combine(mine, nA0, nA1, hi, lo);
         *reinterpret_cast<uint4*>(stage + soffA) = hi;
         *reinterpret_cast<uint4*>(stage + A_HALF_BYTES + soffA) = lo;
       }
       if (curB.live) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaf(nB1, mine[24 + j], nB0 * mine[16 + j]);
-        split8(v, hi, lo);
+        combine(mine + 16, nB0, nB1, hi, lo);
         *reinterpret_cast<uint4*>(stage + soffB) = hi;
         *reinterpret_cast<uint4*>(stage + A_HALF_BYTES + soffB) = lo;
       }
@@ -451,7 +456,6 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       if (!(p.dbg & 32)) fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(a_full(s), 0);
-      ++it;
     };
     for (int pr = p_beg; pr < p_end; ++pr, ++ti) {
       // scale of this tile's rows from the rigorous bound (see header comment)
@@ -522,7 +526,9 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       // ===================== MMA issuer (leader CTA, one thread) =====================
       if (rank == 0 && lane == 0) {
         const uint32_t idesc = umma_idesc_f16(2 * TM, N);
-        int it = 0, ti = 0, cur = -1, nw = 0;
+        int ti = 0, cur = -1, nw = 0;
+        int st_i = 0;
+        uint32_t st_ph = 0u;
 #if GMETA_PAIR_PROF
         long long t_w = 0, t_acc = 0, t_a = 0, t_issue = 0, t_mark = clock64();
 #define MLAP(acc) { const long long now_ = clock64(); acc += now_ - t_mark; t_mark = now_; }
@@ -545,9 +551,10 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
           MLAP(t_acc);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
-          for (int kc = 0; kc < nkc; ++kc, ++it) {
-            const int s = it % NS;
-            const uint32_t ph = (uint32_t)((it / NS) & 1);
+          for (int kc = 0; kc < nkc; ++kc) {
+            const int s = st_i;
+            const uint32_t ph = st_ph;
+            if (++st_i == NS) { st_i = 0; st_ph ^= 1u; }
             MLAP(t_issue);
             mbar_wait_cluster(a_full(s), ph, 6);
             MLAP(t_a);
@@ -626,8 +633,13 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       const float f = live ? nv * exp2i(-(int)scale_e[(ti & 3) * TM + r]) * wis : 0.f;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * ACC_COLS);
       float pmax[4];
+      float* orow[4];                         // transposed side: output row pointers (nullptr: past the tile's rows)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) pmax[i] = 0.f;
+      for (int i = 0; i < 4; ++i) {
+        pmax[i] = 0.f;
+        const int rr = quarter * 32 + 8 * i + tr;
+        orow[i] = rr < nrows ? p.out + (size_t)(row0 + rr) * p.ld_out + 4 * tu : nullptr;
+      }
       uint32_t acc_n[16];
       if (blk0 < blk1) tmem_ld16(t_addr + (uint32_t)(blk0 * 16), acc_n);
       for (int blk = blk0; blk < blk1; ++blk) {
@@ -645,12 +657,19 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
                             f * __uint_as_float(acc[4 * u + 2]), f * __uint_as_float(acc[4 * u + 3])));
         __syncwarp();
         const float4 b4 = ld_f4(bias_s + c0 + 4 * tu);
+        float4 t4[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int rr = 8 * i + tr;
-          const int vr = __shfl_sync(0xffffffffu, v, rr);       // real row of tile row quarter*32 + rr
-          if (quarter * 32 + rr < nrows) {
-            float4 w4 = ld_f4(stg + rr * 16 + ((tu ^ ((rr >> 1) & 3)) << 2));
+          t4[i] = ld_f4(stg + rr * 16 + ((tu ^ ((rr >> 1) & 3)) << 2));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = 8 * i + tr;
+          int vr = 0;
+          if (p.relu_mask) vr = __shfl_sync(0xffffffffu, v, rr);   // real row of tile row quarter*32 + rr
+          if (orow[i]) {
+            float4 w4 = t4[i];
             w4.x += b4.x; w4.y += b4.y; w4.z += b4.z; w4.w += b4.w;
             if (p.relu & 1) { w4.x = fmaxf(w4.x, 0.f); w4.y = fmaxf(w4.y, 0.f); w4.z = fmaxf(w4.z, 0.f); w4.w = fmaxf(w4.w, 0.f); }
             if (p.relu_mask) {
@@ -660,8 +679,8 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
               if (!(m4.z > 0.f)) w4.z = 0.f;
               if (!(m4.w > 0.f)) w4.w = 0.f;
             }
-            pmax[i] = fmaxf(pmax[i], fmaxf(fmaxf(fabsf(w4.x), fabsf(w4.y)), fmaxf(fabsf(w4.z), fabsf(w4.w))));
-            if (!(p.dbg & 1)) st_f4(p.out + (size_t)(row0 + quarter * 32 + rr) * p.ld_out + c0 + 4 * tu, w4);
+            if (p.out_rowmax) pmax[i] = fmaxf(pmax[i], fmaxf(fmaxf(fabsf(w4.x), fabsf(w4.y)), fmaxf(fabsf(w4.z), fabsf(w4.w))));
+            if (!(p.dbg & 1)) st_f4(orow[i] + c0, w4);
           }
         }
       }

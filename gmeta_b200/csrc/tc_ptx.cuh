@@ -51,22 +51,25 @@ __device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar, uint32
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or the
+// hint expires, instead of burning issue slots and shared-memory bandwidth in a software spin loop
+constexpr uint32_t kSuspendHintNs = 20000u;
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+      : "=r"(ok) : "r"(bar), "r"(parity), "r"(kSuspendHintNs) : "memory");
   return ok != 0;
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+      : "=r"(ok) : "r"(bar), "r"(parity), "r"(kSuspendHintNs) : "memory");
   return ok != 0;
 }
 // A printf here would be an ABI call, which makes ptxas cap EVERY warp role at the launch-bound
@@ -87,8 +90,9 @@ __device__ __forceinline__ void wait_timed_out(uint32_t bar, uint32_t parity, in
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int what = 0) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+  unsigned n = 0;
   while (!mbar_try_wait(bar, parity))
-    if (clock64() - t0 > kWaitTimeoutCycles) wait_timed_out(bar, parity, what);
+    if ((++n & 255u) == 0 && clock64() - t0 > kWaitTimeoutCycles) wait_timed_out(bar, parity, what);
 }
 // whole-warp wait: one lane polls (with back-off), the warp re-converges on __syncwarp.  Hundreds of
 // threads spinning on try_wait would otherwise flood the shared-memory pipe of the SM.
@@ -105,8 +109,9 @@ __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, in
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int what = 0) {
   if (mbar_try_wait_cluster(bar, parity)) return;
   const long long t0 = clock64();
+  unsigned n = 0;
   while (!mbar_try_wait_cluster(bar, parity))
-    if (clock64() - t0 > kWaitTimeoutCycles) wait_timed_out(bar, parity, what);
+    if ((++n & 255u) == 0 && clock64() - t0 > kWaitTimeoutCycles) wait_timed_out(bar, parity, what);
 }
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
