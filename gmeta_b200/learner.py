@@ -122,6 +122,57 @@ class _DeviceGraph(object):
         _lib.check(_lib.lib().gmeta_degree_norm(_ptr(self.indptr), N, _ptr(self.norm), _stream()), "degree_norm")
 
 
+def _plan(dg, transposed):
+    """Structure-only layer plan of the CTA-pair tensor-core kernel (csrc/gcn_layer_pair.cu): per-row source
+    records, tile pairs and the hub edge list.  One per orientation of the batched graph, built on first use and
+    shared by every layer and every call on this graph."""
+    key = "_plan_t" if transposed else "_plan"
+    pl = getattr(dg, key, None)
+    if pl is None:
+        L = _lib.lib()
+        ip, ix = (dg.t_indptr, dg.t_indices) if transposed else (dg.indptr, dg.indices)
+        E = int(ix.shape[0])
+        nb = L.gmeta_layer_plan_bytes(dg.n_tiles, 1, dg.N, E)
+        buf = torch.empty(nb + 256, dtype=torch.uint8, device=dg.norm.device)
+        ptr = (buf.data_ptr() + 255) // 256 * 256
+        _lib.check(L.gmeta_layer_plan_build(_ptr(ip), _ptr(ix), _ptr(dg.norm), None, None, _ptr(dg.tile_row0),
+                                            _ptr(dg.tile_nrows), _ptr(dg.tile_task), dg.n_tiles, 1, dg.N, E, ptr,
+                                            _stream()), "layer_plan_build")
+        pl = (buf, ptr)
+        setattr(dg, key, pl)
+    return pl[1]
+
+
+def _row_absmax(x, f):
+    r = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().gmeta_row_absmax(_ptr(x), x.shape[1], x.shape[0], f, _ptr(r), _stream()), "row_absmax")
+    return r
+
+
+def _layer(dg, inp, rmax_in, W, trans_w, ldw, b, fi, fo, relu, mask, out, impl, transposed=False, want_rmax=True):
+    """One fused GCN layer over the whole batched graph through gmeta_gcn_layer_fwd_ex: with the input's per-row
+    abs-max the library picks the CTA-pair tensor-core kernel where the shape allows (else 3xTF32 / FFMA) and
+    returns the output's per-row abs-max for the next layer."""
+    L = _lib.lib()
+    ip, ix = (dg.t_indptr, dg.t_indices) if transposed else (dg.indptr, dg.indices)
+    E = int(ix.shape[0])
+    dev = inp.device
+    use_ex = impl in (_lib.IMPL_AUTO, _lib.IMPL_TCPAIR) and rmax_in is not None
+    rmax_out = torch.empty(dg.N, dtype=torch.float32, device=dev) if (use_ex and want_rmax) else None
+    if use_ex:
+        nb = L.gmeta_gcn_layer_fwd_ex_workspace_bytes(1, 0, dg.n_tiles, dg.N, E, fi, fo, impl)
+    else:
+        nb = L.gmeta_gcn_layer_fwd_workspace_bytes(1, 0, fi, fo, impl)
+    scratch = torch.empty(max(nb, 16) + 256, dtype=torch.uint8, device=dev)
+    sp = (scratch.data_ptr() + 255) // 256 * 256
+    _lib.check(L.gmeta_gcn_layer_fwd_ex(
+        _ptr(inp), inp.shape[1], None, None, _ptr(ip), _ptr(ix), _ptr(dg.norm), _ptr(dg.tile_row0),
+        _ptr(dg.tile_nrows), _ptr(dg.tile_task), dg.n_tiles, 1, _ptr(W), 0, ldw, trans_w, _ptr(b), 0, fi, fo, relu,
+        _ptr(mask), _ptr(out), out.shape[1], impl, sp, nb, dg.N, E, _ptr(rmax_in) if use_ex else None,
+        _ptr(rmax_out), _plan(dg, transposed) if use_ex else None, _stream()), "gcn_layer_fwd")
+    return rmax_out
+
+
 def _device_graph(g, dev):
     dg = getattr(g, "_gmeta_dev", None)
     if dg is None or dg.norm.device != dev:
@@ -142,16 +193,12 @@ class _ClassifierFn(torch.autograd.Function):
         acts, inp, ld_in = [], x, x.shape[1]
         n_conv = len(spec.conv)
         ws = [v.detach().contiguous() for v in vars]
+        rmax = _row_absmax(x, spec.conv[0][0]) if impl in (_lib.IMPL_AUTO, _lib.IMPL_TCPAIR) else None
         for l, (fi, fo) in enumerate(spec.conv):
             ld_out = _round_up(fo, 4)
             out = torch.empty(dg.N, ld_out, dtype=torch.float32, device=dev)
-            nb = L.gmeta_gcn_layer_fwd_workspace_bytes(1, 0, fi, fo, impl)
-            scratch = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
-            _lib.check(L.gmeta_gcn_layer_fwd(
-                _ptr(inp), ld_in, None, None, _ptr(dg.indptr), _ptr(dg.indices), _ptr(dg.norm),
-                _ptr(dg.tile_row0), _ptr(dg.tile_nrows), _ptr(dg.tile_task), dg.n_tiles, 1,
-                _ptr(ws[2 * l]), 0, fo, 0, _ptr(ws[2 * l + 1]), 0, fi, fo, 1, None, _ptr(out), ld_out,
-                impl, _ptr(scratch), nb, _stream()), "gcn_layer_fwd")
+            rmax = _layer(dg, inp, rmax, ws[2 * l], 0, fo, ws[2 * l + 1], fi, fo, 1, None, out, impl,
+                          want_rmax=l + 1 < n_conv)
             acts.append(out)
             inp, ld_in = out, ld_out
         cps = 2 if spec.link_pred else 1
@@ -190,13 +237,9 @@ class _ClassifierFn(torch.autograd.Function):
             if l > 0:
                 ld_lo = acts[l - 1].shape[1]
                 dz_lo = torch.empty(dg.N, ld_lo, dtype=torch.float32, device=dev)
-                nb = L.gmeta_gcn_layer_fwd_workspace_bytes(1, 0, fo, fi, ctx.impl)
-                scratch = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
-                _lib.check(L.gmeta_gcn_layer_fwd(
-                    _ptr(dz), dz.shape[1], None, None, _ptr(dg.t_indptr), _ptr(dg.t_indices), _ptr(dg.norm),
-                    _ptr(dg.tile_row0), _ptr(dg.tile_nrows), _ptr(dg.tile_task), dg.n_tiles, 1,
-                    _ptr(ws[2 * l]), 0, fo, 1, None, 0, fo, fi, 0, _ptr(acts[l - 1]), _ptr(dz_lo), ld_lo,
-                    ctx.impl, _ptr(scratch), nb, _stream()), "gcn_layer dgrad")
+                rm = _row_absmax(dz, fo) if ctx.impl in (_lib.IMPL_AUTO, _lib.IMPL_TCPAIR) else None
+                _layer(dg, dz, rm, ws[2 * l], 1, fo, None, fo, fi, 0, acts[l - 1], dz_lo, ctx.impl, transposed=True,
+                       want_rmax=False)
                 dz = dz_lo
         return (None, None, None, None, None) + tuple(grads)
 

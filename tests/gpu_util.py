@@ -69,6 +69,9 @@ def layer_fwd(g, x, W, b, f_in, f_out, relu=1, transposed=False, trans_w=0, mask
     ip, ix = (g.t_indptr, g.t_indices) if transposed else (g.indptr, g.indices)
     if ldw is None:
         ldw = f_in if trans_w else f_out
+    if impl == _lib.IMPL_TCPAIR:
+        return _layer_fwd_pair(g, x, W, b, f_in, f_out, relu, trans_w, mask, row_map, w_stride, b_stride, ldw, ld_out,
+                               dst_rows, (t_row0, t_nrows, t_task), ip, ix, out)
     nb = _lib.lib().gmeta_gcn_layer_fwd_workspace_bytes(g.T, w_stride, f_in, f_out, impl)
     ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev())
     rc = _lib.lib().gmeta_gcn_layer_fwd(p(x), x.shape[1], p(row_map), p(dst_rows), p(ip), p(ix), p(g.norm), p(t_row0),
@@ -76,6 +79,30 @@ def layer_fwd(g, x, W, b, f_in, f_out, relu=1, transposed=False, trans_w=0, mask
                                         trans_w, p(b), b_stride, f_in, f_out, relu, p(mask), p(out), ld_out, impl,
                                         p(ws), nb, stream())
     _lib.check(rc, "gcn_layer_fwd")
+    return out
+
+
+def _layer_fwd_pair(g, x, W, b, f_in, f_out, relu, trans_w, mask, row_map, w_stride, b_stride, ldw, ld_out, dst_rows,
+                    tiles, ip, ix, out):
+    """The CTA-pair tensor-core path through gmeta_gcn_layer_fwd_ex: per-row abs-max of the input, plan built
+    inside the call, and the row abs-max it emits for the next layer checked against the output."""
+    L = _lib.lib()
+    t_row0, t_nrows, t_task = tiles
+    n_rows, n_edges = out.shape[0], int(ix.shape[0])
+    rmax_in = torch.empty(x.shape[0], dtype=torch.float32, device=dev())
+    _lib.check(L.gmeta_row_absmax(p(x), x.shape[1], x.shape[0], f_in, p(rmax_in), stream()), "row_absmax")
+    rmax_out = torch.full((n_rows,), float('nan'), dtype=torch.float32, device=dev())
+    nb = L.gmeta_gcn_layer_fwd_ex_workspace_bytes(g.T, w_stride, t_row0.shape[0], n_rows, n_edges, f_in, f_out,
+                                                  _lib.IMPL_TCPAIR)
+    ws = torch.empty(max(nb, 16) + 256, dtype=torch.uint8, device=dev())
+    ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+    rc = L.gmeta_gcn_layer_fwd_ex(p(x), x.shape[1], p(row_map), p(dst_rows), p(ip), p(ix), p(g.norm), p(t_row0),
+                                  p(t_nrows), p(t_task), t_row0.shape[0], g.T, p(W), w_stride, ldw, trans_w, p(b),
+                                  b_stride, f_in, f_out, relu, p(mask), p(out), ld_out, _lib.IMPL_TCPAIR, ws_ptr, nb,
+                                  n_rows, n_edges, p(rmax_in), p(rmax_out), None, stream())
+    _lib.check(rc, "gcn_layer_fwd_ex")
+    torch.cuda.synchronize()
+    assert torch.equal(rmax_out, out[:, :f_out].abs().amax(1)), "row abs-max emitted for the next layer"
     return out
 
 

@@ -1,7 +1,8 @@
 """GPU parity of every C-ABI op against the oracle and the reference-generated golden fixtures.
 
 Tolerances (fp32): north_star asks logits within 1e-4 of the reference's fp32 CPU path; the
-per-op bounds here are tighter (FFMA path: 2e-5 abs + 1e-5 rel; 3xTF32 path: 5e-5 abs + 2e-5 rel)
+per-op bounds here are tighter (FFMA path: 2e-5 abs + 1e-5 rel; tensor-core paths -- 3xTF32 and the
+CTA-pair scaled FP16 hi/lo split --: 5e-5 abs + 2e-5 rel)
 so that a 2-3 layer stack plus K inner steps stays inside 1e-4.
 """
 import os
@@ -16,16 +17,17 @@ from tests import gpu_util as U
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-IMPLS = [_lib.IMPL_SIMT, _lib.IMPL_TCGEN05]
-TOL = {_lib.IMPL_SIMT: (2e-5, 1e-5), _lib.IMPL_TCGEN05: (5e-5, 2e-5)}
+IMPLS = [_lib.IMPL_SIMT, _lib.IMPL_TCGEN05, _lib.IMPL_TCPAIR]
+TC_IMPLS = (_lib.IMPL_TCGEN05, _lib.IMPL_TCPAIR)
+TOL = {_lib.IMPL_SIMT: (2e-5, 1e-5), _lib.IMPL_TCGEN05: (5e-5, 2e-5), _lib.IMPL_TCPAIR: (5e-5, 2e-5)}
 
 
 def _fwd_or_skip(impl, *a, **k):
     try:
         return U.layer_fwd(*a, impl=impl, **k)
     except _lib.GMetaError as e:
-        if impl == _lib.IMPL_TCGEN05 and "not supported" in str(e):
-            pytest.skip("shape not covered by the tcgen05 path (FFMA path covers it)")
+        if impl in TC_IMPLS and "not supported" in str(e):
+            pytest.skip("shape not covered by this tensor-core path (FFMA path covers it)")
         raise
 
 
@@ -79,7 +81,7 @@ def test_layer_forward_and_gradients_vs_reference_golden(impl):
         try:
             y = U.layer_fwd(g, x, w, b, fi, fo, impl=impl)
         except _lib.GMetaError:
-            if impl == _lib.IMPL_TCGEN05:
+            if impl in TC_IMPLS:
                 continue
             raise
         ran += 1
@@ -94,7 +96,7 @@ def test_layer_forward_and_gradients_vs_reference_golden(impl):
         try:
             dx = U.layer_fwd(g, dz, w, None, fo, fi, relu=0, transposed=True, trans_w=1, impl=impl)
         except _lib.GMetaError:
-            if impl == _lib.IMPL_TCGEN05:
+            if impl in TC_IMPLS:
                 continue
             raise
         U.report("case %d dX" % k, dx[:, :fi], d[q + 'dx'], 5 * atol, 5 * rtol)
@@ -228,8 +230,8 @@ def test_layer_on_row_subset_with_dropped_neighbours(impl):
         y = U.layer_fwd(g, U.f32(xc), U.f32(W), U.f32(b), f_in, f_out, relu=0, row_map=U.i32(pos), w_stride=f_in * f_out,
                         b_stride=f_out, impl=impl, dst_rows=U.i32(sel), tiles=tiles, mask=U.f32(mask))
     except _lib.GMetaError:
-        if impl == _lib.IMPL_TCGEN05:
-            pytest.skip("shape not covered by the tcgen05 path")
+        if impl in TC_IMPLS:
+            pytest.skip("shape not covered by the tensor-core path")
         raise
     xz = np.where(keep[:, None], x, 0.0).astype(np.float32)        # dropped neighbour == zero row
     want, _, _ = _oracle_multitask(src, dst, trp, xz, W, b, relu=False)
