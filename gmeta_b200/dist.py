@@ -64,3 +64,23 @@ def allreduce_sum_(flat):
     if is_dist():
         td.all_reduce(flat, op=td.ReduceOp.SUM)
     return flat
+
+
+def gather_rows(rows):
+    """Concatenate every rank's [n_r, C] float rows (n_r may differ) on all ranks: evaluation episodes
+    are sharded like training tasks and only their accuracy rows are exchanged."""
+    import numpy as np
+    if not is_dist():
+        return rows
+    dev = 'cuda' if td.get_backend() == 'nccl' else 'cpu'
+    w, r = world_size(), rank()
+    cnt = torch.zeros(w, dtype=torch.int64, device=dev)
+    cnt[r] = rows.shape[0]
+    td.all_reduce(cnt)
+    m, c = int(cnt.max().item()), rows.shape[1]
+    buf = torch.zeros(w, max(m, 1), c, dtype=torch.float32, device=dev)
+    if rows.shape[0]:
+        buf[r, :rows.shape[0]] = torch.as_tensor(rows, dtype=torch.float32).to(dev)
+    td.all_reduce(buf)
+    buf, cnt = buf.cpu().numpy(), cnt.cpu().numpy()
+    return np.concatenate([buf[k, :cnt[k]] for k in range(w)], axis=0)

@@ -420,6 +420,21 @@ class Meta(nn.Module):
         self.last["d2h_bytes"] = int(host.numel() * 4)
         return host.numpy().astype(np.float32)                            # meta.py:232-234
 
+    def finetunning_batch(self, x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry, feat):
+        """Fine-tune on E independent episodes at once: every episode starts from the current
+        weights and gets its own fast-weight copy, exactly as E calls of `finetunning` would (meta.py:175-234
+        deep-copies the net per call), but as ONE batched inner loop.  Returns np.float32 [E, update_step_test+1];
+        `self.net` is not modified."""
+        K = self.update_step_test
+        if len(x_spt) == 0:
+            return np.zeros((0, K + 1), dtype=np.float32)
+        theta = self._flat_theta(self.net.parameters(), _dev())
+        acc_q, _, _ = self._run(x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry, feat,
+                                K, False, theta)
+        host = acc_q.cpu()
+        self.last["d2h_bytes"] = int(host.numel() * 4)
+        return host.numpy().astype(np.float32)
+
     def forward(self, x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry, feat):
         if self.method == 'G-Meta':
             accs = self.forward_ProtoMAML(x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry, feat)

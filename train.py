@@ -1,0 +1,169 @@
+#!/usr/bin/env python
+"""G-Meta training CLI on the B200-native hot path -- same flags, defaults, data directory layout and
+printed lines as the reference's G-Meta/train.py (flags :153-177, flow :31-148).
+
+    python train.py --data_dir DATA/ --task_setup Disjoint [--epoch 10 --task_num 8 ...]
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 train.py ...   # task-sharded
+
+Differences from the reference, all on purpose:
+  * graphs come from graph_csr.npz (or graph_dgl.pkl where DGL is importable), see gmeta_b200/data_io.py;
+  * `Meta` runs the inner loop of all tasks of a meta-batch as fused CUDA launches (no CPU path: a
+    missing GPU or extension is an error, not a fallback);
+  * validation / test episodes are evaluated `--eval_batch` at a time (each with its own copy of the
+    weights, exactly like the reference's one-by-one deepcopy loop, meta.py:175-234) instead of serially;
+  * under torchrun every rank takes the tasks `rank, rank+world, ...` of each meta-batch and the
+    meta-gradient is all-reduced once per step; evaluation episodes are sharded the same way;
+  * python's `random` is seeded too (the reference leaves it unseeded, so its runs are not reproducible).
+String booleans ('True'/'False') and prefix-abbreviated flags work as in the reference (argparse).
+"""
+import argparse
+import copy
+import os
+import random
+import time
+
+import numpy as np
+import psutil
+import torch
+from torch.utils.data import DataLoader
+
+from gmeta_b200 import data_io, dist
+from gmeta_b200.meta import Meta
+from gmeta_b200.subgraph_data_processing import Subgraphs, collate
+
+
+def build_config(feat, args, labels_num):
+    """Model topology, train.py:67-75."""
+    config = [('GraphConv', [feat[0].shape[1], args.hidden_dim])]
+    if args.h > 1:
+        config = config + [('GraphConv', [args.hidden_dim, args.hidden_dim])] * (args.h - 1)
+    config = config + [('Linear', [args.hidden_dim, labels_num])]
+    if args.link_pred_mode == 'True':
+        config.append(('LinkPred', [True]))
+    return config
+
+
+def evaluate(maml, db, feat, args):
+    """Fine-tune on every episode of `db` (meta.py:175-234 per episode), `eval_batch` episodes per
+    launch, sharded over ranks; returns the per-episode accuracy rows in dataset order."""
+    loader = DataLoader(db, max(1, args.eval_batch), shuffle=True, num_workers=args.num_workers,
+                        collate_fn=collate)
+    rows = []
+    for batch in loader:
+        rows.append(maml.finetunning_batch(*dist.shard_meta_batch(batch), feat))
+    accs = np.concatenate(rows, axis=0)
+    return dist.gather_rows(accs)
+
+
+def main(args):
+    torch.manual_seed(222)
+    torch.cuda.manual_seed_all(222)
+    np.random.seed(222)
+    random.seed(222)
+    world, rank = 1, 0
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_from_env("nccl")
+        world, rank = dist.world_size(), dist.rank()
+    say = print if rank == 0 else (lambda *a, **k: None)
+    say(args)
+
+    root = args.data_dir
+    feat = data_io.load_features(root)
+    graphs = data_io.load_graphs(root)
+    if args.task_setup == 'Shared' and args.task_mode == 'True':
+        root = os.path.join(root, 'task' + str(args.task_n))
+    info = data_io.load_labels(root)
+    total_class = len(np.unique(np.array(list(info.values()))))
+    say('There are {} classes '.format(total_class))
+    labels_num = args.n_way if args.task_setup == 'Disjoint' else total_class     # train.py:58-61
+
+    config = build_config(feat, args, labels_num)
+    if not torch.cuda.is_available():
+        raise SystemExit("train.py: no CUDA device -- gmeta_b200 has no CPU path")
+    device = torch.device('cuda', torch.cuda.current_device())
+    maml = Meta(args, config).to(device)
+    num = sum(int(np.prod(p.shape)) for p in maml.parameters() if p.requires_grad)
+    say(maml)
+    say('Total trainable tensors:', num)
+
+    max_acc = 0
+    model_max = copy.deepcopy(maml)
+    mk = lambda mode, b: Subgraphs(root, mode, info, n_way=args.n_way, k_shot=args.k_spt, k_query=args.k_qry,  # noqa: E731
+                                   batchsz=b, args=args, adjs=graphs, h=args.h)
+    db_train, db_val, db_test = mk('train', args.batchsz), mk('val', 100), mk('test', 100)
+    say('------ Start Training ------')
+    s_start = time.time()
+    max_memory = 0
+    for epoch in range(args.epoch):
+        db = DataLoader(db_train, args.task_num, shuffle=True, num_workers=args.num_workers, collate_fn=collate)
+        s_f = time.time()
+        s_r = s_f
+        for step, batch in enumerate(db):
+            data_loading_time = time.time() - (s_r if step >= 1 else s_f)
+            s = time.time()
+            if len(batch[0]) < world:            # a trailing meta-batch with fewer tasks than ranks
+                continue
+            maml.global_task_num = len(batch[0])  # meta.py:161 divides by the whole meta-batch's task count
+            accs = maml(*dist.shard_meta_batch(batch), feat)
+            max_memory = max(max_memory, float(psutil.virtual_memory().used / (1024 ** 3)))
+            if step % args.train_result_report_steps == 0:
+                say('Epoch:', epoch + 1, ' Step:', step, ' training acc:', str(accs[-1])[:5], ' time elapsed:',
+                    str(time.time() - s)[:5], ' data loading takes:', str(data_loading_time)[:5],
+                    ' Memory usage:', str(float(psutil.virtual_memory().used / (1024 ** 3)))[:5])
+            s_r = time.time()
+        accs = evaluate(maml, db_val, feat, args).mean(axis=0).astype(np.float16)
+        say('Epoch:', epoch + 1, ' Val acc:', str(accs[-1])[:5])
+        if accs[-1] > max_acc:
+            max_acc = accs[-1]
+            model_max = copy.deepcopy(maml)
+
+    rows = evaluate(maml, db_test, feat, args)
+    accs = rows.mean(axis=0).astype(np.float16)
+    say('Test acc:', str(accs[1])[:5])
+    # the reference keeps appending to the same list (train.py:130-145), so its "early stopped" number
+    # averages both test passes; reproduced
+    rows = np.concatenate([rows, evaluate(model_max, db_test, feat, args)], axis=0)
+    accs = rows.mean(axis=0).astype(np.float16)
+    say('Early Stopped Test acc:', str(accs[-1])[:5])
+    say('Total Time:', str(time.time() - s_start)[:5])
+    say('Max Momory:', str(max_memory)[:5])
+    return accs
+
+
+def parse(argv=None):
+    argparser = argparse.ArgumentParser()
+    argparser.add_argument('--epoch', type=int, help='epoch number', default=10)
+    argparser.add_argument('--n_way', type=int, help='n way', default=3)
+    argparser.add_argument('--k_spt', type=int, help='k shot for support set', default=3)
+    argparser.add_argument('--k_qry', type=int, help='k shot for query set', default=24)
+    argparser.add_argument('--task_num', type=int, help='meta batch size, namely task num', default=8)
+    argparser.add_argument('--meta_lr', type=float, help='meta-level outer learning rate', default=1e-3)
+    argparser.add_argument('--update_lr', type=float, help='task-level inner update learning rate', default=1e-3)
+    argparser.add_argument('--update_step', type=int, help='task-level inner update steps', default=5)
+    argparser.add_argument('--update_step_test', type=int, help='update steps for finetunning', default=10)
+    argparser.add_argument('--input_dim', type=int, help='input feature dim', default=1)
+    argparser.add_argument('--hidden_dim', type=int, help='hidden dim', default=64)
+    argparser.add_argument('--attention_size', type=int, help='dim of attention_size', default=32)
+    argparser.add_argument("--data_dir", default=None, type=str, required=True, help="The input data dir.")
+    argparser.add_argument("--no_finetune", default=True, type=str, required=False, help="no finetune mode.")
+    argparser.add_argument("--task_setup", default='Disjoint', type=str, required=True,
+                           help="Select from Disjoint or Shared Setup. For Disjoint-Label, single/multiple graphs are both considered.")
+    argparser.add_argument("--method", default='G-Meta', type=str, required=False, help="Use G-Meta")
+    argparser.add_argument('--task_n', type=int, help='task number', default=1)
+    argparser.add_argument("--task_mode", default='False', type=str, required=False, help="For Evaluating on Tasks")
+    argparser.add_argument("--val_result_report_steps", default=100, type=int, required=False, help="validation report")
+    argparser.add_argument("--train_result_report_steps", default=30, type=int, required=False, help="training report")
+    argparser.add_argument("--num_workers", default=0, type=int, required=False, help="num of workers")
+    argparser.add_argument("--batchsz", default=1000, type=int, required=False, help="batch size")
+    argparser.add_argument("--link_pred_mode", default='False', type=str, required=False, help="For Link Prediction")
+    argparser.add_argument("--h", default=2, type=int, required=False, help="neighborhood size")
+    argparser.add_argument('--sample_nodes', type=int, help='sample nodes if above this number of nodes', default=1000)
+    # not in the reference
+    argparser.add_argument('--eval_batch', type=int, default=25,
+                           help='validation/test episodes fine-tuned per launch (1 = one by one like the reference)')
+    return argparser.parse_args(argv)
+
+
+if __name__ == '__main__':
+    main(parse())
