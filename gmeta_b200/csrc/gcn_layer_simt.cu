@@ -368,6 +368,108 @@ int gcn_layer_fwd_simt(const GatherSrc& g, const int32_t* tile_row0, const int32
 
 using namespace gmeta;
 
+namespace gmeta {
+namespace {
+// one warp per output row: out[i, c] = (scale_dst ? norm[v] : 1) * sum_e norm[u_e] * in[map(u_e), c], v = dst_rows ? dst_rows[i] : i.
+// Edge records are loaded coalesced (one per lane) and broadcast; eight row segments are in flight per lane;
+// summation follows edge order (deterministic).  Columns [f_in, ld_out) are written as zero.
+template <bool VEC>
+__global__ void __launch_bounds__(256) aggregate_rows_kernel(GatherSrc g, int n_rows, int scale_dst,
+                                                             float* __restrict__ out, int ld_out) {
+  const int lane = threadIdx.x & 31;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_rows; i += nw) {
+    const int v = g.dst_rows ? g.dst_rows[i] : i;
+    const int beg = g.indptr[v], end = g.indptr[v + 1];
+    const float nv = scale_dst ? g.norm[v] : 1.f;
+    for (int c0 = 0; c0 < ld_out; c0 += 128) {
+      const int kcol = c0 + 4 * lane;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int base = beg; base < end; base += 32) {
+        int u_src = 0;
+        float u_norm = 0.f;
+        if (base + lane < end) {
+          const int u = g.indices[base + lane];
+          u_norm = g.norm[u];
+          u_src = g.in_row_map ? g.in_row_map[u] : u;
+          if (u_src < 0) { u_src = 0; u_norm = 0.f; }
+        }
+        const int cnt = min(32, end - base);
+        for (int j0 = 0; j0 < cnt; j0 += 8) {
+          float4 x[8];
+          float w[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int src = __shfl_sync(0xffffffffu, u_src, (j0 + j) & 31);
+            w[j] = __shfl_sync(0xffffffffu, u_norm, (j0 + j) & 31);
+            if (j0 + j >= cnt) w[j] = 0.f;
+            x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (w[j] != 0.f && kcol < g.f_in) {
+              const float* p = g.in + (size_t)src * g.ld_in + kcol;
+              if (VEC) {
+                x[j] = ld_f4(p);
+              } else {
+                x[j].x = p[0];
+                if (kcol + 1 < g.f_in) x[j].y = p[1];
+                if (kcol + 2 < g.f_in) x[j].z = p[2];
+                if (kcol + 3 < g.f_in) x[j].w = p[3];
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            acc.x = fmaf(w[j], x[j].x, acc.x);
+            acc.y = fmaf(w[j], x[j].y, acc.y);
+            acc.z = fmaf(w[j], x[j].z, acc.z);
+            acc.w = fmaf(w[j], x[j].w, acc.w);
+          }
+        }
+      }
+      if (kcol < ld_out) {
+        float r[4] = {acc.x * nv, acc.y * nv, acc.z * nv, acc.w * nv};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (kcol + k < ld_out) out[(size_t)i * ld_out + kcol + k] = kcol + k < g.f_in ? r[k] : 0.f;
+      }
+    }
+  }
+}
+
+__global__ void identity_graph_kernel(int32_t* __restrict__ iota, float* __restrict__ ones, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += gridDim.x * blockDim.x) {
+    iota[i] = i;
+    if (i < n) ones[i] = 1.f;
+  }
+}
+}  // namespace
+
+// iota[0..n] = 0..n and ones[0..n) = 1: the CSR (indptr == indices == iota) and degree norm of a graph
+// whose every row has exactly itself as in-neighbour with weight 1
+int fill_identity_graph(int32_t* iota, float* ones, int n, cudaStream_t stream) {
+  if (n < 0) return GMETA_ERR_BAD_ARG;
+  const int grid = ceil_div(n + 1, 256) < 4 * kNumSMs ? ceil_div(n + 1, 256) : 4 * kNumSMs;
+  identity_graph_kernel<<<grid, 256, 0, stream>>>(iota, ones, n);
+  return check_launch();
+}
+}  // namespace gmeta
+
+extern "C" int gmeta_aggregate_rows(const float* in, int32_t ld_in, const int32_t* in_row_map, const int32_t* dst_rows,
+                                    const int32_t* indptr, const int32_t* indices, const float* norm, int32_t n_rows,
+                                    int32_t f_in, int32_t scale_dst, float* out, int32_t ld_out, void* stream) {
+  if (n_rows < 0 || f_in <= 0 || ld_in < f_in || ld_out < f_in) return GMETA_ERR_BAD_ARG;
+  if (n_rows == 0) return GMETA_OK;
+  if (!in || !indptr || !indices || !norm || !out) return GMETA_ERR_BAD_ARG;
+  GatherSrc g;
+  g.in = in; g.in_row_map = in_row_map; g.dst_rows = dst_rows; g.indptr = indptr; g.indices = indices; g.norm = norm;
+  g.ld_in = ld_in; g.f_in = f_in;
+  const int grid = ceil_div(n_rows, 8) < 16 * kNumSMs ? ceil_div(n_rows, 8) : 16 * kNumSMs;
+  if (ld_in % 4 == 0 && f_in % 4 == 0 && aligned16(in))
+    aggregate_rows_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(g, n_rows, scale_dst, out, ld_out);
+  else
+    aggregate_rows_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(g, n_rows, scale_dst, out, ld_out);
+  return check_launch();
+}
+
 extern "C" int gmeta_degree_norm(const int32_t* indptr, int32_t n_nodes, float* norm, void* stream) {
   if (n_nodes < 0 || (n_nodes > 0 && (!indptr || !norm))) return GMETA_ERR_BAD_ARG;
   if (n_nodes == 0) return GMETA_OK;

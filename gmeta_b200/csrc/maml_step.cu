@@ -9,6 +9,8 @@
 
 namespace gmeta {
 
+int fill_identity_graph(int32_t* iota, float* ones, int n, cudaStream_t stream);
+
 int proto_loss_launch(bool spt, const float* logits, int n_out, const int32_t* task_sub_ptr, int n_tasks,
                       const int32_t* class_pos, const int32_t* class_occ, const int32_t* n_classes,
                       int n_support, int max_classes, int max_rows, float grad_scale, float* protos,
@@ -47,6 +49,12 @@ struct StepBuffers {
   float* acc_s;
   void* wgrad_ws;
   int64_t wgrad_ws_bytes;
+  // pruned forward: the first layer's normalised neighbourhood sums over its active rows (weights do not
+  // enter them: computed once per meta-step) and the identity graph the layer kernels then run on
+  float* agg_spt;
+  float* agg_qry;
+  int32_t* iota;
+  float* ones;
   void* layer_ws;            // weight image of the tensor-core layer kernel
   int64_t layer_ws_bytes;
   int ld[GMETA_MAX_LAYERS];
@@ -97,6 +105,11 @@ void carve(const gmeta_step_args_t* a, void* ws, StepBuffers& b) {
       if (a->qry.n_act[l] > rows_q) rows_q = a->qry.n_act[l];
     }
   }
+  const int64_t n0s = a->pruned_forward ? a->spt.n_act[0] : 0, n0q = a->pruned_forward ? a->qry.n_act[0] : 0;
+  b.agg_spt = c.take<float>(n0s * a->ld_feat);
+  b.agg_qry = c.take<float>(n0q * a->ld_feat);
+  b.iota = c.take<int32_t>(a->pruned_forward ? (n0s > n0q ? n0s : n0q) + 1 : 0);
+  b.ones = c.take<float>(a->pruned_forward ? (n0s > n0q ? n0s : n0q) : 0);
   b.dz_spt[0] = c.take<float>(rows_s * ld_max);
   b.dz_spt[1] = c.take<float>(m.n_layers > 1 ? rows_s * ld_max : 0);
   b.dz_qry[0] = c.take<float>(a->compute_meta_grad ? rows_q * ld_max : 0);
@@ -136,6 +149,15 @@ struct Runner {
     const gmeta_model_t& m = a->model;
     const bool pruned = a->pruned_forward != 0;
     for (int l = 0; l < m.n_layers && ok(); ++l) {
+      if (l == 0 && pruned) {
+        // cached aggregation: a dense contraction of the pre-summed rows (identity graph, unit norms)
+        run(gmeta_gcn_layer_fwd(&set == &a->spt ? b.agg_spt : b.agg_qry, a->ld_feat, nullptr, nullptr, b.iota, b.iota,
+                                b.ones, set.act_tile_row0[0], set.act_tile_nrows[0], set.act_tile_task[0],
+                                set.n_act_tiles[0], set.n_tasks, W + m.w_off[0], stride, m.f_out[0], 0, W + m.b_off[0],
+                                stride, m.f_in[0], m.f_out[0], 1, nullptr, act[0], b.ld[0], a->impl, b.layer_ws,
+                                b.layer_ws_bytes, s));
+        continue;
+      }
       const float* in = l == 0 ? a->feat_table : act[l - 1];
       const int ld_in = l == 0 ? a->ld_feat : b.ld[l - 1];
       // pruned: layer l over its active rows only (compact output); its inputs are the compact
@@ -175,6 +197,12 @@ struct Runner {
     for (int l = L - 1; l >= 0 && ok(); --l) {
       const float* in = l == 0 ? a->feat_table : act[l - 1];
       const int ld_in = l == 0 ? a->ld_feat : b.ld[l - 1];
+      if (l == 0 && pruned) {   // dW1 = (cached n_v M_v)^T dZ_1 over the active rows
+        run(gmeta_gcn_layer_wgrad(&set == &a->spt ? b.agg_spt : b.agg_qry, a->ld_feat, nullptr, nullptr, b.iota, b.iota,
+                                  b.ones, set.act_task_ptr[0], set.n_tasks, dz[cur], b.ld[0], m.f_in[0], m.f_out[0],
+                                  gout + m.w_off[0], P, gout + m.b_off[0], P, b.wgrad_ws, b.wgrad_ws_bytes, s));
+        continue;
+      }
       run(gmeta_gcn_layer_wgrad(in, ld_in, l == 0 ? set.feat_row : (pruned ? set.row_pos[l - 1] : nullptr),
                                 sparse ? set.act_rows[l] : nullptr,
                                 set.indptr, set.indices, set.norm, sparse ? set.act_task_ptr[l] : set.task_row_ptr,
@@ -260,6 +288,15 @@ extern "C" int gmeta_maml_step(const gmeta_step_args_t* a, void* stream) {
       if (a->compute_meta_grad || a->pruned_forward)
         r.run(gmeta_build_row_pos(qr.act_rows[l], qr.n_act[l], qr.n_nodes, qr.row_pos[l], s));
     }
+  }
+
+  if (a->pruned_forward) {
+    const int n0s = sp.n_act[0], n0q = qr.n_act[0];
+    r.run(fill_identity_graph(b.iota, b.ones, n0s > n0q ? n0s : n0q, s));
+    r.run(gmeta_aggregate_rows(a->feat_table, a->ld_feat, sp.feat_row, sp.act_rows[0], sp.indptr, sp.indices, sp.norm,
+                               n0s, m.f_in[0], 1, b.agg_spt, a->ld_feat, s));
+    r.run(gmeta_aggregate_rows(a->feat_table, a->ld_feat, qr.feat_row, qr.act_rows[0], qr.indptr, qr.indices, qr.norm,
+                               n0q, m.f_in[0], 1, b.agg_qry, a->ld_feat, s));
   }
 
   for (int k = 0; k < K && r.ok(); ++k) {

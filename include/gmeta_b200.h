@@ -212,6 +212,15 @@ int gmeta_gcn_layer_wgrad(const float* in, int32_t ld_in, const int32_t* in_row_
                           float* dW, int64_t dw_task_stride, float* db, int64_t db_task_stride,
                           void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Normalised neighbourhood sum alone -- the aggregation half of GraphConv.forward (learner.py:29-32,41-45):
+ *   out[i, :f_in] = (scale_dst ? norm[v] : 1) * sum_{(u -> v)} norm[u] * in[map(u), :],  v = dst_rows ? dst_rows[i] : i
+ * (columns f_in..ld_out-1 are zeroed).  For the FIRST layer this depends on the graph and the features only,
+ * not on the weights, so the ProtoMAML driver computes it once per meta-step and runs every first-layer
+ * forward / weight gradient of the inner loop on the cached rows ("cached A.X"). */
+int gmeta_aggregate_rows(const float* in, int32_t ld_in, const int32_t* in_row_map, const int32_t* dst_rows,
+                         const int32_t* indptr, const int32_t* indices, const float* norm, int32_t n_rows,
+                         int32_t f_in, int32_t scale_dst, float* out, int32_t ld_out, void* stream);
+
 /* Centre-row readout + linear head (learner.py:159-175):
  *   r_s = H[centre_row[s]]   (link_pred: H[centre_row[2s]] || H[centre_row[2s+1]])
  *   logits[s,c] = sum_k r_s[k] * Wlin[t][c,k] + blin[t][c],  t = task of subgraph s. */
