@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--tasks", type=int, default=0, help="tasks per rank (default: the config's task_num)")
     ap.add_argument("--batches", type=int, default=3, help="distinct pre-extracted meta-batches to cycle")
     ap.add_argument("--kernel-impl", type=int, default=0, help="0 auto, 1 FFMA, 2 tcgen05")
-    ap.add_argument("--cpu-tasks", type=int, default=2, help="tasks in the bounded CPU sample")
+    ap.add_argument("--cpu-tasks", type=int, default=8, help="tasks per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -200,7 +200,7 @@ def main():
         ds = make_dataset(args.workload, scale=args.scale)
         n_tasks = max(1, args.cpu_tasks)
         batch = ds.sample_meta_batch(np.random.default_rng(1000), n_tasks)
-        steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+        steps, warmup = max(1, args.steps), max(0, args.warmup)     # a step = n_tasks tasks of the workload (bounded sample)
         cb = cpu_arm(ds, batch, n_tasks, steps, warmup)
         cfg = workload_desc(ds, n_tasks)
         cfg["note"] = "reference CPU path = oracle port (the reference's own files need DGL, absent here)"
@@ -285,7 +285,7 @@ def main():
     roof = layer_roofline(m, dbs[0], peaks, args.kernel_impl)
     cb = None
     if not args.no_cpu_baseline:
-        cb = cpu_arm(ds, batches[0], max(1, args.cpu_tasks), 1, 1)
+        cb = cpu_arm(ds, batches[0], max(1, args.cpu_tasks), 3, 1)   # ~10-20 s of host work
     cfg = workload_desc(ds, tasks)
     cfg.update({"parallelism": "task-sharded x%d" % world, "l2_policy": "inputs larger than L2 (packed meta-batch "
                 "activations %.1f GB per step; %d distinct meta-batches cycled)"

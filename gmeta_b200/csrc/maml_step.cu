@@ -51,8 +51,10 @@ struct StepBuffers {
   int64_t wgrad_ws_bytes;
   // pruned forward: the first layer's normalised neighbourhood sums over its active rows (weights do not
   // enter them: computed once per meta-step) and the identity graph the layer kernels then run on
-  float* agg_spt;
-  float* agg_qry;
+  float* agg_spt[GMETA_MAX_LAYERS];   // [n_act[l], ld_in(l)]: aggregated input of layer l (l = 0: of the features, once per step)
+  float* agg_qry[GMETA_MAX_LAYERS];
+  float* dagg;                        // aggregated dZ of the data-gradient step (one at a time)
+  int n_ident;                        // rows of the identity graph
   int32_t* iota;
   float* ones;
   void* layer_ws;            // weight image of the tensor-core layer kernel
@@ -106,10 +108,20 @@ void carve(const gmeta_step_args_t* a, void* ws, StepBuffers& b) {
     }
   }
   const int64_t n0s = a->pruned_forward ? a->spt.n_act[0] : 0, n0q = a->pruned_forward ? a->qry.n_act[0] : 0;
-  b.agg_spt = c.take<float>(n0s * a->ld_feat);
-  b.agg_qry = c.take<float>(n0q * a->ld_feat);
-  b.iota = c.take<int32_t>(a->pruned_forward ? (n0s > n0q ? n0s : n0q) + 1 : 0);
-  b.ones = c.take<float>(a->pruned_forward ? (n0s > n0q ? n0s : n0q) : 0);
+  b.agg_spt[0] = c.take<float>(n0s * a->ld_feat);
+  b.agg_qry[0] = c.take<float>(n0q * a->ld_feat);
+  int64_t n_max = n0s > n0q ? n0s : n0q;
+  for (int l = 1; l < m.n_layers; ++l) {
+    const int64_t ns = a->pruned_forward ? a->spt.n_act[l] : 0, nq = a->pruned_forward ? a->qry.n_act[l] : 0;
+    b.agg_spt[l] = c.take<float>(ns * b.ld[l - 1]);
+    b.agg_qry[l] = c.take<float>(nq * b.ld[l - 1]);
+    if (ns > n_max) n_max = ns;
+    if (nq > n_max) n_max = nq;
+  }
+  b.dagg = c.take<float>(a->pruned_forward && m.n_layers > 1 ? n_max * ld_max : 0);
+  b.n_ident = a->pruned_forward ? (int)n_max : 0;
+  b.iota = c.take<int32_t>(a->pruned_forward ? n_max + 1 : 0);
+  b.ones = c.take<float>(a->pruned_forward ? n_max : 0);
   b.dz_spt[0] = c.take<float>(rows_s * ld_max);
   b.dz_spt[1] = c.take<float>(m.n_layers > 1 ? rows_s * ld_max : 0);
   b.dz_qry[0] = c.take<float>(a->compute_meta_grad ? rows_q * ld_max : 0);
@@ -149,13 +161,20 @@ struct Runner {
     const gmeta_model_t& m = a->model;
     const bool pruned = a->pruned_forward != 0;
     for (int l = 0; l < m.n_layers && ok(); ++l) {
-      if (l == 0 && pruned) {
-        // cached aggregation: a dense contraction of the pre-summed rows (identity graph, unit norms)
-        run(gmeta_gcn_layer_fwd(&set == &a->spt ? b.agg_spt : b.agg_qry, a->ld_feat, nullptr, nullptr, b.iota, b.iota,
-                                b.ones, set.act_tile_row0[0], set.act_tile_nrows[0], set.act_tile_task[0],
-                                set.n_act_tiles[0], set.n_tasks, W + m.w_off[0], stride, m.f_out[0], 0, W + m.b_off[0],
-                                stride, m.f_in[0], m.f_out[0], 1, nullptr, act[0], b.ld[0], a->impl, b.layer_ws,
-                                b.layer_ws_bytes, s));
+      if (pruned) {
+        // The neighbourhood sums of the layer's active rows come from a chip-wide gather (one warp per row;
+        // layer 0: cached for the whole meta-step, the weights do not enter it), the contraction then runs
+        // dense on the pre-summed rows: identity graph, unit norms.  Every in-neighbour of an active row of
+        // layer l is an active row of layer l-1 by construction, so row_pos[l-1] maps it to its compact row.
+        float* agg = (&set == &a->spt ? b.agg_spt : b.agg_qry)[l];
+        const int ld_agg = l == 0 ? a->ld_feat : b.ld[l - 1];
+        if (l > 0)
+          run(gmeta_aggregate_rows(act[l - 1], b.ld[l - 1], set.row_pos[l - 1], set.act_rows[l], set.indptr, set.indices,
+                                   set.norm, set.n_act[l], m.f_in[l], 1, agg, ld_agg, s));
+        run(gmeta_gcn_layer_fwd(agg, ld_agg, nullptr, nullptr, b.iota, b.iota, b.ones, set.act_tile_row0[l],
+                                set.act_tile_nrows[l], set.act_tile_task[l], set.n_act_tiles[l], set.n_tasks,
+                                W + m.w_off[l], stride, m.f_out[l], 0, W + m.b_off[l], stride, m.f_in[l], m.f_out[l], 1,
+                                nullptr, act[l], b.ld[l], a->impl, b.layer_ws, b.layer_ws_bytes, s));
         continue;
       }
       const float* in = l == 0 ? a->feat_table : act[l - 1];
@@ -197,10 +216,24 @@ struct Runner {
     for (int l = L - 1; l >= 0 && ok(); --l) {
       const float* in = l == 0 ? a->feat_table : act[l - 1];
       const int ld_in = l == 0 ? a->ld_feat : b.ld[l - 1];
-      if (l == 0 && pruned) {   // dW1 = (cached n_v M_v)^T dZ_1 over the active rows
-        run(gmeta_gcn_layer_wgrad(&set == &a->spt ? b.agg_spt : b.agg_qry, a->ld_feat, nullptr, nullptr, b.iota, b.iota,
-                                  b.ones, set.act_task_ptr[0], set.n_tasks, dz[cur], b.ld[0], m.f_in[0], m.f_out[0],
-                                  gout + m.w_off[0], P, gout + m.b_off[0], P, b.wgrad_ws, b.wgrad_ws_bytes, s));
+      if (pruned) {
+        // dW_l = (n_v M_v)^T dZ_l with the aggregated rows the forward kept; the data gradient is the same two
+        // steps as a forward on the transposed graph: gather n_v dZ_v over the out-neighbours that are active at
+        // layer l (the others are dropped through row_pos[l]), then the dense contraction with W^T, masked by
+        // the ReLU of the layer below.
+        const float* agg = (&set == &a->spt ? b.agg_spt : b.agg_qry)[l];
+        run(gmeta_gcn_layer_wgrad(agg, ld_in, nullptr, nullptr, b.iota, b.iota, b.ones, set.act_task_ptr[l], set.n_tasks,
+                                  dz[cur], b.ld[l], m.f_in[l], m.f_out[l], gout + m.w_off[l], P, gout + m.b_off[l], P,
+                                  b.wgrad_ws, b.wgrad_ws_bytes, s));
+        if (l > 0) {
+          run(gmeta_aggregate_rows(dz[cur], b.ld[l], set.row_pos[l], set.act_rows[l - 1], set.t_indptr, set.t_indices,
+                                   set.norm, set.n_act[l - 1], m.f_out[l], 1, b.dagg, b.ld[l], s));
+          run(gmeta_gcn_layer_fwd(b.dagg, b.ld[l], nullptr, nullptr, b.iota, b.iota, b.ones, set.act_tile_row0[l - 1],
+                                  set.act_tile_nrows[l - 1], set.act_tile_task[l - 1], set.n_act_tiles[l - 1], set.n_tasks,
+                                  W + m.w_off[l], stride, m.f_out[l], 1, nullptr, 0, m.f_out[l], m.f_in[l], 2, act[l - 1],
+                                  dz[cur ^ 1], b.ld[l - 1], a->impl, b.layer_ws, b.layer_ws_bytes, s));
+          cur ^= 1;
+        }
         continue;
       }
       run(gmeta_gcn_layer_wgrad(in, ld_in, l == 0 ? set.feat_row : (pruned ? set.row_pos[l - 1] : nullptr),
@@ -292,11 +325,11 @@ extern "C" int gmeta_maml_step(const gmeta_step_args_t* a, void* stream) {
 
   if (a->pruned_forward) {
     const int n0s = sp.n_act[0], n0q = qr.n_act[0];
-    r.run(fill_identity_graph(b.iota, b.ones, n0s > n0q ? n0s : n0q, s));
+    r.run(fill_identity_graph(b.iota, b.ones, b.n_ident, s));
     r.run(gmeta_aggregate_rows(a->feat_table, a->ld_feat, sp.feat_row, sp.act_rows[0], sp.indptr, sp.indices, sp.norm,
-                               n0s, m.f_in[0], 1, b.agg_spt, a->ld_feat, s));
+                               n0s, m.f_in[0], 1, b.agg_spt[0], a->ld_feat, s));
     r.run(gmeta_aggregate_rows(a->feat_table, a->ld_feat, qr.feat_row, qr.act_rows[0], qr.indptr, qr.indices, qr.norm,
-                               n0q, m.f_in[0], 1, b.agg_qry, a->ld_feat, s));
+                               n0q, m.f_in[0], 1, b.agg_qry[0], a->ld_feat, s));
   }
 
   for (int k = 0; k < K && r.ok(); ++k) {
