@@ -828,45 +828,43 @@ __device__ __forceinline__ void hub_accumulate(const float* __restrict__ in, int
   }
 }
 
-// one warp per hub with at most HUB_BIG records
+// One launch for all hub rows.  CTAs [0, HUB_BIG_CTAS): one CTA (8 warps) per hub with more than HUB_BIG
+// records -- warp w sums the 32-record blocks w, w+8, ..., the partials are added in warp order; the other
+// CTAs: one warp per smaller hub.  The big hubs are scheduled first (launch order) and the small ones fill in
+// behind them, so the launch has one tail instead of two.  (Interleaving the two kinds was measured slower.)
+constexpr int HUB_BIG_CTAS = 3 * kNumSMs;
+constexpr int HUB_SMALL_CTAS = 8 * kNumSMs;
 template <int VEC>
-__global__ void __launch_bounds__(256) hub_small_kernel(const float* __restrict__ in, int ld_in,
-                                                        const float* __restrict__ in_rowmax, const int* __restrict__ hdr,
-                                                        const int* __restrict__ hub_beg, const int* __restrict__ hub_deg,
-                                                        const int* __restrict__ hub_src, const float* __restrict__ hub_nrm,
-                                                        float* __restrict__ mlong, float* __restrict__ mlong_bound) {
-  const int lane = threadIdx.x & 31;
-  const int n_hub = hdr[0];
-  const int nw = (gridDim.x * blockDim.x) >> 5;
-  for (int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < n_hub; slot += nw) {
-    const int n = (hub_deg[slot] + 3) & ~3;
-    if (n > HUB_BIG) continue;
-    const int beg = hub_beg[slot];
-    float acc[VEC], bacc = 0.f;
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
-    hub_accumulate<VEC>(in, ld_in, in_rowmax, hub_src + beg, hub_nrm + beg, n, lane, acc, bacc);
-    VecLd<VEC>::st(mlong + (size_t)slot * (32 * VEC) + lane * VEC, acc);
-#pragma unroll
-    for (int o = 16; o; o >>= 1) bacc += __shfl_xor_sync(0xffffffffu, bacc, o);
-    if (lane == 0) mlong_bound[slot] = bacc;
-  }
-}
-
-// one CTA (8 warps) per big hub: warp w sums the 32-record blocks w, w+8, ...; partials added in warp order
-template <int VEC>
-__global__ void __launch_bounds__(256) hub_big_kernel(const float* __restrict__ in, int ld_in,
-                                                      const float* __restrict__ in_rowmax, const int* __restrict__ hdr,
-                                                      const int* __restrict__ big_list, const int* __restrict__ hub_beg,
-                                                      const int* __restrict__ hub_deg, const int* __restrict__ hub_src,
-                                                      const float* __restrict__ hub_nrm, float* __restrict__ mlong,
-                                                      float* __restrict__ mlong_bound) {
+__global__ void __launch_bounds__(256) hub_prepass_kernel(const float* __restrict__ in, int ld_in,
+                                                          const float* __restrict__ in_rowmax, const int* __restrict__ hdr,
+                                                          const int* __restrict__ big_list, const int* __restrict__ hub_beg,
+                                                          const int* __restrict__ hub_deg, const int* __restrict__ hub_src,
+                                                          const float* __restrict__ hub_nrm, float* __restrict__ mlong,
+                                                          float* __restrict__ mlong_bound) {
   constexpr int K = 32 * VEC;
   __shared__ float part[8][K];
   __shared__ float bpart[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (blockIdx.x >= HUB_BIG_CTAS) {
+    const int n_hub = hdr[0];
+    const int nw = (gridDim.x - HUB_BIG_CTAS) * 8;
+    for (int slot = (blockIdx.x - HUB_BIG_CTAS) * 8 + warp; slot < n_hub; slot += nw) {
+      const int n = (hub_deg[slot] + 3) & ~3;
+      if (n > HUB_BIG) continue;
+      const int beg = hub_beg[slot];
+      float acc[VEC], bacc = 0.f;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+      hub_accumulate<VEC>(in, ld_in, in_rowmax, hub_src + beg, hub_nrm + beg, n, lane, acc, bacc);
+      VecLd<VEC>::st(mlong + (size_t)slot * K + lane * VEC, acc);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) bacc += __shfl_xor_sync(0xffffffffu, bacc, o);
+      if (lane == 0) mlong_bound[slot] = bacc;
+    }
+    return;
+  }
   const int n_big = hdr[3];
-  for (int i = blockIdx.x; i < n_big; i += gridDim.x) {
+  for (int i = blockIdx.x; i < n_big; i += HUB_BIG_CTAS) {
     const int slot = big_list[i];
     const int n = (hub_deg[slot] + 3) & ~3, beg = hub_beg[slot];
     float acc[VEC], bacc = 0.f;
@@ -900,12 +898,8 @@ __global__ void __launch_bounds__(256) hub_big_kernel(const float* __restrict__ 
 template <int VEC>
 int hub_prepass_launch(const float* in, int ld_in, const float* in_rowmax, const Plan& pl, float* mlong,
                        float* mlong_bound, cudaStream_t stream) {
-  hub_small_kernel<VEC><<<8 * kNumSMs, 256, 0, stream>>>(in, ld_in, in_rowmax, pl.hdr, pl.hub_beg, pl.hub_deg, pl.hub_src,
-                                                        pl.hub_nrm, mlong, mlong_bound);
-  int rc = check_launch();
-  if (rc != GMETA_OK) return rc;
-  hub_big_kernel<VEC><<<4 * kNumSMs, 256, 0, stream>>>(in, ld_in, in_rowmax, pl.hdr, pl.big_list, pl.hub_beg, pl.hub_deg,
-                                                      pl.hub_src, pl.hub_nrm, mlong, mlong_bound);
+  hub_prepass_kernel<VEC><<<HUB_BIG_CTAS + HUB_SMALL_CTAS, 256, 0, stream>>>(
+      in, ld_in, in_rowmax, pl.hdr, pl.big_list, pl.hub_beg, pl.hub_deg, pl.hub_src, pl.hub_nrm, mlong, mlong_bound);
   return check_launch();
 }
 
@@ -1142,7 +1136,7 @@ int gcn_layer_fwd_pair(const GatherSrc& g, const int32_t* tile_row0, const int32
   const Plan pl = carve_plan(const_cast<void*>(plan), n_tiles, n_tasks, n_rows, n_edges);
   if (cudaMemsetAsync(ws.w_absmax, 0, (size_t)n_copies * 4, stream) != cudaSuccess) return GMETA_ERR_LAUNCH;
   {
-    w_absmax_kernel<<<dim3(8, n_copies), 256, 0, stream>>>(W, w_task_stride, ldw, trans_w, K, N, ws.w_absmax);
+    w_absmax_kernel<<<dim3(32, n_copies), 256, 0, stream>>>(W, w_task_stride, ldw, trans_w, K, N, ws.w_absmax);
     if ((rc = check_launch()) != GMETA_OK) return rc;
     const long long total = (long long)n_copies * (K / 8) * N;
     const int grid = (int)((total + 255) / 256 < 8 * kNumSMs ? (total + 255) / 256 : 8 * kNumSMs);
