@@ -1,0 +1,56 @@
+// Host-side helper of the packing step (no device code): concatenates the per-task CSR arrays of a
+// meta-batch into the packed-set layout (include/gmeta_b200.h) with node / edge offsets applied, on a
+// few host threads.  Replaces the per-task numpy loops of gmeta_b200/packing.py:fill_set, which were the
+// largest part of the end-to-end step once the device work had shrunk below them.  Pure integer work:
+// the reference does the equivalent inside dgl.batch (subgraph_data_processing.py:399-406).
+#include <atomic>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+// dst[i] = src[i] + add  (int32), plain loop: the compiler vectorises it
+inline void add_copy(int32_t* __restrict__ dst, const int32_t* __restrict__ src, int64_t n, int32_t add) {
+  for (int64_t i = 0; i < n; ++i) dst[i] = src[i] + add;
+}
+}  // namespace
+
+extern "C" int gmeta_host_pack_csr(int32_t n_tasks, const int32_t* const* indptr, const int32_t* const* indices,
+                                   const int32_t* const* t_indptr, const int32_t* const* t_indices,
+                                   const int64_t* node_off, const int64_t* edge_off, int32_t* out_indptr,
+                                   int32_t* out_indices, int32_t* out_t_indptr, int32_t* out_t_indices,
+                                   int32_t n_threads) {
+  if (n_tasks < 0 || !node_off || !edge_off || !out_indptr || !out_t_indptr) return GMETA_ERR_BAD_ARG;
+  if (n_tasks > 0 && (!indptr || !indices || !t_indptr || !t_indices)) return GMETA_ERR_BAD_ARG;
+  if (node_off[n_tasks] > 0x7fffffffLL || edge_off[n_tasks] > 0x7fffffffLL) return GMETA_ERR_UNSUPPORTED;
+  out_indptr[0] = 0;
+  out_t_indptr[0] = 0;
+  std::atomic<int> next(0);
+  const int n_units = 4 * n_tasks;      // (task, array) units, handed out dynamically
+  auto work = [&]() {
+    for (int u = next.fetch_add(1); u < n_units; u = next.fetch_add(1)) {
+      const int t = u >> 2;
+      const int64_t a = node_off[t], n = node_off[t + 1] - a, ea = edge_off[t], e = edge_off[t + 1] - ea;
+      switch (u & 3) {
+        case 0: add_copy(out_indptr + a + 1, indptr[t] + 1, n, (int32_t)ea); break;
+        case 1: add_copy(out_t_indptr + a + 1, t_indptr[t] + 1, n, (int32_t)ea); break;
+        case 2: if (e) add_copy(out_indices + ea, indices[t], e, (int32_t)a); break;
+        default: if (e) add_copy(out_t_indices + ea, t_indices[t], e, (int32_t)a); break;
+      }
+    }
+  };
+  int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+  if (nt > 16) nt = 16;
+  if (nt > n_units) nt = n_units;
+  if (nt <= 1) {
+    work();
+    return GMETA_OK;
+  }
+  std::vector<std::thread> pool;
+  pool.reserve(nt - 1);
+  for (int i = 0; i < nt - 1; ++i) pool.emplace_back(work);
+  work();
+  for (auto& th : pool) th.join();
+  return GMETA_OK;
+}

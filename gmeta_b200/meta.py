@@ -285,13 +285,9 @@ class Meta(nn.Module):
             raise RuntimeError("feature width %d does not match the first GraphConv (%d)"
                                % (db.ft.f0, self.spec.conv[0][0]))
         L = len(self.spec.conv)
-        db.ps_s = packing.plan_set(x_spt, c_spt, 0, L)
-        db.ps_q = packing.plan_set(x_qry, c_qry, db.ps_s.end, L)
         if self._staging is None or self._staging.device != dev:
             self._staging = packing.Staging(dev)
-        buf = self._staging.reserve(db.ps_q.end)
-        packing.fill_set(buf, db.ps_s, x_spt, y_spt, c_spt, n_spt, g_spt, db.ft.graph_row_off)
-        packing.fill_set(buf, db.ps_q, x_qry, y_qry, c_qry, n_qry, g_qry, db.ft.graph_row_off)
+        db.ps_s, db.ps_q, _ = packing.pack_meta_batch(self._staging, batch, db.ft.graph_row_off, L, _lib.lib())
         if own_buffer:
             db.ints = torch.empty(db.ps_q.end, dtype=torch.int32, device=dev)
             db.ints.copy_(self._staging.host[:db.ps_q.end], non_blocking=True)

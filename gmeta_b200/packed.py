@@ -63,6 +63,7 @@ class PackedSubgraphBatch(object):
         self.batch_num_nodes = [int(x) for x in batch_num_nodes]
         self.n_nodes = int(indptr.shape[0] - 1)
         self.n_edges = int(indices.shape[0])
+        self.parent_ids = None
 
     @staticmethod
     def batch(subgraphs):
@@ -84,7 +85,10 @@ class PackedSubgraphBatch(object):
             np.add(s.t_indptr[1:], ea, out=t_indptr[a + 1:b + 1])
             np.add(s.indices, a, out=indices[ea:eb])
             np.add(s.t_indices, a, out=t_indices[ea:eb])
-        return PackedSubgraphBatch(indptr, indices, t_indptr, t_indices, ns.tolist())
+        pb = PackedSubgraphBatch(indptr, indices, t_indptr, t_indices, ns.tolist())
+        # parent ids of all nodes in batch order (the n_spt / n_qry lists of an episode, concatenated once here)
+        pb.parent_ids = np.concatenate([s.parent_nid for s in subgraphs]) if len(subgraphs) else np.zeros(0, np.int64)
+        return pb
 
     # duck-typing of the DGL batched graph members the hot path touches
     def to(self, device):

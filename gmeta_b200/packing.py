@@ -181,6 +181,143 @@ def validate_labels(y_spt, y_qry, k_spt):
     return max_classes
 
 
+# ------------------------------------------------------------------------------------------------
+# Fast path used by Meta.upload_batch: same layout and values as plan_set + fill_set, but the bulk
+# CSR concatenation runs in the library on host threads (gmeta_host_pack_csr), the active-row lists
+# are derived once from the PACKED arrays instead of per task, and the parent ids a
+# PackedSubgraphBatch carries from batch time are used instead of re-concatenating the id lists.
+# ------------------------------------------------------------------------------------------------
+def _i32c(a):
+    return a if (a.dtype == np.int32 and a.flags.c_contiguous) else np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _np(x):
+    return x.numpy() if hasattr(x, "numpy") else np.asarray(x)
+
+
+def _plan_base(graphs, centres):
+    ps = PackedSetHost()
+    ps.T = len(graphs)
+    ns = np.array([g.n_nodes for g in graphs], dtype=np.int64)
+    es = np.array([g.n_edges for g in graphs], dtype=np.int64)
+    ss = np.array([len(g.batch_num_nodes) for g in graphs], dtype=np.int64)
+    ps.node_off = np.concatenate([[0], np.cumsum(ns)])
+    ps.edge_off = np.concatenate([[0], np.cumsum(es)])
+    ps.sub_off = np.concatenate([[0], np.cumsum(ss)])
+    ps.N, ps.E, ps.S = int(ps.node_off[-1]), int(ps.edge_off[-1]), int(ps.sub_off[-1])
+    ps.max_rows_per_task = int(ss.max()) if ps.T else 0
+    c0 = centres[0]
+    ps.cps = 2 if (hasattr(c0, "dim") and c0.dim() == 2) or (isinstance(c0, np.ndarray) and c0.ndim == 2) else 1
+    ps.tiles = tile_table(ps.node_off.astype(np.int64))
+    ps.n_tiles = int(ps.tiles[0].shape[0])
+    ps.sizes = {"indptr": ps.N + 1, "indices": ps.E, "t_indptr": ps.N + 1, "t_indices": ps.E,
+                "tile_row0": ps.n_tiles, "tile_nrows": ps.n_tiles, "tile_task": ps.n_tiles,
+                "task_row_ptr": ps.T + 1, "task_sub_ptr": ps.T + 1, "centre_row": ps.S * ps.cps,
+                "feat_row": ps.N, "labels": ps.S, "centre_pos": ps.S * ps.cps}
+    return ps
+
+
+def _act_capacity(ps, n_layers):
+    """Upper bound (int32 elements) of the active-row segments of one set."""
+    per_layer = _al(ps.N) + _al(ps.T + 1) + 3 * _al(ps.N // 128 + ps.T + 1)
+    return n_layers * per_layer
+
+
+def _fill_base(buf, ps, graphs, labels, centres, node_ids, graph_idx, graph_row_off, lib, n_threads):
+    import ctypes as C
+    o, N, E, T = ps.off, ps.N, ps.E, ps.T
+    keep = [[_i32c(getattr(g, k)) for g in graphs] for k in ("indptr", "indices", "t_indptr", "t_indices")]
+    ptrs = [(C.c_void_p * max(T, 1))(*[a.__array_interface__['data'][0] for a in arrs]) for arrs in keep]
+    base = buf.__array_interface__['data'][0]
+    rc = lib.gmeta_host_pack_csr(T, ptrs[0], ptrs[1], ptrs[2], ptrs[3], ps.node_off.ctypes.data, ps.edge_off.ctypes.data,
+                                 base + 4 * o["indptr"], base + 4 * o["indices"], base + 4 * o["t_indptr"],
+                                 base + 4 * o["t_indices"], n_threads)
+    if rc != 0:
+        raise RuntimeError("gmeta_host_pack_csr failed (%d)" % rc)
+    bnn = [np.asarray(g.batch_num_nodes, dtype=np.int64) for g in graphs]
+    sub_first = np.concatenate([np.cumsum(b) - b + ps.node_off[t] for t, b in enumerate(bnn)]) if T else np.zeros(0, np.int64)
+    c_all = np.concatenate([_np(c).astype(np.int64).reshape(len(b), -1) for c, b in zip(centres, bnn)]) if T else \
+        np.zeros((0, ps.cps), np.int64)
+    centre = buf[o["centre_row"]:o["centre_row"] + ps.S * ps.cps]
+    centre[:] = (c_all + sub_first[:, None]).reshape(-1)
+    buf[o["labels"]:o["labels"] + ps.S] = np.concatenate([_np(y) for y in labels]) if T else 0
+    feat_row = buf[o["feat_row"]:o["feat_row"] + N]
+    single_graph = graph_row_off.shape[0] == 1
+    for t, g in enumerate(graphs):
+        a, b = int(ps.node_off[t]), int(ps.node_off[t + 1])
+        ids = getattr(g, "parent_ids", None)
+        # the ids a batch carries from batch time are trusted only if they agree with the id lists on the
+        # first subgraph (the two come from the same sampler call, subgraph_data_processing.py:356-377)
+        if ids is None or ids.shape[0] != b - a or (len(node_ids[t]) and not np.array_equal(
+                ids[:bnn[t][0]], np.asarray(node_ids[t][0], dtype=np.int64))):
+            ids = _flat_ids(node_ids[t])                                      # meta.py:119-120
+        if single_graph:
+            feat_row[a:b] = ids
+        else:
+            feat_row[a:b] = ids + np.repeat(graph_row_off[np.asarray(graph_idx[t], dtype=np.int64)], bnn[t])
+    buf[o["tile_row0"]:o["tile_row0"] + ps.n_tiles] = ps.tiles[0]
+    buf[o["tile_nrows"]:o["tile_nrows"] + ps.n_tiles] = ps.tiles[1]
+    buf[o["tile_task"]:o["tile_task"] + ps.n_tiles] = ps.tiles[2]
+    buf[o["task_row_ptr"]:o["task_row_ptr"] + T + 1] = ps.node_off
+    buf[o["task_sub_ptr"]:o["task_sub_ptr"] + T + 1] = ps.sub_off
+
+
+def _plan_fill_act(buf, ps, off, n_layers):
+    """Active rows per layer from the packed arrays (global sorted row ids are grouped by task because a task
+    is a contiguous row range), their task pointers and tile tables, appended at `off`."""
+    o = ps.off
+    ps.n_layers = n_layers
+    ps.act = [{} for _ in range(n_layers)]
+    if n_layers == 0:
+        return off
+    indptr = buf[o["indptr"]:o["indptr"] + ps.N + 1]
+    indices = buf[o["indices"]:o["indices"] + ps.E]
+    centre = buf[o["centre_row"]:o["centre_row"] + ps.S * ps.cps]
+    flags = np.zeros(ps.N, dtype=np.bool_)       # sorted unique ids through a bitmap: cheaper than sorting
+    flags[centre] = True
+    rows = np.flatnonzero(flags)
+    per_layer = [None] * n_layers
+    per_layer[n_layers - 1] = rows
+    for l in range(n_layers - 1, 0, -1):
+        flags[rows] = False
+        flags[_rows_concat(indptr, indices, rows)] = True
+        rows = np.flatnonzero(flags)
+        per_layer[l - 1] = rows
+    for l in range(n_layers):
+        rows = per_layer[l]
+        tptr = np.searchsorted(rows, ps.node_off).astype(np.int64)
+        tiles = tile_table(tptr)
+        a = {"rows": rows, "task_ptr": tptr, "tiles": tiles, "n": int(rows.shape[0]), "n_tiles": int(tiles[0].shape[0])}
+        ps.act[l] = a
+        for k, arr, n in (("act_rows", rows, a["n"]), ("act_task_ptr", tptr, ps.T + 1), ("act_tile_row0", tiles[0], a["n_tiles"]),
+                          ("act_tile_nrows", tiles[1], a["n_tiles"]), ("act_tile_task", tiles[2], a["n_tiles"])):
+            key = "%s%d" % (k, l)
+            ps.sizes[key] = n
+            o[key] = off
+            buf[off:off + n] = arr
+            off += _al(n)
+    buf[o["centre_pos"]:o["centre_pos"] + ps.S * ps.cps] = np.searchsorted(per_layer[n_layers - 1], centre)
+    return off
+
+
+def pack_meta_batch(staging, batch, graph_row_off, n_layers, lib, n_threads=0):
+    """Pack both sets of a collated meta-batch into the staging buffer; returns (ps_spt, ps_qry, n_int32)."""
+    x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry = batch
+    ps_s, ps_q = _plan_base(x_spt, c_spt), _plan_base(x_qry, c_qry)
+    off = 0
+    for ps in (ps_s, ps_q):
+        for k, n in ps.sizes.items():
+            ps.off[k] = off
+            off += _al(n)
+    buf = staging.reserve(off + _act_capacity(ps_s, n_layers) + _act_capacity(ps_q, n_layers))
+    _fill_base(buf, ps_s, x_spt, y_spt, c_spt, n_spt, g_spt, graph_row_off, lib, n_threads)
+    _fill_base(buf, ps_q, x_qry, y_qry, c_qry, n_qry, g_qry, graph_row_off, lib, n_threads)
+    off = _plan_fill_act(buf, ps_s, off, n_layers)
+    off = _plan_fill_act(buf, ps_q, off, n_layers)
+    ps_s.end = ps_q.end = off
+    return ps_s, ps_q, off
+
+
 class Staging(object):
     """Grow-only pinned host buffer + device buffer for the packed integer arrays."""
 

@@ -212,6 +212,16 @@ int gmeta_gcn_layer_wgrad(const float* in, int32_t ld_in, const int32_t* in_row_
                           float* dW, int64_t dw_task_stride, float* db, int64_t db_task_stride,
                           void* workspace, int64_t workspace_bytes, void* stream);
 
+/* HOST helper (no device work, no stream): packs the per-task CSR arrays of one set of a meta-batch into the
+ * packed-set layout -- out_indptr[node_off[t] + 1 + i] = indptr[t][1 + i] + edge_off[t],
+ * out_indices[edge_off[t] + e] = indices[t][e] + node_off[t], same for the transposed arrays -- on up to
+ * n_threads host threads (0 = hardware concurrency, capped at 16).  What dgl.batch does for the reference
+ * (subgraph_data_processing.py:399-406).  Output pointers are host memory (the pinned staging buffer). */
+int gmeta_host_pack_csr(int32_t n_tasks, const int32_t* const* indptr, const int32_t* const* indices,
+                        const int32_t* const* t_indptr, const int32_t* const* t_indices,
+                        const int64_t* node_off, const int64_t* edge_off, int32_t* out_indptr,
+                        int32_t* out_indices, int32_t* out_t_indptr, int32_t* out_t_indices, int32_t n_threads);
+
 /* Normalised neighbourhood sum alone -- the aggregation half of GraphConv.forward (learner.py:29-32,41-45):
  *   out[i, :f_in] = (scale_dst ? norm[v] : 1) * sum_{(u -> v)} norm[u] * in[map(u), :],  v = dst_rows ? dst_rows[i] : i
  * (columns f_in..ld_out-1 are zeroed).  For the FIRST layer this depends on the graph and the features only,

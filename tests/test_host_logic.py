@@ -246,3 +246,34 @@ def test_product_code_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in src.replace("the oracle", ""), fn
+
+
+@pytest.mark.parametrize("kind", H.TINY_KINDS)
+def test_fast_packing_equals_reference_packing(kind):
+    """Meta.upload_batch's path (threaded gmeta_host_pack_csr + active rows from the packed arrays + parent ids
+    carried by the batch) against the plain per-task numpy packing, segment by segment."""
+    ds = H.tiny_dataset(kind)
+    mb = ds.sample_meta_batch(np.random.default_rng(4), 3)
+    xs, ys, xq, yq, cs, cq, ns, nq, gs, gq = mb
+    L = ds.h
+    goff = np.concatenate([[0], np.cumsum([f.shape[0] for f in ds.feats])])[:-1]
+    st = packing.Staging(torch.device("cpu"))
+    for variant in ("carried ids", "id lists"):
+        if variant == "id lists":
+            for g in xs + xq:
+                g.parent_ids = None
+        ps_s, ps_q, end = packing.pack_meta_batch(st, mb, goff, L, _lib.lib(), n_threads=3)
+        fast = st.host.numpy()
+        for ps, (x, y, c, n, g) in ((ps_s, (xs, ys, cs, ns, gs)), (ps_q, (xq, yq, cq, nq, gq))):
+            ref = packing.plan_set(x, c, 0, L)
+            buf = np.zeros(ref.end, dtype=np.int32)
+            packing.fill_set(buf, ref, x, y, c, n, g, goff)
+            assert (ps.N, ps.E, ps.S, ps.T, ps.n_tiles, ps.cps, ps.max_rows_per_task) == \
+                (ref.N, ref.E, ref.S, ref.T, ref.n_tiles, ref.cps, ref.max_rows_per_task)
+            assert set(ps.sizes) == set(ref.sizes)
+            for k, n_el in ref.sizes.items():
+                assert ps.sizes[k] == n_el, k
+                assert ps.off[k] % 4 == 0 and ps.off[k] + n_el <= end
+                assert np.array_equal(fast[ps.off[k]:ps.off[k] + n_el], buf[ref.off[k]:ref.off[k] + n_el]), (variant, k)
+            for l in range(L):
+                assert ps.act[l]["n"] == ref.act[l]["n"] and ps.act[l]["n_tiles"] == ref.act[l]["n_tiles"]
