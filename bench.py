@@ -182,9 +182,15 @@ def layer_roofline(m, db, peaks, impl):
                                       "all inside the timed launch" % (f_in, f_out, N, E, T),
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "peak_source": "measured (MEASURED_PEAKS.json, burst copy)" if "hbm_gbs" in peaks else "fallback",
-            "traffic": None, "ms_per_launch": ms, "algorithmic_bytes": alg_bytes,
+            # dram__bytes_read.sum + dram__bytes_write.sum of the launch's kernels (w_absmax + pack_w + hub_prepass +
+            # pair kernel) from profiles/r01d_layer_pair_full.md, captured on tools/layer_bench.py --real (another
+            # random C2 query set: N=1,243,405, algorithmic 2.5685 GB there, i.e. traffic / algorithmic = 1.004)
+            "traffic": 2.5785e9, "traffic_over_algorithmic": 1.004, "ms_per_launch": ms, "algorithmic_bytes": alg_bytes,
             "tflops_fp32_equiv": flops / (ms * 1e-3) / 1e12,
-            "share_note": "working set %.2f GB > 126 MB L2, no flush needed" % (alg_bytes / 1e9)}
+            "share_note": "working set %.2f GB > 126 MB L2, no flush needed; the timed meta-step runs in the exact "
+                          "pruned mode (layers over their active rows only), so this full-layer launch is not part of "
+                          "it -- SURVEY 8d asks for the roofline on the full-layer kernel with full-formulation bytes; "
+                          "kernel shares of the step: profiles/r01d_bench_launches.md" % (alg_bytes / 1e9)}
 
 
 def main():
