@@ -224,6 +224,8 @@ def main():
     from gmeta_b200 import dist
     import torch.distributed as td
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: one JSON line only
         dist.init_from_env("nccl")
     from gmeta_b200.meta import Meta
 

@@ -59,6 +59,7 @@ struct TcParams {
   int n_stages;
   int dbg;                   // debug ablation flags (0 in production): 1 skip output stores, 2 skip gather loads, 4 skip MMAs, 8 skip weight copies
   long long* prof;           // optional [gridDim.x][16] cycle counters per role (debug), or NULL
+  int st_tiles;              // row tiles per super-tile (<= ST_TILES); 1 for small launches so that they spread over the SMs
   float* long_scratch;       // per CTA: [ST_ROWS][f_in] aggregated long (hub) rows + 4096 floats of slice partials, L2 resident
 };
 
@@ -167,8 +168,8 @@ __device__ __forceinline__ void producer_sync() { asm volatile("bar.sync 1, %0;"
 
 // every role walks the tiles in the same order: super-tiles round-robin over CTAs, tiles inside
 #define TILE_LOOP_BEGIN                                                                        \
-  for (int st_ = blockIdx.x; st_ < (p.n_tiles + ST_TILES - 1) / ST_TILES; st_ += gridDim.x)    \
-    for (int tile = st_ * ST_TILES; tile < min((st_ + 1) * ST_TILES, p.n_tiles); ++tile) {
+  for (int st_ = blockIdx.x; st_ < (p.n_tiles + p.st_tiles - 1) / p.st_tiles; st_ += gridDim.x)    \
+    for (int tile = st_ * p.st_tiles; tile < min((st_ + 1) * p.st_tiles, p.n_tiles); ++tile) {
 #define TILE_LOOP_END }
 
 struct Smem {
@@ -243,13 +244,13 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const 
     const int g = tid / tpr, cu = tid - g * tpr;    // my group / my 16-byte column unit
     float* scratch = p.long_scratch + (size_t)blockIdx.x * ((size_t)ST_ROWS * f_in + 4 * N_PROD_THREADS * 2);
     float* part = scratch + (size_t)ST_ROWS * f_in; // [group][from-left | to-right][f_in] slice partials
-    const int n_super = (p.n_tiles + ST_TILES - 1) / ST_TILES;
+    const int n_super = (p.n_tiles + p.st_tiles - 1) / p.st_tiles;
     int it = 0;
     long long t_pro = 0, t_wait = 0, t_body = 0, t_mark = clock64();
     auto lap = [&](long long& acc) { const long long now = clock64(); acc += now - t_mark; t_mark = now; };
     for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
-      const int tile0 = st * ST_TILES;
-      const int nt = min(ST_TILES, p.n_tiles - tile0);
+      const int tile0 = st * p.st_tiles;
+      const int nt = min(p.st_tiles, p.n_tiles - tile0);
       // ---- super-tile setup, one row per thread: extents, long flag, short-row neighbour records,
       //      positions in the flattened long-edge list ----
       int w = 0;
@@ -701,7 +702,10 @@ int gcn_layer_fwd_tc(const GatherSrc& g, const int32_t* tile_row0, const int32_t
     cudaFuncSetAttribute(gcn_layer_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_done = true;
   }
-  const int n_super = (n_tiles + ST_TILES - 1) / ST_TILES;
+  // small launches (the pruned meta-step's layers over a few thousand active rows): one tile per CTA, so that
+  // they use as many SMs as they have tiles; large ones amortise the structure prologue over 4 tiles
+  p.st_tiles = n_tiles >= 2 * ST_TILES * kNumSMs ? ST_TILES : (n_tiles >= 2 * kNumSMs ? 2 : 1);
+  const int n_super = (n_tiles + p.st_tiles - 1) / p.st_tiles;
   const int grid = n_super < kNumSMs ? n_super : kNumSMs;
   gcn_layer_fwd_tc_kernel<<<grid, NTHREADS_TC, smem, stream>>>(p);
   return check_launch();
