@@ -44,7 +44,7 @@ class StepArgs(C.Structure):
                 ("update_lr", f32), ("grad_scale", f32), ("compute_meta_grad", i32), ("dense_backward", i32),
                 ("impl", i32), ("pruned_forward", i32),
                 ("meta_grad", vp), ("loss_q", vp), ("acc_q", vp), ("loss_s", vp), ("logits_spt0", vp),
-                ("workspace", vp), ("workspace_bytes", i64)]
+                ("workspace", vp), ("workspace_bytes", i64), ("feat_rowmax", vp)]
 
 
 _SIGNATURES = {

@@ -57,6 +57,13 @@ struct StepBuffers {
   int n_ident;                        // rows of the identity graph
   int32_t* iota;
   float* ones;
+  // full-formulation forwards through the CTA-pair path: structure plans (layer 0 maps rows through feat_row,
+  // the upper layers do not) and the row abs-max chain
+  bool use_ex;
+  void* plan_spt[2];
+  void* plan_qry[2];
+  float* rmax_spt[2];
+  float* rmax_qry[2];
   void* layer_ws;            // weight image of the tensor-core layer kernel
   int64_t layer_ws_bytes;
   int ld[GMETA_MAX_LAYERS];
@@ -139,9 +146,25 @@ void carve(const gmeta_step_args_t* a, void* ws, StepBuffers& b) {
     if (w > b.wgrad_ws_bytes) b.wgrad_ws_bytes = w;
   }
   b.wgrad_ws = c.take<char>(b.wgrad_ws_bytes);
+  b.use_ex = !a->pruned_forward && a->feat_rowmax && (a->impl == GMETA_IMPL_AUTO || a->impl == GMETA_IMPL_TCPAIR);
+  for (int i = 0; i < 2; ++i) {
+    const bool need = b.use_ex && (i == 0 || m.n_layers > 1);
+    b.plan_spt[i] = c.take<char>(need ? gmeta_layer_plan_bytes(a->spt.n_tiles, (int)T, (int)Ns, a->spt.n_edges) : 0);
+    b.plan_qry[i] = c.take<char>(need ? gmeta_layer_plan_bytes(a->qry.n_tiles, (int)T, (int)Nq, a->qry.n_edges) : 0);
+    b.rmax_spt[i] = c.take<float>(need ? Ns : 0);
+    b.rmax_qry[i] = c.take<float>(need ? Nq : 0);
+  }
   b.layer_ws_bytes = 0;
   for (int l = 0; l < m.n_layers; ++l) {
-    const int64_t w = gmeta_gcn_layer_fwd_workspace_bytes((int)T, P, m.f_in[l], m.f_out[l], a->impl);
+    int64_t w = gmeta_gcn_layer_fwd_workspace_bytes((int)T, P, m.f_in[l], m.f_out[l], a->impl);
+    if (b.use_ex) {
+      const int64_t ws = gmeta_gcn_layer_fwd_ex_workspace_bytes((int)T, P, a->spt.n_tiles, (int)Ns, a->spt.n_edges,
+                                                                 m.f_in[l], m.f_out[l], a->impl);
+      const int64_t wq = gmeta_gcn_layer_fwd_ex_workspace_bytes((int)T, P, a->qry.n_tiles, (int)Nq, a->qry.n_edges,
+                                                                 m.f_in[l], m.f_out[l], a->impl);
+      if (ws > w) w = ws;
+      if (wq > w) w = wq;
+    }
     if (w > b.layer_ws_bytes) b.layer_ws_bytes = w;
   }
   b.layer_ws = c.take<char>(b.layer_ws_bytes);
@@ -183,6 +206,20 @@ struct Runner {
       // activations of layer l-1, addressed through row_pos[l-1] (every in-neighbour of an active
       // row of layer l is an active row of layer l-1 by construction)
       const int32_t* map = l == 0 ? set.feat_row : (pruned ? set.row_pos[l - 1] : nullptr);
+      if (b.use_ex) {
+        // every row of every layer (the reference's formulation): CTA-pair tensor-core path where the shape allows,
+        // with the structure plan built once per step and the row abs-max handed from layer to layer
+        const bool is_spt = &set == &a->spt;
+        float* const* rmax = is_spt ? b.rmax_spt : b.rmax_qry;
+        void* const* plan = is_spt ? b.plan_spt : b.plan_qry;
+        run(gmeta_gcn_layer_fwd_ex(in, ld_in, map, nullptr, set.indptr, set.indices, set.norm, set.tile_row0,
+                                   set.tile_nrows, set.tile_task, set.n_tiles, set.n_tasks, W + m.w_off[l], stride,
+                                   m.f_out[l], 0, W + m.b_off[l], stride, m.f_in[l], m.f_out[l], 1, nullptr, act[l],
+                                   b.ld[l], a->impl, b.layer_ws, b.layer_ws_bytes, set.n_nodes, set.n_edges,
+                                   l == 0 ? a->feat_rowmax : rmax[(l - 1) & 1], l + 1 < m.n_layers ? rmax[l & 1] : nullptr,
+                                   plan[l == 0 ? 0 : 1], s));
+        continue;
+      }
       run(gmeta_gcn_layer_fwd(in, ld_in, map, pruned ? set.act_rows[l] : nullptr, set.indptr, set.indices, set.norm,
                               pruned ? set.act_tile_row0[l] : set.tile_row0,
                               pruned ? set.act_tile_nrows[l] : set.tile_nrows,
@@ -323,6 +360,14 @@ extern "C" int gmeta_maml_step(const gmeta_step_args_t* a, void* stream) {
     }
   }
 
+  if (b.use_ex) {
+    for (int i = 0; i < (m.n_layers > 1 ? 2 : 1); ++i) {
+      r.run(gmeta_layer_plan_build(sp.indptr, sp.indices, sp.norm, i == 0 ? sp.feat_row : nullptr, nullptr, sp.tile_row0,
+                                   sp.tile_nrows, sp.tile_task, sp.n_tiles, T, sp.n_nodes, sp.n_edges, b.plan_spt[i], s));
+      r.run(gmeta_layer_plan_build(qr.indptr, qr.indices, qr.norm, i == 0 ? qr.feat_row : nullptr, nullptr, qr.tile_row0,
+                                   qr.tile_nrows, qr.tile_task, qr.n_tiles, T, qr.n_nodes, qr.n_edges, b.plan_qry[i], s));
+    }
+  }
   if (a->pruned_forward) {
     const int n0s = sp.n_act[0], n0q = qr.n_act[0];
     r.run(fill_identity_graph(b.iota, b.ones, b.n_ident, s));

@@ -154,6 +154,10 @@ class FeatureTable(object):
             self.table[r:r + f.shape[0], :self.f0].copy_(torch.from_numpy(np.ascontiguousarray(f)))
             r += f.shape[0]
         self._keep = feat          # keeps id(feat) unique while cached
+        # max |row| of the table, once: input scale bound of the CTA-pair tensor-core layer path
+        self.rowmax = torch.empty(self.table.shape[0], dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib().gmeta_row_absmax(self.table.data_ptr(), self.ld, self.table.shape[0], self.f0,
+                                               self.rowmax.data_ptr(), _stream()), "row_absmax")
 
 
 class _DeviceBatch(object):
@@ -313,6 +317,7 @@ class Meta(nn.Module):
         a.spt = self._c_set(ps_s, base, dev, "s_")
         a.qry = self._c_set(ps_q, base, dev, "q_")
         a.feat_table, a.ld_feat = ft.table.data_ptr(), ft.ld
+        a.feat_rowmax = ft.rowmax.data_ptr()
         a.theta = flat_theta.data_ptr()
         a.update_step, a.n_support, a.max_classes = steps, self.k_spt, db.max_classes
         a.spt_max_rows_per_task, a.qry_max_rows_per_task = ps_s.max_rows_per_task, ps_q.max_rows_per_task

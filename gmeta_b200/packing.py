@@ -167,8 +167,13 @@ def validate_labels(y_spt, y_qry, k_spt):
     for ys, yq in zip(y_spt, y_qry):
         ys = ys.numpy() if hasattr(ys, "numpy") else np.asarray(ys)
         yq = yq.numpy() if hasattr(yq, "numpy") else np.asarray(yq)
-        cs, ns = np.unique(ys, return_counts=True)
-        cq, nq = np.unique(yq, return_counts=True)
+        if ys.size and yq.size and ys.min() >= 0 and yq.min() >= 0 and max(ys.max(), yq.max()) < 4096:
+            ns, nq = np.bincount(ys), np.bincount(yq)      # small non-negative labels: counting beats sorting
+            cs, cq = np.flatnonzero(ns), np.flatnonzero(nq)
+            ns, nq = ns[cs], nq[cq]
+        else:
+            cs, ns = np.unique(ys, return_counts=True)
+            cq, nq = np.unique(yq, return_counts=True)
         if ns.min() < k_spt:
             raise RuntimeError("stack expects each tensor to be equal size: a support class has fewer "
                                "than k_spt=%d members (meta.py:42)" % k_spt)

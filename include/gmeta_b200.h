@@ -345,6 +345,9 @@ typedef struct gmeta_step_args {
   float* logits_spt0;            /* optional [S_spt, n_out]: support logits of step 0 (debug/parity) */
   void* workspace;
   int64_t workspace_bytes;
+  const float* feat_rowmax;      /* optional [rows of feat_table]: max |feat_table[r, :]| (gmeta_row_absmax, once per
+                                    table).  With it the full-formulation forwards (pruned_forward == 0) take the
+                                    CTA-pair tensor-core layer path where the shape allows. */
 } gmeta_step_args_t;
 
 int64_t gmeta_maml_step_workspace_bytes(const gmeta_step_args_t* args);

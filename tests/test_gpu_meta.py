@@ -141,22 +141,28 @@ def test_pruned_forward_equals_full_forward():
     agree to fp32 summation-order noise of the weight-gradient reductions."""
     from gmeta_b200.meta import Meta
     from gmeta_b200.synthetic import make_dataset
-    for name, scale, tasks in (('C1', 0.3, 4), ('C4', 1.0, 3)):
-        ds = make_dataset(name, scale=scale)
-        mb = ds.sample_meta_batch(np.random.default_rng(5), tasks)
-        outs = []
-        for pruned in (False, True):
-            args = ds.args()
-            args.pruned_forward = pruned
-            torch.manual_seed(222)
-            m = Meta(args, ds.config()).to(U.dev())
-            m.return_meta_grad = True
-            accs = m(*mb, ds.feats)
-            outs.append((accs, m.last["loss_q"], [g.clone() for g in m.last["meta_grad"]], m.last["gpu_launches"]))
-        np.testing.assert_allclose(outs[0][0], outs[1][0], atol=1e-6, err_msg=name)
-        assert abs(outs[0][1] - outs[1][1]) < 1e-6, name
-        for k, (a, b) in enumerate(zip(outs[0][2], outs[1][2])):
-            U.report("%s grad[%d] full vs pruned" % (name, k), b, a, 1e-7 + 1e-5 * float(a.abs().max()), 1e-4)
+    # strict: both modes on the same layer kernel (FFMA).  AUTO: the full formulation takes the CTA-pair
+    # path where the shape allows while the pruned mode does not; the two contractions round differently at the
+    # 1e-6 level, which can flip the ReLU of a pre-activation that is ~0 and switch one row's contribution
+    # (~1e-5) to a bias-gradient entry on or off -- hence the looser bound there.
+    for impl, g_atol in ((_lib.IMPL_SIMT, 0.0), (_lib.IMPL_AUTO, 3e-5)):
+        for name, scale, tasks in (('C1', 0.3, 4), ('C4', 1.0, 3)):
+            ds = make_dataset(name, scale=scale)
+            mb = ds.sample_meta_batch(np.random.default_rng(5), tasks)
+            outs = []
+            for pruned in (False, True):
+                args = ds.args()
+                args.pruned_forward = pruned
+                args.impl = impl
+                torch.manual_seed(222)
+                m = Meta(args, ds.config()).to(U.dev())
+                m.return_meta_grad = True
+                accs = m(*mb, ds.feats)
+                outs.append((accs, m.last["loss_q"], [g.clone() for g in m.last["meta_grad"]], m.last["gpu_launches"]))
+            np.testing.assert_allclose(outs[0][0], outs[1][0], atol=1e-6, err_msg=name)
+            assert abs(outs[0][1] - outs[1][1]) < (1e-6 if g_atol == 0.0 else 1e-5), name
+            for k, (a, b) in enumerate(zip(outs[0][2], outs[1][2])):
+                U.report("%s grad[%d] full vs pruned" % (name, k), b, a, g_atol + 1e-7 + 1e-5 * float(a.abs().max()), 1e-4)
 
 
 def test_task_batching_equals_task_by_task():

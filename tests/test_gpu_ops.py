@@ -422,3 +422,33 @@ def test_bad_arguments_return_error_codes():
     x = U.f32(np.zeros((2, 4)))
     with pytest.raises(_lib.GMetaError):
         U.layer_fwd(g, x, U.f32(np.zeros((8, 4))), None, 8, 4)             # ld_in < f_in
+
+
+@pytest.mark.parametrize("f_in", [128, 50, 5, 1])
+def test_aggregate_rows_matches_oracle_aggregation(f_in):
+    """gmeta_aggregate_rows = the aggregation half of GraphConv.forward (learner.py:29-45): n_v * sum n_u x_u over a
+    row subset, through a row map with dropped neighbours, vector and scalar column paths."""
+    rng = np.random.default_rng(31 + f_in)
+    T = 3
+    g, src, dst, trp, x, W, b, _, _ = _random_multitask(rng, T, 500, 3.0, f_in, 16)
+    N = int(trp[-1])
+    keep = rng.random(N) < 0.6
+    pos = np.full(N, -1, dtype=np.int64)
+    pos[keep] = np.arange(int(keep.sum()))
+    ld = (f_in + 3) // 4 * 4
+    xc = np.zeros((int(keep.sum()), ld), dtype=np.float32)
+    xc[:, :f_in] = x[keep]
+    sel = np.sort(rng.choice(N, 700, replace=False))
+    out = torch.full((sel.shape[0], ld), float('nan'), dtype=torch.float32, device=U.dev())
+    for scale_dst in (1, 0):
+        rc = _lib.lib().gmeta_aggregate_rows(U.p(U.f32(xc)), ld, U.p(U.i32(pos)), U.p(U.i32(sel)), U.p(g.indptr), U.p(g.indices),
+                                             U.p(g.norm), sel.shape[0], f_in, scale_dst, U.p(out), ld, U.stream())
+        _lib.check(rc, "aggregate_rows")
+        og = O.OGraph(src, dst, N)
+        norm = torch.pow(og.in_degrees().float().clamp(min=1), -0.5).unsqueeze(1)
+        xz = torch.tensor(np.where(keep[:, None], x, 0.0).astype(np.float32))
+        want = og.aggregate_sum(xz * norm)
+        if scale_dst:
+            want = want * norm
+        U.report("aggregate_rows f_in=%d scale_dst=%d" % (f_in, scale_dst), out[:, :f_in], want[sel], 2e-5, 1e-5)
+        assert torch.all(out[:, f_in:] == 0)
