@@ -116,6 +116,38 @@ def cpu_arm(ds, batch_host, n_tasks, steps, warmup):
                       % (n_tasks, ds.update_step, steps, warmup), "s_per_step": t}
 
 
+def device_extraction(ds, batch, host_s):
+    """h-hop subgraph extraction of one meta-batch's centres on the device (csrc/khop.cu through
+    subgraphs.DeviceExtractor: parent CSR resident in HBM, packed CSR of all subgraphs out) next to the host
+    extractor's time for the same batch.  Reported beside the inner-loop metric, not inside it."""
+    from gmeta_b200.subgraphs import DeviceExtractor
+    xs, ys, xq, yq, cs, cq, ns, nq, gs, gq = batch
+    gi, ca, cb = [], [], []
+    for c_t, n_t, g_t in list(zip(cs, ns, gs)) + list(zip(cq, nq, gq)):
+        c_t = np.asarray(c_t)
+        for k in range(len(n_t)):
+            gi.append(g_t[k])
+            if ds.link_pred:
+                ca.append(int(n_t[k][int(c_t[k][0])]))
+                cb.append(int(n_t[k][int(c_t[k][1])]))
+            else:
+                ca.append(int(n_t[k][int(c_t[k])]))
+    ex = DeviceExtractor(ds.graphs)
+    run = lambda: ex.extract(np.array(gi), np.array(ca), np.array(cb) if ds.link_pred else None, h=ds.h,  # noqa: E731
+                             sample_nodes=ds.sample_nodes)
+    out = run()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        out = run()
+    e1.record()
+    torch.cuda.synchronize()
+    return {"requests": len(gi), "device_ms_per_meta_batch": e0.elapsed_time(e1) / 3, "host_s_per_meta_batch": host_s,
+            "packed_nodes": out["N"], "packed_edges": out["E"],
+            "note": "gmeta_khop_select + gmeta_khop_build for every support and query centre of one meta-batch"}
+
+
 def layer_roofline(m, db, peaks, impl):
     """Time the dominant kernel -- the fused GCN layer (hidden->hidden) over the packed QUERY set
     of the whole meta-batch -- alone, CUDA events on its launch stream, working set > L2."""
@@ -315,6 +347,7 @@ def main():
     if rank != 0:
         return
     roof = layer_roofline(m, dbs[0], peaks, args.kernel_impl)
+    extraction = device_extraction(ds, batches[0], extract_s)
     cb = None
     if not args.no_cpu_baseline:
         cb = cpu_arm(ds, batches[0], max(1, args.cpu_tasks), 3, 1)   # ~10-20 s of host work
@@ -332,6 +365,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cb}
+    if extraction:
+        line["extraction"] = extraction
     if full_steps:
         line["full_formulation"] = {
             "value": tasks * world * full_steps / (ms_full * 1e-3), "unit": UNIT, "ms_per_step": ms_full / full_steps,

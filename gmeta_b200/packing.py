@@ -278,13 +278,16 @@ def _plan_fill_act(buf, ps, off, n_layers):
     indptr = buf[o["indptr"]:o["indptr"] + ps.N + 1]
     indices = buf[o["indices"]:o["indices"] + ps.E]
     centre = buf[o["centre_row"]:o["centre_row"] + ps.S * ps.cps]
-    flags = np.zeros(ps.N, dtype=np.bool_)       # sorted unique ids through a bitmap: cheaper than sorting
-    flags[centre] = True
-    rows = np.flatnonzero(flags)
+    rows = np.unique(centre.astype(np.int64))     # a few thousand centres: sorting is cheap
     per_layer = [None] * n_layers
     per_layer[n_layers - 1] = rows
+    flags = None
     for l in range(n_layers - 1, 0, -1):
-        flags[rows] = False
+        # sorted unique ids of ~10^5 neighbours through a bitmap: cheaper than sorting them
+        if flags is None:
+            flags = np.zeros(ps.N, dtype=np.bool_)
+        else:
+            flags[rows] = False
         flags[_rows_concat(indptr, indices, rows)] = True
         rows = np.flatnonzero(flags)
         per_layer[l - 1] = rows
