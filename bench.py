@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--cpu-tasks", type=int, default=8, help="tasks per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full", action="store_true", help="skip the full-formulation (unpruned) arm")
+    ap.add_argument("--no-device-extract", action="store_true", help="skip the device-extraction end-to-end arm")
     return ap.parse_args()
 
 
@@ -313,6 +314,29 @@ def main():
     ms_e2e = f0.elapsed_time(f1)
     h2d, d2h = m.last["h2d_bytes"], m.last["d2h_bytes"]
 
+    # ---------------- end to end INCLUDING subgraph extraction, meta-batch built in HBM ----------------
+    # Host input per step: centre node ids + labels only (the reference's pre-sampled task lists,
+    # subgraph_data_processing.py:150-292); extraction, batching and the step run on the device.
+    ms_dev, dev_h2d = 0.0, 0
+    if not args.no_device_extract:
+        from gmeta_b200.device_batch import CentreRequests
+        reqs = []
+        for b in batches:
+            xs, ys, xq, yq, cs, cq, ns, nq, gs, gq = b
+            reqs.append((CentreRequests.from_host_batch(xs, cs, ns, gs, ys), CentreRequests.from_host_batch(xq, cq, nq, gq, yq)))
+        for i in range(2):
+            m.forward_device(ds.graphs, reqs[i % len(reqs)][0], reqs[i % len(reqs)][1], ds.feats, ds.h, ds.sample_nodes)
+        barrier()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        for i in range(args.steps):
+            r = reqs[i % len(reqs)]
+            m.forward_device(ds.graphs, r[0], r[1], ds.feats, ds.h, ds.sample_nodes, seed=222 + i)
+        h1.record()
+        barrier()
+        ms_dev = h0.elapsed_time(h1)
+        dev_h2d = m.last["h2d_bytes"]
+
     # ---------------- the reference's formulation (every row of every layer in every forward) ----------------
     # Same meta-step without the exact receptive-field pruning: here the full-layer kernel that `roofline`
     # reports on IS the dominant kernel of the step (its forwards go through the same CTA-pair path).
@@ -336,10 +360,10 @@ def main():
         full_launches = mf.last["gpu_launches"]
         del mf
 
-    t = torch.tensor([ms_total, ms_e2e, ms_full], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms_total, ms_e2e, ms_full, ms_dev], dtype=torch.float64, device="cuda")
     if world > 1:
         td.all_reduce(t, op=td.ReduceOp.MAX)      # max over ranks
-    ms_total, ms_e2e, ms_full = float(t[0]), float(t[1]), float(t[2])
+    ms_total, ms_e2e, ms_full, ms_dev = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     total_tasks = tasks * world * args.steps
     value = total_tasks / (ms_total * 1e-3)
     e2e_value = total_tasks / (ms_e2e * 1e-3)
@@ -367,6 +391,14 @@ def main():
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cb}
     if extraction:
         line["extraction"] = extraction
+    if ms_dev > 0:
+        line["e2e_with_device_extraction"] = {
+            "value": total_tasks / (ms_dev * 1e-3), "unit": UNIT, "ms_per_step": ms_dev / args.steps,
+            "h2d_bytes_per_step": int(dev_h2d), "d2h_bytes_per_step": int(d2h),
+            "note": "Meta.forward_device: host ships centre ids + labels; h-hop extraction (sampling cap by the device "
+                    "hash sampler), batching, transposed CSR, active rows and the whole meta-step on the device; "
+                    "`e2e` above starts from host-extracted subgraphs and excludes the %.2f s per meta-batch the host "
+                    "extractor takes" % extract_s}
     if full_steps:
         line["full_formulation"] = {
             "value": tasks * world * full_steps / (ms_full * 1e-3), "unit": UNIT, "ms_per_step": ms_full / full_steps,

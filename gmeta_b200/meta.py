@@ -233,7 +233,7 @@ class Meta(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ("_staging", "_feat_cache", "_ws", "_scratch"):
+            if k in ("_staging", "_feat_cache", "_ws", "_scratch", "_extractor"):
                 new.__dict__[k] = {} if k == "_scratch" else None
             else:
                 new.__dict__[k] = deepcopy(v, memo)
@@ -301,6 +301,43 @@ class Meta(nn.Module):
             db.ints = self._staging.dev
         db.h2d_bytes = db.ps_q.end * 4
         return db
+
+    def build_batch_on_device(self, graphs, req_spt, req_qry, feat, h, sample_nodes=1000, seed=222):
+        """A meta-batch assembled entirely in HBM (device_batch.py): `graphs` are the dataset's ParentGraphs (their
+        CSR is uploaded once and cached), `req_*` the CentreRequests of the support / query set.  The host ships
+        only centre ids and labels; extraction, batching, the transposed CSR and the active-row lists are device
+        work.  The result is interchangeable with `upload_batch`'s."""
+        from . import device_batch
+        from .subgraphs import DeviceExtractor
+        dev = _dev()
+        key = (id(graphs), len(graphs))
+        if getattr(self, "_extractor", None) is None or self._extractor[0] != key:
+            self._extractor = (key, DeviceExtractor(graphs, dev), graphs)
+        db = _DeviceBatch()
+        db.T = int(req_spt.sub_off.shape[0] - 1)
+        T = db.T
+        split = lambda r: [r.labels[r.sub_off[t]:r.sub_off[t + 1]] for t in range(T)]      # noqa: E731
+        db.max_classes = packing.validate_labels(split(req_spt), split(req_qry), self.k_spt)
+        db.ft = self._features(feat, dev)
+        if db.ft.f0 != self.spec.conv[0][0]:
+            raise RuntimeError("feature width %d does not match the first GraphConv (%d)"
+                               % (db.ft.f0, self.spec.conv[0][0]))
+        db.ps_s, db.ps_q, db.ints = device_batch.build(self._extractor[1], req_spt, req_qry, h, sample_nodes,
+                                                       len(self.spec.conv), seed)
+        db.h2d_bytes = int(8 * (req_spt.graph_idx.shape[0] + req_qry.graph_idx.shape[0]) *
+                           (3 if req_spt.centre_b is not None else 2))
+        return db
+
+    def forward_device(self, graphs, req_spt, req_qry, feat, h, sample_nodes=1000, seed=222):
+        """`forward` for a meta-batch given as centre requests: subgraph extraction included, on the device."""
+        K = self.update_step
+        db = self.build_batch_on_device(graphs, req_spt, req_qry, feat, h, sample_nodes, seed)
+        host = self.step_device(db).cpu()
+        if host[K + 2] != 0:
+            self.meta_optim.step_count -= 1
+        self.last.update({"loss_q": float(host[K + 1]), "skipped": bool(host[K + 2] != 0),
+                          "d2h_bytes": int(host.numel() * 4)})
+        return host[:K + 1].numpy().astype(np.float32)
 
     def _enqueue(self, db, steps, train, flat_theta):
         """Enqueue the whole inner loop for an uploaded meta-batch.  Returns device tensors
