@@ -339,6 +339,18 @@ class Meta(nn.Module):
                           "d2h_bytes": int(host.numel() * 4)})
         return host[:K + 1].numpy().astype(np.float32)
 
+    def finetunning_batch_device(self, graphs, req_spt, req_qry, feat, h, sample_nodes=1000, seed=222):
+        """`finetunning_batch` for episodes given as centre requests (extraction on the device)."""
+        K = self.update_step_test
+        if req_spt.sub_off.shape[0] <= 1:
+            return np.zeros((0, K + 1), dtype=np.float32)
+        db = self.build_batch_on_device(graphs, req_spt, req_qry, feat, h, sample_nodes, seed)
+        theta = self._flat_theta(self.net.parameters(), _dev())
+        acc_q, _, _ = self._enqueue(db, K, False, theta)
+        host = acc_q.cpu()
+        self.last["d2h_bytes"] = int(host.numel() * 4)
+        return host.numpy().astype(np.float32)
+
     def _enqueue(self, db, steps, train, flat_theta):
         """Enqueue the whole inner loop for an uploaded meta-batch.  Returns device tensors
         (acc_q [T,K+1], loss_q [T,K+1], meta_grad [P] or None)."""

@@ -226,6 +226,33 @@ class Subgraphs(Dataset):
     def __len__(self):
         return self.batchsz
 
+    def centre_requests(self, indices):
+        """The tasks `indices` as centre requests for device-side extraction (device_batch.CentreRequests for the
+        support and the query set): graph id, centre node id(s) and label of every item, nothing else -- the
+        subgraphs are then extracted, batched and consumed in HBM (Meta.forward_device).  Labels follow
+        __getitem__ (Disjoint: relabelled 0..n_way-1 in a random order per task, :390-397)."""
+        from .device_batch import CentreRequests
+
+        def half(task, relabel):
+            items = [item for sublist in task for item in sublist]
+            parts = [item.split('_') for item in items]
+            y = np.array([self.subgraph2label[item] for item in items]).astype(np.int64)
+            if relabel is not None:
+                y = np.array([relabel[int(v)] for v in y], dtype=np.int64)
+            cb = [int(p[2]) for p in parts] if self.link_pred_mode else None
+            return [int(p[0]) for p in parts], [int(p[1]) for p in parts], cb, y
+
+        spt, qry = [], []
+        for index in indices:
+            relabel = None
+            if self.task_setup == 'Disjoint':
+                unique = np.unique([self.subgraph2label[item] for sub in self.support_x_batch[index] for item in sub])
+                random.shuffle(unique)
+                relabel = {int(l): k for k, l in enumerate(unique)}
+            spt.append(half(self.support_x_batch[index], relabel))
+            qry.append(half(self.query_x_batch[index], relabel))
+        return CentreRequests.from_tasks(spt), CentreRequests.from_tasks(qry)
+
 
 def collate(samples):
     """List of episodes -> ten lists (one entry per task), as train.py:26-29."""

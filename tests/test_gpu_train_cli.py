@@ -27,8 +27,9 @@ def _cli_dataset(kind):
                            update_step=3, update_lr=0.05, meta_lr=5e-4, task_num=2, sample_nodes=60, update_step_test=4)
 
 
+@pytest.mark.parametrize("device_extract", ['False', 'True'])
 @pytest.mark.parametrize("kind", ['disjoint', 'link'])
-def test_train_cli_runs_and_learns_something_finite(tmp_path, kind, capsys):
+def test_train_cli_runs_and_learns_something_finite(tmp_path, kind, device_extract, capsys):
     train = _load_train()
     ds = _cli_dataset(kind)
     root = data_io.write_synthetic_dataset(str(tmp_path / kind), ds, np.random.default_rng(5), frac=(0.5, 0.25, 0.25))
@@ -38,6 +39,7 @@ def test_train_cli_runs_and_learns_something_finite(tmp_path, kind, capsys):
             "--sample_nodes", str(ds.sample_nodes), "--train_result_report_steps", "1", "--eval_batch", "7"]
     if ds.link_pred:
         argv += ["--link_pred_mode", "True"]
+    argv += ["--device_extract", device_extract]
     accs = train.main(train.parse(argv))
     out = capsys.readouterr().out
     for line in ("There are", "Total trainable tensors:", "------ Start Training ------", "Epoch: 1  Step: 0  training acc:",

@@ -153,7 +153,7 @@ def test_cli_flags_and_defaults_match_the_reference():
                 sample_nodes=1000)                                   # train.py:153-177
     for k, v in want.items():
         assert got[k] == v, k
-    assert set(got) - set(want) == {"eval_batch"}
+    assert set(got) - set(want) == {"eval_batch", "device_extract"}
     a = train.parse(["--data_dir", "x/", "--task_setup", "Shared", "--link_pred", "True", "--hid", "128"])   # prefixes
     assert a.link_pred_mode == 'True' and a.hidden_dim == 128
     cfg = train.build_config([np.zeros((4, 5))], a, 2)                # train.py:67-75
@@ -163,3 +163,28 @@ def test_cli_flags_and_defaults_match_the_reference():
         src = open(os.path.join(ref_loader.REFERENCE_DIR, "train.py")).read()
         flags = set(re.findall(r"add_argument\(['\"]--([a-z_]+)['\"]", src))
         assert flags == set(want)
+
+
+@pytest.mark.parametrize("kind", ['disjoint', 'shared', 'link'])
+def test_centre_requests_describe_the_same_episodes(tmp_path, kind):
+    """Subgraphs.centre_requests (input of the device-side extraction) against __getitem__ of the same tasks."""
+    ds, root = _write(tmp_path, kind, False)
+    info = data_io.load_labels(root)
+    db = Subgraphs(root, 'train', info, n_way=ds.n_way, k_shot=ds.k_spt, k_query=ds.k_qry, batchsz=4, args=_args(ds),
+                   adjs=data_io.load_graphs(root), h=ds.h)
+    _seed(21)
+    eps = [db[i] for i in (2, 0)]
+    _seed(21)
+    req_s, req_q = db.centre_requests([2, 0])
+    for req, (ix, iy, ic, inn, ig) in ((req_s, (0, 1, 4, 6, 8)), (req_q, (2, 3, 5, 7, 9))):
+        assert req.sub_off.tolist() == np.concatenate([[0], np.cumsum([len(e[ig]) for e in eps])]).tolist()
+        assert req.labels.tolist() == [int(v) for e in eps for v in e[iy]]
+        assert req.graph_idx.tolist() == [g for e in eps for g in e[ig]]
+        k = 0
+        for e in eps:
+            for s in range(len(e[ig])):
+                c = np.atleast_1d(e[ic][s].numpy())
+                assert req.centre_a[k] == e[inn][s][int(c[0])]
+                if ds.link_pred:
+                    assert req.centre_b[k] == e[inn][s][int(c[1])]
+                k += 1

@@ -13,6 +13,8 @@ Differences from the reference, all on purpose:
     weights, exactly like the reference's one-by-one deepcopy loop, meta.py:175-234) instead of serially;
   * under torchrun every rank takes the tasks `rank, rank+world, ...` of each meta-batch and the
     meta-gradient is all-reduced once per step; evaluation episodes are sharded the same way;
+  * `--device_extract True` moves the h-hop extraction to the GPU as well (Meta.forward_device): the host then
+    handles item names and labels only;
   * python's `random` is seeded too (the reference leaves it unseeded, so its runs are not reproducible).
 String booleans ('True'/'False') and prefix-abbreviated flags work as in the reference (argparse).
 """
@@ -43,9 +45,22 @@ def build_config(feat, args, labels_num):
     return config
 
 
-def evaluate(maml, db, feat, args):
+def task_index_batches(n, batch, shuffle=True):
+    """Index batches like DataLoader(shuffle=True) draws them (torch's RNG, identical on every rank)."""
+    order = torch.randperm(n).tolist() if shuffle else list(range(n))
+    return [order[i:i + batch] for i in range(0, n, batch)]
+
+
+def evaluate(maml, db, feat, args, graphs=None):
     """Fine-tune on every episode of `db` (meta.py:175-234 per episode), `eval_batch` episodes per
     launch, sharded over ranks; returns the per-episode accuracy rows in dataset order."""
+    if args.device_extract == 'True':
+        rows = []
+        for idx in task_index_batches(len(db), max(1, args.eval_batch)):
+            mine = dist.shard_tasks(len(idx))
+            req_s, req_q = db.centre_requests([idx[i] for i in mine])
+            rows.append(maml.finetunning_batch_device(graphs, req_s, req_q, feat, args.h, args.sample_nodes))
+        return dist.gather_rows(np.concatenate(rows, axis=0))
     loader = DataLoader(db, max(1, args.eval_batch), shuffle=True, num_workers=args.num_workers,
                         collate_fn=collate)
     rows = []
@@ -96,34 +111,44 @@ def main(args):
     s_start = time.time()
     max_memory = 0
     for epoch in range(args.epoch):
-        db = DataLoader(db_train, args.task_num, shuffle=True, num_workers=args.num_workers, collate_fn=collate)
+        if args.device_extract == 'True':
+            # centre ids + labels only: the subgraphs are extracted, batched and consumed in HBM
+            db = ((db_train.centre_requests([idx[i] for i in dist.shard_tasks(len(idx))]), len(idx))
+                  for idx in task_index_batches(len(db_train), args.task_num))
+        else:
+            db = DataLoader(db_train, args.task_num, shuffle=True, num_workers=args.num_workers, collate_fn=collate)
         s_f = time.time()
         s_r = s_f
         for step, batch in enumerate(db):
             data_loading_time = time.time() - (s_r if step >= 1 else s_f)
             s = time.time()
-            if len(batch[0]) < world:            # a trailing meta-batch with fewer tasks than ranks
+            n_tasks = batch[1] if args.device_extract == 'True' else len(batch[0])
+            if n_tasks < world:                  # a trailing meta-batch with fewer tasks than ranks
                 continue
-            maml.global_task_num = len(batch[0])  # meta.py:161 divides by the whole meta-batch's task count
-            accs = maml(*dist.shard_meta_batch(batch), feat)
+            maml.global_task_num = n_tasks        # meta.py:161 divides by the whole meta-batch's task count
+            if args.device_extract == 'True':
+                accs = maml.forward_device(graphs, batch[0][0], batch[0][1], feat, args.h, args.sample_nodes,
+                                           seed=222 + 1000 * epoch + step)
+            else:
+                accs = maml(*dist.shard_meta_batch(batch), feat)
             max_memory = max(max_memory, float(psutil.virtual_memory().used / (1024 ** 3)))
             if step % args.train_result_report_steps == 0:
                 say('Epoch:', epoch + 1, ' Step:', step, ' training acc:', str(accs[-1])[:5], ' time elapsed:',
                     str(time.time() - s)[:5], ' data loading takes:', str(data_loading_time)[:5],
                     ' Memory usage:', str(float(psutil.virtual_memory().used / (1024 ** 3)))[:5])
             s_r = time.time()
-        accs = evaluate(maml, db_val, feat, args).mean(axis=0).astype(np.float16)
+        accs = evaluate(maml, db_val, feat, args, graphs).mean(axis=0).astype(np.float16)
         say('Epoch:', epoch + 1, ' Val acc:', str(accs[-1])[:5])
         if accs[-1] > max_acc:
             max_acc = accs[-1]
             model_max = copy.deepcopy(maml)
 
-    rows = evaluate(maml, db_test, feat, args)
+    rows = evaluate(maml, db_test, feat, args, graphs)
     accs = rows.mean(axis=0).astype(np.float16)
     say('Test acc:', str(accs[1])[:5])
     # the reference keeps appending to the same list (train.py:130-145), so its "early stopped" number
     # averages both test passes; reproduced
-    rows = np.concatenate([rows, evaluate(model_max, db_test, feat, args)], axis=0)
+    rows = np.concatenate([rows, evaluate(model_max, db_test, feat, args, graphs)], axis=0)
     accs = rows.mean(axis=0).astype(np.float16)
     say('Early Stopped Test acc:', str(accs[-1])[:5])
     say('Total Time:', str(time.time() - s_start)[:5])
@@ -162,6 +187,9 @@ def parse(argv=None):
     # not in the reference
     argparser.add_argument('--eval_batch', type=int, default=25,
                            help='validation/test episodes fine-tuned per launch (1 = one by one like the reference)')
+    argparser.add_argument('--device_extract', type=str, default='False',
+                           help="'True': h-hop subgraphs are extracted on the GPU (the host ships centre ids only); "
+                                "the sampling cap then uses the device sampler instead of numpy's")
     return argparser.parse_args(argv)
 
 
