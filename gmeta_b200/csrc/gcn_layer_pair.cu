@@ -29,15 +29,16 @@
 //     that a small edge-parallel kernel aggregates first; the fused kernel then reads a hub like
 //     a single neighbour with weight 1.
 //
-// Warp roles per CTA (704 threads): warps 0..15 gather producers (one row per thread quad,
-// 32-float K chunks, the next chunk's segments requested before the current one is reduced:
-// fp32 sum -> scaled FP16 hi/lo -> 64B-swizzled K-major operand stage), warp 16 weight loader
-// (cp.async.bulk of the pre-split, pre-swizzled image), warp 17 MMA issuer (leader CTA only; one
-// thread), warps 18..21 epilogue (tcgen05.ld, * norm * 2^-e + bias, ReLU, transposed through
-// shared memory so that every store instruction writes whole 128-byte row segments, mask, row
-// abs-max for the next layer).  Hand-offs are mbarriers; the peer CTA signals the leader's
-// barriers through the cluster address space, the MMA thread releases operand stages /
-// accumulators in both CTAs with multicast commits.
+// Warp roles per CTA (640 threads; register budgets re-balanced per warpgroup with setmaxnreg): warps 0..7
+// gather producers (a lane quad owns two rows, 32-float K chunks, the next chunk's segments requested before
+// the current one is reduced: fp32 sum -> scaled FP16 hi/lo -> 64B-swizzled K-major operand stage), warp 12
+// weight loader (cp.async.bulk of the pre-split, pre-swizzled image), warp 13 MMA issuer (leader CTA only; one
+// thread), warps 8..11 and 16..19 epilogue, one column half each (tcgen05.ld with the next block in flight,
+// * norm * 2^-e + bias, ReLU, transposed through shared memory so that a store instruction writes 8 rows x 64
+// contiguous bytes, mask, row abs-max for the next layer).  Hand-offs are mbarriers waited on with the hardware
+// suspend hint; the peer CTA signals the leader's barriers through the cluster address space, the MMA thread
+// releases operand stages / accumulators in both CTAs with multicast commits.  Hub rows are summed beforehand
+// by hub_prepass_kernel (whole chip, one warp per small hub, one CTA per big hub).
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -1069,7 +1070,7 @@ bool gcn_layer_fwd_pair_supported(const GatherSrc& g, int f_out, const float* bi
                                   const float* relu_mask, const float* out, int ld_out, int n_tasks) {
   if (bias && (!aligned16(bias) || b_task_stride % 4 != 0)) return false;
   if (relu_mask && !aligned16(relu_mask)) return false;
-  if (g.f_in != 64 && g.f_in != 128 && g.f_in != 256) return false;   // hub warps: K/8 columns per warp
+  if (g.f_in != 64 && g.f_in != 128 && g.f_in != 256) return false;   // hub pre-pass: K/32 columns per lane
   if (f_out % 16 != 0 || f_out < 16 || f_out > 256) return false;
   if (g.ld_in % 8 != 0 || (reinterpret_cast<uintptr_t>(g.in) & 31u) || g.ld_in < g.f_in) return false;   // 256-bit loads
   if (ld_out % 8 != 0 || (reinterpret_cast<uintptr_t>(out) & 31u)) return false;

@@ -72,3 +72,31 @@ def test_shard_tasks_partitions_every_task_once():
             assert seen == list(range(T))
             sizes = [len(dist.shard_tasks(T, r, world)) for r in range(world)]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _gather_worker(rank, world, port, q):
+    import numpy as np
+    import torch.distributed as td
+    from gmeta_b200 import dist
+    td.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    rows = np.full((rank + 1, 3), float(rank), dtype=np.float32)        # unequal shares: 1 row on rank 0, 2 on rank 1
+    out = dist.gather_rows(rows)
+    q.put((rank, out.tolist(), dist.shard_tasks(5)))
+    td.destroy_process_group()
+
+
+def test_gather_rows_and_task_sharding_world2():
+    """Evaluation episodes are sharded like training tasks and only accuracy rows are exchanged (train.py)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    ps = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for p in ps:
+        p.join(timeout=60)
+    want = [[0.0] * 3, [1.0] * 3, [1.0] * 3]
+    assert got[0][1] == want and got[1][1] == want
+    assert got[0][2] == [0, 2, 4] and got[1][2] == [1, 3]
