@@ -188,3 +188,37 @@ def test_centre_requests_describe_the_same_episodes(tmp_path, kind):
                 if ds.link_pred:
                     assert req.centre_b[k] == e[inn][s][int(c[1])]
                 k += 1
+
+
+@pytest.mark.parametrize("kind", ['disjoint', 'shared', 'link'])
+def test_sampler_against_committed_reference_fixture(tmp_path, kind):
+    """Same check as test_episodes_match_the_unmodified_reference, against tests/golden/sampler_<kind>.json that
+    oracle/make_golden_sampler.py recorded from the reference class -- runs where the reference is not mounted."""
+    import json
+    from oracle import make_golden_sampler as G
+    with open(os.path.join(ROOT, "tests", "golden", "sampler_%s.json" % kind)) as f:
+        gold = json.load(f)
+    root = str(tmp_path / kind)
+    ds = G.write_dataset(kind, root)
+    info = data_io.load_labels(root)
+    G.seed_all(G.SEED_TASKS)
+    ours = Subgraphs(root, 'train', info, n_way=ds.n_way, k_shot=ds.k_spt, k_query=ds.k_qry, batchsz=G.BATCHSZ,
+                     args=G.sampler_args(ds), adjs=data_io.load_graphs(root), h=ds.h)
+    assert ours.support_x_batch == gold["support_x_batch"] and ours.query_x_batch == gold["query_x_batch"]
+    for idx, ep in enumerate(gold["episodes"]):
+        G.seed_all(G.SEED_EP + idx)
+        o = ours[idx]
+        assert o[1].tolist() == ep["y_spt"] and o[3].tolist() == ep["y_qry"]
+        assert list(o[8]) == ep["g_spt"] and list(o[9]) == ep["g_qry"]
+        for (gi, ci, ni), subs in zip(((0, 4, 6), (2, 5, 7)), ep["sets"]):
+            og = o[gi]
+            off = np.concatenate([[0], np.cumsum(og.batch_num_nodes)])
+            odst = np.repeat(np.arange(og.n_nodes), np.diff(og.indptr))
+            assert len(subs) == len(og.batch_num_nodes)
+            for k, sub in enumerate(subs):
+                on = np.asarray(o[ni][k])
+                assert on.tolist() == sub["nodes"]
+                assert on[np.atleast_1d(o[ci][k].numpy())].tolist() == sub["centres"]
+                m = (odst >= off[k]) & (odst < off[k + 1])
+                edges = sorted(zip(on[og.indices[m] - off[k]].tolist(), on[odst[m] - off[k]].tolist()))
+                assert [list(e) for e in edges] == [list(e) for e in sub["edges"]]
