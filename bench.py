@@ -312,6 +312,7 @@ def main():
     barrier()
     sampler.stop_flag = True
     ms_e2e = f0.elapsed_time(f1)
+    host_pack_ms = getattr(m, "host_pack_ms", None)
     h2d, d2h = m.last["h2d_bytes"], m.last["d2h_bytes"]
 
     # ---------------- end to end INCLUDING subgraph extraction, meta-batch built in HBM ----------------
@@ -381,7 +382,7 @@ def main():
                 % (4e-9 * m.last["n_nodes"][1] * ds.hidden_dim * 2, len(batches)),
                 "packed_nodes_spt_qry": m.last["n_nodes"], "packed_edges_spt_qry": m.last["n_edges"],
                 "kernel_impl": {0: "auto", 1: "ffma", 2: "tcgen05-3xtf32"}[args.kernel_impl],
-                "subgraph_extraction_s_per_meta_batch_host": extract_s,
+                "subgraph_extraction_s_per_meta_batch_host": extract_s, "host_pack_ms_last_step": host_pack_ms,
                 "final_accs": [float(a) for a in accs], "loss_q": float(last_out[-2])})
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,

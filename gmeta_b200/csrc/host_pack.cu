@@ -54,3 +54,68 @@ extern "C" int gmeta_host_pack_csr(int32_t n_tasks, const int32_t* const* indptr
   for (auto& th : pool) th.join();
   return GMETA_OK;
 }
+
+// feat_row[node_off[t] + i] = ids[t][i] + goff, goff = the feature-table row of node 0 of the graph the node's
+// subgraph came from: sub_goff[t][k] for the nodes [sub_ptr[t][k], sub_ptr[t][k+1]) (NULL sub_goff: one graph,
+// offset 0).  What meta.py:119-120 does with numpy fancy indexing + vstack per task.
+extern "C" int gmeta_host_pack_feat_rows(int32_t n_tasks, const int64_t* const* ids, const int64_t* const* sub_ptr,
+                                         const int64_t* const* sub_goff, const int32_t* n_sub, const int64_t* node_off,
+                                         int32_t* out_feat_row, int32_t n_threads) {
+  if (n_tasks < 0 || !node_off || !out_feat_row || (n_tasks > 0 && !ids)) return GMETA_ERR_BAD_ARG;
+  if (sub_goff && (!sub_ptr || !n_sub)) return GMETA_ERR_BAD_ARG;
+  std::atomic<int> next(0);
+  auto work = [&]() {
+    for (int t = next.fetch_add(1); t < n_tasks; t = next.fetch_add(1)) {
+      int32_t* dst = out_feat_row + node_off[t];
+      const int64_t n = node_off[t + 1] - node_off[t];
+      const int64_t* src = ids[t];
+      if (!sub_goff) {
+        for (int64_t i = 0; i < n; ++i) dst[i] = (int32_t)src[i];
+      } else {
+        for (int k = 0; k < n_sub[t]; ++k) {
+          const int64_t g = sub_goff[t][k];
+          for (int64_t i = sub_ptr[t][k]; i < sub_ptr[t][k + 1]; ++i) dst[i] = (int32_t)(src[i] + g);
+        }
+      }
+    }
+  };
+  int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+  if (nt > 16) nt = 16;
+  if (nt > n_tasks) nt = n_tasks;
+  if (nt <= 1) {
+    work();
+    return GMETA_OK;
+  }
+  std::vector<std::thread> pool;
+  pool.reserve(nt - 1);
+  for (int i = 0; i < nt - 1; ++i) pool.emplace_back(work);
+  work();
+  for (auto& th : pool) th.join();
+  return GMETA_OK;
+}
+
+// Active rows of one layer from those of the layer above: the sorted distinct in-neighbours of `rows`
+// (packed CSR by destination), through a caller-owned zeroed byte map of n_nodes entries (left zeroed again).
+// Returns the count (<= capacity of out_rows = n_nodes), or a negative error.
+extern "C" int64_t gmeta_host_active_in_neighbours(const int32_t* indptr, const int32_t* indices, const int64_t* rows,
+                                                   int64_t n_rows, int64_t n_nodes, uint8_t* flags, int64_t* out_rows) {
+  if (n_rows < 0 || n_nodes < 0 || (n_rows > 0 && (!indptr || !indices || !rows)) || !flags || !out_rows)
+    return GMETA_ERR_BAD_ARG;
+  int64_t lo = n_nodes, hi = -1;
+  for (int64_t i = 0; i < n_rows; ++i) {
+    const int64_t v = rows[i];
+    for (int32_t e = indptr[v]; e < indptr[v + 1]; ++e) {
+      const int32_t u = indices[e];
+      flags[u] = 1;
+      if (u < lo) lo = u;
+      if (u > hi) hi = u;
+    }
+  }
+  int64_t n = 0;
+  for (int64_t u = lo; u <= hi; ++u)
+    if (flags[u]) {
+      out_rows[n++] = u;
+      flags[u] = 0;
+    }
+  return n;
+}

@@ -12,6 +12,8 @@ parent id instead of on the CPU every step (meta.py:119-120).  No CPU fallback.
 import ctypes as C
 from copy import deepcopy
 
+import time
+
 import numpy as np
 import torch
 from torch import nn
@@ -291,7 +293,9 @@ class Meta(nn.Module):
         L = len(self.spec.conv)
         if self._staging is None or self._staging.device != dev:
             self._staging = packing.Staging(dev)
+        t0 = time.perf_counter()
         db.ps_s, db.ps_q, _ = packing.pack_meta_batch(self._staging, batch, db.ft.graph_row_off, L, _lib.lib())
+        self.host_pack_ms = 1e3 * (time.perf_counter() - t0)
         if own_buffer:
             db.ints = torch.empty(db.ps_q.end, dtype=torch.int32, device=dev)
             db.ints.copy_(self._staging.host[:db.ps_q.end], non_blocking=True)

@@ -246,20 +246,30 @@ def _fill_base(buf, ps, graphs, labels, centres, node_ids, graph_idx, graph_row_
     centre = buf[o["centre_row"]:o["centre_row"] + ps.S * ps.cps]
     centre[:] = (c_all + sub_first[:, None]).reshape(-1)
     buf[o["labels"]:o["labels"] + ps.S] = np.concatenate([_np(y) for y in labels]) if T else 0
-    feat_row = buf[o["feat_row"]:o["feat_row"] + N]
     single_graph = graph_row_off.shape[0] == 1
+    all_ids = []
     for t, g in enumerate(graphs):
-        a, b = int(ps.node_off[t]), int(ps.node_off[t + 1])
         ids = getattr(g, "parent_ids", None)
         # the ids a batch carries from batch time are trusted only if they agree with the id lists on the
         # first subgraph (the two come from the same sampler call, subgraph_data_processing.py:356-377)
-        if ids is None or ids.shape[0] != b - a or (len(node_ids[t]) and not np.array_equal(
-                ids[:bnn[t][0]], np.asarray(node_ids[t][0], dtype=np.int64))):
-            ids = _flat_ids(node_ids[t])                                      # meta.py:119-120
-        if single_graph:
-            feat_row[a:b] = ids
-        else:
-            feat_row[a:b] = ids + np.repeat(graph_row_off[np.asarray(graph_idx[t], dtype=np.int64)], bnn[t])
+        if ids is None or ids.shape[0] != g.n_nodes or ids.dtype != np.int64 or not ids.flags.c_contiguous or (
+                len(node_ids[t]) and not np.array_equal(ids[:bnn[t][0]], np.asarray(node_ids[t][0], dtype=np.int64))):
+            ids = np.ascontiguousarray(_flat_ids(node_ids[t]))                # meta.py:119-120
+        all_ids.append(ids)
+    vpa = lambda arrs: (C.c_void_p * max(T, 1))(*[a.__array_interface__['data'][0] for a in arrs])   # noqa: E731
+    if single_graph:
+        sub_ptr = sub_goff = n_sub = None
+        rc = lib.gmeta_host_pack_feat_rows(T, vpa(all_ids), None, None, None, ps.node_off.ctypes.data,
+                                           base + 4 * o["feat_row"], n_threads)
+    else:
+        sub_ptr = [np.concatenate([[0], np.cumsum(b)]).astype(np.int64) for b in bnn]
+        sub_goff = [np.ascontiguousarray(graph_row_off[np.asarray(graph_idx[t], dtype=np.int64)], dtype=np.int64)
+                    for t in range(T)]
+        n_sub = np.array([len(b) for b in bnn], dtype=np.int32)
+        rc = lib.gmeta_host_pack_feat_rows(T, vpa(all_ids), vpa(sub_ptr), vpa(sub_goff), n_sub.ctypes.data,
+                                           ps.node_off.ctypes.data, base + 4 * o["feat_row"], n_threads)
+    if rc != 0:
+        raise RuntimeError("gmeta_host_pack_feat_rows failed (%d)" % rc)
     buf[o["tile_row0"]:o["tile_row0"] + ps.n_tiles] = ps.tiles[0]
     buf[o["tile_nrows"]:o["tile_nrows"] + ps.n_tiles] = ps.tiles[1]
     buf[o["tile_task"]:o["tile_task"] + ps.n_tiles] = ps.tiles[2]
@@ -267,7 +277,7 @@ def _fill_base(buf, ps, graphs, labels, centres, node_ids, graph_idx, graph_row_
     buf[o["task_sub_ptr"]:o["task_sub_ptr"] + T + 1] = ps.sub_off
 
 
-def _plan_fill_act(buf, ps, off, n_layers):
+def _plan_fill_act(buf, ps, off, n_layers, lib=None):
     """Active rows per layer from the packed arrays (global sorted row ids are grouped by task because a task
     is a contiguous row range), their task pointers and tile tables, appended at `off`."""
     o = ps.off
@@ -283,13 +293,21 @@ def _plan_fill_act(buf, ps, off, n_layers):
     per_layer[n_layers - 1] = rows
     flags = None
     for l in range(n_layers - 1, 0, -1):
-        # sorted unique ids of ~10^5 neighbours through a bitmap: cheaper than sorting them
+        # sorted distinct in-neighbours of ~10^3-10^5 rows through a byte map: cheaper than sorting them
         if flags is None:
-            flags = np.zeros(ps.N, dtype=np.bool_)
+            flags = np.zeros(ps.N, dtype=np.uint8)
+            scratch = np.empty(ps.N, dtype=np.int64)
+        if lib is not None:
+            rows = np.ascontiguousarray(rows, dtype=np.int64)
+            n = lib.gmeta_host_active_in_neighbours(indptr.ctypes.data, indices.ctypes.data, rows.ctypes.data,
+                                                    rows.shape[0], ps.N, flags.ctypes.data, scratch.ctypes.data)
+            if n < 0:
+                raise RuntimeError("gmeta_host_active_in_neighbours failed (%d)" % n)
+            rows = scratch[:n].copy()
         else:
-            flags[rows] = False
-        flags[_rows_concat(indptr, indices, rows)] = True
-        rows = np.flatnonzero(flags)
+            flags[_rows_concat(indptr, indices, rows)] = 1
+            rows = np.flatnonzero(flags)
+            flags[rows] = 0
         per_layer[l - 1] = rows
     for l in range(n_layers):
         rows = per_layer[l]
@@ -320,8 +338,8 @@ def pack_meta_batch(staging, batch, graph_row_off, n_layers, lib, n_threads=0):
     buf = staging.reserve(off + _act_capacity(ps_s, n_layers) + _act_capacity(ps_q, n_layers))
     _fill_base(buf, ps_s, x_spt, y_spt, c_spt, n_spt, g_spt, graph_row_off, lib, n_threads)
     _fill_base(buf, ps_q, x_qry, y_qry, c_qry, n_qry, g_qry, graph_row_off, lib, n_threads)
-    off = _plan_fill_act(buf, ps_s, off, n_layers)
-    off = _plan_fill_act(buf, ps_q, off, n_layers)
+    off = _plan_fill_act(buf, ps_s, off, n_layers, lib)
+    off = _plan_fill_act(buf, ps_q, off, n_layers, lib)
     ps_s.end = ps_q.end = off
     return ps_s, ps_q, off
 

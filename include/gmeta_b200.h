@@ -222,6 +222,17 @@ int gmeta_host_pack_csr(int32_t n_tasks, const int32_t* const* indptr, const int
                         const int64_t* node_off, const int64_t* edge_off, int32_t* out_indptr,
                         int32_t* out_indices, int32_t* out_t_indptr, int32_t* out_t_indices, int32_t n_threads);
 
+/* HOST helpers of the same packing step.  gmeta_host_pack_feat_rows: feat_row[node_off[t] + i] = ids[t][i] + the
+ * feature-table offset of the node's graph (sub_goff[t][k] for the nodes [sub_ptr[t][k], sub_ptr[t][k+1]) of task t;
+ * NULL sub_goff = one graph) -- the per-task feature gather of meta.py:119-120 as an index.
+ * gmeta_host_active_in_neighbours: sorted distinct in-neighbours of `rows` in the packed CSR (the rows of layer l-1
+ * the rows of layer l depend on); `flags` is a zeroed n_nodes-byte scratch map, returned zeroed; returns the count. */
+int gmeta_host_pack_feat_rows(int32_t n_tasks, const int64_t* const* ids, const int64_t* const* sub_ptr,
+                              const int64_t* const* sub_goff, const int32_t* n_sub, const int64_t* node_off,
+                              int32_t* out_feat_row, int32_t n_threads);
+int64_t gmeta_host_active_in_neighbours(const int32_t* indptr, const int32_t* indices, const int64_t* rows,
+                                        int64_t n_rows, int64_t n_nodes, uint8_t* flags, int64_t* out_rows);
+
 /* Normalised neighbourhood sum alone -- the aggregation half of GraphConv.forward (learner.py:29-32,41-45):
  *   out[i, :f_in] = (scale_dst ? norm[v] : 1) * sum_{(u -> v)} norm[u] * in[map(u), :],  v = dst_rows ? dst_rows[i] : i
  * (columns f_in..ld_out-1 are zeroed).  For the FIRST layer this depends on the graph and the features only,
