@@ -100,10 +100,10 @@ def pack_set_on_device(extractor, req, h, sample_nodes, n_layers, seed):
     t_indptr[1:] = torch.cumsum(torch.bincount(indices.long(), minlength=N), 0).to(torch.int32)
     centre = out["centre_row"][:ps.S * ps.cps]
     seg = {"indptr": indptr, "indices": indices, "t_indptr": t_indptr, "t_indices": t_indices,
-           "tile_row0": torch.as_tensor(ps.tiles[0], device=dev), "tile_nrows": torch.as_tensor(ps.tiles[1], device=dev),
-           "tile_task": torch.as_tensor(ps.tiles[2], device=dev), "task_row_ptr": node_off_dev.to(torch.int32),
-           "task_sub_ptr": sub_off_dev.to(torch.int32), "centre_row": centre, "feat_row": out["feat_row"][:N],
-           "labels": torch.as_tensor(req.labels.astype(np.int32), device=dev)}
+           "centre_row": centre, "feat_row": out["feat_row"][:N]}
+    # small host-derived segments: shipped with ONE copy per meta-batch (build())
+    hseg = {"tile_row0": ps.tiles[0], "tile_nrows": ps.tiles[1], "tile_task": ps.tiles[2], "task_row_ptr": ps.node_off,
+            "task_sub_ptr": req.sub_off, "labels": req.labels}
     # active rows per layer: centres, then the in-neighbours of the layer above (sorted global row ids are grouped
     # by task because a task is a contiguous row range)
     ps.n_layers = n_layers
@@ -120,29 +120,40 @@ def pack_set_on_device(extractor, req, h, sample_nodes, n_layers, seed):
             tiles = tile_table(tptr[l].astype(np.int64))
             ps.act[l] = {"n": int(per_layer[l].shape[0]), "n_tiles": int(tiles[0].shape[0])}
             seg["act_rows%d" % l] = per_layer[l].to(torch.int32)
-            seg["act_task_ptr%d" % l] = torch.as_tensor(tptr[l].astype(np.int32), device=dev)
+            hseg["act_task_ptr%d" % l] = tptr[l]
             for k, arr in zip(("act_tile_row0", "act_tile_nrows", "act_tile_task"), tiles):
-                seg["%s%d" % (k, l)] = torch.as_tensor(arr, device=dev)
+                hseg["%s%d" % (k, l)] = arr
         seg["centre_pos"] = torch.searchsorted(per_layer[n_layers - 1], centre.long()).to(torch.int32)
     else:
         seg["centre_pos"] = torch.zeros_like(centre)
-    ps.sizes = {k: int(v.shape[0]) for k, v in seg.items()}
-    return ps, seg
+    ps.sizes = {k: int(v.shape[0]) for k, v in list(hseg.items()) + list(seg.items())}
+    return ps, seg, hseg
 
 
 def build(extractor, req_spt, req_qry, h, sample_nodes, n_layers, seed=222):
     """Both sets of a meta-batch -> (ps_spt, ps_qry, one int32 device buffer holding every segment)."""
     sets = [pack_set_on_device(extractor, r, h, sample_nodes, n_layers, seed + 7919 * i)
             for i, r in enumerate((req_spt, req_qry))]
+    # layout: [host-derived small segments of both sets | device-derived segments of both sets]
     off = 0
-    for ps, seg in sets:
+    for ps, seg, hseg in sets:
+        for k in hseg:
+            ps.off[k] = off
+            off += packing._al(ps.sizes[k])
+    n_host = off
+    for ps, seg, hseg in sets:
         for k in seg:
             ps.off[k] = off
             off += packing._al(ps.sizes[k])
-    ints = torch.zeros(max(off, 4), dtype=torch.int32, device=extractor.dev)
-    for ps, seg in sets:
+    host = np.zeros(max(n_host, 4), dtype=np.int32)
+    for ps, seg, hseg in sets:
+        for k, v in hseg.items():
+            host[ps.off[k]:ps.off[k] + ps.sizes[k]] = v
+    ints = torch.empty(max(off, 4), dtype=torch.int32, device=extractor.dev)
+    ints[:host.shape[0]].copy_(torch.from_numpy(host))                      # the batch's one host->device copy of structure
+    for ps, seg, hseg in sets:
         for k, v in seg.items():
             if ps.sizes[k]:
-                ints[ps.off[k]:ps.off[k] + ps.sizes[k]] = v.to(torch.int32)
+                ints[ps.off[k]:ps.off[k] + ps.sizes[k]] = v
         ps.end = off
     return sets[0][0], sets[1][0], ints
