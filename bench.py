@@ -66,32 +66,63 @@ def workload_desc(ds, tasks):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed regions (B200_PROFILING.md): NVML polled every few
+    milliseconds (the timed region of a 10-step run is only ~60 ms), nvidia-smi as the fallback."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.stop_flag = index, False
+        self.sm, self.mx, self.reasons, self.source = [], [], set(), "nvml"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nv, self.source = None, "nvidia-smi"
 
-    def run(self):
+    def _nvml_sample(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        mask = int(get(self.h))
+        for bit, name in ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
+                          (0x4, "sw_power_cap")):
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _smi_sample(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+        r = [c.strip() for c in out.stdout.strip().split(",")]
+        if len(r) >= 7 and r[0].replace('.', '').isdigit():
+            self.sm.append(float(r[0]))
+            self.mx.append(float(r[1]))
+            for i in range(4):
+                if r[3 + i].startswith("Active"):
+                    self.reasons.add(self.NAMES[i])
+
+    def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+                if self.nv is not None:
+                    self._nvml_sample()
+                else:
+                    self._smi_sample()
             except Exception:
-                pass
-            time.sleep(0.1)
+                if self.nv is not None:           # NVML query failed: fall back for the rest of the run
+                    self.nv, self.source = None, "nvidia-smi"
+            time.sleep(0.005 if self.nv is not None else 0.1)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].startswith("Active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
 def cpu_arm(ds, batch_host, n_tasks, steps, warmup):
