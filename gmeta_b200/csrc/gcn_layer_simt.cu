@@ -370,66 +370,116 @@ using namespace gmeta;
 
 namespace gmeta {
 namespace {
-// one warp per output row: out[i, c] = (scale_dst ? norm[v] : 1) * sum_e norm[u_e] * in[map(u_e), c], v = dst_rows ? dst_rows[i] : i.
-// Edge records are loaded coalesced (one per lane) and broadcast; eight row segments are in flight per lane;
-// summation follows edge order (deterministic).  Columns [f_in, ld_out) are written as zero.
+// out[i, c] = (scale_dst ? norm[v] : 1) * sum_e norm[u_e] * in[map(u_e), c], v = dst_rows ? dst_rows[i] : i.
+// A CTA (8 warps) takes 8 consecutive rows.  Rows with at most AGG_LONG in-edges: one warp per row, edge records
+// loaded coalesced (one per lane) and broadcast, eight row segments in flight per lane.  Longer rows (the hubs of
+// a 2-hop subgraph: up to ~1000 in-edges) would serialise one warp for tens of microseconds, so they are
+// summed afterwards by the whole CTA -- warp w takes the 32-record blocks w, w+8, ... and the eight partials are
+// added in warp order.  Summation order is fixed either way (deterministic).  Columns [f_in, ld_out) are zeroed.
+constexpr int AGG_LONG = 64;
+
+// acc += sum over the 32-record blocks b0, b0 + stride, ... < end of norm[u] * in[map(u), kcol .. kcol+3]
 template <bool VEC>
-__global__ void __launch_bounds__(256) aggregate_rows_kernel(GatherSrc g, int n_rows, int scale_dst,
-                                                             float* __restrict__ out, int ld_out) {
-  const int lane = threadIdx.x & 31;
-  const int nw = (gridDim.x * blockDim.x) >> 5;
-  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_rows; i += nw) {
-    const int v = g.dst_rows ? g.dst_rows[i] : i;
-    const int beg = g.indptr[v], end = g.indptr[v + 1];
-    const float nv = scale_dst ? g.norm[v] : 1.f;
-    for (int c0 = 0; c0 < ld_out; c0 += 128) {
-      const int kcol = c0 + 4 * lane;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int base = beg; base < end; base += 32) {
-        int u_src = 0;
-        float u_norm = 0.f;
-        if (base + lane < end) {
-          const int u = g.indices[base + lane];
-          u_norm = g.norm[u];
-          u_src = g.in_row_map ? g.in_row_map[u] : u;
-          if (u_src < 0) { u_src = 0; u_norm = 0.f; }
-        }
-        const int cnt = min(32, end - base);
-        for (int j0 = 0; j0 < cnt; j0 += 8) {
-          float4 x[8];
-          float w[8];
+__device__ __forceinline__ void agg_accumulate(const GatherSrc& g, int b0, int end, int stride, int kcol, int lane,
+                                               float4& acc) {
+  for (int base = b0; base < end; base += stride) {
+    int u_src = 0;
+    float u_norm = 0.f;
+    if (base + lane < end) {
+      const int u = g.indices[base + lane];
+      u_norm = g.norm[u];
+      u_src = g.in_row_map ? g.in_row_map[u] : u;
+      if (u_src < 0) { u_src = 0; u_norm = 0.f; }
+    }
+    const int cnt = min(32, end - base);
+    for (int j0 = 0; j0 < cnt; j0 += 8) {
+      float4 x[8];
+      float w[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int src = __shfl_sync(0xffffffffu, u_src, (j0 + j) & 31);
-            w[j] = __shfl_sync(0xffffffffu, u_norm, (j0 + j) & 31);
-            if (j0 + j >= cnt) w[j] = 0.f;
-            x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (w[j] != 0.f && kcol < g.f_in) {
-              const float* p = g.in + (size_t)src * g.ld_in + kcol;
-              if (VEC) {
-                x[j] = ld_f4(p);
-              } else {
-                x[j].x = p[0];
-                if (kcol + 1 < g.f_in) x[j].y = p[1];
-                if (kcol + 2 < g.f_in) x[j].z = p[2];
-                if (kcol + 3 < g.f_in) x[j].w = p[3];
-              }
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            acc.x = fmaf(w[j], x[j].x, acc.x);
-            acc.y = fmaf(w[j], x[j].y, acc.y);
-            acc.z = fmaf(w[j], x[j].z, acc.z);
-            acc.w = fmaf(w[j], x[j].w, acc.w);
+      for (int j = 0; j < 8; ++j) {
+        const int src = __shfl_sync(0xffffffffu, u_src, (j0 + j) & 31);
+        w[j] = __shfl_sync(0xffffffffu, u_norm, (j0 + j) & 31);
+        if (j0 + j >= cnt) w[j] = 0.f;
+        x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (w[j] != 0.f && kcol < g.f_in) {
+          const float* p = g.in + (size_t)src * g.ld_in + kcol;
+          if (VEC) {
+            x[j] = ld_f4(p);
+          } else {
+            x[j].x = p[0];
+            if (kcol + 1 < g.f_in) x[j].y = p[1];
+            if (kcol + 2 < g.f_in) x[j].z = p[2];
+            if (kcol + 3 < g.f_in) x[j].w = p[3];
           }
         }
       }
-      if (kcol < ld_out) {
-        float r[4] = {acc.x * nv, acc.y * nv, acc.z * nv, acc.w * nv};
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (kcol + k < ld_out) out[(size_t)i * ld_out + kcol + k] = kcol + k < g.f_in ? r[k] : 0.f;
+      for (int j = 0; j < 8; ++j) {
+        acc.x = fmaf(w[j], x[j].x, acc.x);
+        acc.y = fmaf(w[j], x[j].y, acc.y);
+        acc.z = fmaf(w[j], x[j].z, acc.z);
+        acc.w = fmaf(w[j], x[j].w, acc.w);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void agg_store(const GatherSrc& g, float* __restrict__ out, int ld_out, int i, int kcol,
+                                          float4 acc, float nv) {
+  if (kcol >= ld_out) return;
+  const float r[4] = {acc.x * nv, acc.y * nv, acc.z * nv, acc.w * nv};
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (kcol + k < ld_out) out[(size_t)i * ld_out + kcol + k] = kcol + k < g.f_in ? r[k] : 0.f;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) aggregate_rows_kernel(GatherSrc g, int n_rows, int scale_dst,
+                                                             float* __restrict__ out, int ld_out) {
+  __shared__ int long_rows[8];
+  __shared__ int n_long;
+  __shared__ float4 part[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int row0 = blockIdx.x * 8; row0 < n_rows; row0 += gridDim.x * 8) {
+    if (threadIdx.x == 0) n_long = 0;
+    __syncthreads();
+    const int i = row0 + warp;
+    if (i < n_rows) {
+      const int v = g.dst_rows ? g.dst_rows[i] : i;
+      const int beg = g.indptr[v], end = g.indptr[v + 1];
+      if (end - beg > AGG_LONG) {
+        if (lane == 0) long_rows[atomicAdd(&n_long, 1)] = i;     // the order of this list does not affect any value
+      } else {
+        const float nv = scale_dst ? g.norm[v] : 1.f;
+        for (int c0 = 0; c0 < ld_out; c0 += 128) {
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          agg_accumulate<VEC>(g, beg, end, 32, c0 + 4 * lane, lane, acc);
+          agg_store(g, out, ld_out, i, c0 + 4 * lane, acc, nv);
+        }
+      }
+    }
+    __syncthreads();
+    const int nl = n_long;
+    for (int q = 0; q < nl; ++q) {
+      const int il = long_rows[q];
+      const int v = g.dst_rows ? g.dst_rows[il] : il;
+      const int beg = g.indptr[v], end = g.indptr[v + 1];
+      const float nv = scale_dst ? g.norm[v] : 1.f;
+      for (int c0 = 0; c0 < ld_out; c0 += 128) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        agg_accumulate<VEC>(g, beg + 32 * warp, end, 256, c0 + 4 * lane, lane, acc);
+        part[warp][lane] = acc;
+        __syncthreads();
+        if (warp == 0) {
+          float4 t = part[0][lane];
+#pragma unroll
+          for (int w = 1; w < 8; ++w) {
+            const float4 p = part[w][lane];
+            t.x += p.x; t.y += p.y; t.z += p.z; t.w += p.w;
+          }
+          agg_store(g, out, ld_out, il, c0 + 4 * lane, t, nv);
+        }
+        __syncthreads();
       }
     }
   }

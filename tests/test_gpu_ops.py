@@ -438,7 +438,7 @@ def test_aggregate_rows_matches_oracle_aggregation(f_in):
     ld = (f_in + 3) // 4 * 4
     xc = np.zeros((int(keep.sum()), ld), dtype=np.float32)
     xc[:, :f_in] = x[keep]
-    sel = np.sort(rng.choice(N, 700, replace=False))
+    sel = np.unique(np.concatenate([rng.choice(N, 700, replace=False), trp[:-1]]))   # incl. the hubs (> 64 in-edges: CTA path)
     out = torch.full((sel.shape[0], ld), float('nan'), dtype=torch.float32, device=U.dev())
     for scale_dst in (1, 0):
         rc = _lib.lib().gmeta_aggregate_rows(U.p(U.f32(xc)), ld, U.p(U.i32(pos)), U.p(U.i32(sel)), U.p(g.indptr), U.p(g.indices),
