@@ -289,8 +289,9 @@ def main():
     from gmeta_b200 import dist
     import torch.distributed as td
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: one JSON line only
+        # NCCL writes its version banner / debug lines to stdout by default: send them to stderr so that stdout
+        # carries the one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_from_env("nccl")
     from gmeta_b200.meta import Meta
 
