@@ -258,8 +258,29 @@ def layer_roofline(m, db, peaks, impl):
                           "kernel shares of the step: profiles/r01d_bench_launches.md" % (alg_bytes / 1e9)}
 
 
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    """stdout must carry the ONE JSON line only, but libraries print there too (NCCL's version banner, dataset
+    builders): keep a private handle on the real stdout for the result and point fd 1 at stderr for everybody else."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def emit(line):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -275,13 +296,12 @@ def main():
         cb = cpu_arm(ds, batch, n_tasks, steps, warmup)
         cfg = workload_desc(ds, n_tasks)
         cfg["note"] = "reference CPU path = oracle port (the reference's own files need DGL, absent here)"
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
+        emit({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
                           "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
                           "ms_per_step": cb["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
                           "cpu_baseline": cb,
-                          "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
-                                  "d2h_bytes_per_step": 0}}))
+              "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (gmeta_b200 has no CPU path)"
@@ -289,9 +309,6 @@ def main():
     from gmeta_b200 import dist
     import torch.distributed as td
     if world > 1:
-        # NCCL writes its version banner / debug lines to stdout by default: send them to stderr so that stdout
-        # carries the one JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_from_env("nccl")
     from gmeta_b200.meta import Meta
 
@@ -438,7 +455,7 @@ def main():
             "steps": full_steps, "gpu_launches_per_step": int(full_launches),
             "note": "same meta-step with every layer over all rows (pruned_forward=0): the reference's own formulation; "
                     "its forwards are the full-layer launches `roofline` is measured on"}
-    print(json.dumps(line))
+    emit(line)
 
 
 if __name__ == "__main__":
