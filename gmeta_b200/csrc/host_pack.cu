@@ -3,6 +3,7 @@
 // few host threads.  Replaces the per-task numpy loops of gmeta_b200/packing.py:fill_set, which were the
 // largest part of the end-to-end step once the device work had shrunk below them.  Pure integer work:
 // the reference does the equivalent inside dgl.batch (subgraph_data_processing.py:399-406).
+#include <algorithm>
 #include <atomic>
 #include <thread>
 #include <vector>
@@ -101,21 +102,22 @@ extern "C" int64_t gmeta_host_active_in_neighbours(const int32_t* indptr, const 
                                                    int64_t n_rows, int64_t n_nodes, uint8_t* flags, int64_t* out_rows) {
   if (n_rows < 0 || n_nodes < 0 || (n_rows > 0 && (!indptr || !indices || !rows)) || !flags || !out_rows)
     return GMETA_ERR_BAD_ARG;
-  int64_t lo = n_nodes, hi = -1;
+  // collect the distinct neighbours in visiting order (the byte map de-duplicates); the lists of ascending
+  // centre rows in disjoint subgraph ranges usually come out sorted already, otherwise sort
+  int64_t n = 0, prev = -1;
+  bool sorted = true;
   for (int64_t i = 0; i < n_rows; ++i) {
     const int64_t v = rows[i];
     for (int32_t e = indptr[v]; e < indptr[v + 1]; ++e) {
       const int32_t u = indices[e];
+      if (flags[u]) continue;
       flags[u] = 1;
-      if (u < lo) lo = u;
-      if (u > hi) hi = u;
+      out_rows[n++] = u;
+      if (u < prev) sorted = false;
+      prev = u;
     }
   }
-  int64_t n = 0;
-  for (int64_t u = lo; u <= hi; ++u)
-    if (flags[u]) {
-      out_rows[n++] = u;
-      flags[u] = 0;
-    }
+  if (!sorted) std::sort(out_rows, out_rows + n);
+  for (int64_t i = 0; i < n; ++i) flags[out_rows[i]] = 0;
   return n;
 }

@@ -277,7 +277,7 @@ def _fill_base(buf, ps, graphs, labels, centres, node_ids, graph_idx, graph_row_
     buf[o["task_sub_ptr"]:o["task_sub_ptr"] + T + 1] = ps.sub_off
 
 
-def _plan_fill_act(buf, ps, off, n_layers, lib=None):
+def _plan_fill_act(buf, ps, off, n_layers, lib=None, staging=None):
     """Active rows per layer from the packed arrays (global sorted row ids are grouped by task because a task
     is a contiguous row range), their task pointers and tile tables, appended at `off`."""
     o = ps.off
@@ -295,10 +295,12 @@ def _plan_fill_act(buf, ps, off, n_layers, lib=None):
     for l in range(n_layers - 1, 0, -1):
         # sorted distinct in-neighbours of ~10^3-10^5 rows through a byte map: cheaper than sorting them
         if flags is None:
-            flags = np.zeros(ps.N, dtype=np.uint8)
-            scratch = np.empty(ps.N, dtype=np.int64)
+            # byte map over the rows: kept (zeroed) in the staging object between steps when there is one
+            flags = staging.byte_map(ps.N) if staging is not None else np.zeros(ps.N, dtype=np.uint8)
         if lib is not None:
             rows = np.ascontiguousarray(rows, dtype=np.int64)
+            tot = int((indptr[rows + 1].astype(np.int64) - indptr[rows]).sum())
+            scratch = np.empty(min(ps.N, tot) + 1, dtype=np.int64)
             n = lib.gmeta_host_active_in_neighbours(indptr.ctypes.data, indices.ctypes.data, rows.ctypes.data,
                                                     rows.shape[0], ps.N, flags.ctypes.data, scratch.ctypes.data)
             if n < 0:
@@ -338,8 +340,8 @@ def pack_meta_batch(staging, batch, graph_row_off, n_layers, lib, n_threads=0):
     buf = staging.reserve(off + _act_capacity(ps_s, n_layers) + _act_capacity(ps_q, n_layers))
     _fill_base(buf, ps_s, x_spt, y_spt, c_spt, n_spt, g_spt, graph_row_off, lib, n_threads)
     _fill_base(buf, ps_q, x_qry, y_qry, c_qry, n_qry, g_qry, graph_row_off, lib, n_threads)
-    off = _plan_fill_act(buf, ps_s, off, n_layers, lib)
-    off = _plan_fill_act(buf, ps_q, off, n_layers, lib)
+    off = _plan_fill_act(buf, ps_s, off, n_layers, lib, staging)
+    off = _plan_fill_act(buf, ps_q, off, n_layers, lib, staging)
     ps_s.end = ps_q.end = off
     return ps_s, ps_q, off
 
@@ -358,6 +360,12 @@ class Staging(object):
             self.host = torch.empty(cap, dtype=torch.int32, pin_memory=torch.cuda.is_available())
             self.dev = torch.empty(cap, dtype=torch.int32, device=self.device)
         return self.host.numpy()
+
+    def byte_map(self, n):
+        """Zeroed uint8 scratch of at least n entries; users hand it back zeroed."""
+        if getattr(self, "_flags", None) is None or self._flags.shape[0] < n:
+            self._flags = np.zeros(int(n * 1.25) + 64, dtype=np.uint8)
+        return self._flags
 
     def upload(self, n):
         self.dev[:n].copy_(self.host[:n], non_blocking=True)
