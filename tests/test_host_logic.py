@@ -242,10 +242,16 @@ def test_extraction_sampling_cap():
 
 def test_product_code_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "gmeta_b200")
-    for fn in os.listdir(pkg):
-        if fn.endswith(".py"):
-            src = open(os.path.join(pkg, fn)).read()
-            assert "oracle" not in src.replace("the oracle", ""), fn
+    files = [os.path.join(pkg, fn) for fn in os.listdir(pkg) if fn.endswith(".py")] + [os.path.join(ROOT, "train.py")]
+    files += [os.path.join(pkg, "csrc", fn) for fn in os.listdir(os.path.join(pkg, "csrc")) if fn.endswith((".cu", ".cuh"))]
+    assert len(files) > 20
+    for path in files:
+        src = open(path).read()
+        assert "oracle" not in src.replace("the oracle", ""), path
+    # bench.py may use the oracle, but only for the CPU baseline / reference arm (cpu_arm)
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    assert bench.count("from oracle import") == 1
+    assert bench.split("from oracle import")[0].rsplit("\ndef ", 1)[1].startswith("cpu_arm(")
 
 
 @pytest.mark.parametrize("kind", H.TINY_KINDS)
