@@ -215,7 +215,7 @@ int gmeta_gcn_layer_wgrad(const float* in, int32_t ld_in, const int32_t* in_row_
 /* HOST helper (no device work, no stream): packs the per-task CSR arrays of one set of a meta-batch into the
  * packed-set layout -- out_indptr[node_off[t] + 1 + i] = indptr[t][1 + i] + edge_off[t],
  * out_indices[edge_off[t] + e] = indices[t][e] + node_off[t], same for the transposed arrays -- on up to
- * n_threads host threads (0 = hardware concurrency, capped at 16).  What dgl.batch does for the reference
+ * n_threads host threads (0 = hardware concurrency, capped at 8).  What dgl.batch does for the reference
  * (subgraph_data_processing.py:399-406).  Output pointers are host memory (the pinned staging buffer). */
 int gmeta_host_pack_csr(int32_t n_tasks, const int32_t* const* indptr, const int32_t* const* indices,
                         const int32_t* const* t_indptr, const int32_t* const* t_indices,
