@@ -17,7 +17,13 @@ runs its own 32-task share (weak scaling, task-sharded; one NCCL all-reduce per 
           CUDA events on its launch stream; algorithmic bytes per SURVEY 8d / DESIGN.md.
   cpu_baseline : the oracle port of the reference (oracle/gmeta_oracle.py, torch CPU, all host
           threads) on a bounded sample (a few tasks of the same workload).
-`--impl reference` prints the CPU arm as its own line (rank 0 only).
+  parity_in_run : before anything is timed, the first --cpu-tasks tasks of the first meta-batch go through a fresh
+          Meta.forward on the GPU and through the CPU arm from the same seed-222 weights; accuracies must agree up to
+          the rows the CPU arm itself marks as near-ties (top-2 log-probability gap < 2e-4), the query loss to 1e-4.
+  timing  : exactly --steps steps are timed first (`contract`), then the same loop keeps running until >= 2 s have
+          been timed in total; `value` / `ms_per_step` / `e2e` are the means over that whole >= 2 s region.
+`--impl reference` prints the CPU arm as its own line (rank 0 only): the unmodified reference through
+oracle/ref_loader.py when /root/reference is mounted (build container), else the oracle port (GPU box).
 """
 import argparse
 import json
@@ -52,6 +58,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full", action="store_true", help="skip the full-formulation (unpruned) arm")
     ap.add_argument("--no-device-extract", action="store_true", help="skip the device-extraction end-to-end arm")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C3 / C4 / C5 strong-scaling blocks")
     return ap.parse_args()
 
 
@@ -125,27 +132,87 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
-def cpu_arm(ds, batch_host, n_tasks, steps, warmup):
-    """The reference's CPU path (oracle port, bit-for-bit checked against the unmodified reference
-    in tests/) on `n_tasks` tasks of the workload, all host threads."""
+TIE_GAP = 2e-4   # twice the stated logit tolerance (north_star: logits within 1e-4, identical argmax)
+
+
+def cpu_arm(ds, batch_host, n_tasks, steps, warmup, want_first=False):
+    """The reference's CPU path on `n_tasks` tasks of the workload, all host threads: the UNMODIFIED reference
+    (G-Meta/meta.py + learner.py through oracle/ref_loader.py and the DGL stand-in) when its tree is mounted,
+    else the oracle port (bit-for-bit checked against it in tests/).  With want_first the first step's accuracy
+    vector, query loss and per-step near-tie row counts are returned for the in-run parity gate (port only)."""
     from oracle import gmeta_oracle as O
+    from oracle import ref_loader
     torch.set_num_threads(os.cpu_count() or 1)
     sub = tuple(lst[:n_tasks] for lst in batch_host)
     xs, ys, xq, yq, cs, cq, ns, nq, gs, gq = sub
-    oxs = [O.OGraph.from_csr(x.indptr, x.indices, x.batch_num_nodes) for x in xs]
-    oxq = [O.OGraph.from_csr(x.indptr, x.indices, x.batch_num_nodes) for x in xq]
-    torch.manual_seed(222)
-    om = O.OracleMeta(ds.args(), ds.config(), fast=True)
+    first = None
+    use_ref = ref_loader.available() and not want_first
+    if use_ref:
+        _, ref_meta, _ = ref_loader.load()
+        dgl = ref_loader.shim_dgl()
+        to_dgl = lambda p: dgl.DGLGraph(*p.edges(), p.n_nodes, batch_num_nodes=p.batch_num_nodes)   # noqa: E731
+        gxs, gxq = [to_dgl(x) for x in xs], [to_dgl(x) for x in xq]
+        torch.manual_seed(222)
+        model = ref_meta.Meta(ds.args(), ds.config())
+        kind, how = "reference", "unmodified G-Meta/meta.py + learner.py (oracle/ref_loader.py, DGL stand-in: index_add SpMM)"
+    else:
+        gxs = [O.OGraph.from_csr(x.indptr, x.indices, x.batch_num_nodes) for x in xs]
+        gxq = [O.OGraph.from_csr(x.indptr, x.indices, x.batch_num_nodes) for x in xq]
+        torch.manual_seed(222)
+        model = O.OracleMeta(ds.args(), ds.config(), fast=True)
+        kind, how = "port", "oracle/gmeta_oracle.py with MKL CSR SpMM"
+    ties = []
+    if want_first:
+        inner = O._proto_nll
+
+        def counted(dists, n_classes, n_query):
+            top = torch.topk(torch.log_softmax(-dists.detach(), dim=1), 2, dim=1).values
+            ties.append(int(((top[:, 0] - top[:, 1]) < TIE_GAP).sum()))
+            return inner(dists, n_classes, n_query)
+        O._proto_nll = counted
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        om.forward(oxs, ys, oxq, yq, cs, cq, ns, nq, gs, gq, ds.feats)
+        accs = model.forward(gxs, ys, gxq, yq, cs, cq, ns, nq, gs, gq, ds.feats)
         times.append(time.perf_counter() - t0)
-    t = float(np.mean(times[warmup:]))
-    return {"value": n_tasks / t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "%d tasks of the same workload per step (full update_step=%d inner loop + Adam), "
-                      "%d timed steps after %d warm-up; oracle/gmeta_oracle.py with MKL CSR SpMM"
-                      % (n_tasks, ds.update_step, steps, warmup), "s_per_step": t}
+        if it == 0 and want_first:
+            O._proto_nll = inner
+            K, per = ds.update_step, 2 * ds.update_step + 1
+            q = np.zeros(K + 1, dtype=np.int64)      # call order per task: spt0, qry0, qry1, (spt_k, qry_k+1)...
+            for t in range(n_tasks):
+                c = ties[t * per:(t + 1) * per]
+                q[0] += c[1]
+                q[1] += c[2]
+                for k in range(1, K):
+                    q[k + 1] += c[2 + 2 * k]
+            first = {"accs": np.asarray(accs, dtype=np.float64), "loss_q": model.last_loss_q, "near_ties": q,
+                     "rows_per_step": n_tasks * len(yq[0])}
+    t = float(np.mean(times[warmup:])) if steps > 0 else float("nan")
+    out = {"value": n_tasks / t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+           "sample": "%d of the workload's tasks per step (full update_step=%d inner loop + Adam), "
+                     "%d timed steps after %d warm-up; %s" % (n_tasks, ds.update_step, steps, warmup, how),
+           "s_per_step": t}
+    return (out, first) if want_first else out
+
+
+def parity_gate(ds, batch, n_tasks, kernel_impl, dev):
+    """GPU vs CPU arm on the same tasks from the same seed-222 weights, before any timing."""
+    from gmeta_b200.meta import Meta
+    cb, first = cpu_arm(ds, batch, n_tasks, 5, 1, want_first=True)
+    margs = ds.args()
+    margs.impl = kernel_impl
+    torch.manual_seed(222)
+    m = Meta(margs, ds.config()).to(dev)
+    accs = np.asarray(m(*tuple(lst[:n_tasks] for lst in batch), ds.feats), dtype=np.float64)
+    flips = np.abs(accs - first["accs"]) * first["rows_per_step"]
+    d_loss = abs(m.last["loss_q"] - first["loss_q"])
+    ok = bool(np.all(flips <= first["near_ties"] + 1e-3) and d_loss < 1e-4)
+    rep = {"ok": ok, "tasks": n_tasks, "accs_gpu": [float(a) for a in accs], "accs_cpu": [float(a) for a in first["accs"]],
+           "argmax_flips_per_step": [int(round(f)) for f in flips], "cpu_near_tie_rows_per_step": first["near_ties"].tolist(),
+           "loss_q_gpu": m.last["loss_q"], "loss_q_cpu": first["loss_q"], "abs_loss_diff": d_loss,
+           "rule": "accuracy vectors equal up to the rows whose CPU top-2 log-probability gap is < %g; |loss_q diff| < 1e-4" % TIE_GAP}
+    del m
+    return ok, rep, cb
 
 
 def device_extraction(ds, batch, host_s):
@@ -278,6 +345,72 @@ def emit(line):
     out.flush()
 
 
+MIN_TIMED_S = 2.0
+
+
+def timed_region(step_fn, steps, world, td):
+    """Time exactly `steps` calls of step_fn(i) (the contract's K steps), then keep calling it in blocks of `steps`
+    until >= MIN_TIMED_S have been timed in total.  CUDA events on the current stream, a barrier + synchronize on
+    both sides of every block, max over ranks.  Returns (ms of the first K steps, total ms, total steps)."""
+    def block(i0):
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(i0, i0 + steps):
+            step_fn(i)
+        e1.record()
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t[0])
+    ms_k = block(0)
+    total_ms, total_steps = ms_k, steps
+    more = int(np.ceil(max(0.0, MIN_TIMED_S * 1e3 - ms_k) / max(ms_k, 1e-3)))    # identical on all ranks (reduced time)
+    for r in range(min(more, 2000)):
+        total_ms += block((r + 1) * steps)
+        total_steps += steps
+    return ms_k, total_ms, total_steps
+
+
+def strong_scaling_config(name, world, rank, local_rank, kernel_impl, steps, warmup, td):
+    """One of BASELINE.json's multi-GPU configs (C3 / C4 / C5) as the README runs it: ONE meta-batch of the config's
+    task_num tasks, sharded round-robin over the ranks (strong scaling), one all-reduce per step.  Device-resident
+    timing like `value`.  Every rank samples the same global meta-batches (same seed) and keeps its own tasks."""
+    from gmeta_b200 import dist
+    from gmeta_b200.meta import Meta
+    from gmeta_b200.synthetic import make_dataset
+    ds = make_dataset(name)
+    T = ds.task_num
+    if T % world != 0:
+        return {"skipped": "task_num=%d does not shard over %d ranks" % (T, world)}
+    rng = np.random.default_rng(4000)
+    batches = [ds.sample_meta_batch(rng, T) for _ in range(3)]
+    margs = ds.args()
+    margs.impl = kernel_impl
+    torch.manual_seed(222)
+    m = Meta(margs, ds.config()).to(torch.device("cuda", local_rank))
+    m.global_task_num = T
+    dbs = [m.upload_batch(dist.shard_meta_batch(b, rank, world), ds.feats, own_buffer=True) for b in batches]
+    for i in range(max(3, warmup)):
+        out = m.step_device(dbs[i % len(dbs)])
+    ms_k, ms_tot, n = timed_region(lambda i: m.step_device(dbs[i % len(dbs)]), steps, world, td)
+    out = m.step_device(dbs[0]).cpu().numpy()
+    gn = np.array([g.n for g in ds.graphs])
+    ge = np.array([g.number_of_edges() for g in ds.graphs])
+    return {"value": T * n / (ms_tot * 1e-3), "unit": UNIT, "scaling": "strong", "task_num": T, "tasks_per_rank": T // world,
+            "ms_per_step": ms_tot / n, "timed_steps": n, "timed_s": ms_tot * 1e-3,
+            "workload": workload_desc(ds, T // world)["workload"],
+            "graphs": {"count": len(ds.graphs), "nodes_mean": float(gn.mean()), "nodes_min": int(gn.min()), "nodes_max": int(gn.max()),
+                       "directed_nnz_mean": float(ge.mean()), "directed_nnz_min": int(ge.min()), "directed_nnz_max": int(ge.max())},
+            "packed_nodes_spt_qry_rank0": m.last["n_nodes"], "packed_edges_spt_qry_rank0": m.last["n_edges"],
+            "gpu_launches_per_step": int(m.last["gpu_launches"]), "loss_q": float(out[-2])}
+
+
 def main():
     args = parse()
     claim_stdout()
@@ -294,18 +427,18 @@ def main():
         batch = ds.sample_meta_batch(np.random.default_rng(1000), n_tasks)
         steps, warmup = max(1, args.steps), max(0, args.warmup)     # a step = n_tasks tasks of the workload (bounded sample)
         cb = cpu_arm(ds, batch, n_tasks, steps, warmup)
-        cfg = workload_desc(ds, n_tasks)
-        cfg["note"] = "reference CPU path = oracle port (the reference's own files need DGL, absent here)"
+        cfg = workload_desc(ds, args.tasks or ds.task_num)           # the workload sampled FROM: same string as our arm's
         emit({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
-                          "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
-                          "ms_per_step": cb["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
-                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
-                          "cpu_baseline": cb,
+              "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+              "ms_per_step": cb["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
+              "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+              "cpu_baseline": cb,
               "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (gmeta_b200 has no CPU path)"
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     from gmeta_b200 import dist
     import torch.distributed as td
     if world > 1:
@@ -318,10 +451,20 @@ def main():
     t0 = time.perf_counter()
     batches = [ds.sample_meta_batch(rng, tasks) for _ in range(args.batches)]
     extract_s = (time.perf_counter() - t0) / args.batches
+
+    # ---------------- parity gate: nothing is timed before the GPU path agrees with the CPU arm ----------------
+    parity, cb = None, None
+    if rank == 0 and not args.no_cpu_baseline:
+        ok, parity, cb = parity_gate(ds, batches[0], min(tasks, max(1, args.cpu_tasks)), args.kernel_impl, dev)
+        if not ok:
+            emit({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world, "parity_in_run": False, "parity": parity,
+                  "error": "GPU path disagrees with the CPU arm on the same tasks: nothing timed"})
+            sys.exit(3)
+
     margs = ds.args()
     margs.impl = args.kernel_impl
     torch.manual_seed(222)
-    m = Meta(margs, ds.config()).to(torch.device("cuda", local_rank))
+    m = Meta(margs, ds.config()).to(dev)
     peaks = {}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(pk):
@@ -334,40 +477,38 @@ def main():
 
     # ---------------- device-resident arm ----------------
     dbs = [m.upload_batch(b, ds.feats, own_buffer=True) for b in batches]
-    for i in range(args.warmup):
+    for i in range(max(3, args.warmup)):
         m.step_device(dbs[i % len(dbs)])
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = 0
-    e0.record()
-    for i in range(args.steps):
-        out_dev = m.step_device(dbs[i % len(dbs)])
-        launches += m.last["gpu_launches"]
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    last_out = out_dev.cpu().numpy()
+    launches = [0]
+    outs = [None]
+
+    def dev_step(i):
+        outs[0] = m.step_device(dbs[i % len(dbs)])
+        if i < args.steps:
+            launches[0] += m.last["gpu_launches"]
+    ms_k, ms_total, n_total = timed_region(dev_step, args.steps, world, td)
+    last_out = outs[0].cpu().numpy()
+    launches_per_step = m.last["gpu_launches"]
     # ---------------- end-to-end arm (host batch in, accuracy vector out) ----------------
     for i in range(min(2, args.warmup)):
         m(*batches[i % len(batches)], ds.feats)
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for i in range(args.steps):
-        accs = m(*batches[i % len(batches)], ds.feats)
-    f1.record()
-    barrier()
+    accs_box = [None]
+
+    def e2e_step(i):
+        accs_box[0] = m(*batches[i % len(batches)], ds.feats)
+    ms_e2e_k, ms_e2e, n_e2e = timed_region(e2e_step, args.steps, world, td)
+    accs = accs_box[0]
     sampler.stop_flag = True
-    ms_e2e = f0.elapsed_time(f1)
     host_pack_ms = getattr(m, "host_pack_ms", None)
     h2d, d2h = m.last["h2d_bytes"], m.last["d2h_bytes"]
 
     # ---------------- end to end INCLUDING subgraph extraction, meta-batch built in HBM ----------------
     # Host input per step: centre node ids + labels only (the reference's pre-sampled task lists,
     # subgraph_data_processing.py:150-292); extraction, batching and the step run on the device.
-    ms_dev, dev_h2d = 0.0, 0
+    ms_dev, dev_h2d, dev_steps = 0.0, 0, 0
     if not args.no_device_extract:
         from gmeta_b200.device_batch import CentreRequests
         reqs = []
@@ -377,9 +518,10 @@ def main():
         for i in range(2):
             m.forward_device(ds.graphs, reqs[i % len(reqs)][0], reqs[i % len(reqs)][1], ds.feats, ds.h, ds.sample_nodes)
         barrier()
+        dev_steps = max(args.steps, 20)
         h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         h0.record()
-        for i in range(args.steps):
+        for i in range(dev_steps):
             r = reqs[i % len(reqs)]
             m.forward_device(ds.graphs, r[0], r[1], ds.feats, ds.h, ds.sample_nodes, seed=222 + i)
         h1.record()
@@ -396,10 +538,10 @@ def main():
         margs_f.impl = args.kernel_impl
         margs_f.pruned_forward = False
         torch.manual_seed(222)
-        mf = Meta(margs_f, ds.config()).to(torch.device("cuda", local_rank))
+        mf = Meta(margs_f, ds.config()).to(dev)
         mf.step_device(dbs[0])
         barrier()
-        full_steps = 3
+        full_steps = 10
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         for i in range(full_steps):
@@ -410,41 +552,55 @@ def main():
         full_launches = mf.last["gpu_launches"]
         del mf
 
-    t = torch.tensor([ms_total, ms_e2e, ms_full, ms_dev], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms_full, ms_dev], dtype=torch.float64, device="cuda")
     if world > 1:
         td.all_reduce(t, op=td.ReduceOp.MAX)      # max over ranks
-    ms_total, ms_e2e, ms_full, ms_dev = float(t[0]), float(t[1]), float(t[2]), float(t[3])
-    total_tasks = tasks * world * args.steps
-    value = total_tasks / (ms_total * 1e-3)
-    e2e_value = total_tasks / (ms_e2e * 1e-3)
+    ms_full, ms_dev = float(t[0]), float(t[1])
+    value = tasks * world * n_total / (ms_total * 1e-3)
+    e2e_value = tasks * world * n_e2e / (ms_e2e * 1e-3)
+
+    # ---------------- BASELINE.json configs[2..4] on their GPU counts: strong scaling, tasks sharded ----------------
+    # C5 (task_num 64) at every N: the 1 -> 8 curve the README quotes; C3 (task_num 4) at N <= 4; C4 (task_num 8) at N <= 8.
+    cfg_blocks = {}
+    if args.workload == "C2" and args.scale == 1.0 and not args.no_configs:
+        free = [m, dbs]
+        for name in ("C3", "C4", "C5"):
+            cfg_blocks[name] = strong_scaling_config(name, world, rank, local_rank, args.kernel_impl, args.steps,
+                                                     args.warmup, td)
+        del free
 
     if rank != 0:
         return
     roof = layer_roofline(m, dbs[0], peaks, args.kernel_impl)
     extraction = device_extraction(ds, batches[0], extract_s)
-    cb = None
-    if not args.no_cpu_baseline:
-        cb = cpu_arm(ds, batches[0], max(1, args.cpu_tasks), 3, 1)   # ~10-20 s of host work
     cfg = workload_desc(ds, tasks)
     cfg.update({"parallelism": "task-sharded x%d" % world, "l2_policy": "inputs larger than L2 (packed meta-batch "
                 "activations %.1f GB per step; %d distinct meta-batches cycled)"
                 % (4e-9 * m.last["n_nodes"][1] * ds.hidden_dim * 2, len(batches)),
                 "packed_nodes_spt_qry": m.last["n_nodes"], "packed_edges_spt_qry": m.last["n_edges"],
-                "kernel_impl": {0: "auto", 1: "ffma", 2: "tcgen05-3xtf32"}[args.kernel_impl],
+                "kernel_impl": {0: "auto", 1: "ffma", 2: "tcgen05-3xtf32", 3: "tcpair"}[args.kernel_impl],
                 "subgraph_extraction_s_per_meta_batch_host": extract_s, "host_pack_ms_last_step": host_pack_ms,
                 "final_accs": [float(a) for a in accs], "loss_q": float(last_out[-2])})
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": ms_total / n_total, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "timed": {"steps_timed": n_total, "timed_s": ms_total * 1e-3,
+                      "contract": {"steps": args.steps, "ms_per_step": ms_k / args.steps,
+                                   "value": tasks * world * args.steps / (ms_k * 1e-3)},
+                      "note": "value / ms_per_step are means over steps_timed >= --steps meta-steps (>= %.0f s timed); "
+                              "`contract` is the first --steps of them alone" % MIN_TIMED_S},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cb}
+                    "ms_per_step": ms_e2e / n_e2e, "steps_timed": n_e2e, "timed_s": ms_e2e * 1e-3,
+                    "contract_ms_per_step": ms_e2e_k / args.steps},
+            "gpu_launches": int(launches[0]), "gpu_launches_per_step": int(launches_per_step),
+            "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cb,
+            "parity_in_run": bool(parity["ok"]) if parity else None, "parity": parity}
     if extraction:
         line["extraction"] = extraction
     if ms_dev > 0:
         line["e2e_with_device_extraction"] = {
-            "value": total_tasks / (ms_dev * 1e-3), "unit": UNIT, "ms_per_step": ms_dev / args.steps,
-            "h2d_bytes_per_step": int(dev_h2d), "d2h_bytes_per_step": int(d2h),
+            "value": tasks * world * dev_steps / (ms_dev * 1e-3), "unit": UNIT, "ms_per_step": ms_dev / dev_steps,
+            "steps": dev_steps, "h2d_bytes_per_step": int(dev_h2d), "d2h_bytes_per_step": int(d2h),
             "note": "Meta.forward_device: host ships centre ids + labels; h-hop extraction (sampling cap by the device "
                     "hash sampler), batching, transposed CSR, active rows and the whole meta-step on the device; "
                     "`e2e` above starts from host-extracted subgraphs and excludes the %.2f s per meta-batch the host "
@@ -455,6 +611,8 @@ def main():
             "steps": full_steps, "gpu_launches_per_step": int(full_launches),
             "note": "same meta-step with every layer over all rows (pruned_forward=0): the reference's own formulation; "
                     "its forwards are the full-layer launches `roofline` is measured on"}
+    if cfg_blocks:
+        line["configs"] = cfg_blocks
     emit(line)
 
 

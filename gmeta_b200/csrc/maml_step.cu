@@ -312,18 +312,30 @@ struct Runner {
 
 using namespace gmeta;
 
+// At the step level GMETA_IMPL_TCPAIR means "the CTA-pair path wherever a launch has the structure plan and the
+// row abs-max it needs" -- which is what AUTO selects; the launches without them (pruned forwards on the identity
+// graph, data gradients) cannot take it and fall back inside the library like AUTO does.
+static gmeta_step_args_t step_level_args(const gmeta_step_args_t* a) {
+  gmeta_step_args_t c = *a;
+  if (c.impl == GMETA_IMPL_TCPAIR) c.impl = GMETA_IMPL_AUTO;
+  return c;
+}
+
 extern "C" int64_t gmeta_maml_step_workspace_bytes(const gmeta_step_args_t* args) {
   if (validate(args) != GMETA_OK) return -1;
+  const gmeta_step_args_t c = step_level_args(args);
   StepBuffers b;
-  carve(args, nullptr, b);
+  carve(&c, nullptr, b);
   return b.total;
 }
 
 extern "C" int gmeta_last_launch_count(void) { return g_launch_count; }
 
-extern "C" int gmeta_maml_step(const gmeta_step_args_t* a, void* stream) {
-  int rc = validate(a);
+extern "C" int gmeta_maml_step(const gmeta_step_args_t* a_in, void* stream) {
+  int rc = validate(a_in);
   if (rc != GMETA_OK) return rc;
+  const gmeta_step_args_t a_copy = step_level_args(a_in);
+  const gmeta_step_args_t* a = &a_copy;
   if (!a->workspace || !a->theta || !a->feat_table || !a->loss_q || !a->acc_q || !a->loss_s)
     return GMETA_ERR_BAD_ARG;
   if (a->compute_meta_grad && !a->meta_grad) return GMETA_ERR_BAD_ARG;

@@ -162,6 +162,25 @@ class FeatureTable(object):
                                                self.rowmax.data_ptr(), _stream()), "row_absmax")
 
 
+def _feat_fingerprint(feat):
+    """Cheap identity + content fingerprint of the caller's feature arrays: length, and for a bounded sample of
+    the arrays (first, last, up to eight evenly spaced) the data pointer, shape, dtype and a strided checksum of
+    64 values.  The reference re-reads `feat` every step (meta.py:119-120); a resident table must notice when an
+    array was swapped or rewritten in place.  `Meta.refresh_features` forces a re-upload for changes the sample
+    cannot see."""
+    n = len(feat)
+    if n == 0:
+        return (0,)
+    fp = [n]
+    for i in sorted(set([0, n - 1] + list(range(0, n, max(1, n // 8))))):
+        a = np.asarray(feat[i])
+        flat = a.reshape(-1)
+        step = max(1, flat.shape[0] // 64)
+        fp.append((i, a.__array_interface__['data'][0], a.shape, a.dtype.str,
+                   float(np.asarray(flat[::step], dtype=np.float64).sum())))
+    return tuple(fp)
+
+
 class _DeviceBatch(object):
     """An uploaded meta-batch: segment plans of both sets + the device int32 buffer holding them."""
     __slots__ = ("T", "max_classes", "ft", "ps_s", "ps_q", "ints", "h2d_bytes")
@@ -235,7 +254,9 @@ class Meta(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ("_staging", "_feat_cache", "_ws", "_scratch", "_extractor"):
+            if k == "_feat_cache":
+                new.__dict__[k] = v          # the resident table is read-only: copies share it (train.py:87,127)
+            elif k in ("_staging", "_ws", "_scratch", "_extractor"):
                 new.__dict__[k] = {} if k == "_scratch" else None
             else:
                 new.__dict__[k] = deepcopy(v, memo)
@@ -243,10 +264,18 @@ class Meta(nn.Module):
 
     # -- helpers --
     def _features(self, feat, dev):
-        key = (id(feat), len(feat))
-        if self._feat_cache is None or self._feat_cache[0] != key:
+        key = (id(feat), _feat_fingerprint(feat))
+        if self._feat_cache is None or self._feat_cache[0] != key or self._feat_cache[1].table.device != dev:
             self._feat_cache = (key, FeatureTable(feat, dev))
         return self._feat_cache[1]
+
+    def refresh_features(self, feat=None):
+        """Drop the resident feature table (and re-upload `feat` now when given).  Call after modifying feature
+        arrays in place in a way the sampled fingerprint cannot see; swapped arrays, resized arrays and rewritten
+        arrays (normalisation, augmentation) are noticed by `_features` on its own."""
+        self._feat_cache = None
+        if feat is not None:
+            self._features(feat, _dev())
 
     def _buf(self, name, shape, dtype, dev, zero=False):
         t = self._scratch.get(name)

@@ -64,9 +64,13 @@ class PackedSubgraphBatch(object):
         self.n_nodes = int(indptr.shape[0] - 1)
         self.n_edges = int(indices.shape[0])
         self.parent_ids = None
+        self.parent_id_lists = None
 
     @staticmethod
-    def batch(subgraphs):
+    def batch(subgraphs, id_lists=None):
+        """`id_lists`: the per-subgraph parent-id sequences the caller will hand to Meta.forward as n_spt / n_qry
+        next to this batch (default: the subgraphs' own `parent_nid` arrays).  The batch remembers those very
+        objects: packing uses the pre-concatenated `parent_ids` only when it is later given the same objects."""
         ns = np.array([s.n for s in subgraphs], dtype=np.int64)
         es = np.array([s.indices.shape[0] for s in subgraphs], dtype=np.int64)
         n_off = np.concatenate([[0], np.cumsum(ns)])
@@ -88,6 +92,7 @@ class PackedSubgraphBatch(object):
         pb = PackedSubgraphBatch(indptr, indices, t_indptr, t_indices, ns.tolist())
         # parent ids of all nodes in batch order (the n_spt / n_qry lists of an episode, concatenated once here)
         pb.parent_ids = np.concatenate([s.parent_nid for s in subgraphs]) if len(subgraphs) else np.zeros(0, np.int64)
+        pb.parent_id_lists = id_lists if id_lists is not None else [s.parent_nid for s in subgraphs]
         return pb
 
     # duck-typing of the DGL batched graph members the hot path touches

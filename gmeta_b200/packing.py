@@ -250,10 +250,14 @@ def _fill_base(buf, ps, graphs, labels, centres, node_ids, graph_idx, graph_row_
     all_ids = []
     for t, g in enumerate(graphs):
         ids = getattr(g, "parent_ids", None)
-        # the ids a batch carries from batch time are trusted only if they agree with the id lists on the
-        # first subgraph (the two come from the same sampler call, subgraph_data_processing.py:356-377)
-        if ids is None or ids.shape[0] != g.n_nodes or ids.dtype != np.int64 or not ids.flags.c_contiguous or (
-                len(node_ids[t]) and not np.array_equal(ids[:bnn[t][0]], np.asarray(node_ids[t][0], dtype=np.int64))):
+        # the ids a batch concatenated at batch time replace the id lists (meta.py:119-120 reads n_spt / n_qry) only
+        # when the lists ARE the objects the batch was built from -- re-sampled, permuted or filtered id lists are
+        # different objects and are honoured through the slow path
+        src = getattr(g, "parent_id_lists", None)
+        same = src is not None and (src is node_ids[t] or (
+            len(src) == len(node_ids[t]) and all(a is b for a, b in zip(src, node_ids[t]))))
+        if (not same or ids is None or ids.shape[0] != g.n_nodes or ids.dtype != np.int64
+                or not ids.flags.c_contiguous):
             ids = np.ascontiguousarray(_flat_ids(node_ids[t]))                # meta.py:119-120
         all_ids.append(ids)
     vpa = lambda arrs: (C.c_void_p * max(T, 1))(*[a.__array_interface__['data'][0] for a in arrs])   # noqa: E731

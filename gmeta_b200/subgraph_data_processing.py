@@ -218,8 +218,8 @@ class Subgraphs(Dataset):
                 support_y_relative[support_y == l] = idx
                 query_y_relative[query_y == l] = idx
             support_y, query_y = support_y_relative, query_y_relative
-        return (PackedSubgraphBatch.batch(support_x), torch.LongTensor(support_y),
-                PackedSubgraphBatch.batch(query_x), torch.LongTensor(query_y),
+        return (PackedSubgraphBatch.batch(support_x, support_node_idx), torch.LongTensor(support_y),
+                PackedSubgraphBatch.batch(query_x, query_node_idx), torch.LongTensor(query_y),
                 torch.LongTensor(support_center), torch.LongTensor(query_center),
                 support_node_idx, query_node_idx, support_graph_idx, query_graph_idx)
 

@@ -138,8 +138,8 @@ class SyntheticDataset(object):
             subs = [self.subgraph(g, i, j, rng) for g, i, j, _ in items]
             y = np.array([c if relabel is None else relabel[c] for _, _, _, c in items], dtype=np.int64)
             centre = np.array([s.centre for s in subs], dtype=np.int64)
-            return (PackedSubgraphBatch.batch(subs), torch.LongTensor(y), torch.LongTensor(centre),
-                    [s.parent_nid for s in subs], [g for g, _, _, _ in items])
+            pb = PackedSubgraphBatch.batch(subs)
+            return (pb, torch.LongTensor(y), torch.LongTensor(centre), pb.parent_id_lists, [g for g, _, _, _ in items])
 
         xs, ys, cs, ns, gs = build(spt_items)
         xq, yq, cq, nq, gq = build(qry_items)

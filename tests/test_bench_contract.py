@@ -16,9 +16,21 @@ from gmeta_b200.packed import csr_transpose
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+import pytest
+
+
+@pytest.mark.parametrize("mounted", [True, False])
+def test_reference_arm_prints_one_json_line_with_the_contract_keys(mounted):
+    """mounted: the unmodified reference through oracle/ref_loader.py (build container only, kind "reference");
+    not mounted (the GPU box): the oracle port (kind "port")."""
+    from oracle import ref_loader
+    if mounted and not ref_loader.available():
+        pytest.skip("reference tree not mounted")
+    env = dict(os.environ)
+    if not mounted:
+        env["GMETA_REFERENCE_DIR"] = "/nonexistent"
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--cpu-tasks", "1", "--scale", "0.03"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          "--cpu-tasks", "1", "--scale", "0.03"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, out.stdout[:500]
@@ -30,7 +42,7 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["unit"] == "meta-tasks/s" and d["value"] > 0 and d["steps"] == 1
     assert "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert cb["kind"] == ("reference" if mounted else "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
