@@ -140,8 +140,7 @@ def cpu_arm(ds, batch_host, n_tasks, steps, warmup, want_first=False):
     (G-Meta/meta.py + learner.py through oracle/ref_loader.py and the DGL stand-in) when its tree is mounted,
     else the oracle port (bit-for-bit checked against it in tests/).  With want_first the first step's accuracy
     vector, query loss and per-step near-tie row counts are returned for the in-run parity gate (port only)."""
-    from oracle import gmeta_oracle as O
-    from oracle import ref_loader
+    from oracle import gmeta_oracle as O, ref_loader
     torch.set_num_threads(os.cpu_count() or 1)
     sub = tuple(lst[:n_tasks] for lst in batch_host)
     xs, ys, xq, yq, cs, cq, ns, nq, gs, gq = sub
