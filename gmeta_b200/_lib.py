@@ -8,7 +8,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgmeta_b200.so")
+# GMETA_B200_LIB: another build of the same library (e.g. one compiled with per-role cycle counters for triage)
+LIB_PATH = os.environ.get("GMETA_B200_LIB") or os.path.join(_HERE, "libgmeta_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 MAX_LAYERS = 3

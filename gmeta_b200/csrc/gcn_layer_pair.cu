@@ -28,14 +28,25 @@
 //     2-hop subgraph batch have <= 2), and for longer rows (hubs) a slot in a flattened edge list
 //     that a small edge-parallel kernel aggregates first; the fused kernel then reads a hub like
 //     a single neighbour with weight 1.
+//   * Local subgraphs are star-like: most rows are leaves whose only in-neighbour is a hub they share
+//     with hundreds of other leaves, so their aggregated rows M[v,:] = n_u * in[u,:] are IDENTICAL
+//     (a C2 query set: 1.28 M rows, 0.17 M distinct (sources, norms) records per task).  The plan
+//     therefore cuts the rows of a task into "compute tiles": a run of up to 1024 consecutive
+//     output rows holding at most 128 distinct records ("slots").  Only the slots are gathered,
+//     split and contracted on the tensor cores (one 128-row MMA tile per compute tile, 6.5x fewer
+//     than rows / 128); the epilogue stages the accumulator block in shared memory and EXPANDS it:
+//     out[v,:] = act(norm[v] * 2^-e * acc[slot(v),:] + bias), every output row still written once,
+//     every input row still read once -- the same arithmetic per row as without the sharing, so
+//     results are bit-identical to the undeduplicated kernel.
 //
 // Warp roles per CTA (640 threads; register budgets re-balanced per warpgroup with setmaxnreg): warps 0..7
 // gather producers (a lane quad owns two rows, 32-float K chunks, the next chunk's segments requested before
 // the current one is reduced: fp32 sum -> scaled FP16 hi/lo -> 64B-swizzled K-major operand stage), warp 12
 // weight loader (cp.async.bulk of the pre-split, pre-swizzled image), warp 13 MMA issuer (leader CTA only; one
-// thread), warps 8..11 and 16..19 epilogue, one column half each (tcgen05.ld with the next block in flight,
-// * norm * 2^-e + bias, ReLU, transposed through shared memory so that a store instruction writes 8 rows x 64
-// contiguous bytes, mask, row abs-max for the next layer).  Hand-offs are mbarriers waited on with the hardware
+// thread), warps 8..11 and 16..19 epilogue: per 64-column block the accumulators of the 128 slots go
+// tcgen05.ld -> swizzled shared-memory block (the next block's load in flight), then all eight warps expand
+// it to the tile's output rows -- a lane octet per row, 128 contiguous bytes per store: * norm * 2^-e + bias,
+// ReLU / mask, row abs-max for the next layer.  Hand-offs are mbarriers waited on with the hardware
 // suspend hint; the peer CTA signals the leader's barriers through the cluster address space, the MMA thread
 // releases operand stages / accumulators in both CTAs with multicast commits.  Hub rows are summed beforehand
 // by hub_prepass_kernel (whole chip, one warp per small hub, one CTA per big hub).
@@ -74,9 +85,15 @@ constexpr int MAX_STAGES = 6;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_COLS = 256;
 constexpr int PRE = 2;                         // in-neighbours per row the fused kernel gathers itself
-constexpr int EPI_STAGE_BYTES = N_EPI_WARPS * 32 * 16 * 4;   // one 32x16 fp32 transpose tile per epilogue warp (XOR-swizzled)
+constexpr int RMAX = 1024;                     // output rows per compute tile (<= 128 distinct slots among them)
+constexpr int EBLK = 64;                       // accumulator columns per expansion block
+constexpr int EPI_STAGE_BYTES = TM * EBLK * 4; // one [128 slots][64 columns] fp32 block (16-byte units XOR-swizzled by slot)
 constexpr int BAR_BYTES = 256;
-constexpr int SMEM_FIXED = BAR_BYTES /*barriers*/ + 4 * TM /*row scale exponents*/ + ACC_COLS * 4 /*bias*/ + 2 * TM * 4 /*row max exchange*/ + EPI_STAGE_BYTES;
+constexpr int SMEM_FIXED = BAR_BYTES /*barriers*/ + 4 * TM /*slot scale exponents*/ + ACC_COLS * 4 /*bias*/ +
+                           RMAX * 8 /*row -> (slot, factor)*/ + RMAX * 4 /*row abs-max*/ + EPI_STAGE_BYTES;
+constexpr int GROUP_TILES = 32;                // caller tiles (<= 4096 rows) one warp of the dedupe pass walks through
+constexpr int GROUP_CAP = 80;                  // compute-tile entries reserved per group (<= 4096/97 + 32 forced closes)
+constexpr int PAIR_FIXED_COST = 192;           // per-pair overhead of the cluster schedule, in output rows
 constexpr int SMEM_MAX = 227 * 1024;
 constexpr int HUB_BIG = 128;                    // hubs with more (padded) edge records are aggregated by a whole CTA
 constexpr int PT_MAXT = 2048;                  // tasks the pair-table kernel handles
@@ -84,21 +101,25 @@ constexpr int SCALE_TARGET = 13;               // scaled bound in [2^13, 2^14): 
 constexpr int SCALE_CLAMP = 100;
 
 // ---- plan (graph structure + tiling only; built once per packed set and operand mapping) ----
-struct PlanRec {      // 16 bytes per output row
+struct PlanRec {      // 16 bytes
   int r0, r1;         // mapped source rows of in-neighbours 0/1; hub row: r0 = slot, r1 = -1
   float n0, n1;       // their norms (0 = absent or dropped)
 };
-struct PairEnt {      // 64 bytes; nrows[1] = 0 when the task has an odd tile count
-  int row0[2], nrows[2];
-  int task, tile[2], pad;
-  int hub_eb[2], hub_ne[2];   // the tile's slice of the padded hub edge list: first record, record count
-  int pad2[4];
+struct CTile { int row0, nrows, nslots, task; };   // compute tile: output rows [row0, row0 + nrows), nslots <= 128 distinct records
+struct PairEnt {      // 64 bytes; nrows[1] = nslots[1] = 0 when the task has an odd tile count
+  int row0[2], nslots[2];     // first 16 bytes: what the gather producers need (slot s of a tile: srec[row0 + s])
+  int nrows[2], task, cost0;  // cost0: schedule cost of all pairs before this one
+  int pad[8];
 };
 struct Plan {
-  int* hdr;           // [0] n_hubs  [1] n_hub_edges  [2] n_pairs  [3] n_big_hubs
-  PlanRec* rec;       // [n_rows]
-  PairEnt* pairs;     // [cap_pairs] two tiles of the same task each
-  int2* tile_hubs;    // [n_tiles] (first record, record count) of the tile's slice of the hub edge list
+  int* hdr;           // [0] n_hubs  [1] n_hub_edges  [2] n_pairs  [3] n_big_hubs  [4] n_compute_tiles
+  PlanRec* rec;       // [n_rows] record of every output row (input of the dedupe pass)
+  PlanRec* srec;      // [n_rows] records of the slots of a compute tile at srec[tile.row0 + slot]
+  uint8_t* row_slot;  // [n_rows] slot of every output row inside its compute tile
+  CTile* ctiles;      // [n_groups * GROUP_CAP] compute tiles, per dedupe group
+  int* group_nt;      // [n_groups] compute tiles of the group; after pair_table_kernel: exclusive prefix
+  PairEnt* pairs;     // [cap_pairs] two compute tiles of the same task each
+  int* cl_beg;        // [kNumSMs / 2 + 1] first pair of every cluster: contiguous runs of equal schedule cost
   int* hub_row;       // [cap_hub] real row of each hub slot
   int* hub_beg;       // [cap_hub] first record of the slot
   int* hub_deg;       // [cap_hub]
@@ -106,7 +127,6 @@ struct Plan {
   // hub edge list, grouped by tile then hub, every hub padded to a multiple of 4 records (pads: norm 0)
   int* hub_src;       // [cap_edges] mapped source row
   float* hub_nrm;     // [cap_edges]
-  int* hub_slot;      // [cap_edges] hub slot the record belongs to
   int64_t total;
 };
 struct Workspace {
@@ -120,7 +140,8 @@ struct Workspace {
 };
 
 inline int64_t al(int64_t x) { return (x + 255) / 256 * 256; }
-inline int cap_pairs_for(int n_tiles, int n_tasks) { return (n_tiles + n_tasks) / 2 + 1; }
+inline int n_groups_for(int n_tiles) { return (n_tiles + GROUP_TILES - 1) / GROUP_TILES; }
+inline int cap_pairs_for(int n_tiles, int n_tasks) { return (n_groups_for(n_tiles) * GROUP_CAP + n_tasks) / 2 + 1; }
 inline int cap_hub_for(int n_rows, int n_edges) {
   const int64_t by_edges = (int64_t)n_edges / (PRE + 1) + 1;
   return (int)(by_edges < n_rows ? by_edges : n_rows) + 1;
@@ -135,11 +156,15 @@ struct Carver {
 Plan carve_plan(void* base, int n_tiles, int n_tasks, int n_rows, int n_edges) {
   Plan pl;
   Carver c{reinterpret_cast<char*>(base), 0};
-  const int cp = cap_pairs_for(n_tiles, n_tasks), ch = cap_hub_for(n_rows, n_edges);
+  const int cp = cap_pairs_for(n_tiles, n_tasks), ch = cap_hub_for(n_rows, n_edges), ng = n_groups_for(n_tiles);
   pl.hdr = reinterpret_cast<int*>(c.take(256));
   pl.rec = reinterpret_cast<PlanRec*>(c.take((int64_t)n_rows * 16));
+  pl.srec = reinterpret_cast<PlanRec*>(c.take((int64_t)n_rows * 16));
+  pl.row_slot = reinterpret_cast<uint8_t*>(c.take((int64_t)n_rows));
+  pl.ctiles = reinterpret_cast<CTile*>(c.take((int64_t)ng * GROUP_CAP * 16));
+  pl.group_nt = reinterpret_cast<int*>(c.take((int64_t)ng * 4));
   pl.pairs = reinterpret_cast<PairEnt*>(c.take((int64_t)cp * 64));
-  pl.tile_hubs = reinterpret_cast<int2*>(c.take((int64_t)n_tiles * 8));
+  pl.cl_beg = reinterpret_cast<int*>(c.take((kNumSMs / 2 + 1) * 4));
   pl.hub_row = reinterpret_cast<int*>(c.take((int64_t)ch * 4));
   pl.hub_beg = reinterpret_cast<int*>(c.take((int64_t)ch * 4));
   pl.hub_deg = reinterpret_cast<int*>(c.take((int64_t)ch * 4));
@@ -147,7 +172,6 @@ Plan carve_plan(void* base, int n_tiles, int n_tasks, int n_rows, int n_edges) {
   const int64_t ce = (int64_t)n_edges + 3LL * ch + 64;
   pl.hub_src = reinterpret_cast<int*>(c.take(ce * 4));
   pl.hub_nrm = reinterpret_cast<float*>(c.take(ce * 4));
-  pl.hub_slot = reinterpret_cast<int*>(c.take(ce * 4));
   pl.total = c.off;
   return pl;
 }
@@ -181,9 +205,11 @@ struct PairParams {
   const float* in_rowmax;
   const float* mlong;
   const float* mlong_bound;
-  const PlanRec* rec;
+  const PlanRec* srec;           // slot records of the compute tiles
+  const uint8_t* row_slot;       // output row -> slot of its compute tile
   const int* hdr;
   const PairEnt* pairs;
+  const int* cl_beg;             // first pair of every cluster (kNumSMs / 2 clusters), or NULL = equal pair counts
   const int32_t* dst_rows;
   const float* norm;
   const __half* w_image;
@@ -345,10 +371,11 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
   const uint32_t w_ready = bar0 + 8u * (2 * MAX_STAGES + 5);             // leader's: both CTAs hold the task's weights
   const uint32_t w_free = bar0 + 8u * (2 * MAX_STAGES + 6);              // per CTA: MMAs of the previous task are done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + BAR_BYTES - 16);
-  int8_t* scale_e = reinterpret_cast<int8_t*>(bars) + BAR_BYTES;               // [4][TM]
+  int8_t* scale_e = reinterpret_cast<int8_t*>(bars) + BAR_BYTES;               // [4][TM] per slot
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + BAR_BYTES + 4 * TM);   // [ACC_COLS]
-  float* rmax_s = bias_s + ACC_COLS;                                     // [2 tile parities][TM] row abs-max of the upper column half
-  float* epi_s = rmax_s + 2 * TM;                                        // [8 warps][32 rows][16 floats]
+  float2* rinfo_s = reinterpret_cast<float2*>(bias_s + ACC_COLS);        // [RMAX] (slot as int bits, output factor) of a tile's rows
+  float* rmax_s = reinterpret_cast<float*>(rinfo_s + RMAX);              // [RMAX] running row abs-max over the column blocks
+  float* epi_s = rmax_s + RMAX;                                          // [TM slots][EBLK floats]
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();   // SWIZZLE_128B operand tiles need a 1024-byte aligned base
@@ -375,13 +402,21 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // contiguous run of tile pairs for this cluster
+  // contiguous run of tile pairs for this cluster: equal schedule cost (output rows + a per-pair constant) from the
+  // plan when the grid is the full chip, equal pair counts otherwise
   const int n_pairs = p.hdr[2];
   const int n_cl = gridDim.x >> 1, cid = blockIdx.x >> 1;
-  const int ppc = (n_pairs + n_cl - 1) / n_cl;
-  const int p_beg = cid * ppc < n_pairs ? cid * ppc : n_pairs;
-  const int p_end = p_beg + ppc < n_pairs ? p_beg + ppc : n_pairs;
-  // row range of this CTA's tile in a pair entry (loaded as two 16-byte halves)
+  int p_beg, p_end;
+  if (p.cl_beg && n_cl == kNumSMs / 2) {
+    p_beg = p.cl_beg[cid];
+    p_end = p.cl_beg[cid + 1];
+  } else {
+    const int ppc = (n_pairs + n_cl - 1) / n_cl;
+    p_beg = cid * ppc < n_pairs ? cid * ppc : n_pairs;
+    p_end = p_beg + ppc < n_pairs ? p_beg + ppc : n_pairs;
+  }
+  // the gather side of this CTA's compute tile in a pair entry: its slots live at srec[row0 + s], s < nslots
+  // (the producers' "rows" below are slots: the distinct (sources, norms) records of the tile's output rows)
   auto ent_tile = [&](int pr, int& row0, int& nrows) {
     const int4 e = __ldg(reinterpret_cast<const int4*>(p.pairs + pr));
     row0 = rank ? e.y : e.x;
@@ -414,8 +449,8 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       ent_tile(p_beg, row0, nrows);
       if (p_beg + 1 < p_end) ent_tile(p_beg + 1, row0_n, nrows_n);
       int4 rcA = make_int4(0, 0, 0, 0), rcB = make_int4(0, 0, 0, 0);
-      if (rA < nrows) rcA = __ldg(reinterpret_cast<const int4*>(p.rec + row0 + rA));
-      if (rA + 64 < nrows) rcB = __ldg(reinterpret_cast<const int4*>(p.rec + row0 + rA + 64));
+      if (rA < nrows) rcA = __ldg(reinterpret_cast<const int4*>(p.srec + row0 + rA));
+      if (rA + 64 < nrows) rcB = __ldg(reinterpret_cast<const int4*>(p.srec + row0 + rA + 64));
       curA.decode(rcA, rA < nrows, p, sub);
       curB.decode(rcB, rA + 64 < nrows, p, sub);
       gather_request(buf0, curA, 0, p.dbg);
@@ -479,8 +514,8 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       PLAP(t_setup);
       for (int kc = 0; kc < nkc; kc += 2) {
         if (kc == 0) {
-          if (liveA_n) rcA_n = __ldg(reinterpret_cast<const int4*>(p.rec + row0_n + rA));
-          if (liveB_n) rcB_n = __ldg(reinterpret_cast<const int4*>(p.rec + row0_n + rA + 64));
+          if (liveA_n) rcA_n = __ldg(reinterpret_cast<const int4*>(p.srec + row0_n + rA));
+          if (liveB_n) rcB_n = __ldg(reinterpret_cast<const int4*>(p.srec + row0_n + rA + 64));
         }
         if (kc == ((nkc >> 2) << 1)) {
           nxtA.decode(rcA_n, liveA_n, p, sub);
@@ -590,20 +625,20 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       }
     }
   } else {
-    // ===================== epilogue (8 warps) =====================
-    // Warps 16..19 drain the lower half of the accumulator columns, warps 8..11 the upper half; warp w may
-    // read TMEM lanes 32*(w%4)..+31, so warps w and w+8 share the same 32 rows.  Per 16-column block:
-    // tcgen05.ld (the next block is already in flight) -> * norm * 2^-e -> transposed through shared memory
-    // so that a store instruction writes 8 rows x 64 contiguous bytes -> + bias, ReLU / mask, row abs-max.
+    // ===================== epilogue (8 warps): accumulator slots -> output rows =====================
+    // Warp w may read TMEM lanes 32*(w%4)..+31 (= slots), so warps w and w+8 share 32 slots and take 16 of a block's
+    // 32 columns each.  Per 32-column block: tcgen05.ld (the next block is already in flight) -> raw accumulators
+    // into a [128 slots][32 columns] shared-memory block (16-byte units XOR-swizzled by slot) -> one named barrier
+    // -> all eight warps expand the block to the tile's output rows: a lane octet per row reads its slot's 128 bytes,
+    // * norm[v] * 2^-e(slot) * 2^-e(W) + bias, ReLU / mask, running row abs-max, one 128-byte row segment per octet.
     reg_set<REGS_EPI>();
     const int quarter = warp & 3;
     const int half = warp < WARP_EPI0 ? 1 : 0;
-    const int r = quarter * 32 + lane;       // accumulator row of this lane
-    const int et = half * 128 + r;           // index among the 256 epilogue threads
-    float* stg = epi_s + (half * 4 + quarter) * 32 * 16;   // [32 rows][4 x 16-byte units, unit ^ ((row / 2) % 4)]
-    const int tr = lane >> 2, tu = lane & 3; // transposed side: rows 8*i + tr, 16-byte unit tu of the 16-column block
-    const int nblk = N >> 4;
-    const int blk0 = half ? (nblk + 1) >> 1 : 0, blk1 = half ? nblk : (nblk + 1) >> 1;
+    const int ew = half * 4 + quarter;       // epilogue warp 0..7
+    const int et = ew * 32 + lane;           // index among the 256 epilogue threads
+    const int oct = lane >> 3, u = lane & 7; // expansion: octet `oct` of the warp owns a row, lane u its 16-byte unit
+    const int slot_l = quarter * 32 + lane;  // staging: the accumulator row (slot) this lane drains
+    const int nblk = (N + EBLK - 1) / EBLK;
     int ti = 0, bias_task = -1;
 #if GMETA_PAIR_PROF
     long long t_wacc = 0, t_epi = 0, t_mark = clock64();
@@ -613,98 +648,146 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
 #endif
     for (int pr = p_beg; pr < p_end; ++pr, ++ti) {
       const int buf = ti & 1;
-      const PairEnt* ent = p.pairs + pr;
-      const int row0 = __ldg(&ent->row0[rank]), nrows = __ldg(&ent->nrows[rank]), task = __ldg(&ent->task);
-      const bool live = r < nrows;
-      const int oi = row0 + (live ? r : 0);                           // output row (compact or dense)
-      const int v = p.dst_rows ? p.dst_rows[oi] : oi;                 // real row: norm and mask
-      const float nv = p.norm[v];
+      const int4 e0 = __ldg(reinterpret_cast<const int4*>(p.pairs + pr));
+      const int4 e1 = __ldg(reinterpret_cast<const int4*>(p.pairs + pr) + 1);
+      const int row0 = rank ? e0.y : e0.x, nrows = rank ? e1.y : e1.x, task = e1.z;
+      // row -> (slot, norm) of this tile's output rows, requested before the accumulators are waited for
+      int rs[RMAX / 256];
+      float rn[RMAX / 256];
+#pragma unroll
+      for (int j = 0; j < RMAX / 256; ++j) {
+        const int r = et + 256 * j;
+        rs[j] = 0;
+        rn[j] = 0.f;
+        if (r < nrows) {
+          rs[j] = (int)__ldg(p.row_slot + row0 + r);
+          rn[j] = p.norm[p.dst_rows ? p.dst_rows[row0 + r] : row0 + r];
+        }
+      }
       const float wis = p.w_inv_scale[p.image_task_stride ? task : 0];
+      // every epilogue warp is done with the previous tile's row table, bias and staging blocks
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (task != bias_task) {     // the task's bias -> shared memory, once per task
         bias_task = task;
-        asm volatile("bar.sync 2, 256;" ::: "memory");     // every epilogue warp is done with the old bias
         const float* bias = p.bias ? p.bias + (long long)task * p.b_task_stride : nullptr;
         if (et < ACC_COLS) bias_s[et] = (bias && et < N) ? bias[et] : 0.f;
-        asm volatile("bar.sync 2, 256;" ::: "memory");
       }
       ELAP(t_epi);
       mbar_wait(acc_full(buf), (uint32_t)((ti >> 1) & 1), 7);
       ELAP(t_wacc);
       tc_fence_after();
-      const float f = live ? nv * exp2i(-(int)scale_e[(ti & 3) * TM + r]) * wis : 0.f;
-      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * ACC_COLS);
-      float pmax[4];
-      float* orow[4];                         // transposed side: output row pointers (nullptr: past the tile's rows)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        pmax[i] = 0.f;
-        const int rr = quarter * 32 + 8 * i + tr;
-        orow[i] = rr < nrows ? p.out + (size_t)(row0 + rr) * p.ld_out + 4 * tu : nullptr;
+      for (int j = 0; j < RMAX / 256; ++j) {
+        const int r = et + 256 * j;
+        if (r < nrows)
+          rinfo_s[r] = make_float2(__int_as_float(rs[j]), rn[j] * exp2i(-(int)scale_e[(ti & 3) * TM + rs[j]]) * wis);
       }
-      uint32_t acc_n[16];
-      if (blk0 < blk1) tmem_ld16(t_addr + (uint32_t)(blk0 * 16), acc_n);
-      for (int blk = blk0; blk < blk1; ++blk) {
-        const int c0 = blk * 16;
-        uint32_t acc[16];
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * ACC_COLS + 32 * half);
+      uint32_t acc_n[32];
+      if (32 * half < N) tmem_ld32(t_addr, acc_n);
+      for (int blk = 0; blk < nblk; ++blk) {
+        const bool mine = blk * EBLK + 32 * half < N;     // this warp's 32 columns of the block exist
         tmem_ld_wait();
+        if (blk) asm volatile("bar.sync 1, 256;" ::: "memory");     // the previous block has been expanded by everybody
+        if (mine) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = acc_n[j];
-        if (blk + 1 < blk1) tmem_ld16(t_addr + (uint32_t)(c0 + 16), acc_n);   // next block in flight
-        __syncwarp();                             // the previous block's transposed reads are done
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          st_f4(stg + lane * 16 + ((u ^ ((lane >> 1) & 3)) << 2),
-                make_float4(f * __uint_as_float(acc[4 * u]), f * __uint_as_float(acc[4 * u + 1]),
-                            f * __uint_as_float(acc[4 * u + 2]), f * __uint_as_float(acc[4 * u + 3])));
-        __syncwarp();
-        const float4 b4 = ld_f4(bias_s + c0 + 4 * tu);
-        float4 t4[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rr = 8 * i + tr;
-          t4[i] = ld_f4(stg + rr * 16 + ((tu ^ ((rr >> 1) & 3)) << 2));
+          for (int j = 0; j < 8; ++j)
+            st_f4(epi_s + slot_l * EBLK + ((8 * half + (j ^ (slot_l & 7))) << 2),
+                  make_float4(__uint_as_float(acc_n[4 * j]), __uint_as_float(acc_n[4 * j + 1]),
+                              __uint_as_float(acc_n[4 * j + 2]), __uint_as_float(acc_n[4 * j + 3])));
         }
+        if (blk + 1 < nblk) {
+          if ((blk + 1) * EBLK + 32 * half < N) tmem_ld32(t_addr + (uint32_t)((blk + 1) * EBLK), acc_n);   // next block in flight
+        } else {
+          tc_fence_before();          // the tile's accumulators have been read: hand the buffer back
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (blk + 1 == nblk && lane == 0) mbar_arrive_cluster(acc_empty(buf), 0);
+        // expansion: lane u of an octet holds columns [c0, c0 + 4) and [c0 + 32, c0 + 36) of the octet's row
+        const int c0 = blk * EBLK + 4 * u;
+        const bool ok0 = c0 < N, ok1 = c0 + 32 < N;
+        const float4 b0 = ok0 ? ld_f4(bias_s + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 b1 = ok1 ? ld_f4(bias_s + c0 + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool relu = (p.relu & 1) != 0, last = blk + 1 == nblk;
+        const float* msk = p.relu_mask;
+        float* const outp = p.out + c0;
+        float* const rmx = p.out_rowmax;
+        const int ldo = p.ld_out;
+        const bool st_on = !(p.dbg & 1);
+        constexpr int UNR = 2;
+        for (int rb = ew * 4; rb < nrows; rb += 32 * UNR) {
+          float2 ri[UNR];
+          float4 x0[UNR], x1[UNR];
+          bool live[UNR];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rr = 8 * i + tr;
-          int vr = 0;
-          if (p.relu_mask) vr = __shfl_sync(0xffffffffu, v, rr);   // real row of tile row quarter*32 + rr
-          if (orow[i]) {
-            float4 w4 = t4[i];
-            w4.x += b4.x; w4.y += b4.y; w4.z += b4.z; w4.w += b4.w;
-            if (p.relu & 1) { w4.x = fmaxf(w4.x, 0.f); w4.y = fmaxf(w4.y, 0.f); w4.z = fmaxf(w4.z, 0.f); w4.w = fmaxf(w4.w, 0.f); }
-            if (p.relu_mask) {
-              const float4 m4 = ld_f4(p.relu_mask + (size_t)((p.relu & 2) ? row0 + quarter * 32 + rr : vr) * p.ld_out + c0 + 4 * tu);
-              if (!(m4.x > 0.f)) w4.x = 0.f;
-              if (!(m4.y > 0.f)) w4.y = 0.f;
-              if (!(m4.z > 0.f)) w4.z = 0.f;
-              if (!(m4.w > 0.f)) w4.w = 0.f;
-            }
-            if (p.out_rowmax) pmax[i] = fmaxf(pmax[i], fmaxf(fmaxf(fabsf(w4.x), fabsf(w4.y)), fmaxf(fabsf(w4.z), fabsf(w4.w))));
-            if (!(p.dbg & 1)) st_f4(orow[i] + c0, w4);
+          for (int j = 0; j < UNR; ++j) {
+            const int r = rb + 32 * j + oct;
+            live[j] = r < nrows;
+            ri[j] = rinfo_s[live[j] ? r : 0];
           }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(acc_empty(buf), 0);
-      if (p.out_rowmax) {
-        // row abs-max over all columns: the upper-half warp hands its part to the lower-half warp of the same rows
-        float* rm = rmax_s + (ti & 1) * TM + quarter * 32;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float m = pmax[i];
-          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-          pmax[i] = m;
-          if (half && tu == 0) rm[8 * i + tr] = m;
-        }
-        asm volatile("bar.sync %0, 64;" ::"r"(3 + quarter) : "memory");
-        if (!half && tu == 0) {
+          for (int j = 0; j < UNR; ++j) {
+            const int slot = __float_as_int(ri[j].x);
+            const float* srow = epi_s + slot * EBLK + ((u ^ (slot & 7)) << 2);
+            x0[j] = ld_f4(srow);
+            x1[j] = ld_f4(srow + 32);
+          }
+          float mx[UNR];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rr = 8 * i + tr;
-            if (quarter * 32 + rr < nrows) p.out_rowmax[row0 + quarter * 32 + rr] = fmaxf(pmax[i], rm[rr]);
+          for (int j = 0; j < UNR; ++j) {
+            const int r = rb + 32 * j + oct;
+            const float f = ri[j].y;
+            float4 w0 = make_float4(fmaf(f, x0[j].x, b0.x), fmaf(f, x0[j].y, b0.y), fmaf(f, x0[j].z, b0.z), fmaf(f, x0[j].w, b0.w));
+            float4 w1 = make_float4(fmaf(f, x1[j].x, b1.x), fmaf(f, x1[j].y, b1.y), fmaf(f, x1[j].z, b1.z), fmaf(f, x1[j].w, b1.w));
+            if (relu) {
+              w0.x = fmaxf(w0.x, 0.f); w0.y = fmaxf(w0.y, 0.f); w0.z = fmaxf(w0.z, 0.f); w0.w = fmaxf(w0.w, 0.f);
+              w1.x = fmaxf(w1.x, 0.f); w1.y = fmaxf(w1.y, 0.f); w1.z = fmaxf(w1.z, 0.f); w1.w = fmaxf(w1.w, 0.f);
+            }
+            const size_t orow = (size_t)(row0 + r) * ldo;
+            if (msk && live[j]) {
+              const int oi = row0 + r;
+              const int mr = (p.relu & 2) ? oi : (p.dst_rows ? p.dst_rows[oi] : oi);    // compact mask / mask by real row
+              const float* mp = msk + (size_t)mr * ldo + c0;
+              if (ok0) {
+                const float4 m4 = ld_f4(mp);
+                if (!(m4.x > 0.f)) w0.x = 0.f;
+                if (!(m4.y > 0.f)) w0.y = 0.f;
+                if (!(m4.z > 0.f)) w0.z = 0.f;
+                if (!(m4.w > 0.f)) w0.w = 0.f;
+              }
+              if (ok1) {
+                const float4 m4 = ld_f4(mp + 32);
+                if (!(m4.x > 0.f)) w1.x = 0.f;
+                if (!(m4.y > 0.f)) w1.y = 0.f;
+                if (!(m4.z > 0.f)) w1.z = 0.f;
+                if (!(m4.w > 0.f)) w1.w = 0.f;
+              }
+            }
+            if (live[j] && st_on) {
+              if (ok0) st_f4(outp + orow, w0);
+              if (ok1) st_f4(outp + orow + 32, w1);
+            }
+            float m = 0.f;
+            if (ok0) m = fmaxf(fmaxf(fabsf(w0.x), fabsf(w0.y)), fmaxf(fabsf(w0.z), fabsf(w0.w)));
+            if (ok1) m = fmaxf(m, fmaxf(fmaxf(fabsf(w1.x), fabsf(w1.y)), fmaxf(fabsf(w1.z), fabsf(w1.w))));
+            mx[j] = m;
+          }
+          if (rmx) {
+            // row abs-max over the octet's lanes: the butterflies of the UNR rows are independent and overlap
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1)
+#pragma unroll
+              for (int j = 0; j < UNR; ++j) mx[j] = fmaxf(mx[j], __shfl_xor_sync(0xffffffffu, mx[j], o));
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+              const int r = rb + 32 * j + oct;
+              if (live[j] && u == 0) {          // the same lane owns row r in every block: no synchronisation needed
+                float m = mx[j];
+                if (blk) m = fmaxf(m, rmax_s[r]);
+                if (!last) rmax_s[r] = m;
+                else rmx[row0 + r] = m;
+              }
+            }
           }
         }
       }
@@ -952,7 +1035,6 @@ __global__ void plan_tiles_kernel(const int32_t* __restrict__ indptr, const int3
     }
     hbase = __shfl_sync(0xffffffffu, hbase, 0);
     ebase = __shfl_sync(0xffffffffu, ebase, 0);
-    if (lane == 0) pl.tile_hubs[tile] = make_int2(ebase, n_e);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int r = 32 * j + lane;
@@ -1001,23 +1083,125 @@ __global__ void plan_hub_edges_kernel(const int32_t* __restrict__ indptr, const 
       }
       pl.hub_src[dst + e] = s < 0 ? 0 : s;
       pl.hub_nrm[dst + e] = s < 0 ? 0.f : nr;
-      pl.hub_slot[dst + e] = slot;
     }
   }
 }
 
-// tiles -> pairs of tiles of the same task (tiles of a task are contiguous in the tile table)
-__global__ void __launch_bounds__(1024) pair_table_kernel(const int32_t* __restrict__ tile_row0,
+// ------------------------------------------------------------------------------------------
+// compute tiles: runs of consecutive output rows with at most TM distinct records
+// ------------------------------------------------------------------------------------------
+// One warp walks GROUP_TILES consecutive caller tiles (<= 4096 rows) in batches of 32 rows and assigns every row
+// the slot of its record (r0, r1, n0, n1) inside the current compute tile: the distinct records of a batch are
+// taken in lane order, each looked up among the tile's slots by the whole warp (<= 4 comparisons per lane) and
+// appended when new -- deterministic, no atomics.  A compute tile is closed before a batch that could overflow
+// TM slots or RMAX rows, at a task change, and at the end of the group.  Rows sharing a record produce the same
+// aggregated row, so only the slots are gathered and contracted; the epilogue expands them (see the header).
+__global__ void __launch_bounds__(128) plan_dedupe_kernel(const int32_t* __restrict__ tile_row0,
                                                           const int32_t* __restrict__ tile_nrows,
-                                                          const int32_t* __restrict__ tile_task, int n_tiles,
-                                                          int n_tasks, Plan pl) {
+                                                          const int32_t* __restrict__ tile_task, int n_tiles, Plan pl) {
+  __shared__ int4 skeys[4][TM];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int g = blockIdx.x * 4 + w;
+  if (g * GROUP_TILES >= n_tiles) return;
+  int4* keys = skeys[w];
+  CTile* out = pl.ctiles + (size_t)g * GROUP_CAP;
+  int nt = 0;                 // compute tiles emitted by this group
+  bool open = false;
+  int c_row0 = 0, c_rows = 0, c_cnt = 0, c_task = 0;
+  auto close = [&]() {
+    if (open && c_rows > 0) {
+      if (lane == 0) out[nt] = CTile{c_row0, c_rows, c_cnt, c_task};
+      ++nt;
+    }
+    open = false;
+  };
+  const int t_end = min(n_tiles, (g + 1) * GROUP_TILES);
+  for (int tile = g * GROUP_TILES; tile < t_end; ++tile) {
+    const int row0 = tile_row0[tile], nrows = tile_nrows[tile], task = tile_task[tile];
+    if (open && (task != c_task || row0 != c_row0 + c_rows)) close();
+    for (int b = 0; b < nrows; b += 32) {
+      if (open && (c_cnt + 32 > TM || c_rows + 32 > RMAX)) close();
+      if (!open) { open = true; c_row0 = row0 + b; c_rows = 0; c_cnt = 0; c_task = task; }
+      const bool valid = b + lane < nrows;
+      int4 key = make_int4(0, 0, 0, 0);
+      if (valid) key = *reinterpret_cast<const int4*>(pl.rec + row0 + b + lane);
+      int my_slot = 0;
+      unsigned todo = __ballot_sync(0xffffffffu, valid);
+      while (todo) {
+        const int l = __ffs(todo) - 1;
+        int4 kl;
+        kl.x = __shfl_sync(0xffffffffu, key.x, l);
+        kl.y = __shfl_sync(0xffffffffu, key.y, l);
+        kl.z = __shfl_sync(0xffffffffu, key.z, l);
+        kl.w = __shfl_sync(0xffffffffu, key.w, l);
+        const bool same = valid && key.x == kl.x && key.y == kl.y && key.z == kl.z && key.w == kl.w;
+        const unsigned grp = __ballot_sync(0xffffffffu, same);
+        int found = -1;
+        for (int s = lane; s < c_cnt; s += 32) {
+          const int4 k = keys[s];
+          if (k.x == kl.x && k.y == kl.y && k.z == kl.z && k.w == kl.w) found = s;
+        }
+        const unsigned fb = __ballot_sync(0xffffffffu, found >= 0);
+        int slot;
+        if (fb) {
+          slot = __shfl_sync(0xffffffffu, found, __ffs(fb) - 1);
+        } else {
+          slot = c_cnt;
+          if (lane == 0) {
+            keys[c_cnt] = kl;
+            *reinterpret_cast<int4*>(pl.srec + c_row0 + c_cnt) = kl;
+          }
+          ++c_cnt;
+          __syncwarp();
+        }
+        if (same) my_slot = slot;
+        todo &= ~grp;
+      }
+      if (valid) pl.row_slot[row0 + b + lane] = (uint8_t)my_slot;
+      c_rows += min(32, nrows - b);
+    }
+  }
+  close();
+  if (lane == 0) pl.group_nt[g] = nt;
+}
+
+// in-place exclusive prefix sum of a[0..n) by one CTA; returns the total (in every thread)
+__device__ int block_excl_scan(int* __restrict__ a, int n, int* sh /* [blockDim.x + 1] */) {
+  int carry = 0;
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int x = i < n ? a[i] : 0;
+    sh[threadIdx.x] = x;
+    __syncthreads();
+    for (int d = 1; d < blockDim.x; d <<= 1) {
+      const int y = threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += y;
+      __syncthreads();
+    }
+    if (i < n) a[i] = carry + sh[threadIdx.x] - x;
+    carry += sh[blockDim.x - 1];
+    __syncthreads();
+  }
+  return carry;
+}
+
+// compute tiles -> pairs of tiles of the same task (the tiles of a task are contiguous: groups follow the row
+// order), the schedule cost in front of every pair and the first pair of every cluster
+__global__ void __launch_bounds__(1024) pair_table_kernel(int n_groups, int n_tasks, Plan pl) {
   __shared__ int first[PT_MAXT], cnt[PT_MAXT], base[PT_MAXT], tmp[PT_MAXT];
+  __shared__ int sh[1025];
   for (int t = threadIdx.x; t < n_tasks; t += blockDim.x) { first[t] = 0x7fffffff; cnt[t] = 0; }
   __syncthreads();
-  for (int i = threadIdx.x; i < n_tiles; i += blockDim.x) {
-    const int t = tile_task[i];
-    atomicMin(&first[t], i);
-    atomicAdd(&cnt[t], 1);
+  // dense index of every compute tile = (tiles of the groups before it) + position inside its group
+  const int n_ct = block_excl_scan(pl.group_nt, n_groups, sh);
+  for (int g = threadIdx.x; g < n_groups; g += blockDim.x) {
+    const int d0 = pl.group_nt[g], d1 = g + 1 < n_groups ? pl.group_nt[g + 1] : n_ct;
+    for (int j = 0; j < d1 - d0; ++j) {
+      const int t = pl.ctiles[(size_t)g * GROUP_CAP + j].task;
+      atomicMin(&first[t], d0 + j);
+      atomicAdd(&cnt[t], 1);
+    }
   }
   __syncthreads();
   // inclusive scan of ceil(cnt/2) over tasks (Hillis-Steele, double buffered)
@@ -1033,26 +1217,56 @@ __global__ void __launch_bounds__(1024) pair_table_kernel(const int32_t* __restr
   const int total = n_tasks > 0 ? a[n_tasks - 1] : 0;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     PairEnt e;
-    e.row0[0] = e.row0[1] = e.nrows[0] = e.nrows[1] = e.task = e.pad = 0;
-    e.tile[0] = e.tile[1] = -1;
-    e.hub_eb[0] = e.hub_eb[1] = e.hub_ne[0] = e.hub_ne[1] = 0;
-    e.pad2[0] = e.pad2[1] = e.pad2[2] = e.pad2[3] = 0;
+    e.row0[0] = e.row0[1] = e.nslots[0] = e.nslots[1] = e.nrows[0] = e.nrows[1] = e.task = e.cost0 = 0;
+    for (int k = 0; k < 8; ++k) e.pad[k] = 0;
     pl.pairs[i] = e;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < n_tiles; i += blockDim.x) {
-    const int t = tile_task[i];
-    const int j = i - first[t];
-    PairEnt* e = pl.pairs + a[t] - ((cnt[t] + 1) >> 1) + (j >> 1);
-    e->row0[j & 1] = tile_row0[i];
-    e->nrows[j & 1] = tile_nrows[i];
-    e->tile[j & 1] = i;
-    const int2 th = pl.tile_hubs[i];
-    e->hub_eb[j & 1] = th.x;
-    e->hub_ne[j & 1] = th.y;
-    if (!(j & 1)) e->task = t;
+  for (int g = threadIdx.x; g < n_groups; g += blockDim.x) {
+    const int d0 = pl.group_nt[g], d1 = g + 1 < n_groups ? pl.group_nt[g + 1] : n_ct;
+    for (int j = 0; j < d1 - d0; ++j) {
+      const CTile ct = pl.ctiles[(size_t)g * GROUP_CAP + j];
+      const int t = ct.task;
+      const int jj = d0 + j - first[t];
+      PairEnt* e = pl.pairs + a[t] - ((cnt[t] + 1) >> 1) + (jj >> 1);
+      e->row0[jj & 1] = ct.row0;
+      e->nslots[jj & 1] = ct.nslots;
+      e->nrows[jj & 1] = ct.nrows;
+      if (!(jj & 1)) e->task = t;
+    }
   }
-  if (threadIdx.x == 0) pl.hdr[2] = total;
+  __syncthreads();
+  // schedule cost in front of every pair (its output rows + a per-pair constant), then the cluster boundaries:
+  // pair i goes to cluster floor(cost0[i] * n_cl / total_cost) -- contiguous runs, tasks stay together
+  int carry = 0;
+  for (int b0 = 0; b0 < total; b0 += blockDim.x) {
+    const int i = b0 + threadIdx.x;
+    const int x = i < total ? pl.pairs[i].nrows[0] + pl.pairs[i].nrows[1] + PAIR_FIXED_COST : 0;
+    sh[threadIdx.x] = x;
+    __syncthreads();
+    for (int d = 1; d < blockDim.x; d <<= 1) {
+      const int y = threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += y;
+      __syncthreads();
+    }
+    if (i < total) pl.pairs[i].cost0 = carry + sh[threadIdx.x] - x;
+    carry += sh[blockDim.x - 1];
+    __syncthreads();
+  }
+  const long long total_cost = carry;
+  constexpr int n_cl = kNumSMs / 2;
+  for (int c = threadIdx.x; c <= n_cl; c += blockDim.x) {
+    // first pair whose cost0 >= c * total_cost / n_cl
+    const long long want = (total_cost * c + n_cl - 1) / n_cl;
+    int lo = 0, hi = total;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (pl.pairs[mid].cost0 < want) lo = mid + 1; else hi = mid;
+    }
+    pl.cl_beg[c] = c == n_cl ? total : lo;
+  }
+  if (threadIdx.x == 0) { pl.hdr[2] = total; pl.hdr[4] = n_ct; }
 }
 
 int g_pair_dbg = 0;
@@ -1099,7 +1313,10 @@ int layer_plan_build(const int32_t* indptr, const int32_t* indices, const float*
   if ((rc = check_launch()) != GMETA_OK) return rc;
   plan_hub_edges_kernel<<<4 * kNumSMs, 256, 0, stream>>>(indptr, indices, norm, in_row_map, pl);
   if ((rc = check_launch()) != GMETA_OK) return rc;
-  pair_table_kernel<<<1, 1024, 0, stream>>>(tile_row0, tile_nrows, tile_task, n_tiles, n_tasks, pl);
+  const int n_groups = n_groups_for(n_tiles);
+  plan_dedupe_kernel<<<ceil_div(n_groups, 4), 128, 0, stream>>>(tile_row0, tile_nrows, tile_task, n_tiles, pl);
+  if ((rc = check_launch()) != GMETA_OK) return rc;
+  pair_table_kernel<<<1, 1024, 0, stream>>>(n_groups, n_tasks, pl);
   return check_launch();
 }
 
@@ -1154,7 +1371,7 @@ int gcn_layer_fwd_pair(const GatherSrc& g, const int32_t* tile_row0, const int32
   PairParams p;
   p.in = g.in; p.ld_in = g.ld_in; p.f_in = K; p.in_rowmax = in_rowmax;
   p.mlong = ws.mlong; p.mlong_bound = ws.mlong_bound;
-  p.rec = pl.rec; p.hdr = pl.hdr; p.pairs = pl.pairs;
+  p.srec = pl.srec; p.row_slot = pl.row_slot; p.hdr = pl.hdr; p.pairs = pl.pairs; p.cl_beg = pl.cl_beg;
   p.dst_rows = g.dst_rows; p.norm = g.norm;
   p.w_image = ws.w_image; p.image_task_stride = n_copies > 1 ? 2LL * K * N : 0; p.w_inv_scale = ws.w_inv_scale;
   p.bias = bias; p.b_task_stride = b_task_stride; p.f_out = N; p.relu = relu; p.relu_mask = relu_mask;
