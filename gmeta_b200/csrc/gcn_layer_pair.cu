@@ -67,16 +67,17 @@ constexpr int A_HALF_BYTES = TM * 64;          // 8 KB: hi (or lo) operand tile 
 constexpr int STAGE_BYTES = 2 * A_HALF_BYTES;  // 16 KB
 // warp roles (register budgets are re-balanced per warpgroup with setmaxnreg)
 constexpr int N_PROD_WARPS = 8;                // warps 0..7   gather producers
-constexpr int WARP_EPI_B0 = 8;                 // warps 8..11  epilogue, upper half of the output columns
+constexpr int WARP_EPI_B0 = 8;                 // warps 8..11  epilogue (first four of sixteen)
 constexpr int WARP_LOAD = 12;                  // warp 12      weight loader (+ TMEM allocation)
 constexpr int WARP_MMA = 13;                   // warp 13      MMA issuer (14, 15 idle)
-constexpr int WARP_EPI0 = 16;                  // warps 16..19 epilogue, lower half of the output columns
-constexpr int N_EPI_WARPS = 8;
-constexpr int NTHREADS = 20 * 32;
-constexpr int REGS_ENTRY = 96;                 // registers per thread at launch: 64K / 640 threads, rounded down to 8
-constexpr int REGS_PROD = 120, REGS_CTRL = 24, REGS_EPI = 96;
-// setmaxnreg re-distributes the registers the CTA got at launch (640 threads x 96 = 61440)
-static_assert(8 * 32 * REGS_PROD + 4 * 32 * REGS_CTRL + 8 * 32 * REGS_EPI <= NTHREADS * REGS_ENTRY,
+constexpr int WARP_EPI0 = 16;                  // warps 16..27 epilogue as well (the expansion is latency-bound: 16 warps)
+constexpr int N_EPI_WARPS = 16;
+constexpr int N_EPI_THREADS = N_EPI_WARPS * 32;
+constexpr int NTHREADS = 28 * 32;
+constexpr int REGS_ENTRY = 72;                 // registers per thread at launch: 64K / 896 threads, rounded down to 8
+constexpr int REGS_PROD = 112, REGS_CTRL = 24, REGS_EPI = 64;
+// setmaxnreg re-distributes the registers the CTA got at launch (896 threads x 72 = 64512)
+static_assert(8 * 32 * REGS_PROD + 4 * 32 * REGS_CTRL + N_EPI_WARPS * 32 * REGS_EPI <= NTHREADS * REGS_ENTRY,
               "register budget");
 #ifndef GMETA_PAIR_PROF
 #define GMETA_PAIR_PROF 0      // 1: per-role cycle counters (costs registers; debug builds only)
@@ -349,6 +350,114 @@ template <> struct VecLd<2> {
     *reinterpret_cast<float2*>(p) = make_float2(d[0], d[1]);
   }
 };
+
+// Expansion of one staged accumulator block to the output rows of a compute tile (epilogue warps).  `stg` is the
+// [TM slots][EBLK] block (16-byte units XOR-swizzled by slot), rinfo[r] = (slot, factor) of tile row r.  Octet `oct`
+// of epilogue warp `ew` owns rows ew*4 + oct + 64*i; its lane u holds columns [c0, c0+4) and [c0+32, c0+36).
+struct ExpandArgs {
+  const float* stg;
+  const float2* rinfo;
+  float* rmax_s;
+  const float* bias_s;
+  float* out;            // + row0 * ld_out already applied
+  float* out_rowmax;     // + row0 already applied (RMX)
+  const float* mask;     // MASK: relu_mask base
+  const int32_t* dst_rows;
+  int ld_out, nrows, row0, n_cols, blk, nblk, relu, store;
+};
+template <bool MASK, bool RMX>
+__device__ __forceinline__ void expand_block(const ExpandArgs& a, int ew, int lane) {
+  constexpr int UNR = 2;
+  constexpr int RSTEP = N_EPI_WARPS * 4;       // rows the epilogue warps cover per pass
+  const int oct = lane >> 3, u = lane & 7;
+  const int c0 = a.blk * EBLK + 4 * u;
+  const bool ok0 = c0 < a.n_cols, ok1 = c0 + 32 < a.n_cols;
+  const float4 b0 = ok0 ? ld_f4(a.bias_s + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 b1 = ok1 ? ld_f4(a.bias_s + c0 + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool relu = (a.relu & 1) != 0, first = a.blk == 0, last = a.blk + 1 == a.nblk;
+  const int nrows = a.nrows, ldo = a.ld_out;
+  const bool st0 = ok0 && a.store, st1 = ok1 && a.store;
+  const float* const stg_u = a.stg;
+  float* const outp = a.out + c0;
+  for (int rb = ew * 4 + oct; rb < nrows + oct; rb += RSTEP * UNR) {   // rb - oct < nrows: uniform trip count per warp
+    float2 ri[UNR];
+    float4 x0[UNR], x1[UNR];
+#pragma unroll
+    for (int j = 0; j < UNR; ++j) {
+      const int r = rb + RSTEP * j;
+      ri[j] = a.rinfo[r < nrows ? r : 0];
+    }
+#pragma unroll
+    for (int j = 0; j < UNR; ++j) {
+      const int slot = __float_as_int(ri[j].x);
+      const float* srow = stg_u + slot * EBLK + ((u ^ (slot & 7)) << 2);
+      x0[j] = ld_f4(srow);
+      x1[j] = ld_f4(srow + 32);
+    }
+    float mx[UNR];
+#pragma unroll
+    for (int j = 0; j < UNR; ++j) {
+      const int r = rb + RSTEP * j;
+      const bool live = r < nrows;
+      const float f = ri[j].y;
+      float4 w0 = make_float4(fmaf(f, x0[j].x, b0.x), fmaf(f, x0[j].y, b0.y), fmaf(f, x0[j].z, b0.z), fmaf(f, x0[j].w, b0.w));
+      float4 w1 = make_float4(fmaf(f, x1[j].x, b1.x), fmaf(f, x1[j].y, b1.y), fmaf(f, x1[j].z, b1.z), fmaf(f, x1[j].w, b1.w));
+      if (relu) {
+        w0.x = fmaxf(w0.x, 0.f); w0.y = fmaxf(w0.y, 0.f); w0.z = fmaxf(w0.z, 0.f); w0.w = fmaxf(w0.w, 0.f);
+        w1.x = fmaxf(w1.x, 0.f); w1.y = fmaxf(w1.y, 0.f); w1.z = fmaxf(w1.z, 0.f); w1.w = fmaxf(w1.w, 0.f);
+      }
+      if (MASK) {
+        if (live) {
+          const int oi = a.row0 + r;
+          const int mr = (a.relu & 2) ? oi : (a.dst_rows ? a.dst_rows[oi] : oi);    // compact mask / mask by real row
+          const float* mp = a.mask + (size_t)mr * ldo + c0;
+          if (ok0) {
+            const float4 m4 = ld_f4(mp);
+            if (!(m4.x > 0.f)) w0.x = 0.f;
+            if (!(m4.y > 0.f)) w0.y = 0.f;
+            if (!(m4.z > 0.f)) w0.z = 0.f;
+            if (!(m4.w > 0.f)) w0.w = 0.f;
+          }
+          if (ok1) {
+            const float4 m4 = ld_f4(mp + 32);
+            if (!(m4.x > 0.f)) w1.x = 0.f;
+            if (!(m4.y > 0.f)) w1.y = 0.f;
+            if (!(m4.z > 0.f)) w1.z = 0.f;
+            if (!(m4.w > 0.f)) w1.w = 0.f;
+          }
+        }
+      }
+      float* o = outp + (size_t)r * ldo;
+      if (live && st0) st_f4(o, w0);
+      if (live && st1) st_f4(o + 32, w1);
+      if (RMX) {
+        float m = 0.f;
+        if (ok0) m = fmaxf(fmaxf(fabsf(w0.x), fabsf(w0.y)), fmaxf(fabsf(w0.z), fabsf(w0.w)));
+        if (ok1) m = fmaxf(m, fmaxf(fmaxf(fabsf(w1.x), fabsf(w1.y)), fmaxf(fabsf(w1.z), fabsf(w1.w))));
+        mx[j] = m;
+      }
+    }
+    if (RMX) {
+      // row abs-max over the octet's lanes: the butterflies of the UNR rows are independent and overlap
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1)
+#pragma unroll
+        for (int j = 0; j < UNR; ++j) mx[j] = fmaxf(mx[j], __shfl_xor_sync(0xffffffffu, mx[j], o));
+      if (u == 0) {          // the same lane owns row r in every block: no synchronisation needed
+#pragma unroll
+        for (int j = 0; j < UNR; ++j) {
+          const int r = rb + RSTEP * j;
+          if (r < nrows) {
+            float m = mx[j];
+            if (!first) m = fmaxf(m, a.rmax_s[r]);
+            if (!last) a.rmax_s[r] = m;
+            else a.out_rowmax[r] = m;
+          }
+        }
+      }
+    }
+  }
+}
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 gcn_layer_fwd_pair_kernel(const PairParams p) {
@@ -625,23 +734,23 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       }
     }
   } else {
-    // ===================== epilogue (8 warps): accumulator slots -> output rows =====================
-    // Warp w may read TMEM lanes 32*(w%4)..+31 (= slots), so warps w and w+8 share 32 slots and take 16 of a block's
-    // 32 columns each.  Per 32-column block: tcgen05.ld (the next block is already in flight) -> raw accumulators
-    // into a [128 slots][32 columns] shared-memory block (16-byte units XOR-swizzled by slot) -> one named barrier
-    // -> all eight warps expand the block to the tile's output rows: a lane octet per row reads its slot's 128 bytes,
-    // * norm[v] * 2^-e(slot) * 2^-e(W) + bias, ReLU / mask, running row abs-max, one 128-byte row segment per octet.
+    // ===================== epilogue (16 warps): accumulator slots -> output rows =====================
+    // Warp w may read TMEM lanes 32*(w%4)..+31 (= slots): the four warps of a lane quarter take 16 of a block's 64
+    // columns each.  Per 64-column block: tcgen05.ld -> raw accumulators into the [128 slots][64 columns]
+    // shared-memory block (16-byte units XOR-swizzled by slot) -> named barrier -> all sixteen warps expand the
+    // block to the tile's output rows: a lane octet per row reads its slot's 256 bytes, * norm[v] * 2^-e(slot) *
+    // 2^-e(W) + bias, ReLU / mask, running row abs-max, two 128-byte row segments per octet.  The expansion is
+    // bound by shared-memory and store latency, not by issue slots or bytes: hence 16 warps with 64 registers.
     reg_set<REGS_EPI>();
     const int quarter = warp & 3;
-    const int half = warp < WARP_EPI0 ? 1 : 0;
-    const int ew = half * 4 + quarter;       // epilogue warp 0..7
-    const int et = ew * 32 + lane;           // index among the 256 epilogue threads
-    const int oct = lane >> 3, u = lane & 7; // expansion: octet `oct` of the warp owns a row, lane u its 16-byte unit
+    const int cpart = warp < WARP_EPI0 ? 0 : 1 + ((warp - WARP_EPI0) >> 2);   // which 16 columns of a block: 0..3
+    const int ew = cpart * 4 + quarter;      // epilogue warp 0..15
+    const int et = ew * 32 + lane;           // index among the 512 epilogue threads
     const int slot_l = quarter * 32 + lane;  // staging: the accumulator row (slot) this lane drains
     const int nblk = (N + EBLK - 1) / EBLK;
     int ti = 0, bias_task = -1;
 #if GMETA_PAIR_PROF
-    long long t_wacc = 0, t_epi = 0, t_mark = clock64();
+    long long t_wacc = 0, t_epi = 0, t_stage = 0, t_expand = 0, t_mark = clock64();
 #define ELAP(acc) { const long long now_ = clock64(); acc += now_ - t_mark; t_mark = now_; }
 #else
 #define ELAP(acc)
@@ -652,11 +761,11 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       const int4 e1 = __ldg(reinterpret_cast<const int4*>(p.pairs + pr) + 1);
       const int row0 = rank ? e0.y : e0.x, nrows = rank ? e1.y : e1.x, task = e1.z;
       // row -> (slot, norm) of this tile's output rows, requested before the accumulators are waited for
-      int rs[RMAX / 256];
-      float rn[RMAX / 256];
+      int rs[RMAX / N_EPI_THREADS];
+      float rn[RMAX / N_EPI_THREADS];
 #pragma unroll
-      for (int j = 0; j < RMAX / 256; ++j) {
-        const int r = et + 256 * j;
+      for (int j = 0; j < RMAX / N_EPI_THREADS; ++j) {
+        const int r = et + N_EPI_THREADS * j;
         rs[j] = 0;
         rn[j] = 0.f;
         if (r < nrows) {
@@ -666,7 +775,7 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       }
       const float wis = p.w_inv_scale[p.image_task_stride ? task : 0];
       // every epilogue warp is done with the previous tile's row table, bias and staging blocks
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_THREADS) : "memory");
       if (task != bias_task) {     // the task's bias -> shared memory, once per task
         bias_task = task;
         const float* bias = p.bias ? p.bias + (long long)task * p.b_task_stride : nullptr;
@@ -677,126 +786,55 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       ELAP(t_wacc);
       tc_fence_after();
 #pragma unroll
-      for (int j = 0; j < RMAX / 256; ++j) {
-        const int r = et + 256 * j;
+      for (int j = 0; j < RMAX / N_EPI_THREADS; ++j) {
+        const int r = et + N_EPI_THREADS * j;
         if (r < nrows)
           rinfo_s[r] = make_float2(__int_as_float(rs[j]), rn[j] * exp2i(-(int)scale_e[(ti & 3) * TM + rs[j]]) * wis);
       }
-      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * ACC_COLS + 32 * half);
-      uint32_t acc_n[32];
-      if (32 * half < N) tmem_ld32(t_addr, acc_n);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * ACC_COLS + 16 * cpart);
+      ExpandArgs xa;
+      xa.stg = epi_s; xa.rinfo = rinfo_s; xa.rmax_s = rmax_s; xa.bias_s = bias_s;
+      xa.out = p.out + (size_t)row0 * p.ld_out;
+      xa.out_rowmax = p.out_rowmax ? p.out_rowmax + row0 : nullptr;
+      xa.mask = p.relu_mask; xa.dst_rows = p.dst_rows;
+      xa.ld_out = p.ld_out; xa.nrows = nrows; xa.row0 = row0; xa.n_cols = N; xa.nblk = nblk; xa.relu = p.relu;
+      xa.store = !(p.dbg & 1);
+      ELAP(t_epi);
       for (int blk = 0; blk < nblk; ++blk) {
-        const bool mine = blk * EBLK + 32 * half < N;     // this warp's 32 columns of the block exist
-        tmem_ld_wait();
-        if (blk) asm volatile("bar.sync 1, 256;" ::: "memory");     // the previous block has been expanded by everybody
+        const bool mine = blk * EBLK + 16 * cpart < N;    // this warp's 16 columns of the block exist
+        if (blk) asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_THREADS) : "memory");   // the previous block has been expanded by everybody
         if (mine) {
+          uint32_t acc[16];
+          tmem_ld16(t_addr + (uint32_t)(blk * EBLK), acc);
+          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            st_f4(epi_s + slot_l * EBLK + ((8 * half + (j ^ (slot_l & 7))) << 2),
-                  make_float4(__uint_as_float(acc_n[4 * j]), __uint_as_float(acc_n[4 * j + 1]),
-                              __uint_as_float(acc_n[4 * j + 2]), __uint_as_float(acc_n[4 * j + 3])));
+          for (int j = 0; j < 4; ++j) {
+            const int x = 4 * cpart + j;      // logical 16-byte unit of the 64-column row
+            st_f4(epi_s + slot_l * EBLK + (((x & 8) | ((x & 7) ^ (slot_l & 7))) << 2),
+                  make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
+                              __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3])));
+          }
         }
-        if (blk + 1 < nblk) {
-          if ((blk + 1) * EBLK + 32 * half < N) tmem_ld32(t_addr + (uint32_t)((blk + 1) * EBLK), acc_n);   // next block in flight
-        } else {
-          tc_fence_before();          // the tile's accumulators have been read: hand the buffer back
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (blk + 1 == nblk) tc_fence_before();           // the tile's accumulators have been read: hand the buffer back
+        asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_THREADS) : "memory");
         if (blk + 1 == nblk && lane == 0) mbar_arrive_cluster(acc_empty(buf), 0);
-        // expansion: lane u of an octet holds columns [c0, c0 + 4) and [c0 + 32, c0 + 36) of the octet's row
-        const int c0 = blk * EBLK + 4 * u;
-        const bool ok0 = c0 < N, ok1 = c0 + 32 < N;
-        const float4 b0 = ok0 ? ld_f4(bias_s + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 b1 = ok1 ? ld_f4(bias_s + c0 + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const bool relu = (p.relu & 1) != 0, last = blk + 1 == nblk;
-        const float* msk = p.relu_mask;
-        float* const outp = p.out + c0;
-        float* const rmx = p.out_rowmax;
-        const int ldo = p.ld_out;
-        const bool st_on = !(p.dbg & 1);
-        constexpr int UNR = 2;
-        for (int rb = ew * 4; rb < nrows; rb += 32 * UNR) {
-          float2 ri[UNR];
-          float4 x0[UNR], x1[UNR];
-          bool live[UNR];
-#pragma unroll
-          for (int j = 0; j < UNR; ++j) {
-            const int r = rb + 32 * j + oct;
-            live[j] = r < nrows;
-            ri[j] = rinfo_s[live[j] ? r : 0];
-          }
-#pragma unroll
-          for (int j = 0; j < UNR; ++j) {
-            const int slot = __float_as_int(ri[j].x);
-            const float* srow = epi_s + slot * EBLK + ((u ^ (slot & 7)) << 2);
-            x0[j] = ld_f4(srow);
-            x1[j] = ld_f4(srow + 32);
-          }
-          float mx[UNR];
-#pragma unroll
-          for (int j = 0; j < UNR; ++j) {
-            const int r = rb + 32 * j + oct;
-            const float f = ri[j].y;
-            float4 w0 = make_float4(fmaf(f, x0[j].x, b0.x), fmaf(f, x0[j].y, b0.y), fmaf(f, x0[j].z, b0.z), fmaf(f, x0[j].w, b0.w));
-            float4 w1 = make_float4(fmaf(f, x1[j].x, b1.x), fmaf(f, x1[j].y, b1.y), fmaf(f, x1[j].z, b1.z), fmaf(f, x1[j].w, b1.w));
-            if (relu) {
-              w0.x = fmaxf(w0.x, 0.f); w0.y = fmaxf(w0.y, 0.f); w0.z = fmaxf(w0.z, 0.f); w0.w = fmaxf(w0.w, 0.f);
-              w1.x = fmaxf(w1.x, 0.f); w1.y = fmaxf(w1.y, 0.f); w1.z = fmaxf(w1.z, 0.f); w1.w = fmaxf(w1.w, 0.f);
-            }
-            const size_t orow = (size_t)(row0 + r) * ldo;
-            if (msk && live[j]) {
-              const int oi = row0 + r;
-              const int mr = (p.relu & 2) ? oi : (p.dst_rows ? p.dst_rows[oi] : oi);    // compact mask / mask by real row
-              const float* mp = msk + (size_t)mr * ldo + c0;
-              if (ok0) {
-                const float4 m4 = ld_f4(mp);
-                if (!(m4.x > 0.f)) w0.x = 0.f;
-                if (!(m4.y > 0.f)) w0.y = 0.f;
-                if (!(m4.z > 0.f)) w0.z = 0.f;
-                if (!(m4.w > 0.f)) w0.w = 0.f;
-              }
-              if (ok1) {
-                const float4 m4 = ld_f4(mp + 32);
-                if (!(m4.x > 0.f)) w1.x = 0.f;
-                if (!(m4.y > 0.f)) w1.y = 0.f;
-                if (!(m4.z > 0.f)) w1.z = 0.f;
-                if (!(m4.w > 0.f)) w1.w = 0.f;
-              }
-            }
-            if (live[j] && st_on) {
-              if (ok0) st_f4(outp + orow, w0);
-              if (ok1) st_f4(outp + orow + 32, w1);
-            }
-            float m = 0.f;
-            if (ok0) m = fmaxf(fmaxf(fabsf(w0.x), fabsf(w0.y)), fmaxf(fabsf(w0.z), fabsf(w0.w)));
-            if (ok1) m = fmaxf(m, fmaxf(fmaxf(fabsf(w1.x), fabsf(w1.y)), fmaxf(fabsf(w1.z), fabsf(w1.w))));
-            mx[j] = m;
-          }
-          if (rmx) {
-            // row abs-max over the octet's lanes: the butterflies of the UNR rows are independent and overlap
-#pragma unroll
-            for (int o = 1; o < 8; o <<= 1)
-#pragma unroll
-              for (int j = 0; j < UNR; ++j) mx[j] = fmaxf(mx[j], __shfl_xor_sync(0xffffffffu, mx[j], o));
-#pragma unroll
-            for (int j = 0; j < UNR; ++j) {
-              const int r = rb + 32 * j + oct;
-              if (live[j] && u == 0) {          // the same lane owns row r in every block: no synchronisation needed
-                float m = mx[j];
-                if (blk) m = fmaxf(m, rmax_s[r]);
-                if (!last) rmax_s[r] = m;
-                else rmx[row0 + r] = m;
-              }
-            }
-          }
+        ELAP(t_stage);
+        xa.blk = blk;
+        if (p.relu_mask) {
+          if (p.out_rowmax) expand_block<true, true>(xa, ew, lane);
+          else expand_block<true, false>(xa, ew, lane);
+        } else {
+          if (p.out_rowmax) expand_block<false, true>(xa, ew, lane);
+          else expand_block<false, false>(xa, ew, lane);
         }
+        ELAP(t_expand);
       }
     }
     ELAP(t_epi);
 #if GMETA_PAIR_PROF
     if (p.prof && warp == WARP_EPI0 && lane == 0) {
       long long* o = p.prof + blockIdx.x * 16 + 10;
-      o[0] = t_wacc; o[1] = t_epi;
+      o[0] = t_wacc; o[1] = t_epi; o[2] = t_stage; o[3] = t_expand;
     }
 #endif
   }

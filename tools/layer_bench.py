@@ -135,9 +135,15 @@ def main():
             L.gmeta_debug_set_pair_profile(None)
             pr = prof.cpu().numpy().reshape(148, 16).astype(np.float64)
             names = ["prod0.setup", "prod0.wait_empty", "prod0.body", "prod15.setup", "prod15.wait_empty", "prod15.body",
-                     "mma.wait_w", "mma.wait_acc_empty", "mma.wait_a_full", "mma.issue", "epi.wait_acc_full", "epi.body"]
+                     "mma.wait_w", "mma.wait_acc_empty", "mma.wait_a_full", "mma.issue", "epi.wait_acc_full", "epi.other",
+                     "epi.stage", "epi.expand"]
             res["pair_profile_kcycles_mean_per_cta"] = {n: round(float(pr[:, i].mean()) / 1e3, 1) for i, n in enumerate(names)}
             res["pair_profile_leader_only"] = {n: round(float(pr[0::2, i].mean()) / 1e3, 1) for i, n in enumerate(names)}
+            res["pair_profile_max_per_cta"] = {n: round(float(pr[:, i].max()) / 1e3, 1) for i, n in enumerate(names)}
+            res["pair_profile_min_per_cta"] = {n: round(float(pr[:, i].min()) / 1e3, 1) for i, n in enumerate(names)}
+            tot = pr[:, 10] + pr[:, 11] + pr[:, 12] + pr[:, 13]
+            res["pair_profile_epi_total_kcycles"] = {"mean": round(float(tot.mean()) / 1e3, 1), "max": round(float(tot.max()) / 1e3, 1),
+                                                     "min": round(float(tot.min()) / 1e3, 1)}
         if impl in (2, 3) and a.ablate:
             set_flags = L.gmeta_debug_set_tc_flags if impl == 2 else L.gmeta_debug_set_pair_flags
             for fl in [int(v) for v in a.ablate.split(",")]:
