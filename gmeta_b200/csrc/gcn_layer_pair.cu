@@ -94,7 +94,7 @@ constexpr int SMEM_FIXED = BAR_BYTES /*barriers*/ + 4 * TM /*slot scale exponent
                            RMAX * 8 /*row -> (slot, factor)*/ + RMAX * 4 /*row abs-max*/ + EPI_STAGE_BYTES;
 constexpr int GROUP_TILES = 32;                // caller tiles (<= 4096 rows) one warp of the dedupe pass walks through
 constexpr int GROUP_CAP = 80;                  // compute-tile entries reserved per group (<= 4096/97 + 32 forced closes)
-constexpr int PAIR_FIXED_COST = 192;           // per-pair overhead of the cluster schedule, in output rows
+constexpr int PAIR_FIXED_COST = 320;           // per-pair overhead of the cluster schedule, in output rows (measured: ~17k of ~61k cycles per tile)
 constexpr int SMEM_MAX = 227 * 1024;
 constexpr int HUB_BIG = 128;                    // hubs with more (padded) edge records are aggregated by a whole CTA
 constexpr int PT_MAXT = 2048;                  // tasks the pair-table kernel handles
@@ -851,38 +851,34 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
 // ------------------------------------------------------------------------------------------
 // weights: abs-max per copy, then the scaled FP16 hi/lo image in the operand layout
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) w_absmax_kernel(const float* __restrict__ W, long long w_stride, int ldw,
-                                                       int trans, int K, int N, unsigned* __restrict__ absmax) {
-  __shared__ float red[8];
-  const float* w = W + (long long)blockIdx.y * w_stride;
+// One CTA per weight copy: abs-max of the copy (block reduction), then its scaled FP16 hi/lo image.
+__global__ void __launch_bounds__(1024) pack_w_pair_kernel(const float* __restrict__ W, long long w_stride, int ldw,
+                                                           int trans, int K, int N, __half* __restrict__ image,
+                                                           long long image_stride, float* __restrict__ w_inv_scale) {
+  __shared__ float red[32];
+  __shared__ float s_max;
+  const int c = blockIdx.x;
+  const float* w = W + c * w_stride;
   const int inner = trans ? K : N, total = K * N;
   float m = 0.f;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
-    m = fmaxf(m, fabsf(w[(size_t)(i / inner) * ldw + (i % inner)]));
+  for (int i = threadIdx.x; i < total; i += blockDim.x) m = fmaxf(m, fabsf(w[(size_t)(i / inner) * ldw + (i % inner)]));
 #pragma unroll
   for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
-    atomicMax(absmax + blockIdx.y, __float_as_uint(m));   // non-negative floats order like their bit patterns
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) s_max = m;
   }
-}
-
-__global__ void pack_w_pair_kernel(const float* __restrict__ W, long long w_stride, int ldw, int trans, int K, int N,
-                                   int n_copies, const unsigned* __restrict__ absmax, __half* __restrict__ image,
-                                   long long image_stride, float* __restrict__ w_inv_scale) {
+  __syncthreads();
+  const int e = scale_exponent(s_max);
+  const float sc = exp2i(e);
+  if (threadIdx.x == 0) w_inv_scale[c] = exp2i(-e);
   const int ku = K / 8, nwc = K / WCH, hn = N / 2;
-  const long long total = (long long)n_copies * ku * N;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int n = (int)(i % N);
-    const int u = (int)((i / N) % ku);
-    const int c = (int)(i / ((long long)N * ku));
-    const int e = scale_exponent(__uint_as_float(absmax[c]));
-    const float sc = exp2i(e);
-    if (n == 0 && u == 0) w_inv_scale[c] = exp2i(-e);
-    const float* w = W + c * w_stride;
+  for (int i = threadIdx.x; i < ku * N; i += blockDim.x) {
+    const int n = i % N, u = i / N;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -1274,12 +1270,13 @@ __global__ void __launch_bounds__(1024) pair_table_kernel(int n_groups, int n_ta
     }
   }
   __syncthreads();
-  // schedule cost in front of every pair (its output rows + a per-pair constant), then the cluster boundaries:
+  // schedule cost in front of every pair (output rows of its larger tile + a per-pair constant), then the cluster boundaries:
   // pair i goes to cluster floor(cost0[i] * n_cl / total_cost) -- contiguous runs, tasks stay together
   int carry = 0;
   for (int b0 = 0; b0 < total; b0 += blockDim.x) {
     const int i = b0 + threadIdx.x;
-    const int x = i < total ? pl.pairs[i].nrows[0] + pl.pairs[i].nrows[1] + PAIR_FIXED_COST : 0;
+    // the two CTAs of a cluster expand their tiles side by side: a pair costs its larger tile
+    const int x = i < total ? max(pl.pairs[i].nrows[0], pl.pairs[i].nrows[1]) + PAIR_FIXED_COST : 0;
     sh[threadIdx.x] = x;
     __syncthreads();
     for (int d = 1; d < blockDim.x; d <<= 1) {
@@ -1390,16 +1387,9 @@ int gcn_layer_fwd_pair(const GatherSrc& g, const int32_t* tile_row0, const int32
     plan = ws.plan;
   }
   const Plan pl = carve_plan(const_cast<void*>(plan), n_tiles, n_tasks, n_rows, n_edges);
-  if (cudaMemsetAsync(ws.w_absmax, 0, (size_t)n_copies * 4, stream) != cudaSuccess) return GMETA_ERR_LAUNCH;
-  {
-    w_absmax_kernel<<<dim3(32, n_copies), 256, 0, stream>>>(W, w_task_stride, ldw, trans_w, K, N, ws.w_absmax);
-    if ((rc = check_launch()) != GMETA_OK) return rc;
-    const long long total = (long long)n_copies * (K / 8) * N;
-    const int grid = (int)((total + 255) / 256 < 8 * kNumSMs ? (total + 255) / 256 : 8 * kNumSMs);
-    pack_w_pair_kernel<<<grid, 256, 0, stream>>>(W, w_task_stride, ldw, trans_w, K, N, n_copies, ws.w_absmax,
-                                                ws.w_image, 2LL * K * N, ws.w_inv_scale);
-    if ((rc = check_launch()) != GMETA_OK) return rc;
-  }
+  pack_w_pair_kernel<<<n_copies, 1024, 0, stream>>>(W, w_task_stride, ldw, trans_w, K, N, ws.w_image, 2LL * K * N,
+                                                    ws.w_inv_scale);
+  if ((rc = check_launch()) != GMETA_OK) return rc;
   if (!(g_pair_dbg & 16)) {     // hub rows first (debug flag 16: skip, results are wrong)
     if (K == 256) rc = hub_prepass_launch<8>(g.in, g.ld_in, in_rowmax, pl, ws.mlong, ws.mlong_bound, stream);
     else if (K == 128) rc = hub_prepass_launch<4>(g.in, g.ld_in, in_rowmax, pl, ws.mlong, ws.mlong_bound, stream);

@@ -82,6 +82,18 @@ def _check_against_oracle(ds, mb, monkeypatch, pruned, impl=_lib.IMPL_AUTO, fine
     m = Meta(args, ds.config()).to(U.dev())
     m.return_meta_grad = True
     m.keep_logits_spt0 = True
+    # Weights: the reference's initialisers (seed 222).  Biases: small random values instead of the reference's
+    # zeros.  With zero biases a centre node WITHOUT in-edges has last-layer pre-activation z[j] = b_fast[j] =
+    # -lr * (sum_s dlogits[s,:]) . Wlin[:,j] for every unit j that is alive on all support rows -- and the prototype
+    # loss is translation invariant, so that sum is mathematically zero: z[j] is pure rounding noise, its ReLU (and
+    # with it that row's whole contribution to the bias gradient) is undetermined in the reference itself
+    # (tools/diag_c2_grad.py: every gradient matches the oracle to 1e-8 except that bias).  Non-zero biases remove
+    # the degeneracy without touching any code path.
+    gen = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for prm in m.net.parameters():
+            if prm.dim() == 1:
+                prm.copy_((0.02 * torch.randn(prm.shape, generator=gen)).to(prm.device))
     params = [p.detach().cpu().clone().requires_grad_(True) for p in m.net.parameters()]
     oxs, oxq = [H.to_ograph(x) for x in xs], [H.to_ograph(x) for x in xq]
 
