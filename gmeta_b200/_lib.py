@@ -45,7 +45,8 @@ class StepArgs(C.Structure):
                 ("update_lr", f32), ("grad_scale", f32), ("compute_meta_grad", i32), ("dense_backward", i32),
                 ("impl", i32), ("pruned_forward", i32),
                 ("meta_grad", vp), ("loss_q", vp), ("acc_q", vp), ("loss_s", vp), ("logits_spt0", vp),
-                ("workspace", vp), ("workspace_bytes", i64), ("feat_rowmax", vp)]
+                ("workspace", vp), ("workspace_bytes", i64), ("feat_rowmax", vp), ("aux_stream", vp),
+                ("step_stats", vp)]
 
 
 _SIGNATURES = {
@@ -79,6 +80,7 @@ _SIGNATURES = {
     "gmeta_sgd_update": (C.c_int, [vp, i64, vp, f32, i32, i32, vp, vp]),
     "gmeta_sum_over_tasks": (C.c_int, [vp, vp, i32, i32, vp, vp]),
     "gmeta_adam_update": (C.c_int, [vp, vp, vp, vp, i32, f64, f64, f64, f64, i32, f32, vp, vp, vp]),
+    "gmeta_adam_step": (C.c_int, [vp, vp, vp, vp, i32, f64, f64, f64, f64, vp, f32, vp, f32, vp, i32, vp, vp]),
     "gmeta_khop_workspace_bytes": (i64, [i32, i32, i32]),
     "gmeta_khop_select": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, C.c_uint64, vp, vp, vp, vp, i64, vp]),
     "gmeta_khop_build": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]),

@@ -1,36 +1,6 @@
 // C-ABI entry points that dispatch between implementations, plus version / error strings.
 #include "common.cuh"
-
-namespace gmeta {
-int gcn_layer_fwd_simt(const GatherSrc& g, const int32_t* tile_row0, const int32_t* tile_nrows,
-                       const int32_t* tile_task, int n_tiles, const float* W, int64_t w_task_stride,
-                       int ldw, int trans_w, const float* bias, int64_t b_task_stride, int f_out,
-                       int relu, const float* relu_mask, float* out, int ld_out, cudaStream_t stream);
-bool gcn_layer_fwd_tc_supported(const GatherSrc& g, int ldw, int trans_w, int f_out, const float* out,
-                                int ld_out);
-int64_t gcn_layer_fwd_tc_workspace_bytes(int n_copies, int f_in, int f_out);
-int gcn_layer_fwd_tc(const GatherSrc& g, const int32_t* tile_row0, const int32_t* tile_nrows,
-                     const int32_t* tile_task, int n_tiles, int n_copies, const float* W, int64_t w_task_stride,
-                     int ldw, int trans_w, const float* bias, int64_t b_task_stride, int f_out, int relu,
-                     const float* relu_mask, float* out, int ld_out, void* workspace, int64_t workspace_bytes,
-                     cudaStream_t stream);
-bool gcn_layer_fwd_pair_supported(const GatherSrc& g, int f_out, const float* bias, int64_t b_task_stride,
-                                  const float* relu_mask, const float* out, int ld_out, int n_tasks);
-int64_t gcn_layer_fwd_pair_workspace_bytes(int n_copies, int n_tiles, int n_tasks, int n_rows, int n_edges, int f_in,
-                                           int f_out);
-int gcn_layer_fwd_pair(const GatherSrc& g, const int32_t* tile_row0, const int32_t* tile_nrows,
-                       const int32_t* tile_task, int n_tiles, int n_tasks, int n_copies, int n_rows, int n_edges,
-                       const float* in_rowmax, const void* plan, const float* W, int64_t w_task_stride, int ldw,
-                       int trans_w, const float* bias, int64_t b_task_stride, int f_out, int relu,
-                       const float* relu_mask, float* out, int ld_out, float* out_rowmax, void* workspace,
-                       int64_t workspace_bytes, cudaStream_t stream);
-int64_t layer_plan_bytes(int n_tiles, int n_tasks, int n_rows, int n_edges);
-int layer_plan_build(const int32_t* indptr, const int32_t* indices, const float* norm, const int32_t* in_row_map,
-                     const int32_t* dst_rows, const int32_t* tile_row0, const int32_t* tile_nrows,
-                     const int32_t* tile_task, int n_tiles, int n_tasks, int n_rows, int n_edges, void* plan,
-                     cudaStream_t stream);
-int row_absmax(const float* x, int ld, int n_rows, int f, float* out, cudaStream_t stream);
-}  // namespace gmeta
+#include "internal.cuh"
 
 using namespace gmeta;
 
@@ -85,7 +55,7 @@ extern "C" int gmeta_gcn_layer_fwd_ex(const float* in, int32_t ld_in, const int3
   if (impl == GMETA_IMPL_TCGEN05 || (impl == GMETA_IMPL_AUTO && tc_ok && ws_ok))
     rc = gcn_layer_fwd_tc(g, tile_row0, tile_nrows, tile_task, n_tiles, n_copies, W, w_task_stride, ldw,
                           trans_w, bias, b_task_stride, f_out, relu, relu_mask, out, ld_out, workspace,
-                          workspace_bytes, s);
+                          workspace_bytes, nullptr, 0, s);
   else if (impl != GMETA_IMPL_AUTO && impl != GMETA_IMPL_SIMT)
     return GMETA_ERR_BAD_ARG;
   else

@@ -18,6 +18,7 @@
 #include <cstdio>
 
 #include "common.cuh"
+#include "internal.cuh"
 
 namespace gmeta {
 namespace {
@@ -637,6 +638,59 @@ __global__ void pack_w_umma_kernel(const float* __restrict__ W, long long w_stri
   }
 }
 
+// Inner SGD step on the per-task fast weights (meta.py:126,151) fused with the operand images of the updated weights
+// for every tensor-core layer launch that will use them (forward orientation of each layer, transposed orientation
+// for the data gradients): the images are recomputed from (w_in, grad), so the two halves of the kernel are
+// independent and one launch replaces the update plus one split per layer call.
+__global__ void sgd_pack_kernel(const float* __restrict__ w_in, long long w_in_stride, const float* __restrict__ grad,
+                                float lr, int n_copies, int n_params, float* __restrict__ w_out, const TcPackPlan plan,
+                                float* __restrict__ image, long long n_update, long long n_units) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_update + n_units; i += stride) {
+    if (i < n_update) {
+      const int t = (int)(i / n_params);
+      const int p = (int)(i - (long long)t * n_params);
+      // p - lr * g, rounded as torch does it (mul, then sub): meta.py:126
+      w_out[i] = w_in[t * w_in_stride + p] - __fmul_rn(lr, grad[i]);
+      continue;
+    }
+    long long r = i - n_update;
+    int sidx = 0;
+    long long per_copy = 0;
+#pragma unroll
+    for (int k = 0; k < 2 * GMETA_MAX_LAYERS; ++k)
+      if (k < plan.n_seg) per_copy += (long long)(plan.seg[k].K / KCH) * plan.seg[k].N * 8;
+    const int c = (int)(r / per_copy);
+    r -= (long long)c * per_copy;
+    while (true) {
+      const long long n = (long long)(plan.seg[sidx].K / KCH) * plan.seg[sidx].N * 8;
+      if (r < n) break;
+      r -= n;
+      ++sidx;
+    }
+    const TcPackSeg sg = plan.seg[sidx];
+    const int unit = (int)(r & 7);
+    long long rest = r >> 3;
+    const int n = (int)(rest % sg.N);
+    const int kc = (int)(rest / sg.N);
+    const float* w = w_in + c * w_in_stride + sg.w_off;
+    const float* gr = grad ? grad + (long long)c * n_params + sg.w_off : nullptr;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = kc * KCH + unit * 4 + j;
+      const long long e = sg.trans ? (long long)n * sg.ldw + k : (long long)k * sg.ldw + n;
+      v[j] = gr ? w[e] - __fmul_rn(lr, gr[e]) : w[e];
+    }
+    const float4 hi = make_float4(tf32_hi(v[0]), tf32_hi(v[1]), tf32_hi(v[2]), tf32_hi(v[3]));
+    const float4 lo = make_float4(v[0] - hi.x, v[1] - hi.y, v[2] - hi.z, v[3] - hi.w);
+    float* chunk = image + c * plan.img_copy_stride + sg.img_off + (size_t)kc * 2 * sg.N * KCH;
+    const int off = n * KCH + ((unit ^ (n & 7)) << 2);
+    st_f4(chunk + off, hi);
+    st_f4(chunk + (size_t)sg.N * KCH + off, lo);
+  }
+}
+
 constexpr int kSmemFixed = 1024 /*alignment slack*/ + 256 /*barriers*/ + (int)sizeof(ProdSmem);
 
 long long* g_tc_prof = nullptr;   // set through gmeta_debug_set_tc_profile
@@ -664,25 +718,31 @@ static int64_t image_bytes(int n_copies, int f_in, int f_out) {
   return ((int64_t)n_copies * 2 * f_in * f_out * (int64_t)sizeof(float) + 255) / 256 * 256;
 }
 
+int64_t gcn_layer_fwd_tc_scratch_bytes(int f_in) {
+  return (int64_t)kNumSMs * ((int64_t)ST_ROWS * f_in + 4 * N_PROD_THREADS * 2) * (int64_t)sizeof(float);
+}
+
 int64_t gcn_layer_fwd_tc_workspace_bytes(int n_copies, int f_in, int f_out) {
   // weight image + per-CTA scratch rows for long (hub) rows
-  return image_bytes(n_copies, f_in, f_out) + (int64_t)kNumSMs * ((int64_t)ST_ROWS * f_in + 4 * N_PROD_THREADS * 2) * (int64_t)sizeof(float);
+  return image_bytes(n_copies, f_in, f_out) + gcn_layer_fwd_tc_scratch_bytes(f_in);
 }
 
 int gcn_layer_fwd_tc(const GatherSrc& g, const int32_t* tile_row0, const int32_t* tile_nrows,
                      const int32_t* tile_task, int n_tiles, int n_copies, const float* W, int64_t w_task_stride,
                      int ldw, int trans_w, const float* bias, int64_t b_task_stride, int f_out, int relu,
                      const float* relu_mask, float* out, int ld_out, void* workspace, int64_t workspace_bytes,
-                     cudaStream_t stream) {
+                     const float* prepacked, int64_t prepacked_stride, cudaStream_t stream) {
   const int K = g.f_in, N = f_out;
   if (!workspace || !aligned16(workspace)) return GMETA_ERR_WORKSPACE;
-  if (workspace_bytes < gcn_layer_fwd_tc_workspace_bytes(n_copies, K, N)) return GMETA_ERR_WORKSPACE;
-  float* image = reinterpret_cast<float*>(workspace);
-  const long long image_stride = 2LL * K * N;
-  {
+  if (workspace_bytes < (prepacked ? gcn_layer_fwd_tc_scratch_bytes(K) : gcn_layer_fwd_tc_workspace_bytes(n_copies, K, N)))
+    return GMETA_ERR_WORKSPACE;
+  const float* image = prepacked ? prepacked : reinterpret_cast<float*>(workspace);
+  const long long image_stride = prepacked ? prepacked_stride : 2LL * K * N;
+  if (!prepacked) {
     const long long total = (long long)n_copies * (K / KCH) * N * 8;
     const int grid = (int)((total + 255) / 256 < 8 * kNumSMs ? (total + 255) / 256 : 8 * kNumSMs);
-    pack_w_umma_kernel<<<grid, 256, 0, stream>>>(W, w_task_stride, ldw, trans_w, K, N, n_copies, image, image_stride);
+    pack_w_umma_kernel<<<grid, 256, 0, stream>>>(W, w_task_stride, ldw, trans_w, K, N, n_copies,
+                                                 reinterpret_cast<float*>(workspace), image_stride);
     int rc = check_launch();
     if (rc != GMETA_OK) return rc;
   }
@@ -695,7 +755,7 @@ int gcn_layer_fwd_tc(const GatherSrc& g, const int32_t* tile_row0, const int32_t
   p.n_stages = stages_for(N);
   p.prof = g_tc_prof;
   p.dbg = g_tc_dbg;
-  p.long_scratch = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + image_bytes(n_copies, K, N));
+  p.long_scratch = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + (prepacked ? 0 : image_bytes(n_copies, K, N)));
   const size_t smem = (size_t)p.n_stages * (2 * A_TILE_BYTES + 2 * N * KCH * 4) + kSmemFixed;
   static bool attr_done = false;
   if (!attr_done) {
@@ -708,6 +768,21 @@ int gcn_layer_fwd_tc(const GatherSrc& g, const int32_t* tile_row0, const int32_t
   const int n_super = (n_tiles + p.st_tiles - 1) / p.st_tiles;
   const int grid = n_super < kNumSMs ? n_super : kNumSMs;
   gcn_layer_fwd_tc_kernel<<<grid, NTHREADS_TC, smem, stream>>>(p);
+  return check_launch();
+}
+
+int gcn_tc_sgd_pack(const float* w_in, int64_t w_in_stride, const float* grad, float lr, int n_copies, int n_params,
+                    float* w_out, const TcPackPlan& plan, float* image, cudaStream_t stream) {
+  if (!w_in || n_copies <= 0 || n_params <= 0 || (grad && !w_out) || (plan.n_seg > 0 && !image)) return GMETA_ERR_BAD_ARG;
+  long long per_copy = 0;
+  for (int k = 0; k < plan.n_seg; ++k) per_copy += (long long)(plan.seg[k].K / KCH) * plan.seg[k].N * 8;
+  const long long n_update = grad ? (long long)n_copies * n_params : 0;
+  const long long n_units = per_copy * n_copies;
+  if (n_update + n_units == 0) return GMETA_OK;
+  const long long blocks = (n_update + n_units + 255) / 256;
+  const int grid = (int)(blocks < 16 * kNumSMs ? blocks : 16 * kNumSMs);
+  sgd_pack_kernel<<<grid, 256, 0, stream>>>(w_in, w_in_stride, grad, lr, n_copies, n_params, w_out, plan, image,
+                                            n_update, n_units);
   return check_launch();
 }
 

@@ -5,7 +5,17 @@
 // last query loss through the query forward (weights fast_K) and, via the prototypes, through
 // the last support forward (weights fast_{K-1}); SURVEY 3.2.  No host synchronisation, no
 // allocation: every buffer is carved out of the caller's workspace.
+//
+// Schedule.  The query forward of step k only produces an accuracy / loss (meta.py:131-141,152-157); nothing on the
+// support chain depends on it.  With an auxiliary stream (gmeta_step_args_t::aux_stream) the K query forwards that
+// need no gradient run on it, beside the support forward/backward/SGD chain of the following steps (event fork /
+// join, prototypes and fast weights double buffered) -- under stream capture this becomes a two-branch CUDA graph.
+// The fast weights' tensor-core operand images (both orientations of every layer that takes the tensor-core
+// kernel) are written by the same launch as the SGD update, once per step, instead of once per layer call.
+#include <vector>
+
 #include "common.cuh"
+#include "internal.cuh"
 
 namespace gmeta {
 
@@ -44,7 +54,7 @@ struct StepBuffers {
   float* logits_q;
   float* dlogits_s;
   float* dlogits_q;
-  float* protos;
+  float* protos[2];          // prototypes of the support forward of step k live in protos[k & 1]
   float* dprotos;
   float* acc_s;
   void* wgrad_ws;
@@ -64,8 +74,14 @@ struct StepBuffers {
   void* plan_qry[2];
   float* rmax_spt[2];
   float* rmax_qry[2];
-  void* layer_ws;            // weight image of the tensor-core layer kernel
+  void* layer_ws;            // weight image / scratch of the tensor-core layer kernels (main stream)
+  void* layer_ws_aux;        // same for launches on the auxiliary stream
   int64_t layer_ws_bytes;
+  // prepacked tensor-core operand images: [fwd orientation of layer l | transposed orientation of layer l >= 1]
+  bool tc_img[GMETA_MAX_LAYERS][2];      // [l][orientation]: that launch takes the streamed-weight tensor-core kernel
+  TcPackPlan pack;
+  float* img_theta;          // one copy (theta)
+  float* img_fast[2];        // T copies each (fast[k & 1])
   int ld[GMETA_MAX_LAYERS];
   int64_t total;
 };
@@ -137,7 +153,8 @@ void carve(const gmeta_step_args_t* a, void* ws, StepBuffers& b) {
   b.logits_q = c.take<float>(Sq * C);
   b.dlogits_s = c.take<float>(Ss * C);
   b.dlogits_q = c.take<float>(Sq * C);
-  b.protos = c.take<float>(T * MC * C);
+  b.protos[0] = c.take<float>(T * MC * C);
+  b.protos[1] = c.take<float>(T * MC * C);
   b.dprotos = c.take<float>(T * MC * C);
   b.acc_s = c.take<float>(T);
   b.wgrad_ws_bytes = 0;
@@ -168,20 +185,112 @@ void carve(const gmeta_step_args_t* a, void* ws, StepBuffers& b) {
     if (w > b.layer_ws_bytes) b.layer_ws_bytes = w;
   }
   b.layer_ws = c.take<char>(b.layer_ws_bytes);
+  b.layer_ws_aux = c.take<char>(a->aux_stream ? b.layer_ws_bytes : 0);
+  // Operand images of the weights for the launches that take the streamed-weight tensor-core kernel: the pruned
+  // mode's dense contractions (identity graph) and every data gradient.  Activations and dZ buffers are carved
+  // 256-byte aligned with ld % 4 == 0, so the shape alone decides.
+  b.pack.n_seg = 0;
+  b.pack.img_copy_stride = 0;
+  const bool tc_wanted = a->impl == GMETA_IMPL_AUTO || a->impl == GMETA_IMPL_TCGEN05;
+  for (int l = 0; l < m.n_layers; ++l) {
+    for (int o = 0; o < 2; ++o) {
+      const int K = o ? m.f_out[l] : m.f_in[l], N = o ? m.f_in[l] : m.f_out[l];
+      const int ld_in = o ? b.ld[l] : (l == 0 ? a->ld_feat : b.ld[l - 1]);
+      bool use = tc_wanted && K % 32 == 0 && K >= 32 && K <= 2048 && N % 16 == 0 && N >= 16 && N <= 256 && ld_in % 4 == 0;
+      if (o == 0 && !a->pruned_forward) use = false;               // full formulation: forwards go through gmeta_gcn_layer_fwd[_ex]
+      if (o == 1 && (l == 0 || !a->pruned_forward)) use = false;   // features carry no gradient; unpruned: generic path
+      b.tc_img[l][o] = use;
+      if (use) {
+        TcPackSeg& sg = b.pack.seg[b.pack.n_seg++];
+        sg.w_off = m.w_off[l]; sg.K = K; sg.N = N; sg.ldw = m.f_out[l]; sg.trans = o;
+        sg.img_off = b.pack.img_copy_stride;
+        b.pack.img_copy_stride += 2LL * K * N;
+      }
+    }
+  }
+  b.img_theta = c.take<float>(b.pack.img_copy_stride);
+  b.img_fast[0] = c.take<float>(T * b.pack.img_copy_stride);
+  b.img_fast[1] = c.take<float>(T * b.pack.img_copy_stride);
   b.total = c.off;
+}
+
+// Events for the fork / join between the main and the auxiliary stream: created once per host thread, reused by
+// every step (timing disabled; recording an event does not synchronise anything).
+struct EventPool {
+  std::vector<cudaEvent_t> ev;
+  cudaEvent_t get(size_t i) {
+    while (ev.size() <= i) {
+      cudaEvent_t e = nullptr;
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      ev.push_back(e);
+    }
+    return ev[i];
+  }
+};
+thread_local EventPool g_events;
+
+__global__ void step_stats_kernel(const float* __restrict__ loss_q, const float* __restrict__ acc_q, int n_tasks,
+                                  int n_cols, float* __restrict__ out) {
+  // out[0] = sum_t loss_q[t][K], out[1 + k] = sum_t acc_q[t][k]; tasks added in index order (deterministic)
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > n_cols) return;
+  float s = 0.f;
+  if (k == 0) {
+    for (int t = 0; t < n_tasks; ++t) s += loss_q[(size_t)t * n_cols + n_cols - 1];
+  } else {
+    for (int t = 0; t < n_tasks; ++t) s += acc_q[(size_t)t * n_cols + k - 1];
+  }
+  out[k] = s;
 }
 
 struct Runner {
   const gmeta_step_args_t* a;
   StepBuffers b;
-  cudaStream_t s;
+  cudaStream_t s;            // stream of the launches being enqueued (main or auxiliary)
+  void* ws;                  // tensor-core scratch of that stream
   int rc = GMETA_OK;
 
   bool ok() const { return rc == GMETA_OK; }
   void run(int code) { if (rc == GMETA_OK) rc = code; }
+  void on(cudaStream_t stream, void* scratch) { s = stream; ws = scratch; }
 
-  void forward(const gmeta_packed_set_t& set, float* const* act, const float* W, int64_t stride, float* logits) {
+  // Weight version: -1 = theta (one shared copy), 0 / 1 = fast[v] (one copy per task)
+  struct Weights {
+    const float* W;
+    int64_t stride;
+    const float* img;        // operand images of this version, or NULL
+  };
+  Weights theta() const { return Weights{a->theta, 0, b.img_theta}; }
+  Weights fast(int v) const { return Weights{b.fast[v], (int64_t)a->model.n_params_padded, b.img_fast[v]}; }
+
+  // dense contraction of pre-summed rows (identity graph): out = act(in . B + bias), B = W_l or W_l^T
+  void dense(const float* in, int ld_in, const int32_t* t_row0, const int32_t* t_nrows, const int32_t* t_task,
+             int n_tiles, int n_tasks, const Weights& w, int l, int orient, int relu, const float* relu_mask, float* out,
+             int ld_out) {
     const gmeta_model_t& m = a->model;
+    const int K = orient ? m.f_out[l] : m.f_in[l], N = orient ? m.f_in[l] : m.f_out[l];
+    const float* bias = orient ? nullptr : w.W + m.b_off[l];
+    if (b.tc_img[l][orient] && n_tiles > 0) {
+      int seg = 0;       // images are laid out in (layer, orientation) order
+      for (int i = 0; i < 2 * l + orient; ++i)
+        if (b.tc_img[i >> 1][i & 1]) ++seg;
+      GatherSrc g;
+      g.in = in; g.in_row_map = nullptr; g.dst_rows = nullptr; g.indptr = b.iota; g.indices = b.iota; g.norm = b.ones;
+      g.ld_in = ld_in; g.f_in = K;
+      run(gcn_layer_fwd_tc(g, t_row0, t_nrows, t_task, n_tiles, w.stride == 0 ? 1 : n_tasks, w.W + m.w_off[l], w.stride,
+                           m.f_out[l], orient, bias, w.stride, N, relu, relu_mask, out, ld_out, ws, b.layer_ws_bytes,
+                           w.img + b.pack.seg[seg].img_off, w.stride == 0 ? 0 : b.pack.img_copy_stride, s));
+      return;
+    }
+    run(gmeta_gcn_layer_fwd(in, ld_in, nullptr, nullptr, b.iota, b.iota, b.ones, t_row0, t_nrows, t_task, n_tiles, n_tasks,
+                            w.W + m.w_off[l], w.stride, m.f_out[l], orient, bias, w.stride, K, N, relu, relu_mask, out,
+                            ld_out, a->impl, ws, b.layer_ws_bytes, s));
+  }
+
+  void forward(const gmeta_packed_set_t& set, float* const* act, const Weights& w, float* logits) {
+    const gmeta_model_t& m = a->model;
+    const float* W = w.W;
+    const int64_t stride = w.stride;
     const bool pruned = a->pruned_forward != 0;
     for (int l = 0; l < m.n_layers && ok(); ++l) {
       if (pruned) {
@@ -194,18 +303,13 @@ struct Runner {
         if (l > 0)
           run(gmeta_aggregate_rows(act[l - 1], b.ld[l - 1], set.row_pos[l - 1], set.act_rows[l], set.indptr, set.indices,
                                    set.norm, set.n_act[l], m.f_in[l], 1, agg, ld_agg, s));
-        run(gmeta_gcn_layer_fwd(agg, ld_agg, nullptr, nullptr, b.iota, b.iota, b.ones, set.act_tile_row0[l],
-                                set.act_tile_nrows[l], set.act_tile_task[l], set.n_act_tiles[l], set.n_tasks,
-                                W + m.w_off[l], stride, m.f_out[l], 0, W + m.b_off[l], stride, m.f_in[l], m.f_out[l], 1,
-                                nullptr, act[l], b.ld[l], a->impl, b.layer_ws, b.layer_ws_bytes, s));
+        dense(agg, ld_agg, set.act_tile_row0[l], set.act_tile_nrows[l], set.act_tile_task[l], set.n_act_tiles[l],
+              set.n_tasks, w, l, 0, 1, nullptr, act[l], b.ld[l]);
         continue;
       }
       const float* in = l == 0 ? a->feat_table : act[l - 1];
       const int ld_in = l == 0 ? a->ld_feat : b.ld[l - 1];
-      // pruned: layer l over its active rows only (compact output); its inputs are the compact
-      // activations of layer l-1, addressed through row_pos[l-1] (every in-neighbour of an active
-      // row of layer l is an active row of layer l-1 by construction)
-      const int32_t* map = l == 0 ? set.feat_row : (pruned ? set.row_pos[l - 1] : nullptr);
+      const int32_t* map = l == 0 ? set.feat_row : nullptr;
       if (b.use_ex) {
         // every row of every layer (the reference's formulation): CTA-pair tensor-core path where the shape allows,
         // with the structure plan built once per step and the row abs-max handed from layer to layer
@@ -215,18 +319,15 @@ struct Runner {
         run(gmeta_gcn_layer_fwd_ex(in, ld_in, map, nullptr, set.indptr, set.indices, set.norm, set.tile_row0,
                                    set.tile_nrows, set.tile_task, set.n_tiles, set.n_tasks, W + m.w_off[l], stride,
                                    m.f_out[l], 0, W + m.b_off[l], stride, m.f_in[l], m.f_out[l], 1, nullptr, act[l],
-                                   b.ld[l], a->impl, b.layer_ws, b.layer_ws_bytes, set.n_nodes, set.n_edges,
+                                   b.ld[l], a->impl, ws, b.layer_ws_bytes, set.n_nodes, set.n_edges,
                                    l == 0 ? a->feat_rowmax : rmax[(l - 1) & 1], l + 1 < m.n_layers ? rmax[l & 1] : nullptr,
                                    plan[l == 0 ? 0 : 1], s));
         continue;
       }
-      run(gmeta_gcn_layer_fwd(in, ld_in, map, pruned ? set.act_rows[l] : nullptr, set.indptr, set.indices, set.norm,
-                              pruned ? set.act_tile_row0[l] : set.tile_row0,
-                              pruned ? set.act_tile_nrows[l] : set.tile_nrows,
-                              pruned ? set.act_tile_task[l] : set.tile_task,
-                              pruned ? set.n_act_tiles[l] : set.n_tiles, set.n_tasks,
-                              W + m.w_off[l], stride, m.f_out[l], 0, W + m.b_off[l], stride, m.f_in[l],
-                              m.f_out[l], 1, nullptr, act[l], b.ld[l], a->impl, b.layer_ws, b.layer_ws_bytes, s));
+      run(gmeta_gcn_layer_fwd(in, ld_in, map, nullptr, set.indptr, set.indices, set.norm, set.tile_row0, set.tile_nrows,
+                              set.tile_task, set.n_tiles, set.n_tasks, W + m.w_off[l], stride, m.f_out[l], 0,
+                              W + m.b_off[l], stride, m.f_in[l], m.f_out[l], 1, nullptr, act[l], b.ld[l], a->impl, ws,
+                              b.layer_ws_bytes, s));
     }
     const int L = m.n_layers;
     run(gmeta_readout_linear_fwd(act[L - 1], b.ld[L - 1], m.f_out[L - 1], pruned ? set.centre_pos : set.centre_row,
@@ -234,9 +335,11 @@ struct Runner {
                                  W + m.wlin_off, stride, W + m.blin_off, stride, m.n_out, logits, s));
   }
 
-  void backward(const gmeta_packed_set_t& set, float* const* act, float* const* dz, const float* W,
-                int64_t stride, const float* dlogits, float* gout) {
+  void backward(const gmeta_packed_set_t& set, float* const* act, float* const* dz, const Weights& w,
+                const float* dlogits, float* gout) {
     const gmeta_model_t& m = a->model;
+    const float* W = w.W;
+    const int64_t stride = w.stride;
     const int L = m.n_layers;
     const int64_t P = m.n_params_padded;
     const bool sparse = !a->dense_backward;
@@ -265,16 +368,13 @@ struct Runner {
         if (l > 0) {
           run(gmeta_aggregate_rows(dz[cur], b.ld[l], set.row_pos[l], set.act_rows[l - 1], set.t_indptr, set.t_indices,
                                    set.norm, set.n_act[l - 1], m.f_out[l], 1, b.dagg, b.ld[l], s));
-          run(gmeta_gcn_layer_fwd(b.dagg, b.ld[l], nullptr, nullptr, b.iota, b.iota, b.ones, set.act_tile_row0[l - 1],
-                                  set.act_tile_nrows[l - 1], set.act_tile_task[l - 1], set.n_act_tiles[l - 1], set.n_tasks,
-                                  W + m.w_off[l], stride, m.f_out[l], 1, nullptr, 0, m.f_out[l], m.f_in[l], 2, act[l - 1],
-                                  dz[cur ^ 1], b.ld[l - 1], a->impl, b.layer_ws, b.layer_ws_bytes, s));
+          dense(b.dagg, b.ld[l], set.act_tile_row0[l - 1], set.act_tile_nrows[l - 1], set.act_tile_task[l - 1],
+                set.n_act_tiles[l - 1], set.n_tasks, w, l, 1, 2, act[l - 1], dz[cur ^ 1], b.ld[l - 1]);
           cur ^= 1;
         }
         continue;
       }
-      run(gmeta_gcn_layer_wgrad(in, ld_in, l == 0 ? set.feat_row : (pruned ? set.row_pos[l - 1] : nullptr),
-                                sparse ? set.act_rows[l] : nullptr,
+      run(gmeta_gcn_layer_wgrad(in, ld_in, l == 0 ? set.feat_row : nullptr, sparse ? set.act_rows[l] : nullptr,
                                 set.indptr, set.indices, set.norm, sparse ? set.act_task_ptr[l] : set.task_row_ptr,
                                 set.n_tasks, dz[cur], b.ld[l], m.f_in[l], m.f_out[l], gout + m.w_off[l], P,
                                 gout + m.b_off[l], P, b.wgrad_ws, b.wgrad_ws_bytes, s));
@@ -289,18 +389,19 @@ struct Runner {
                                 sparse ? set.act_tile_nrows[l - 1] : set.tile_nrows,
                                 sparse ? set.act_tile_task[l - 1] : set.tile_task,
                                 sparse ? set.n_act_tiles[l - 1] : set.n_tiles, set.n_tasks, W + m.w_off[l], stride,
-                                m.f_out[l], 1, nullptr, 0, m.f_out[l], m.f_in[l], pruned ? 2 : 0, act[l - 1], dz[cur ^ 1],
-                                b.ld[l - 1], a->impl, b.layer_ws, b.layer_ws_bytes, s));
+                                m.f_out[l], 1, nullptr, 0, m.f_out[l], m.f_in[l], 0, act[l - 1], dz[cur ^ 1],
+                                b.ld[l - 1], a->impl, ws, b.layer_ws_bytes, s));
         cur ^= 1;
       }
     }
   }
 
-  void qry_loss(int k, bool want_grad) {
+  // query loss / accuracy of step `k` against the prototypes of the support forward that used weight version pv
+  void qry_loss(int k, int pv, bool want_grad) {
     const gmeta_packed_set_t& q = a->qry;
     // prototypes (and their count) come from the support set of the same task (meta.py:132,154)
     run(proto_loss_launch(false, b.logits_q, a->model.n_out, q.task_sub_ptr, q.n_tasks, q.class_pos, nullptr,
-                          a->spt.n_classes, 0, a->max_classes, max_rows_q, a->grad_scale, b.protos,
+                          a->spt.n_classes, 0, a->max_classes, max_rows_q, a->grad_scale, b.protos[pv],
                           a->loss_q + k, a->acc_q + k, a->update_step + 1, want_grad ? b.dlogits_q : nullptr,
                           want_grad ? b.dprotos : nullptr, s));
   }
@@ -342,7 +443,6 @@ extern "C" int gmeta_maml_step(const gmeta_step_args_t* a_in, void* stream) {
   if (!aligned16(a->workspace)) return GMETA_ERR_ALIGN;
   Runner r;
   r.a = a;
-  r.s = (cudaStream_t)stream;
   carve(a, a->workspace, r.b);
   if (r.b.total > a->workspace_bytes) return GMETA_ERR_WORKSPACE;
   g_launch_count = 0;
@@ -353,11 +453,26 @@ extern "C" int gmeta_maml_step(const gmeta_step_args_t* a_in, void* stream) {
   const int T = sp.n_tasks, K = a->update_step;
   const int64_t P = m.n_params_padded;
   StepBuffers& b = r.b;
-  cudaStream_t s = r.s;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t sq = a->aux_stream ? (cudaStream_t)a->aux_stream : s;
+  const bool two = sq != s;
+  r.on(s, b.layer_ws);
+  // fork / join helpers (no-ops on one stream).  Events: 0 prologue, 1 + k support step k done, 1 + K + k query k done
+  auto signal = [&](int ev, cudaStream_t from) {
+    if (!two || !r.ok()) return;
+    cudaEvent_t e = g_events.get((size_t)ev);
+    if (!e || cudaEventRecord(e, from) != cudaSuccess) r.rc = GMETA_ERR_LAUNCH;
+  };
+  auto wait = [&](int ev, cudaStream_t on) {
+    if (!two || !r.ok()) return;
+    cudaEvent_t e = g_events.get((size_t)ev);
+    if (!e || cudaStreamWaitEvent(on, e, 0) != cudaSuccess) r.rc = GMETA_ERR_LAUNCH;
+  };
   // shared memory of the loss kernels is sized for the task with the most subgraphs
   r.max_rows_s = a->spt_max_rows_per_task > 0 ? a->spt_max_rows_per_task : sp.n_subgraphs;
   r.max_rows_q = a->qry_max_rows_per_task > 0 ? a->qry_max_rows_per_task : qr.n_subgraphs;
 
+  // ---- prologue (main stream): structure-only bookkeeping of both sets, operand images of theta ----
   if (cudaMemsetAsync(b.g_spt, 0, (size_t)T * P * sizeof(float), s) != cudaSuccess) return GMETA_ERR_LAUNCH;
   if (cudaMemsetAsync(b.g_qry, 0, (size_t)T * P * sizeof(float), s) != cudaSuccess) return GMETA_ERR_LAUNCH;
   r.run(gmeta_degree_norm(sp.indptr, sp.n_nodes, sp.norm, s));
@@ -371,7 +486,6 @@ extern "C" int gmeta_maml_step(const gmeta_step_args_t* a_in, void* stream) {
         r.run(gmeta_build_row_pos(qr.act_rows[l], qr.n_act[l], qr.n_nodes, qr.row_pos[l], s));
     }
   }
-
   if (b.use_ex) {
     for (int i = 0; i < (m.n_layers > 1 ? 2 : 1); ++i) {
       r.run(gmeta_layer_plan_build(sp.indptr, sp.indices, sp.norm, i == 0 ? sp.feat_row : nullptr, nullptr, sp.tile_row0,
@@ -380,40 +494,66 @@ extern "C" int gmeta_maml_step(const gmeta_step_args_t* a_in, void* stream) {
                                    qr.tile_nrows, qr.tile_task, qr.n_tiles, T, qr.n_nodes, qr.n_edges, b.plan_qry[i], s));
     }
   }
+  if (a->pruned_forward) r.run(fill_identity_graph(b.iota, b.ones, b.n_ident, s));
+  if (b.pack.n_seg > 0)
+    r.run(gcn_tc_sgd_pack(a->theta, 0, nullptr, 0.f, 1, (int)P, nullptr, b.pack, b.img_theta, s));
+  signal(0, s);
+  wait(0, sq);
   if (a->pruned_forward) {
-    const int n0s = sp.n_act[0], n0q = qr.n_act[0];
-    r.run(fill_identity_graph(b.iota, b.ones, b.n_ident, s));
+    // layer-0 neighbourhood sums of both sets (features and structure only): the query set's on the auxiliary stream
     r.run(gmeta_aggregate_rows(a->feat_table, a->ld_feat, sp.feat_row, sp.act_rows[0], sp.indptr, sp.indices, sp.norm,
-                               n0s, m.f_in[0], 1, b.agg_spt[0], a->ld_feat, s));
+                               sp.n_act[0], m.f_in[0], 1, b.agg_spt[0], a->ld_feat, s));
     r.run(gmeta_aggregate_rows(a->feat_table, a->ld_feat, qr.feat_row, qr.act_rows[0], qr.indptr, qr.indices, qr.norm,
-                               n0q, m.f_in[0], 1, b.agg_qry[0], a->ld_feat, s));
+                               qr.n_act[0], m.f_in[0], 1, b.agg_qry[0], a->ld_feat, sq));
   }
 
+  // ---- K inner steps.  Main stream: support forward -> loss -> backward -> SGD (+ operand images).  The query
+  // forward of step k (weights fast_k, prototypes of support forward k) follows on the auxiliary stream; the one
+  // whose loss is back-propagated (k = K-1 when training) stays on the main stream. ----
   for (int k = 0; k < K && r.ok(); ++k) {
-    const float* Wcur = k == 0 ? a->theta : b.fast[(k - 1) & 1];
-    const int64_t stride = k == 0 ? 0 : P;
-    r.forward(sp, b.act_spt, Wcur, stride, b.logits_s);
+    const Runner::Weights wcur = k == 0 ? r.theta() : r.fast((k - 1) & 1);
+    if (k >= 2) wait(1 + K + (k - 2), s);       // query k-2 has read fast[k & 1] and protos[k & 1]
+    r.on(s, b.layer_ws);
+    r.forward(sp, b.act_spt, wcur, b.logits_s);
     if (k == 0 && a->logits_spt0 && r.ok())
       if (cudaMemcpyAsync(a->logits_spt0, b.logits_s, (size_t)sp.n_subgraphs * m.n_out * sizeof(float),
                           cudaMemcpyDeviceToDevice, s) != cudaSuccess) r.rc = GMETA_ERR_LAUNCH;
     r.run(proto_loss_launch(true, b.logits_s, m.n_out, sp.task_sub_ptr, T, sp.class_pos, sp.class_occ,
-                            sp.n_classes, a->n_support, a->max_classes, r.max_rows_s, 1.0f, b.protos,
+                            sp.n_classes, a->n_support, a->max_classes, r.max_rows_s, 1.0f, b.protos[k & 1],
                             a->loss_s + k, b.acc_s, K, b.dlogits_s, nullptr, s));
-    r.backward(sp, b.act_spt, b.dz_spt, Wcur, stride, b.dlogits_s, b.g_spt);
-    r.run(gmeta_sgd_update(Wcur, stride, b.g_spt, a->update_lr, T, (int)P, b.fast[k & 1], s));
-    if (k == 0) {  // query loss / accuracy before the first update (meta.py:129-134)
-      r.forward(qr, b.act_qry, a->theta, 0, b.logits_q);
-      r.qry_loss(0, false);
+    r.backward(sp, b.act_spt, b.dz_spt, wcur, b.dlogits_s, b.g_spt);
+    // fast_k = w - lr * g (meta.py:126,151) and its operand images, one launch
+    r.run(gcn_tc_sgd_pack(wcur.W, wcur.stride, b.g_spt, a->update_lr, T, (int)P, b.fast[k & 1], b.pack, b.img_fast[k & 1], s));
+    signal(1 + k, s);
+    const bool last_on_main = a->compute_meta_grad && k == K - 1;
+    if (last_on_main) {
+      wait(1 + K + (k - 1), s);                 // the auxiliary stream is done with the query buffers
+      r.on(s, b.layer_ws);
+    } else {
+      wait(1 + k, sq);
+      r.on(sq, two ? b.layer_ws_aux : b.layer_ws);
     }
-    r.forward(qr, b.act_qry, b.fast[k & 1], P, b.logits_q);
-    r.qry_loss(k + 1, a->compute_meta_grad && k == K - 1);
+    if (k == 0) {  // query loss / accuracy before the first update (meta.py:129-134)
+      r.forward(qr, b.act_qry, r.theta(), b.logits_q);
+      r.qry_loss(0, 0, false);
+    }
+    r.forward(qr, b.act_qry, r.fast(k & 1), b.logits_q);
+    r.qry_loss(k + 1, k & 1, last_on_main);
+    if (!last_on_main) signal(1 + K + k, sq);
   }
+  r.on(s, b.layer_ws);
   if (a->compute_meta_grad && r.ok()) {
-    r.backward(qr, b.act_qry, b.dz_qry, b.fast[(K - 1) & 1], P, b.dlogits_q, b.g_qry);
+    r.backward(qr, b.act_qry, b.dz_qry, r.fast((K - 1) & 1), b.dlogits_q, b.g_qry);
     r.run(gmeta_proto_grad_to_support(b.dprotos, m.n_out, a->max_classes, sp.task_sub_ptr, T, sp.class_pos,
                                       sp.class_occ, a->n_support, sp.n_subgraphs, b.dlogits_s, s));
-    r.backward(sp, b.act_spt, b.dz_spt, b.fast[(K - 2) & 1], P, b.dlogits_s, b.g_spt);
+    r.backward(sp, b.act_spt, b.dz_spt, r.fast((K - 2) & 1), b.dlogits_s, b.g_spt);
     r.run(gmeta_sum_over_tasks(b.g_qry, b.g_spt, T, (int)P, a->meta_grad, s));
+  } else {
+    wait(1 + K + (K - 1), s);                   // join: every query forward has finished
+  }
+  if (a->step_stats && r.ok()) {
+    step_stats_kernel<<<1, 64, 0, s>>>(a->loss_q, a->acc_q, T, K + 1, a->step_stats);
+    r.run(check_launch());
   }
   return r.rc;
 }

@@ -183,32 +183,44 @@ def _feat_fingerprint(feat):
 
 class _DeviceBatch(object):
     """An uploaded meta-batch: segment plans of both sets + the device int32 buffer holding them."""
-    __slots__ = ("T", "max_classes", "ft", "ps_s", "ps_q", "ints", "h2d_bytes")
+    __slots__ = ("T", "max_classes", "ft", "ps_s", "ps_q", "ints", "h2d_bytes", "resident")
 
 
 class FusedAdam(object):
-    """`meta_optim` (meta.py:97): Adam(lr, betas=(0.9,0.999), eps=1e-8) over the flat parameter
-    buffer, one kernel, with the reference's NaN-skip (meta.py:163-164) evaluated on the device."""
+    """`meta_optim` (meta.py:97): Adam(lr, betas=(0.9,0.999), eps=1e-8) over the flat parameter buffer with the
+    reference's NaN-skip (meta.py:163-164).  Step count, gate and bias corrections live on the device
+    (`gmeta_adam_step`): the count advances only when the update is applied -- like torch.optim.Adam, which the
+    reference does not call on a skipped step -- and the launches are identical every step (CUDA-graph safe)."""
 
     def __init__(self, n_params, lr, betas=(0.9, 0.999), eps=1e-8):
         self.lr, self.betas, self.eps = lr, betas, eps
         self.n_params = n_params
-        self.step_count = 0
         self.exp_avg = None
         self.exp_avg_sq = None
+        self.state = None          # int32[8] on the device: [0] step count, [1] skipped flag of the last step
 
     def _state(self, dev):
         if self.exp_avg is None or self.exp_avg.device != dev:
+            steps = 0 if self.state is None else int(self.state[0])
             self.exp_avg = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
             self.exp_avg_sq = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
+            self.state = torch.zeros(8, dtype=torch.int32, device=dev)
+            self.state[0] = steps
 
-    def step(self, flat_param, flat_grad, loss_gate=None, skipped=None, grad_scale=1.0):
+    @property
+    def step_count(self):
+        """Applied (non-skipped) steps so far; reads the device counter (synchronises)."""
+        return 0 if self.state is None else int(self.state[0])
+
+    def step(self, flat_param, flat_grad, loss_sum=None, loss_scale=1.0, acc_sums=None, step_out=None, grad_scale=1.0):
+        """One Adam step on the flat buffer.  The update is skipped iff *loss_sum * loss_scale is NaN; with step_out
+        (float[n_acc + 2]) the call also writes acc_sums * loss_scale, the gate value and the skipped flag."""
         self._state(flat_param.device)
-        self.step_count += 1
-        _lib.check(_lib.lib().gmeta_adam_update(
+        n_acc = 0 if acc_sums is None else int(acc_sums.numel())
+        _lib.check(_lib.lib().gmeta_adam_step(
             _ptr(flat_param), _ptr(flat_grad), _ptr(self.exp_avg), _ptr(self.exp_avg_sq), self.n_params,
-            self.lr, self.betas[0], self.betas[1], self.eps, self.step_count, grad_scale,
-            _ptr(loss_gate), _ptr(skipped), _stream()), "adam_update")
+            self.lr, self.betas[0], self.betas[1], self.eps, _ptr(self.state), grad_scale,
+            _ptr(loss_sum), loss_scale, _ptr(acc_sums), n_acc, _ptr(step_out), _stream()), "adam_step")
 
     def state_dict(self):
         return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
@@ -244,6 +256,13 @@ class Meta(nn.Module):
         self._feat_cache = None
         self._ws = None
         self._scratch = {}
+        self._theta_flat = None        # flat parameter buffer the net's parameters are views of
+        self._aux_stream = None        # second stream for the query forwards (gmeta_step_args_t::aux_stream)
+        self._graphs = {}              # captured meta-steps of device-resident batches
+        self._alloc_gen = 0            # bumped whenever a scratch / workspace buffer is re-allocated
+        # replay device-resident meta-steps (step_device on a batch with its own buffer) from CUDA graphs
+        self.use_graphs = bool(getattr(args, 'use_graphs', True))
+        self.two_streams = bool(getattr(args, 'two_streams', True))
         self.last = {}                 # diagnostics of the most recent call (loss, launches, bytes)
         self.return_meta_grad = False  # tests: keep a copy of the reduced meta-gradient
         self.global_task_num = None    # set when ranks hold unequal task shares
@@ -256,8 +275,8 @@ class Meta(nn.Module):
         for k, v in self.__dict__.items():
             if k == "_feat_cache":
                 new.__dict__[k] = v          # the resident table is read-only: copies share it (train.py:87,127)
-            elif k in ("_staging", "_ws", "_scratch", "_extractor"):
-                new.__dict__[k] = {} if k == "_scratch" else None
+            elif k in ("_staging", "_ws", "_scratch", "_extractor", "_theta_flat", "_aux_stream", "_graphs"):
+                new.__dict__[k] = {} if k in ("_scratch", "_graphs") else None
             else:
                 new.__dict__[k] = deepcopy(v, memo)
         return new
@@ -283,6 +302,7 @@ class Meta(nn.Module):
         if t is None or t.numel() < n or t.dtype != dtype or t.device != dev:
             t = torch.empty(max(n, 1), dtype=dtype, device=dev)
             self._scratch[name] = t
+            self._alloc_gen += 1           # captured graphs hold the old pointer
         v = t[:n].view(shape)
         if zero:
             v.zero_()
@@ -313,6 +333,7 @@ class Meta(nn.Module):
         x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry = batch
         dev = _dev()
         db = _DeviceBatch()
+        db.resident = bool(own_buffer)
         db.T = len(x_spt)
         db.max_classes = packing.validate_labels(y_spt, y_qry, self.k_spt)
         db.ft = self._features(feat, dev)
@@ -347,6 +368,7 @@ class Meta(nn.Module):
         if getattr(self, "_extractor", None) is None or self._extractor[0] != key:
             self._extractor = (key, DeviceExtractor(graphs, dev), graphs)
         db = _DeviceBatch()
+        db.resident = False
         db.T = int(req_spt.sub_off.shape[0] - 1)
         T = db.T
         split = lambda r: [r.labels[r.sub_off[t]:r.sub_off[t + 1]] for t in range(T)]      # noqa: E731
@@ -366,8 +388,6 @@ class Meta(nn.Module):
         K = self.update_step
         db = self.build_batch_on_device(graphs, req_spt, req_qry, feat, h, sample_nodes, seed)
         host = self.step_device(db).cpu()
-        if host[K + 2] != 0:
-            self.meta_optim.step_count -= 1
         self.last.update({"loss_q": float(host[K + 1]), "skipped": bool(host[K + 2] != 0),
                           "d2h_bytes": int(host.numel() * 4)})
         return host[:K + 1].numpy().astype(np.float32)
@@ -384,9 +404,10 @@ class Meta(nn.Module):
         self.last["d2h_bytes"] = int(host.numel() * 4)
         return host.numpy().astype(np.float32)
 
-    def _enqueue(self, db, steps, train, flat_theta):
+    def _enqueue(self, db, steps, train, flat_theta, meta_grad=None, stats=None):
         """Enqueue the whole inner loop for an uploaded meta-batch.  Returns device tensors
-        (acc_q [T,K+1], loss_q [T,K+1], meta_grad [P] or None)."""
+        (acc_q [T,K+1], loss_q [T,K+1], meta_grad [P] or None).  `meta_grad` / `stats`: where the summed
+        meta-gradient [P] and the step's scalars [K+2] (sum of last query losses, accuracy sums) go."""
         L = _lib.lib()
         dev = _dev()
         T, ps_s, ps_q, ft = db.T, db.ps_s, db.ps_q, db.ft
@@ -410,7 +431,8 @@ class Meta(nn.Module):
         a.pruned_forward = 1 if (self.pruned_forward and not self.dense_backward) else 0
         a.impl = self.impl
         P = self.spec.n_params_padded
-        meta_grad = self._buf("meta_grad", (P,), torch.float32, dev) if train else None
+        if train and meta_grad is None:
+            meta_grad = self._buf("meta_grad", (P,), torch.float32, dev)
         loss_q = self._buf("loss_q", (T, steps + 1), torch.float32, dev)
         acc_q = self._buf("acc_q", (T, steps + 1), torch.float32, dev)
         loss_s = self._buf("loss_s", (T, steps), torch.float32, dev)
@@ -420,12 +442,18 @@ class Meta(nn.Module):
         if getattr(self, "keep_logits_spt0", False):
             logits0 = self._buf("logits0", (ps_s.S, self.spec.n_out), torch.float32, dev)
         a.logits_spt0 = _ptr(logits0)
+        a.step_stats = _ptr(stats)
+        if self.two_streams and a.pruned_forward:      # full-formulation launches fill the chip on their own
+            if self._aux_stream is None or self._aux_stream.device != dev:
+                self._aux_stream = torch.cuda.Stream(device=dev)
+            a.aux_stream = self._aux_stream.cuda_stream
         nbytes = L.gmeta_maml_step_workspace_bytes(C.byref(a))
         if nbytes < 0:
             raise _lib.GMetaError("invalid meta-step arguments")
         if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:
             self._ws = None
             self._ws = torch.empty(int(nbytes * 1.1) + 4096, dtype=torch.uint8, device=dev)
+            self._alloc_gen += 1
         a.workspace, a.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
         _lib.check(L.gmeta_maml_step(C.byref(a), _stream()), "maml_step")
         self.last = {"h2d_bytes": db.h2d_bytes, "gpu_launches": L.gmeta_last_launch_count(),
@@ -447,37 +475,71 @@ class Meta(nn.Module):
         return local_tasks * dist.world_size()
 
     def _flat_theta(self, params, dev):
-        flat = self._buf("theta", (self.spec.n_params_padded,), torch.float32, dev, zero=True)
-        return self.spec.flatten([p.to(dev) for p in params], flat)
+        """The flat parameter buffer [W1 | b1 | ... | Wlin | blin] of the C ABI.  The net's parameters are kept as
+        VIEWS of it, so neither the inner loop (reads theta) nor the fused Adam (updates it in place) needs a copy
+        in or out; the aliasing is re-established whenever something replaced a parameter's storage (`.to()`,
+        deepcopy, `p.data = ...`)."""
+        params = list(params)
+        flat = self._theta_flat
+        ok = flat is not None and flat.device == dev and all(
+            p.device == dev and p.data_ptr() == flat.data_ptr() + 4 * off and p.is_contiguous()
+            for p, off in zip(params, self.spec.offsets))
+        if not ok:
+            flat = torch.zeros(self.spec.n_params_padded, dtype=torch.float32, device=dev)
+            self.spec.flatten([p.to(dev) for p in params], flat)
+            for p, v in zip(params, self.spec.unflatten(flat)):
+                p.data = v
+            self._theta_flat = flat
+            self._alloc_gen += 1
+        return flat
 
     # -- public API (meta.py:236-244) --
     def step_device(self, db):
         """One training meta-step on an uploaded batch, everything on the device: inner loop, the
         single all-reduce, fused Adam.  Returns a device tensor [K+3] = mean accuracies (K+1),
-        mean query loss, skipped flag -- no host synchronisation."""
+        mean query loss, skipped flag -- no host synchronisation.
+
+        The inner loop of a batch that owns its device buffer (upload_batch(own_buffer=True): device-resident
+        training loops) is captured into a CUDA graph on its second use and replayed afterwards: ~250 launches on
+        two streams become one graph launch."""
         from . import dist
         dev = _dev()
         K = self.update_step
-        theta = self._flat_theta(self.net.parameters(), dev)
-        acc_q, loss_q, meta_grad = self._enqueue(db, K, True, theta)
         P = self.spec.n_params_padded
+        theta = self._flat_theta(self.net.parameters(), dev)
         T_global = self._global_task_num(db.T)
-        # [meta-grad | sum_t loss_q^K | sum_t acc_q[0..K]] -- the one collective of a meta-step
-        red = self._buf("reduce", (P + 1 + K + 1,), torch.float32, dev)
-        red[:P].copy_(meta_grad)
-        red[P] = loss_q[:, K].sum()
-        red[P + 1:] = acc_q.sum(0)
-        dist.allreduce_sum_(red)
-        gate = red[P:P + 1] / T_global                                    # meta.py:161
-        skipped = self._buf("skipped", (1,), torch.int32, dev)
-        self.meta_optim.step(theta, red[:P], loss_gate=gate, skipped=skipped)   # meta.py:163-169
-        for p, v in zip(self.net.parameters(), self.spec.unflatten(theta)):
-            p.data.copy_(v)
+        # [meta-grad | sum_t loss_q^K | sum_t acc_q[0..K]] -- the one collective of a meta-step; the inner loop
+        # writes straight into it
+        red = self._buf("reduce", (P + K + 2,), torch.float32, dev)
         out = self._buf("step_out", (K + 3,), torch.float32, dev)
-        out[:K + 1] = red[P + 1:] / T_global                              # meta.py:171
-        out[K + 1] = gate[0]
-        out[K + 2] = skipped[0].float()
-        self.last["gpu_launches"] += 1                                    # the Adam kernel
+        key = None
+        if self.use_graphs and getattr(db, "resident", False) and not getattr(self, "keep_logits_spt0", False):
+            key = (db.ints.data_ptr(), db.ps_q.end, db.ft.table.data_ptr(), K, T_global, self._alloc_gen)
+            if self._graphs and next(iter(self._graphs))[-1] != self._alloc_gen:
+                self._graphs.clear()               # a buffer moved: every captured pointer set is stale
+        entry = self._graphs.get(key) if key is not None else None
+        if entry is not None and entry[0] is not None:
+            entry[0].replay()
+            self.last = dict(entry[1])
+        else:
+            if key is not None and entry is None and len(self._graphs) < 16:
+                self._enqueue(db, K, True, theta, meta_grad=red[:P], stats=red[P:])     # first use: eager (allocates)
+                if key[-1] == self._alloc_gen:
+                    self._graphs[key] = (None, None)                                    # next use: capture
+            elif key is not None and entry is not None:
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue(db, K, True, theta, meta_grad=red[:P], stats=red[P:])
+                self._graphs[key] = (g, dict(self.last))
+                g.replay()
+            else:
+                self._enqueue(db, K, True, theta, meta_grad=red[:P], stats=red[P:])
+        dist.allreduce_sum_(red)
+        # meta.py:161-171: gate = sum loss / task_num, NaN -> skip; Adam on theta (the net's own storage)
+        self.meta_optim.step(theta, red[:P], loss_sum=red[P:P + 1], loss_scale=1.0 / T_global, acc_sums=red[P + 1:],
+                             step_out=out)
+        self.last["gpu_launches"] = self.last.get("gpu_launches", 0) + 2          # Adam: prepare + apply
         if self.return_meta_grad:
             self.last["meta_grad"] = [g.clone() for g in self.spec.unflatten(red[:P])]
         return out
@@ -486,8 +548,6 @@ class Meta(nn.Module):
         K = self.update_step
         db = self.upload_batch((x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry), feat)
         host = self.step_device(db).cpu()                                 # the step's only D2H + sync
-        if host[K + 2] != 0:
-            self.meta_optim.step_count -= 1                               # skipped step: no Adam state change
         self.last.update({"loss_q": float(host[K + 1]), "skipped": bool(host[K + 2] != 0),
                           "d2h_bytes": int(host.numel() * 4)})
         return host[:K + 1].numpy().astype(np.float32)

@@ -321,6 +321,18 @@ int gmeta_adam_update(float* param, const float* grad, float* exp_avg, float* ex
                       int32_t step, float grad_scale, const float* loss_gate, int32_t* skipped,
                       void* stream);
 
+/* The same Adam step with every changing scalar on the DEVICE, so that the launches are identical from step to step
+ * and can be replayed from a CUDA graph: `state` is a caller-owned, zero-initialised int32[8] -- [0] the step count
+ * (incremented only when the update is applied, like torch.optim.Adam under the reference's NaN skip,
+ * meta.py:163-169), [1] the skipped flag of the last call, [2..3] bias-correction scalars.  The gate is
+ * *loss_sum * loss_scale (meta.py:161: sum of the tasks' last query losses / task_num); loss_sum == NULL never skips.
+ * If step_out != NULL: step_out[k] = acc_sums[k] * loss_scale for k < n_acc (meta.py:171), step_out[n_acc] = the
+ * gate value, step_out[n_acc + 1] = skipped (0 / 1).  Two launches. */
+int gmeta_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int32_t n_params,
+                    double lr, double beta1, double beta2, double eps, int32_t* state, float grad_scale,
+                    const float* loss_sum, float loss_scale, const float* acc_sums, int32_t n_acc,
+                    float* step_out, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Whole first-order ProtoMAML inner loop for every task of a packed meta-batch, enqueued
  * from C++ in one call (replaces the body of Meta.forward_ProtoMAML, meta.py:118-161, and of
@@ -359,6 +371,13 @@ typedef struct gmeta_step_args {
   const float* feat_rowmax;      /* optional [rows of feat_table]: max |feat_table[r, :]| (gmeta_row_absmax, once per
                                     table).  With it the full-formulation forwards (pruned_forward == 0) take the
                                     CTA-pair tensor-core layer path where the shape allows. */
+  void* aux_stream;              /* optional second cudaStream_t (not the one passed to gmeta_maml_step): the query
+                                    forwards that need no gradient are enqueued on it, beside the support chain of
+                                    the following steps; forked from / joined back into the main stream with events,
+                                    so the call still behaves like work on the main stream only (and can be captured
+                                    into a CUDA graph).  NULL: everything on the main stream. */
+  float* step_stats;             /* optional [K+2]: sum_t loss_q[t][K], then sum_t acc_q[t][0..K] (the scalars of the
+                                    meta-step's all-reduce, meta.py:161,171), written by one extra launch */
 } gmeta_step_args_t;
 
 int64_t gmeta_maml_step_workspace_bytes(const gmeta_step_args_t* args);

@@ -220,6 +220,62 @@ def test_subgraph_order_and_node_permutation_equivariance():
     U.report("node relabelling", run(shuffled), base, 2e-6)
 
 
+def test_two_streams_and_graph_replay_equal_the_serial_eager_step():
+    """The schedule is an implementation detail: query forwards on the auxiliary stream and CUDA-graph replay of a
+    device-resident batch give bit-identical step outputs, weights and Adam state to the one-stream eager step."""
+    from gmeta_b200.meta import Meta
+    from gmeta_b200.synthetic import make_dataset
+    ds = make_dataset('C1', scale=0.3)
+    ds.update_lr = 0.05
+    mb = ds.sample_meta_batch(np.random.default_rng(3), 4)
+    results = []
+    for two, graphs in ((False, False), (True, False), (True, True)):
+        args = ds.args()
+        args.two_streams, args.use_graphs = two, graphs
+        torch.manual_seed(222)
+        m = Meta(args, ds.config()).to(U.dev())
+        db = m.upload_batch(mb, ds.feats, own_buffer=True)
+        outs = [m.step_device(db).clone() for _ in range(4)]       # eager, capture, replay, replay
+        if graphs:
+            assert any(v[0] is not None for v in m._graphs.values()), "the step must have been captured"
+        torch.cuda.synchronize()
+        results.append((torch.stack(outs).cpu(), [p.detach().cpu().clone() for p in m.net.parameters()],
+                        m.meta_optim.step_count))
+    for r in results[1:]:
+        assert torch.equal(r[0], results[0][0])
+        assert r[2] == results[0][2] == 4
+        for a, b in zip(r[1], results[0][1]):
+            assert torch.equal(a, b)
+
+
+def test_parameters_alias_the_flat_buffer_and_survive_deepcopy():
+    """The net's parameters are views of the flat theta buffer the kernels update in place; deepcopy (train.py:87,127)
+    and in-place edits keep working, and a copy trains independently of the original."""
+    from gmeta_b200.meta import Meta
+    ds = H.tiny_dataset('disjoint')
+    mb = ds.sample_meta_batch(np.random.default_rng(2))
+    torch.manual_seed(4)
+    m = Meta(ds.args(), ds.config()).to(U.dev())
+    m(*mb, ds.feats)
+    flat = m._theta_flat
+    for p, off in zip(m.net.parameters(), m.spec.offsets):
+        assert p.data_ptr() == flat.data_ptr() + 4 * off
+    twin = copy.deepcopy(m)
+    w_before = [p.detach().clone() for p in m.net.parameters()]
+    a1 = twin(*mb, ds.feats)
+    for p, q in zip(m.net.parameters(), w_before):
+        assert torch.equal(p, q)                                   # training the copy leaves the original alone
+    a2 = m(*mb, ds.feats)
+    np.testing.assert_allclose(a1, a2, atol=0)
+    for p, q in zip(m.net.parameters(), twin.net.parameters()):
+        assert torch.equal(p, q)
+    with torch.no_grad():
+        for p in m.net.parameters():
+            p.mul_(0.5)                                            # in-place edits reach the kernels
+    a3 = m(*mb, ds.feats)
+    assert a3.shape == a2.shape
+
+
 def test_missing_extension_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libgmeta_b200.so")

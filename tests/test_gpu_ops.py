@@ -423,6 +423,40 @@ def test_sgd_and_adam_match_torch():
     assert int(skipped) == 1 and torch.equal(before, p_dev)                # NaN loss: no update (meta.py:163-164)
 
 
+def test_adam_step_device_state_matches_torch_and_skips_like_the_reference():
+    """gmeta_adam_step (step count, gate and bias corrections on the device; CUDA-graph safe) vs torch.optim.Adam:
+    a NaN loss skips the update AND leaves the step count alone, exactly like not calling Adam.step (meta.py:163-169)."""
+    L = _lib.lib()
+    rng = np.random.default_rng(9)
+    P, n_acc = 1000, 4
+    theta = rng.standard_normal(P, dtype=np.float32)
+    p_ref = torch.tensor(theta.copy(), requires_grad=True)
+    opt = torch.optim.Adam([p_ref], lr=1e-3)
+    p_dev, m, v = U.f32(theta), torch.zeros(P, device=U.dev()), torch.zeros(P, device=U.dev())
+    state = torch.zeros(8, dtype=torch.int32, device=U.dev())
+    acc = U.f32([1.0, 2.0, 3.0, 4.0])
+    out = torch.zeros(n_acc + 2, device=U.dev())
+    applied = 0
+    for it in range(8):
+        gr = (rng.standard_normal(P, dtype=np.float32) * (10.0 ** rng.integers(-4, 1))).astype(np.float32)
+        nan_step = it in (2, 5)
+        loss = U.f32([float('nan') if nan_step else 6.0])
+        if not nan_step:
+            p_ref.grad = torch.tensor(gr)
+            opt.step()
+            applied += 1
+        before = p_dev.clone()
+        _lib.check(L.gmeta_adam_step(U.p(p_dev), U.p(U.f32(gr)), U.p(m), U.p(v), P, 1e-3, 0.9, 0.999, 1e-8, U.p(state), 1.0,
+                                     U.p(loss), 0.5, U.p(acc), n_acc, U.p(out), U.stream()))
+        assert int(state[0]) == applied and int(state[1]) == int(nan_step)
+        o = out.cpu().numpy()
+        np.testing.assert_allclose(o[:n_acc], [0.5, 1.0, 1.5, 2.0])
+        assert o[n_acc + 1] == float(nan_step) and (np.isnan(o[n_acc]) if nan_step else o[n_acc] == 3.0)
+        if nan_step:
+            assert torch.equal(before, p_dev)
+        U.report("adam_step %d" % it, p_dev, p_ref.detach(), 1e-7, 1e-6)
+
+
 def test_bad_arguments_return_error_codes():
     L = _lib.lib()
     assert L.gmeta_degree_norm(None, 5, None, None) == -1
