@@ -194,8 +194,9 @@ struct WgradParams {
   int f_out;
   int n_split;
   int vec_dz;
-  float* part_w;  // [T][n_split][f_in][f_out]
-  float* part_b;  // [T][n_split][f_out]
+  float* part_w;  // [T][n_split][f_in][f_out], or dW itself when n_split == 1
+  float* part_b;  // [T][n_split][f_out], or db itself
+  long long pw_task_stride, pw_split_stride, pb_task_stride, pb_split_stride;
 };
 
 template <bool VEC>
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gcn_layer_wgrad_simt_kernel(const
       }
     }
 
-    float* pw = p.part_w + ((size_t)task * p.n_split + sp) * f_in * f_out;
+    float* pw = p.part_w + task * p.pw_task_stride + sp * p.pw_split_stride;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int k = k0 + (i < 4 ? 4 * ty + i : 64 + 4 * ty + (i - 4));
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gcn_layer_wgrad_simt_kernel(const
       }
     }
     if (kb == 0 && ty == 0) {
-      float* pb = p.part_b + ((size_t)task * p.n_split + sp) * f_out;
+      float* pb = p.part_b + task * p.pb_task_stride + sp * p.pb_split_stride;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int jj = j0 + (j < 4 ? 4 * tx + j : 64 + 4 * tx + (j - 4));
@@ -435,7 +436,8 @@ __device__ __forceinline__ void agg_store(const GatherSrc& g, float* __restrict_
 
 template <bool VEC>
 __global__ void __launch_bounds__(256) aggregate_rows_kernel(GatherSrc g, int n_rows, int scale_dst,
-                                                             float* __restrict__ out, int ld_out) {
+                                                             float* __restrict__ out, int ld_out,
+                                                             const int32_t* __restrict__ pos_ptr) {
   __shared__ int long_rows[8];
   __shared__ int n_long;
   __shared__ float4 part[8][32];
@@ -446,7 +448,7 @@ __global__ void __launch_bounds__(256) aggregate_rows_kernel(GatherSrc g, int n_
     const int i = row0 + warp;
     if (i < n_rows) {
       const int v = g.dst_rows ? g.dst_rows[i] : i;
-      const int beg = g.indptr[v], end = g.indptr[v + 1];
+      const int beg = pos_ptr ? pos_ptr[i] : g.indptr[v], end = pos_ptr ? pos_ptr[i + 1] : g.indptr[v + 1];
       if (end - beg > AGG_LONG) {
         if (lane == 0) long_rows[atomicAdd(&n_long, 1)] = i;     // the order of this list does not affect any value
       } else {
@@ -463,7 +465,7 @@ __global__ void __launch_bounds__(256) aggregate_rows_kernel(GatherSrc g, int n_
     for (int q = 0; q < nl; ++q) {
       const int il = long_rows[q];
       const int v = g.dst_rows ? g.dst_rows[il] : il;
-      const int beg = g.indptr[v], end = g.indptr[v + 1];
+      const int beg = pos_ptr ? pos_ptr[il] : g.indptr[v], end = pos_ptr ? pos_ptr[il + 1] : g.indptr[v + 1];
       const float nv = scale_dst ? g.norm[v] : 1.f;
       for (int c0 = 0; c0 < ld_out; c0 += 128) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -503,21 +505,109 @@ int fill_identity_graph(int32_t* iota, float* ones, int n, cudaStream_t stream) 
 }
 }  // namespace gmeta
 
-extern "C" int gmeta_aggregate_rows(const float* in, int32_t ld_in, const int32_t* in_row_map, const int32_t* dst_rows,
-                                    const int32_t* indptr, const int32_t* indices, const float* norm, int32_t n_rows,
-                                    int32_t f_in, int32_t scale_dst, float* out, int32_t ld_out, void* stream) {
+namespace gmeta {
+// pos_indptr != NULL: the in-neighbour list of output row i is indices[pos_indptr[i] .. pos_indptr[i+1]) (a CSR indexed
+// by output POSITION, e.g. the active out-neighbour lists of active_out_lists_build) instead of the graph row's.
+int aggregate_rows_impl(const float* in, int32_t ld_in, const int32_t* in_row_map, const int32_t* dst_rows,
+                        const int32_t* indptr, const int32_t* indices, const float* norm, int32_t n_rows,
+                        int32_t f_in, int32_t scale_dst, float* out, int32_t ld_out, const int32_t* pos_indptr,
+                        cudaStream_t stream) {
   if (n_rows < 0 || f_in <= 0 || ld_in < f_in || ld_out < f_in) return GMETA_ERR_BAD_ARG;
   if (n_rows == 0) return GMETA_OK;
-  if (!in || !indptr || !indices || !norm || !out) return GMETA_ERR_BAD_ARG;
+  if (!in || !(indptr || pos_indptr) || !indices || !norm || !out) return GMETA_ERR_BAD_ARG;
   GatherSrc g;
   g.in = in; g.in_row_map = in_row_map; g.dst_rows = dst_rows; g.indptr = indptr; g.indices = indices; g.norm = norm;
   g.ld_in = ld_in; g.f_in = f_in;
   const int grid = ceil_div(n_rows, 8) < 16 * kNumSMs ? ceil_div(n_rows, 8) : 16 * kNumSMs;
   if (ld_in % 4 == 0 && f_in % 4 == 0 && aligned16(in))
-    aggregate_rows_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(g, n_rows, scale_dst, out, ld_out);
+    aggregate_rows_kernel<true><<<grid, 256, 0, stream>>>(g, n_rows, scale_dst, out, ld_out, pos_indptr);
   else
-    aggregate_rows_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(g, n_rows, scale_dst, out, ld_out);
+    aggregate_rows_kernel<false><<<grid, 256, 0, stream>>>(g, n_rows, scale_dst, out, ld_out, pos_indptr);
   return check_launch();
+}
+
+namespace {
+// One warp per listed row u = rows[i]: its out-neighbours v (CSR by source) with keep[v] >= 0, counted (fill == 0:
+// count[i]) or written in CSR order to out_idx[ptr[i] ..) (fill != 0).
+__global__ void active_out_kernel(const int32_t* __restrict__ rows, int n_rows, const int32_t* __restrict__ t_indptr,
+                                  const int32_t* __restrict__ t_indices, const int32_t* __restrict__ keep, int fill,
+                                  int32_t* __restrict__ count, const int32_t* __restrict__ ptr,
+                                  int32_t* __restrict__ out_idx) {
+  const int lane = threadIdx.x & 31;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_rows; i += (gridDim.x * blockDim.x) >> 5) {
+    const int u = rows[i];
+    const int beg = t_indptr[u], end = t_indptr[u + 1];
+    int n = 0;
+    const int base = fill ? ptr[i] : 0;
+    for (int e0 = beg; e0 < end; e0 += 128) {          // four independent 32-edge batches in flight
+      int v[4];
+      bool k[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int e = e0 + 32 * q + lane;
+        v[q] = e < end ? t_indices[e] : -1;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) k[q] = v[q] >= 0 && keep[v[q]] >= 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const unsigned bal = __ballot_sync(0xffffffffu, k[q]);
+        if (fill && k[q]) out_idx[base + n + __popc(bal & ((1u << lane) - 1u))] = v[q];
+        n += __popc(bal);
+      }
+    }
+    if (!fill && lane == 0) count[i] = n;
+  }
+}
+
+// exclusive prefix sum of a[0..n) into out[0..n], out[n] = total; one CTA
+__global__ void __launch_bounds__(1024) excl_scan_kernel(const int32_t* __restrict__ a, int n, int32_t* __restrict__ out) {
+  __shared__ int sh[1024];
+  int carry = 0;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int x = i < n ? a[i] : 0;
+    sh[threadIdx.x] = x;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+      const int y = threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += y;
+      __syncthreads();
+    }
+    if (i < n) out[i] = carry + sh[threadIdx.x] - x;
+    carry += sh[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] = carry;
+}
+}  // namespace
+
+// Active out-neighbour lists: for every row u of `rows` (the active rows of layer l-1) the rows v it has an edge TO
+// that are active at layer l (keep[v] >= 0), as a CSR indexed by the position of u in `rows`.  The data gradient of
+// the pruned backward sums over exactly these; walking the full out-edge list of a hub (thousands of edges, one or
+// two of them active) on every backward is what this replaces -- built once per meta-step.
+// count: scratch [n_rows]; ptr: [n_rows + 1]; out_idx: capacity = number of edges of the set.
+int active_out_lists_build(const int32_t* rows, int n_rows, const int32_t* t_indptr, const int32_t* t_indices,
+                           const int32_t* keep, int32_t* count, int32_t* ptr, int32_t* out_idx, cudaStream_t stream) {
+  if (n_rows == 0) return GMETA_OK;
+  const int grid = ceil_div(n_rows, 8) < 8 * kNumSMs ? ceil_div(n_rows, 8) : 8 * kNumSMs;
+  active_out_kernel<<<grid, 256, 0, stream>>>(rows, n_rows, t_indptr, t_indices, keep, 0, count, nullptr, nullptr);
+  int rc = check_launch();
+  if (rc != GMETA_OK) return rc;
+  excl_scan_kernel<<<1, 1024, 0, stream>>>(count, n_rows, ptr);
+  if ((rc = check_launch()) != GMETA_OK) return rc;
+  active_out_kernel<<<grid, 256, 0, stream>>>(rows, n_rows, t_indptr, t_indices, keep, 1, nullptr, ptr, out_idx);
+  return check_launch();
+}
+}  // namespace gmeta
+
+extern "C" int gmeta_aggregate_rows(const float* in, int32_t ld_in, const int32_t* in_row_map, const int32_t* dst_rows,
+                                    const int32_t* indptr, const int32_t* indices, const float* norm, int32_t n_rows,
+                                    int32_t f_in, int32_t scale_dst, float* out, int32_t ld_out, void* stream) {
+  if (n_rows > 0 && !indptr) return GMETA_ERR_BAD_ARG;
+  return aggregate_rows_impl(in, ld_in, in_row_map, dst_rows, indptr, indices, norm, n_rows, f_in, scale_dst, out, ld_out,
+                             nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int gmeta_degree_norm(const int32_t* indptr, int32_t n_nodes, float* norm, void* stream) {
@@ -534,12 +624,15 @@ extern "C" int64_t gmeta_gcn_layer_wgrad_workspace_bytes(int32_t n_tasks, int32_
   return (int64_t)n_tasks * s * ((int64_t)f_in * f_out + f_out) * (int64_t)sizeof(float);
 }
 
-extern "C" int gmeta_gcn_layer_wgrad(const float* in, int32_t ld_in, const int32_t* in_row_map,
-                                     const int32_t* dst_rows, const int32_t* indptr, const int32_t* indices, const float* norm,
-                                     const int32_t* task_row_ptr, int32_t n_tasks, const float* dZ,
-                                     int32_t ld_dz, int32_t f_in, int32_t f_out, float* dW,
-                                     int64_t dw_task_stride, float* db, int64_t db_task_stride,
-                                     void* workspace, int64_t workspace_bytes, void* stream) {
+namespace gmeta {
+// rows_hint: total number of rows the task_row_ptr covers (-1 = unknown).  With few rows per task the row-range split
+// would only produce empty partials: the split count is capped by the average number of 32-row chunks per task,
+// and with a single range per task the kernel writes dW / db directly (no partials, no reduction launch).
+int gcn_layer_wgrad_impl(const float* in, int32_t ld_in, const int32_t* in_row_map, const int32_t* dst_rows,
+                         const int32_t* indptr, const int32_t* indices, const float* norm, const int32_t* task_row_ptr,
+                         int32_t n_tasks, const float* dZ, int32_t ld_dz, int32_t f_in, int32_t f_out, float* dW,
+                         int64_t dw_task_stride, float* db, int64_t db_task_stride, void* workspace,
+                         int64_t workspace_bytes, int64_t rows_hint, cudaStream_t s) {
   if (!in || !indptr || !norm || !task_row_ptr || !dZ || !dW || !db || !workspace)
     return GMETA_ERR_BAD_ARG;
   if (n_tasks <= 0 || f_in <= 0 || f_out <= 0 || ld_in < f_in || ld_dz < f_out) return GMETA_ERR_BAD_ARG;
@@ -550,9 +643,23 @@ extern "C" int gmeta_gcn_layer_wgrad(const float* in, int32_t ld_in, const int32
   p.g.norm = norm; p.g.ld_in = ld_in; p.g.f_in = f_in;
   p.task_row_ptr = task_row_ptr; p.n_tasks = n_tasks; p.dZ = dZ; p.ld_dz = ld_dz; p.f_out = f_out;
   p.n_split = pick_wgrad_split(n_tasks, f_in, f_out);
+  if (rows_hint >= 0) {
+    // a 32-row chunk costs a CTA ~2 us, a reduction launch ~13 us: up to 8 chunks per task run unsplit
+    const int64_t avg_chunks = (rows_hint / n_tasks + WG_ROWS - 1) / WG_ROWS;
+    if (avg_chunks <= 8) p.n_split = 1;
+    else if (avg_chunks / 4 < p.n_split) p.n_split = (int)(avg_chunks / 4);
+  }
   p.vec_dz = (ld_dz % 4 == 0) && aligned16(dZ);
-  p.part_w = (float*)workspace;
-  p.part_b = p.part_w + (size_t)n_tasks * p.n_split * f_in * f_out;
+  const int n_w = f_in * f_out;
+  if (p.n_split == 1) {
+    p.part_w = dW; p.pw_task_stride = dw_task_stride; p.pw_split_stride = 0;
+    p.part_b = db; p.pb_task_stride = db_task_stride; p.pb_split_stride = 0;
+  } else {
+    p.part_w = (float*)workspace;
+    p.part_b = p.part_w + (size_t)n_tasks * p.n_split * n_w;
+    p.pw_task_stride = (long long)p.n_split * n_w; p.pw_split_stride = n_w;
+    p.pb_task_stride = (long long)p.n_split * f_out; p.pb_split_stride = f_out;
+  }
   const bool vec_in = (ld_in % 4 == 0) && aligned16(in) && ld_in >= round_up(f_in, 4);
   const int n_work = n_tasks * ceil_div(f_in, KP) * ceil_div(f_out, BN) * p.n_split;
   static bool attr_done = false;
@@ -561,17 +668,27 @@ extern "C" int gmeta_gcn_layer_wgrad(const float* in, int32_t ld_in, const int32
     cudaFuncSetAttribute(gcn_layer_wgrad_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem);
     attr_done = true;
   }
-  cudaStream_t s = (cudaStream_t)stream;
   if (vec_in)
     gcn_layer_wgrad_simt_kernel<true><<<n_work, NTHREADS, kWgSmem, s>>>(p);
   else
     gcn_layer_wgrad_simt_kernel<false><<<n_work, NTHREADS, kWgSmem, s>>>(p);
   int rc = check_launch();
-  if (rc != GMETA_OK) return rc;
-  const int n_w = f_in * f_out;
+  if (rc != GMETA_OK || p.n_split == 1) return rc;
   const long long total = (long long)n_tasks * (n_w + f_out);
   const int grid = (int)((total + 255) / 256 < 8 * kNumSMs ? (total + 255) / 256 : 8 * kNumSMs);
   wgrad_reduce_kernel<<<grid, 256, 0, s>>>(p.part_w, p.part_b, n_tasks, p.n_split, n_w, f_out, dW,
                                           dw_task_stride, db, db_task_stride);
   return check_launch();
+}
+}  // namespace gmeta
+
+extern "C" int gmeta_gcn_layer_wgrad(const float* in, int32_t ld_in, const int32_t* in_row_map,
+                                     const int32_t* dst_rows, const int32_t* indptr, const int32_t* indices, const float* norm,
+                                     const int32_t* task_row_ptr, int32_t n_tasks, const float* dZ,
+                                     int32_t ld_dz, int32_t f_in, int32_t f_out, float* dW,
+                                     int64_t dw_task_stride, float* db, int64_t db_task_stride,
+                                     void* workspace, int64_t workspace_bytes, void* stream) {
+  return gcn_layer_wgrad_impl(in, ld_in, in_row_map, dst_rows, indptr, indices, norm, task_row_ptr, n_tasks, dZ, ld_dz,
+                              f_in, f_out, dW, dw_task_stride, db, db_task_stride, workspace, workspace_bytes, -1,
+                              (cudaStream_t)stream);
 }

@@ -9,6 +9,18 @@ int gcn_layer_fwd_simt(const GatherSrc& g, const int32_t* tile_row0, const int32
                        int ldw, int trans_w, const float* bias, int64_t b_task_stride, int f_out,
                        int relu, const float* relu_mask, float* out, int ld_out, cudaStream_t stream);
 
+int aggregate_rows_impl(const float* in, int32_t ld_in, const int32_t* in_row_map, const int32_t* dst_rows,
+                        const int32_t* indptr, const int32_t* indices, const float* norm, int32_t n_rows,
+                        int32_t f_in, int32_t scale_dst, float* out, int32_t ld_out, const int32_t* pos_indptr,
+                        cudaStream_t stream);
+int active_out_lists_build(const int32_t* rows, int n_rows, const int32_t* t_indptr, const int32_t* t_indices,
+                           const int32_t* keep, int32_t* count, int32_t* ptr, int32_t* out_idx, cudaStream_t stream);
+int gcn_layer_wgrad_impl(const float* in, int32_t ld_in, const int32_t* in_row_map, const int32_t* dst_rows,
+                         const int32_t* indptr, const int32_t* indices, const float* norm, const int32_t* task_row_ptr,
+                         int32_t n_tasks, const float* dZ, int32_t ld_dz, int32_t f_in, int32_t f_out, float* dW,
+                         int64_t dw_task_stride, float* db, int64_t db_task_stride, void* workspace,
+                         int64_t workspace_bytes, int64_t rows_hint, cudaStream_t s);
+
 // ---- streamed-weight tensor-core layer kernel (gcn_layer_tc.cu) ----
 bool gcn_layer_fwd_tc_supported(const GatherSrc& g, int ldw, int trans_w, int f_out, const float* out,
                                 int ld_out);

@@ -64,6 +64,12 @@ struct StepBuffers {
   float* agg_spt[GMETA_MAX_LAYERS];   // [n_act[l], ld_in(l)]: aggregated input of layer l (l = 0: of the features, once per step)
   float* agg_qry[GMETA_MAX_LAYERS];
   float* dagg;                        // aggregated dZ of the data-gradient step (one at a time)
+  // active out-neighbour lists of the pruned backward (layer l >= 1: rows of act[l-1] -> their out-neighbours in act[l])
+  int32_t* aout_ptr_spt[GMETA_MAX_LAYERS];
+  int32_t* aout_idx_spt[GMETA_MAX_LAYERS];
+  int32_t* aout_ptr_qry[GMETA_MAX_LAYERS];
+  int32_t* aout_idx_qry[GMETA_MAX_LAYERS];
+  int32_t* aout_count;
   int n_ident;                        // rows of the identity graph
   int32_t* iota;
   float* ones;
@@ -142,6 +148,14 @@ void carve(const gmeta_step_args_t* a, void* ws, StepBuffers& b) {
     if (nq > n_max) n_max = nq;
   }
   b.dagg = c.take<float>(a->pruned_forward && m.n_layers > 1 ? n_max * ld_max : 0);
+  for (int l = 0; l < GMETA_MAX_LAYERS; ++l) {
+    const bool need = a->pruned_forward && l >= 1 && l < m.n_layers;
+    b.aout_ptr_spt[l] = c.take<int32_t>(need ? (int64_t)a->spt.n_act[l - 1] + 1 : 0);
+    b.aout_idx_spt[l] = c.take<int32_t>(need ? (int64_t)a->spt.n_edges : 0);
+    b.aout_ptr_qry[l] = c.take<int32_t>(need && a->compute_meta_grad ? (int64_t)a->qry.n_act[l - 1] + 1 : 0);
+    b.aout_idx_qry[l] = c.take<int32_t>(need && a->compute_meta_grad ? (int64_t)a->qry.n_edges : 0);
+  }
+  b.aout_count = c.take<int32_t>(a->pruned_forward ? 2 * n_max : 0);
   b.n_ident = a->pruned_forward ? (int)n_max : 0;
   b.iota = c.take<int32_t>(a->pruned_forward ? n_max + 1 : 0);
   b.ones = c.take<float>(a->pruned_forward ? n_max : 0);
@@ -362,22 +376,25 @@ struct Runner {
         // layer l (the others are dropped through row_pos[l]), then the dense contraction with W^T, masked by
         // the ReLU of the layer below.
         const float* agg = (&set == &a->spt ? b.agg_spt : b.agg_qry)[l];
-        run(gmeta_gcn_layer_wgrad(agg, ld_in, nullptr, nullptr, b.iota, b.iota, b.ones, set.act_task_ptr[l], set.n_tasks,
-                                  dz[cur], b.ld[l], m.f_in[l], m.f_out[l], gout + m.w_off[l], P, gout + m.b_off[l], P,
-                                  b.wgrad_ws, b.wgrad_ws_bytes, s));
+        run(gcn_layer_wgrad_impl(agg, ld_in, nullptr, nullptr, b.iota, b.iota, b.ones, set.act_task_ptr[l], set.n_tasks,
+                                 dz[cur], b.ld[l], m.f_in[l], m.f_out[l], gout + m.w_off[l], P, gout + m.b_off[l], P,
+                                 b.wgrad_ws, b.wgrad_ws_bytes, set.n_act[l], s));
         if (l > 0) {
-          run(gmeta_aggregate_rows(dz[cur], b.ld[l], set.row_pos[l], set.act_rows[l - 1], set.t_indptr, set.t_indices,
-                                   set.norm, set.n_act[l - 1], m.f_out[l], 1, b.dagg, b.ld[l], s));
+          const bool is_spt = &set == &a->spt;
+          run(aggregate_rows_impl(dz[cur], b.ld[l], set.row_pos[l], set.act_rows[l - 1], nullptr,
+                                  (is_spt ? b.aout_idx_spt : b.aout_idx_qry)[l], set.norm, set.n_act[l - 1], m.f_out[l], 1,
+                                  b.dagg, b.ld[l], (is_spt ? b.aout_ptr_spt : b.aout_ptr_qry)[l], s));
           dense(b.dagg, b.ld[l], set.act_tile_row0[l - 1], set.act_tile_nrows[l - 1], set.act_tile_task[l - 1],
                 set.n_act_tiles[l - 1], set.n_tasks, w, l, 1, 2, act[l - 1], dz[cur ^ 1], b.ld[l - 1]);
           cur ^= 1;
         }
         continue;
       }
-      run(gmeta_gcn_layer_wgrad(in, ld_in, l == 0 ? set.feat_row : nullptr, sparse ? set.act_rows[l] : nullptr,
-                                set.indptr, set.indices, set.norm, sparse ? set.act_task_ptr[l] : set.task_row_ptr,
-                                set.n_tasks, dz[cur], b.ld[l], m.f_in[l], m.f_out[l], gout + m.w_off[l], P,
-                                gout + m.b_off[l], P, b.wgrad_ws, b.wgrad_ws_bytes, s));
+      run(gcn_layer_wgrad_impl(in, ld_in, l == 0 ? set.feat_row : nullptr, sparse ? set.act_rows[l] : nullptr,
+                               set.indptr, set.indices, set.norm, sparse ? set.act_task_ptr[l] : set.task_row_ptr,
+                               set.n_tasks, dz[cur], b.ld[l], m.f_in[l], m.f_out[l], gout + m.w_off[l], P,
+                               gout + m.b_off[l], P, b.wgrad_ws, b.wgrad_ws_bytes,
+                               sparse ? set.n_act[l] : set.n_nodes, s));
       if (l > 0) {
         // data gradient = the forward kernel on the transposed graph with W^T, masked by the
         // ReLU of the layer below (features carry no gradient, so layer 0 stops here).  Sparse:
@@ -472,40 +489,39 @@ extern "C" int gmeta_maml_step(const gmeta_step_args_t* a_in, void* stream) {
   r.max_rows_s = a->spt_max_rows_per_task > 0 ? a->spt_max_rows_per_task : sp.n_subgraphs;
   r.max_rows_q = a->qry_max_rows_per_task > 0 ? a->qry_max_rows_per_task : qr.n_subgraphs;
 
-  // ---- prologue (main stream): structure-only bookkeeping of both sets, operand images of theta ----
+  // ---- prologue: structure-only bookkeeping and the layer-0 neighbourhood sums -- the support set's and the operand
+  // images of theta on the main stream, the query set's on the auxiliary stream (forked here; its first forward
+  // waits for the first support step anyway) ----
   if (cudaMemsetAsync(b.g_spt, 0, (size_t)T * P * sizeof(float), s) != cudaSuccess) return GMETA_ERR_LAUNCH;
   if (cudaMemsetAsync(b.g_qry, 0, (size_t)T * P * sizeof(float), s) != cudaSuccess) return GMETA_ERR_LAUNCH;
-  r.run(gmeta_degree_norm(sp.indptr, sp.n_nodes, sp.norm, s));
-  r.run(gmeta_degree_norm(qr.indptr, qr.n_nodes, qr.norm, s));
-  r.run(gmeta_proto_label_prep(sp.labels, sp.task_sub_ptr, T, sp.class_pos, sp.class_occ, sp.n_classes, s));
-  r.run(gmeta_proto_label_prep(qr.labels, qr.task_sub_ptr, T, qr.class_pos, qr.class_occ, qr.n_classes, s));
-  if (!a->dense_backward) {   // row -> position maps of the active-row lists (structure only: once per step)
-    for (int l = 0; l < m.n_layers; ++l) {
-      r.run(gmeta_build_row_pos(sp.act_rows[l], sp.n_act[l], sp.n_nodes, sp.row_pos[l], s));
-      if (a->compute_meta_grad || a->pruned_forward)
-        r.run(gmeta_build_row_pos(qr.act_rows[l], qr.n_act[l], qr.n_nodes, qr.row_pos[l], s));
-    }
-  }
-  if (b.use_ex) {
-    for (int i = 0; i < (m.n_layers > 1 ? 2 : 1); ++i) {
-      r.run(gmeta_layer_plan_build(sp.indptr, sp.indices, sp.norm, i == 0 ? sp.feat_row : nullptr, nullptr, sp.tile_row0,
-                                   sp.tile_nrows, sp.tile_task, sp.n_tiles, T, sp.n_nodes, sp.n_edges, b.plan_spt[i], s));
-      r.run(gmeta_layer_plan_build(qr.indptr, qr.indices, qr.norm, i == 0 ? qr.feat_row : nullptr, nullptr, qr.tile_row0,
-                                   qr.tile_nrows, qr.tile_task, qr.n_tiles, T, qr.n_nodes, qr.n_edges, b.plan_qry[i], s));
-    }
+  signal(0, s);
+  wait(0, sq);
+  for (int side = 0; side < 2 && r.ok(); ++side) {
+    const gmeta_packed_set_t& set = side ? qr : sp;
+    cudaStream_t st = side ? sq : s;
+    void* const* plan = side ? b.plan_qry : b.plan_spt;
+    r.run(gmeta_degree_norm(set.indptr, set.n_nodes, set.norm, st));
+    r.run(gmeta_proto_label_prep(set.labels, set.task_sub_ptr, T, set.class_pos, set.class_occ, set.n_classes, st));
+    if (!a->dense_backward && (side == 0 || a->compute_meta_grad || a->pruned_forward))
+      for (int l = 0; l < m.n_layers; ++l)   // row -> position maps of the active-row lists (structure only)
+        r.run(gmeta_build_row_pos(set.act_rows[l], set.n_act[l], set.n_nodes, set.row_pos[l], st));
+    if (b.use_ex)
+      for (int i = 0; i < (m.n_layers > 1 ? 2 : 1); ++i)
+        r.run(gmeta_layer_plan_build(set.indptr, set.indices, set.norm, i == 0 ? set.feat_row : nullptr, nullptr,
+                                     set.tile_row0, set.tile_nrows, set.tile_task, set.n_tiles, T, set.n_nodes,
+                                     set.n_edges, plan[i], st));
+    if (a->pruned_forward && (side == 0 || a->compute_meta_grad))
+      for (int l = 1; l < m.n_layers; ++l)   // out-neighbour lists of the data gradients (structure only)
+        r.run(active_out_lists_build(set.act_rows[l - 1], set.n_act[l - 1], set.t_indptr, set.t_indices, set.row_pos[l],
+                                     b.aout_count + (side ? b.n_ident : 0), (side ? b.aout_ptr_qry : b.aout_ptr_spt)[l],
+                                     (side ? b.aout_idx_qry : b.aout_idx_spt)[l], st));
+    if (a->pruned_forward)   // layer-0 sums: features and structure only, once per meta-step
+      r.run(gmeta_aggregate_rows(a->feat_table, a->ld_feat, set.feat_row, set.act_rows[0], set.indptr, set.indices,
+                                 set.norm, set.n_act[0], m.f_in[0], 1, (side ? b.agg_qry : b.agg_spt)[0], a->ld_feat, st));
   }
   if (a->pruned_forward) r.run(fill_identity_graph(b.iota, b.ones, b.n_ident, s));
   if (b.pack.n_seg > 0)
     r.run(gcn_tc_sgd_pack(a->theta, 0, nullptr, 0.f, 1, (int)P, nullptr, b.pack, b.img_theta, s));
-  signal(0, s);
-  wait(0, sq);
-  if (a->pruned_forward) {
-    // layer-0 neighbourhood sums of both sets (features and structure only): the query set's on the auxiliary stream
-    r.run(gmeta_aggregate_rows(a->feat_table, a->ld_feat, sp.feat_row, sp.act_rows[0], sp.indptr, sp.indices, sp.norm,
-                               sp.n_act[0], m.f_in[0], 1, b.agg_spt[0], a->ld_feat, s));
-    r.run(gmeta_aggregate_rows(a->feat_table, a->ld_feat, qr.feat_row, qr.act_rows[0], qr.indptr, qr.indices, qr.norm,
-                               qr.n_act[0], m.f_in[0], 1, b.agg_qry[0], a->ld_feat, sq));
-  }
 
   // ---- K inner steps.  Main stream: support forward -> loss -> backward -> SGD (+ operand images).  The query
   // forward of step k (weights fast_k, prototypes of support forward k) follows on the auxiliary stream; the one
