@@ -12,7 +12,9 @@ runs its own 32-task share (weak scaling, task-sharded; one NCCL all-reduce per 
 
   value : device-resident -- packed meta-batches already in HBM when the timed region starts.
   e2e   : through the reference-facing call Meta.forward(host batch): host packing, ONE pinned
-          H2D copy of the packed integer arrays, the device work, D2H of the accuracy vector.
+          H2D copy of the packed integer arrays, the device work, D2H of the accuracy vector -- every step,
+          all inside the timed region; like train.py's loop, batch i+1 is handed to Meta.prefetch (packer thread
+          + copy stream) before step i is run, so its packing and copy overlap step i.
   roofline : the dominant kernel (fused GCN layer, query set, hidden->hidden) timed alone with
           CUDA events on its launch stream; algorithmic bytes per SURVEY 8d / DESIGN.md.
   cpu_baseline : the oracle port of the reference (oracle/gmeta_oracle.py, torch CPU, all host
@@ -497,6 +499,8 @@ def main():
     accs_box = [None]
 
     def e2e_step(i):
+        # the training loop's own pattern (train.py): hand the NEXT batch to the packer thread, then run this one
+        m.prefetch(*batches[(i + 1) % len(batches)], ds.feats)
         accs_box[0] = m(*batches[i % len(batches)], ds.feats)
     ms_e2e_k, ms_e2e, n_e2e = timed_region(e2e_step, args.steps, world, td)
     accs = accs_box[0]

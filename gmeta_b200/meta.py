@@ -183,7 +183,7 @@ def _feat_fingerprint(feat):
 
 class _DeviceBatch(object):
     """An uploaded meta-batch: segment plans of both sets + the device int32 buffer holding them."""
-    __slots__ = ("T", "max_classes", "ft", "ps_s", "ps_q", "ints", "h2d_bytes", "resident")
+    __slots__ = ("T", "max_classes", "ft", "ps_s", "ps_q", "ints", "h2d_bytes", "resident", "ready", "pack_ms")
 
 
 class FusedAdam(object):
@@ -256,6 +256,10 @@ class Meta(nn.Module):
         self._feat_cache = None
         self._ws = None
         self._scratch = {}
+        self._pool = None              # worker thread of `prefetch`
+        self._copy_stream = None
+        self._prefetched = None
+        self._slot_i = 0
         self._theta_flat = None        # flat parameter buffer the net's parameters are views of
         self._aux_stream = None        # second stream for the query forwards (gmeta_step_args_t::aux_stream)
         self._graphs = {}              # captured meta-steps of device-resident batches
@@ -275,7 +279,8 @@ class Meta(nn.Module):
         for k, v in self.__dict__.items():
             if k == "_feat_cache":
                 new.__dict__[k] = v          # the resident table is read-only: copies share it (train.py:87,127)
-            elif k in ("_staging", "_ws", "_scratch", "_extractor", "_theta_flat", "_aux_stream", "_graphs"):
+            elif k in ("_staging", "_ws", "_scratch", "_extractor", "_theta_flat", "_aux_stream", "_graphs", "_pool",
+                       "_copy_stream", "_prefetched"):
                 new.__dict__[k] = {} if k in ("_scratch", "_graphs") else None
             else:
                 new.__dict__[k] = deepcopy(v, memo)
@@ -325,35 +330,94 @@ class Meta(nn.Module):
             cs.row_pos[l] = self._buf("%srow_pos%d" % (tag, l), (ps.N,), torch.int32, dev).data_ptr()
         return cs
 
-    def upload_batch(self, batch, feat, own_buffer=False):
-        """Pack one collated meta-batch (host, integer only) and copy it to the device with ONE
-        async transfer from pinned memory.  With own_buffer=True the device copy gets its own
-        allocation (so several batches can stay resident, e.g. for device-resident benchmarking);
-        otherwise the grow-only staging buffer is reused."""
-        x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry = batch
-        dev = _dev()
+    # -- host batch -> device: packing + ONE pinned H2D copy, optionally one step ahead on a worker thread --
+    def _pack_threads(self):
+        """Host threads of the CSR packer: the cores of the box shared between the ranks on it, 8 at most."""
+        import os
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+        return max(1, min(8, (os.cpu_count() or 1) // local_world))
+
+    def _slot(self, dev):
+        """Next staging slot of a ring of four (pinned buffer + device buffer each): the step in flight, the batch
+        being packed behind it, one more pending prefetch and a spare."""
+        if self._staging is None or self._staging[0].device != dev:
+            self._staging = [packing.Staging(dev) for _ in range(4)]
+            self._slot_i = 0
+        self._slot_i = (self._slot_i + 1) % len(self._staging)
+        slot = self._staging[self._slot_i]
+        for e in [e for e in (self._prefetched or []) if e[3] is slot]:
+            e[2].result()                      # an abandoned prefetch still owns this slot: retire it
+            self._prefetched.remove(e)
+        return slot
+
+    def _pack_upload(self, batch, ft, slot, dev, own_buffer, copy_stream):
+        """Pack `batch` into the slot's pinned buffer and start its host->device copy (worker or caller thread)."""
+        torch.cuda.set_device(dev)
+        x_spt, y_spt, x_qry, y_qry = batch[:4]
         db = _DeviceBatch()
         db.resident = bool(own_buffer)
         db.T = len(x_spt)
         db.max_classes = packing.validate_labels(y_spt, y_qry, self.k_spt)
-        db.ft = self._features(feat, dev)
-        if db.ft.f0 != self.spec.conv[0][0]:
-            raise RuntimeError("feature width %d does not match the first GraphConv (%d)"
-                               % (db.ft.f0, self.spec.conv[0][0]))
-        L = len(self.spec.conv)
-        if self._staging is None or self._staging.device != dev:
-            self._staging = packing.Staging(dev)
+        db.ft = ft
         t0 = time.perf_counter()
-        db.ps_s, db.ps_q, _ = packing.pack_meta_batch(self._staging, batch, db.ft.graph_row_off, L, _lib.lib())
-        self.host_pack_ms = 1e3 * (time.perf_counter() - t0)
+        db.ps_s, db.ps_q, _ = packing.pack_meta_batch(slot, batch, ft.graph_row_off, len(self.spec.conv), _lib.lib(),
+                                                      n_threads=self._pack_threads())
+        db.pack_ms = 1e3 * (time.perf_counter() - t0)
+        n = db.ps_q.end
         if own_buffer:
-            db.ints = torch.empty(db.ps_q.end, dtype=torch.int32, device=dev)
-            db.ints.copy_(self._staging.host[:db.ps_q.end], non_blocking=True)
-            torch.cuda.current_stream().synchronize()     # staging is reused by the next upload
+            db.ints = torch.empty(n, dtype=torch.int32, device=dev)
+            db.ints.copy_(slot.host[:n], non_blocking=True)
+            torch.cuda.current_stream().synchronize()     # the slot is reused by the next upload
+            db.ready = None
         else:
-            self._staging.upload(db.ps_q.end)
-            db.ints = self._staging.dev
-        db.h2d_bytes = db.ps_q.end * 4
+            slot.upload(n, copy_stream)
+            db.ints, db.ready = slot.dev, slot.copied
+        db.h2d_bytes = n * 4
+        return db
+
+    def prefetch(self, x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry, feat):
+        """Start packing and uploading a meta-batch NOW, on a worker thread and a copy stream, while the current
+        step runs; the next `forward(...)` / `finetunning_batch(...)` given the same lists picks it up.  Same
+        arguments as `forward`.  (The reference's DataLoader hides its batch preparation behind the step in worker
+        processes, train.py:96; this hides the part that is specific to this build.)"""
+        from concurrent.futures import ThreadPoolExecutor
+        dev = _dev()
+        batch = (x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry)
+        ft = self._features(feat, dev)
+        if ft.f0 != self.spec.conv[0][0]:
+            raise RuntimeError("feature width %d does not match the first GraphConv (%d)" % (ft.f0, self.spec.conv[0][0]))
+        if self._pool is None:
+            self._pool = ThreadPoolExecutor(max_workers=1)
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        if self._prefetched is None:
+            self._prefetched = []
+        slot = self._slot(dev)
+        fut = self._pool.submit(self._pack_upload, batch, ft, slot, dev, False, self._copy_stream)
+        # the caller's pattern is prefetch(batch i+1) followed by forward(batch i): two entries can be pending
+        while len(self._prefetched) >= 2:
+            self._prefetched.pop(0)[2].result()            # an abandoned prefetch: let the worker finish with its slot
+        self._prefetched.append((x_spt, feat, fut, slot))
+
+    def upload_batch(self, batch, feat, own_buffer=False):
+        """Pack one collated meta-batch (host, integer only) and copy it to the device with ONE
+        async transfer from pinned memory.  With own_buffer=True the device copy gets its own
+        allocation (so several batches can stay resident, e.g. for device-resident benchmarking);
+        otherwise a slot of the staging ring is used.  A batch that `prefetch` already started is picked up."""
+        dev = _dev()
+        if self._prefetched is None:
+            self._prefetched = []
+        pend = self._prefetched
+        hit = next((e for e in pend if e[0] is batch[0] and e[1] is feat), None) if not own_buffer else None
+        if hit is not None:
+            pend.remove(hit)
+            db = hit[2].result()
+        else:
+            ft = self._features(feat, dev)
+            if ft.f0 != self.spec.conv[0][0]:
+                raise RuntimeError("feature width %d does not match the first GraphConv (%d)"
+                                   % (ft.f0, self.spec.conv[0][0]))
+            db = self._pack_upload(batch, ft, self._slot(dev), dev, own_buffer, None)
+        self.host_pack_ms = db.pack_ms
         return db
 
     def build_batch_on_device(self, graphs, req_spt, req_qry, feat, h, sample_nodes=1000, seed=222):
@@ -368,7 +432,7 @@ class Meta(nn.Module):
         if getattr(self, "_extractor", None) is None or self._extractor[0] != key:
             self._extractor = (key, DeviceExtractor(graphs, dev), graphs)
         db = _DeviceBatch()
-        db.resident = False
+        db.resident, db.ready, db.pack_ms = False, None, 0.0
         db.T = int(req_spt.sub_off.shape[0] - 1)
         T = db.T
         split = lambda r: [r.labels[r.sub_off[t]:r.sub_off[t + 1]] for t in range(T)]      # noqa: E731
@@ -414,6 +478,8 @@ class Meta(nn.Module):
         if train and steps < 2:
             raise RuntimeError("element 0 of tensors does not require grad and does not have a grad_fn "
                                "(update_step must be >= 2, as in the reference: meta.py:137-141,161)")
+        if getattr(db, "ready", None) is not None:
+            torch.cuda.current_stream().wait_event(db.ready)          # the batch's H2D copy (maybe on the copy stream)
         base = db.ints.data_ptr()
         a = _lib.StepArgs()
         a.model = self.spec.c_model()

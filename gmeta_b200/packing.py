@@ -351,14 +351,19 @@ def pack_meta_batch(staging, batch, graph_row_off, n_layers, lib, n_threads=0):
 
 
 class Staging(object):
-    """Grow-only pinned host buffer + device buffer for the packed integer arrays."""
+    """Grow-only pinned host buffer + device buffer for the packed integer arrays.  `copied` is the CUDA event of the
+    last host->device copy out of the pinned buffer: the buffer must not be rewritten (the packer uses non-temporal
+    stores straight into it) before that copy has finished -- `reserve` waits for it."""
 
     def __init__(self, device):
         self.device = device
         self.host = None
         self.dev = None
+        self.copied = None
 
     def reserve(self, n):
+        if self.copied is not None:
+            self.copied.synchronize()          # the previous DMA out of this pinned buffer is done
         if self.host is None or self.host.numel() < n:
             cap = int(n * 1.25) + 1024
             self.host = torch.empty(cap, dtype=torch.int32, pin_memory=torch.cuda.is_available())
@@ -371,6 +376,14 @@ class Staging(object):
             self._flags = np.zeros(int(n * 1.25) + 64, dtype=np.uint8)
         return self._flags
 
-    def upload(self, n):
-        self.dev[:n].copy_(self.host[:n], non_blocking=True)
+    def upload(self, n, stream=None):
+        """Async copy of the first n ints to the device buffer on `stream` (default: the current stream); returns the
+        bytes moved.  The event recorded behind the copy guards the pinned buffer (reserve) and is what a consumer on
+        another stream waits for."""
+        st = stream if stream is not None else torch.cuda.current_stream()
+        with torch.cuda.stream(st):
+            self.dev[:n].copy_(self.host[:n], non_blocking=True)
+            if self.copied is None:
+                self.copied = torch.cuda.Event()
+            self.copied.record(st)
         return n * 4

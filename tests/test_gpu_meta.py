@@ -256,6 +256,33 @@ def test_two_streams_and_graph_replay_equal_the_serial_eager_step():
             assert torch.equal(a, b)
 
 
+def test_prefetch_pipeline_equals_plain_forward():
+    """Meta.prefetch(next batch) + Meta.forward(batch) (packing and H2D of batch i+1 on a worker thread / copy stream
+    while step i runs) gives exactly the accuracies, losses and weights of plain forward calls; a prefetched batch that
+    is not the one forward() then receives is dropped safely."""
+    from gmeta_b200.meta import Meta
+    ds = H.tiny_dataset('shared')
+    rng = np.random.default_rng(12)
+    mbs = [ds.sample_meta_batch(rng) for _ in range(5)]
+    outs = []
+    for mode in ("plain", "prefetch", "mismatch"):
+        torch.manual_seed(9)
+        m = Meta(ds.args(), ds.config()).to(U.dev())
+        accs = []
+        for i, mb in enumerate(mbs):
+            if mode == "prefetch" and i + 1 < len(mbs):
+                m.prefetch(*mbs[i + 1], ds.feats)
+            if mode == "mismatch":
+                m.prefetch(*mbs[(i + 2) % len(mbs)], ds.feats)         # not the batch that comes next
+            accs.append((m(*mb, ds.feats), m.last["loss_q"]))
+        outs.append((accs, [p.detach().cpu().clone() for p in m.net.parameters()]))
+    for o in outs[1:]:
+        for (a, la), (b, lb) in zip(o[0], outs[0][0]):
+            assert np.array_equal(a, b) and la == lb
+        for p, q in zip(o[1], outs[0][1]):
+            assert torch.equal(p, q)
+
+
 def test_parameters_alias_the_flat_buffer_and_survive_deepcopy():
     """The net's parameters are views of the flat theta buffer the kernels update in place; deepcopy (train.py:87,127)
     and in-place edits keep working, and a copy trains independently of the original."""

@@ -119,10 +119,21 @@ def main(args):
             db = DataLoader(db_train, args.task_num, shuffle=True, num_workers=args.num_workers, collate_fn=collate)
         s_f = time.time()
         s_r = s_f
-        for step, batch in enumerate(db):
+        # one-batch lookahead: while step i runs on the GPU, batch i+1 is packed and uploaded (maml.prefetch)
+        if args.device_extract == 'True':
+            prep = lambda bt: (bt, bt[1])                                       # noqa: E731  (requests, global task count)
+        else:
+            prep = lambda bt: (dist.shard_meta_batch(bt), len(bt[0]))           # noqa: E731  this rank's tasks, global count
+        it = iter(db)
+        nxt = next(it, None)
+        nxt = None if nxt is None else prep(nxt)
+        step = -1
+        while nxt is not None:
+            (batch, n_tasks), step = nxt, step + 1
+            nxt = next(it, None)
+            nxt = None if nxt is None else prep(nxt)
             data_loading_time = time.time() - (s_r if step >= 1 else s_f)
             s = time.time()
-            n_tasks = batch[1] if args.device_extract == 'True' else len(batch[0])
             if n_tasks < world:                  # a trailing meta-batch with fewer tasks than ranks
                 continue
             maml.global_task_num = n_tasks        # meta.py:161 divides by the whole meta-batch's task count
@@ -130,7 +141,9 @@ def main(args):
                 accs = maml.forward_device(graphs, batch[0][0], batch[0][1], feat, args.h, args.sample_nodes,
                                            seed=222 + 1000 * epoch + step)
             else:
-                accs = maml(*dist.shard_meta_batch(batch), feat)
+                if nxt is not None and nxt[1] >= world:
+                    maml.prefetch(*nxt[0], feat)
+                accs = maml(*batch, feat)
             max_memory = max(max_memory, float(psutil.virtual_memory().used / (1024 ** 3)))
             if step % args.train_result_report_steps == 0:
                 say('Epoch:', epoch + 1, ' Step:', step, ' training acc:', str(accs[-1])[:5], ' time elapsed:',
