@@ -270,6 +270,7 @@ class Meta(nn.Module):
         self.last = {}                 # diagnostics of the most recent call (loss, launches, bytes)
         self.return_meta_grad = False  # tests: keep a copy of the reduced meta-gradient
         self.global_task_num = None    # set when ranks hold unequal task shares
+        self.collective = True         # False: this instance steps on its own even inside an initialised process group
 
     # -- state that must not travel through copy.deepcopy(maml) (train.py:87,127) --
     def __deepcopy__(self, memo):
@@ -538,7 +539,7 @@ class Meta(nn.Module):
         if self.global_task_num is not None:
             return int(self.global_task_num)
         from . import dist
-        return local_tasks * dist.world_size()
+        return local_tasks * (dist.world_size() if self.collective else 1)
 
     def _flat_theta(self, params, dev):
         """The flat parameter buffer [W1 | b1 | ... | Wlin | blin] of the C ABI.  The net's parameters are kept as
@@ -601,7 +602,8 @@ class Meta(nn.Module):
                 g.replay()
             else:
                 self._enqueue(db, K, True, theta, meta_grad=red[:P], stats=red[P:])
-        dist.allreduce_sum_(red)
+        if self.collective:
+            dist.allreduce_sum_(red)
         # meta.py:161-171: gate = sum loss / task_num, NaN -> skip; Adam on theta (the net's own storage)
         self.meta_optim.step(theta, red[:P], loss_sum=red[P:P + 1], loss_scale=1.0 / T_global, acc_sums=red[P + 1:],
                              step_out=out)
