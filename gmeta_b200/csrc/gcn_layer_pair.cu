@@ -351,6 +351,11 @@ template <> struct VecLd<2> {
   }
 };
 
+// output rows are written once and not read again by this launch: streaming (evict-first) stores
+__device__ __forceinline__ void st_f4_stream(float* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // Expansion of one staged accumulator block to the output rows of a compute tile (epilogue warps).  `stg` is the
 // [TM slots][EBLK] block (16-byte units XOR-swizzled by slot), rinfo[r] = (slot, factor) of tile row r.  Octet `oct`
 // of epilogue warp `ew` owns rows ew*4 + oct + 64*i; its lane u holds columns [c0, c0+4) and [c0+32, c0+36).
@@ -428,8 +433,8 @@ __device__ __forceinline__ void expand_block(const ExpandArgs& a, int ew, int la
         }
       }
       float* o = outp + (size_t)r * ldo;
-      if (live && st0) st_f4(o, w0);
-      if (live && st1) st_f4(o + 32, w1);
+      if (live && st0) st_f4_stream(o, w0);
+      if (live && st1) st_f4_stream(o + 32, w1);
       if (RMX) {
         float m = 0.f;
         if (ok0) m = fmaxf(fmaxf(fabsf(w0.x), fabsf(w0.y)), fmaxf(fabsf(w0.z), fabsf(w0.w)));

@@ -423,6 +423,24 @@ def test_sgd_and_adam_match_torch():
     assert int(skipped) == 1 and torch.equal(before, p_dev)                # NaN loss: no update (meta.py:163-164)
 
 
+def test_public_euclidean_dist_matches_reference_golden_and_raises_like_it():
+    """gmeta_b200.meta.euclidean_dist (meta.py:14-26): squared distances [N, M]; a width mismatch raises the bare
+    Exception of meta.py:20-21.  Checked against the oracle restatement (pinned to the reference) on CPU and GPU
+    tensors, and through proto_loss_qry's distances implicitly elsewhere."""
+    from gmeta_b200.meta import euclidean_dist
+    rng = np.random.default_rng(21)
+    for n, m, d in ((72, 3, 3), (10, 2, 2), (1, 1, 7), (33, 5, 40)):
+        x = torch.tensor(rng.standard_normal((n, d), dtype=np.float32))
+        y = torch.tensor(rng.standard_normal((m, d), dtype=np.float32))
+        want = O.euclidean_dist(x, y)
+        got_cpu = euclidean_dist(x, y)
+        got_dev = euclidean_dist(x.to(U.dev()), y.to(U.dev()))
+        assert got_cpu.shape == (n, m) and torch.equal(got_cpu, want)
+        U.report("euclidean_dist [%d,%d,%d]" % (n, m, d), got_dev, want, 1e-6, 1e-6)
+    with pytest.raises(Exception):
+        euclidean_dist(torch.zeros(4, 3), torch.zeros(2, 5))
+
+
 def test_adam_step_device_state_matches_torch_and_skips_like_the_reference():
     """gmeta_adam_step (step count, gate and bias corrections on the device; CUDA-graph safe) vs torch.optim.Adam:
     a NaN loss skips the update AND leaves the step count alone, exactly like not calling Adam.step (meta.py:163-169)."""
