@@ -61,6 +61,8 @@ def parse():
     ap.add_argument("--no-full", action="store_true", help="skip the full-formulation (unpruned) arm")
     ap.add_argument("--no-device-extract", action="store_true", help="skip the device-extraction end-to-end arm")
     ap.add_argument("--no-configs", action="store_true", help="skip the C3 / C4 / C5 strong-scaling blocks")
+    ap.add_argument("--roofline-only", action="store_true",
+                    help="only the full-layer launches of `roofline` on the seeded query set (the command to put under ncu)")
     return ap.parse_args()
 
 
@@ -133,6 +135,10 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
+
+# dram__bytes_read.sum + dram__bytes_write.sum of one full-layer launch (three kernels) per packed-row count N of the
+# seeded query set it was captured on (profiles/r02_layer_pair_full.md)
+PROFILE_TRAFFIC = {1284403: 2.643074e9}
 
 TIE_GAP = 2e-4   # twice the stated logit tolerance (north_star: logits within 1e-4, identical argmax)
 
@@ -316,15 +322,120 @@ def layer_roofline(m, db, peaks, impl):
                                       "all inside the timed launch" % (f_in, f_out, N, E, T),
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "peak_source": "measured (MEASURED_PEAKS.json, burst copy)" if "hbm_gbs" in peaks else "fallback",
-            # dram__bytes_read.sum + dram__bytes_write.sum of the launch's kernels (w_absmax + pack_w + hub_prepass +
-            # pair kernel) from profiles/r01d_layer_pair_full.md, captured on tools/layer_bench.py --real (another
-            # random C2 query set: N=1,243,405, algorithmic 2.5685 GB there, i.e. traffic / algorithmic = 1.004)
-            "traffic": 2.5785e9, "traffic_over_algorithmic": 1.004, "ms_per_launch": ms, "algorithmic_bytes": alg_bytes,
+            # dram__bytes_read.sum + dram__bytes_write.sum summed over the launch's three kernels (weight split + hub
+            # pre-pass + pair kernel) from ONE `ncu --set full` capture of `bench.py --roofline-only` -- the same seeded
+            # query set as this run when N matches (profiles/r02_layer_pair_full.md); null otherwise
+            "traffic": PROFILE_TRAFFIC.get(N), "traffic_over_algorithmic": (PROFILE_TRAFFIC[N] / alg_bytes if N in PROFILE_TRAFFIC else None),
+            "traffic_source": "profiles/r02_layer_pair_full.md (ncu --set full, same seeded query set)" if N in PROFILE_TRAFFIC else None,
+            "ms_per_launch": ms, "algorithmic_bytes": alg_bytes,
             "tflops_fp32_equiv": flops / (ms * 1e-3) / 1e12,
             "share_note": "working set %.2f GB > 126 MB L2, no flush needed; the timed meta-step runs in the exact "
                           "pruned mode (layers over their active rows only), so this full-layer launch is not part of "
                           "it -- SURVEY 8d asks for the roofline on the full-layer kernel with full-formulation bytes; "
-                          "kernel shares of the step: profiles/r01d_bench_launches.md" % (alg_bytes / 1e9)}
+                          "kernel shares of that step and of the full-formulation step (where this launch dominates): "
+                          "profiles/r02_*_launches.md" % (alg_bytes / 1e9)}
+
+
+def pruned_step_roofline(m, db, ds, ms_per_step, peaks):
+    """Algorithmic bytes of the PRUNED meta-step (the one `value` times) from the realised active-row lists, next to
+    the measured step time, plus the two kernels that dominate it timed alone on the query set (CUDA events):
+    gmeta_aggregate_rows (layer-1 neighbourhood sums of the centre rows) and the dense contraction on pre-summed rows.
+    The step's working set (tens of MB) lives in the 126 MB L2 and the step is a chain of ~200 short dependent
+    launches, so its fraction of the HBM roofline says how far the LATENCY-bound chain is from the bandwidth bound."""
+    from gmeta_b200 import _lib
+    L = _lib.lib()
+    dev = db.ints.device
+    spec = m.spec
+    K, T, P = ds.update_step, db.T, spec.n_params_padded
+    ints = db.ints.cpu().numpy()
+    st = torch.cuda.current_stream().cuda_stream
+    per_set = {}
+    for tag, ps in (("spt", db.ps_s), ("qry", db.ps_q)):
+        indptr = ints[ps.off["indptr"]:ps.off["indptr"] + ps.N + 1].astype(np.int64)
+        deg = np.diff(indptr)
+        info = []
+        for l in range(len(spec.conv)):
+            rows = ints[ps.off["act_rows%d" % l]:ps.off["act_rows%d" % l] + ps.act[l]["n"]].astype(np.int64)
+            info.append({"n": int(rows.shape[0]), "in_edges": int(deg[rows].sum())})
+        per_set[tag] = info
+    f = [spec.conv[0][0]] + [c[1] for c in spec.conv]          # widths F0, H, H, ...
+    nl = len(spec.conv)
+
+    def fwd_bytes(info, first):
+        b = 0.0
+        for l in range(nl):
+            if l > 0 or first:      # neighbourhood sums (layer 0: once per step per set)
+                b += 4.0 * (info[l]["in_edges"] * (f[l] + 1) + info[l]["n"] * (f[l] + 2))
+            b += 4.0 * (info[l]["n"] * (f[l] + f[l + 1]) + T * (f[l] * f[l + 1] + f[l + 1]))      # dense contraction
+        return b
+
+    def bwd_bytes(info):
+        b = 0.0
+        for l in range(nl - 1, -1, -1):
+            b += 4.0 * (info[l]["n"] * (f[l] + f[l + 1]) + T * (f[l] + 1) * f[l + 1])             # weight gradient
+            if l > 0:   # data gradient: sums over the active out-neighbours + dense contraction with W^T + ReLU mask
+                b += 4.0 * (info[l]["in_edges"] * (f[l + 1] + 1) + info[l - 1]["n"] * (f[l + 1] + 2))
+                b += 4.0 * (info[l - 1]["n"] * (f[l + 1] + 2 * f[l]) + T * f[l] * f[l + 1])
+        return b
+    s_i, q_i = per_set["spt"], per_set["qry"]
+    step_bytes = (fwd_bytes(s_i, True) + (K - 1) * fwd_bytes(s_i, False) + (K + 1) * bwd_bytes(s_i) +
+                  fwd_bytes(q_i, True) + K * fwd_bytes(q_i, False) + bwd_bytes(q_i) + K * 12.0 * T * P)
+    peak = peaks.get("hbm_gbs", 6650.0)
+    ach = step_bytes / (ms_per_step * 1e-3) / 1e9
+    out = {"bound": "latency (L2-resident working set, ~200 dependent launches)", "algorithmic_bytes": step_bytes,
+           "ms_per_step": ms_per_step, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+           "active_rows": per_set,
+           "formula": "K support fwd+bwd (+1 prototype-path bwd), K+1 query fwd, 1 query bwd over the ACTIVE rows of each "
+                      "layer: gathers 4*(in_edges*(F+1) + n*(F+2)), dense 4*(n*(Fin+Fout) + T*(Fin*Fout+Fout)), weight "
+                      "gradient 4*(n*(Fin+Fout) + T*(Fin+1)*Fout), SGD 12*T*P; layer-0 sums once per step"}
+    # ---- the two dominant kernels alone, query set, layer 1 ----
+    if nl >= 2:
+        ps = db.ps_q
+        base = db.ints.data_ptr()
+        seg = lambda k: base + 4 * ps.off[k]  # noqa: E731
+        H = f[1]
+        n0, n1 = ps.act[0]["n"], ps.act[1]["n"]
+        norm = torch.empty(ps.N, device=dev)
+        _lib.check(L.gmeta_degree_norm(seg("indptr"), ps.N, norm.data_ptr(), st))
+        row_pos0 = torch.empty(ps.N, dtype=torch.int32, device=dev)
+        _lib.check(L.gmeta_build_row_pos(seg("act_rows0"), n0, ps.N, row_pos0.data_ptr(), st))
+        act0 = torch.randn(n0, H, device=dev)
+        agg1 = torch.empty(n1, H, device=dev)
+        out1 = torch.empty(n1, H, device=dev)
+        W = torch.randn(T, P, device=dev) * 0.05
+        cm = spec.c_model()
+        iota = torch.arange(n1 + 1, dtype=torch.int32, device=dev)
+        ones = torch.ones(n1, device=dev)
+        nb = L.gmeta_gcn_layer_fwd_workspace_bytes(T, P, H, H, 0)
+        ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
+
+        def agg():
+            _lib.check(L.gmeta_aggregate_rows(act0.data_ptr(), H, row_pos0.data_ptr(), seg("act_rows1"), seg("indptr"),
+                                              seg("indices"), norm.data_ptr(), n1, H, 1, agg1.data_ptr(), H, st))
+
+        def dense():
+            _lib.check(L.gmeta_gcn_layer_fwd(agg1.data_ptr(), H, None, None, iota.data_ptr(), iota.data_ptr(), ones.data_ptr(),
+                                             seg("act_tile_row01"), seg("act_tile_nrows1"), seg("act_tile_task1"),
+                                             ps.act[1]["n_tiles"], T, W.data_ptr() + 4 * cm.w_off[1], P, H, 0,
+                                             W.data_ptr() + 4 * cm.b_off[1], P, H, H, 1, None, out1.data_ptr(), H, 0,
+                                             ws.data_ptr(), nb, st))
+        kern = {}
+        for name, fn, nbytes in (("aggregate_rows (query, layer 1)", agg, 4.0 * (q_i[1]["in_edges"] * (H + 1) + n1 * (H + 2))),
+                                 ("dense contraction (query, layer 1)", dense, 4.0 * (2 * n1 * H + T * (H * H + H)))):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(50):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) / 50 * 1e3
+            kern[name] = {"us_per_launch": us, "algorithmic_bytes": nbytes, "achieved_GBps": nbytes / us / 1e3,
+                          "note": "L2-resident operands: latency-bound, not a DRAM figure"}
+        out["kernels"] = kern
+    return out
 
 
 _RESULT_OUT = None
@@ -454,6 +565,14 @@ def main():
     batches = [ds.sample_meta_batch(rng, tasks) for _ in range(args.batches)]
     extract_s = (time.perf_counter() - t0) / args.batches
 
+    if args.roofline_only:
+        torch.manual_seed(222)
+        m = Meta(ds.args(), ds.config()).to(dev)
+        db = m.upload_batch(batches[0], ds.feats, own_buffer=True)
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        emit({"roofline": layer_roofline(m, db, peaks, args.kernel_impl)})
+        return
+
     # ---------------- parity gate: nothing is timed before the GPU path agrees with the CPU arm ----------------
     parity, cb = None, None
     if rank == 0 and not args.no_cpu_baseline:
@@ -576,6 +695,7 @@ def main():
     if rank != 0:
         return
     roof = layer_roofline(m, dbs[0], peaks, args.kernel_impl)
+    roof_step = pruned_step_roofline(m, dbs[0], ds, ms_total / n_total, peaks)
     extraction = device_extraction(ds, batches[0], extract_s)
     cfg = workload_desc(ds, tasks)
     cfg.update({"parallelism": "task-sharded x%d" % world, "l2_policy": "inputs larger than L2 (packed meta-batch "
@@ -597,7 +717,7 @@ def main():
                     "ms_per_step": ms_e2e / n_e2e, "steps_timed": n_e2e, "timed_s": ms_e2e * 1e-3,
                     "contract_ms_per_step": ms_e2e_k / args.steps},
             "gpu_launches": int(launches[0]), "gpu_launches_per_step": int(launches_per_step),
-            "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cb,
+            "clocks": sampler.summary(), "roofline": roof, "roofline_step": roof_step, "cpu_baseline": cb,
             "parity_in_run": bool(parity["ok"]) if parity else None, "parity": parity}
     if extraction:
         line["extraction"] = extraction
