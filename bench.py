@@ -131,6 +131,10 @@ class ClockSampler(threading.Thread):
                     self.nv, self.source = None, "nvidia-smi"
             time.sleep(0.005 if self.nv is not None else 0.1)
 
+    def reset(self):
+        """Forget what was sampled so far (warm-up): only the timed regions are reported."""
+        self.sm, self.mx, self.reasons = [], [], set()
+
     def summary(self):
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
@@ -483,9 +487,10 @@ def timed_region(step_fn, steps, world, td):
         return float(t[0])
     ms_k = block(0)
     total_ms, total_steps = ms_k, steps
-    more = int(np.ceil(max(0.0, MIN_TIMED_S * 1e3 - ms_k) / max(ms_k, 1e-3)))    # identical on all ranks (reduced time)
-    for r in range(min(more, 2000)):
-        total_ms += block((r + 1) * steps)
+    r = 0
+    while total_ms < MIN_TIMED_S * 1e3 and r < 2000:      # the reduced times are identical on all ranks: same trip count
+        r += 1
+        total_ms += block(r * steps)
         total_steps += steps
     return ms_k, total_ms, total_steps
 
@@ -509,7 +514,7 @@ def strong_scaling_config(name, world, rank, local_rank, kernel_impl, steps, war
     m = Meta(margs, ds.config()).to(torch.device("cuda", local_rank))
     m.global_task_num = T
     dbs = [m.upload_batch(dist.shard_meta_batch(b, rank, world), ds.feats, own_buffer=True) for b in batches]
-    for i in range(max(3, warmup)):
+    for i in range(max(3, warmup, 2 * len(dbs))):        # every resident batch past its eager pass and its graph capture
         out = m.step_device(dbs[i % len(dbs)])
     ms_k, ms_tot, n = timed_region(lambda i: m.step_device(dbs[i % len(dbs)]), steps, world, td)
     out = m.step_device(dbs[0]).cpu().numpy()
@@ -598,11 +603,12 @@ def main():
 
     # ---------------- device-resident arm ----------------
     dbs = [m.upload_batch(b, ds.feats, own_buffer=True) for b in batches]
-    for i in range(max(3, args.warmup)):
+    sampler = ClockSampler(local_rank)
+    sampler.start()                                      # its first NVML queries land in the warm-up, not in the timed region
+    for i in range(max(3, args.warmup, 2 * len(dbs))):   # every resident batch past its eager pass and its graph capture
         m.step_device(dbs[i % len(dbs)])
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.reset()
     launches = [0]
     outs = [None]
 

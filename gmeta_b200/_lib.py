@@ -84,6 +84,10 @@ _SIGNATURES = {
     "gmeta_khop_workspace_bytes": (i64, [i32, i32, i32]),
     "gmeta_khop_select": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, C.c_uint64, vp, vp, vp, vp, i64, vp]),
     "gmeta_khop_build": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
+    "gmeta_packed_set_finish_workspace_bytes": (i64, [i32, i32, i32]),
+    "gmeta_packed_set_finish": (C.c_int, [vp, vp, i32, i32, vp, vp, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp,
+                                          C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
+                                          vp, vp, vp, i64, vp]),
     "gmeta_maml_step_workspace_bytes": (i64, [C.POINTER(StepArgs)]),
     "gmeta_maml_step": (C.c_int, [C.POINTER(StepArgs), vp]),
     "gmeta_last_launch_count": (C.c_int, []),

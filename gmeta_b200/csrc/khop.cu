@@ -346,7 +346,9 @@ __global__ void __launch_bounds__(KH_THREADS) khop_build_kernel(const BuildParam
   }
 }
 
-inline int khop_grid(int n_req) { return n_req < 2 * kNumSMs ? n_req : 2 * kNumSMs; }
+// one CTA per request, eight resident per SM: the kernels are chains of dependent index loads and barriers, so
+// they are paid for in latency and want every warp slot of the SM (16 KB of shared memory and 32 registers each)
+inline int khop_grid(int n_req) { return n_req < 8 * kNumSMs ? n_req : 8 * kNumSMs; }
 inline int64_t khop_scratch_stride(int max_graph_nodes) {
   return ((int64_t)(max_graph_nodes + 31) / 32 + max_graph_nodes + 64 + 63) / 64 * 64;   // uint32 per CTA
 }

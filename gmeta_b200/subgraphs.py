@@ -137,6 +137,72 @@ class DeviceExtractor(object):
         self.indptr = torch.from_numpy(indptr).to(self.dev)
         self.indices = torch.from_numpy(indices).to(self.dev)
         self._ws = None
+        self._parent = None
+
+    def _workspace(self, nb, slot):
+        import torch
+        if self._ws is None:
+            self._ws = {}
+        ws = self._ws.get(slot)
+        if ws is None or ws.numel() < nb + 256:
+            ws = self._ws[slot] = torch.empty(int(nb) + 256, dtype=torch.uint8, device=self.dev)
+        return (ws.data_ptr() + 255) // 256 * 256
+
+    def select(self, graph_idx, centre_a, centre_b=None, h=2, sample_nodes=1000, seed=222, slot=0):
+        """First half of an extraction (gmeta_khop_select): closures, sampling and the exclusive node / edge
+        sums of the requests, all left on the device.  `slot` picks the workspace, so that the selections of
+        several sets can be in flight before their sizes are read with ONE copy (`totals`)."""
+        import torch
+        L = self.L
+        i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(self.dev, non_blocking=True)  # noqa: E731
+        gi = np.asarray(graph_idx, dtype=np.int64)
+        R = int(gi.shape[0])
+        lo = self.node_off[gi]
+        hi = self.node_off[gi + 1]
+        hops_a, hops_b = (2, 1) if centre_b is not None else (int(h), 0)
+        if centre_b is None and h not in (1, 2, 3):
+            raise NameError("h_hops_neighbor")      # like the reference for other h (:300-311)
+        # the request arrays of a set travel as ONE host->device copy
+        req = np.stack([np.asarray(centre_a, dtype=np.int64) + lo,
+                        (np.asarray(centre_b, dtype=np.int64) + lo) if centre_b is not None else lo, lo, hi]).astype(np.int32)
+        d_req = i32(req)
+        sel = {"R": R, "a": d_req[0], "b": d_req[1] if centre_b is not None else None, "lo": d_req[2], "hi": d_req[3],
+               "req": d_req, "sample_nodes": sample_nodes, "slot": slot,
+               "nb": L.gmeta_khop_workspace_bytes(R, sample_nodes, self.max_graph_nodes),
+               "node_ptr": torch.empty(R + 1, dtype=torch.int32, device=self.dev),
+               "edge_ptr": torch.empty(R + 1, dtype=torch.int32, device=self.dev),
+               "closure_size": torch.empty(max(R, 1), dtype=torch.int32, device=self.dev)}
+        sel["ws_ptr"] = self._workspace(sel["nb"], slot)
+        st = torch.cuda.current_stream().cuda_stream
+        ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        self._lib.check(L.gmeta_khop_select(ptr(self.indptr), ptr(self.indices), ptr(sel["a"]), ptr(sel["b"]), ptr(sel["lo"]),
+                                            ptr(sel["hi"]), R, hops_a, hops_b, sample_nodes, self.max_graph_nodes, seed,
+                                            ptr(sel["node_ptr"]), ptr(sel["edge_ptr"]), ptr(sel["closure_size"]),
+                                            sel["ws_ptr"], sel["nb"], st), "khop_select")
+        return sel
+
+    def totals(self, sels):
+        """Packed node / edge totals of the given selections: the one device->host copy of an extraction."""
+        import torch
+        t = torch.stack([x for s in sels for x in (s["node_ptr"][s["R"]], s["edge_ptr"][s["R"]])]).cpu()
+        for i, s in enumerate(sels):
+            s["N"], s["E"] = int(t[2 * i]), int(t[2 * i + 1])
+
+    def build_into(self, sel, indptr, indices, feat_row, centre_row, parent=None):
+        """Second half (gmeta_khop_build) straight into caller-provided int32 device tensors (views of the packed
+        buffer): indptr [N+1], indices [>= E], feat_row [N], centre_row [R * cps]."""
+        import torch
+        N = sel["N"]
+        if parent is None:
+            if self._parent is None or self._parent.numel() < max(N, 1):
+                self._parent = torch.empty(max(N, 1), dtype=torch.int32, device=self.dev)
+            parent = self._parent
+        st = torch.cuda.current_stream().cuda_stream
+        ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        self._lib.check(self.L.gmeta_khop_build(ptr(self.indptr), ptr(self.indices), ptr(sel["a"]), ptr(sel["b"]), ptr(sel["lo"]),
+                                                sel["R"], sel["sample_nodes"], self.max_graph_nodes, ptr(sel["node_ptr"]),
+                                                ptr(sel["edge_ptr"]), ptr(indptr), ptr(indices), ptr(parent), ptr(feat_row),
+                                                ptr(centre_row), sel["ws_ptr"], sel["nb"], st), "khop_build")
 
     def extract(self, graph_idx, centre_a, centre_b=None, h=2, sample_nodes=1000, seed=222):
         """graph_idx / centre_a / centre_b: int arrays of length R (node ids inside their graph).
@@ -144,40 +210,14 @@ class DeviceExtractor(object):
         (the reference ignores h there, :327-333).  Returns a dict of device tensors (packed layout) and
         the per-request pointers."""
         import torch
-        L = self.L
-        i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(self.dev)  # noqa: E731
-        gi = np.asarray(graph_idx, dtype=np.int64)
-        R = int(gi.shape[0])
-        lo = self.node_off[gi]
-        hi = self.node_off[gi + 1]
-        a = i32(np.asarray(centre_a, dtype=np.int64) + lo)
-        b = i32(np.asarray(centre_b, dtype=np.int64) + lo) if centre_b is not None else None
-        d_lo, d_hi = i32(lo), i32(hi)
-        hops_a, hops_b = (2, 1) if centre_b is not None else (int(h), 0)
-        if centre_b is None and h not in (1, 2, 3):
-            raise NameError("h_hops_neighbor")      # like the reference for other h (:300-311)
-        nb = L.gmeta_khop_workspace_bytes(R, sample_nodes, self.max_graph_nodes)
-        if self._ws is None or self._ws.numel() < nb + 256:
-            self._ws = torch.empty(int(nb) + 256, dtype=torch.uint8, device=self.dev)
-        ws_ptr = (self._ws.data_ptr() + 255) // 256 * 256
-        node_ptr = torch.empty(R + 1, dtype=torch.int32, device=self.dev)
-        edge_ptr = torch.empty(R + 1, dtype=torch.int32, device=self.dev)
-        closure = torch.empty(max(R, 1), dtype=torch.int32, device=self.dev)
-        st = torch.cuda.current_stream().cuda_stream
-        ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
-        self._lib.check(L.gmeta_khop_select(ptr(self.indptr), ptr(self.indices), ptr(a), ptr(b), ptr(d_lo), ptr(d_hi), R,
-                                            hops_a, hops_b, sample_nodes, self.max_graph_nodes, seed, ptr(node_ptr),
-                                            ptr(edge_ptr), ptr(closure), ws_ptr, nb, st), "khop_select")
-        totals = torch.stack((node_ptr[R], edge_ptr[R])).cpu()       # the batch's only D2H: 8 bytes
-        N, E = int(totals[0]), int(totals[1])
-        out = {"node_ptr": node_ptr, "edge_ptr": edge_ptr, "closure_size": closure, "N": N, "E": E,
+        sel = self.select(graph_idx, centre_a, centre_b, h, sample_nodes, seed)
+        self.totals([sel])                                            # the batch's only D2H: 8 bytes
+        N, E, R = sel["N"], sel["E"], sel["R"]
+        out = {"node_ptr": sel["node_ptr"], "edge_ptr": sel["edge_ptr"], "closure_size": sel["closure_size"], "N": N, "E": E,
                "indptr": torch.empty(N + 1, dtype=torch.int32, device=self.dev),
                "indices": torch.empty(max(E, 1), dtype=torch.int32, device=self.dev),
                "parent": torch.empty(max(N, 1), dtype=torch.int32, device=self.dev),
                "feat_row": torch.empty(max(N, 1), dtype=torch.int32, device=self.dev),
-               "centre_row": torch.empty(max(R, 1) * (2 if b is not None else 1), dtype=torch.int32, device=self.dev)}
-        self._lib.check(L.gmeta_khop_build(ptr(self.indptr), ptr(self.indices), ptr(a), ptr(b), ptr(d_lo), R, sample_nodes,
-                                           self.max_graph_nodes, ptr(node_ptr), ptr(edge_ptr), ptr(out["indptr"]),
-                                           ptr(out["indices"]), ptr(out["parent"]), ptr(out["feat_row"]),
-                                           ptr(out["centre_row"]), ws_ptr, nb, st), "khop_build")
+               "centre_row": torch.empty(max(R, 1) * (2 if sel["b"] is not None else 1), dtype=torch.int32, device=self.dev)}
+        self.build_into(sel, out["indptr"], out["indices"], out["feat_row"], out["centre_row"], out["parent"])
         return out

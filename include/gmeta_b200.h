@@ -416,6 +416,30 @@ int gmeta_khop_build(const int32_t* indptr, const int32_t* indices, const int32_
                      int32_t* out_indptr, int32_t* out_indices, int32_t* out_parent, int32_t* out_global,
                      int32_t* out_centre, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Packed-set assembly on the device (csrc/batch_assemble.cu): what gmeta_packed_set_t needs on top of the
+ * extractor's output, derived in HBM without a host round trip -- the structure work of dgl.batch
+ * (subgraph_data_processing.py:399-406) and of the host packer.  Inputs: the packed CSR by destination
+ * (indptr [N+1], indices [E]), sub_node_ptr [S+1] (first packed row of every subgraph: node_ptr of
+ * gmeta_khop_select), task_sub_ptr [T+1] (device), centre_row [n_centres].  Outputs (device, caller-sized):
+ *   t_indptr [N+1], t_indices [E]         CSR by source, destinations ascending inside a row
+ *   task_row_ptr [T+1]; tile_row0/nrows/task [<= ceil(N/128) + T]   tiles of <= 128 rows inside one task
+ *   per GCN layer l < n_layers: act_rows[l] [<= N] (ascending), act_task_ptr[l] [T+1],
+ *     act_tile_row0/nrows/task[l] [<= ceil(N/128) + T]: the rows whose gradient is not structurally zero
+ *     (centres at the last layer, the in-neighbours of the layer above below it, learner.py:166-170)
+ *   centre_pos [n_centres]                position of every centre among act_rows[n_layers - 1]
+ *   counts [2 + 2 * n_layers]             n_tiles, rows of the largest task, n_act[l]..., n_act_tiles[l]...
+ * The pointer arrays are HOST arrays of device pointers.  Integer work: identical to the host packer. */
+int64_t gmeta_packed_set_finish_workspace_bytes(int32_t n_nodes, int32_t n_edges, int32_t n_layers);
+int gmeta_packed_set_finish(const int32_t* indptr, const int32_t* indices, int32_t n_nodes, int32_t n_edges,
+                            const int32_t* sub_node_ptr, const int32_t* task_sub_ptr, int32_t n_tasks,
+                            const int32_t* centre_row, int32_t n_centres, int32_t n_layers,
+                            int32_t* t_indptr, int32_t* t_indices, int32_t* task_row_ptr, int32_t* tile_row0,
+                            int32_t* tile_nrows, int32_t* tile_task, int32_t* const* act_rows,
+                            int32_t* const* act_task_ptr, int32_t* const* act_tile_row0,
+                            int32_t* const* act_tile_nrows, int32_t* const* act_tile_task,
+                            int32_t* centre_pos, int32_t* counts, void* workspace, int64_t workspace_bytes,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif
