@@ -2,7 +2,19 @@
 #include "common.cuh"
 #include "internal.cuh"
 
+#include <cstdlib>
+
 using namespace gmeta;
+
+namespace gmeta {
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("GMETA_B200_PDL");
+    return e && e[0] && e[0] != '0';
+  }();
+  return on;
+}
+}  // namespace gmeta
 
 extern "C" int gmeta_version(void) { return 100; }
 

@@ -318,7 +318,7 @@ extern "C" int gmeta_packed_set_finish(const int32_t* indptr, const int32_t* ind
                                        int32_t* centre_pos, int32_t* counts, void* workspace, int64_t workspace_bytes,
                                        void* stream) {
   if (n_nodes <= 0 || n_edges < 0 || n_tasks <= 0 || n_layers < 0 || n_layers > GMETA_MAX_LAYERS) return GMETA_ERR_BAD_ARG;
-  if (!indptr || !sub_node_ptr || !task_sub_ptr || !centre_row || !t_indptr || !task_row_ptr || !tile_row0 ||
+  if (!indptr || !sub_node_ptr || !centre_row || !t_indptr || !task_row_ptr || !tile_row0 ||
       !tile_nrows || !tile_task || !counts || (n_edges > 0 && (!indices || !t_indices)))
     return GMETA_ERR_BAD_ARG;
   if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return GMETA_ERR_WORKSPACE;

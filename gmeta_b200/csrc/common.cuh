@@ -17,6 +17,34 @@ inline int check_launch() {
   return cudaGetLastError() == cudaSuccess ? GMETA_OK : GMETA_ERR_LAUNCH;
 }
 
+// ---- programmatic dependent launch (opt-in: GMETA_B200_PDL=1) ----
+// Every kernel of the library can be launched with the programmatic-serialization attribute and begins with
+// pdl_prologue(): "my dependents may be scheduled" (they park at their own wait) and "wait until the kernel before
+// me has completed and its writes are visible".  Stream order is unchanged -- a kernel touches memory only after
+// its wait, and it completes only after that, so completion stays transitive along the chain -- but the launch
+// latency and block scheduling of kernel i+1 overlap kernel i.  Measured on the C2 meta-step (~200 dependent
+// launches on two streams, round 2): 2.99 ms per step without, 3.21 ms with it -- the parked blocks of one stream's
+// next kernel take SM slots from the other stream's kernels -- and no measurable change of the full-layer launch
+// or of the eager end-to-end step, so it is OFF unless GMETA_B200_PDL=1.  Both instructions are no-ops in a
+// launch without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+bool pdl_enabled();     // api.cu
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at;
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // errors surface in check_launch()
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 inline int ceil_div(int x, int m) { return (x + m - 1) / m; }

@@ -100,10 +100,6 @@ constexpr int HUB_BIG = 128;                    // hubs with more (padded) edge 
 constexpr int PT_MAXT = 2048;                  // tasks the pair-table kernel handles
 constexpr int SCALE_TARGET = 13;               // scaled bound in [2^13, 2^14): 4x below the FP16 maximum
 constexpr int SCALE_CLAMP = 100;
-#ifndef GMETA_HUB_ROWS
-#define GMETA_HUB_ROWS 6
-#endif
-constexpr int HUB_ROWS = GMETA_HUB_ROWS;         // 8-record rows a producer warp keeps in flight in the fused hub phase
 
 // ---- plan (graph structure + tiling only; built once per packed set and operand mapping) ----
 struct PlanRec {      // 16 bytes
@@ -114,11 +110,10 @@ struct CTile { int row0, nrows, nslots, task; };   // compute tile: output rows 
 struct PairEnt {      // 64 bytes; nrows[1] = nslots[1] = 0 when the task has an odd tile count
   int row0[2], nslots[2];     // first 16 bytes: what the gather producers need (slot s of a tile: srec[row0 + s])
   int nrows[2], task, cost0;  // cost0: schedule cost of all pairs before this one
-  int hub_base[2], h8_beg[2]; // hub rows of the two tiles: first hub id (= row of mlong), first 8-record row of their edge list
-  int n8[2], pad[2];          // 8-record rows of the two tiles' hub edge lists
+  int pad[8];
 };
 struct Plan {
-  int* hdr;           // [0] n_hubs  [1] n_hub_edges  [2] n_pairs  [3] n_big_hubs  [4] n_compute_tiles  [5] hub ids given out  [6] 8-record rows given out
+  int* hdr;           // [0] n_hubs  [1] n_hub_edges  [2] n_pairs  [3] n_big_hubs  [4] n_compute_tiles
   PlanRec* rec;       // [n_rows] record of every output row (input of the dedupe pass)
   PlanRec* srec;      // [n_rows] records of the slots of a compute tile at srec[tile.row0 + slot]
   uint8_t* row_slot;  // [n_rows] slot of every output row inside its compute tile
@@ -133,13 +128,6 @@ struct Plan {
   // hub edge list, grouped by tile then hub, every hub padded to a multiple of 4 records (pads: norm 0)
   int* hub_src;       // [cap_edges] mapped source row
   float* hub_nrm;     // [cap_edges]
-  // the same hubs once more, ordered by compute tile (pair order, then slot order): hub `slot` gets the id
-  // hub_new[slot] (ids of a compute tile are consecutive; mlong / mlong_bound are indexed by id) and its records
-  // lie in tile order, every hub padded to whole rows of 8 records; the sources of a hub's FIRST row carry the
-  // sign bit.  The fused kernel's producers walk a tile's list front to back (hub sums inside the layer kernel).
-  int* hub_new;       // [cap_hub]
-  int* h8_src;        // [cap_edges8]
-  float* h8_nrm;      // [cap_edges8]
   int64_t total;
 };
 struct Workspace {
@@ -185,10 +173,6 @@ Plan carve_plan(void* base, int n_tiles, int n_tasks, int n_rows, int n_edges) {
   const int64_t ce = (int64_t)n_edges + 3LL * ch + 64;
   pl.hub_src = reinterpret_cast<int*>(c.take(ce * 4));
   pl.hub_nrm = reinterpret_cast<float*>(c.take(ce * 4));
-  pl.hub_new = reinterpret_cast<int*>(c.take((int64_t)ch * 4));
-  const int64_t ce8 = (int64_t)n_edges + 7LL * ch + 64;
-  pl.h8_src = reinterpret_cast<int*>(c.take(ce8 * 4));
-  pl.h8_nrm = reinterpret_cast<float*>(c.take(ce8 * 4));
   pl.total = c.off;
   return pl;
 }
@@ -220,11 +204,8 @@ struct PairParams {
   int ld_in;
   int f_in;
   const float* in_rowmax;
-  float* mlong;                  // [hub id][f_in] aggregated hub rows (written by the pre-pass, or by this kernel when `fused`)
-  float* mlong_bound;
-  const int* h8_src;             // tile-ordered hub edge records (fused hub sums)
-  const float* h8_nrm;
-  int fused;                     // 1: the producers sum the hub rows of their tile themselves (f_in == 256), no pre-pass
+  const float* mlong;
+  const float* mlong_bound;
   const PlanRec* srec;           // slot records of the compute tiles
   const uint8_t* row_slot;       // output row -> slot of its compute tile
   const int* hdr;
@@ -291,16 +272,6 @@ __device__ __forceinline__ void ld8(float* d, const float* p) {      // 256-bit 
                : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]), "=f"(d[4]), "=f"(d[5]), "=f"(d[6]), "=f"(d[7])
                : "l"(p));
 }
-// Predicated 256-bit load INTO d (d keeps its contents when !pred).  The destination registers are read-write
-// operands of one asm statement, so no select between "loaded" and "zero" follows the load: a select would wait
-// for the load right behind its issue and serialise the loads that are meant to be in flight together.
-__device__ __forceinline__ void ld8_if(float* d, const float* p, bool pred) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %9, 0;\n\t"
-      "@q ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]), "+f"(d[4]), "+f"(d[5]), "+f"(d[6]), "+f"(d[7])
-      : "l"(p), "r"((unsigned)pred));
-}
 // One output row's gather state for one tile: where its (<= 2) sources live, their norms and abs-max.
 struct RowCtx {
   const float* s0;
@@ -331,10 +302,16 @@ struct RowCtx {
 };
 // buf[0..7] = 8 floats of source 0 at column offset `off`, buf[8..15] = of source 1 (zeros when absent)
 __device__ __forceinline__ void gather_request(float* buf, const RowCtx& c, int off, int dbg) {
+  if (c.a0 != 0.f && !(dbg & 2)) ld8(buf, c.s0 + off);
+  else {
 #pragma unroll
-  for (int j = 0; j < 16; ++j) buf[j] = 0.f;
-  ld8_if(buf, c.s0 + off, c.a0 != 0.f && !(dbg & 2));
-  ld8_if(buf + 8, c.s1 + off, c.a1 != 0.f && !(dbg & 2));
+    for (int j = 0; j < 8; ++j) buf[j] = 0.f;
+  }
+  if (c.a1 != 0.f && !(dbg & 2)) ld8(buf + 8, c.s1 + off);
+  else {
+#pragma unroll
+    for (int j = 8; j < 16; ++j) buf[j] = 0.f;
+  }
 }
 // v = n0 * src0 + n1 * src1 over 8 columns -> scaled FP16 hi/lo
 __device__ __forceinline__ void combine(const float* m, float n0, float n1, uint4& hi, uint4& lo) {
@@ -342,71 +319,6 @@ __device__ __forceinline__ void combine(const float* m, float n0, float n1, uint
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = fmaf(n1, m[8 + j], n0 * m[j]);
   split8(v, hi, lo);
-}
-
-// Hub rows of one compute tile, summed by the CTA's eight producer warps (f_in = 256): warp w owns columns
-// [32w, 32w + 32) of EVERY hub of the tile, a lane quad one record of an 8-record row (8 floats per lane: a warp
-// load fetches eight 128-byte row segments), NR rows in flight per warp.  The records of the next round are
-// fetched one round ahead, one record per lane, and handed to the quads by shuffles.  A hub's sum is the tree
-// over its lanes' partials (records r, r+8, ... per lane, then xor 4, 8, 16): fixed order, no atomics.
-// Row id of hub i of the tile: hub_base + i.  (The scale bounds mlong_bound come from hub_bounds_part.)
-template <int NR>
-__device__ __forceinline__ void hub_phase(const PairParams& p, int warp, int lane, int hub_base, int h8_beg, int n8) {
-  static_assert(NR > 4 && NR <= 8, "records of a round: 32 in the first register pair, the rest in the second");
-  if (n8 <= 0) return;
-  const int esub = lane >> 2;
-  const int coff = warp * 32 + (lane & 3) * 8;
-  const int* const srcp = p.h8_src + (size_t)h8_beg * 8;
-  const float* const nrmp = p.h8_nrm + (size_t)h8_beg * 8;
-  const int ne = n8 * 8;
-  float acc[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-  int hrow = hub_base - 1;               // mlong row of the hub being accumulated
-  int sA = 0, sB = 0, sA2, sB2;
-  float nA = 0.f, nB = 0.f, nA2, nB2;
-  auto fetch = [&](int base, int& a, int& b, float& na, float& nb) {
-    a = b = 0; na = nb = 0.f;
-    if (base + lane < ne) { a = __ldg(srcp + base + lane); na = __ldg(nrmp + base + lane); }
-    if (lane < 8 * (NR - 4) && base + 32 + lane < ne) { b = __ldg(srcp + base + 32 + lane); nb = __ldg(nrmp + base + 32 + lane); }
-  };
-  auto flush = [&]() {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 4);
-      acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 8);
-      acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
-    }
-    if (esub == 0) st_f8(p.mlong + (size_t)hrow * 256 + coff, acc);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-  };
-  fetch(0, sA, sB, nA, nB);
-  for (int base = 0; base < ne; base += 8 * NR) {
-    float x[NR][8];
-#pragma unroll
-    for (int j = 0; j < NR; ++j) {
-      const int sj = __shfl_sync(0xffffffffu, j < 4 ? sA : sB, (j & 3) * 8 + esub);
-      const float wj = __shfl_sync(0xffffffffu, j < 4 ? nA : nB, (j & 3) * 8 + esub);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) x[j][k] = 0.f;
-      ld8_if(x[j], p.in + (size_t)(sj & 0x7fffffff) * p.ld_in + coff, wj != 0.f && !(p.dbg & 2));
-    }
-    fetch(base + 8 * NR, sA2, sB2, nA2, nB2);
-#pragma unroll
-    for (int j = 0; j < NR; ++j) {
-      const int sj = __shfl_sync(0xffffffffu, j < 4 ? sA : sB, (j & 3) * 8 + esub);
-      const float wj = __shfl_sync(0xffffffffu, j < 4 ? nA : nB, (j & 3) * 8 + esub);
-      if (sj < 0) {                    // first row of a hub (uniform over the warp)
-        if (hrow >= hub_base) flush();
-        ++hrow;
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] = fmaf(wj, x[j][k], acc[k]);
-    }
-    sA = sA2; sB = sB2; nA = nA2; nB = nB2;
-  }
-  if (hrow >= hub_base) flush();
 }
 
 template <int R>
@@ -552,9 +464,6 @@ __device__ __forceinline__ void expand_block(const ExpandArgs& a, int ew, int la
   }
 }
 
-// FUSED: the producers sum the hub rows of their tile themselves (hub_phase); a template parameter, not a run-time
-// flag, so that the chunk buffers are provably dead across the hub phase and its loads get the registers.
-template <bool FUSED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 gcn_layer_fwd_pair_kernel(const PairParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -606,8 +515,8 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
   cluster_sync_all();        // peers' barriers are initialised and TMEM is allocated in both CTAs
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // everything above overlapped the tail of the launch before this one (weight split / hub pre-pass, launched with
-  // programmatic serialization); their results are read from here on
+  // everything above overlapped the tail of the launch before this one (the hub pre-pass, launched -- like this
+  // kernel -- with programmatic serialization); its results and the weight images are read from here on
   pdl_wait();
 
   // contiguous run of tile pairs for this cluster: equal schedule cost (output rows + a per-pair constant) from the
@@ -641,7 +550,7 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
     const int soffA = rA * 64 + ((sub ^ ((rA >> 1) & 3)) << 4);          // 64B swizzle: 16-byte unit ^ ((row / 2) % 4)
     const int soffB = soffA + 64 * 64;                                    // row + 64: same swizzle phase
 #if GMETA_PAIR_PROF
-    long long t_setup = 0, t_wait = 0, t_body = 0, t_hub = 0, t_hbar = 0, t_mark = clock64();
+    long long t_setup = 0, t_wait = 0, t_body = 0, t_mark = clock64();
 #define PLAP(acc) { const long long now_ = clock64(); acc += now_ - t_mark; t_mark = now_; }
 #else
 #define PLAP(acc)
@@ -652,7 +561,7 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
     int row0_n = 0, nrows_n = 0, row0_nn = 0, nrows_nn = 0;
     curA.clear(p.in);
     curB.clear(p.in);
-    if (p_beg < p_end && !FUSED) {
+    if (p_beg < p_end) {
       int row0, nrows;
       ent_tile(p_beg, row0, nrows);
       if (p_beg + 1 < p_end) ent_tile(p_beg + 1, row0_n, nrows_n);
@@ -676,7 +585,7 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       if (kc + 1 < nkc) {
         gather_request(other, curA, (kc + 1) * KCH, p.dbg);
         gather_request(other + 16, curB, (kc + 1) * KCH, p.dbg);
-      } else if (!FUSED) {                                      // first chunk of the next tile
+      } else {                                                  // first chunk of the next tile
         gather_request(other, nxtA, 0, p.dbg);
         gather_request(other + 16, nxtB, 0, p.dbg);
       }
@@ -702,24 +611,6 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       if (lane == 0) mbar_arrive_cluster_relaxed(a_full(s), 0);
     };
     for (int pr = p_beg; pr < p_end; ++pr, ++ti) {
-      if constexpr (FUSED) {
-        // the hub rows of this tile first (all eight warps, see hub_phase), then the tile's slot records: the
-        // hub sums and their bounds are read back below by other warps of this CTA -- bar.sync orders them
-        const int4* ep = reinterpret_cast<const int4*>(p.pairs + pr);
-        const int4 e0 = __ldg(ep), e2 = __ldg(ep + 2), e3 = __ldg(ep + 3);
-        const int row0 = rank ? e0.y : e0.x, nrows = rank ? e0.w : e0.z;
-        hub_phase<HUB_ROWS>(p, warp, lane, rank ? e2.y : e2.x, rank ? e2.w : e2.z, rank ? e3.y : e3.x);
-        PLAP(t_hub);
-        asm volatile("bar.sync 2, %0;" ::"n"(N_PROD_WARPS * 32) : "memory");
-        PLAP(t_hbar);
-        int4 rcA = make_int4(0, 0, 0, 0), rcB = make_int4(0, 0, 0, 0);
-        if (rA < nrows) rcA = __ldg(reinterpret_cast<const int4*>(p.srec + row0 + rA));
-        if (rA + 64 < nrows) rcB = __ldg(reinterpret_cast<const int4*>(p.srec + row0 + rA + 64));
-        curA.decode(rcA, rA < nrows, p, sub);
-        curB.decode(rcB, rA + 64 < nrows, p, sub);
-        gather_request(buf0, curA, 0, p.dbg);
-        gather_request(buf0 + 16, curB, 0, p.dbg);
-      }
       // scale of this tile's rows from the rigorous bound (see header comment)
       {
         const int eA = scale_exponent(curA.a0 * curA.rm0 + curA.a1 * curA.rm1);
@@ -732,7 +623,7 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
       // context of the next tile, fetched while this one streams: pair entry two tiles ahead, row records
       // at chunk 0, source abs-max at the middle chunk, first feature segments at the last chunk
       nrows_nn = 0;
-      if (pr + 2 < p_end && !FUSED) ent_tile(pr + 2, row0_nn, nrows_nn);
+      if (pr + 2 < p_end) ent_tile(pr + 2, row0_nn, nrows_nn);
       const bool liveA_n = rA < nrows_n, liveB_n = rA + 64 < nrows_n;
       int4 rcA_n = make_int4(0, 0, 0, 0), rcB_n = make_int4(0, 0, 0, 0);
       nxtA.clear(p.in);
@@ -759,7 +650,6 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
     if (p.prof && (threadIdx.x == 0 || threadIdx.x == 255)) {
       long long* o = p.prof + blockIdx.x * 16 + (threadIdx.x == 0 ? 0 : 3);
       o[0] = t_setup; o[1] = t_wait; o[2] = t_body;
-      if (threadIdx.x == 0) { p.prof[blockIdx.x * 16 + 14] = t_hub; p.prof[blockIdx.x * 16 + 15] = t_hbar; }
     }
 #endif
   } else if (warp >= WARP_LOAD && warp < WARP_EPI0) {
@@ -970,37 +860,15 @@ gcn_layer_fwd_pair_kernel(const PairParams p) {
 // weights: abs-max per copy, then the scaled FP16 hi/lo image in the operand layout
 // ------------------------------------------------------------------------------------------
 // One CTA per weight copy: abs-max of the copy (block reduction), then its scaled FP16 hi/lo image.
-// CTAs beyond the weight copies (fused hub sums only): the scale bounds of the hub rows,
-// mlong_bound[id] = sum_e nrm[e] * max|in[src[e],:]| -- one warp per hub, lane-strided partials + butterfly.
-struct HubBoundArgs {
-  int n_copies;                 // CTAs [0, n_copies) split the weights, the rest walk the hubs
-  const int* hdr; const int* hub_beg; const int* hub_deg; const int* hub_src; const float* hub_nrm; const int* hub_new;
-  const float* in_rowmax;
-  float* mlong_bound;
-};
 __global__ void __launch_bounds__(1024) pack_w_pair_kernel(const float* __restrict__ W, long long w_stride, int ldw,
                                                            int trans, int K, int N, __half* __restrict__ image,
-                                                           long long image_stride, float* __restrict__ w_inv_scale,
-                                                           const HubBoundArgs hb) {
+                                                           long long image_stride, float* __restrict__ w_inv_scale) {
   __shared__ float red[32];
   __shared__ float s_max;
-  pdl_launch_dependents();      // the hub pre-pass does not read the weight images: it may run beside this kernel
-  if ((int)blockIdx.x >= hb.n_copies) {
-    const int lane = threadIdx.x & 31, n_hub = hb.hdr[0];
-    const int nw = (gridDim.x - hb.n_copies) * 32;
-    for (int slot = (blockIdx.x - hb.n_copies) * 32 + (threadIdx.x >> 5); slot < n_hub; slot += nw) {
-      const int beg = hb.hub_beg[slot], deg = hb.hub_deg[slot];
-      float b = 0.f;
-      for (int e = lane; e < deg; e += 32) {
-        const float nr = hb.hub_nrm[beg + e];
-        if (nr != 0.f) b += nr * hb.in_rowmax[hb.hub_src[beg + e]];
-      }
-#pragma unroll
-      for (int o = 16; o; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
-      if (lane == 0) hb.mlong_bound[hb.hub_new[slot]] = b;
-    }
-    return;
-  }
+  // wait BEFORE releasing the dependents: the hub pre-pass behind this kernel runs beside it (it does not read the
+  // weight images) and waits only at its end, so it must not start before the producer of `in` has completed
+  pdl_wait();
+  pdl_launch_dependents();
   const int c = blockIdx.x;
   const float* w = W + c * w_stride;
   const int inner = trans ? K : N, total = K * N;
@@ -1040,6 +908,7 @@ __global__ void __launch_bounds__(1024) pack_w_pair_kernel(const float* __restri
 
 // per-row abs-max of a row-major matrix (one warp per row)
 __global__ void row_absmax_kernel(const float* __restrict__ x, int ld, int n_rows, int f, float* __restrict__ out) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rows; r += (gridDim.x * blockDim.x) >> 5) {
     const float* row = x + (size_t)r * ld;
@@ -1101,15 +970,15 @@ __global__ void __launch_bounds__(256) hub_prepass_kernel(const float* __restric
                                                           const float* __restrict__ in_rowmax, const int* __restrict__ hdr,
                                                           const int* __restrict__ big_list, const int* __restrict__ hub_beg,
                                                           const int* __restrict__ hub_deg, const int* __restrict__ hub_src,
-                                                          const float* __restrict__ hub_nrm, const int* __restrict__ hub_new,
-                                                          float* __restrict__ mlong, float* __restrict__ mlong_bound) {
+                                                          const float* __restrict__ hub_nrm, float* __restrict__ mlong,
+                                                          float* __restrict__ mlong_bound) {
   constexpr int K = 32 * VEC;
   __shared__ float part[8][K];
   __shared__ float bpart[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // Launched with programmatic serialization behind the weight split, which it does not depend on; the layer kernel
-  // behind it may set up (barriers, tensor memory) as soon as all CTAs of this grid are running.  The wait at the
-  // end makes "this grid complete" imply "weight split complete" for the layer kernel's own wait.
+  // Launched with programmatic serialization behind the weight split, which it does not depend on: the two run side
+  // by side; the layer kernel behind it sets up (barriers, tensor memory) as soon as all CTAs of this grid are
+  // running.  The wait at the end makes "this grid complete" imply "weight split complete" for the layer kernel's wait.
   pdl_launch_dependents();
   if (blockIdx.x >= HUB_BIG_CTAS) {
     const int n_hub = hdr[0];
@@ -1122,18 +991,17 @@ __global__ void __launch_bounds__(256) hub_prepass_kernel(const float* __restric
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
       hub_accumulate<VEC>(in, ld_in, in_rowmax, hub_src + beg, hub_nrm + beg, n, lane, acc, bacc);
-      const int id = hub_new[slot];          // rows of mlong follow the compute-tile order
-      VecLd<VEC>::st(mlong + (size_t)id * K + lane * VEC, acc);
+      VecLd<VEC>::st(mlong + (size_t)slot * K + lane * VEC, acc);
 #pragma unroll
       for (int o = 16; o; o >>= 1) bacc += __shfl_xor_sync(0xffffffffu, bacc, o);
-      if (lane == 0) mlong_bound[id] = bacc;
+      if (lane == 0) mlong_bound[slot] = bacc;
     }
     pdl_wait();
     return;
   }
   const int n_big = hdr[3];
   for (int i = blockIdx.x; i < n_big; i += HUB_BIG_CTAS) {
-    const int slot = big_list[i], id = hub_new[slot];
+    const int slot = big_list[i];
     const int n = (hub_deg[slot] + 3) & ~3, beg = hub_beg[slot];
     float acc[VEC], bacc = 0.f;
 #pragma unroll
@@ -1152,12 +1020,12 @@ __global__ void __launch_bounds__(256) hub_prepass_kernel(const float* __restric
       float v = part[0][threadIdx.x];
 #pragma unroll
       for (int w = 1; w < 8; ++w) v += part[w][threadIdx.x];
-      mlong[(size_t)id * K + threadIdx.x] = v;
+      mlong[(size_t)slot * K + threadIdx.x] = v;
     }
     if (threadIdx.x == 0) {
       float v = bpart[0];
       for (int w = 1; w < 8; ++w) v += bpart[w];
-      mlong_bound[id] = v;
+      mlong_bound[slot] = v;
     }
     __syncthreads();
   }
@@ -1167,19 +1035,18 @@ __global__ void __launch_bounds__(256) hub_prepass_kernel(const float* __restric
 template <int VEC>
 int hub_prepass_launch(const float* in, int ld_in, const float* in_rowmax, const Plan& pl, float* mlong,
                        float* mlong_bound, cudaStream_t stream) {
+  // programmatic serialization (always, unlike the library-wide switch of common.cuh: measured 0.71 -> 0.665 ms per
+  // C2 layer launch): runs beside the weight split in front of it, the layer kernel's set-up runs under its tail
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(HUB_BIG_CTAS + HUB_SMALL_CTAS); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
   cudaLaunchAttribute at;
   at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at.val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = &at; cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, hub_prepass_kernel<VEC>, in, ld_in, in_rowmax, (const int*)pl.hdr, (const int*)pl.big_list,
-                         (const int*)pl.hub_beg, (const int*)pl.hub_deg, (const int*)pl.hub_src, (const float*)pl.hub_nrm,
-                         (const int*)pl.hub_new, mlong, mlong_bound) != cudaSuccess) {
-    cudaGetLastError();
-    return GMETA_ERR_LAUNCH;
-  }
-  return GMETA_OK;
+  cudaLaunchKernelEx(&cfg, hub_prepass_kernel<VEC>, in, ld_in, in_rowmax, (const int*)pl.hdr, (const int*)pl.big_list,
+                     (const int*)pl.hub_beg, (const int*)pl.hub_deg, (const int*)pl.hub_src, (const float*)pl.hub_nrm,
+                     mlong, mlong_bound);
+  return check_launch();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1413,7 +1280,7 @@ __global__ void __launch_bounds__(1024) pair_table_kernel(int n_groups, int n_ta
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     PairEnt e;
     e.row0[0] = e.row0[1] = e.nslots[0] = e.nslots[1] = e.nrows[0] = e.nrows[1] = e.task = e.cost0 = 0;
-    e.hub_base[0] = e.hub_base[1] = e.h8_beg[0] = e.h8_beg[1] = e.n8[0] = e.n8[1] = e.pad[0] = e.pad[1] = 0;
+    for (int k = 0; k < 8; ++k) e.pad[k] = 0;
     pl.pairs[i] = e;
   }
   __syncthreads();
@@ -1465,70 +1332,6 @@ __global__ void __launch_bounds__(1024) pair_table_kernel(int n_groups, int n_ta
   if (threadIdx.x == 0) { pl.hdr[2] = total; pl.hdr[4] = n_ct; }
 }
 
-// One warp per compute tile (pair entry side): the tile's hub slots get consecutive ids in slot order (written
-// back into the slot records: the gather side reads mlong[id]), and their edge records are copied into the
-// tile-ordered list h8_* -- each hub padded to whole rows of 8 records (pads: norm 0), the sources of a hub's
-// first row flagged with the sign bit.  Which tile receives which id range (atomic order) affects no value.
-__global__ void plan_tile_hubs_kernel(Plan pl) {
-  const int n_pairs = pl.hdr[2];
-  const int lane = threadIdx.x & 31;
-  const int nw = (gridDim.x * blockDim.x) >> 5;
-  for (int it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < 2 * n_pairs; it += nw) {
-    PairEnt* ent = pl.pairs + (it >> 1);
-    const int side = it & 1;
-    const int row0 = ent->row0[side], nslots = ent->nslots[side];
-    int slot[4], pd8[4], ord[4], off[4];
-    bool hub[4];
-    int n_h = 0, n_r8 = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int s = 32 * j + lane;
-      hub[j] = false; slot[j] = 0; pd8[j] = 0;
-      if (s < nslots) {
-        const PlanRec rc = pl.srec[row0 + s];
-        if (rc.r1 < 0) { hub[j] = true; slot[j] = rc.r0; pd8[j] = (pl.hub_deg[rc.r0] + 7) >> 3; }
-      }
-      const unsigned bal = __ballot_sync(0xffffffffu, hub[j]);
-      ord[j] = n_h + __popc(bal & ((1u << lane) - 1u));
-      n_h += __popc(bal);
-      const int incl = warp_incl_scan(pd8[j], lane);
-      off[j] = n_r8 + incl - pd8[j];
-      n_r8 += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    int hbase = 0, rbase = 0;
-    if (lane == 0) {
-      if (n_h > 0) { hbase = atomicAdd(pl.hdr + 5, n_h); rbase = atomicAdd(pl.hdr + 6, n_r8); }
-      ent->hub_base[side] = hbase; ent->h8_beg[side] = rbase; ent->n8[side] = n_r8;
-    }
-    hbase = __shfl_sync(0xffffffffu, hbase, 0);
-    rbase = __shfl_sync(0xffffffffu, rbase, 0);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (hub[j]) {
-        pl.hub_new[slot[j]] = hbase + ord[j];
-        pl.srec[row0 + 32 * j + lane].r0 = hbase + ord[j];
-      }
-      unsigned todo = __ballot_sync(0xffffffffu, hub[j]);
-      while (todo) {
-        const int l = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int sl = __shfl_sync(0xffffffffu, slot[j], l);
-        const int n8 = __shfl_sync(0xffffffffu, pd8[j], l);
-        const size_t dst = ((size_t)rbase + __shfl_sync(0xffffffffu, off[j], l)) * 8;
-        const int beg = pl.hub_beg[sl], p4 = (pl.hub_deg[sl] + 3) & ~3;
-        for (int e = lane; e < n8 * 8; e += 32) {
-          int sr = 0;
-          float nr = 0.f;
-          if (e < p4) { sr = pl.hub_src[beg + e]; nr = pl.hub_nrm[beg + e]; }
-          if (e < 8) sr |= (int)0x80000000u;
-          pl.h8_src[dst + e] = sr;
-          pl.h8_nrm[dst + e] = nr;
-        }
-      }
-    }
-  }
-}
-
 int g_pair_dbg = 0;
 long long* g_pair_prof = nullptr;
 
@@ -1577,9 +1380,6 @@ int layer_plan_build(const int32_t* indptr, const int32_t* indices, const float*
   plan_dedupe_kernel<<<ceil_div(n_groups, 4), 128, 0, stream>>>(tile_row0, tile_nrows, tile_task, n_tiles, pl);
   if ((rc = check_launch()) != GMETA_OK) return rc;
   pair_table_kernel<<<1, 1024, 0, stream>>>(n_groups, n_tasks, pl);
-  if ((rc = check_launch()) != GMETA_OK) return rc;
-  const int cp = cap_pairs_for(n_tiles, n_tasks);
-  plan_tile_hubs_kernel<<<ceil_div(2 * cp, 8) < 8 * kNumSMs ? ceil_div(2 * cp, 8) : 8 * kNumSMs, 256, 0, stream>>>(pl);
   return check_launch();
 }
 
@@ -1591,7 +1391,7 @@ int64_t gcn_layer_fwd_pair_workspace_bytes(int n_copies, int n_tiles, int n_task
 int row_absmax(const float* x, int ld, int n_rows, int f, float* out, cudaStream_t stream) {
   if (n_rows == 0) return GMETA_OK;
   const int grid = ceil_div(n_rows, 8) < 16 * kNumSMs ? ceil_div(n_rows, 8) : 16 * kNumSMs;
-  row_absmax_kernel<<<grid, 256, 0, stream>>>(x, ld, n_rows, f, out);
+  launch_pdl(row_absmax_kernel, dim3(grid), dim3(256), 0, stream, x, ld, n_rows, f, out);
   return check_launch();
 }
 
@@ -1615,18 +1415,10 @@ int gcn_layer_fwd_pair(const GatherSrc& g, const int32_t* tile_row0, const int32
     plan = ws.plan;
   }
   const Plan pl = carve_plan(const_cast<void*>(plan), n_tiles, n_tasks, n_rows, n_edges);
-  // f_in = 256: the hub rows are summed inside the layer kernel by its producer warps, overlapped with the
-  // expansion epilogue of the previous tile (debug flag 128: the separate pre-pass launch instead); their scale
-  // bounds ride along with the weight split
-  const bool fused = K == 256 && (g_pair_dbg & 256) && !(g_pair_dbg & 128);
-  HubBoundArgs hb;
-  hb.n_copies = n_copies;
-  hb.hdr = pl.hdr; hb.hub_beg = pl.hub_beg; hb.hub_deg = pl.hub_deg; hb.hub_src = pl.hub_src; hb.hub_nrm = pl.hub_nrm;
-  hb.hub_new = pl.hub_new; hb.in_rowmax = in_rowmax; hb.mlong_bound = ws.mlong_bound;
-  pack_w_pair_kernel<<<n_copies + (fused ? kNumSMs : 0), 1024, 0, stream>>>(W, w_task_stride, ldw, trans_w, K, N, ws.w_image,
-                                                                            2LL * K * N, ws.w_inv_scale, hb);
+  launch_pdl(pack_w_pair_kernel, dim3(n_copies), dim3(1024), 0, stream, W, w_task_stride, ldw, trans_w, K, N, ws.w_image,
+             2LL * K * N, ws.w_inv_scale);
   if ((rc = check_launch()) != GMETA_OK) return rc;
-  if (!fused && !(g_pair_dbg & 16)) {     // hub rows first (debug flag 16: skip, results are wrong)
+  if (!(g_pair_dbg & 16)) {     // hub rows first (debug flag 16: skip, results are wrong)
     if (K == 256) rc = hub_prepass_launch<8>(g.in, g.ld_in, in_rowmax, pl, ws.mlong, ws.mlong_bound, stream);
     else if (K == 128) rc = hub_prepass_launch<4>(g.in, g.ld_in, in_rowmax, pl, ws.mlong, ws.mlong_bound, stream);
     else rc = hub_prepass_launch<2>(g.in, g.ld_in, in_rowmax, pl, ws.mlong, ws.mlong_bound, stream);
@@ -1635,7 +1427,6 @@ int gcn_layer_fwd_pair(const GatherSrc& g, const int32_t* tile_row0, const int32
   PairParams p;
   p.in = g.in; p.ld_in = g.ld_in; p.f_in = K; p.in_rowmax = in_rowmax;
   p.mlong = ws.mlong; p.mlong_bound = ws.mlong_bound;
-  p.h8_src = pl.h8_src; p.h8_nrm = pl.h8_nrm; p.fused = fused ? 1 : 0;
   p.srec = pl.srec; p.row_slot = pl.row_slot; p.hdr = pl.hdr; p.pairs = pl.pairs; p.cl_beg = pl.cl_beg;
   p.dst_rows = g.dst_rows; p.norm = g.norm;
   p.w_image = ws.w_image; p.image_task_stride = n_copies > 1 ? 2LL * K * N : 0; p.w_inv_scale = ws.w_inv_scale;
@@ -1648,8 +1439,7 @@ int gcn_layer_fwd_pair(const GatherSrc& g, const int32_t* tile_row0, const int32
   const size_t smem = (size_t)p.w_bytes + (size_t)p.n_stages * STAGE_BYTES + SMEM_FIXED;
   static int n_clusters = -1;
   if (n_clusters < 0) {
-    if (cudaFuncSetAttribute(gcn_layer_fwd_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX) != cudaSuccess ||
-        cudaFuncSetAttribute(gcn_layer_fwd_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX) != cudaSuccess)
+    if (cudaFuncSetAttribute(gcn_layer_fwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX) != cudaSuccess)
       return GMETA_ERR_LAUNCH;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(kNumSMs); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_MAX;
@@ -1658,7 +1448,7 @@ int gcn_layer_fwd_pair(const GatherSrc& g, const int32_t* tile_row0, const int32
     at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
     cfg.attrs = &at; cfg.numAttrs = 1;
     int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, gcn_layer_fwd_pair_kernel<true>, &cfg) != cudaSuccess || nc < 1) {
+    if (cudaOccupancyMaxActiveClusters(&nc, gcn_layer_fwd_pair_kernel, &cfg) != cudaSuccess || nc < 1) {
       cudaGetLastError();
       return GMETA_ERR_UNSUPPORTED;
     }
@@ -1666,17 +1456,12 @@ int gcn_layer_fwd_pair(const GatherSrc& g, const int32_t* tile_row0, const int32
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * n_clusters); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-  cudaLaunchAttribute at[2];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // see pdl_wait in the kernel
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  const cudaError_t le = fused ? cudaLaunchKernelEx(&cfg, gcn_layer_fwd_pair_kernel<true>, p)
-                               : cudaLaunchKernelEx(&cfg, gcn_layer_fwd_pair_kernel<false>, p);
-  if (le != cudaSuccess) {
-    cudaGetLastError();
-    return GMETA_ERR_LAUNCH;
-  }
-  return GMETA_OK;
+  cudaLaunchAttribute at;
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;     // see pdl_wait in the kernel
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, gcn_layer_fwd_pair_kernel, p);
+  return check_launch();
 }
 
 }  // namespace gmeta

@@ -53,6 +53,7 @@ __device__ __forceinline__ float load_w(const float* W, int ldw, int trans, int 
 
 template <bool VEC>
 __global__ void __launch_bounds__(NTHREADS, 2) gcn_layer_fwd_simt_kernel(const FwdParams p) {
+  pdl_prologue();     // programmatic dependent launch: see common.cuh
   extern __shared__ __align__(16) float smem[];
   float* As = smem;                // [TM][LDA]   aggregated rows, one K panel
   float* Bs = smem + TM * LDA;     // [2][KC][LDB] weight chunk, double buffered
@@ -201,6 +202,7 @@ struct WgradParams {
 
 template <bool VEC>
 __global__ void __launch_bounds__(NTHREADS, 2) gcn_layer_wgrad_simt_kernel(const WgradParams p) {
+  pdl_prologue();     // programmatic dependent launch: see common.cuh
   extern __shared__ __align__(16) float smem[];
   float* As = smem;                  // [32][LDA]  norm[v] * M[v, kblock]
   float* Bs = smem + WG_ROWS * LDA;  // [32][LDA]  dZ[v, jblock]
@@ -301,6 +303,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gcn_layer_wgrad_simt_kernel(const
 __global__ void wgrad_reduce_kernel(const float* part_w, const float* part_b, int n_tasks,
                                     int n_split, int n_w, int f_out, float* dW,
                                     long long dw_stride, float* db, long long db_stride) {
+  pdl_prologue();     // programmatic dependent launch: see common.cuh
   const long long total = (long long)n_tasks * (n_w + f_out);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -321,6 +324,7 @@ __global__ void wgrad_reduce_kernel(const float* part_w, const float* part_b, in
 }
 
 __global__ void degree_norm_kernel(const int32_t* indptr, int n, float* norm) {
+  pdl_prologue();     // programmatic dependent launch: see common.cuh
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
     const int d = max(indptr[v + 1] - indptr[v], 1);
     norm[v] = __fdiv_rn(1.0f, __fsqrt_rn((float)d));  // == torch CPU pow(x, -0.5) -> rsqrt path
@@ -359,9 +363,9 @@ int gcn_layer_fwd_simt(const GatherSrc& g, const int32_t* tile_row0, const int32
     attr_done = true;
   }
   if (vec_in)
-    gcn_layer_fwd_simt_kernel<true><<<grid, NTHREADS, kFwdSmem, stream>>>(p);
+    launch_pdl(gcn_layer_fwd_simt_kernel<true>, dim3(grid), dim3(NTHREADS), kFwdSmem, stream, p);
   else
-    gcn_layer_fwd_simt_kernel<false><<<grid, NTHREADS, kFwdSmem, stream>>>(p);
+    launch_pdl(gcn_layer_fwd_simt_kernel<false>, dim3(grid), dim3(NTHREADS), kFwdSmem, stream, p);
   return check_launch();
 }
 
@@ -438,6 +442,7 @@ template <bool VEC>
 __global__ void __launch_bounds__(256) aggregate_rows_kernel(GatherSrc g, int n_rows, int scale_dst,
                                                              float* __restrict__ out, int ld_out,
                                                              const int32_t* __restrict__ pos_ptr) {
+  pdl_prologue();     // programmatic dependent launch: see common.cuh
   __shared__ int long_rows[8];
   __shared__ int n_long;
   __shared__ float4 part[8][32];
@@ -488,6 +493,7 @@ __global__ void __launch_bounds__(256) aggregate_rows_kernel(GatherSrc g, int n_
 }
 
 __global__ void identity_graph_kernel(int32_t* __restrict__ iota, float* __restrict__ ones, int n) {
+  pdl_prologue();     // programmatic dependent launch: see common.cuh
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += gridDim.x * blockDim.x) {
     iota[i] = i;
     if (i < n) ones[i] = 1.f;
@@ -500,7 +506,7 @@ __global__ void identity_graph_kernel(int32_t* __restrict__ iota, float* __restr
 int fill_identity_graph(int32_t* iota, float* ones, int n, cudaStream_t stream) {
   if (n < 0) return GMETA_ERR_BAD_ARG;
   const int grid = ceil_div(n + 1, 256) < 4 * kNumSMs ? ceil_div(n + 1, 256) : 4 * kNumSMs;
-  identity_graph_kernel<<<grid, 256, 0, stream>>>(iota, ones, n);
+  launch_pdl(identity_graph_kernel, dim3(grid), dim3(256), 0, stream, iota, ones, n);
   return check_launch();
 }
 }  // namespace gmeta
@@ -520,9 +526,9 @@ int aggregate_rows_impl(const float* in, int32_t ld_in, const int32_t* in_row_ma
   g.ld_in = ld_in; g.f_in = f_in;
   const int grid = ceil_div(n_rows, 8) < 16 * kNumSMs ? ceil_div(n_rows, 8) : 16 * kNumSMs;
   if (ld_in % 4 == 0 && f_in % 4 == 0 && aligned16(in))
-    aggregate_rows_kernel<true><<<grid, 256, 0, stream>>>(g, n_rows, scale_dst, out, ld_out, pos_indptr);
+    launch_pdl(aggregate_rows_kernel<true>, dim3(grid), dim3(256), 0, stream, g, n_rows, scale_dst, out, ld_out, pos_indptr);
   else
-    aggregate_rows_kernel<false><<<grid, 256, 0, stream>>>(g, n_rows, scale_dst, out, ld_out, pos_indptr);
+    launch_pdl(aggregate_rows_kernel<false>, dim3(grid), dim3(256), 0, stream, g, n_rows, scale_dst, out, ld_out, pos_indptr);
   return check_launch();
 }
 
@@ -533,6 +539,7 @@ __global__ void active_out_kernel(const int32_t* __restrict__ rows, int n_rows, 
                                   const int32_t* __restrict__ t_indices, const int32_t* __restrict__ keep, int fill,
                                   int32_t* __restrict__ count, const int32_t* __restrict__ ptr,
                                   int32_t* __restrict__ out_idx) {
+  pdl_prologue();     // programmatic dependent launch: see common.cuh
   const int lane = threadIdx.x & 31;
   for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_rows; i += (gridDim.x * blockDim.x) >> 5) {
     const int u = rows[i];
@@ -562,6 +569,7 @@ __global__ void active_out_kernel(const int32_t* __restrict__ rows, int n_rows, 
 
 // exclusive prefix sum of a[0..n) into out[0..n], out[n] = total; one CTA
 __global__ void __launch_bounds__(1024) excl_scan_kernel(const int32_t* __restrict__ a, int n, int32_t* __restrict__ out) {
+  pdl_prologue();     // programmatic dependent launch: see common.cuh
   __shared__ int sh[1024];
   int carry = 0;
   for (int base = 0; base < n; base += 1024) {
@@ -592,12 +600,12 @@ int active_out_lists_build(const int32_t* rows, int n_rows, const int32_t* t_ind
                            const int32_t* keep, int32_t* count, int32_t* ptr, int32_t* out_idx, cudaStream_t stream) {
   if (n_rows == 0) return GMETA_OK;
   const int grid = ceil_div(n_rows, 8) < 8 * kNumSMs ? ceil_div(n_rows, 8) : 8 * kNumSMs;
-  active_out_kernel<<<grid, 256, 0, stream>>>(rows, n_rows, t_indptr, t_indices, keep, 0, count, nullptr, nullptr);
+  launch_pdl(active_out_kernel, dim3(grid), dim3(256), 0, stream, rows, n_rows, t_indptr, t_indices, keep, 0, count, nullptr, nullptr);
   int rc = check_launch();
   if (rc != GMETA_OK) return rc;
-  excl_scan_kernel<<<1, 1024, 0, stream>>>(count, n_rows, ptr);
+  launch_pdl(excl_scan_kernel, dim3(1), dim3(1024), 0, stream, count, n_rows, ptr);
   if ((rc = check_launch()) != GMETA_OK) return rc;
-  active_out_kernel<<<grid, 256, 0, stream>>>(rows, n_rows, t_indptr, t_indices, keep, 1, nullptr, ptr, out_idx);
+  launch_pdl(active_out_kernel, dim3(grid), dim3(256), 0, stream, rows, n_rows, t_indptr, t_indices, keep, 1, nullptr, ptr, out_idx);
   return check_launch();
 }
 }  // namespace gmeta
@@ -614,7 +622,7 @@ extern "C" int gmeta_degree_norm(const int32_t* indptr, int32_t n_nodes, float* 
   if (n_nodes < 0 || (n_nodes > 0 && (!indptr || !norm))) return GMETA_ERR_BAD_ARG;
   if (n_nodes == 0) return GMETA_OK;
   const int grid = ceil_div(n_nodes, 256) < 8 * kNumSMs ? ceil_div(n_nodes, 256) : 8 * kNumSMs;
-  degree_norm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(indptr, n_nodes, norm);
+  launch_pdl(degree_norm_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, indptr, n_nodes, norm);
   return check_launch();
 }
 
@@ -669,14 +677,14 @@ int gcn_layer_wgrad_impl(const float* in, int32_t ld_in, const int32_t* in_row_m
     attr_done = true;
   }
   if (vec_in)
-    gcn_layer_wgrad_simt_kernel<true><<<n_work, NTHREADS, kWgSmem, s>>>(p);
+    launch_pdl(gcn_layer_wgrad_simt_kernel<true>, dim3(n_work), dim3(NTHREADS), kWgSmem, s, p);
   else
-    gcn_layer_wgrad_simt_kernel<false><<<n_work, NTHREADS, kWgSmem, s>>>(p);
+    launch_pdl(gcn_layer_wgrad_simt_kernel<false>, dim3(n_work), dim3(NTHREADS), kWgSmem, s, p);
   int rc = check_launch();
   if (rc != GMETA_OK || p.n_split == 1) return rc;
   const long long total = (long long)n_tasks * (n_w + f_out);
   const int grid = (int)((total + 255) / 256 < 8 * kNumSMs ? (total + 255) / 256 : 8 * kNumSMs);
-  wgrad_reduce_kernel<<<grid, 256, 0, s>>>(p.part_w, p.part_b, n_tasks, p.n_split, n_w, f_out, dW,
+  launch_pdl(wgrad_reduce_kernel, dim3(grid), dim3(256), 0, s, p.part_w, p.part_b, n_tasks, p.n_split, n_w, f_out, dW,
                                           dw_task_stride, db, db_task_stride);
   return check_launch();
 }

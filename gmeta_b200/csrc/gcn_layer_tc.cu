@@ -184,6 +184,7 @@ struct Smem {
 };
 
 __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const TcParams p) {
+  pdl_launch_dependents();     // programmatic dependent launch (common.cuh); the wait follows the set-up below
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = p.f_out;
@@ -225,6 +226,7 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();       // barriers and tensor memory were set up under the tail of the kernel before this one
 
   if (warp < N_PROD_WARPS) {
     // ===================== gather producers =====================
@@ -614,6 +616,7 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const 
 // raw fp32 weights (either orientation) -> per-copy UMMA image [K/32][hi|lo][N][32, swizzled]
 __global__ void pack_w_umma_kernel(const float* __restrict__ W, long long w_stride, int ldw, int trans, int K,
                                    int N, int n_copies, float* __restrict__ image, long long image_stride) {
+  pdl_prologue();     // programmatic dependent launch: see common.cuh
   const long long total = (long long)n_copies * (K / KCH) * N * 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -645,6 +648,7 @@ __global__ void pack_w_umma_kernel(const float* __restrict__ W, long long w_stri
 __global__ void sgd_pack_kernel(const float* __restrict__ w_in, long long w_in_stride, const float* __restrict__ grad,
                                 float lr, int n_copies, int n_params, float* __restrict__ w_out, const TcPackPlan plan,
                                 float* __restrict__ image, long long n_update, long long n_units) {
+  pdl_prologue();     // programmatic dependent launch: see common.cuh
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_update + n_units; i += stride) {
     if (i < n_update) {
@@ -741,7 +745,7 @@ int gcn_layer_fwd_tc(const GatherSrc& g, const int32_t* tile_row0, const int32_t
   if (!prepacked) {
     const long long total = (long long)n_copies * (K / KCH) * N * 8;
     const int grid = (int)((total + 255) / 256 < 8 * kNumSMs ? (total + 255) / 256 : 8 * kNumSMs);
-    pack_w_umma_kernel<<<grid, 256, 0, stream>>>(W, w_task_stride, ldw, trans_w, K, N, n_copies,
+    launch_pdl(pack_w_umma_kernel, dim3(grid), dim3(256), 0, stream, W, w_task_stride, ldw, trans_w, K, N, n_copies,
                                                  reinterpret_cast<float*>(workspace), image_stride);
     int rc = check_launch();
     if (rc != GMETA_OK) return rc;
@@ -767,7 +771,7 @@ int gcn_layer_fwd_tc(const GatherSrc& g, const int32_t* tile_row0, const int32_t
   p.st_tiles = n_tiles >= 2 * ST_TILES * kNumSMs ? ST_TILES : (n_tiles >= 2 * kNumSMs ? 2 : 1);
   const int n_super = (n_tiles + p.st_tiles - 1) / p.st_tiles;
   const int grid = n_super < kNumSMs ? n_super : kNumSMs;
-  gcn_layer_fwd_tc_kernel<<<grid, NTHREADS_TC, smem, stream>>>(p);
+  launch_pdl(gcn_layer_fwd_tc_kernel, dim3(grid), dim3(NTHREADS_TC), smem, stream, p);
   return check_launch();
 }
 
@@ -781,7 +785,7 @@ int gcn_tc_sgd_pack(const float* w_in, int64_t w_in_stride, const float* grad, f
   if (n_update + n_units == 0) return GMETA_OK;
   const long long blocks = (n_update + n_units + 255) / 256;
   const int grid = (int)(blocks < 16 * kNumSMs ? blocks : 16 * kNumSMs);
-  sgd_pack_kernel<<<grid, 256, 0, stream>>>(w_in, w_in_stride, grad, lr, n_copies, n_params, w_out, plan, image,
+  launch_pdl(sgd_pack_kernel, dim3(grid), dim3(256), 0, stream, w_in, w_in_stride, grad, lr, n_copies, n_params, w_out, plan, image,
                                             n_update, n_units);
   return check_launch();
 }

@@ -42,11 +42,14 @@ extern "C" int gmeta_host_pack_csr(int32_t n_tasks, const int32_t* const* indptr
                                    const int64_t* node_off, const int64_t* edge_off, int32_t* out_indptr,
                                    int32_t* out_indices, int32_t* out_t_indptr, int32_t* out_t_indices,
                                    int32_t n_threads) {
-  if (n_tasks < 0 || !node_off || !edge_off || !out_indptr || !out_t_indptr) return GMETA_ERR_BAD_ARG;
-  if (n_tasks > 0 && (!indptr || !indices || !t_indptr || !t_indices)) return GMETA_ERR_BAD_ARG;
+  // the by-source arrays are optional (all four of t_indptr / t_indices / out_t_indptr / out_t_indices NULL): the
+  // caller derives them on the device instead (gmeta_packed_set_finish)
+  const bool with_t = t_indptr || t_indices || out_t_indptr || out_t_indices;
+  if (n_tasks < 0 || !node_off || !edge_off || !out_indptr || (with_t && !out_t_indptr)) return GMETA_ERR_BAD_ARG;
+  if (n_tasks > 0 && (!indptr || !indices || (with_t && (!t_indptr || !t_indices)))) return GMETA_ERR_BAD_ARG;
   if (node_off[n_tasks] > 0x7fffffffLL || edge_off[n_tasks] > 0x7fffffffLL) return GMETA_ERR_UNSUPPORTED;
   out_indptr[0] = 0;
-  out_t_indptr[0] = 0;
+  if (with_t) out_t_indptr[0] = 0;
   std::atomic<int> next(0);
   const int n_units = 4 * n_tasks;      // (task, array) units, handed out dynamically
   auto work = [&]() {
@@ -55,9 +58,9 @@ extern "C" int gmeta_host_pack_csr(int32_t n_tasks, const int32_t* const* indptr
       const int64_t a = node_off[t], n = node_off[t + 1] - a, ea = edge_off[t], e = edge_off[t + 1] - ea;
       switch (u & 3) {
         case 0: add_copy(out_indptr + a + 1, indptr[t] + 1, n, (int32_t)ea); break;
-        case 1: add_copy(out_t_indptr + a + 1, t_indptr[t] + 1, n, (int32_t)ea); break;
+        case 1: if (with_t) add_copy(out_t_indptr + a + 1, t_indptr[t] + 1, n, (int32_t)ea); break;
         case 2: if (e) add_copy(out_indices + ea, indices[t], e, (int32_t)a); break;
-        default: if (e) add_copy(out_t_indices + ea, t_indices[t], e, (int32_t)a); break;
+        default: if (with_t && e) add_copy(out_t_indices + ea, t_indices[t], e, (int32_t)a); break;
       }
     }
 #if defined(__SSE2__)

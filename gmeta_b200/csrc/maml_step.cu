@@ -245,6 +245,7 @@ thread_local EventPool g_events;
 
 __global__ void step_stats_kernel(const float* __restrict__ loss_q, const float* __restrict__ acc_q, int n_tasks,
                                   int n_cols, float* __restrict__ out) {
+  pdl_prologue();     // programmatic dependent launch: see common.cuh
   // out[0] = sum_t loss_q[t][K], out[1 + k] = sum_t acc_q[t][k]; tasks added in index order (deterministic)
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k > n_cols) return;
@@ -568,7 +569,7 @@ extern "C" int gmeta_maml_step(const gmeta_step_args_t* a_in, void* stream) {
     wait(1 + K + (K - 1), s);                   // join: every query forward has finished
   }
   if (a->step_stats && r.ok()) {
-    step_stats_kernel<<<1, 64, 0, s>>>(a->loss_q, a->acc_q, T, K + 1, a->step_stats);
+    launch_pdl(step_stats_kernel, dim3(1), dim3(64), 0, s, a->loss_q, a->acc_q, T, K + 1, a->step_stats);
     r.run(check_launch());
   }
   return r.rc;

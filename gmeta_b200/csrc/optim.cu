@@ -11,6 +11,7 @@ namespace {
 __global__ void sgd_update_kernel(const float* __restrict__ w_in, long long w_in_stride,
                                   const float* __restrict__ grad, float lr, int n_tasks, int n_params,
                                   float* __restrict__ w_out) {
+  pdl_prologue();     // programmatic dependent launch: see common.cuh
   const long long total = (long long)n_tasks * n_params;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -23,6 +24,7 @@ __global__ void sgd_update_kernel(const float* __restrict__ w_in, long long w_in
 
 __global__ void sum_over_tasks_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                       int n_tasks, int n_params, float* __restrict__ out) {
+  pdl_prologue();     // programmatic dependent launch: see common.cuh
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_params; p += gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int t = 0; t < n_tasks; ++t) {
@@ -38,6 +40,7 @@ __global__ void adam_update_kernel(float* __restrict__ param, const float* __res
                                    int n_params, float step_size, float one_minus_beta1, float beta2,
                                    float one_minus_beta2, float eps, float bias_c2_sqrt, float grad_scale,
                                    const float* __restrict__ loss_gate, int32_t* __restrict__ skipped) {
+  pdl_prologue();     // programmatic dependent launch: see common.cuh
   const bool skip = loss_gate != nullptr && isnan(*loss_gate);
   if (skipped && blockIdx.x == 0 && threadIdx.x == 0) *skipped = skip ? 1 : 0;
   if (skip) return;
@@ -59,6 +62,7 @@ __global__ void adam_update_kernel(float* __restrict__ param, const float* __res
 __global__ void adam_prepare_kernel(int32_t* __restrict__ state, double lr, double beta1, double beta2,
                                     const float* __restrict__ loss_sum, float loss_scale,
                                     const float* __restrict__ acc_sums, int n_acc, float* __restrict__ step_out) {
+  pdl_prologue();     // programmatic dependent launch: see common.cuh
   const float gate = loss_sum ? *loss_sum * loss_scale : 0.f;      // meta.py:161: losses_q[-1] / task_num
   const bool skip = isnan(gate);                                    // meta.py:163-164
   if (threadIdx.x == 0) {
@@ -86,6 +90,7 @@ __global__ void adam_apply_kernel(float* __restrict__ param, const float* __rest
                                   float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, int n_params,
                                   float one_minus_beta1, float beta2, float one_minus_beta2, float eps, float grad_scale,
                                   const int32_t* __restrict__ state) {
+  pdl_prologue();     // programmatic dependent launch: see common.cuh
   if (state[1]) return;
   const float step_size = __int_as_float(state[2]), bias_c2_sqrt = __int_as_float(state[3]);
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_params; p += gridDim.x * blockDim.x) {
@@ -109,12 +114,12 @@ extern "C" int gmeta_adam_step(float* param, const float* grad, float* exp_avg, 
                                const float* loss_sum, float loss_scale, const float* acc_sums, int32_t n_acc,
                                float* step_out, void* stream) {
   if (!param || !grad || !exp_avg || !exp_avg_sq || !state || n_params <= 0 || n_acc < 0) return GMETA_ERR_BAD_ARG;
-  adam_prepare_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(state, lr, beta1, beta2, loss_sum, loss_scale, acc_sums,
+  launch_pdl(adam_prepare_kernel, dim3(1), dim3(64), 0, (cudaStream_t)stream, state, lr, beta1, beta2, loss_sum, loss_scale, acc_sums,
                                                         n_acc, step_out);
   int rc = check_launch();
   if (rc != GMETA_OK) return rc;
   const int grid = ceil_div(n_params, 256) < 8 * kNumSMs ? ceil_div(n_params, 256) : 8 * kNumSMs;
-  adam_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n_params,
+  launch_pdl(adam_apply_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n_params,
                                                            (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
                                                            (float)eps, grad_scale, state);
   return check_launch();
@@ -125,7 +130,7 @@ extern "C" int gmeta_sgd_update(const float* w_in, int64_t w_in_task_stride, con
   if (!w_in || !grad || !w_out || n_tasks <= 0 || n_params <= 0) return GMETA_ERR_BAD_ARG;
   const long long total = (long long)n_tasks * n_params;
   const int grid = (int)((total + 255) / 256 < 8 * kNumSMs ? (total + 255) / 256 : 8 * kNumSMs);
-  sgd_update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w_in, w_in_task_stride, grad, lr, n_tasks,
+  launch_pdl(sgd_update_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, w_in, w_in_task_stride, grad, lr, n_tasks,
                                                            n_params, w_out);
   return check_launch();
 }
@@ -134,7 +139,7 @@ extern "C" int gmeta_sum_over_tasks(const float* a, const float* b, int32_t n_ta
                                     float* out, void* stream) {
   if (!a || !out || n_tasks <= 0 || n_params <= 0) return GMETA_ERR_BAD_ARG;
   const int grid = ceil_div(n_params, 256) < 8 * kNumSMs ? ceil_div(n_params, 256) : 8 * kNumSMs;
-  sum_over_tasks_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, n_tasks, n_params, out);
+  launch_pdl(sum_over_tasks_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, a, b, n_tasks, n_params, out);
   return check_launch();
 }
 
@@ -148,7 +153,7 @@ extern "C" int gmeta_adam_update(float* param, const float* grad, float* exp_avg
   const double bias_c2 = 1.0 - pow(beta2, (double)step);
   const float step_size = (float)(lr / bias_c1);
   const int grid = ceil_div(n_params, 256) < 8 * kNumSMs ? ceil_div(n_params, 256) : 8 * kNumSMs;
-  adam_update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n_params,
+  launch_pdl(adam_update_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n_params,
                                                             step_size, (float)(1.0 - beta1), (float)beta2,
                                                             (float)(1.0 - beta2), (float)eps,
                                                             (float)sqrt(bias_c2), grad_scale, loss_gate,

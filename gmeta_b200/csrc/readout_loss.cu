@@ -31,6 +31,7 @@ __global__ void readout_linear_fwd_kernel(const float* __restrict__ H, int ld_h,
                                           const float* __restrict__ Wlin, long long w_stride,
                                           const float* __restrict__ blin, long long b_stride,
                                           int n_out, float* __restrict__ logits) {
+  pdl_prologue();     // programmatic dependent launch: see common.cuh
   extern __shared__ float r[];  // [cps * hid]
   const int s = blockIdx.x;
   const int t = find_task(task_sub_ptr, n_tasks, s);
@@ -61,6 +62,7 @@ __global__ void readout_linear_bwd_kernel(const float* __restrict__ H, int ld_h,
                                           float* __restrict__ dWlin, long long dw_stride,
                                           float* __restrict__ dblin, long long db_stride,
                                           const int32_t* __restrict__ row_pos, float* __restrict__ dZ) {
+  pdl_prologue();     // programmatic dependent launch: see common.cuh
   const int t = blockIdx.x;
   const int s0 = task_sub_ptr[t], s1 = task_sub_ptr[t + 1];
   const int width = cps * hid;
@@ -103,6 +105,7 @@ __global__ void proto_label_prep_kernel(const int32_t* __restrict__ labels,
                                         int32_t* __restrict__ class_pos,
                                         int32_t* __restrict__ class_occ,
                                         int32_t* __restrict__ n_classes) {
+  pdl_prologue();     // programmatic dependent launch: see common.cuh
   const int t = blockIdx.x;
   const int s0 = task_sub_ptr[t], n = task_sub_ptr[t + 1] - s0;
   int my_first_count = 0;
@@ -178,6 +181,7 @@ __global__ void proto_loss_kernel(const float* __restrict__ logits, int D,
                                   float* __restrict__ protos_io, float* __restrict__ loss,
                                   float* __restrict__ acc, int out_stride,
                                   float* __restrict__ dlogits, float* __restrict__ dprotos) {
+  pdl_prologue();     // programmatic dependent launch: see common.cuh
   extern __shared__ float sm[];
   const int t = blockIdx.x;
   const int s0 = task_sub_ptr[t], n = task_sub_ptr[t + 1] - s0;
@@ -265,6 +269,7 @@ __global__ void proto_grad_to_support_kernel(const float* __restrict__ dprotos, 
                                              const int32_t* __restrict__ class_pos,
                                              const int32_t* __restrict__ class_occ, int n_support,
                                              int n_sub, float* __restrict__ dlogits) {
+  pdl_prologue();     // programmatic dependent launch: see common.cuh
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_sub * D; i += gridDim.x * blockDim.x) {
     const int s = i / D, k = i - s * D;
     const int t = find_task(task_sub_ptr, n_tasks, s);
@@ -296,7 +301,7 @@ extern "C" int gmeta_readout_linear_fwd(const float* H, int32_t ld_h, int32_t hi
   if (n_subgraphs == 0) return GMETA_OK;
   const size_t smem = (size_t)cps * hid * sizeof(float);
   if (smem > 48 * 1024) return GMETA_ERR_UNSUPPORTED;
-  readout_linear_fwd_kernel<<<n_subgraphs, 128, smem, (cudaStream_t)stream>>>(
+  launch_pdl(readout_linear_fwd_kernel, dim3(n_subgraphs), dim3(128), smem, (cudaStream_t)stream, 
       H, ld_h, hid, centre_row, cps, task_sub_ptr, n_tasks, Wlin, w_task_stride, blin, b_task_stride,
       n_out, logits);
   return check_launch();
@@ -315,7 +320,7 @@ extern "C" int gmeta_readout_linear_bwd(const float* H, int32_t ld_h, int32_t hi
     return GMETA_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   if (cudaMemsetAsync(dZ, 0, (size_t)n_dz_rows * ld_h * sizeof(float), s) != cudaSuccess) return GMETA_ERR_LAUNCH;
-  readout_linear_bwd_kernel<<<dim3(n_tasks, 2), 256, 0, s>>>(H, ld_h, hid, centre_row, cps, task_sub_ptr,
+  launch_pdl(readout_linear_bwd_kernel, dim3(dim3(n_tasks, 2)), dim3(256), 0, s, H, ld_h, hid, centre_row, cps, task_sub_ptr,
                                                             Wlin, w_task_stride, n_out, dlogits, dWlin,
                                                             dw_task_stride, dblin, db_task_stride, row_pos, dZ);
   return check_launch();
@@ -324,6 +329,7 @@ extern "C" int gmeta_readout_linear_bwd(const float* H, int32_t ld_h, int32_t hi
 namespace gmeta {
 namespace {
 __global__ void scatter_row_pos_kernel(const int32_t* __restrict__ rows, int n_rows, int32_t* __restrict__ row_pos) {
+  pdl_prologue();     // programmatic dependent launch: see common.cuh
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += gridDim.x * blockDim.x) row_pos[rows[i]] = i;
 }
 }  // namespace
@@ -336,7 +342,7 @@ extern "C" int gmeta_build_row_pos(const int32_t* rows, int32_t n_rows, int32_t 
   if (n_nodes == 0) return GMETA_OK;
   if (cudaMemsetAsync(row_pos, 0xFF, (size_t)n_nodes * sizeof(int32_t), s) != cudaSuccess) return GMETA_ERR_LAUNCH;
   if (n_rows == 0) return GMETA_OK;
-  scatter_row_pos_kernel<<<ceil_div(n_rows, 256), 256, 0, s>>>(rows, n_rows, row_pos);
+  launch_pdl(scatter_row_pos_kernel, dim3(ceil_div(n_rows, 256)), dim3(256), 0, s, rows, n_rows, row_pos);
   return check_launch();
 }
 
@@ -345,7 +351,7 @@ extern "C" int gmeta_proto_label_prep(const int32_t* labels, const int32_t* task
                                       void* stream) {
   if (!labels || !task_sub_ptr || !class_pos || !class_occ || !n_classes || n_tasks <= 0)
     return GMETA_ERR_BAD_ARG;
-  proto_label_prep_kernel<<<n_tasks, 128, 0, (cudaStream_t)stream>>>(labels, task_sub_ptr, class_pos,
+  launch_pdl(proto_label_prep_kernel, dim3(n_tasks), dim3(128), 0, (cudaStream_t)stream, labels, task_sub_ptr, class_pos,
                                                                    class_occ, n_classes);
   return check_launch();
 }
@@ -367,11 +373,11 @@ static int launch_proto(bool spt, const float* logits, int n_out, const int32_t*
     attr_done = true;
   }
   if (spt)
-    proto_loss_kernel<true><<<n_tasks, 128, smem, s>>>(logits, n_out, task_sub_ptr, class_pos, class_occ,
+    launch_pdl(proto_loss_kernel<true>, dim3(n_tasks), dim3(128), smem, s, logits, n_out, task_sub_ptr, class_pos, class_occ,
                                                       n_classes, n_support, max_classes, grad_scale,
                                                       protos, loss, acc, out_stride, dlogits, dprotos);
   else
-    proto_loss_kernel<false><<<n_tasks, 128, smem, s>>>(logits, n_out, task_sub_ptr, class_pos, class_occ,
+    launch_pdl(proto_loss_kernel<false>, dim3(n_tasks), dim3(128), smem, s, logits, n_out, task_sub_ptr, class_pos, class_occ,
                                                        n_classes, n_support, max_classes, grad_scale,
                                                        protos, loss, acc, out_stride, dlogits, dprotos);
   return check_launch();
@@ -427,7 +433,7 @@ extern "C" int gmeta_proto_grad_to_support(const float* dprotos, int32_t n_out, 
     return GMETA_ERR_BAD_ARG;
   if (n_subgraphs == 0) return GMETA_OK;
   const int total = n_subgraphs * n_out;
-  proto_grad_to_support_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(proto_grad_to_support_kernel, dim3(ceil_div(total, 256)), dim3(256), 0, (cudaStream_t)stream, 
       dprotos, n_out, max_classes, task_sub_ptr, n_tasks, class_pos, class_occ, n_support, n_subgraphs,
       dlogits_spt);
   return check_launch();

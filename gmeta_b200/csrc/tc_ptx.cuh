@@ -21,12 +21,6 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// Programmatic dependent launch (stream order kept, launch latency and prologues overlapped): a kernel launched with
-// the programmatic-serialization attribute may start once every CTA of the kernel before it has executed
-// launch_dependents (or exited); it must execute wait before touching anything the earlier kernel writes -- wait
-// returns when that kernel has completed and its writes are visible.  Both are no-ops in a plain launch.
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }

@@ -228,15 +228,22 @@ def _act_capacity(ps, n_layers):
     return n_layers * per_layer
 
 
-def _fill_base(buf, ps, graphs, labels, centres, node_ids, graph_idx, graph_row_off, lib, n_threads):
+def _fill_base(buf, ps, graphs, labels, centres, node_ids, graph_idx, graph_row_off, lib, n_threads, slim=False):
+    """`slim`: only what the host alone knows (CSR by destination, centres, labels, feature rows, task pointers);
+    the CSR by source and the tile tables are left to gmeta_packed_set_finish on the device."""
     import ctypes as C
     o, N, E, T = ps.off, ps.N, ps.E, ps.T
-    keep = [[_i32c(getattr(g, k)) for g in graphs] for k in ("indptr", "indices", "t_indptr", "t_indices")]
+    keep = [[_i32c(getattr(g, k)) for g in graphs] for k in (("indptr", "indices") if slim else
+                                                             ("indptr", "indices", "t_indptr", "t_indices"))]
     ptrs = [(C.c_void_p * max(T, 1))(*[a.__array_interface__['data'][0] for a in arrs]) for arrs in keep]
     base = buf.__array_interface__['data'][0]
-    rc = lib.gmeta_host_pack_csr(T, ptrs[0], ptrs[1], ptrs[2], ptrs[3], ps.node_off.ctypes.data, ps.edge_off.ctypes.data,
-                                 base + 4 * o["indptr"], base + 4 * o["indices"], base + 4 * o["t_indptr"],
-                                 base + 4 * o["t_indices"], n_threads)
+    if slim:
+        rc = lib.gmeta_host_pack_csr(T, ptrs[0], ptrs[1], None, None, ps.node_off.ctypes.data, ps.edge_off.ctypes.data,
+                                     base + 4 * o["indptr"], base + 4 * o["indices"], None, None, n_threads)
+    else:
+        rc = lib.gmeta_host_pack_csr(T, ptrs[0], ptrs[1], ptrs[2], ptrs[3], ps.node_off.ctypes.data, ps.edge_off.ctypes.data,
+                                     base + 4 * o["indptr"], base + 4 * o["indices"], base + 4 * o["t_indptr"],
+                                     base + 4 * o["t_indices"], n_threads)
     if rc != 0:
         raise RuntimeError("gmeta_host_pack_csr failed (%d)" % rc)
     bnn = [np.asarray(g.batch_num_nodes, dtype=np.int64) for g in graphs]
@@ -274,6 +281,10 @@ def _fill_base(buf, ps, graphs, labels, centres, node_ids, graph_idx, graph_row_
                                            ps.node_off.ctypes.data, base + 4 * o["feat_row"], n_threads)
     if rc != 0:
         raise RuntimeError("gmeta_host_pack_feat_rows failed (%d)" % rc)
+    if slim:
+        buf[o["task_row_ptr"]:o["task_row_ptr"] + T + 1] = ps.node_off
+        buf[o["task_sub_ptr"]:o["task_sub_ptr"] + T + 1] = ps.sub_off
+        return
     buf[o["tile_row0"]:o["tile_row0"] + ps.n_tiles] = ps.tiles[0]
     buf[o["tile_nrows"]:o["tile_nrows"] + ps.n_tiles] = ps.tiles[1]
     buf[o["tile_task"]:o["tile_task"] + ps.n_tiles] = ps.tiles[2]
@@ -350,6 +361,78 @@ def pack_meta_batch(staging, batch, graph_row_off, n_layers, lib, n_threads=0):
     return ps_s, ps_q, off
 
 
+HOST_SEGS = ("indptr", "indices", "centre_row", "feat_row", "labels", "task_sub_ptr", "task_row_ptr")
+
+
+def pack_meta_batch_slim(staging, batch, graph_row_off, n_layers, lib, n_threads=0):
+    """The host half of a meta-batch for Meta.upload_batch: only the segments the host alone knows (HOST_SEGS) are
+    packed -- they form the head of the buffer and are all that is copied to the device; every other segment (CSR by
+    source, tile tables, active rows, centre positions) is laid out behind them at its upper-bound size and filled on
+    the device by `finish_on_device`.  Same values, segment by segment, as pack_meta_batch
+    (tests/test_gpu_meta.py::test_slim_pack_equals_full_pack).  Returns (ps_spt, ps_qry, n_host_int32, n_total_int32)."""
+    x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry = batch
+    sets = [_plan_base(x_spt, c_spt), _plan_base(x_qry, c_qry)]
+    off = 0
+    for ps in sets:
+        ps.n_layers = n_layers
+        for k in HOST_SEGS:
+            ps.off[k] = off
+            off += _al(ps.sizes[k])
+    n_host = off
+    for ps in sets:                       # realised counts of both sets: adjacent, read back with one copy
+        ps.off["counts"] = off
+        off += _al(2 + 2 * n_layers)
+    for ps in sets:
+        cap_t = (ps.N + 127) // 128 + ps.T
+        ps.cap = {"t_indptr": ps.N + 1, "t_indices": ps.E, "tile_row0": cap_t, "tile_nrows": cap_t, "tile_task": cap_t,
+                  "centre_pos": ps.S * ps.cps}
+        for l in range(n_layers):
+            ps.cap["act_rows%d" % l] = ps.N
+            ps.cap["act_task_ptr%d" % l] = ps.T + 1
+            for k in ("act_tile_row0", "act_tile_nrows", "act_tile_task"):
+                ps.cap["%s%d" % (k, l)] = cap_t
+        for k, n in ps.cap.items():
+            ps.off[k] = off
+            off += _al(n)
+    buf = staging.reserve(off)
+    _fill_base(buf, sets[0], x_spt, y_spt, c_spt, n_spt, g_spt, graph_row_off, lib, n_threads, slim=True)
+    _fill_base(buf, sets[1], x_qry, y_qry, c_qry, n_qry, g_qry, graph_row_off, lib, n_threads, slim=True)
+    sets[0].end = sets[1].end = off
+    return sets[0], sets[1], n_host, off
+
+
+def finish_on_device(lib, ints, sets, n_layers, workspace, stream):
+    """Enqueue gmeta_packed_set_finish for both sets of a slim-packed batch living in the device tensor `ints`;
+    `workspace(nbytes)` returns a 256-byte aligned device pointer valid until the passes have run."""
+    import ctypes as C
+    from . import _lib
+    base = ints.data_ptr()
+    for ps in sets:
+        seg = lambda k: base + 4 * ps.off[k]                                 # noqa: E731
+        arr = lambda k: (C.c_void_p * max(n_layers, 1))(*[seg("%s%d" % (k, l)) for l in range(n_layers)])  # noqa: E731
+        nb = lib.gmeta_packed_set_finish_workspace_bytes(ps.N, ps.E, n_layers)
+        _lib.check(lib.gmeta_packed_set_finish(seg("indptr"), seg("indices"), ps.N, ps.E, seg("task_row_ptr"), None, ps.T,
+                                               seg("centre_row"), ps.S * ps.cps, n_layers, seg("t_indptr"), seg("t_indices"),
+                                               seg("task_row_ptr"), seg("tile_row0"), seg("tile_nrows"), seg("tile_task"),
+                                               arr("act_rows"), arr("act_task_ptr"), arr("act_tile_row0"),
+                                               arr("act_tile_nrows"), arr("act_tile_task"), seg("centre_pos"), seg("counts"),
+                                               workspace(nb), nb, stream), "packed_set_finish")
+
+
+def apply_counts(sets, n_layers, counts, counts_off):
+    """Realised tile / active-row counts (host copy of the counts segments starting at int32 offset `counts_off`)
+    -> the size fields of the sets."""
+    for ps in sets:
+        cnt = counts[ps.off["counts"] - counts_off:][:2 + 2 * n_layers]
+        assert int(cnt[0]) == ps.n_tiles, "tile table of the device pass disagrees with the host's"
+        ps.act = [{"n": int(cnt[2 + l]), "n_tiles": int(cnt[2 + n_layers + l])} for l in range(n_layers)]
+        for l in range(n_layers):
+            ps.sizes["act_rows%d" % l] = ps.act[l]["n"]
+            ps.sizes["act_task_ptr%d" % l] = ps.T + 1
+            for k in ("act_tile_row0", "act_tile_nrows", "act_tile_task"):
+                ps.sizes["%s%d" % (k, l)] = ps.act[l]["n_tiles"]
+
+
 class Staging(object):
     """Grow-only pinned host buffer + device buffer for the packed integer arrays.  `copied` is the CUDA event of the
     last host->device copy out of the pinned buffer: the buffer must not be rewritten (the packer uses non-temporal
@@ -369,6 +452,18 @@ class Staging(object):
             self.host = torch.empty(cap, dtype=torch.int32, pin_memory=torch.cuda.is_available())
             self.dev = torch.empty(cap, dtype=torch.int32, device=self.device)
         return self.host.numpy()
+
+    def finish_workspace(self, nbytes):
+        """256-byte aligned device scratch of the slot for gmeta_packed_set_finish (grow-only)."""
+        if getattr(self, "_fws", None) is None or self._fws.numel() < nbytes + 256:
+            self._fws = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=self.device)
+        return (self._fws.data_ptr() + 255) // 256 * 256
+
+    def counts_buffer(self, n):
+        """Pinned host landing zone for the realised counts of a batch (a few dozen ints)."""
+        if getattr(self, "_counts", None) is None or self._counts.numel() < n:
+            self._counts = torch.empty(max(n, 64), dtype=torch.int32, pin_memory=torch.cuda.is_available())
+        return self._counts
 
     def byte_map(self, n):
         """Zeroed uint8 scratch of at least n entries; users hand it back zeroed."""

@@ -216,7 +216,9 @@ int gmeta_gcn_layer_wgrad(const float* in, int32_t ld_in, const int32_t* in_row_
  * packed-set layout -- out_indptr[node_off[t] + 1 + i] = indptr[t][1 + i] + edge_off[t],
  * out_indices[edge_off[t] + e] = indices[t][e] + node_off[t], same for the transposed arrays -- on up to
  * n_threads host threads (0 = hardware concurrency, capped at 8).  What dgl.batch does for the reference
- * (subgraph_data_processing.py:399-406).  Output pointers are host memory (the pinned staging buffer). */
+ * (subgraph_data_processing.py:399-406).  Output pointers are host memory (the pinned staging buffer).  The four
+ * by-source arguments (t_indptr, t_indices, out_t_indptr, out_t_indices) may all be NULL: the caller then derives
+ * the CSR by source on the device (gmeta_packed_set_finish). */
 int gmeta_host_pack_csr(int32_t n_tasks, const int32_t* const* indptr, const int32_t* const* indices,
                         const int32_t* const* t_indptr, const int32_t* const* t_indices,
                         const int64_t* node_off, const int64_t* edge_off, int32_t* out_indptr,
@@ -420,7 +422,8 @@ int gmeta_khop_build(const int32_t* indptr, const int32_t* indices, const int32_
  * extractor's output, derived in HBM without a host round trip -- the structure work of dgl.batch
  * (subgraph_data_processing.py:399-406) and of the host packer.  Inputs: the packed CSR by destination
  * (indptr [N+1], indices [E]), sub_node_ptr [S+1] (first packed row of every subgraph: node_ptr of
- * gmeta_khop_select), task_sub_ptr [T+1] (device), centre_row [n_centres].  Outputs (device, caller-sized):
+ * gmeta_khop_select), task_sub_ptr [T+1] (device; NULL: sub_node_ptr holds the T+1 task row pointers themselves),
+ * centre_row [n_centres].  Outputs (device, caller-sized):
  *   t_indptr [N+1], t_indices [E]         CSR by source, destinations ascending inside a row
  *   task_row_ptr [T+1]; tile_row0/nrows/task [<= ceil(N/128) + T]   tiles of <= 128 rows inside one task
  *   per GCN layer l < n_layers: act_rows[l] [<= N] (ascending), act_task_ptr[l] [T+1],

@@ -39,6 +39,34 @@ def test_device_built_batch_equals_host_packed_batch(kind):
             assert d.act[l]["n"] == h.act[l]["n"] and d.act[l]["n_tiles"] == h.act[l]["n_tiles"]
 
 
+@pytest.mark.parametrize("kind", ['disjoint', 'shared', 'link', 'deep', 'wide'])
+@pytest.mark.parametrize("own", [False, True])
+def test_slim_pack_equals_full_pack(kind, own):
+    """Meta.upload_batch (host packs the CSR by destination only, the rest is derived on the device) holds, segment by
+    segment, what the all-host packer writes."""
+    ds = H.tiny_dataset(kind)
+    mb = ds.sample_meta_batch(np.random.default_rng(21), 3)
+    torch.manual_seed(222)
+    m = Meta(ds.args(), ds.config()).to('cuda')
+    m.device_finish = True
+    db = m.upload_batch(mb, ds.feats, own_buffer=own)
+    torch.cuda.synchronize()
+    got = db.ints.cpu().numpy()
+    L = len(m.spec.conv)
+    goff = np.concatenate([[0], np.cumsum([f.shape[0] for f in ds.feats])])[:-1]
+    st = packing.Staging(torch.device("cpu"))
+    hs, hq, _ = packing.pack_meta_batch(st, mb, goff, L, _lib.lib())
+    want = st.host.numpy()
+    assert db.h2d_bytes < 4 * (hs.N + hs.E + hq.N + hq.E) * 2          # the by-source half never crosses the bus
+    for d, h in ((db.ps_s, hs), (db.ps_q, hq)):
+        assert (d.N, d.E, d.S, d.T, d.n_tiles, d.cps, d.max_rows_per_task) == (h.N, h.E, h.S, h.T, h.n_tiles, h.cps, h.max_rows_per_task)
+        for k, n in h.sizes.items():
+            assert d.sizes[k] == n, k
+            assert np.array_equal(got[d.off[k]:d.off[k] + n], want[h.off[k]:h.off[k] + n]), k
+        for l in range(L):
+            assert d.act[l]["n"] == h.act[l]["n"] and d.act[l]["n_tiles"] == h.act[l]["n_tiles"]
+
+
 @pytest.mark.parametrize("kind", ['disjoint', 'link'])
 def test_training_step_from_centres_equals_step_from_host_batch(kind):
     ds = H.tiny_dataset(kind)

@@ -136,7 +136,7 @@ def main():
             pr = prof.cpu().numpy().reshape(148, 16).astype(np.float64)
             names = ["prod0.setup", "prod0.wait_empty", "prod0.body", "prod15.setup", "prod15.wait_empty", "prod15.body",
                      "mma.wait_w", "mma.wait_acc_empty", "mma.wait_a_full", "mma.issue", "epi.wait_acc_full", "epi.other",
-                     "epi.stage", "epi.expand", "prod0.hub_phase", "prod0.hub_barrier"]
+                     "epi.stage", "epi.expand"]
             res["pair_profile_kcycles_mean_per_cta"] = {n: round(float(pr[:, i].mean()) / 1e3, 1) for i, n in enumerate(names)}
             res["pair_profile_leader_only"] = {n: round(float(pr[0::2, i].mean()) / 1e3, 1) for i, n in enumerate(names)}
             res["pair_profile_max_per_cta"] = {n: round(float(pr[:, i].max()) / 1e3, 1) for i, n in enumerate(names)}

@@ -19,6 +19,7 @@ Differences from the reference, all on purpose:
 String booleans ('True'/'False') and prefix-abbreviated flags work as in the reference (argparse).
 """
 import argparse
+import collections
 import copy
 import os
 import random
@@ -119,19 +120,28 @@ def main(args):
             db = DataLoader(db_train, args.task_num, shuffle=True, num_workers=args.num_workers, collate_fn=collate)
         s_f = time.time()
         s_r = s_f
-        # one-batch lookahead: while step i runs on the GPU, batch i+1 is packed and uploaded (maml.prefetch)
         if args.device_extract == 'True':
             prep = lambda bt: (bt, bt[1])                                       # noqa: E731  (requests, global task count)
         else:
             prep = lambda bt: (dist.shard_meta_batch(bt), len(bt[0]))           # noqa: E731  this rank's tasks, global count
         it = iter(db)
-        nxt = next(it, None)
-        nxt = None if nxt is None else prep(nxt)
+        ahead = collections.deque()
+
+        def pull():
+            """Read one more meta-batch and hand it to the packer thread (maml.prefetch): a two-batch lookahead, so
+            that packing, the host->device copy and the device passes of a batch run while earlier steps do."""
+            bt = next(it, None)
+            if bt is not None:
+                bt = prep(bt)
+                if args.device_extract != 'True' and bt[1] >= world:
+                    maml.prefetch(*bt[0], feat)
+                ahead.append(bt)
+        pull()
+        pull()
         step = -1
-        while nxt is not None:
-            (batch, n_tasks), step = nxt, step + 1
-            nxt = next(it, None)
-            nxt = None if nxt is None else prep(nxt)
+        while ahead:
+            (batch, n_tasks), step = ahead.popleft(), step + 1
+            pull()
             data_loading_time = time.time() - (s_r if step >= 1 else s_f)
             s = time.time()
             if n_tasks < world:                  # a trailing meta-batch with fewer tasks than ranks
@@ -141,8 +151,6 @@ def main(args):
                 accs = maml.forward_device(graphs, batch[0][0], batch[0][1], feat, args.h, args.sample_nodes,
                                            seed=222 + 1000 * epoch + step)
             else:
-                if nxt is not None and nxt[1] >= world:
-                    maml.prefetch(*nxt[0], feat)
                 accs = maml(*batch, feat)
             max_memory = max(max_memory, float(psutil.virtual_memory().used / (1024 ** 3)))
             if step % args.train_result_report_steps == 0:
