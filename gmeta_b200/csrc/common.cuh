@@ -62,6 +62,9 @@ struct GatherSrc {
   const float* norm;
   int ld_in;
   int f_in;
+  // 1: the graph is the identity (row v's only in-neighbour is v, indptr = indices = 0..N, norm = 1, no row map /
+  // row list): the pre-summed rows of the pruned meta-step.  Kernels that honour it skip the index loads.
+  int identity = 0;
 };
 
 // One warp aggregates, for each of its rows r = warp, warp+NW, ... < R, the 4 columns

@@ -200,7 +200,12 @@ struct WgradParams {
   long long pw_task_stride, pw_split_stride, pb_task_stride, pb_split_stride;
 };
 
-template <bool VEC>
+// DENSE (p.g.identity, 16-byte aligned rows, f_in % 4 == 0): the rows of `in` ARE the aggregated rows -- a chunk is
+// loaded with plain coalesced 16-byte loads, all of them in flight at once, and the next chunk's loads are issued
+// before the current chunk is multiplied (registers as the second buffer).  The gather path walks indptr -> indices ->
+// norm -> row per row, four rows in sequence per warp: ~12 us of dependent latency per 32-row chunk against ~2 us of
+// arithmetic, which is what the short support-set launches of the pruned meta-step consisted of.
+template <bool VEC, bool DENSE>
 __global__ void __launch_bounds__(NTHREADS, 2) gcn_layer_wgrad_simt_kernel(const WgradParams p) {
   pdl_prologue();     // programmatic dependent launch: see common.cuh
   extern __shared__ __align__(16) float smem[];
@@ -233,31 +238,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gcn_layer_wgrad_simt_kernel(const
 #pragma unroll
     for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
 
-    for (int c = c_beg; c < c_end; ++c) {
-      const int row0 = rs + c * WG_ROWS;
-      const int nrows = min(WG_ROWS, re - row0);
-      __syncthreads();
-      gather_rows<VEC, WG_ROWS, NWARPS, true>(p.g, row0, nrows, k0, As, LDA);
-      // dZ chunk: 32 rows x 128 columns; thread -> (row = tid/32 + 8*i, 4 columns at 4*(tid%32))
-#pragma unroll
-      for (int i = 0; i < WG_ROWS / NWARPS; ++i) {
-        const int r = (tid >> 5) + NWARPS * i;
-        const int cc = j0 + 4 * (tid & 31);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < nrows) {
-          const float* src = p.dZ + (size_t)(row0 + r) * p.ld_dz + cc;
-          if (p.vec_dz && cc + 4 <= f_out) {
-            v = ld_f4(src);
-          } else {
-            if (cc + 0 < f_out) v.x = src[0];
-            if (cc + 1 < f_out) v.y = src[1];
-            if (cc + 2 < f_out) v.z = src[2];
-            if (cc + 3 < f_out) v.w = src[3];
-          }
-        }
-        st_f4(Bs + r * LDA + 4 * (tid & 31), v);
-      }
-      __syncthreads();
+    auto multiply = [&]() {
 #pragma unroll 4
       for (int r = 0; r < WG_ROWS; ++r) {
         const float4 a0 = ld_f4(As + r * LDA + 4 * ty);
@@ -274,6 +255,63 @@ __global__ void __launch_bounds__(NTHREADS, 2) gcn_layer_wgrad_simt_kernel(const
 #pragma unroll
           for (int j = 0; j < 8; ++j) bsum[j] += b[j];
         }
+      }
+    };
+    // dZ chunk: 32 rows x 128 columns; thread -> (row = tid/32 + 8*i, 4 columns at 4*(tid%32))
+    auto load_dz = [&](int row0, int nrows, int i) {
+      const int r = (tid >> 5) + NWARPS * i;
+      const int cc = j0 + 4 * (tid & 31);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nrows) {
+        const float* src = p.dZ + (size_t)(row0 + r) * p.ld_dz + cc;
+        if (p.vec_dz && cc + 4 <= f_out) {
+          v = ld_f4(src);
+        } else {
+          if (cc + 0 < f_out) v.x = src[0];
+          if (cc + 1 < f_out) v.y = src[1];
+          if (cc + 2 < f_out) v.z = src[2];
+          if (cc + 3 < f_out) v.w = src[3];
+        }
+      }
+      return v;
+    };
+    if constexpr (DENSE) {
+      float4 ra[WG_ROWS / NWARPS], rb[WG_ROWS / NWARPS];
+      auto load_chunk = [&](int c) {
+        const int row0 = rs + c * WG_ROWS;
+        const int nrows = min(WG_ROWS, re - row0);
+        const int kc = k0 + 4 * (tid & 31);
+#pragma unroll
+        for (int i = 0; i < WG_ROWS / NWARPS; ++i) {
+          const int r = (tid >> 5) + NWARPS * i;
+          ra[i] = (r < nrows && kc < f_in) ? ld_f4(p.g.in + (size_t)(row0 + r) * p.g.ld_in + kc) : make_float4(0.f, 0.f, 0.f, 0.f);
+          rb[i] = load_dz(row0, nrows, i);
+        }
+      };
+      if (c_beg < c_end) load_chunk(c_beg);
+      for (int c = c_beg; c < c_end; ++c) {
+        __syncthreads();                       // the previous chunk has been multiplied
+#pragma unroll
+        for (int i = 0; i < WG_ROWS / NWARPS; ++i) {
+          const int r = (tid >> 5) + NWARPS * i;
+          st_f4(As + r * LDA + 4 * (tid & 31), ra[i]);
+          st_f4(Bs + r * LDA + 4 * (tid & 31), rb[i]);
+        }
+        __syncthreads();
+        if (c + 1 < c_end) load_chunk(c + 1);  // in flight while this chunk is multiplied
+        multiply();
+      }
+    } else {
+      for (int c = c_beg; c < c_end; ++c) {
+        const int row0 = rs + c * WG_ROWS;
+        const int nrows = min(WG_ROWS, re - row0);
+        __syncthreads();
+        gather_rows<VEC, WG_ROWS, NWARPS, true>(p.g, row0, nrows, k0, As, LDA);
+#pragma unroll
+        for (int i = 0; i < WG_ROWS / NWARPS; ++i)
+          st_f4(Bs + ((tid >> 5) + NWARPS * i) * LDA + 4 * (tid & 31), load_dz(row0, nrows, i));
+        __syncthreads();
+        multiply();
       }
     }
 
@@ -640,7 +678,7 @@ int gcn_layer_wgrad_impl(const float* in, int32_t ld_in, const int32_t* in_row_m
                          const int32_t* indptr, const int32_t* indices, const float* norm, const int32_t* task_row_ptr,
                          int32_t n_tasks, const float* dZ, int32_t ld_dz, int32_t f_in, int32_t f_out, float* dW,
                          int64_t dw_task_stride, float* db, int64_t db_task_stride, void* workspace,
-                         int64_t workspace_bytes, int64_t rows_hint, cudaStream_t s) {
+                         int64_t workspace_bytes, int64_t rows_hint, cudaStream_t s, int identity_graph) {
   if (!in || !indptr || !norm || !task_row_ptr || !dZ || !dW || !db || !workspace)
     return GMETA_ERR_BAD_ARG;
   if (n_tasks <= 0 || f_in <= 0 || f_out <= 0 || ld_in < f_in || ld_dz < f_out) return GMETA_ERR_BAD_ARG;
@@ -672,14 +710,18 @@ int gcn_layer_wgrad_impl(const float* in, int32_t ld_in, const int32_t* in_row_m
   const int n_work = n_tasks * ceil_div(f_in, KP) * ceil_div(f_out, BN) * p.n_split;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(gcn_layer_wgrad_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem);
-    cudaFuncSetAttribute(gcn_layer_wgrad_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem);
+    cudaFuncSetAttribute(gcn_layer_wgrad_simt_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem);
+    cudaFuncSetAttribute(gcn_layer_wgrad_simt_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem);
+    cudaFuncSetAttribute(gcn_layer_wgrad_simt_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem);
     attr_done = true;
   }
-  if (vec_in)
-    launch_pdl(gcn_layer_wgrad_simt_kernel<true>, dim3(n_work), dim3(NTHREADS), kWgSmem, s, p);
+  p.g.identity = (identity_graph && vec_in && f_in % 4 == 0 && !in_row_map && !dst_rows) ? 1 : 0;
+  if (p.g.identity)
+    launch_pdl(gcn_layer_wgrad_simt_kernel<true, true>, dim3(n_work), dim3(NTHREADS), kWgSmem, s, p);
+  else if (vec_in)
+    launch_pdl(gcn_layer_wgrad_simt_kernel<true, false>, dim3(n_work), dim3(NTHREADS), kWgSmem, s, p);
   else
-    launch_pdl(gcn_layer_wgrad_simt_kernel<false>, dim3(n_work), dim3(NTHREADS), kWgSmem, s, p);
+    launch_pdl(gcn_layer_wgrad_simt_kernel<false, false>, dim3(n_work), dim3(NTHREADS), kWgSmem, s, p);
   int rc = check_launch();
   if (rc != GMETA_OK || p.n_split == 1) return rc;
   const long long total = (long long)n_tasks * (n_w + f_out);
@@ -698,5 +740,5 @@ extern "C" int gmeta_gcn_layer_wgrad(const float* in, int32_t ld_in, const int32
                                      void* workspace, int64_t workspace_bytes, void* stream) {
   return gcn_layer_wgrad_impl(in, ld_in, in_row_map, dst_rows, indptr, indices, norm, task_row_ptr, n_tasks, dZ, ld_dz,
                               f_in, f_out, dW, dw_task_stride, db, db_task_stride, workspace, workspace_bytes, -1,
-                              (cudaStream_t)stream);
+                              (cudaStream_t)stream, 0);
 }

@@ -263,8 +263,13 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const 
         if (j < nt && r < p.tile_nrows[tile0 + j]) {
           const int oi = p.tile_row0[tile0 + j] + r;
           const int v = p.g.dst_rows ? p.g.dst_rows[oi] : oi;
-          rb = p.g.indptr[v];
-          d = p.g.indptr[v + 1] - rb;
+          if (p.g.identity) {              // pre-summed rows: row v's only "neighbour" is v itself, weight 1
+            rb = v;
+            d = 1;
+          } else {
+            rb = p.g.indptr[v];
+            d = p.g.indptr[v + 1] - rb;
+          }
         }
         const bool lg = d > PRE;
         ps->beg[tid] = rb;
@@ -276,10 +281,15 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const 
           int off = 0;
           float nn = 0.f;
           if (!lg && i < d) {
-            const int u = p.g.indices[rb + i];
-            const int srow = p.g.in_row_map ? p.g.in_row_map[u] : u;
-            nn = srow < 0 ? 0.f : p.g.norm[u];        // negative map entry: neighbour dropped
-            off = (srow < 0 ? 0 : srow) * p.g.ld_in;
+            if (p.g.identity) {
+              nn = 1.f;
+              off = rb * p.g.ld_in;
+            } else {
+              const int u = p.g.indices[rb + i];
+              const int srow = p.g.in_row_map ? p.g.in_row_map[u] : u;
+              nn = srow < 0 ? 0.f : p.g.norm[u];        // negative map entry: neighbour dropped
+              off = (srow < 0 ? 0 : srow) * p.g.ld_in;
+            }
           }
           ps->s_off[tid][i] = off;
           ps->s_nrm[tid][i] = nn;

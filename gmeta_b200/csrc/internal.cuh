@@ -19,7 +19,7 @@ int gcn_layer_wgrad_impl(const float* in, int32_t ld_in, const int32_t* in_row_m
                          const int32_t* indptr, const int32_t* indices, const float* norm, const int32_t* task_row_ptr,
                          int32_t n_tasks, const float* dZ, int32_t ld_dz, int32_t f_in, int32_t f_out, float* dW,
                          int64_t dw_task_stride, float* db, int64_t db_task_stride, void* workspace,
-                         int64_t workspace_bytes, int64_t rows_hint, cudaStream_t s);
+                         int64_t workspace_bytes, int64_t rows_hint, cudaStream_t s, int identity_graph = 0);
 
 // ---- streamed-weight tensor-core layer kernel (gcn_layer_tc.cu) ----
 bool gcn_layer_fwd_tc_supported(const GatherSrc& g, int ldw, int trans_w, int f_out, const float* out,

@@ -291,7 +291,7 @@ struct Runner {
         if (b.tc_img[i >> 1][i & 1]) ++seg;
       GatherSrc g;
       g.in = in; g.in_row_map = nullptr; g.dst_rows = nullptr; g.indptr = b.iota; g.indices = b.iota; g.norm = b.ones;
-      g.ld_in = ld_in; g.f_in = K;
+      g.ld_in = ld_in; g.f_in = K; g.identity = 1;
       run(gcn_layer_fwd_tc(g, t_row0, t_nrows, t_task, n_tiles, w.stride == 0 ? 1 : n_tasks, w.W + m.w_off[l], w.stride,
                            m.f_out[l], orient, bias, w.stride, N, relu, relu_mask, out, ld_out, ws, b.layer_ws_bytes,
                            w.img + b.pack.seg[seg].img_off, w.stride == 0 ? 0 : b.pack.img_copy_stride, s));
@@ -379,7 +379,7 @@ struct Runner {
         const float* agg = (&set == &a->spt ? b.agg_spt : b.agg_qry)[l];
         run(gcn_layer_wgrad_impl(agg, ld_in, nullptr, nullptr, b.iota, b.iota, b.ones, set.act_task_ptr[l], set.n_tasks,
                                  dz[cur], b.ld[l], m.f_in[l], m.f_out[l], gout + m.w_off[l], P, gout + m.b_off[l], P,
-                                 b.wgrad_ws, b.wgrad_ws_bytes, set.n_act[l], s));
+                                 b.wgrad_ws, b.wgrad_ws_bytes, set.n_act[l], s, /*identity_graph=*/1));
         if (l > 0) {
           const bool is_spt = &set == &a->spt;
           run(aggregate_rows_impl(dz[cur], b.ld[l], set.row_pos[l], set.act_rows[l - 1], nullptr,
