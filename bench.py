@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the synthetic graph (debug only)")
     ap.add_argument("--tasks", type=int, default=0, help="tasks per rank (default: the config's task_num)")
-    ap.add_argument("--batches", type=int, default=3, help="distinct pre-extracted meta-batches to cycle")
+    ap.add_argument("--batches", type=int, default=5, help="distinct pre-extracted meta-batches to cycle")
     ap.add_argument("--kernel-impl", type=int, default=0, help="0 auto, 1 FFMA, 2 tcgen05")
     ap.add_argument("--cpu-tasks", type=int, default=8, help="tasks per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -463,6 +463,7 @@ def emit(line):
 
 
 MIN_TIMED_S = 2.0
+LOOKAHEAD = 3                # batches handed to Meta.prefetch ahead of the one being stepped (train.py does the same)
 CLOCK_WARMUP_STEPS = 150     # device-resident warm-up steps before a timed region (>= 0.3 s of work on every config)
 
 
@@ -633,11 +634,12 @@ def main():
     accs_box = [None]
 
     def e2e_step(i):
-        # the training loop's own pattern (train.py): a two-batch lookahead -- batch i+2 goes to the packer thread, then
+        # the training loop's own pattern (train.py): a three-batch lookahead -- batch i+3 goes to a packer thread, then
         # batch i (packed, copied and finished on the device while earlier steps ran) is stepped
         if i == 0:
             m.prefetch(*batches[1 % len(batches)], ds.feats)
-        m.prefetch(*batches[(i + 2) % len(batches)], ds.feats)
+            m.prefetch(*batches[2 % len(batches)], ds.feats)
+        m.prefetch(*batches[(i + LOOKAHEAD) % len(batches)], ds.feats)
         accs_box[0] = m(*batches[i % len(batches)], ds.feats)
     ms_e2e_k, ms_e2e, n_e2e = timed_region(e2e_step, args.steps, world, td)
     accs = accs_box[0]

@@ -90,6 +90,11 @@ _SIGNATURES = {
                                           vp, vp, vp, i64, vp]),
     "gmeta_maml_step_workspace_bytes": (i64, [C.POINTER(StepArgs)]),
     "gmeta_maml_step": (C.c_int, [C.POINTER(StepArgs), vp]),
+    "gmeta_step_graph_create": (C.c_int, [C.POINTER(vp)]),
+    "gmeta_step_graph_destroy": (None, [vp]),
+    "gmeta_step_graph_prepare": (C.c_int, [vp, C.POINTER(StepArgs), vp]),
+    "gmeta_step_graph_launch": (C.c_int, [vp, vp]),
+    "gmeta_step_graph_stats": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i32)]),
     "gmeta_last_launch_count": (C.c_int, []),
     "gmeta_debug_set_tc_profile": (None, [vp]),
     "gmeta_debug_set_tc_flags": (None, [C.c_int]),

@@ -574,3 +574,91 @@ extern "C" int gmeta_maml_step(const gmeta_step_args_t* a_in, void* stream) {
   }
   return r.rc;
 }
+
+// ------------------------------------------------------------------------------------------
+// The meta-step as an UPDATABLE CUDA graph, for batches whose shapes change from step to step (host batches): the
+// ~200 launches of a step are captured (no device work), the executable graph of the previous batch is updated in
+// place with the new launch parameters (same topology: cudaGraphExecUpdate, ~0.2 ms on the host) and launched as one
+// unit.  The caller prepares batch i+1 while step i runs on the device, so the per-launch cost of an eager step
+// (~4 us of gap behind each of the 200 small kernels) leaves the critical path.  Capture is thread-local: packer
+// threads keep issuing copies and allocations meanwhile.  `stream` of prepare must not be the legacy default stream.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct StepGraph {
+  cudaGraphExec_t exec = nullptr;
+  int launches = 0;
+  int updates = 0, instantiations = 0;
+};
+}  // namespace
+
+extern "C" int gmeta_step_graph_create(void** handle) {
+  if (!handle) return GMETA_ERR_BAD_ARG;
+  *handle = new StepGraph();
+  return GMETA_OK;
+}
+
+extern "C" void gmeta_step_graph_destroy(void* handle) {
+  StepGraph* g = reinterpret_cast<StepGraph*>(handle);
+  if (!g) return;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  delete g;
+}
+
+extern "C" int gmeta_step_graph_prepare(void* handle, const gmeta_step_args_t* args, void* stream) {
+  StepGraph* g = reinterpret_cast<StepGraph*>(handle);
+  if (!g || !args || !stream) return GMETA_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    return GMETA_ERR_LAUNCH;
+  }
+  const int rc = gmeta_maml_step(args, stream);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+  if (rc != GMETA_OK || ce != cudaSuccess || !graph) {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    return rc != GMETA_OK ? rc : GMETA_ERR_LAUNCH;
+  }
+  g->launches = g_launch_count;
+  if (g->exec) {
+    cudaGraphExecUpdateResultInfo info;
+    if (cudaGraphExecUpdate(g->exec, graph, &info) == cudaSuccess) {
+      ++g->updates;
+    } else {                              // topology changed (e.g. a reduction launch appeared): rebuild
+      cudaGetLastError();
+      cudaGraphExecDestroy(g->exec);
+      g->exec = nullptr;
+    }
+  }
+  if (!g->exec) {
+    if (cudaGraphInstantiate(&g->exec, graph, 0) != cudaSuccess) {
+      cudaGetLastError();
+      g->exec = nullptr;
+      cudaGraphDestroy(graph);
+      return GMETA_ERR_LAUNCH;
+    }
+    ++g->instantiations;
+  }
+  cudaGraphDestroy(graph);
+  return GMETA_OK;
+}
+
+extern "C" int gmeta_step_graph_launch(void* handle, void* stream) {
+  StepGraph* g = reinterpret_cast<StepGraph*>(handle);
+  if (!g || !g->exec) return GMETA_ERR_BAD_ARG;
+  if (cudaGraphLaunch(g->exec, (cudaStream_t)stream) != cudaSuccess) {
+    cudaGetLastError();
+    return GMETA_ERR_LAUNCH;
+  }
+  g_launch_count = g->launches;
+  return GMETA_OK;
+}
+
+extern "C" int gmeta_step_graph_stats(void* handle, int32_t* updates, int32_t* instantiations) {
+  StepGraph* g = reinterpret_cast<StepGraph*>(handle);
+  if (!g) return GMETA_ERR_BAD_ARG;
+  if (updates) *updates = g->updates;
+  if (instantiations) *instantiations = g->instantiations;
+  return GMETA_OK;
+}

@@ -183,7 +183,7 @@ def _feat_fingerprint(feat):
 
 class _DeviceBatch(object):
     """An uploaded meta-batch: segment plans of both sets + the device int32 buffer holding them."""
-    __slots__ = ("T", "max_classes", "ft", "ps_s", "ps_q", "ints", "h2d_bytes", "resident", "ready", "pack_ms", "pending")
+    __slots__ = ("T", "max_classes", "ft", "ps_s", "ps_q", "ints", "h2d_bytes", "resident", "ready", "pack_ms", "pending", "graph")
 
 
 class FusedAdam(object):
@@ -263,6 +263,10 @@ class Meta(nn.Module):
         self._theta_flat = None        # flat parameter buffer the net's parameters are views of
         self._aux_stream = None        # second stream for the query forwards (gmeta_step_args_t::aux_stream)
         self._graphs = {}              # captured meta-steps of device-resident batches
+        self._step_graphs = None       # updatable graphs of host-batch steps (gmeta_step_graph_*): handles, round robin
+        self._sg_i = 0
+        self._cap_stream = None
+        self._picked = None            # a prefetched batch picked up early, with its step graph prepared
         self._alloc_gen = 0            # bumped whenever a scratch / workspace buffer is re-allocated
         # replay device-resident meta-steps (step_device on a batch with its own buffer) from CUDA graphs
         self.use_graphs = bool(getattr(args, 'use_graphs', True))
@@ -271,7 +275,10 @@ class Meta(nn.Module):
         # False = everything packed on the host.  Measured on 1 GPU (C2, round 2): 5.2 vs 4.6 ms per step -- the
         # device passes compete with the step they run beside -- so the host packer stays the default.
         self.device_finish = bool(getattr(args, 'device_finish', False))
-        self.pack_workers = 2          # packer threads of `prefetch` (a two-batch lookahead keeps both busy)
+        self.pack_workers = 3          # packer threads of `prefetch` (the callers' three-batch lookahead keeps them busy)
+        # host batches: run the step as an updatable CUDA graph prepared one batch ahead (gmeta_step_graph_*)
+        self.graph_host_batches = bool(getattr(args, 'graph_host_batches', True))
+        self.prepare_ahead = True
         self.two_streams = bool(getattr(args, 'two_streams', True))
         self.last = {}                 # diagnostics of the most recent call (loss, launches, bytes)
         self.return_meta_grad = False  # tests: keep a copy of the reduced meta-gradient
@@ -287,7 +294,7 @@ class Meta(nn.Module):
             if k == "_feat_cache":
                 new.__dict__[k] = v          # the resident table is read-only: copies share it (train.py:87,127)
             elif k in ("_staging", "_ws", "_scratch", "_extractor", "_theta_flat", "_aux_stream", "_graphs", "_pool",
-                       "_copy_stream", "_prefetched"):
+                       "_copy_stream", "_prefetched", "_step_graphs", "_cap_stream", "_picked"):
                 new.__dict__[k] = {} if k in ("_scratch", "_graphs") else None
             else:
                 new.__dict__[k] = deepcopy(v, memo)
@@ -339,17 +346,22 @@ class Meta(nn.Module):
 
     # -- host batch -> device: packing + ONE pinned H2D copy, optionally one step ahead on a worker thread --
     def _pack_threads(self):
-        """Host threads of the CSR packer: the cores of the box shared between the ranks on it and the packer
-        workers of a rank, 8 at most."""
+        """Host threads of one CSR packing call.  Synchronous uploads use the cores of the box shared between the ranks
+        on it (8 at most).  Under `prefetch` the parallelism comes from the packer workers themselves -- one thread
+        each: with every core busy packing, the step's own host side (launches, graph update, the driver's
+        servicing of the running step) is starved and the DEVICE time of a step grows (measured on C2: 4.4 ms with
+        5 threads per worker against 3.6 ms with one)."""
         import os
-        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))) * (self.pack_workers if self._pool is not None else 1)
+        if self._pool is not None:
+            return 1
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
         return max(1, min(8, (os.cpu_count() or 1) // local_world))
 
     def _slot(self, dev):
-        """Next staging slot of a ring of four (pinned buffer + device buffer each): the step in flight, the batch
-        being packed behind it, one more pending prefetch and a spare."""
+        """Next staging slot of a ring of six (pinned buffer + device buffer each): the step in flight, the batch picked
+        up ahead of it, up to three pending prefetches and a spare."""
         if self._staging is None or self._staging[0].device != dev:
-            self._staging = [packing.Staging(dev) for _ in range(4)]
+            self._staging = [packing.Staging(dev) for _ in range(6)]
             self._slot_i = 0
         self._slot_i = (self._slot_i + 1) % len(self._staging)
         slot = self._staging[self._slot_i]
@@ -442,10 +454,10 @@ class Meta(nn.Module):
             self._prefetched = []
         slot = self._slot(dev)
         fut = self._pool.submit(self._pack_upload, batch, ft, slot, dev, False, self._copy_stream)
-        # the caller's pattern is prefetch(batch i+2) followed by forward(batch i): three entries can be pending (a
-        # two-batch lookahead keeps the packer thread, the copy and the device passes of a batch off the step's
-        # critical path even when they take as long as the step itself)
-        while len(self._prefetched) >= 3:
+        # the caller's pattern is prefetch(batch i+3) followed by forward(batch i): four entries can be pending (the
+        # lookahead keeps the packer threads and the copy of a batch off the step's critical path even when they
+        # take longer than the step itself)
+        while len(self._prefetched) >= 4:
             self._prefetched.pop(0)[2].result()            # an abandoned prefetch: let the worker finish with its slot
         self._prefetched.append((x_spt, feat, fut, slot))
 
@@ -458,6 +470,13 @@ class Meta(nn.Module):
         if self._prefetched is None:
             self._prefetched = []
         pend = self._prefetched
+        if self._picked is not None and not own_buffer:
+            x0, f0, db = self._picked
+            self._picked = None
+            if x0 is batch[0] and f0 is feat:
+                self.pickup_wait_ms = (0.0, 0.0)
+                self.host_pack_ms = db.pack_ms
+                return db
         hit = next((e for e in pend if e[0] is batch[0] and e[1] is feat), None) if not own_buffer else None
         t0 = time.perf_counter()
         if hit is not None:
@@ -528,14 +547,24 @@ class Meta(nn.Module):
         """Enqueue the whole inner loop for an uploaded meta-batch.  Returns device tensors
         (acc_q [T,K+1], loss_q [T,K+1], meta_grad [P] or None).  `meta_grad` / `stats`: where the summed
         meta-gradient [P] and the step's scalars [K+2] (sum of last query losses, accuracy sums) go."""
+        a, info, (acc_q, loss_q, meta_grad) = self._build_args(db, steps, train, flat_theta, meta_grad, stats)
+        if getattr(db, "ready", None) is not None:
+            torch.cuda.current_stream().wait_event(db.ready)          # the batch's H2D copy (maybe on the copy stream)
+        L = _lib.lib()
+        _lib.check(L.gmeta_maml_step(C.byref(a), _stream()), "maml_step")
+        info["gpu_launches"] = L.gmeta_last_launch_count()
+        self.last = info
+        return acc_q, loss_q, meta_grad
+
+    def _build_args(self, db, steps, train, flat_theta, meta_grad=None, stats=None):
+        """The argument block of gmeta_maml_step for an uploaded meta-batch (allocates / grows the buffers it points
+        to; launches nothing).  Returns (args, diagnostics, (acc_q, loss_q, meta_grad))."""
         L = _lib.lib()
         dev = _dev()
         T, ps_s, ps_q, ft = db.T, db.ps_s, db.ps_q, db.ft
         if train and steps < 2:
             raise RuntimeError("element 0 of tensors does not require grad and does not have a grad_fn "
                                "(update_step must be >= 2, as in the reference: meta.py:137-141,161)")
-        if getattr(db, "ready", None) is not None:
-            torch.cuda.current_stream().wait_event(db.ready)          # the batch's H2D copy (maybe on the copy stream)
         base = db.ints.data_ptr()
         a = _lib.StepArgs()
         a.model = self.spec.c_model()
@@ -577,11 +606,10 @@ class Meta(nn.Module):
             self._ws = torch.empty(int(nbytes * 1.1) + 4096, dtype=torch.uint8, device=dev)
             self._alloc_gen += 1
         a.workspace, a.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
-        _lib.check(L.gmeta_maml_step(C.byref(a), _stream()), "maml_step")
-        self.last = {"h2d_bytes": db.h2d_bytes, "gpu_launches": L.gmeta_last_launch_count(),
-                     "n_nodes": (ps_s.N, ps_q.N), "n_edges": (ps_s.E, ps_q.E), "workspace_bytes": int(nbytes),
-                     "logits_spt0": logits0, "loss_s": loss_s}
-        return acc_q, loss_q, meta_grad
+        info = {"h2d_bytes": db.h2d_bytes, "gpu_launches": 0,
+                "n_nodes": (ps_s.N, ps_q.N), "n_edges": (ps_s.E, ps_q.E), "workspace_bytes": int(nbytes),
+                "logits_spt0": logits0, "loss_s": loss_s}
+        return a, info, (acc_q, loss_q, meta_grad)
 
     def _run(self, x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry, feat,
              steps, train, flat_theta):
@@ -615,6 +643,56 @@ class Meta(nn.Module):
             self._alloc_gen += 1
         return flat
 
+    def _prepare_step_graph(self, db):
+        """Capture the training step of a host batch into the next updatable graph (no device work): called for the
+        NEXT batch while the current step runs, so that a step costs the host one graph launch.  Returns
+        (handle, diagnostics, validity key) or None when capture is not possible right now."""
+        dev = _dev()
+        L = _lib.lib()
+        K, P = self.update_step, self.spec.n_params_padded
+        theta = self._flat_theta(self.net.parameters(), dev)
+        T_global = self._global_task_num(db.T)
+        red = self._buf("reduce", (P + K + 2,), torch.float32, dev)
+        a, info, _ = self._build_args(db, K, True, theta, meta_grad=red[:P], stats=red[P:])
+        if self._step_graphs is None:
+            self._step_graphs = []
+            for _ in range(3):
+                h = C.c_void_p()
+                _lib.check(L.gmeta_step_graph_create(C.byref(h)), "step_graph_create")
+                self._step_graphs.append(h)
+            self._cap_stream = torch.cuda.Stream(device=dev)
+        self._sg_i = (self._sg_i + 1) % len(self._step_graphs)
+        h = self._step_graphs[self._sg_i]
+        rc = L.gmeta_step_graph_prepare(h, C.byref(a), self._cap_stream.cuda_stream)
+        if rc != 0:
+            return None
+        info["gpu_launches"] = L.gmeta_last_launch_count()
+        db.graph = (h, info, (self._alloc_gen, theta.data_ptr(), T_global))
+        return db.graph
+
+    def _prepare_ahead(self):
+        """While the step just launched runs: if the next prefetched batch has left the packer thread, pick it up and
+        prepare its step graph now."""
+        if not (self.use_graphs and self.graph_host_batches and self.prepare_ahead) or self._picked is not None \
+                or not self._prefetched:
+            return
+        x0, feat, fut, slot = self._prefetched[0]
+        t0 = time.perf_counter()
+        try:
+            # the device is busy with the step for a few milliseconds: waiting for the packer here costs nothing that
+            # the next pick-up would not have to wait for anyway
+            db = fut.result(timeout=0.003)
+        except Exception:
+            return
+        self._prefetched.pop(0)
+        t1 = time.perf_counter()
+        db = self._finalize(db)
+        t2 = time.perf_counter()
+        self._prepare_step_graph(db)
+        self._picked = (x0, feat, db)
+        # diagnostics: waited for the packer thread, for the batch's copy, host time of capture + graph update (ms)
+        self.ahead_ms = (1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (time.perf_counter() - t2))
+
     # -- public API (meta.py:236-244) --
     def step_device(self, db):
         """One training meta-step on an uploaded batch, everything on the device: inner loop, the
@@ -640,7 +718,18 @@ class Meta(nn.Module):
             if self._graphs and next(iter(self._graphs))[-1] != self._alloc_gen:
                 self._graphs.clear()               # a buffer moved: every captured pointer set is stale
         entry = self._graphs.get(key) if key is not None else None
-        if entry is not None and entry[0] is not None:
+        sg = None
+        if key is None and self.use_graphs and self.graph_host_batches and getattr(db, "ready", None) is not None \
+                and not getattr(self, "keep_logits_spt0", False):        # host batches in a staging slot
+            sg = getattr(db, "graph", None)
+            if sg is None or sg[2] != (self._alloc_gen, theta.data_ptr(), T_global):
+                sg = self._prepare_step_graph(db)
+        if sg is not None:
+            if getattr(db, "ready", None) is not None:
+                torch.cuda.current_stream().wait_event(db.ready)
+            _lib.check(_lib.lib().gmeta_step_graph_launch(sg[0], _stream()), "step_graph_launch")
+            self.last = dict(sg[1])
+        elif entry is not None and entry[0] is not None:
             entry[0].replay()
             self.last = dict(entry[1])
         else:
@@ -670,7 +759,9 @@ class Meta(nn.Module):
     def forward_ProtoMAML(self, x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry, feat):
         K = self.update_step
         db = self.upload_batch((x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, n_spt, n_qry, g_spt, g_qry), feat)
-        host = self.step_device(db).cpu()                                 # the step's only D2H + sync
+        out = self.step_device(db)
+        self._prepare_ahead()                                             # the next batch's launches, while this step runs
+        host = out.cpu()                                                  # the step's only D2H + sync
         self.last.update({"loss_q": float(host[K + 1]), "skipped": bool(host[K + 2] != 0),
                           "d2h_bytes": int(host.numel() * 4)})
         return host[:K + 1].numpy().astype(np.float32)

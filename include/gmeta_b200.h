@@ -418,6 +418,17 @@ int gmeta_khop_build(const int32_t* indptr, const int32_t* indices, const int32_
                      int32_t* out_indptr, int32_t* out_indices, int32_t* out_parent, int32_t* out_global,
                      int32_t* out_centre, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The meta-step as an updatable CUDA graph, for batches whose shapes change from step to step.  `prepare` captures
+ * what gmeta_maml_step(args) would enqueue (no device work is done; capture is thread-local, `stream` must not be the
+ * legacy default stream) and updates the handle's executable graph in place -- re-instantiating it only when the
+ * launch topology changed; `launch` runs it on any stream.  Prepare batch i+1 while step i runs and the ~200 launches
+ * of a step leave the critical path.  The argument buffers must stay valid until the launch has completed. */
+int gmeta_step_graph_create(void** handle);
+void gmeta_step_graph_destroy(void* handle);
+int gmeta_step_graph_prepare(void* handle, const gmeta_step_args_t* args, void* stream);
+int gmeta_step_graph_launch(void* handle, void* stream);
+int gmeta_step_graph_stats(void* handle, int32_t* updates, int32_t* instantiations);
+
 /* Packed-set assembly on the device (csrc/batch_assemble.cu): what gmeta_packed_set_t needs on top of the
  * extractor's output, derived in HBM without a host round trip -- the structure work of dgl.batch
  * (subgraph_data_processing.py:399-406) and of the host packer.  Inputs: the packed CSR by destination

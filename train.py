@@ -128,7 +128,7 @@ def main(args):
         ahead = collections.deque()
 
         def pull():
-            """Read one more meta-batch and hand it to the packer thread (maml.prefetch): a two-batch lookahead, so
+            """Read one more meta-batch and hand it to the packer thread (maml.prefetch): a three-batch lookahead, so
             that packing, the host->device copy and the device passes of a batch run while earlier steps do."""
             bt = next(it, None)
             if bt is not None:
@@ -136,6 +136,7 @@ def main(args):
                 if args.device_extract != 'True' and bt[1] >= world:
                     maml.prefetch(*bt[0], feat)
                 ahead.append(bt)
+        pull()
         pull()
         pull()
         step = -1
