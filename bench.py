@@ -61,6 +61,9 @@ def parse():
     ap.add_argument("--no-full", action="store_true", help="skip the full-formulation (unpruned) arm")
     ap.add_argument("--no-device-extract", action="store_true", help="skip the device-extraction end-to-end arm")
     ap.add_argument("--no-configs", action="store_true", help="skip the C3 / C4 / C5 strong-scaling blocks")
+    ap.add_argument("--profile-run", action="store_true",
+                    help="for runs under a profiler only: no clock warm-up, exactly --steps timed steps per arm, no CUDA "
+                         "graphs (so that ncu lists the kernels); the JSON line carries \"profile_run\": true")
     ap.add_argument("--roofline-only", action="store_true",
                     help="only the full-layer launches of `roofline` on the seeded query set (the command to put under ncu)")
     return ap.parse_args()
@@ -142,7 +145,7 @@ class ClockSampler(threading.Thread):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one full-layer launch (three kernels) per packed-row count N of the
 # seeded query set it was captured on (profiles/r02_layer_pair_full.md)
-PROFILE_TRAFFIC = {1284403: 2.643074e9}
+PROFILE_TRAFFIC = {1284403: 2.640419e9}
 
 TIE_GAP = 2e-4   # twice the stated logit tolerance (north_star: logits within 1e-4, identical argmax)
 
@@ -534,7 +537,10 @@ def strong_scaling_config(name, world, rank, local_rank, kernel_impl, steps, war
 
 
 def main():
+    global MIN_TIMED_S, CLOCK_WARMUP_STEPS
     args = parse()
+    if args.profile_run:
+        MIN_TIMED_S, CLOCK_WARMUP_STEPS = 0.0, 0
     claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -593,6 +599,8 @@ def main():
 
     margs = ds.args()
     margs.impl = args.kernel_impl
+    if args.profile_run:
+        margs.use_graphs = False          # the kernels of a step appear one by one in the profiler's launch list
     torch.manual_seed(222)
     m = Meta(margs, ds.config()).to(dev)
     peaks = {}
@@ -738,6 +746,8 @@ def main():
             "gpu_launches": int(launches[0]), "gpu_launches_per_step": int(launches_per_step),
             "clocks": sampler.summary(), "roofline": roof, "roofline_step": roof_step, "cpu_baseline": cb,
             "parity_in_run": bool(parity["ok"]) if parity else None, "parity": parity}
+    if args.profile_run:
+        line["profile_run"] = True         # not a measurement: no clock warm-up, eager steps, exactly --steps per arm
     if extraction:
         line["extraction"] = extraction
     if ms_dev > 0:

@@ -71,6 +71,8 @@ struct StepBuffers {
   int32_t* aout_idx_qry[GMETA_MAX_LAYERS];
   int32_t* aout_count;
   int n_ident;                        // rows of the identity graph
+  float* agg_bwd;                     // full-formulation forwards + sparse backward: aggregated input of the layer whose
+                                      // weight gradient is being taken, [max n_act[l], max ld_in]
   int32_t* iota;
   float* ones;
   // full-formulation forwards through the CTA-pair path: structure plans (layer 0 maps rows through feat_row,
@@ -156,9 +158,23 @@ void carve(const gmeta_step_args_t* a, void* ws, StepBuffers& b) {
     b.aout_idx_qry[l] = c.take<int32_t>(need && a->compute_meta_grad ? (int64_t)a->qry.n_edges : 0);
   }
   b.aout_count = c.take<int32_t>(a->pruned_forward ? 2 * n_max : 0);
-  b.n_ident = a->pruned_forward ? (int)n_max : 0;
-  b.iota = c.take<int32_t>(a->pruned_forward ? n_max + 1 : 0);
-  b.ones = c.take<float>(a->pruned_forward ? n_max : 0);
+  // full-formulation forwards with the structurally-sparse backward: the weight gradient takes the same two steps as in
+  // pruned mode (chip-wide neighbourhood sums of the active rows, then the dense contraction), into this scratch
+  const bool sparse_full = !a->pruned_forward && !a->dense_backward;
+  if (sparse_full) {
+    for (int l = 0; l < m.n_layers; ++l) {
+      if (a->spt.n_act[l] > n_max) n_max = a->spt.n_act[l];
+      if (a->qry.n_act[l] > n_max) n_max = a->qry.n_act[l];
+    }
+  }
+  int64_t ld_in_max = a->ld_feat;
+  for (int l = 1; l < m.n_layers; ++l)
+    if (b.ld[l - 1] > ld_in_max) ld_in_max = b.ld[l - 1];
+  b.agg_bwd = c.take<float>(sparse_full ? n_max * ld_in_max : 0);
+  const bool ident = a->pruned_forward || sparse_full;
+  b.n_ident = ident ? (int)n_max : 0;
+  b.iota = c.take<int32_t>(ident ? n_max + 1 : 0);
+  b.ones = c.take<float>(ident ? n_max : 0);
   b.dz_spt[0] = c.take<float>(rows_s * ld_max);
   b.dz_spt[1] = c.take<float>(m.n_layers > 1 ? rows_s * ld_max : 0);
   b.dz_qry[0] = c.take<float>(a->compute_meta_grad ? rows_q * ld_max : 0);
@@ -391,11 +407,21 @@ struct Runner {
         }
         continue;
       }
-      run(gcn_layer_wgrad_impl(in, ld_in, l == 0 ? set.feat_row : nullptr, sparse ? set.act_rows[l] : nullptr,
-                               set.indptr, set.indices, set.norm, sparse ? set.act_task_ptr[l] : set.task_row_ptr,
-                               set.n_tasks, dz[cur], b.ld[l], m.f_in[l], m.f_out[l], gout + m.w_off[l], P,
-                               gout + m.b_off[l], P, b.wgrad_ws, b.wgrad_ws_bytes,
-                               sparse ? set.n_act[l] : set.n_nodes, s));
+      if (sparse) {
+        // dW_l = (n_v M_v)^T dZ_l over the active rows: their neighbourhood sums by the chip-wide gather (one warp per
+        // row), then the dense contraction -- instead of re-gathering M inside every (row chunk, column block) item
+        run(gmeta_aggregate_rows(in, ld_in, l == 0 ? set.feat_row : nullptr, set.act_rows[l], set.indptr, set.indices,
+                                 set.norm, set.n_act[l], m.f_in[l], 1, b.agg_bwd, ld_in, s));
+        run(gcn_layer_wgrad_impl(b.agg_bwd, ld_in, nullptr, nullptr, b.iota, b.iota, b.ones, set.act_task_ptr[l],
+                                 set.n_tasks, dz[cur], b.ld[l], m.f_in[l], m.f_out[l], gout + m.w_off[l], P,
+                                 gout + m.b_off[l], P, b.wgrad_ws, b.wgrad_ws_bytes, set.n_act[l], s,
+                                 /*identity_graph=*/1));
+      } else {
+        run(gcn_layer_wgrad_impl(in, ld_in, l == 0 ? set.feat_row : nullptr, nullptr, set.indptr, set.indices, set.norm,
+                                 set.task_row_ptr, set.n_tasks, dz[cur], b.ld[l], m.f_in[l], m.f_out[l],
+                                 gout + m.w_off[l], P, gout + m.b_off[l], P, b.wgrad_ws, b.wgrad_ws_bytes, set.n_nodes,
+                                 s, 0));
+      }
       if (l > 0) {
         // data gradient = the forward kernel on the transposed graph with W^T, masked by the
         // ReLU of the layer below (features carry no gradient, so layer 0 stops here).  Sparse:
@@ -520,7 +546,7 @@ extern "C" int gmeta_maml_step(const gmeta_step_args_t* a_in, void* stream) {
       r.run(gmeta_aggregate_rows(a->feat_table, a->ld_feat, set.feat_row, set.act_rows[0], set.indptr, set.indices,
                                  set.norm, set.n_act[0], m.f_in[0], 1, (side ? b.agg_qry : b.agg_spt)[0], a->ld_feat, st));
   }
-  if (a->pruned_forward) r.run(fill_identity_graph(b.iota, b.ones, b.n_ident, s));
+  if (b.n_ident > 0) r.run(fill_identity_graph(b.iota, b.ones, b.n_ident, s));
   if (b.pack.n_seg > 0)
     r.run(gcn_tc_sgd_pack(a->theta, 0, nullptr, 0.f, 1, (int)P, nullptr, b.pack, b.img_theta, s));
 
