@@ -272,9 +272,18 @@ class Meta(nn.Module):
         self.use_graphs = bool(getattr(args, 'use_graphs', True))
         # host batches: True = the host packs only the CSR by destination and the device derives the rest behind the
         # copy (gmeta_packed_set_finish: 21 MB instead of 37 MB over the bus per C2 batch, 40% less packing);
-        # False = everything packed on the host.  Measured on 1 GPU (C2, round 2): 5.2 vs 4.6 ms per step -- the
-        # device passes compete with the step they run beside -- so the host packer stays the default.
-        self.device_finish = bool(getattr(args, 'device_finish', False))
+        # False = everything packed on the host.  The device passes compete with the step they run beside (1 GPU, C2:
+        # 5.2 vs 4.6 ms per step with the host packer), but with several ranks per box the HOST is what a step waits
+        # for (8 ranks on 32 cores: 11 ms to pack a batch on one thread), so the default follows the cores a rank has.
+        df = getattr(args, 'device_finish', None)
+        if df is None:
+            import os
+            env = os.environ.get("GMETA_B200_DEVICE_FINISH")
+            if env is not None:
+                df = env not in ("", "0")
+            else:
+                df = (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))) < 8
+        self.device_finish = bool(df)
         self.pack_workers = 3          # packer threads of `prefetch` (the callers' three-batch lookahead keeps them busy)
         # host batches: run the step as an updatable CUDA graph prepared one batch ahead (gmeta_step_graph_*)
         self.graph_host_batches = bool(getattr(args, 'graph_host_batches', True))
