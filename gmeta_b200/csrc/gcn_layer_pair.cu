@@ -92,7 +92,10 @@ constexpr int EPI_STAGE_BYTES = TM * EBLK * 4; // one [128 slots][64 columns] fp
 constexpr int BAR_BYTES = 256;
 constexpr int SMEM_FIXED = BAR_BYTES /*barriers*/ + 4 * TM /*slot scale exponents*/ + ACC_COLS * 4 /*bias*/ +
                            RMAX * 8 /*row -> (slot, factor)*/ + RMAX * 4 /*row abs-max*/ + EPI_STAGE_BYTES;
-constexpr int GROUP_TILES = 32;                // caller tiles (<= 4096 rows) one warp of the dedupe pass walks through
+#ifndef GMETA_GROUP_TILES
+#define GMETA_GROUP_TILES 32
+#endif
+constexpr int GROUP_TILES = GMETA_GROUP_TILES;  // caller tiles (<= 4096 rows) one warp of the dedupe pass walks through
 constexpr int GROUP_CAP = 80;                  // compute-tile entries reserved per group (<= 4096/97 + 32 forced closes)
 constexpr int PAIR_FIXED_COST = 320;           // per-pair overhead of the cluster schedule, in output rows (measured: ~17k of ~61k cycles per tile)
 constexpr int SMEM_MAX = 227 * 1024;
