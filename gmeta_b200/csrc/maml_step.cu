@@ -612,6 +612,7 @@ extern "C" int gmeta_maml_step(const gmeta_step_args_t* a_in, void* stream) {
 namespace {
 struct StepGraph {
   cudaGraphExec_t exec = nullptr;
+  cudaEvent_t uploaded = nullptr;     // the executable graph's (updated) launch data is resident on the device
   int launches = 0;
   int updates = 0, instantiations = 0;
 };
@@ -627,6 +628,7 @@ extern "C" void gmeta_step_graph_destroy(void* handle) {
   StepGraph* g = reinterpret_cast<StepGraph*>(handle);
   if (!g) return;
   if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->uploaded) cudaEventDestroy(g->uploaded);
   delete g;
 }
 
@@ -667,12 +669,21 @@ extern "C" int gmeta_step_graph_prepare(void* handle, const gmeta_step_args_t* a
     ++g->instantiations;
   }
   cudaGraphDestroy(graph);
+  // push the (patched) launch data to the device now, on the preparing stream, instead of in front of the launch
+  if (!g->uploaded && cudaEventCreateWithFlags(&g->uploaded, cudaEventDisableTiming) != cudaSuccess) {
+    cudaGetLastError();
+    g->uploaded = nullptr;
+  }
+  if (g->uploaded) {
+    if (cudaGraphUpload(g->exec, s) != cudaSuccess || cudaEventRecord(g->uploaded, s) != cudaSuccess) cudaGetLastError();
+  }
   return GMETA_OK;
 }
 
 extern "C" int gmeta_step_graph_launch(void* handle, void* stream) {
   StepGraph* g = reinterpret_cast<StepGraph*>(handle);
   if (!g || !g->exec) return GMETA_ERR_BAD_ARG;
+  if (g->uploaded && cudaStreamWaitEvent((cudaStream_t)stream, g->uploaded, 0) != cudaSuccess) cudaGetLastError();
   if (cudaGraphLaunch(g->exec, (cudaStream_t)stream) != cudaSuccess) {
     cudaGetLastError();
     return GMETA_ERR_LAUNCH;

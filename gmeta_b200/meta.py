@@ -181,6 +181,27 @@ def _feat_fingerprint(feat):
     return tuple(fp)
 
 
+def _keep_packers_off_the_step_cores():
+    """Initialiser of the packer threads: when a rank has at least 8 host cores, the packers (and the C++ threads they
+    start) stay off the first four cores of the rank's share, which are left to the thread that launches the steps and
+    to the driver's own threads -- a launched step runs measurably slower on the DEVICE when every core is busy packing
+    (DESIGN 4).  GMETA_B200_NO_PIN=1 disables it."""
+    import os
+    if os.environ.get("GMETA_B200_NO_PIN", "") not in ("", "0") or not hasattr(os, "sched_setaffinity"):
+        return
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+        rank = int(os.environ.get("LOCAL_RANK", "0")) % world
+        per = len(cores) // world
+        if per < 8:
+            return
+        mine = cores[rank * per:(rank + 1) * per]
+        os.sched_setaffinity(0, mine[4:])
+    except OSError:
+        pass
+
+
 class _DeviceBatch(object):
     """An uploaded meta-batch: segment plans of both sets + the device int32 buffer holding them."""
     __slots__ = ("T", "max_classes", "ft", "ps_s", "ps_q", "ints", "h2d_bytes", "resident", "ready", "pack_ms", "pending", "graph")
@@ -457,7 +478,7 @@ class Meta(nn.Module):
         if ft.f0 != self.spec.conv[0][0]:
             raise RuntimeError("feature width %d does not match the first GraphConv (%d)" % (ft.f0, self.spec.conv[0][0]))
         if self._pool is None:
-            self._pool = ThreadPoolExecutor(max_workers=self.pack_workers)
+            self._pool = ThreadPoolExecutor(max_workers=self.pack_workers, initializer=_keep_packers_off_the_step_cores)
             self._copy_stream = torch.cuda.Stream(device=dev)
         if self._prefetched is None:
             self._prefetched = []

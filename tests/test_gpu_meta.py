@@ -257,24 +257,35 @@ def test_two_streams_and_graph_replay_equal_the_serial_eager_step():
 
 
 def test_prefetch_pipeline_equals_plain_forward():
-    """Meta.prefetch(next batch) + Meta.forward(batch) (packing and H2D of batch i+1 on a worker thread / copy stream
-    while step i runs) gives exactly the accuracies, losses and weights of plain forward calls; a prefetched batch that
-    is not the one forward() then receives is dropped safely."""
+    """Every way a host batch can reach the step gives exactly the accuracies, losses and weights of plain eager
+    forward calls: the step as an updatable CUDA graph (prepared at the step, or one batch ahead while the previous step
+    runs), Meta.prefetch with a one- or three-batch lookahead (packing and H2D on worker threads / the copy stream),
+    the slim host packing with the device passes behind the copy; a prefetched batch that is not the one forward() then
+    receives is dropped safely."""
     from gmeta_b200.meta import Meta
     ds = H.tiny_dataset('shared')
     rng = np.random.default_rng(12)
-    mbs = [ds.sample_meta_batch(rng) for _ in range(5)]
+    mbs = [ds.sample_meta_batch(rng) for _ in range(7)]
     outs = []
-    for mode in ("plain", "prefetch", "mismatch"):
+    for mode in ("eager", "graph", "prefetch", "lookahead3", "lookahead3+device_finish", "mismatch"):
         torch.manual_seed(9)
         m = Meta(ds.args(), ds.config()).to(U.dev())
+        m.graph_host_batches = mode != "eager"
+        m.device_finish = mode.endswith("device_finish")
         accs = []
         for i, mb in enumerate(mbs):
             if mode == "prefetch" and i + 1 < len(mbs):
                 m.prefetch(*mbs[i + 1], ds.feats)
+            if mode.startswith("lookahead3"):
+                for j in ((1, 2, 3) if i == 0 else (3,)):
+                    if i + j < len(mbs):
+                        m.prefetch(*mbs[i + j], ds.feats)
             if mode == "mismatch":
                 m.prefetch(*mbs[(i + 2) % len(mbs)], ds.feats)         # not the batch that comes next
             accs.append((m(*mb, ds.feats), m.last["loss_q"]))
+            assert m.last["gpu_launches"] > 0
+        if mode.startswith("lookahead3"):
+            assert m._step_graphs is not None                           # the steps ran as graphs prepared ahead
         outs.append((accs, [p.detach().cpu().clone() for p in m.net.parameters()]))
     for o in outs[1:]:
         for (a, la), (b, lb) in zip(o[0], outs[0][0]):

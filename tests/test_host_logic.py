@@ -289,3 +289,29 @@ def test_fast_packing_equals_reference_packing(kind):
                 assert np.array_equal(fast[ps.off[k]:ps.off[k] + n_el], buf[ref.off[k]:ref.off[k] + n_el]), (variant, k)
             for l in range(L):
                 assert ps.act[l]["n"] == ref.act[l]["n"] and ps.act[l]["n_tiles"] == ref.act[l]["n_tiles"]
+
+
+def test_slim_host_pack_writes_the_same_host_segments_as_the_full_packer():
+    """packing.pack_meta_batch_slim packs only what the host alone knows; those segments equal the full packer's and the
+    device-derived ones are laid out behind them at their upper bounds (the device half is tested on the GPU)."""
+    import torch
+    from gmeta_b200 import packing
+    from tests import helpers as H
+    for kind in ('disjoint', 'link', 'shared'):
+        ds = H.tiny_dataset(kind)
+        mb = ds.sample_meta_batch(np.random.default_rng(3), 3)
+        goff = np.concatenate([[0], np.cumsum([f.shape[0] for f in ds.feats])])[:-1]
+        L = ds.h                                   # one GraphConv per hop
+        full, slim = packing.Staging(torch.device("cpu")), packing.Staging(torch.device("cpu"))
+        fs, fq, _ = packing.pack_meta_batch(full, mb, goff, L, _lib.lib())
+        ss, sq, n_host, n_total = packing.pack_meta_batch_slim(slim, mb, goff, L, _lib.lib())
+        a, b = full.host.numpy(), slim.host.numpy()
+        assert n_host < n_total
+        for f, s_ in ((fs, ss), (fq, sq)):
+            assert (f.N, f.E, f.S, f.T, f.n_tiles, f.cps) == (s_.N, s_.E, s_.S, s_.T, s_.n_tiles, s_.cps)
+            for k in packing.HOST_SEGS:
+                n = f.sizes[k]
+                assert s_.off[k] + n <= n_host
+                assert np.array_equal(a[f.off[k]:f.off[k] + n], b[s_.off[k]:s_.off[k] + n]), k
+            for k, cap in s_.cap.items():
+                assert s_.off[k] >= n_host and cap >= f.sizes[k], k

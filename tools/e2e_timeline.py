@@ -90,6 +90,10 @@ def forward_mode(label):
 m.step_device_orig = m.step_device
 forward_mode("graph prepared ahead")
 m.step_device = m.step_device_orig
+m.two_streams = False
+forward_mode("graph prepared ahead, one stream")
+m.two_streams = True
+m.step_device = m.step_device_orig
 m.prepare_ahead = False
 forward_mode("graph prepared at the step")
 m.step_device = m.step_device_orig
