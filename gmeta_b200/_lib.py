@@ -15,6 +15,8 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 MAX_LAYERS = 3
 TILE_ROWS = 128
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, IMPL_TCPAIR = 0, 1, 2, 3
+AGG_GCN, AGG_MEAN, AGG_SUM = 0, 1, 2
+AGGREGATIONS = {"gcn": AGG_GCN, "mean": AGG_MEAN, "sum": AGG_SUM}
 
 i32, i64, f32, f64, vp = C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_void_p
 
@@ -24,7 +26,7 @@ class PackedSet(C.Structure):
                                     "centres_per_subgraph")] + \
                [(n, vp) for n in ("indptr", "indices", "t_indptr", "t_indices", "tile_row0", "tile_nrows",
                                    "tile_task", "task_row_ptr", "task_sub_ptr", "centre_row", "feat_row",
-                                   "labels", "norm", "class_pos", "class_occ", "n_classes")] + \
+                                   "labels", "norm", "norm_dst", "class_pos", "class_occ", "n_classes")] + \
                [("n_act", i32 * MAX_LAYERS), ("n_act_tiles", i32 * MAX_LAYERS)] + \
                [(n, vp * MAX_LAYERS) for n in ("act_rows", "act_task_ptr", "act_tile_row0", "act_tile_nrows",
                                                "act_tile_task", "row_pos")] + \
@@ -35,7 +37,7 @@ class Model(C.Structure):
     _fields_ = [("n_layers", i32), ("f_in", i32 * MAX_LAYERS), ("f_out", i32 * MAX_LAYERS),
                 ("n_out", i32), ("link_pred", i32), ("n_params_padded", i32),
                 ("w_off", i32 * MAX_LAYERS), ("b_off", i32 * MAX_LAYERS), ("wlin_off", i32),
-                ("blin_off", i32)]
+                ("blin_off", i32), ("aggregation", i32)]
 
 
 class StepArgs(C.Structure):
@@ -58,6 +60,12 @@ _SIGNATURES = {
     "gmeta_gcn_layer_fwd_workspace_bytes": (i64, [i32, i64, i32, i32, i32]),
     "gmeta_gcn_layer_fwd_ex": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, i64, i32, i32, vp, i64,
                                          i32, i32, i32, vp, vp, i32, i32, vp, i64, i32, i32, vp, vp, vp, vp]),
+    "gmeta_gcn_layer_fwd_nd": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, i64, i32, i32, vp, i64,
+                                         i32, i32, i32, vp, vp, i32, i32, vp, i64, i32, i32, vp, vp, vp, vp]),
+    "gmeta_aggregate_rows_nd": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, i32, vp]),
+    "gmeta_gcn_layer_wgrad_nd": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp, i64, vp, i64,
+                                           vp, i64, vp]),
+    "gmeta_aggregation_norms": (C.c_int, [vp, i32, i32, vp, vp, vp]),
     "gmeta_layer_plan_bytes": (i64, [i32, i32, i32, i32]),
     "gmeta_layer_plan_build": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]),
     "gmeta_gcn_layer_fwd_ex_workspace_bytes": (i64, [i32, i64, i32, i32, i32, i32, i32, i32]),

@@ -7,6 +7,7 @@
 using namespace gmeta;
 
 namespace gmeta {
+thread_local const float* g_norm_dst = nullptr;
 bool pdl_enabled() {
   static const bool on = [] {
     const char* e = std::getenv("GMETA_B200_PDL");
@@ -46,7 +47,7 @@ extern "C" int gmeta_gcn_layer_fwd_ex(const float* in, int32_t ld_in, const int3
   if (n_tiles == 0) return GMETA_OK;
   GatherSrc g;
   g.in = in; g.in_row_map = in_row_map; g.dst_rows = dst_rows; g.indptr = indptr; g.indices = indices; g.norm = norm;
-  g.ld_in = ld_in; g.f_in = f_in;
+  g.ld_in = ld_in; g.f_in = f_in; g.norm_dst = g_norm_dst;
   cudaStream_t s = (cudaStream_t)stream;
   const int n_copies = w_task_stride == 0 ? 1 : n_tasks;
   const bool ws_aligned = workspace && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0;
@@ -90,6 +91,27 @@ extern "C" int gmeta_gcn_layer_fwd(const float* in, int32_t ld_in, const int32_t
                                 tile_task, n_tiles, n_tasks, W, w_task_stride, ldw, trans_w, bias, b_task_stride, f_in,
                                 f_out, relu, relu_mask, out, ld_out, impl, workspace, workspace_bytes, 0, 0, nullptr,
                                 nullptr, nullptr, stream);
+}
+
+// Same layer with separate scales for a row as a source (`norm`) and as a destination (`norm_dst`):
+//   out[i,:] = act( norm_dst[v] * (sum_u norm[u] * in[map(u),:]) . B + bias )
+// norm_dst == NULL is gmeta_gcn_layer_fwd_ex.  Mean aggregation: norm = 1, norm_dst = 1 / max(in_deg, 1); plain sum: both 1
+// (gmeta_aggregation_norms fills them).  A plan built with gmeta_layer_plan_build holds the SOURCE scales.
+extern "C" int gmeta_gcn_layer_fwd_nd(const float* in, int32_t ld_in, const int32_t* in_row_map,
+                                      const int32_t* dst_rows, const int32_t* indptr, const int32_t* indices,
+                                      const float* norm, const float* norm_dst, const int32_t* tile_row0,
+                                      const int32_t* tile_nrows, const int32_t* tile_task, int32_t n_tiles,
+                                      int32_t n_tasks, const float* W, int64_t w_task_stride, int32_t ldw,
+                                      int32_t trans_w, const float* bias, int64_t b_task_stride, int32_t f_in,
+                                      int32_t f_out, int32_t relu, const float* relu_mask, float* out, int32_t ld_out,
+                                      int32_t impl, void* workspace, int64_t workspace_bytes, int32_t n_rows,
+                                      int32_t n_edges, const float* in_rowmax, float* out_rowmax, const void* plan,
+                                      void* stream) {
+  NormDstScope scope(norm_dst);
+  return gmeta_gcn_layer_fwd_ex(in, ld_in, in_row_map, dst_rows, indptr, indices, norm, tile_row0, tile_nrows, tile_task,
+                                n_tiles, n_tasks, W, w_task_stride, ldw, trans_w, bias, b_task_stride, f_in, f_out, relu,
+                                relu_mask, out, ld_out, impl, workspace, workspace_bytes, n_rows, n_edges, in_rowmax,
+                                out_rowmax, plan, stream);
 }
 
 extern "C" int64_t gmeta_gcn_layer_fwd_workspace_bytes(int32_t n_tasks, int64_t w_task_stride, int32_t f_in,

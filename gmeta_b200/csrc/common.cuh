@@ -17,6 +17,15 @@ inline int check_launch() {
   return cudaGetLastError() == cudaSuccess ? GMETA_OK : GMETA_ERR_LAUNCH;
 }
 
+// Destination-side scales of the layer call being issued on this host thread (NULL = symmetric, the reference's GraphConv):
+// set by the *_nd entry points and by the step driver around the calls they forward to, read where a GatherSrc is filled.
+extern thread_local const float* g_norm_dst;
+struct NormDstScope {
+  const float* saved;
+  explicit NormDstScope(const float* p) : saved(g_norm_dst) { g_norm_dst = p; }
+  ~NormDstScope() { g_norm_dst = saved; }
+};
+
 // ---- programmatic dependent launch (opt-in: GMETA_B200_PDL=1) ----
 // Every kernel of the library can be launched with the programmatic-serialization attribute and begins with
 // pdl_prologue(): "my dependents may be scheduled" (they park at their own wait) and "wait until the kernel before
@@ -59,13 +68,17 @@ struct GatherSrc {
   const int32_t* dst_rows;    // nullable; real row of compact row i (adjacency, norm, mask use the real row)
   const int32_t* indptr;
   const int32_t* indices;
-  const float* norm;
+  const float* norm;          // scale of a row as a SOURCE (norm[u] above)
   int ld_in;
   int f_in;
   // 1: the graph is the identity (row v's only in-neighbour is v, indptr = indices = 0..N, norm = 1, no row map /
   // row list): the pre-summed rows of the pruned meta-step.  Kernels that honour it skip the index loads.
   int identity = 0;
+  // scale of a row as a DESTINATION (the factor in front of the sum); NULL = `norm` (the reference's symmetric
+  // GraphConv normalisation, learner.py:29-49).  Mean aggregation: norm = 1, norm_dst = 1 / in-degree.
+  const float* norm_dst = nullptr;
 };
+__device__ __forceinline__ float dst_norm(const GatherSrc& g, int v) { return (g.norm_dst ? g.norm_dst : g.norm)[v]; }
 
 // One warp aggregates, for each of its rows r = warp, warp+NW, ... < R, the 4 columns
 // [kcol, kcol+4) (kcol = k0 + 4*lane) of M[row0+r] into As[r*lda + 4*lane .. +3]; rows >= nrows
@@ -150,7 +163,7 @@ __device__ __forceinline__ void gather_rows(const GatherSrc& g, int row0, int nr
       }
     }
     if (SCALE_DST && r < nrows) {
-      const float nv = g.norm[g.dst_rows ? g.dst_rows[row0 + r] : row0 + r];
+      const float nv = dst_norm(g, g.dst_rows ? g.dst_rows[row0 + r] : row0 + r);
       acc.x *= nv; acc.y *= nv; acc.z *= nv; acc.w *= nv;
     }
     st_f4(As + r * lda + 4 * lane, acc);

@@ -1431,7 +1431,7 @@ int gcn_layer_fwd_pair(const GatherSrc& g, const int32_t* tile_row0, const int32
   p.in = g.in; p.ld_in = g.ld_in; p.f_in = K; p.in_rowmax = in_rowmax;
   p.mlong = ws.mlong; p.mlong_bound = ws.mlong_bound;
   p.srec = pl.srec; p.row_slot = pl.row_slot; p.hdr = pl.hdr; p.pairs = pl.pairs; p.cl_beg = pl.cl_beg;
-  p.dst_rows = g.dst_rows; p.norm = g.norm;
+  p.dst_rows = g.dst_rows; p.norm = g.norm_dst ? g.norm_dst : g.norm;     // the epilogue scales destinations
   p.w_image = ws.w_image; p.image_task_stride = n_copies > 1 ? 2LL * K * N : 0; p.w_inv_scale = ws.w_inv_scale;
   p.bias = bias; p.b_task_stride = b_task_stride; p.f_out = N; p.relu = relu; p.relu_mask = relu_mask;
   p.out = out; p.ld_out = ld_out; p.out_rowmax = out_rowmax;

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gcn_layer_fwd_simt_kernel(const F
       if (r >= nrows) continue;
       const int orow = row0 + r;                                     // output row (compact or dense)
       const int v = p.g.dst_rows ? p.g.dst_rows[orow] : orow;        // real row: norm and mask
-      const float nv = p.g.norm[v];
+      const float nv = dst_norm(p.g, v);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int c = col0 + 64 * h + 4 * tx;
@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(256) aggregate_rows_kernel(GatherSrc g, int n_
       if (end - beg > AGG_LONG) {
         if (lane == 0) long_rows[atomicAdd(&n_long, 1)] = i;     // the order of this list does not affect any value
       } else {
-        const float nv = scale_dst ? g.norm[v] : 1.f;
+        const float nv = scale_dst ? dst_norm(g, v) : 1.f;
         for (int c0 = 0; c0 < ld_out; c0 += 128) {
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
           agg_accumulate<VEC>(g, beg, end, 32, c0 + 4 * lane, lane, acc);
@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(256) aggregate_rows_kernel(GatherSrc g, int n_
       const int il = long_rows[q];
       const int v = g.dst_rows ? g.dst_rows[il] : il;
       const int beg = pos_ptr ? pos_ptr[il] : g.indptr[v], end = pos_ptr ? pos_ptr[il + 1] : g.indptr[v + 1];
-      const float nv = scale_dst ? g.norm[v] : 1.f;
+      const float nv = scale_dst ? dst_norm(g, v) : 1.f;
       for (int c0 = 0; c0 < ld_out; c0 += 128) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         agg_accumulate<VEC>(g, beg + 32 * warp, end, 256, c0 + 4 * lane, lane, acc);
@@ -561,7 +561,7 @@ int aggregate_rows_impl(const float* in, int32_t ld_in, const int32_t* in_row_ma
   if (!in || !(indptr || pos_indptr) || !indices || !norm || !out) return GMETA_ERR_BAD_ARG;
   GatherSrc g;
   g.in = in; g.in_row_map = in_row_map; g.dst_rows = dst_rows; g.indptr = indptr; g.indices = indices; g.norm = norm;
-  g.ld_in = ld_in; g.f_in = f_in;
+  g.ld_in = ld_in; g.f_in = f_in; g.norm_dst = g_norm_dst;
   const int grid = ceil_div(n_rows, 8) < 16 * kNumSMs ? ceil_div(n_rows, 8) : 16 * kNumSMs;
   if (ld_in % 4 == 0 && f_in % 4 == 0 && aligned16(in))
     launch_pdl(aggregate_rows_kernel<true>, dim3(grid), dim3(256), 0, stream, g, n_rows, scale_dst, out, ld_out, pos_indptr);
@@ -656,6 +656,41 @@ extern "C" int gmeta_aggregate_rows(const float* in, int32_t ld_in, const int32_
                              nullptr, (cudaStream_t)stream);
 }
 
+extern "C" int gmeta_aggregate_rows_nd(const float* in, int32_t ld_in, const int32_t* in_row_map, const int32_t* dst_rows,
+                                       const int32_t* indptr, const int32_t* indices, const float* norm,
+                                       const float* norm_dst, int32_t n_rows, int32_t f_in, int32_t scale_dst, float* out,
+                                       int32_t ld_out, void* stream) {
+  NormDstScope scope(norm_dst);
+  return gmeta_aggregate_rows(in, ld_in, in_row_map, dst_rows, indptr, indices, norm, n_rows, f_in, scale_dst, out, ld_out,
+                              stream);
+}
+
+namespace gmeta {
+namespace {
+__global__ void aggregation_norms_kernel(const int32_t* indptr, int n, int mode, float* norm_src, float* norm_dst) {
+  pdl_prologue();
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+    const int d = max(indptr[v + 1] - indptr[v], 1);
+    float s = 1.f, r = 1.f;
+    if (mode == GMETA_AGG_GCN) s = r = __fdiv_rn(1.0f, __fsqrt_rn((float)d));
+    else if (mode == GMETA_AGG_MEAN) r = __fdiv_rn(1.0f, (float)d);
+    norm_src[v] = s;
+    norm_dst[v] = r;
+  }
+}
+}  // namespace
+}  // namespace gmeta
+
+extern "C" int gmeta_aggregation_norms(const int32_t* indptr, int32_t n_nodes, int32_t mode, float* norm_src,
+                                       float* norm_dst, void* stream) {
+  if (n_nodes < 0 || (n_nodes > 0 && (!indptr || !norm_src || !norm_dst))) return GMETA_ERR_BAD_ARG;
+  if (mode != GMETA_AGG_GCN && mode != GMETA_AGG_MEAN && mode != GMETA_AGG_SUM) return GMETA_ERR_BAD_ARG;
+  if (n_nodes == 0) return GMETA_OK;
+  const int grid = ceil_div(n_nodes, 256) < 8 * kNumSMs ? ceil_div(n_nodes, 256) : 8 * kNumSMs;
+  launch_pdl(aggregation_norms_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, indptr, n_nodes, mode, norm_src, norm_dst);
+  return check_launch();
+}
+
 extern "C" int gmeta_degree_norm(const int32_t* indptr, int32_t n_nodes, float* norm, void* stream) {
   if (n_nodes < 0 || (n_nodes > 0 && (!indptr || !norm))) return GMETA_ERR_BAD_ARG;
   if (n_nodes == 0) return GMETA_OK;
@@ -686,7 +721,7 @@ int gcn_layer_wgrad_impl(const float* in, int32_t ld_in, const int32_t* in_row_m
   if (!aligned16(workspace)) return GMETA_ERR_ALIGN;
   WgradParams p;
   p.g.in = in; p.g.in_row_map = in_row_map; p.g.dst_rows = dst_rows; p.g.indptr = indptr; p.g.indices = indices;
-  p.g.norm = norm; p.g.ld_in = ld_in; p.g.f_in = f_in;
+  p.g.norm = norm; p.g.ld_in = ld_in; p.g.f_in = f_in; p.g.norm_dst = g_norm_dst;
   p.task_row_ptr = task_row_ptr; p.n_tasks = n_tasks; p.dZ = dZ; p.ld_dz = ld_dz; p.f_out = f_out;
   p.n_split = pick_wgrad_split(n_tasks, f_in, f_out);
   if (rows_hint >= 0) {
@@ -741,4 +776,15 @@ extern "C" int gmeta_gcn_layer_wgrad(const float* in, int32_t ld_in, const int32
   return gcn_layer_wgrad_impl(in, ld_in, in_row_map, dst_rows, indptr, indices, norm, task_row_ptr, n_tasks, dZ, ld_dz,
                               f_in, f_out, dW, dw_task_stride, db, db_task_stride, workspace, workspace_bytes, -1,
                               (cudaStream_t)stream, 0);
+}
+
+extern "C" int gmeta_gcn_layer_wgrad_nd(const float* in, int32_t ld_in, const int32_t* in_row_map, const int32_t* dst_rows,
+                                        const int32_t* indptr, const int32_t* indices, const float* norm,
+                                        const float* norm_dst, const int32_t* task_row_ptr, int32_t n_tasks,
+                                        const float* dZ, int32_t ld_dz, int32_t f_in, int32_t f_out, float* dW,
+                                        int64_t dw_task_stride, float* db, int64_t db_task_stride, void* workspace,
+                                        int64_t workspace_bytes, void* stream) {
+  NormDstScope scope(norm_dst);
+  return gmeta_gcn_layer_wgrad(in, ld_in, in_row_map, dst_rows, indptr, indices, norm, task_row_ptr, n_tasks, dZ, ld_dz,
+                               f_in, f_out, dW, dw_task_stride, db, db_task_stride, workspace, workspace_bytes, stream);
 }

@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const 
       const bool live = r < nrows;
       const int oi = row0 + (live ? r : 0);                          // output row (compact or dense)
       const int v = p.g.dst_rows ? p.g.dst_rows[oi] : oi;            // real row: norm and mask
-      const float nv = p.g.norm[v];
+      const float nv = dst_norm(p.g, v);
       const float* mrow = p.relu_mask ? p.relu_mask + (size_t)((p.relu & 2) ? oi : v) * p.ld_out : nullptr;
       lap(t_epi);
       mbar_wait(acc_full(buf), (uint32_t)((ti >> 1) & 1));

@@ -282,6 +282,9 @@ struct Runner {
   int rc = GMETA_OK;
 
   bool ok() const { return rc == GMETA_OK; }
+  // scales of a transposed pass (data gradient): the forward's destination scale acts on the sources and vice versa
+  static const float* t_src(const gmeta_packed_set_t& set) { return set.norm_dst ? set.norm_dst : set.norm; }
+  static const float* t_dst(const gmeta_packed_set_t& set) { return set.norm_dst ? set.norm : nullptr; }
   void run(int code) { if (rc == GMETA_OK) rc = code; }
   void on(cudaStream_t stream, void* scratch) { s = stream; ws = scratch; }
 
@@ -332,8 +335,11 @@ struct Runner {
         float* agg = (&set == &a->spt ? b.agg_spt : b.agg_qry)[l];
         const int ld_agg = l == 0 ? a->ld_feat : b.ld[l - 1];
         if (l > 0)
-          run(gmeta_aggregate_rows(act[l - 1], b.ld[l - 1], set.row_pos[l - 1], set.act_rows[l], set.indptr, set.indices,
-                                   set.norm, set.n_act[l], m.f_in[l], 1, agg, ld_agg, s));
+          {
+            NormDstScope nd(set.norm_dst);
+            run(gmeta_aggregate_rows(act[l - 1], b.ld[l - 1], set.row_pos[l - 1], set.act_rows[l], set.indptr, set.indices,
+                                     set.norm, set.n_act[l], m.f_in[l], 1, agg, ld_agg, s));
+          }
         dense(agg, ld_agg, set.act_tile_row0[l], set.act_tile_nrows[l], set.act_tile_task[l], set.n_act_tiles[l],
               set.n_tasks, w, l, 0, 1, nullptr, act[l], b.ld[l]);
         continue;
@@ -347,18 +353,24 @@ struct Runner {
         const bool is_spt = &set == &a->spt;
         float* const* rmax = is_spt ? b.rmax_spt : b.rmax_qry;
         void* const* plan = is_spt ? b.plan_spt : b.plan_qry;
-        run(gmeta_gcn_layer_fwd_ex(in, ld_in, map, nullptr, set.indptr, set.indices, set.norm, set.tile_row0,
-                                   set.tile_nrows, set.tile_task, set.n_tiles, set.n_tasks, W + m.w_off[l], stride,
-                                   m.f_out[l], 0, W + m.b_off[l], stride, m.f_in[l], m.f_out[l], 1, nullptr, act[l],
-                                   b.ld[l], a->impl, ws, b.layer_ws_bytes, set.n_nodes, set.n_edges,
-                                   l == 0 ? a->feat_rowmax : rmax[(l - 1) & 1], l + 1 < m.n_layers ? rmax[l & 1] : nullptr,
-                                   plan[l == 0 ? 0 : 1], s));
+        {
+          NormDstScope nd(set.norm_dst);
+          run(gmeta_gcn_layer_fwd_ex(in, ld_in, map, nullptr, set.indptr, set.indices, set.norm, set.tile_row0,
+                                     set.tile_nrows, set.tile_task, set.n_tiles, set.n_tasks, W + m.w_off[l], stride,
+                                     m.f_out[l], 0, W + m.b_off[l], stride, m.f_in[l], m.f_out[l], 1, nullptr, act[l],
+                                     b.ld[l], a->impl, ws, b.layer_ws_bytes, set.n_nodes, set.n_edges,
+                                     l == 0 ? a->feat_rowmax : rmax[(l - 1) & 1], l + 1 < m.n_layers ? rmax[l & 1] : nullptr,
+                                     plan[l == 0 ? 0 : 1], s));
+        }
         continue;
       }
-      run(gmeta_gcn_layer_fwd(in, ld_in, map, nullptr, set.indptr, set.indices, set.norm, set.tile_row0, set.tile_nrows,
-                              set.tile_task, set.n_tiles, set.n_tasks, W + m.w_off[l], stride, m.f_out[l], 0,
-                              W + m.b_off[l], stride, m.f_in[l], m.f_out[l], 1, nullptr, act[l], b.ld[l], a->impl, ws,
-                              b.layer_ws_bytes, s));
+      {
+        NormDstScope nd(set.norm_dst);
+        run(gmeta_gcn_layer_fwd(in, ld_in, map, nullptr, set.indptr, set.indices, set.norm, set.tile_row0, set.tile_nrows,
+                                set.tile_task, set.n_tiles, set.n_tasks, W + m.w_off[l], stride, m.f_out[l], 0,
+                                W + m.b_off[l], stride, m.f_in[l], m.f_out[l], 1, nullptr, act[l], b.ld[l], a->impl, ws,
+                                b.layer_ws_bytes, s));
+      }
     }
     const int L = m.n_layers;
     run(gmeta_readout_linear_fwd(act[L - 1], b.ld[L - 1], m.f_out[L - 1], pruned ? set.centre_pos : set.centre_row,
@@ -398,9 +410,12 @@ struct Runner {
                                  b.wgrad_ws, b.wgrad_ws_bytes, set.n_act[l], s, /*identity_graph=*/1));
         if (l > 0) {
           const bool is_spt = &set == &a->spt;
-          run(aggregate_rows_impl(dz[cur], b.ld[l], set.row_pos[l], set.act_rows[l - 1], nullptr,
-                                  (is_spt ? b.aout_idx_spt : b.aout_idx_qry)[l], set.norm, set.n_act[l - 1], m.f_out[l], 1,
-                                  b.dagg, b.ld[l], (is_spt ? b.aout_ptr_spt : b.aout_ptr_qry)[l], s));
+          {
+            NormDstScope nd(t_dst(set));      // transposed pass: the two scale arrays swap roles
+            run(aggregate_rows_impl(dz[cur], b.ld[l], set.row_pos[l], set.act_rows[l - 1], nullptr,
+                                    (is_spt ? b.aout_idx_spt : b.aout_idx_qry)[l], t_src(set), set.n_act[l - 1], m.f_out[l], 1,
+                                    b.dagg, b.ld[l], (is_spt ? b.aout_ptr_spt : b.aout_ptr_qry)[l], s));
+          }
           dense(b.dagg, b.ld[l], set.act_tile_row0[l - 1], set.act_tile_nrows[l - 1], set.act_tile_task[l - 1],
                 set.n_act_tiles[l - 1], set.n_tasks, w, l, 1, 2, act[l - 1], dz[cur ^ 1], b.ld[l - 1]);
           cur ^= 1;
@@ -410,31 +425,40 @@ struct Runner {
       if (sparse) {
         // dW_l = (n_v M_v)^T dZ_l over the active rows: their neighbourhood sums by the chip-wide gather (one warp per
         // row), then the dense contraction -- instead of re-gathering M inside every (row chunk, column block) item
-        run(gmeta_aggregate_rows(in, ld_in, l == 0 ? set.feat_row : nullptr, set.act_rows[l], set.indptr, set.indices,
-                                 set.norm, set.n_act[l], m.f_in[l], 1, b.agg_bwd, ld_in, s));
+        {
+          NormDstScope nd(set.norm_dst);
+          run(gmeta_aggregate_rows(in, ld_in, l == 0 ? set.feat_row : nullptr, set.act_rows[l], set.indptr, set.indices,
+                                   set.norm, set.n_act[l], m.f_in[l], 1, b.agg_bwd, ld_in, s));
+        }
         run(gcn_layer_wgrad_impl(b.agg_bwd, ld_in, nullptr, nullptr, b.iota, b.iota, b.ones, set.act_task_ptr[l],
                                  set.n_tasks, dz[cur], b.ld[l], m.f_in[l], m.f_out[l], gout + m.w_off[l], P,
                                  gout + m.b_off[l], P, b.wgrad_ws, b.wgrad_ws_bytes, set.n_act[l], s,
                                  /*identity_graph=*/1));
       } else {
-        run(gcn_layer_wgrad_impl(in, ld_in, l == 0 ? set.feat_row : nullptr, nullptr, set.indptr, set.indices, set.norm,
-                                 set.task_row_ptr, set.n_tasks, dz[cur], b.ld[l], m.f_in[l], m.f_out[l],
-                                 gout + m.w_off[l], P, gout + m.b_off[l], P, b.wgrad_ws, b.wgrad_ws_bytes, set.n_nodes,
-                                 s, 0));
+        {
+          NormDstScope nd(set.norm_dst);
+          run(gcn_layer_wgrad_impl(in, ld_in, l == 0 ? set.feat_row : nullptr, nullptr, set.indptr, set.indices, set.norm,
+                                   set.task_row_ptr, set.n_tasks, dz[cur], b.ld[l], m.f_in[l], m.f_out[l],
+                                   gout + m.w_off[l], P, gout + m.b_off[l], P, b.wgrad_ws, b.wgrad_ws_bytes, set.n_nodes,
+                                   s, 0));
+        }
       }
       if (l > 0) {
         // data gradient = the forward kernel on the transposed graph with W^T, masked by the
         // ReLU of the layer below (features carry no gradient, so layer 0 stops here).  Sparse:
         // only rows with an out-edge into an active row of layer l are computed, reading the
         // compact dZ_l through row_pos[l] (inactive out-neighbours are dropped).
-        run(gmeta_gcn_layer_fwd(dz[cur], b.ld[l], sparse ? set.row_pos[l] : nullptr,
-                                sparse ? set.act_rows[l - 1] : nullptr, set.t_indptr, set.t_indices, set.norm,
-                                sparse ? set.act_tile_row0[l - 1] : set.tile_row0,
-                                sparse ? set.act_tile_nrows[l - 1] : set.tile_nrows,
-                                sparse ? set.act_tile_task[l - 1] : set.tile_task,
-                                sparse ? set.n_act_tiles[l - 1] : set.n_tiles, set.n_tasks, W + m.w_off[l], stride,
-                                m.f_out[l], 1, nullptr, 0, m.f_out[l], m.f_in[l], 0, act[l - 1], dz[cur ^ 1],
-                                b.ld[l - 1], a->impl, ws, b.layer_ws_bytes, s));
+        {
+          NormDstScope nd(t_dst(set));      // transposed pass: the two scale arrays swap roles
+          run(gmeta_gcn_layer_fwd(dz[cur], b.ld[l], sparse ? set.row_pos[l] : nullptr,
+                                  sparse ? set.act_rows[l - 1] : nullptr, set.t_indptr, set.t_indices, t_src(set),
+                                  sparse ? set.act_tile_row0[l - 1] : set.tile_row0,
+                                  sparse ? set.act_tile_nrows[l - 1] : set.tile_nrows,
+                                  sparse ? set.act_tile_task[l - 1] : set.tile_task,
+                                  sparse ? set.n_act_tiles[l - 1] : set.n_tiles, set.n_tasks, W + m.w_off[l], stride,
+                                  m.f_out[l], 1, nullptr, 0, m.f_out[l], m.f_in[l], 0, act[l - 1], dz[cur ^ 1],
+                                  b.ld[l - 1], a->impl, ws, b.layer_ws_bytes, s));
+        }
         cur ^= 1;
       }
     }
@@ -527,7 +551,8 @@ extern "C" int gmeta_maml_step(const gmeta_step_args_t* a_in, void* stream) {
     const gmeta_packed_set_t& set = side ? qr : sp;
     cudaStream_t st = side ? sq : s;
     void* const* plan = side ? b.plan_qry : b.plan_spt;
-    r.run(gmeta_degree_norm(set.indptr, set.n_nodes, set.norm, st));
+    if (m.aggregation == GMETA_AGG_GCN && !set.norm_dst) r.run(gmeta_degree_norm(set.indptr, set.n_nodes, set.norm, st));
+    else r.run(gmeta_aggregation_norms(set.indptr, set.n_nodes, m.aggregation, set.norm, set.norm_dst, st));
     r.run(gmeta_proto_label_prep(set.labels, set.task_sub_ptr, T, set.class_pos, set.class_occ, set.n_classes, st));
     if (!a->dense_backward && (side == 0 || a->compute_meta_grad || a->pruned_forward))
       for (int l = 0; l < m.n_layers; ++l)   // row -> position maps of the active-row lists (structure only)
@@ -543,8 +568,11 @@ extern "C" int gmeta_maml_step(const gmeta_step_args_t* a_in, void* stream) {
                                      b.aout_count + (side ? b.n_ident : 0), (side ? b.aout_ptr_qry : b.aout_ptr_spt)[l],
                                      (side ? b.aout_idx_qry : b.aout_idx_spt)[l], st));
     if (a->pruned_forward)   // layer-0 sums: features and structure only, once per meta-step
-      r.run(gmeta_aggregate_rows(a->feat_table, a->ld_feat, set.feat_row, set.act_rows[0], set.indptr, set.indices,
-                                 set.norm, set.n_act[0], m.f_in[0], 1, (side ? b.agg_qry : b.agg_spt)[0], a->ld_feat, st));
+      {
+        NormDstScope nd(set.norm_dst);
+        r.run(gmeta_aggregate_rows(a->feat_table, a->ld_feat, set.feat_row, set.act_rows[0], set.indptr, set.indices,
+                                   set.norm, set.n_act[0], m.f_in[0], 1, (side ? b.agg_qry : b.agg_spt)[0], a->ld_feat, st));
+      }
   }
   if (b.n_ident > 0) r.run(fill_identity_graph(b.iota, b.ones, b.n_ident, s));
   if (b.pack.n_seg > 0)

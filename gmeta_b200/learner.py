@@ -30,6 +30,7 @@ class ModelSpec(object):
 
     def __init__(self, config):
         self.link_pred = config[-1][0] == 'LinkPred'                      # learner.py:78-79
+        self.aggregation = _lib.AGG_GCN                                   # the reference's GraphConv; see Classifier
         self.conv = [tuple(p) for n, p in config if n == 'GraphConv']
         lin = [tuple(p) for n, p in config if n == 'Linear']
         if len(lin) != 1 or not 1 <= len(self.conv) <= _lib.MAX_LAYERS:
@@ -69,6 +70,7 @@ class ModelSpec(object):
                 m.wlin_off, m.blin_off = self.offsets[k], self.offsets[k + 1]
             k += 2
         m.n_out, m.link_pred, m.n_params_padded = self.n_out, int(self.link_pred), self.n_params_padded
+        m.aggregation = int(getattr(self, "aggregation", _lib.AGG_GCN))
         return m
 
     def flatten(self, tensors, out=None):
@@ -105,8 +107,9 @@ def tile_table(task_row_ptr):
 class _DeviceGraph(object):
     """Device copy of one PackedSubgraphBatch as a single-task packed set (cached on the batch)."""
 
-    def __init__(self, g, dev):
+    def __init__(self, g, dev, aggregation=_lib.AGG_GCN):
         N = g.n_nodes
+        self.aggregation = aggregation
         trp = np.array([0, N], dtype=np.int32)
         row0, nrows, task = tile_table(trp)
         i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(dev)  # noqa: E731
@@ -118,8 +121,23 @@ class _DeviceGraph(object):
         self.sub_off = torch.as_tensor(np.concatenate([[0], np.cumsum(g.batch_num_nodes)])[:-1]).to(dev)
         self.S = len(g.batch_num_nodes)
         self.task_sub_ptr = i32(np.array([0, self.S]))
+        # norm: scale of a row as a source; norm_dst: as a destination (None = the same array: the reference's
+        # symmetric GraphConv normalisation, learner.py:29-49)
         self.norm = torch.empty(N, dtype=torch.float32, device=dev)
-        _lib.check(_lib.lib().gmeta_degree_norm(_ptr(self.indptr), N, _ptr(self.norm), _stream()), "degree_norm")
+        self.norm_dst = None
+        if aggregation == _lib.AGG_GCN:
+            _lib.check(_lib.lib().gmeta_degree_norm(_ptr(self.indptr), N, _ptr(self.norm), _stream()), "degree_norm")
+        else:
+            self.norm_dst = torch.empty(N, dtype=torch.float32, device=dev)
+            _lib.check(_lib.lib().gmeta_aggregation_norms(_ptr(self.indptr), N, aggregation, _ptr(self.norm),
+                                                          _ptr(self.norm_dst), _stream()), "aggregation_norms")
+
+    def scales(self, transposed):
+        """(source scales, destination scales or None) of a layer call; a data gradient runs on the transposed graph
+        with the two arrays swapped."""
+        if transposed and self.norm_dst is not None:
+            return self.norm_dst, self.norm
+        return self.norm, self.norm_dst
 
 
 def _plan(dg, transposed):
@@ -135,7 +153,7 @@ def _plan(dg, transposed):
         nb = L.gmeta_layer_plan_bytes(dg.n_tiles, 1, dg.N, E)
         buf = torch.empty(nb + 256, dtype=torch.uint8, device=dg.norm.device)
         ptr = (buf.data_ptr() + 255) // 256 * 256
-        _lib.check(L.gmeta_layer_plan_build(_ptr(ip), _ptr(ix), _ptr(dg.norm), None, None, _ptr(dg.tile_row0),
+        _lib.check(L.gmeta_layer_plan_build(_ptr(ip), _ptr(ix), _ptr(dg.scales(transposed)[0]), None, None, _ptr(dg.tile_row0),
                                             _ptr(dg.tile_nrows), _ptr(dg.tile_task), dg.n_tiles, 1, dg.N, E, ptr,
                                             _stream()), "layer_plan_build")
         pl = (buf, ptr)
@@ -165,18 +183,19 @@ def _layer(dg, inp, rmax_in, W, trans_w, ldw, b, fi, fo, relu, mask, out, impl, 
         nb = L.gmeta_gcn_layer_fwd_workspace_bytes(1, 0, fi, fo, impl)
     scratch = torch.empty(max(nb, 16) + 256, dtype=torch.uint8, device=dev)
     sp = (scratch.data_ptr() + 255) // 256 * 256
-    _lib.check(L.gmeta_gcn_layer_fwd_ex(
-        _ptr(inp), inp.shape[1], None, None, _ptr(ip), _ptr(ix), _ptr(dg.norm), _ptr(dg.tile_row0),
+    n_src, n_dst = dg.scales(transposed)
+    _lib.check(L.gmeta_gcn_layer_fwd_nd(
+        _ptr(inp), inp.shape[1], None, None, _ptr(ip), _ptr(ix), _ptr(n_src), _ptr(n_dst), _ptr(dg.tile_row0),
         _ptr(dg.tile_nrows), _ptr(dg.tile_task), dg.n_tiles, 1, _ptr(W), 0, ldw, trans_w, _ptr(b), 0, fi, fo, relu,
         _ptr(mask), _ptr(out), out.shape[1], impl, sp, nb, dg.N, E, _ptr(rmax_in) if use_ex else None,
         _ptr(rmax_out), _plan(dg, transposed) if use_ex else None, _stream()), "gcn_layer_fwd")
     return rmax_out
 
 
-def _device_graph(g, dev):
+def _device_graph(g, dev, aggregation=_lib.AGG_GCN):
     dg = getattr(g, "_gmeta_dev", None)
-    if dg is None or dg.norm.device != dev:
-        dg = _DeviceGraph(g, dev)
+    if dg is None or dg.norm.device != dev or dg.aggregation != aggregation:
+        dg = _DeviceGraph(g, dev, aggregation)
         g._gmeta_dev = dg
     return dg
 
@@ -230,8 +249,8 @@ class _ClassifierFn(torch.autograd.Function):
             inp = x if l == 0 else acts[l - 1]
             nbytes = L.gmeta_gcn_layer_wgrad_workspace_bytes(1, fi, fo)
             wsb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            _lib.check(L.gmeta_gcn_layer_wgrad(
-                _ptr(inp), inp.shape[1], None, None, _ptr(dg.indptr), _ptr(dg.indices), _ptr(dg.norm),
+            _lib.check(L.gmeta_gcn_layer_wgrad_nd(
+                _ptr(inp), inp.shape[1], None, None, _ptr(dg.indptr), _ptr(dg.indices), _ptr(dg.norm), _ptr(dg.norm_dst),
                 _ptr(dg.task_row_ptr), 1, _ptr(dz), dz.shape[1], fi, fo, _ptr(grads[2 * l]), 0,
                 _ptr(grads[2 * l + 1]), 0, _ptr(wsb), nbytes, _stream()), "gcn_layer_wgrad")
             if l > 0:
@@ -245,11 +264,18 @@ class _ClassifierFn(torch.autograd.Function):
 
 
 class Classifier(nn.Module):
-    def __init__(self, config, impl=_lib.IMPL_AUTO):
+    def __init__(self, config, impl=_lib.IMPL_AUTO, aggregation="gcn"):
+        """`aggregation`: "gcn" (the reference's symmetric-normalised GraphConv, the default and the only mode the
+        reference has), "mean" (GraphSAGE-style mean over the in-neighbours) or "sum" -- the latter two have no
+        reference counterpart (parity is against the oracle's restatement only)."""
         super(Classifier, self).__init__()
         self.vars = nn.ParameterList()
         self.config = config
         self.spec = ModelSpec(config)
+        if aggregation not in _lib.AGGREGATIONS:
+            raise ValueError("aggregation must be one of %s" % sorted(_lib.AGGREGATIONS))
+        self.aggregation = aggregation
+        self.spec.aggregation = _lib.AGGREGATIONS[aggregation]
         self.LinkPred_mode = self.spec.link_pred
         self.impl = impl
         for name, param in config:                                      # learner.py:81-97
@@ -272,7 +298,7 @@ class Classifier(nn.Module):
         _lib.lib()
         dev = torch.device('cuda', torch.cuda.current_device())
         h = torch.as_tensor(features).float().to(dev)                    # learner.py:144-145
-        dg = _device_graph(g, dev)
+        dg = _device_graph(g, dev, self.spec.aggregation)
         to_fetch = torch.as_tensor(to_fetch).to(dev).long()
         if self.LinkPred_mode:                                           # learner.py:165-168
             centre = torch.stack((to_fetch[:, 0] + dg.sub_off, to_fetch[:, 1] + dg.sub_off), 1)

@@ -267,7 +267,10 @@ class Meta(nn.Module):
         # rows are read out, learner.py:166-170); False: every row of every layer, like the reference.
         self.pruned_forward = bool(getattr(args, 'pruned_forward', not self.dense_backward))
 
-        self.net = Classifier(config, impl=self.impl)
+        # neighbourhood aggregation: "gcn" = the reference's GraphConv (default); "mean" / "sum" have no reference
+        # counterpart (args.aggregation, train.py --aggregation)
+        self.aggregation = str(getattr(args, 'aggregation', 'gcn'))
+        self.net = Classifier(config, impl=self.impl, aggregation=self.aggregation)
         self.net = self.net.to(device)
         self.spec = self.net.spec
         self.meta_optim = FusedAdam(self.spec.n_params_padded, self.meta_lr)
@@ -364,6 +367,8 @@ class Meta(nn.Module):
         for k in packing._SEGS:
             setattr(cs, k, base_ptr + 4 * ps.off[k])
         cs.norm = self._buf(tag + "norm", (ps.N,), torch.float32, dev).data_ptr()
+        if self.spec.aggregation != _lib.AGG_GCN:      # separate destination-side scales (mean / sum aggregation)
+            cs.norm_dst = self._buf(tag + "norm_dst", (ps.N,), torch.float32, dev).data_ptr()
         cs.class_pos = self._buf(tag + "cpos", (ps.S,), torch.int32, dev).data_ptr()
         cs.class_occ = self._buf(tag + "cocc", (ps.S,), torch.int32, dev).data_ptr()
         cs.n_classes = self._buf(tag + "ncls", (ps.T,), torch.int32, dev).data_ptr()

@@ -41,6 +41,13 @@ extern "C" {
 #define GMETA_TILE_ROWS 128
 #define GMETA_MAX_LAYERS 3          /* h in {1,2,3}: subgraph_data_processing.py:300-311 */
 
+/* neighbourhood aggregation of a GCN layer: out_v = r_v * sum_u s_u x_u.  GCN: s = r = clamp(in_deg,1)^-1/2 -- the
+ * reference's GraphConv (learner.py:29-49) and the only mode it has; MEAN: s = 1, r = 1/clamp(in_deg,1) (GraphSAGE-style
+ * mean, named by north_star, no reference counterpart); SUM: s = r = 1. */
+#define GMETA_AGG_GCN 0
+#define GMETA_AGG_MEAN 1
+#define GMETA_AGG_SUM 2
+
 #define GMETA_IMPL_AUTO 0
 #define GMETA_IMPL_SIMT 1           /* fp32 FFMA, any shape */
 #define GMETA_IMPL_TCGEN05 2        /* tcgen05.mma kind::tf32, 3xTF32 error-compensated, weights streamed per tile */
@@ -71,7 +78,8 @@ typedef struct gmeta_packed_set {
   const int32_t* centre_row;     /* [S * centres_per_subgraph] packed row of the centre node(s) */
   const int32_t* feat_row;       /* [N] row of the device feature table feeding layer 1, or NULL */
   const int32_t* labels;         /* [S] raw class labels */
-  float* norm;                   /* [N] clamp(in_deg,1)^-1/2, filled by gmeta_degree_norm */
+  float* norm;                   /* [N] scale of a row as a source; GCN: clamp(in_deg,1)^-1/2 (filled by the step) */
+  float* norm_dst;               /* [N] scale of a row as a destination, or NULL = norm (required when model.aggregation != GCN) */
   int32_t* class_pos;            /* [S] rank of the label among the task's sorted unique labels */
   int32_t* class_occ;            /* [S] how many earlier subgraphs of the task share the label */
   int32_t* n_classes;            /* [T] */
@@ -106,11 +114,16 @@ typedef struct gmeta_model {
   int32_t b_off[GMETA_MAX_LAYERS];
   int32_t wlin_off;
   int32_t blin_off;
+  int32_t aggregation;           /* GMETA_AGG_* (0 = the reference's symmetric normalisation) */
 } gmeta_model_t;
 
 /* norm[v] = 1/sqrt(max(indptr[v+1]-indptr[v], 1)), IEEE-rounded.
  * Replaces learner.py:29 `torch.pow(graph.in_degrees().float().clamp(min=1), -0.5)`. */
 int gmeta_degree_norm(const int32_t* indptr, int32_t n_nodes, float* norm, void* stream);
+/* Source / destination scales of an aggregation mode (GMETA_AGG_*) from the in-degrees; mode GCN writes the
+ * gmeta_degree_norm values into both arrays. */
+int gmeta_aggregation_norms(const int32_t* indptr, int32_t n_nodes, int32_t mode, float* norm_src, float* norm_dst,
+                            void* stream);
 
 /* One fused GCN layer over a packed set (replaces GraphConv.forward, learner.py:25-56, and the
  * features gather of meta.py:119-120 when in_row_map != NULL):
@@ -168,6 +181,21 @@ int gmeta_gcn_layer_fwd_ex(const float* in, int32_t ld_in, const int32_t* in_row
                            void* workspace, int64_t workspace_bytes,
                            int32_t n_rows, int32_t n_edges, const float* in_rowmax, float* out_rowmax,
                            const void* plan, void* stream);
+/* gmeta_gcn_layer_fwd_ex with separate scales for a row as a source (`norm`) and as a destination (`norm_dst`):
+ *   out[i,:] = act( norm_dst[v] * (sum_u norm[u] * in[map(u),:]) . B + bias );  norm_dst == NULL: norm (the _ex call).
+ * Mean / sum aggregation (GMETA_AGG_*; arrays from gmeta_aggregation_norms).  The data gradient of such a layer is the
+ * same call on the transposed graph with the two arrays SWAPPED; a plan holds the source scales. */
+int gmeta_gcn_layer_fwd_nd(const float* in, int32_t ld_in, const int32_t* in_row_map,
+                           const int32_t* dst_rows, const int32_t* indptr, const int32_t* indices, const float* norm,
+                           const float* norm_dst, const int32_t* tile_row0, const int32_t* tile_nrows,
+                           const int32_t* tile_task, int32_t n_tiles, int32_t n_tasks,
+                           const float* W, int64_t w_task_stride, int32_t ldw, int32_t trans_w,
+                           const float* bias, int64_t b_task_stride,
+                           int32_t f_in, int32_t f_out, int32_t relu, const float* relu_mask,
+                           float* out, int32_t ld_out, int32_t impl,
+                           void* workspace, int64_t workspace_bytes,
+                           int32_t n_rows, int32_t n_edges, const float* in_rowmax, float* out_rowmax,
+                           const void* plan, void* stream);
 int64_t gmeta_gcn_layer_fwd_ex_workspace_bytes(int32_t n_tasks, int64_t w_task_stride, int32_t n_tiles,
                                                int32_t n_rows, int32_t n_edges, int32_t f_in,
                                                int32_t f_out, int32_t impl);
@@ -211,6 +239,13 @@ int gmeta_gcn_layer_wgrad(const float* in, int32_t ld_in, const int32_t* in_row_
                           const float* dZ, int32_t ld_dz, int32_t f_in, int32_t f_out,
                           float* dW, int64_t dw_task_stride, float* db, int64_t db_task_stride,
                           void* workspace, int64_t workspace_bytes, void* stream);
+/* same with a separate destination scale: dW[t] = sum_v (norm_dst[v] M_v)^T dZ_v  (norm_dst == NULL: norm) */
+int gmeta_gcn_layer_wgrad_nd(const float* in, int32_t ld_in, const int32_t* in_row_map,
+                             const int32_t* dst_rows, const int32_t* indptr, const int32_t* indices, const float* norm,
+                             const float* norm_dst, const int32_t* task_row_ptr, int32_t n_tasks,
+                             const float* dZ, int32_t ld_dz, int32_t f_in, int32_t f_out,
+                             float* dW, int64_t dw_task_stride, float* db, int64_t db_task_stride,
+                             void* workspace, int64_t workspace_bytes, void* stream);
 
 /* HOST helper (no device work, no stream): packs the per-task CSR arrays of one set of a meta-batch into the
  * packed-set layout -- out_indptr[node_off[t] + 1 + i] = indptr[t][1 + i] + edge_off[t],
@@ -243,6 +278,10 @@ int64_t gmeta_host_active_in_neighbours(const int32_t* indptr, const int32_t* in
 int gmeta_aggregate_rows(const float* in, int32_t ld_in, const int32_t* in_row_map, const int32_t* dst_rows,
                          const int32_t* indptr, const int32_t* indices, const float* norm, int32_t n_rows,
                          int32_t f_in, int32_t scale_dst, float* out, int32_t ld_out, void* stream);
+/* same with a separate destination scale (used when scale_dst != 0; norm_dst == NULL: norm) */
+int gmeta_aggregate_rows_nd(const float* in, int32_t ld_in, const int32_t* in_row_map, const int32_t* dst_rows,
+                            const int32_t* indptr, const int32_t* indices, const float* norm, const float* norm_dst,
+                            int32_t n_rows, int32_t f_in, int32_t scale_dst, float* out, int32_t ld_out, void* stream);
 
 /* Centre-row readout + linear head (learner.py:159-175):
  *   r_s = H[centre_row[s]]   (link_pred: H[centre_row[2s]] || H[centre_row[2s+1]])

@@ -82,8 +82,21 @@ class OGraph(object):
         return out.index_add(0, self.dst, h[self.src])
 
 
-def gcn_layer(g, feat, weight, bias, in_feats, out_feats, relu=True, fast=False):
-    """ReLU(norm * A (norm * feat) W + b), norm = clamp(in_deg,1)^-1/2 (learner.py:25-56)."""
+def gcn_layer(g, feat, weight, bias, in_feats, out_feats, relu=True, fast=False, aggregation="gcn"):
+    """ReLU(norm * A (norm * feat) W + b), norm = clamp(in_deg,1)^-1/2 (learner.py:25-56).
+
+    `aggregation` other than "gcn" is NOT in the reference (its GraphConv has the symmetric normalisation only): "mean"
+    = ReLU(D^-1 A feat W + b), "sum" = ReLU(A feat W + b), restated from their textbook definitions -- PARITY UNPINNED
+    for these two modes (nothing under /root/reference computes them)."""
+    if aggregation != "gcn":
+        deg = g.in_degrees().float().clamp(min=1)
+        rst = torch.matmul(g.aggregate_sum(feat, fast), weight)
+        if aggregation == "mean":
+            rst = rst * (1.0 / deg).reshape(-1, 1)
+        elif aggregation != "sum":
+            raise ValueError(aggregation)
+        rst = rst + bias
+        return F.relu(rst) if relu else rst
     norm = torch.pow(g.in_degrees().float().clamp(min=1), -0.5)       # :29
     norm = norm.reshape(norm.shape + (1,) * (feat.dim() - 1))          # :30-31
     feat = feat * norm                                                 # :32
@@ -119,7 +132,7 @@ def init_params(config):
     return [p.requires_grad_(True) for p in out]
 
 
-def classifier_forward(config, vars, g, to_fetch, features, fast=False):
+def classifier_forward(config, vars, g, to_fetch, features, fast=False, aggregation="gcn"):
     """Classifier.forward (learner.py:134-194): h GraphConv layers over the whole batched
     graph, centre-row gather (pair concat in LinkPred mode), linear head."""
     lp = is_link_pred(config)
@@ -129,7 +142,7 @@ def classifier_forward(config, vars, g, to_fetch, features, fast=False):
     seen = 0
     for name, param in config:
         if name == 'GraphConv':
-            h = gcn_layer(g, h, vars[idx], vars[idx + 1], param[0], param[1], True, fast)
+            h = gcn_layer(g, h, vars[idx], vars[idx + 1], param[0], param[1], True, fast, aggregation)
             idx += 2
             seen += 1
             if seen == n_conv:                                         # :159-170
@@ -203,13 +216,14 @@ class OracleMeta(object):
         self.update_step_test = args.update_step_test
         self.config = config
         self.fast = fast
+        self.aggregation = str(getattr(args, "aggregation", "gcn"))      # not in the reference; see gcn_layer
         self.vars = params if params is not None else init_params(config)
         self.meta_optim = torch.optim.Adam(self.vars, lr=self.meta_lr)   # meta.py:97
         self.last_loss_q = None
         self.last_losses_q = None
 
     def _net(self, g, c, feat, vars):
-        return classifier_forward(self.config, vars, g, c, feat, self.fast)
+        return classifier_forward(self.config, vars, g, c, feat, self.fast, getattr(self, "aggregation", "gcn"))
 
     def _inner(self, vars0, x_spt, y_spt, x_qry, y_qry, c_spt, c_qry, feat_spt, feat_qry, steps,
                losses_q, corrects):

@@ -153,7 +153,7 @@ def test_cli_flags_and_defaults_match_the_reference():
                 sample_nodes=1000)                                   # train.py:153-177
     for k, v in want.items():
         assert got[k] == v, k
-    assert set(got) - set(want) == {"eval_batch", "device_extract"}
+    assert set(got) - set(want) == {"eval_batch", "device_extract", "aggregation"}
     a = train.parse(["--data_dir", "x/", "--task_setup", "Shared", "--link_pred", "True", "--hid", "128"])   # prefixes
     assert a.link_pred_mode == 'True' and a.hidden_dim == 128
     cfg = train.build_config([np.zeros((4, 5))], a, 2)                # train.py:67-75

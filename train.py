@@ -212,6 +212,9 @@ def parse(argv=None):
     argparser.add_argument('--device_extract', type=str, default='False',
                            help="'True': h-hop subgraphs are extracted on the GPU (the host ships centre ids only); "
                                 "the sampling cap then uses the device sampler instead of numpy's")
+    argparser.add_argument('--aggregation', type=str, default='gcn',
+                           help="not in the reference: neighbourhood aggregation of the GraphConv layers -- 'gcn' (the "
+                                "reference's symmetric normalisation), 'mean' or 'sum'")
     return argparser.parse_args(argv)
 
 
