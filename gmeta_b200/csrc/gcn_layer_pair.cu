@@ -932,13 +932,16 @@ __global__ void row_absmax_kernel(const float* __restrict__ x, int ld, int n_row
 template <int VEC>
 __device__ __forceinline__ void hub_accumulate(const float* __restrict__ in, int ld_in, const float* __restrict__ in_rowmax,
                                                const int* __restrict__ src, const float* __restrict__ nrm, int n,
-                                               int lane, float (&acc)[VEC], float& bacc) {
-  // records [0, n) of one hub (n a multiple of 4), 32 at a time; lane covers columns [lane*VEC, lane*VEC + VEC)
+                                               int lane, float (&acc)[VEC], float& bacc, bool pre = false, int s_pre = 0,
+                                               float n_pre = 0.f) {
+  // records [0, n) of one hub (n a multiple of 4), 32 at a time; lane covers columns [lane*VEC, lane*VEC + VEC).
+  // `pre`: the first block's record of this lane (source, norm) was fetched ahead by the caller.
   for (int b = 0; b < n; b += 32) {
     const int idx = b + lane;
     int s_l = 0;
     float n_l = 0.f;
-    if (idx < n) { s_l = src[idx]; n_l = nrm[idx]; }
+    if (b == 0 && pre) { s_l = s_pre; n_l = n_pre; }
+    else if (idx < n) { s_l = src[idx]; n_l = nrm[idx]; }
     if (n_l != 0.f) bacc += n_l * in_rowmax[s_l];
     const int cnt = n - b < 32 ? n - b : 32;
     for (int j0 = 0; j0 < cnt; j0 += 8) {
@@ -986,14 +989,34 @@ __global__ void __launch_bounds__(256) hub_prepass_kernel(const float* __restric
   if (blockIdx.x >= HUB_BIG_CTAS) {
     const int n_hub = hdr[0];
     const int nw = (gridDim.x - HUB_BIG_CTAS) * 8;
-    for (int slot = (blockIdx.x - HUB_BIG_CTAS) * 8 + warp; slot < n_hub; slot += nw) {
-      const int n = (hub_deg[slot] + 3) & ~3;
+    // A small hub is a chain of three dependent loads (degree / first record -> its records -> the rows) for 3..128
+    // records of work, so the chain is started ahead: (degree, first record) two hubs ahead, the first 32 records one
+    // hub ahead -- only the row loads of the current hub are waited for.
+    const int slot0 = (blockIdx.x - HUB_BIG_CTAS) * 8 + warp;
+    auto meta = [&](int slot, int& n, int& beg) {
+      n = 0; beg = 0;
+      if (slot < n_hub) { n = (hub_deg[slot] + 3) & ~3; beg = hub_beg[slot]; }
+    };
+    auto first_records = [&](int n, int beg, int& s_l, float& n_l) {
+      s_l = 0; n_l = 0.f;
+      if (n <= HUB_BIG && lane < n) { s_l = hub_src[beg + lane]; n_l = hub_nrm[beg + lane]; }
+    };
+    int n1, beg1, n2, beg2, s1;
+    float w1;
+    meta(slot0, n1, beg1);
+    meta(slot0 + nw, n2, beg2);
+    first_records(n1, beg1, s1, w1);
+    for (int slot = slot0; slot < n_hub; slot += nw) {
+      const int n = n1, beg = beg1, s_cur = s1;
+      const float w_cur = w1;
+      n1 = n2; beg1 = beg2;
+      first_records(n1, beg1, s1, w1);
+      meta(slot + 2 * nw, n2, beg2);
       if (n > HUB_BIG) continue;
-      const int beg = hub_beg[slot];
       float acc[VEC], bacc = 0.f;
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
-      hub_accumulate<VEC>(in, ld_in, in_rowmax, hub_src + beg, hub_nrm + beg, n, lane, acc, bacc);
+      hub_accumulate<VEC>(in, ld_in, in_rowmax, hub_src + beg, hub_nrm + beg, n, lane, acc, bacc, true, s_cur, w_cur);
       VecLd<VEC>::st(mlong + (size_t)slot * K + lane * VEC, acc);
 #pragma unroll
       for (int o = 16; o; o >>= 1) bacc += __shfl_xor_sync(0xffffffffu, bacc, o);

@@ -294,6 +294,41 @@ def test_prefetch_pipeline_equals_plain_forward():
             assert torch.equal(p, q)
 
 
+def test_step_graph_survives_topology_changes():
+    """Host batches whose launch topology differs from step to step (task counts 3 / 1 / 2: a different number of tiles,
+    split and unsplit weight gradients, empty launches dropped) go through the updatable step graph -- updated in place
+    when the topology allows, rebuilt otherwise -- and give exactly the eager results."""
+    import ctypes as C
+    from gmeta_b200.meta import Meta
+    ds = H.tiny_dataset('disjoint')
+    rng = np.random.default_rng(21)
+    mbs = [ds.sample_meta_batch(rng, t) for t in (3, 1, 2, 3, 3, 1, 2, 2)]
+    outs = []
+    for graphs in (False, True):
+        torch.manual_seed(9)
+        m = Meta(ds.args(), ds.config()).to(U.dev())
+        m.graph_host_batches = graphs
+        accs = []
+        for i, mb in enumerate(mbs):
+            m.global_task_num = len(mb[0])
+            for j in ((1, 2) if i == 0 else (2,)):
+                if graphs and i + j < len(mbs):
+                    m.prefetch(*mbs[i + j], ds.feats)
+            accs.append((m(*mb, ds.feats), m.last["loss_q"]))
+        outs.append((accs, [p.detach().cpu().clone() for p in m.net.parameters()]))
+        if graphs:
+            ups = inst = 0
+            for h in m._step_graphs:
+                u, k = C.c_int32(), C.c_int32()
+                _lib.check(_lib.lib().gmeta_step_graph_stats(h, C.byref(u), C.byref(k)))
+                ups, inst = ups + u.value, inst + k.value
+            assert ups + inst >= len(mbs) and inst >= 1
+    for (a, la), (b, lb) in zip(outs[1][0], outs[0][0]):
+        assert np.array_equal(a, b) and la == lb
+    for p, q in zip(outs[1][1], outs[0][1]):
+        assert torch.equal(p, q)
+
+
 def test_parameters_alias_the_flat_buffer_and_survive_deepcopy():
     """The net's parameters are views of the flat theta buffer the kernels update in place; deepcopy (train.py:87,127)
     and in-place edits keep working, and a copy trains independently of the original."""
