@@ -145,7 +145,7 @@ class ClockSampler(threading.Thread):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one full-layer launch (three kernels) per packed-row count N of the
 # seeded query set it was captured on (profiles/r02_layer_pair_full.md)
-PROFILE_TRAFFIC = {1284403: 2.644922e9}
+PROFILE_TRAFFIC = {1284403: 2.641477e9}
 
 TIE_GAP = 2e-4   # twice the stated logit tolerance (north_star: logits within 1e-4, identical argmax)
 

@@ -86,7 +86,10 @@ constexpr int MAX_STAGES = 6;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_COLS = 256;
 constexpr int PRE = 2;                         // in-neighbours per row the fused kernel gathers itself
-constexpr int RMAX = 1024;                     // output rows per compute tile (<= 128 distinct slots among them)
+#ifndef GMETA_RMAX
+#define GMETA_RMAX 1024
+#endif
+constexpr int RMAX = GMETA_RMAX;                     // output rows per compute tile (<= 128 distinct slots among them)
 constexpr int EBLK = 64;                       // accumulator columns per expansion block
 constexpr int EPI_STAGE_BYTES = TM * EBLK * 4; // one [128 slots][64 columns] fp32 block (16-byte units XOR-swizzled by slot)
 constexpr int BAR_BYTES = 256;
@@ -97,9 +100,15 @@ constexpr int SMEM_FIXED = BAR_BYTES /*barriers*/ + 4 * TM /*slot scale exponent
 #endif
 constexpr int GROUP_TILES = GMETA_GROUP_TILES;  // caller tiles (<= 4096 rows) one warp of the dedupe pass walks through
 constexpr int GROUP_CAP = 80;                  // compute-tile entries reserved per group (<= 4096/97 + 32 forced closes)
-constexpr int PAIR_FIXED_COST = 320;           // per-pair overhead of the cluster schedule, in output rows (measured: ~17k of ~61k cycles per tile)
+#ifndef GMETA_PAIR_FIXED_COST
+#define GMETA_PAIR_FIXED_COST 320
+#endif
+constexpr int PAIR_FIXED_COST = GMETA_PAIR_FIXED_COST;           // per-pair overhead of the cluster schedule, in output rows (measured: ~17k of ~61k cycles per tile)
 constexpr int SMEM_MAX = 227 * 1024;
-constexpr int HUB_BIG = 128;                    // hubs with more (padded) edge records are aggregated by a whole CTA
+#ifndef GMETA_HUB_BIG
+#define GMETA_HUB_BIG 64        // swept on the C2 query set (with GMETA_EXPAND_UNR 1): 32: 0.635 ms, 64: 0.605, 96: 0.612, 128: 0.620
+#endif
+constexpr int HUB_BIG = GMETA_HUB_BIG;                    // hubs with more (padded) edge records are aggregated by a whole CTA
 constexpr int PT_MAXT = 2048;                  // tasks the pair-table kernel handles
 constexpr int SCALE_TARGET = 13;               // scaled bound in [2^13, 2^14): 4x below the FP16 maximum
 constexpr int SCALE_CLAMP = 100;
@@ -375,7 +384,10 @@ struct ExpandArgs {
 };
 template <bool MASK, bool RMX>
 __device__ __forceinline__ void expand_block(const ExpandArgs& a, int ew, int lane) {
-  constexpr int UNR = 2;
+#ifndef GMETA_EXPAND_UNR
+#define GMETA_EXPAND_UNR 1      // rows per octet and iteration (swept on the C2 query set: 1: 0.606 ms, 2: 0.626, 4: 0.669 per launch)
+#endif
+  constexpr int UNR = GMETA_EXPAND_UNR;
   constexpr int RSTEP = N_EPI_WARPS * 4;       // rows the epilogue warps cover per pass
   const int oct = lane >> 3, u = lane & 7;
   const int c0 = a.blk * EBLK + 4 * u;
@@ -969,7 +981,10 @@ __device__ __forceinline__ void hub_accumulate(const float* __restrict__ in, int
 // records -- warp w sums the 32-record blocks w, w+8, ..., the partials are added in warp order; the other
 // CTAs: one warp per smaller hub.  The big hubs are scheduled first (launch order) and the small ones fill in
 // behind them, so the launch has one tail instead of two.  (Interleaving the two kinds was measured slower.)
-constexpr int HUB_BIG_CTAS = 3 * kNumSMs;
+#ifndef GMETA_HUB_BIG_CTAS
+#define GMETA_HUB_BIG_CTAS 3
+#endif
+constexpr int HUB_BIG_CTAS = GMETA_HUB_BIG_CTAS * kNumSMs;
 constexpr int HUB_SMALL_CTAS = 8 * kNumSMs;
 template <int VEC>
 __global__ void __launch_bounds__(256) hub_prepass_kernel(const float* __restrict__ in, int ld_in,
