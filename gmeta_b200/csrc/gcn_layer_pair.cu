@@ -39,14 +39,15 @@
 //     every input row still read once -- the same arithmetic per row as without the sharing, so
 //     results are bit-identical to the undeduplicated kernel.
 //
-// Warp roles per CTA (640 threads; register budgets re-balanced per warpgroup with setmaxnreg): warps 0..7
-// gather producers (a lane quad owns two rows, 32-float K chunks, the next chunk's segments requested before
+// Warp roles per CTA (896 threads = 28 warps; register budgets re-balanced per warpgroup with setmaxnreg: 112 / 24 / 64):
+// warps 0..7 gather producers (a lane quad owns two slots, 32-float K chunks, the next chunk's segments requested before
 // the current one is reduced: fp32 sum -> scaled FP16 hi/lo -> 64B-swizzled K-major operand stage), warp 12
 // weight loader (cp.async.bulk of the pre-split, pre-swizzled image), warp 13 MMA issuer (leader CTA only; one
-// thread), warps 8..11 and 16..19 epilogue: per 64-column block the accumulators of the 128 slots go
-// tcgen05.ld -> swizzled shared-memory block (the next block's load in flight), then all eight warps expand
-// it to the tile's output rows -- a lane octet per row, 128 contiguous bytes per store: * norm * 2^-e + bias,
-// ReLU / mask, row abs-max for the next layer.  Hand-offs are mbarriers waited on with the hardware
+// thread), warps 8..11 and 16..27 epilogue (sixteen warps): per 64-column block the accumulators of the 128 slots go
+// tcgen05.ld -> swizzled shared-memory block, then all sixteen warps expand it to the tile's output rows -- a lane
+// octet per row, one row per iteration, 128 contiguous bytes per streaming store: * norm * 2^-e + bias, ReLU / mask,
+// row abs-max for the next layer.  The launch before this kernel (hub pre-pass) and this one are chained with
+// programmatic dependent launch: everything up to the first global read runs under the pre-pass tail.  Hand-offs are mbarriers waited on with the hardware
 // suspend hint; the peer CTA signals the leader's barriers through the cluster address space, the MMA thread
 // releases operand stages / accumulators in both CTAs with multicast commits.  Hub rows are summed beforehand
 // by hub_prepass_kernel (whole chip, one warp per small hub, one CTA per big hub).
