@@ -68,7 +68,7 @@ constexpr int A_HALF_BYTES = TM * 64;          // 8 KB: hi (or lo) operand tile 
 constexpr int STAGE_BYTES = 2 * A_HALF_BYTES;  // 16 KB
 // warp roles (register budgets are re-balanced per warpgroup with setmaxnreg)
 constexpr int N_PROD_WARPS = 8;                // warps 0..7   gather producers
-constexpr int WARP_EPI_B0 = 8;                 // warps 8..11  epilogue (first four of sixteen)
+// warps 8..11: epilogue (first four of sixteen)
 constexpr int WARP_LOAD = 12;                  // warp 12      weight loader (+ TMEM allocation)
 constexpr int WARP_MMA = 13;                   // warp 13      MMA issuer (14, 15 idle)
 constexpr int WARP_EPI0 = 16;                  // warps 16..27 epilogue as well (the expansion is latency-bound: 16 warps)
@@ -243,25 +243,10 @@ struct PairParams {
   long long* prof;               // optional [gridDim.x][16] cycle counters per role (debug), or NULL
 };
 
-struct F8 { float v[8]; };
-__device__ __forceinline__ F8 ld_f8(const float* p) {      // 256-bit global load (32-byte aligned)
-  F8 r;
-  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
-               : "l"(p));
-  return r;
-}
 __device__ __forceinline__ void st_f8(float* p, const float (&v)[8]) {   // 256-bit global store: one full sector per lane
   asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
 }
-__device__ __forceinline__ F8 zero_f8() {
-  F8 r;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) r.v[j] = 0.f;
-  return r;
-}
-
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
