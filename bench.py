@@ -556,6 +556,7 @@ def main():
         steps, warmup = max(1, args.steps), max(0, args.warmup)     # a step = n_tasks tasks of the workload (bounded sample)
         cb = cpu_arm(ds, batch, n_tasks, steps, warmup)
         cfg = workload_desc(ds, args.tasks or ds.task_num)           # the workload sampled FROM: same string as our arm's
+        cfg["parallelism"] = "task-sharded x%d" % args.gpus          # (the CPU arm itself runs on rank 0's host cores)
         emit({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
               "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
               "ms_per_step": cb["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -727,11 +728,12 @@ def main():
     cfg = workload_desc(ds, tasks)
     cfg.update({"parallelism": "task-sharded x%d" % world, "l2_policy": "inputs larger than L2 (packed meta-batch "
                 "activations %.1f GB per step; %d distinct meta-batches cycled)"
-                % (4e-9 * m.last["n_nodes"][1] * ds.hidden_dim * 2, len(batches)),
-                "packed_nodes_spt_qry": m.last["n_nodes"], "packed_edges_spt_qry": m.last["n_edges"],
+                % (4e-9 * m.last["n_nodes"][1] * ds.hidden_dim * 2, len(batches))})
+    # what this particular run saw (kept out of `config`, which names the workload and is shared with the reference arm)
+    run_info = {"packed_nodes_spt_qry": m.last["n_nodes"], "packed_edges_spt_qry": m.last["n_edges"],
                 "kernel_impl": {0: "auto", 1: "ffma", 2: "tcgen05-3xtf32", 3: "tcpair"}[args.kernel_impl],
                 "subgraph_extraction_s_per_meta_batch_host": extract_s, "host_pack_ms_last_step": host_pack_ms,
-                "final_accs": [float(a) for a in accs], "loss_q": float(last_out[-2])})
+                "final_accs": [float(a) for a in accs], "loss_q": float(last_out[-2])}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / n_total, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
@@ -745,7 +747,7 @@ def main():
                     "contract_ms_per_step": ms_e2e_k / args.steps},
             "gpu_launches": int(launches[0]), "gpu_launches_per_step": int(launches_per_step),
             "clocks": sampler.summary(), "roofline": roof, "roofline_step": roof_step, "cpu_baseline": cb,
-            "parity_in_run": bool(parity["ok"]) if parity else None, "parity": parity}
+            "parity_in_run": bool(parity["ok"]) if parity else None, "parity": parity, "run_info": run_info}
     if args.profile_run:
         line["profile_run"] = True         # not a measurement: no clock warm-up, eager steps, exactly --steps per arm
     if extraction:
