@@ -73,6 +73,9 @@ _SIGNATURES = {
     "gmeta_host_pack_csr": (C.c_int, [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32]),
     "gmeta_host_pack_feat_rows": (C.c_int, [i32, vp, vp, vp, vp, vp, vp, i32]),
     "gmeta_host_active_in_neighbours": (i64, [vp, vp, vp, i64, i64, vp, vp]),
+    "gmeta_host_pack_small": (C.c_int, [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "gmeta_host_active_rows": (i64, [vp, vp, i64, vp, i64, vp, i32, i32, vp, vp, vp, i64, vp, vp, vp]),
+    "gmeta_host_validate_labels": (C.c_int, [i32, vp, vp, vp, vp, i32]),
     "gmeta_aggregate_rows": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, vp, i32, vp]),
     "gmeta_gcn_layer_wgrad_workspace_bytes": (i64, [i32, i32, i32]),
     "gmeta_gcn_layer_wgrad": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp, i64, vp, i64,

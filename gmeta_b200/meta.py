@@ -412,7 +412,7 @@ class Meta(nn.Module):
         db = _DeviceBatch()
         db.resident = bool(own_buffer)
         db.T = len(x_spt)
-        db.max_classes = packing.validate_labels(y_spt, y_qry, self.k_spt)
+        db.max_classes = packing.validate_labels(y_spt, y_qry, self.k_spt, _lib.lib())
         db.ft = ft
         t0 = time.perf_counter()
         n_layers = len(self.spec.conv)

@@ -159,10 +159,27 @@ def fill_set(buf, ps, graphs, labels, centres, node_ids, graph_idx, graph_row_of
             buf[o["%s%d" % (k, l)]:o["%s%d" % (k, l)] + a["n_tiles"]] = arr
 
 
-def validate_labels(y_spt, y_qry, k_spt):
+def validate_labels(y_spt, y_qry, k_spt, lib=None):
     """The equal-count requirements the reference enforces implicitly through torch.stack
     (meta.py:42,65-66): every support class has >= k_spt members, query classes are balanced
-    and the same as the support classes."""
+    and the same as the support classes.  With `lib` the check is one library call for all tasks."""
+    if lib is not None and len(y_spt):
+        import ctypes as C
+        T = len(y_spt)
+        keep = []
+        vpa = lambda ys: (C.c_void_p * T)(*[_ptr_i64(y, keep) for y in ys])      # noqa: E731
+        ns = np.array([len(y) for y in y_spt], dtype=np.int32)
+        nq = np.array([len(y) for y in y_qry], dtype=np.int32)
+        rc = lib.gmeta_host_validate_labels(T, vpa(y_spt), ns.ctypes.data, vpa(y_qry), nq.ctypes.data, k_spt)
+        if rc == -1:
+            raise RuntimeError("stack expects each tensor to be equal size: a support class has fewer "
+                               "than k_spt=%d members (meta.py:42)" % k_spt)
+        if rc == -2:
+            raise RuntimeError("stack expects each tensor to be equal size: query classes are not "
+                               "balanced (meta.py:65)")
+        if rc == -3:
+            raise RuntimeError("support and query sets must hold the same classes (meta.py:56-79)")
+        return int(rc)
     max_classes = 1
     for ys, yq in zip(y_spt, y_qry):
         ys = ys.numpy() if hasattr(ys, "numpy") else np.asarray(ys)
@@ -200,6 +217,37 @@ def _np(x):
     return x.numpy() if hasattr(x, "numpy") else np.asarray(x)
 
 
+def _csr_ptrs(g):
+    """Addresses of a batched graph's four int32 CSR arrays (indptr, indices, t_indptr, t_indices), cached on the graph
+    together with the arrays they belong to (a replaced array invalidates the entry)."""
+    c = getattr(g, "_gmeta_ptrs", None)
+    arrs = (g.indptr, g.indices, g.t_indptr, g.t_indices)
+    if c is not None and all(a is b for a, b in zip(c[0], arrs)):
+        return c[1]
+    fixed = tuple(_i32c(a) for a in arrs)
+    p = tuple(a.ctypes.data for a in fixed)
+    try:
+        g._gmeta_ptrs = (arrs, p, fixed)
+    except AttributeError:
+        pass
+    return p
+
+
+def _ptr_i64(x, keep):
+    """Address of `x` as a contiguous int64 array (torch tensor, numpy array or sequence); whatever had to be created for
+    it is appended to `keep`.  The common case -- an int64 torch tensor or numpy array -- costs one attribute call: the
+    packer threads run beside the thread that launches the steps, and every microsecond they spend in the interpreter is
+    taken from it."""
+    if isinstance(x, torch.Tensor):
+        if x.dtype == torch.int64 and x.is_contiguous() and x.device.type == "cpu":
+            return x.data_ptr()
+        x = x.cpu().numpy()
+    if not (isinstance(x, np.ndarray) and x.dtype == np.int64 and x.flags.c_contiguous):
+        x = np.ascontiguousarray(x, dtype=np.int64)
+        keep.append(x)
+    return x.ctypes.data
+
+
 def _plan_base(graphs, centres):
     ps = PackedSetHost()
     ps.T = len(graphs)
@@ -233,9 +281,7 @@ def _fill_base(buf, ps, graphs, labels, centres, node_ids, graph_idx, graph_row_
     the CSR by source and the tile tables are left to gmeta_packed_set_finish on the device."""
     import ctypes as C
     o, N, E, T = ps.off, ps.N, ps.E, ps.T
-    keep = [[_i32c(getattr(g, k)) for g in graphs] for k in (("indptr", "indices") if slim else
-                                                             ("indptr", "indices", "t_indptr", "t_indices"))]
-    ptrs = [(C.c_void_p * max(T, 1))(*[a.__array_interface__['data'][0] for a in arrs]) for arrs in keep]
+    ptrs = [(C.c_void_p * max(T, 1))(*col) for col in zip(*[_csr_ptrs(g) for g in graphs])] if T else [None] * 4
     base = buf.__array_interface__['data'][0]
     if slim:
         rc = lib.gmeta_host_pack_csr(T, ptrs[0], ptrs[1], None, None, ps.node_off.ctypes.data, ps.edge_off.ctypes.data,
@@ -246,13 +292,22 @@ def _fill_base(buf, ps, graphs, labels, centres, node_ids, graph_idx, graph_row_
                                      base + 4 * o["t_indices"], n_threads)
     if rc != 0:
         raise RuntimeError("gmeta_host_pack_csr failed (%d)" % rc)
-    bnn = [np.asarray(g.batch_num_nodes, dtype=np.int64) for g in graphs]
-    sub_first = np.concatenate([np.cumsum(b) - b + ps.node_off[t] for t, b in enumerate(bnn)]) if T else np.zeros(0, np.int64)
-    c_all = np.concatenate([_np(c).astype(np.int64).reshape(len(b), -1) for c, b in zip(centres, bnn)]) if T else \
-        np.zeros((0, ps.cps), np.int64)
-    centre = buf[o["centre_row"]:o["centre_row"] + ps.S * ps.cps]
-    centre[:] = (c_all + sub_first[:, None]).reshape(-1)
-    buf[o["labels"]:o["labels"] + ps.S] = np.concatenate([_np(y) for y in labels]) if T else 0
+    # centre rows, labels, task pointers and the row tiles: one library call (no interpreter lock held meanwhile)
+    keep64 = []
+    bnn = [g.batch_num_nodes if (isinstance(g.batch_num_nodes, np.ndarray) and g.batch_num_nodes.dtype == np.int64)
+           else np.asarray(g.batch_num_nodes, dtype=np.int64) for g in graphs]
+    n_sub_arr = np.array([b.shape[0] for b in bnn], dtype=np.int32)
+    pa = lambda xs: (C.c_void_p * max(T, 1))(*[_ptr_i64(x, keep64) for x in xs])                        # noqa: E731
+    vpa64 = pa
+    cen, lab = centres, labels
+    seg = lambda k: base + 4 * o[k]                                                                      # noqa: E731
+    rc = lib.gmeta_host_pack_small(T, ps.cps, vpa64(bnn), n_sub_arr.ctypes.data, vpa64(cen), vpa64(lab),
+                                   ps.node_off.ctypes.data, ps.sub_off.ctypes.data, seg("centre_row"), seg("labels"),
+                                   seg("task_row_ptr"), seg("task_sub_ptr"), None if slim else seg("tile_row0"),
+                                   None if slim else seg("tile_nrows"), None if slim else seg("tile_task"))
+    if rc != 0:
+        raise RuntimeError("gmeta_host_pack_small failed (%d): centres / labels / batch_num_nodes do not match the "
+                           "batched graphs" % rc)
     single_graph = graph_row_off.shape[0] == 1
     all_ids = []
     for t, g in enumerate(graphs):
@@ -281,15 +336,6 @@ def _fill_base(buf, ps, graphs, labels, centres, node_ids, graph_idx, graph_row_
                                            ps.node_off.ctypes.data, base + 4 * o["feat_row"], n_threads)
     if rc != 0:
         raise RuntimeError("gmeta_host_pack_feat_rows failed (%d)" % rc)
-    if slim:
-        buf[o["task_row_ptr"]:o["task_row_ptr"] + T + 1] = ps.node_off
-        buf[o["task_sub_ptr"]:o["task_sub_ptr"] + T + 1] = ps.sub_off
-        return
-    buf[o["tile_row0"]:o["tile_row0"] + ps.n_tiles] = ps.tiles[0]
-    buf[o["tile_nrows"]:o["tile_nrows"] + ps.n_tiles] = ps.tiles[1]
-    buf[o["tile_task"]:o["tile_task"] + ps.n_tiles] = ps.tiles[2]
-    buf[o["task_row_ptr"]:o["task_row_ptr"] + T + 1] = ps.node_off
-    buf[o["task_sub_ptr"]:o["task_sub_ptr"] + T + 1] = ps.sub_off
 
 
 def _plan_fill_act(buf, ps, off, n_layers, lib=None, staging=None):
@@ -303,6 +349,25 @@ def _plan_fill_act(buf, ps, off, n_layers, lib=None, staging=None):
     indptr = buf[o["indptr"]:o["indptr"] + ps.N + 1]
     indices = buf[o["indices"]:o["indices"] + ps.E]
     centre = buf[o["centre_row"]:o["centre_row"] + ps.S * ps.cps]
+    if lib is not None:
+        # every layer's rows, task pointers, tile tables and the centre positions in ONE library call
+        flags = staging.byte_map(ps.N) if staging is not None else np.zeros(ps.N, dtype=np.uint8)
+        scratch = staging.i64_scratch(2 * (ps.N + 1)) if staging is not None else np.empty(2 * (ps.N + 1), dtype=np.int64)
+        seg_off = np.zeros(n_layers * 5, dtype=np.int64)
+        seg_n = np.zeros(n_layers * 5, dtype=np.int64)
+        base = buf.__array_interface__['data'][0]
+        end = lib.gmeta_host_active_rows(indptr.ctypes.data, indices.ctypes.data, ps.N, centre.ctypes.data, ps.S * ps.cps,
+                                         ps.node_off.ctypes.data, ps.T, n_layers, flags.ctypes.data, scratch.ctypes.data,
+                                         base, off, seg_off.ctypes.data, seg_n.ctypes.data, base + 4 * o["centre_pos"])
+        if end < 0:
+            raise RuntimeError("gmeta_host_active_rows failed (%d)" % end)
+        for l in range(n_layers):
+            for j, k in enumerate(("act_rows", "act_task_ptr", "act_tile_row0", "act_tile_nrows", "act_tile_task")):
+                key = "%s%d" % (k, l)
+                o[key] = int(seg_off[l * 5 + j])
+                ps.sizes[key] = int(seg_n[l * 5 + j])
+            ps.act[l] = {"n": int(seg_n[l * 5]), "n_tiles": int(seg_n[l * 5 + 2])}
+        return int(end)
     rows = np.unique(centre.astype(np.int64))     # a few thousand centres: sorting is cheap
     per_layer = [None] * n_layers
     per_layer[n_layers - 1] = rows
@@ -464,6 +529,11 @@ class Staging(object):
         if getattr(self, "_counts", None) is None or self._counts.numel() < n:
             self._counts = torch.empty(max(n, 64), dtype=torch.int32, pin_memory=torch.cuda.is_available())
         return self._counts
+
+    def i64_scratch(self, n):
+        if getattr(self, "_i64", None) is None or self._i64.shape[0] < n:
+            self._i64 = np.empty(int(n * 1.25) + 64, dtype=np.int64)
+        return self._i64
 
     def byte_map(self, n):
         """Zeroed uint8 scratch of at least n entries; users hand it back zeroed."""

@@ -283,6 +283,24 @@ int gmeta_aggregate_rows_nd(const float* in, int32_t ld_in, const int32_t* in_ro
                             const int32_t* indptr, const int32_t* indices, const float* norm, const float* norm_dst,
                             int32_t n_rows, int32_t f_in, int32_t scale_dst, float* out, int32_t ld_out, void* stream);
 
+/* HOST helpers of the packer (no device work): the small segments of one set -- centre rows (learner.py:161-170), labels,
+ * task pointers, row tiles (out_tile_* may be NULL) -- from the per-task arrays; the active rows of every layer with their
+ * task pointers / tile tables / centre positions written behind each other at buf[off...] (returns the next free
+ * offset; seg_off / seg_n [n_layers * 5]: act_rows, act_task_ptr, act_tile_row0, act_tile_nrows, act_tile_task per
+ * layer); and the label requirements of meta.py:42,65-66 for all tasks (returns the largest class count, or -1: a
+ * support class with fewer than k_spt members, -2: unbalanced query classes, -3: support / query classes differ). */
+int gmeta_host_pack_small(int32_t n_tasks, int32_t cps, const int64_t* const* bnn, const int32_t* n_sub,
+                          const int64_t* const* centres, const int64_t* const* labels, const int64_t* node_off,
+                          const int64_t* sub_off, int32_t* out_centre_row, int32_t* out_labels,
+                          int32_t* out_task_row_ptr, int32_t* out_task_sub_ptr, int32_t* out_tile_row0,
+                          int32_t* out_tile_nrows, int32_t* out_tile_task);
+int64_t gmeta_host_active_rows(const int32_t* indptr, const int32_t* indices, int64_t n_nodes, const int32_t* centre_row,
+                               int64_t n_centres, const int64_t* node_off, int32_t n_tasks, int32_t n_layers,
+                               uint8_t* flags, int64_t* scratch, int32_t* buf, int64_t off, int64_t* seg_off,
+                               int64_t* seg_n, int32_t* out_centre_pos);
+int gmeta_host_validate_labels(int32_t n_tasks, const int64_t* const* y_spt, const int32_t* n_spt,
+                               const int64_t* const* y_qry, const int32_t* n_qry, int32_t k_spt);
+
 /* Centre-row readout + linear head (learner.py:159-175):
  *   r_s = H[centre_row[s]]   (link_pred: H[centre_row[2s]] || H[centre_row[2s+1]])
  *   logits[s,c] = sum_k r_s[k] * Wlin[t][c,k] + blin[t][c],  t = task of subgraph s. */
