@@ -190,6 +190,47 @@ def test_label_validation_mirrors_reference_errors():
         packing.validate_labels([y([0, 0, 1, 1])], [y([0, 1, 1])], 2)      # unbalanced query
 
 
+def test_label_validation_in_the_library_agrees_with_the_numpy_check():
+    """Meta.forward validates through gmeta_host_validate_labels (one call for all tasks, no interpreter lock held);
+    same verdict and same class count as the numpy restatement on good, bad, large-valued and negative labels."""
+    y = torch.LongTensor
+    L = _lib.lib()
+    cases = [
+        ([y([0, 0, 1, 1])], [y([0, 1, 1, 0])], 2),
+        ([y([0, 0, 1])], [y([0, 1])], 2),                                  # a support class below k_spt
+        ([y([0, 0, 1, 1])], [y([0, 1, 1])], 2),                            # unbalanced query
+        ([y([0, 0, 1, 1])], [y([0, 2, 0, 2])], 2),                         # different classes, same counts
+        ([y([5, 5, 7, 7, 9, 9])], [y([9, 7, 5])], 2),
+        ([y([-3, -3, 40000, 40000])], [y([40000, -3])], 2),                # outside the counting fast path
+        ([y([2 ** 40, 2 ** 40, 1, 1])], [y([1, 2 ** 40, 1, 2 ** 40])], 2),
+        ([y([0, 0, 1, 1]), y([3, 3, 4, 4, 5, 5])], [y([0, 1]), y([5, 4, 3])], 2),   # max classes over the tasks
+        ([y([0, 0, 1, 1]), y([3, 3, 4, 4, 5])], [y([0, 1]), y([5, 4, 3])], 2),      # second task bad
+        ([np.array([1, 1, 0, 0])], [[0, 1]], 2),                           # numpy array / plain list
+    ]
+    rng = np.random.default_rng(9)
+    for _ in range(40):
+        n_cls, k = int(rng.integers(1, 6)), int(rng.integers(1, 4))
+        cls = rng.choice(50, n_cls, replace=False)
+        ys = np.repeat(cls, k + rng.integers(0, 2, n_cls))                  # sometimes more than k_spt members
+        yq = np.repeat(cls, int(rng.integers(1, 4)))
+        if rng.random() < 0.3:
+            yq = yq[:-1] if yq.shape[0] > 1 else yq                         # unbalance it
+        if rng.random() < 0.2:
+            yq = yq.copy()
+            yq[yq == cls[0]] = 99                                           # other class, same counts
+        cases.append(([y(rng.permutation(ys))], [y(rng.permutation(yq))], k))
+
+    def verdict(fn):
+        try:
+            return fn()
+        except RuntimeError as e:
+            return str(e)
+    for ys, yq, k in cases:
+        a = verdict(lambda: packing.validate_labels(ys, yq, k))
+        b = verdict(lambda: packing.validate_labels(ys, yq, k, L))
+        assert a == b, (ys, yq, k, a, b)
+
+
 def test_extraction_matches_reference_generate_subgraph():
     """Same node set / induced edges as Subgraphs.generate_subgraph when the neighbourhood is
     below the sampling cap (subgraph_data_processing.py:295-321), for h = 1, 2, 3."""
