@@ -356,3 +356,61 @@ def test_slim_host_pack_writes_the_same_host_segments_as_the_full_packer():
                 assert np.array_equal(a[f.off[k]:f.off[k] + n], b[s_.off[k]:s_.off[k] + n]), k
             for k, cap in s_.cap.items():
                 assert s_.off[k] >= n_host and cap >= f.sizes[k], k
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_host_packers_on_ragged_random_batches(seed):
+    """Ragged inputs the tiny datasets do not produce: subgraphs of ONE node, subgraphs without edges, multi-edges,
+    tasks of different subgraph counts, several parent graphs, two centres per subgraph.  The library packer
+    (pack_meta_batch), the slim packer and the plain numpy packing (plan_set + fill_set) must agree segment by segment."""
+    from gmeta_b200.packed import PackedSubgraphBatch, SubgraphCSR
+    rng = np.random.default_rng(100 + seed)
+    n_graphs = int(rng.integers(1, 4))
+    graph_n = [int(rng.integers(40, 90)) for _ in range(n_graphs)]
+    goff = np.concatenate([[0], np.cumsum(graph_n)])[:-1]
+    link = bool(seed % 2)
+    L = 1 + seed % 3
+    T = int(rng.integers(1, 5))
+
+    def subgraph(gi):
+        n = int(rng.choice([1, 2, 3, 7, 20, 33]))
+        e = 0 if rng.random() < 0.25 else int(rng.integers(0, 4 * n + 1))
+        src, dst = rng.integers(0, n, e), rng.integers(0, n, e)          # multi-edges and self-loops may occur
+        ids = rng.choice(graph_n[gi], n, replace=False)
+        c = [int(rng.integers(0, n)), int(rng.integers(0, n))] if link else int(rng.integers(0, n))
+        return SubgraphCSR.from_edges(src, dst, n, ids, c)
+
+    def one_set(max_sub):
+        xs, ys, cs, ns, gs = [], [], [], [], []
+        for _ in range(T):
+            S = int(rng.integers(1, max_sub + 1))
+            gi = [int(rng.integers(0, n_graphs)) for _ in range(S)]
+            subs = [subgraph(g) for g in gi]
+            xs.append(PackedSubgraphBatch.batch(subs))
+            ys.append(torch.LongTensor(rng.integers(0, 3, S)))
+            cs.append(torch.LongTensor(np.array([s.centre for s in subs])))
+            ns.append(xs[-1].parent_id_lists)
+            gs.append(gi)
+        return xs, ys, cs, ns, gs
+    xs, ys, cs, ns, gs = one_set(4)
+    xq, yq, cq, nq, gq = one_set(9)
+    mb = (xs, ys, xq, yq, cs, cq, ns, nq, gs, gq)
+    full, slim = packing.Staging(torch.device("cpu")), packing.Staging(torch.device("cpu"))
+    ps_s, ps_q, end = packing.pack_meta_batch(full, mb, goff, L, _lib.lib(), n_threads=2)
+    ss, sq, n_host, n_total = packing.pack_meta_batch_slim(slim, mb, goff, L, _lib.lib(), n_threads=2)
+    fast, sl = full.host.numpy(), slim.host.numpy()
+    for ps, s_, (x, y, c, n, g) in ((ps_s, ss, (xs, ys, cs, ns, gs)), (ps_q, sq, (xq, yq, cq, nq, gq))):
+        ref = packing.plan_set(x, c, 0, L)
+        buf = np.zeros(ref.end, dtype=np.int32)
+        packing.fill_set(buf, ref, x, y, c, n, g, goff)
+        assert (ps.N, ps.E, ps.S, ps.T, ps.n_tiles, ps.cps) == (ref.N, ref.E, ref.S, ref.T, ref.n_tiles, ref.cps)
+        assert ps.cps == (2 if link else 1)
+        for k, n_el in ref.sizes.items():
+            assert ps.sizes[k] == n_el, k
+            assert np.array_equal(fast[ps.off[k]:ps.off[k] + n_el], buf[ref.off[k]:ref.off[k] + n_el]), k
+        for k in packing.HOST_SEGS:
+            n_el = ref.sizes[k]
+            assert np.array_equal(sl[s_.off[k]:s_.off[k] + n_el], buf[ref.off[k]:ref.off[k] + n_el]), k
+        # the feature rows are the parent ids shifted by their graph's first row (meta.py:119-120)
+        want = np.concatenate([np.concatenate([np.asarray(ids) + goff[gi] for ids, gi in zip(n[t], g[t])]) for t in range(ps.T)])
+        assert np.array_equal(fast[ps.off["feat_row"]:ps.off["feat_row"] + ps.N], want)
