@@ -58,6 +58,13 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 inline int ceil_div(int x, int m) { return (x + m - 1) / m; }
 
+// ReLU as torch computes it (learner.py:49 F.relu): a NaN pre-activation stays NaN, so that a NaN anywhere reaches the
+// mean query loss and the reference's NaN skip (meta.py:163-164) fires.  fmaxf(NaN, 0) would return 0.  One FMNMX.NAN.
+__device__ __forceinline__ float relu_keep_nan(float v) {
+  float r;
+  asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(v));
+  return r;
+}
 __device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 

@@ -409,8 +409,8 @@ __device__ __forceinline__ void expand_block(const ExpandArgs& a, int ew, int la
       float4 w0 = make_float4(fmaf(f, x0[j].x, b0.x), fmaf(f, x0[j].y, b0.y), fmaf(f, x0[j].z, b0.z), fmaf(f, x0[j].w, b0.w));
       float4 w1 = make_float4(fmaf(f, x1[j].x, b1.x), fmaf(f, x1[j].y, b1.y), fmaf(f, x1[j].z, b1.z), fmaf(f, x1[j].w, b1.w));
       if (relu) {
-        w0.x = fmaxf(w0.x, 0.f); w0.y = fmaxf(w0.y, 0.f); w0.z = fmaxf(w0.z, 0.f); w0.w = fmaxf(w0.w, 0.f);
-        w1.x = fmaxf(w1.x, 0.f); w1.y = fmaxf(w1.y, 0.f); w1.z = fmaxf(w1.z, 0.f); w1.w = fmaxf(w1.w, 0.f);
+        w0.x = relu_keep_nan(w0.x); w0.y = relu_keep_nan(w0.y); w0.z = relu_keep_nan(w0.z); w0.w = relu_keep_nan(w0.w);
+        w1.x = relu_keep_nan(w1.x); w1.y = relu_keep_nan(w1.y); w1.z = relu_keep_nan(w1.z); w1.w = relu_keep_nan(w1.w);
       }
       if (MASK) {
         if (live) {

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gcn_layer_fwd_simt_kernel(const F
           if (c + j < f_out) {
             val = nv * acc[i][4 * h + j];
             if (bias) val += bias[c + j];
-            if (p.relu & 1) val = fmaxf(val, 0.f);
+            if (p.relu & 1) val = relu_keep_nan(val);
             if (p.relu_mask && !(p.relu_mask[(size_t)((p.relu & 2) ? orow : v) * p.ld_out + c + j] > 0.f)) val = 0.f;
           }
           o[j] = val;

@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) gcn_layer_fwd_tc_kernel(const 
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           float val = fmaf(nv, __uint_as_float(acc[j]), bias_s[c0 + j]);
-          if (p.relu & 1) val = fmaxf(val, 0.f);
+          if (p.relu & 1) val = relu_keep_nan(val);
           o[j] = val;
         }
         if (mrow && live) {

@@ -91,3 +91,41 @@ def test_meta_on_degenerate_subgraphs_matches_oracle(link, pruned, device_finish
     # the second step carries the Adam state
     want2 = om.forward(og(xs), ys, og(xq), yq, cs, cq, ns, nq, gs, gq, feats)
     np.testing.assert_allclose(m(*mb, feats), want2, atol=1e-6)
+
+
+@pytest.mark.parametrize("graphs", [True, False])
+def test_nan_loss_skips_the_outer_update_like_the_reference(graphs):
+    """meta.py:163-164: a NaN mean query loss leaves the parameters and the optimiser alone.  A meta-batch with one NaN
+    feature row makes the loss NaN: parameters bit-identical afterwards, Adam's step count not advanced, and the next
+    clean step equals the oracle's FIRST step (same accuracies, same gradient) -- with and without CUDA graphs."""
+    from gmeta_b200.meta import Meta
+    mb, feats = _ragged_meta_batch(77, False)
+    cfg = [('GraphConv', [12, 16]), ('GraphConv', [16, 16]), ('Linear', [16, 3])]
+    args = argparse.Namespace(update_lr=0.05, meta_lr=1e-3, n_way=3, k_spt=2, k_qry=3, task_num=3, update_step=3,
+                              update_step_test=4, method='G-Meta', use_graphs=graphs, graph_host_batches=graphs)
+    torch.manual_seed(222)
+    m = Meta(args, cfg).to(U.dev())
+    m.return_meta_grad = True
+    _nonzero_biases(m.net.parameters())
+    params = [p.detach().cpu().clone().requires_grad_(True) for p in m.net.parameters()]
+    before = [p.detach().clone() for p in m.net.parameters()]
+    bad = [f.copy() for f in feats]
+    for f in bad:
+        f[:] = np.nan                              # whichever rows the tasks touch
+    accs_bad = m(*mb, bad)
+    assert accs_bad.shape == (args.update_step + 1,)
+    assert m.last["skipped"] and np.isnan(m.last["loss_q"])
+    for a, b in zip(before, m.net.parameters()):
+        assert torch.equal(a, b)
+    assert m.meta_optim.step_count == 0
+    om = O.OracleMeta(args, cfg, params=params)
+    xs, ys, xq, yq, cs, cq, ns, nq, gs, gq = mb
+    og = lambda xs_: [H.to_ograph(x) for x in xs_]                                                       # noqa: E731
+    want = om.forward(og(xs), ys, og(xq), yq, cs, cq, ns, nq, gs, gq, feats)
+    accs = m(*mb, feats)                           # new feature arrays: the device table is rebuilt from them
+    np.testing.assert_allclose(accs, want, atol=1e-6)
+    assert not m.last["skipped"] and m.meta_optim.step_count == 1
+    for k, (g, r) in enumerate(zip(m.last["meta_grad"], om.last_grads)):
+        U.report("meta-grad[%d]" % k, g, r, 2e-5 + 1e-4 * float(r.abs().max()), 1e-3)
+    want2 = om.forward(og(xs), ys, og(xq), yq, cs, cq, ns, nq, gs, gq, feats)
+    np.testing.assert_allclose(m(*mb, feats), want2, atol=1e-6)       # Adam state: one applied step on both sides
