@@ -106,3 +106,47 @@ def test_meta_forward_and_finetunning_fresh_batches(kind, steps):
         for p_ref, g, p in zip(m.net.parameters(), om.last_grads, om.vars):
             assert torch.equal(p_ref.grad, g), (kind, it)
             assert torch.equal(p_ref.detach(), p.detach()), (kind, it)
+
+
+@pytest.mark.parametrize("link", [False, True])
+def test_meta_on_degenerate_batches_and_nan_skip(link):
+    """The inputs of tests/test_gpu_meta_ragged.py (one-node and edgeless subgraphs, a task without any edge, multi-edges,
+    several parent graphs) through the unmodified reference and the oracle: finetunning, two forward steps bit-equal;
+    then an all-NaN feature table: both skip the outer update (meta.py:163-164), parameters untouched."""
+    import argparse
+    from tests.test_gpu_meta_ragged import _ragged_meta_batch
+    _, meta, _ = ref_loader.load()
+    dgl = ref_loader.shim_dgl()
+    mb, feats = _ragged_meta_batch(31 + int(link), link)
+    cfg = [('GraphConv', [12, 16]), ('GraphConv', [16, 16]), ('Linear', [16, 3])] + ([('LinkPred', [True])] if link else [])
+    args = argparse.Namespace(update_lr=0.05, meta_lr=1e-3, n_way=3, k_spt=2, k_qry=3, task_num=3, update_step=3,
+                              update_step_test=4, method='G-Meta')
+    torch.manual_seed(222)
+    m = meta.Meta(args, cfg)
+    gen = torch.Generator().manual_seed(11)
+    with torch.no_grad():
+        for p in m.net.parameters():
+            if p.dim() == 1:
+                p.copy_(0.05 * torch.randn(p.shape, generator=gen))
+    om = O.OracleMeta(args, cfg, params=[p.detach().clone().requires_grad_(True) for p in m.net.parameters()])
+    xs, ys, xq, yq, cs, cq, ns, nq, gs, gq = mb
+    dxs, dxq = [_to_dgl(dgl, x) for x in xs], [_to_dgl(dgl, x) for x in xq]
+    oxs, oxq = [H.to_ograph(x) for x in xs], [H.to_ograph(x) for x in xq]
+    one = lambda v: [v[1]]                                                                                # noqa: E731
+    fin_ref = m.finetunning(one(dxs), one(ys), one(dxq), one(yq), one(cs), one(cq), one(ns), one(nq), one(gs), one(gq), feats)
+    fin = om.finetunning(one(oxs), one(ys), one(oxq), one(yq), one(cs), one(cq), one(ns), one(nq), one(gs), one(gq), feats)
+    assert np.array_equal(np.asarray(fin_ref, dtype=np.float32), fin)
+    for it in range(2):
+        acc_ref = m(dxs, ys, dxq, yq, cs, cq, ns, nq, gs, gq, feats)
+        acc = om.forward(oxs, ys, oxq, yq, cs, cq, ns, nq, gs, gq, feats)
+        assert np.array_equal(np.asarray(acc_ref, dtype=np.float32), acc), it
+        for p_ref, g, p in zip(m.net.parameters(), om.last_grads, om.vars):
+            assert torch.equal(p_ref.grad, g) and torch.equal(p_ref.detach(), p.detach()), it
+    # NaN features: the mean query loss is NaN on both sides and neither applies the outer step
+    bad = [np.full_like(f, np.nan) for f in feats]
+    before = [p.detach().clone() for p in m.net.parameters()]
+    m(dxs, ys, dxq, yq, cs, cq, ns, nq, gs, gq, bad)
+    om.forward(oxs, ys, oxq, yq, cs, cq, ns, nq, gs, gq, bad)
+    assert np.isnan(om.last_loss_q)
+    for b, p_ref, p in zip(before, m.net.parameters(), om.vars):
+        assert torch.equal(b, p_ref.detach()) and torch.equal(b, p.detach())
