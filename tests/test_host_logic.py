@@ -414,3 +414,36 @@ def test_host_packers_on_ragged_random_batches(seed):
         # the feature rows are the parent ids shifted by their graph's first row (meta.py:119-120)
         want = np.concatenate([np.concatenate([np.asarray(ids) + goff[gi] for ids, gi in zip(n[t], g[t])]) for t in range(ps.T)])
         assert np.array_equal(fast[ps.off["feat_row"]:ps.off["feat_row"] + ps.N], want)
+
+
+def _tiny_meta(method='G-Meta'):
+    import argparse
+    from gmeta_b200.meta import Meta
+    cfg = [('GraphConv', [12, 16]), ('GraphConv', [16, 16]), ('Linear', [16, 3])]
+    args = argparse.Namespace(update_lr=0.05, meta_lr=1e-3, n_way=3, k_spt=2, k_qry=3, task_num=2, update_step=2,
+                              update_step_test=2, method=method)
+    return Meta(args, cfg), cfg
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="the point is a box without a GPU")
+def test_product_fails_loudly_without_a_gpu():
+    """No CPU path and no silent fallback: on a box without a CUDA device Meta.forward / finetunning / Classifier.forward
+    raise GMetaError instead of computing anything (the oracle is never reached: test_product_code_never_imports_the_oracle)."""
+    ds = H.tiny_dataset('disjoint')
+    mb = ds.sample_meta_batch(np.random.default_rng(1))
+    m, _ = _tiny_meta()
+    for call in (m.forward, m.finetunning, m.finetunning_batch):
+        with pytest.raises(_lib.GMetaError, match="CUDA device"):
+            call(*mb, ds.feats)
+    xs, ys, xq, yq, cs, cq, ns, nq, gs, gq = mb
+    with pytest.raises(_lib.GMetaError, match="CUDA device"):
+        m.net(xs[0], cs[0], torch.zeros(xs[0].n_nodes, 12))
+
+
+def test_unknown_method_fails_like_the_reference():
+    """meta.py:236-246: only 'G-Meta' is defined; any other --method leaves `accs` unbound."""
+    m, _ = _tiny_meta(method='MAML')
+    with pytest.raises(UnboundLocalError):
+        m.forward(*([None] * 11))
+    with pytest.raises(UnboundLocalError):
+        m.finetunning(*([None] * 11))
